@@ -1,0 +1,241 @@
+"""
+Deterministic synthetic metagenome communities for parity tests and the bench.
+
+The reference (cerebis/bin3C) consumes a name-sorted BAM (contact_map.py:534-545,
+718-771).  The hot path this package accelerates starts one step later, at the
+*packed pair record* stream: for every usable read pair, the two BAM reference
+ids and one "both mates passed the matcher" bit (contact_map.py:733-739).  This
+module synthesises that stream, together with the per-reference table the
+reference builds from the BAM header + FASTA (contact_map.py:545-564), following
+the recipe in SURVEY.md section 8(d):
+
+  * G genomes; genome sizes and abundances are lognormal(sigma=1);
+  * N contigs assigned to genomes by size; contig length lognormal(ln 8000, 1)
+    clipped to [1000, 1e6] (or a Pareto tail for the "heavy" profile);
+  * sites = max(1, L // 256);
+  * end-1 contig ~ L * abundance; end-2 is the same contig w.p. 0.80, a contig of
+    the same genome (~ L) w.p. 0.18, any contig (~ L) w.p. 0.02;
+  * pass bit ~ Bernoulli(0.85);
+  * BAM reference ids interleave the N usable contigs with ~10 % excluded (short)
+    references, and ~1 % of pair ends land on an excluded reference;
+  * contig order is shuffled, so assembly order != genome order.
+
+Packed pair record (little-endian uint64), the wire format of the path:
+    bits  0..30  BAM reference id of mate 1
+    bit   31     pass flag (1 = both mates satisfy the matcher)
+    bits 32..62  BAM reference id of mate 2
+    bit   63     reserved, must be 0
+"""
+from collections import namedtuple
+
+import numpy as np
+
+# same field names and order as the reference's SeqInfo (contact_map.py:20)
+SeqInfo = namedtuple('SeqInfo', ['offset', 'refid', 'name', 'length', 'sites'])
+
+PASS_BIT = np.uint64(1) << np.uint64(31)
+TID_MASK = np.uint64(0x7FFFFFFF)
+
+
+def pack_pairs(tid_i, tid_j, passed):
+    """Pack (tid_i, tid_j, pass) arrays into uint64 pair records."""
+    tid_i = np.asarray(tid_i)
+    tid_j = np.asarray(tid_j)
+    passed = np.asarray(passed)
+    assert tid_i.shape == tid_j.shape == passed.shape
+    if tid_i.size:
+        assert tid_i.min() >= 0 and tid_j.min() >= 0, 'reference ids must be non-negative'
+        assert tid_i.max() < 2 ** 31 and tid_j.max() < 2 ** 31, 'reference ids must fit 31 bits'
+    rec = tid_i.astype(np.uint64)
+    rec |= tid_j.astype(np.uint64) << np.uint64(32)
+    rec |= (passed.astype(bool).astype(np.uint64)) << np.uint64(31)
+    return rec
+
+
+def unpack_pairs(rec):
+    """Inverse of pack_pairs -> (tid_i int64, tid_j int64, passed bool)."""
+    rec = np.asarray(rec, dtype=np.uint64)
+    tid_i = (rec & TID_MASK).astype(np.int64)
+    tid_j = ((rec >> np.uint64(32)) & TID_MASK).astype(np.int64)
+    passed = (rec & PASS_BIT) != 0
+    return tid_i, tid_j, passed
+
+
+class Community(object):
+    """
+    A synthetic community: the reference-table side (what ContactMap.__init__ derives
+    from the BAM header and FASTA) and the pair-record side (what _bin_map consumes).
+    """
+
+    def __init__(self, n_refs, ref_index, lengths, sites, genome_of, records, seed, profile):
+        self.n_refs = int(n_refs)            # number of BAM references (usable + excluded)
+        self.ref_index = ref_index           # int64[N]: BAM reference id of internal contig k (ascending)
+        self.lengths = lengths               # int32[N]
+        self.sites = sites                   # int32[N]
+        self.genome_of = genome_of           # int32[N] ground-truth genome id (not used by the path)
+        self.records = records               # uint64[P] packed pair records
+        self.seed = seed
+        self.profile = profile
+
+    @property
+    def n_contigs(self):
+        return len(self.ref_index)
+
+    @property
+    def n_pairs(self):
+        return len(self.records)
+
+    def seq_info(self):
+        """List of SeqInfo in internal order, as contact_map.py:545-564 would build it."""
+        out = []
+        offset = 0
+        for k in range(self.n_contigs):
+            ln = int(self.lengths[k])
+            out.append(SeqInfo(offset, int(self.ref_index[k]), 'ctg{:07d}'.format(k), ln, int(self.sites[k])))
+            offset += ln
+        return out
+
+    def tid2idx(self):
+        """Dense BAM-reference-id -> internal index table, -1 for excluded references.
+        Device-side form of ContactMap.make_reverse_index('refid') (contact_map.py:818-832)."""
+        lut = np.full(self.n_refs, -1, dtype=np.int32)
+        lut[self.ref_index] = np.arange(self.n_contigs, dtype=np.int32)
+        return lut
+
+
+def _contig_lengths(rng, n, profile):
+    if profile == 'heavy':
+        ln = (rng.pareto(1.2, size=n) + 1.0) * 1000.0
+        return np.clip(ln, 1000, 5_000_000).astype(np.int64)
+    ln = rng.lognormal(mean=np.log(8000.0), sigma=1.0, size=n)
+    return np.clip(ln, 1000, 1_000_000).astype(np.int64)
+
+
+def make_community(n_genomes, n_contigs, n_pairs, seed, profile='lognormal',
+                   p_same=0.80, p_genome=0.18, p_pass=0.85, excl_ref_frac=0.10,
+                   excl_end_frac=0.01, chunk=1 << 24):
+    """
+    Build a deterministic synthetic community.  All randomness comes from
+    numpy.random.default_rng(seed); the same arrays feed the oracle and the GPU path.
+    """
+    rng = np.random.default_rng(seed)
+    G, N, P = int(n_genomes), int(n_contigs), int(n_pairs)
+    assert G >= 1 and N >= G
+
+    # genomes: relative size and abundance
+    g_size = rng.lognormal(0.0, 1.0, size=G)
+    g_abund = rng.lognormal(0.0, 1.0, size=G)
+
+    # every genome gets at least one contig, the remainder by size
+    genome_sorted = np.concatenate([np.arange(G), rng.choice(G, size=N - G, p=g_size / g_size.sum())])
+    genome_sorted.sort()
+    lengths_sorted = _contig_lengths(rng, N, profile)
+
+    # genome-sorted working order "s"; internal (assembly) order is a shuffle of it
+    g_start = np.searchsorted(genome_sorted, np.arange(G), side='left')
+    g_end = np.searchsorted(genome_sorted, np.arange(G), side='right')
+    cum_len = np.concatenate([[0.0], np.cumsum(lengths_sorted.astype(np.float64))])
+    w1 = lengths_sorted * g_abund[genome_sorted]
+    cum_w1 = np.cumsum(w1)
+    cum_w1 /= cum_w1[-1]
+
+    perm = rng.permutation(N)            # s -> internal index
+    lengths = np.empty(N, dtype=np.int32)
+    lengths[perm] = lengths_sorted
+    genome_of = np.empty(N, dtype=np.int32)
+    genome_of[perm] = genome_sorted
+    sites = np.maximum(1, lengths // 256).astype(np.int32)
+
+    # BAM references: usable contigs interleaved with excluded (short) references
+    n_excl = max(1, int(round(N * excl_ref_frac)))
+    n_refs = N + n_excl
+    is_excl = np.zeros(n_refs, dtype=bool)
+    is_excl[rng.choice(n_refs, size=n_excl, replace=False)] = True
+    ref_index = np.flatnonzero(~is_excl).astype(np.int64)     # internal k -> tid (ascending)
+    excl_tids = np.flatnonzero(is_excl).astype(np.int64)
+
+    records = np.empty(P, dtype=np.uint64)
+    for lo in range(0, P, chunk):
+        m = min(chunk, P - lo)
+        s1 = np.searchsorted(cum_w1, rng.random(m), side='right')
+        np.minimum(s1, N - 1, out=s1)
+        kind = rng.random(m)
+        s2 = s1.copy()
+        # same genome, contig ~ L
+        sel = np.flatnonzero((kind >= p_same) & (kind < p_same + p_genome))
+        g = genome_sorted[s1[sel]]
+        u = cum_len[g_start[g]] + rng.random(len(sel)) * (cum_len[g_end[g]] - cum_len[g_start[g]])
+        s2[sel] = np.clip(np.searchsorted(cum_len, u, side='right') - 1, g_start[g], g_end[g] - 1)
+        # any contig ~ L
+        sel = np.flatnonzero(kind >= p_same + p_genome)
+        u = rng.random(len(sel)) * cum_len[-1]
+        s2[sel] = np.clip(np.searchsorted(cum_len, u, side='right') - 1, 0, N - 1)
+
+        t1 = ref_index[perm[s1]]
+        t2 = ref_index[perm[s2]]
+        # a few ends land on excluded references
+        e = rng.random(m)
+        sel = np.flatnonzero(e < excl_end_frac)
+        t1[sel] = excl_tids[rng.integers(0, n_excl, size=len(sel))]
+        sel = np.flatnonzero((e >= excl_end_frac) & (e < 2 * excl_end_frac))
+        t2[sel] = excl_tids[rng.integers(0, n_excl, size=len(sel))]
+        # mate order is arbitrary in a BAM
+        swap = rng.random(m) < 0.5
+        a = np.where(swap, t2, t1)
+        b = np.where(swap, t1, t2)
+        records[lo:lo + m] = pack_pairs(a, b, rng.random(m) < p_pass)
+
+    return Community(n_refs, ref_index, lengths, sites, genome_of, records, seed, profile)
+
+
+# the BASELINE.json configs, made concrete
+CONFIGS = {
+    'C1': dict(n_genomes=10, n_contigs=2_000, n_pairs=1_000_000, seed=1001),
+    'C2': dict(n_genomes=100, n_contigs=50_000, n_pairs=50_000_000, seed=1002),
+    'C3': dict(n_genomes=500, n_contigs=250_000, n_pairs=500_000_000, seed=1003),
+    'C4': dict(n_genomes=2000, n_contigs=1_000_000, n_pairs=2_000_000_000, seed=1004, profile='heavy'),
+}
+
+
+def make_config(name, scale=1.0):
+    """Community for a named BASELINE config; scale<1 shrinks the pair count only."""
+    kw = dict(CONFIGS[name])
+    kw['n_pairs'] = max(1, int(kw['n_pairs'] * scale))
+    return make_community(**kw)
+
+
+def make_block_csr(n_rows, nnz_target, seed, mean_block=400):
+    """
+    C5 microbench matrix: a random block-structured symmetric CSR with
+    heavy-tailed block sizes, positive diagonal, values uniform(0.5, 1.5) / (s_i * s_j).
+    Returns (indptr int64, indices int32, data float64).  Rows are shuffled so that blocks
+    are scattered through the index space like assembly-order contigs.
+    """
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n = int(n_rows)
+    sizes = []
+    tot = 0
+    while tot < n:
+        b = int(min(n - tot, max(2, rng.pareto(1.5) * mean_block * 0.5 + 2)))
+        sizes.append(b)
+        tot += b
+    sizes = np.array(sizes, dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    blk_of = np.repeat(np.arange(len(sizes)), sizes)
+    # upper-triangle entries inside blocks, each row picks partners within its block
+    per_row = max(1, int(nnz_target // (2 * n)))
+    r = np.repeat(np.arange(n, dtype=np.int64), per_row)
+    c = starts[blk_of[r]] + (rng.random(len(r)) * sizes[blk_of[r]]).astype(np.int64)
+    keep = r != c
+    r, c = r[keep], c[keep]
+    perm = rng.permutation(n)
+    r, c = perm[r], perm[c]
+    s = rng.integers(4, 400, size=n).astype(np.float64)
+    v = rng.uniform(0.5, 1.5, size=len(r)) / (s[r] * s[c])
+    up = sp.coo_matrix((v, (np.minimum(r, c), np.maximum(r, c))), shape=(n, n)).tocsr()
+    up.sum_duplicates()
+    d = sp.diags(rng.uniform(0.5, 1.5, size=n) / (s * s))
+    m = (up + up.T + d).tocsr()
+    m.sort_indices()
+    return m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data.astype(np.float64)

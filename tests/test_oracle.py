@@ -1,0 +1,126 @@
+"""
+CPU tests: the oracle restatement (oracle/oracle.py) against the golden vectors produced by
+the reference's own functions (tests/golden/make_golden.py), plus internal consistency of
+the loop and vectorised forms.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from bin3c_b200 import synth
+from oracle import oracle
+from conftest import golden_lut
+
+
+def _seq_map(g):
+    n = len(g['lengths'])
+    return sp.coo_matrix((g['map_data'], (g['map_row'], g['map_col'])), shape=(n, n), dtype=np.uint32)
+
+
+def test_pack_roundtrip():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 2 ** 31, size=1000)
+    b = rng.integers(0, 2 ** 31, size=1000)
+    p = rng.random(1000) < 0.5
+    ra, rb, rp = synth.unpack_pairs(synth.pack_pairs(a, b, p))
+    assert np.array_equal(ra, a) and np.array_equal(rb, b) and np.array_equal(rp, p)
+
+
+def test_accumulate_bit_exact(golden):
+    g = golden
+    n = len(g['lengths'])
+    ti, tj, ok = synth.unpack_pairs(g['records'])
+    up, counts = oracle.bin_pairs_fast(ti, tj, ok, golden_lut(g), n)
+    assert [counts['accepted'], counts['ref_excluded'], counts['poor_match']] == g['counts'].tolist()
+    full = oracle.symmetrise(up)
+    assert full.dtype == np.uint32
+    # reference get_coo is canonical row-major (Q10): identical arrays, not just identical matrix
+    assert np.array_equal(full.row, g['map_row'])
+    assert np.array_equal(full.col, g['map_col'])
+    assert np.array_equal(full.data, g['map_data'])
+    assert oracle.map_weight(full) == int(g['map_weight'])
+
+
+def test_loop_equals_vectorised(golden):
+    g = golden
+    if len(g['records']) > 40000:
+        return
+    n = len(g['lengths'])
+    ti, tj, ok = synth.unpack_pairs(g['records'])
+    idx_of = {int(t): k for k, t in enumerate(g['ref_index'])}
+    dok, c1 = oracle.bin_pairs_loop(ti, tj, ok, idx_of, n)
+    m1 = oracle.dok_to_coo(dok, n)
+    up, c2 = oracle.bin_pairs_fast(ti, tj, ok, golden_lut(g), n)
+    m2 = oracle.symmetrise(up)
+    assert c1 == c2
+    assert np.array_equal(m1.row, m2.row) and np.array_equal(m1.col, m2.col) and np.array_equal(m1.data, m2.data)
+
+
+def test_mask_bit_exact(golden):
+    g = golden
+    m = _seq_map(g)
+    assert np.array_equal(oracle.max_offdiag(m), g['signal'])
+    assert np.array_equal(oracle.acceptance_mask(g['lengths'], m, int(g['min_len']), int(g['min_sig'])), g['mask'])
+
+
+def _normed(g):
+    m = _seq_map(g)
+    s = oracle.get_sites(g['sites'])
+    return sp.coo_matrix((oracle.norm_by_sites(m.row, m.col, m.data.astype(np.float64), s), (m.row, m.col)),
+                         shape=m.shape)
+
+
+def test_kr_matches_reference(golden):
+    g = golden
+    bal, x, n_iter = oracle.kr_biostochastic(_normed(g))
+    assert n_iter == int(g['kr_n_iter'])
+    # same SciPy kernels, same operation order -> the restatement is expected to be exact;
+    # the contract tolerance is 1e-9 (BASELINE.json north_star)
+    assert np.max(np.abs(x - g['kr_x']) / np.abs(g['kr_x'])) <= 1e-12
+    bal.sort_indices()
+    assert np.array_equal(bal.indptr, g['bal_indptr'])
+    assert np.array_equal(bal.indices, g['bal_indices'])
+    assert np.max(np.abs(bal.data - g['bal_data']) / np.abs(g['bal_data'])) <= 1e-12
+
+
+def test_kr_is_bistochastic(golden):
+    g = golden
+    a = _normed(g).tocsr()
+    res = oracle.kr_scale_vector(a)
+    assert res.n_zero_diag == int(g['kr_zero_diag'])
+    work = a + sp.diags((a.diagonal() == 0).astype(float))
+    rows = res.x * work.dot(res.x)
+    assert np.max(np.abs(rows - 1)) < 1e-5
+
+
+def test_compress_and_edges(golden):
+    g = golden
+    n = len(g['lengths'])
+    bal = sp.csr_matrix((g['bal_data'], g['bal_indices'], g['bal_indptr']), shape=(n, n))
+    sub = oracle.compress(bal.tocoo(), g['mask'])
+    assert sub.shape[0] == int(g['sub_n']) and sub.nnz == int(g['sub_nnz'])
+    u, v, w, scl = oracle.graph_edges(sub)
+    assert scl == float(g['scl'])
+    assert np.array_equal(u, g['edge_u']) and np.array_equal(v, g['edge_v'])
+    # nx.Graph keeps the last-written of (u,v)/(v,u), which differ by <= 1 ulp (Q9)
+    assert np.max(np.abs(w - g['edge_w']) / np.abs(g['edge_w'])) <= 1e-12
+
+
+def test_run_path_end_to_end(golden):
+    g = golden
+    ti, tj, ok = synth.unpack_pairs(g['records'])
+    r = oracle.run_path(ti, tj, ok, golden_lut(g), g['lengths'], g['sites'],
+                        min_len=int(g['min_len']), min_sig=int(g['min_sig']))
+    assert np.array_equal(r['mask'], g['mask'])
+    assert r['n_iter'] == int(g['kr_n_iter'])
+    assert np.array_equal(r['u'], g['edge_u']) and np.array_equal(r['v'], g['edge_v'])
+    assert np.max(np.abs(r['w'] - g['edge_w']) / np.abs(g['edge_w'])) <= 1e-12
+
+
+def test_compress_edge_cases():
+    m = sp.coo_matrix(np.arange(16, dtype=float).reshape(4, 4))
+    full = oracle.compress(m, np.ones(4, dtype=bool))
+    assert full.shape == (4, 4) and full.nnz == m.nnz
+    none = oracle.compress(m, np.zeros(4, dtype=bool))
+    assert none.shape == (0, 0) and none.nnz == 0
+    some = oracle.compress(m, np.array([True, False, True, False]))
+    assert np.array_equal(some.toarray(), np.array([[0., 2.], [8., 10.]]))

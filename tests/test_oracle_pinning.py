@@ -1,0 +1,53 @@
+"""
+Live pinning: where the reference tree is present (the build container), run its own
+functions verbatim (oracle/ref_exec.py) beside the oracle restatement on fresh seeded
+inputs.  Skipped on the GPU box, which has no /root/reference; the committed golden
+vectors (tests/test_oracle.py) carry the same check there.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from bin3c_b200 import synth
+from oracle import oracle, ref_exec
+
+pytestmark = pytest.mark.skipif(not ref_exec.available(), reason='reference tree not present')
+
+
+@pytest.fixture(scope='module')
+def fns():
+    return ref_exec.load()
+
+
+@pytest.mark.parametrize('seed,n,p', [(101, 120, 4000), (102, 700, 25000), (103, 64, 300)])
+def test_reference_functions_vs_oracle(fns, seed, n, p):
+    com = synth.make_community(n_genomes=3, n_contigs=n, n_pairs=p, seed=seed)
+    ti, tj, ok = synth.unpack_pairs(com.records)
+    idx_of = {int(t): k for k, t in enumerate(com.ref_index)}
+    dok, counts = oracle.bin_pairs_loop(ti, tj, ok, idx_of, n)
+
+    acc = fns['Sparse2DAccumulator'](n)
+    for (i, j), c in dok.items():
+        acc[i, j] = c
+    ref_map = acc.get_coo()
+    mine = oracle.dok_to_coo(dok, n)
+    assert ref_map.dtype == mine.dtype == np.uint32
+    assert np.array_equal(ref_map.row, mine.row) and np.array_equal(ref_map.col, mine.col)
+    assert np.array_equal(ref_map.data, mine.data)
+
+    assert np.array_equal(np.asarray(fns['max_offdiag'](ref_map)), oracle.max_offdiag(mine))
+
+    s = oracle.get_sites(com.sites)
+    fm = sp.coo_matrix((oracle.norm_by_sites(mine.row, mine.col, mine.data.astype(float), s),
+                        (mine.row, mine.col)), shape=mine.shape)
+    rb, rx, rn, _ = ref_exec.kr_with_iterations(fns, fm)
+    ob, ox, on = oracle.kr_biostochastic(fm)
+    assert rn == on
+    assert np.max(np.abs(rx - ox) / np.abs(rx)) <= 1e-12
+    assert abs(rb - ob).max() <= 1e-12 * abs(rb).max()
+
+    mask = oracle.acceptance_mask(com.lengths, mine, 1000, 2)
+    if 0 < mask.sum() < n:
+        rc = fns['compress'](rb.tocoo(), mask).tocsr()
+        oc = oracle.compress(rb.tocoo(), mask).tocsr()
+        assert rc.shape == oc.shape and abs(rc - oc).max() == 0
