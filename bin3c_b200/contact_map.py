@@ -1,0 +1,471 @@
+"""
+Host-side mirror of the hot-path surface of the reference's mzd/contact_map.py
+(cerebis/bin3C @ 76ad2a9): the ContactMap methods that build, filter, normalise and balance
+the contig x contig contact matrix, with the same names, arguments and error behaviour.
+
+    ContactMap.__init__ (reference table part)   contact_map.py:545-600
+    ContactMap._bin_map                          contact_map.py:602-809
+    ContactMap.make_reverse_index                contact_map.py:818-832
+    ContactMap.map_weight / is_empty             contact_map.py:834-844
+    ContactMap.set_primary_acceptance_mask       contact_map.py:856-909
+    ContactMap.prepare_seq_map                   contact_map.py:911-945
+    ContactMap.get_subspace                      contact_map.py:947-999
+    ContactMap._bisto_seq / _get_sites / _norm_seq   contact_map.py:1087-1145
+    SeqOrder (the five bookkeeping methods the path uses)   contact_map.py:159-447
+
+The difference from the reference is the input: BAM decoding (pysam) is outside the path
+(SURVEY.md section 8f), so `bam_file` is a PairRecords object -- the BAM header's reference
+table plus the packed pair-record stream -- instead of a file name.  Device buffers live in
+`self._dev` and never reach a pickle: seq_map / processed_map materialise on the host as the
+same SciPy containers the reference stores (Q10) the first time they are read.
+"""
+import logging
+from collections import OrderedDict
+
+import numpy as np
+import scipy.sparse as scisp
+
+from . import device as dev
+from .exceptions import NoneAcceptedException, ParsingError
+from .synth import SeqInfo
+
+logger = logging.getLogger('mzd.contact_map')
+
+
+class PairRecords(object):
+    """
+    What the path needs from a name-sorted BAM: the header's reference table and, per usable
+    read pair, one packed record (see include/bin3c_b200.h).
+
+    :param references: reference names (or None -> 'ref{n}')
+    :param lengths: reference lengths, int array [n_refs]   (bam.lengths)
+    :param sites: restriction-site count per reference; stands in for the FASTA pass of
+                  contact_map.py:520-531.  A negative value marks "not present in the FASTA".
+    :param records: uint64 packed pair records, NumPy array (host) or CUDA tensor (device)
+    """
+
+    def __init__(self, lengths, sites, records, references=None):
+        self.lengths = np.asarray(lengths, dtype=np.int64)
+        self.sites = np.asarray(sites, dtype=np.int64)
+        assert self.lengths.shape == self.sites.shape
+        self.references = references
+        self.records = records
+
+    @property
+    def n_refs(self):
+        return len(self.lengths)
+
+    def name(self, n):
+        return self.references[n] if self.references is not None else 'ref{:07d}'.format(n)
+
+    @classmethod
+    def from_community(cls, com, short_len=500):
+        """PairRecords of a synthetic Community: excluded references are short (length < min_len)."""
+        lengths = np.full(com.n_refs, short_len, dtype=np.int64)
+        sites = np.ones(com.n_refs, dtype=np.int64)
+        lengths[com.ref_index] = com.lengths
+        sites[com.ref_index] = com.sites
+        return cls(lengths, sites, com.records)
+
+
+class SeqOrder(object):
+    """Ordering / masking state of the sequences (contact_map.py:159-483); only what the path uses."""
+
+    FORWARD = 1
+    REVERSE = -1
+    ACCEPTED = True
+    EXCLUDED = False
+
+    STRUCT_TYPE = np.dtype([('pos', np.int32), ('ori', np.int8), ('mask', np.bool_), ('length', np.int32)])
+
+    def __init__(self, seq_info):
+        n = len(seq_info)
+        self._positions = None
+        self.order = np.empty(n, dtype=SeqOrder.STRUCT_TYPE)
+        self.order['pos'] = np.arange(n, dtype=np.int32)
+        self.order['ori'] = SeqOrder.FORWARD
+        self.order['mask'] = SeqOrder.ACCEPTED
+        self.order['length'] = np.fromiter((s.length for s in seq_info), dtype=np.int32, count=n)
+        self._update_positions()
+
+    def _update_positions(self):
+        # masked sequences last, then by current position (contact_map.py:203-213), without the Python loop
+        sorted_indices = np.lexsort([self.order['pos'], ~self.order['mask']])
+        self.order['pos'][sorted_indices] = np.arange(len(sorted_indices), dtype=np.int32)
+        self._positions = np.argsort(self.order['pos'])
+
+    def set_mask_only(self, _mask):
+        _mask = np.asarray(_mask, dtype=np.bool_)
+        assert len(_mask) == len(self.order), 'supplied mask must be the same length as existing order'
+        self.order['mask'] = _mask
+        self._update_positions()
+
+    def mask_vector(self):
+        return self.order['mask']
+
+    def count_accepted(self):
+        return self.order['mask'].sum()
+
+    def count_excluded(self):
+        return len(self.order) - self.count_accepted()
+
+    def accepted(self):
+        return np.where(self.order['mask'])[0]
+
+    def excluded(self):
+        return np.where(~self.order['mask'])[0]
+
+    def lengths(self, exclude_masked=False):
+        if exclude_masked:
+            return self.order['length'][self.order['mask']]
+        return self.order['length']
+
+
+class ContactMap(object):
+
+    def __init__(self, bam_file, enzymes, seq_file, min_insert, min_mapq=0, min_len=0, min_sig=1, min_extent=0,
+                 min_size=0, max_fold=None, random_seed=None, strong=None, bin_size=None, tip_size=None,
+                 precount=False):
+
+        assert isinstance(bam_file, PairRecords), \
+            'bam_file must be a PairRecords (BAM decoding is outside the accelerated path)'
+        assert tip_size is None, 'tip-based maps are out of scope (unreachable from the bin3C CLI)'
+        assert bin_size is None, 'extent (binned) maps are out of scope (plot-only consumer)'
+        assert not min_insert, 'min_insert needs alignment positions, which packed pair records do not carry'
+
+        self.strong = strong
+        self.bam_file = None            # records are not retained on the (pickled) instance
+        self.bin_size = bin_size
+        self.min_mapq = min_mapq
+        self.min_insert = min_insert
+        self.min_len = min_len
+        self.min_sig = min_sig
+        self.min_extent = min_extent
+        self.min_size = min_size
+        self.max_fold = max_fold
+        self.random_state = np.random.RandomState(random_seed)
+        self.seq_info = []
+        self.seq_file = seq_file
+        self.grouping = None
+        self.extent_map = None
+        self.order = None
+        self.tip_size = tip_size
+        self.precount = precount
+        self.total_reads = None
+        self.cov_info = None
+        self.primary_acceptance_mask = None
+        self.bisto_scale = None
+        self.seq_analyzer = None
+        self.enzymes = enzymes
+        self.pair_counts = None
+        self.kr_info = None
+        self._host = {}                 # lazily materialised SciPy containers
+        self._dev = {}                  # device-resident state, never pickled
+
+        # the set of active sequences, first filtration step is by length (contact_map.py:545-564)
+        ref_count = {'seq_missing': 0, 'too_short': 0}
+        logger.info('Reading sequences...')
+        too_short = bam_file.lengths < min_len
+        missing = ~too_short & (bam_file.sites < 0)
+        ref_count['too_short'] = int(too_short.sum())
+        ref_count['seq_missing'] = int(missing.sum())
+        keep = np.flatnonzero(~too_short & ~missing)
+        offset = 0
+        for n in keep:
+            rlen = int(bam_file.lengths[n])
+            self.seq_info.append(SeqInfo(offset, int(n), bam_file.name(n), rlen, int(bam_file.sites[n])))
+            offset += rlen
+
+        self.total_len = offset
+        self.total_seq = len(self.seq_info)
+        self.n_refs = bam_file.n_refs
+        self.current_mask = np.ones(self.total_seq, dtype=np.bool_)
+
+        if self.total_seq == 0:
+            logger.info('No sequences in BAM found in FASTA')
+            raise ParsingError('No sequences in BAM found in FASTA')
+
+        logger.info('Accepted {} sequences covering {} bp'.format(self.total_seq, self.total_len))
+        logger.info('References excluded: {}'.format(ref_count))
+
+        self.order = SeqOrder(self.seq_info)
+
+        # accumulate
+        self._bin_map(bam_file)
+
+        # create an initial acceptance mask
+        self.set_primary_acceptance_mask()
+
+    # ---- pickling: host containers only ------------------------------------------------------
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_host'] = {'seq_map': self.seq_map, 'processed_map': self.processed_map}
+        state['_dev'] = {}
+        return state
+
+    @property
+    def seq_map(self):
+        """coo_matrix[uint32], symmetric, canonical row-major -- what get_coo() returns (Q10)."""
+        if self._host.get('seq_map') is None and 'seq_map' in self._dev:
+            self._host['seq_map'] = self._dev['seq_map'].to_scipy_coo()
+        return self._host.get('seq_map')
+
+    @seq_map.setter
+    def seq_map(self, m):
+        self._host['seq_map'] = m
+        self._dev.pop('seq_map', None)
+
+    @property
+    def processed_map(self):
+        if self._host.get('processed_map') is None and 'processed_map' in self._dev:
+            self._host['processed_map'] = self._dev['processed_map'].to_scipy_csr()
+        return self._host.get('processed_map')
+
+    @processed_map.setter
+    def processed_map(self, m):
+        self._host['processed_map'] = m
+        self._dev.pop('processed_map', None)
+
+    def _seq_map_dev(self):
+        if 'seq_map' not in self._dev:
+            self._dev['seq_map'] = dev.DeviceCSR.from_scipy(self._host['seq_map'], np.uint32)
+        return self._dev['seq_map']
+
+    def _processed_dev(self):
+        if 'processed_map' not in self._dev:
+            self._dev['processed_map'] = dev.DeviceCSR.from_scipy(self._host['processed_map'], np.float64)
+        return self._dev['processed_map']
+
+    # ---- accumulation ------------------------------------------------------------------------
+    def _bin_map(self, bam, chunk_records=1 << 24):
+        """
+        Accumulate read-pair observations from the supplied pair records (contact_map.py:602-809).
+        Filter order, canonicalisation and counters follow the reference loop (:733-739, :774-777,
+        :796); the matcher outcome (:612-622) arrives as the record's pass bit.
+
+        Host records are streamed to the device in chunks on a side stream so the copy of chunk k+1
+        overlaps the classification of chunk k.
+        """
+        import torch
+        dev.require_cuda()
+        counts = OrderedDict({
+            'accepted': 0,
+            'not_tip': 0,
+            'short_insert': 0,
+            'ref_excluded': 0,
+            'median_excluded': 0,
+            'end_buffered': 0,
+            'poor_match': 0})
+
+        lut = np.full(self.n_refs, -1, dtype=np.int32)
+        idx = self.make_reverse_index('refid')
+        lut[np.fromiter(idx.keys(), dtype=np.int64, count=len(idx))] = \
+            np.fromiter(idx.values(), dtype=np.int32, count=len(idx))
+
+        records = bam.records
+        n_rec = int(records.numel()) if isinstance(records, torch.Tensor) else len(records)
+        acc = dev.Accumulator(self.total_seq, lut, max(n_rec, 1))
+
+        if isinstance(records, torch.Tensor) and records.is_cuda:
+            acc.add(records)
+        else:
+            host = records if isinstance(records, torch.Tensor) else \
+                torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint64).view(np.int64))
+            main = torch.cuda.current_stream()
+            copy_stream = torch.cuda.Stream()
+            copy_stream.wait_stream(main)
+            pending = []
+            for lo in range(0, n_rec, chunk_records):
+                hi = min(lo + chunk_records, n_rec)
+                with torch.cuda.stream(copy_stream):
+                    d = host[lo:hi].to('cuda', non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                main.wait_event(ev)
+                d.record_stream(main)
+                acc.add(d)
+                pending.append(d)
+            del pending
+
+        csr, info = acc.finish(symmetric=True)
+        self._host['seq_map'] = None
+        self._dev['seq_map'] = csr
+        counts['accepted'] = info['accepted']
+        counts['ref_excluded'] = info['ref_excluded']
+        counts['poor_match'] = info['poor_match']
+        self.pair_counts = counts
+        self._map_weight = info['map_weight']
+
+        logger.info('Pair accounting: {}'.format(counts))
+        logger.info('Total extent map weight {}'.format(self.map_weight()))
+
+    @staticmethod
+    def get_fields():
+        return SeqInfo._fields
+
+    def make_reverse_index(self, field_name):
+        """Reverse look-up from a seq_info field to the internal index (contact_map.py:818-832)."""
+        rev_idx = {}
+        for n, seq in enumerate(self.seq_info):
+            fv = getattr(seq, field_name)
+            if fv in rev_idx:
+                raise RuntimeError('field contains non-unique entries, a 1-1 mapping cannot be made')
+            rev_idx[fv] = n
+        return rev_idx
+
+    def map_weight(self):
+        """:return: the total map weight (sum ij) -- off-diagonals count twice (Q7)"""
+        if getattr(self, '_map_weight', None) is not None:
+            return self._map_weight
+        return self.seq_map.sum()
+
+    def is_empty(self):
+        return self.map_weight() == 0
+
+    def is_tipbased(self):
+        return self.tip_size is not None
+
+    # ---- filtering ---------------------------------------------------------------------------
+    def get_primary_acceptance_mask(self):
+        assert self.primary_acceptance_mask is not None, 'Primary acceptance mask has not be initialized'
+        return self.primary_acceptance_mask.copy()
+
+    def set_primary_acceptance_mask(self, min_len=None, min_sig=None, max_fold=None, update=False):
+        """
+        Determine and set the filter mask (contact_map.py:856-909):
+        (length >= min_len) & (max off-diagonal raw count >= min_sig)   (Q4, Q5).
+        """
+        import torch
+        assert max_fold is None, 'Filtering on max_fold is currently disabled'
+
+        if not min_len:
+            min_len = self.min_len
+        if not min_sig:
+            min_sig = self.min_sig
+
+        assert min_len, 'Filtering criteria min_len is None'
+        assert min_sig, 'Filtering criteria min_sig is None'
+
+        logger.debug('Setting primary acceptance mask with '
+                     'filtering criterion min_len: {} min_sig: {}'.format(min_len, min_sig))
+
+        if not update and self.primary_acceptance_mask is not None:
+            logger.debug('Using existing mask')
+            return self.get_primary_acceptance_mask()
+
+        csr = self._seq_map_dev()
+        lengths = dev.to_device(np.ascontiguousarray(self.order.lengths()), torch.int32)
+        signal = dev.max_offdiag(csr)
+        self._dev['signal'] = signal
+        mask_len = dev.acceptance_mask(lengths, signal, min_len, 0)
+        mask_sig = dev.acceptance_mask(lengths, signal, np.iinfo(np.int32).min, min_sig)
+        mask = dev.acceptance_mask(lengths, signal, min_len, min_sig)
+        self._dev['mask'] = mask
+        host = torch.stack([mask_len, mask_sig, mask]).cpu().numpy().astype(np.bool_)
+        logger.debug('Minimum length threshold removing: {}'.format(self.total_seq - host[0].sum()))
+        logger.debug('Minimum signal threshold removing: {}'.format(self.total_seq - host[1].sum()))
+
+        self.primary_acceptance_mask = host[2]
+        logger.debug('Accepted sequences: {}'.format(self.primary_acceptance_mask.sum()))
+        return self.get_primary_acceptance_mask()
+
+    # ---- normalisation + balancing -----------------------------------------------------------------
+    def prepare_seq_map(self, norm=True, bisto=False, mean_type='geometric'):
+        """
+        Prepare the sequence map by normalisation and balancing (contact_map.py:911-945).  KR runs
+        on the full N x N map, before masked contigs are removed, as the reference does (Q3).
+        """
+        logger.info('Preparing sequence map with full dimensions: {}'.format((self.total_seq, self.total_seq)))
+
+        _mask = self.get_primary_acceptance_mask()
+        self.order.set_mask_only(_mask)
+
+        if self.order.count_accepted() < 1:
+            raise NoneAcceptedException()
+
+        _map = self._seq_map_dev()
+
+        if norm:
+            _map = self._norm_seq(_map, self.is_tipbased(), mean_type=mean_type, use_sites=True)
+            logger.debug('Map normalized')
+        else:
+            import torch
+            _map = dev.DeviceCSR(_map.n, _map.indptr, _map.indices,
+                                 dev.site_norm(_map, dev.to_device(np.ones(_map.n, np.int32), torch.int32)).data)
+
+        if bisto:
+            _map, scl = self._bisto_seq(_map)
+            self.bisto_scale = scl
+            logger.debug('Map balanced')
+
+        self._host['processed_map'] = None
+        self._dev['processed_map'] = _map
+
+    def _bisto_seq(self, _map):
+        """Make a contact map bistochastic (contact_map.py:1087-1101)."""
+        logger.debug('Balancing contact map')
+        if isinstance(_map, dev.DeviceCSR):
+            x, info = dev.kr_scale_vector(_map)
+            self.kr_info = info
+            sp_logger = logging.getLogger('mzd.sparse_utils')
+            if info['zero_diag']:
+                sp_logger.warning('treating {} zeros on diagonal as ones'.format(info['zero_diag']))
+            sp_logger.debug('It took {} iterations to achieve bistochasticity'.format(info['n_iter']))
+            return dev.kr_apply(_map, x), x.cpu().numpy()
+        from . import sparse_utils
+        return sparse_utils.kr_biostochastic(_map)
+
+    def _get_sites(self):
+        _sites = np.array([si.sites for si in self.seq_info], dtype=np.float64)
+        # all sequences are assumed to have a minimum of 1 site -- even if not observed (Q6)
+        _sites[np.where(_sites == 0)] = 1
+        return _sites
+
+    def _norm_seq(self, _map, tip_based, use_sites=True, mean_type='geometric'):
+        """
+        Normalise a sequence map by the restriction-site counts of the interacting contigs
+        (contact_map.py:1110-1145 with fast_norm_fullseq_bysite, :100-113).
+        """
+        import torch
+        assert not tip_based, 'tip-based maps are out of scope'
+        if not use_sites:
+            raise NotImplementedError('length-based normalisation is dead code from the bin3C CLI '
+                                      '(prepare_seq_map hard-codes use_sites=True, contact_map.py:933)')
+        logger.debug('Doing site based normalisation')
+        sites = dev.to_device(np.array([si.sites for si in self.seq_info], dtype=np.int32), torch.int32)
+        if isinstance(_map, dev.DeviceCSR):
+            return dev.site_norm(_map, sites)
+        # host matrix in, host matrix out (same container type as given)
+        csr = dev.DeviceCSR.from_scipy(_map, np.float64)
+        out = dev.site_norm(csr, sites).to_scipy_csr()
+        return out.asformat(_map.getformat())
+
+    # ---- subspace ------------------------------------------------------------------------------
+    def get_subspace(self, permute=False, external_mask=None, marginalise=False, flatten=True, dtype=np.float64):
+        """
+        Using an already normalized full seq_map, return the map without filtered elements
+        (contact_map.py:947-999).  Returns a coo_matrix, as sparse_utils.compress does.
+        """
+        assert (not marginalise and not flatten) or np.logical_xor(marginalise, flatten), \
+            'marginalise and flatten are mutually exclusive'
+        if permute:
+            raise NotImplementedError('reordering is plot-only (contact_map.py:1066-1085) and out of scope')
+
+        res = self._subspace_dev(external_mask, want_sub=True, want_edges=False, scale=False)
+        if res is None:
+            return self.processed_map.tocoo().astype(dtype)
+        logger.info('After removing filtered sequences map dimensions: {}'.format((res['n_accepted'],) * 2))
+        return res['sub'].to_scipy_coo().astype(dtype)
+
+    def _subspace_dev(self, external_mask, want_sub, want_edges, scale, force=False):
+        import torch
+        if external_mask is not None:
+            _mask = self.get_primary_acceptance_mask()
+            logger.info('Beginning with sequences after primary filtering: {}'.format(_mask.sum()))
+            _mask &= external_mask
+            logger.info('Active sequences after applying external mask: {}'.format(_mask.sum()))
+            self.order.set_mask_only(_mask)
+        if not force and not self.order.count_accepted() < self.total_seq:
+            return None
+        mask = dev.to_device(self.order.mask_vector().astype(np.uint8), torch.uint8)
+        return dev.compress_edges(self._processed_dev(), mask, want_sub=want_sub, want_edges=want_edges, scale=scale)

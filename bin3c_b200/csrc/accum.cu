@@ -1,0 +1,802 @@
+// Pair accumulation: packed pair records -> exact-count canonical CSR (upper or symmetric).
+//
+// Replaces the per-pair Python loop of ContactMap._bin_map (contact_map.py:720-798), the
+// tid->index dict (contact_map.py:818-832) and Sparse2DAccumulator.get_coo
+// (sparse_utils.py:246-266).  Stages (all HBM-bound integer work, no tensor cores):
+//
+//   k_classify     one streaming pass over the records (8 B/pair).  tid -> index through a
+//                  bitmap+rank table staged in shared memory (the reference assigns indices in
+//                  BAM order, contact_map.py:545-564, so index = rank of tid among the kept
+//                  references); exclusion test, then matcher bit (Q12); diagonal pairs are
+//                  counted in a shared-memory histogram (most Hi-C pairs are intra-contig),
+//                  off-diagonal pairs become keys (i << b | j), staged in shared memory and
+//                  appended to the key buffer with one global atomic per 4096-record tile.
+//   k_rs_*         LSD radix sort of the keys, 8-bit digits, only the 2b significant bits.
+//   k_rle_*        run-length reduce of the sorted keys -> unique (i,j) + exact counts.
+//   k_emit_*       upper and lower halves + diagonal scattered into canonical CSR; the lower
+//                  half's order comes from a stable sort of (j, e) on j's bits alone.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace b3c {
+
+// ---- counters kept in the workspace ---------------------------------------------------
+enum { C_NKEYS = 0, C_ACCEPT, C_EXCL, C_POOR, C_NNZ_UO, C_NNZ_DIAG, C_WEIGHT, C_LUT_OK, C_OVERFLOW, C_COUNT = 16 };
+
+constexpr int CLS_THREADS = 1024;
+constexpr int CLS_RPT = 4;                       // records per thread per tile (two 128-bit loads)
+constexpr int CLS_TILE = CLS_THREADS * CLS_RPT;  // 4096 records = 32 KB of input per tile
+constexpr int SMEM_MAX = 232448;                 // 227 KB opt-in limit per CTA on sm_100
+
+constexpr int RS_THREADS = 512;
+constexpr int RS_KPT = 8;
+constexpr int RS_TILE = RS_THREADS * RS_KPT;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_BITS = 8;
+constexpr int RS_BINS = 1 << RS_BITS;
+constexpr int RS_BLOCKS = kNumSMs * 4;
+
+struct AccumState {
+    int64_t cap = 0;
+    int32_t n_seq = 0, n_refs = 0;
+    int b = 0;                // bits per index in the key
+    int64_t rank_words = 0;   // 64-bit words of the tid bitmap
+    bool smem_diag = false, smem_rank = false;
+    int cls_smem = 0, cls_grid = 0;
+    const int32_t *d_lut = nullptr;
+    int64_t o_ctr, o_diag, o_bits, o_pref, o_keys_a, o_keys_b, o_uniq, o_pos, o_cnt, o_hist, o_heads,
+        o_up_ptr, o_lo_ptr, o_len, o_indptr_f, o_indptr_u, o_scan_tmp, o_tmp64, total;
+    bool reduced = false;
+    int64_t nnz_uo = 0, nnz_diag = 0;
+    int comp_in_a = 0;        // which key buffer holds the (j,e)-sorted composite after reduce
+};
+
+static std::mutex g_mu;
+static std::unordered_map<void *, AccumState> g_states;
+
+static int key_bits_for(int32_t n_seq) {
+    int b = 1;
+    while ((1ll << b) < (int64_t)n_seq) ++b;
+    return b;
+}
+
+static void layout(AccumState &st) {
+    Carver c;
+    const int64_t cap = st.cap > 0 ? st.cap : 1;
+    const int64_t n1 = (int64_t)st.n_seq + 1;
+    st.o_ctr = c.take(C_COUNT * 8);
+    st.o_diag = c.take((int64_t)st.n_seq * 4);
+    st.o_bits = c.take(st.rank_words * 8);
+    st.o_pref = c.take(st.rank_words * 4);
+    st.o_tmp64 = c.take((st.rank_words + 1) * 8 * 2);
+    st.o_keys_a = c.take(cap * 8);
+    st.o_keys_b = c.take(cap * 8);
+    st.o_uniq = c.take(cap * 8);
+    st.o_pos = c.take((cap + 1) * 4);
+    st.o_cnt = c.take(cap * 4);
+    st.o_hist = c.take((int64_t)RS_BINS * RS_BLOCKS * 4);
+    st.o_heads = c.take((RS_BLOCKS + 2) * 8 * 2);
+    st.o_up_ptr = c.take(n1 * 8);
+    st.o_lo_ptr = c.take(n1 * 8);
+    st.o_len = c.take(n1 * 8);
+    st.o_indptr_f = c.take(n1 * 8);
+    st.o_indptr_u = c.take(n1 * 8);
+    int64_t m = st.n_seq > st.rank_words ? st.n_seq : st.rank_words;
+    if (m < RS_BLOCKS) m = RS_BLOCKS;
+    st.o_scan_tmp = c.take(scan_tmp_elems(m) * 8);
+    st.total = c.cur;
+}
+
+static void plan(AccumState &st, int64_t cap, int32_t n_seq, int32_t n_refs) {
+    st.cap = cap;
+    st.n_seq = n_seq;
+    st.n_refs = n_refs;
+    st.b = key_bits_for(n_seq);
+    st.rank_words = ceil_div(n_refs > 0 ? n_refs : 1, 64);
+    // shared-memory plan of k_classify: header | staging | rank table | diagonal histogram
+    const int64_t hdr = 32;
+    const int64_t rank_bytes = align_up(st.rank_words * 8, 16) + align_up(st.rank_words * 4, 16);
+    const int64_t diag_bytes = align_up((int64_t)n_seq * 4, 16);
+    const int64_t stage32 = (int64_t)CLS_TILE * 4, stage64 = (int64_t)CLS_TILE * 8;
+    st.smem_diag = st.smem_rank = false;
+    if (st.b <= 16 && hdr + stage32 + rank_bytes + diag_bytes <= SMEM_MAX) {
+        st.smem_diag = st.smem_rank = true;
+        st.cls_smem = (int)(hdr + stage32 + rank_bytes + diag_bytes);
+    } else if (st.b <= 16 && hdr + stage32 + diag_bytes <= SMEM_MAX) {
+        st.smem_diag = true;
+        st.cls_smem = (int)(hdr + stage32 + diag_bytes);
+    } else if (hdr + stage64 + rank_bytes <= SMEM_MAX) {
+        st.smem_rank = true;
+        st.cls_smem = (int)(hdr + stage64 + rank_bytes);
+    } else {
+        st.cls_smem = (int)(hdr + stage64);
+    }
+    st.cls_grid = kNumSMs;      // persistent: one 1024-thread CTA per SM, tiles strided over the grid
+    layout(st);
+}
+
+// ---- rank table (bitmap + prefix popcount) -------------------------------------------------
+__global__ void k_rank_bits(const int32_t *__restrict__ lut, int32_t n_refs, int64_t n_words,
+                            unsigned long long *__restrict__ bits, int64_t *__restrict__ cnt) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    unsigned long long m = 0;
+    const int64_t t0 = w * 64;
+    for (int k = 0; k < 64; ++k) {
+        const int64_t t = t0 + k;
+        if (t < n_refs && lut[t] >= 0) m |= 1ull << k;
+    }
+    bits[w] = m;
+    cnt[w] = __popcll(m);
+}
+
+__global__ void k_rank_verify(const int32_t *__restrict__ lut, int32_t n_refs, int32_t n_seq,
+                              const unsigned long long *__restrict__ bits, const int64_t *__restrict__ pref64,
+                              uint32_t *__restrict__ pref, int64_t n_words, unsigned long long *__restrict__ ctr) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_words) pref[t] = (uint32_t)pref64[t];
+    if (t >= n_refs) return;
+    const int32_t v = lut[t];
+    if (v < 0) return;
+    const int64_t w = t >> 6;
+    const int bit = (int)(t & 63);
+    const int64_t expect = pref64[w] + __popcll(bits[w] & ((1ull << bit) - 1ull));
+    if (expect != (int64_t)v || v >= n_seq) ctr[C_LUT_OK] = 0;   // benign race: every writer stores 0
+}
+
+// ---- classify ------------------------------------------------------------------------------
+struct ClsParams {
+    const uint64_t *rec;
+    int64_t n_rec;
+    const int32_t *lut;
+    int32_t n_refs, n_seq;
+    int b;
+    int64_t rank_words;
+    const unsigned long long *g_bits;
+    const uint32_t *g_pref;
+    uint32_t *diag;
+    uint64_t *keys;
+    int64_t cap;
+    unsigned long long *ctr;
+};
+
+template <bool SMEM_DIAG, bool RANK>
+__device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char *smem) {
+    using stage_t = typename std::conditional<SMEM_DIAG, uint32_t, uint64_t>::type;
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(smem);
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + 8);
+    stage_t *s_stage = reinterpret_cast<stage_t *>(smem + 32);
+    unsigned char *cur = smem + 32 + sizeof(stage_t) * CLS_TILE;
+    const unsigned long long *s_bits = nullptr;
+    const uint32_t *s_pref = nullptr;
+    if (RANK) {
+        unsigned long long *wb = reinterpret_cast<unsigned long long *>(cur);
+        cur += (P.rank_words * 8 + 15) / 16 * 16;
+        uint32_t *wp = reinterpret_cast<uint32_t *>(cur);
+        cur += (P.rank_words * 4 + 15) / 16 * 16;
+        for (int64_t i = threadIdx.x; i < P.rank_words; i += CLS_THREADS) {
+            wb[i] = P.g_bits[i];
+            wp[i] = P.g_pref[i];
+        }
+        s_bits = wb;
+        s_pref = wp;
+    }
+    uint32_t *s_diag = reinterpret_cast<uint32_t *>(cur);
+    if (SMEM_DIAG)
+        for (int i = threadIdx.x; i < P.n_seq; i += CLS_THREADS) s_diag[i] = 0;
+    if (threadIdx.x == 0) *s_cnt = 0;
+    __syncthreads();
+
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    unsigned n_acc = 0, n_excl = 0, n_poor = 0;
+    const int64_t n_tiles = (P.n_rec + CLS_TILE - 1) / CLS_TILE;
+
+    auto lookup = [&](uint32_t t) -> int32_t {
+        if (t >= (uint32_t)P.n_refs) return -1;
+        if (RANK) {
+            const unsigned long long m = s_bits[t >> 6];
+            const unsigned bit = t & 63u;
+            if (!((m >> bit) & 1ull)) return -1;
+            return (int32_t)(s_pref[t >> 6] + __popcll(m & ((1ull << bit) - 1ull)));
+        } else {
+            const int32_t v = __ldg(P.lut + t);
+            return v < P.n_seq ? v : -1;
+        }
+    };
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * CLS_TILE;
+        // two 128-bit streaming loads per thread, both issued before use
+        uint4 v[CLS_RPT / 2];
+        bool ok[CLS_RPT];
+#pragma unroll
+        for (int l = 0; l < CLS_RPT / 2; ++l) {
+            const int64_t i = base + ((int64_t)l * CLS_THREADS + threadIdx.x) * 2;
+            ok[2 * l] = i < P.n_rec;
+            ok[2 * l + 1] = i + 1 < P.n_rec;
+            if (ok[2 * l + 1]) {
+                v[l] = ld_stream_u4(P.rec + i);
+            } else if (ok[2 * l]) {
+                const uint2 t = ld_stream_u2(P.rec + i);
+                v[l] = make_uint4(t.x, t.y, 0u, 0u);
+            } else {
+                v[l] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CLS_RPT; ++k) {
+            const uint32_t lo = (k & 1) ? v[k >> 1].z : v[k >> 1].x;
+            const uint32_t hi = (k & 1) ? v[k >> 1].w : v[k >> 1].y;
+            bool off = false;
+            uint64_t key = 0;
+            if (ok[k]) {
+                const uint32_t ti = lo & 0x7fffffffu, tj = hi & 0x7fffffffu;
+                const int32_t ix = lookup(ti);
+                const int32_t jx = (tj == ti) ? ix : lookup(tj);
+                if (ix < 0 || jx < 0) {
+                    ++n_excl;                                   // contact_map.py:733-735
+                } else if (!(lo >> 31)) {
+                    ++n_poor;                                   // contact_map.py:737-739
+                } else {
+                    ++n_acc;                                    // contact_map.py:796
+                    if (ix == jx) {
+                        if (SMEM_DIAG) atomicAdd(&s_diag[ix], 1u);
+                        else atomicAdd(&P.diag[ix], 1u);
+                    } else {
+                        const uint32_t a = min(ix, jx), c = max(ix, jx);   // contact_map.py:774-777
+                        key = ((uint64_t)a << P.b) | c;
+                        off = true;
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(kFullMask, off);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                unsigned at = 0;
+                if ((int)lane == leader) at = atomicAdd(s_cnt, __popc(m));
+                at = __shfl_sync(kFullMask, at, leader);
+                if (off) s_stage[at + __popc(m & lt)] = (stage_t)key;
+            }
+        }
+        __syncthreads();
+        const unsigned total = *s_cnt;
+        if (threadIdx.x == 0 && total) *s_base = atomicAdd(&P.ctr[C_NKEYS], (unsigned long long)total);
+        __syncthreads();
+        if (total) {
+            const unsigned long long gb = *s_base;
+            if ((int64_t)(gb + total) <= P.cap) {
+                for (unsigned i = threadIdx.x; i < total; i += CLS_THREADS) P.keys[gb + i] = (uint64_t)s_stage[i];
+            } else if (threadIdx.x == 0) {
+                P.ctr[C_OVERFLOW] = 1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *s_cnt = 0;
+        // the next tile's first staging write happens after its own ballot, and every thread has
+        // passed the barrier above, so the reset is ordered by the barrier at the end of that tile;
+        // an explicit barrier keeps the reset ahead of the next tile's atomics
+        __syncthreads();
+    }
+
+    if (SMEM_DIAG) {
+        for (int i = threadIdx.x; i < P.n_seq; i += CLS_THREADS) {
+            const uint32_t c = s_diag[i];
+            if (c) atomicAdd(&P.diag[i], c);
+        }
+    }
+    // counters: warp reduce, then one atomic per warp
+    n_acc = warp_sum(n_acc);
+    n_excl = warp_sum(n_excl);
+    n_poor = warp_sum(n_poor);
+    if (lane == 0) {
+        if (n_acc) atomicAdd(&P.ctr[C_ACCEPT], (unsigned long long)n_acc);
+        if (n_excl) atomicAdd(&P.ctr[C_EXCL], (unsigned long long)n_excl);
+        if (n_poor) atomicAdd(&P.ctr[C_POOR], (unsigned long long)n_poor);
+    }
+}
+
+template <bool SMEM_DIAG, bool SMEM_RANK>
+__global__ void __launch_bounds__(CLS_THREADS, 1) k_classify(ClsParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // the rank table is only valid when the tid->index map is the dense rank map (checked on device)
+    const bool rank_ok = SMEM_RANK && (P.ctr[C_LUT_OK] != 0);
+    if (rank_ok) classify_tiles<SMEM_DIAG, true>(P, smem);
+    else classify_tiles<SMEM_DIAG, false>(P, smem);
+}
+
+// ---- LSD radix sort --------------------------------------------------------------------
+__device__ __forceinline__ void rs_segment(int64_t n, int64_t *lo, int64_t *hi, int64_t *t0, int64_t *t1) {
+    const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    const int64_t tpb = (n_tiles + gridDim.x - 1) / gridDim.x;
+    *t0 = min((int64_t)blockIdx.x * tpb, n_tiles);
+    *t1 = min(*t0 + tpb, n_tiles);
+    *lo = *t0 * RS_TILE;
+    *hi = min(n, *t1 * RS_TILE);
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restrict__ keys,
+                                                        const unsigned long long *__restrict__ d_n, int shift,
+                                                        unsigned mask, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t s_h[RS_BINS];
+    for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) s_h[i] = 0;
+    __syncthreads();
+    int64_t lo, hi, t0, t1;
+    rs_segment((int64_t)*d_n, &lo, &hi, &t0, &t1);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RS_THREADS)
+        atomicAdd(&s_h[(unsigned)(keys[i] >> shift) & mask], 1u);
+    __syncthreads();
+    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) hist[(int64_t)d * gridDim.x + blockIdx.x] = s_h[d];
+}
+
+// single block: exclusive scan of m uint32 values in place
+__global__ void __launch_bounds__(1024) k_scan_u32_single(uint32_t *__restrict__ a, int64_t m) {
+    __shared__ uint32_t s_w[33];
+    const int64_t per = (m + 1023) / 1024;
+    const int64_t lo = min(m, (int64_t)threadIdx.x * per), hi = min(m, lo + per);
+    uint32_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += a[i];
+    uint32_t tot;
+    uint32_t ex = block_scan_excl<uint32_t>(s, s_w, &tot);
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint32_t v = a[i];
+        a[i] = ex;
+        ex += v;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__restrict__ in,
+                                                           uint64_t *__restrict__ out,
+                                                           const unsigned long long *__restrict__ d_n, int shift,
+                                                           unsigned mask, const uint32_t *__restrict__ offs) {
+    __shared__ uint32_t s_wcnt[RS_WARPS][RS_BINS + 1];
+    __shared__ uint32_t s_off[RS_BINS];
+    __shared__ uint32_t s_tot[RS_BINS];
+    __shared__ uint32_t s_bin[RS_BINS];
+    __shared__ uint32_t s_scan[33];
+    extern __shared__ __align__(16) unsigned char rs_dyn[];
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(rs_dyn);     // RS_TILE keys (32 KB, dynamic)
+
+    const int64_t n = (int64_t)*d_n;
+    int64_t lo, hi, t0, t1;
+    rs_segment(n, &lo, &hi, &t0, &t1);
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5, lt = lanemask_lt();
+    if (threadIdx.x < RS_BINS) s_off[threadIdx.x] = offs[(int64_t)threadIdx.x * gridDim.x + blockIdx.x];
+
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int64_t base = tile * RS_TILE;
+        const int cnt = (int)min((int64_t)RS_TILE, n - base);
+        for (int i = threadIdx.x; i < RS_WARPS * (RS_BINS + 1); i += RS_THREADS) (&s_wcnt[0][0])[i] = 0;
+        uint64_t key[RS_KPT];
+        uint32_t dg[RS_KPT], rk[RS_KPT];
+#pragma unroll
+        for (int k = 0; k < RS_KPT; ++k) {
+            const int idx = warp * (32 * RS_KPT) + k * 32 + lane;     // warp-striped: order == index order
+            const bool valid = idx < cnt;
+            key[k] = valid ? in[base + idx] : 0ull;
+            dg[k] = valid ? ((unsigned)(key[k] >> shift) & mask) : (unsigned)RS_BINS;
+        }
+        __syncthreads();
+        // stable rank inside the warp, one item row at a time
+#pragma unroll
+        for (int k = 0; k < RS_KPT; ++k) {
+            const unsigned m = __match_any_sync(kFullMask, dg[k]);
+            const uint32_t prior = s_wcnt[warp][dg[k]];
+            rk[k] = prior + __popc(m & lt);
+            __syncwarp();
+            if ((int)lane == __ffs(m) - 1) s_wcnt[warp][dg[k]] = prior + __popc(m);
+            __syncwarp();
+        }
+        __syncthreads();
+        // per digit: exclusive scan over warps, tile total
+        if (threadIdx.x < RS_BINS) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) {
+                const uint32_t c = s_wcnt[w][threadIdx.x];
+                s_wcnt[w][threadIdx.x] = run;
+                run += c;
+            }
+            s_tot[threadIdx.x] = run;
+        }
+        __syncthreads();
+        {
+            const uint32_t v = (threadIdx.x < RS_BINS) ? s_tot[threadIdx.x] : 0u;
+            uint32_t tot;
+            const uint32_t ex = block_scan_excl<uint32_t>(v, s_scan, &tot);
+            if (threadIdx.x < RS_BINS) s_bin[threadIdx.x] = ex;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RS_KPT; ++k)
+            if (dg[k] < (unsigned)RS_BINS) s_keys[s_bin[dg[k]] + s_wcnt[warp][dg[k]] + rk[k]] = key[k];
+        __syncthreads();
+        for (int q = threadIdx.x; q < cnt; q += RS_THREADS) {
+            const uint64_t kk = s_keys[q];
+            const unsigned d = (unsigned)(kk >> shift) & mask;
+            out[(int64_t)s_off[d] + (q - (int)s_bin[d])] = kk;
+        }
+        __syncthreads();
+        if (threadIdx.x < RS_BINS) s_off[threadIdx.x] += s_tot[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// sort keys on bits [bit_lo, bit_hi); returns the index (0=a,1=b) of the buffer with the result
+static int radix_sort(uint64_t *a, uint64_t *b, const unsigned long long *d_n, int bit_lo, int bit_hi,
+                      uint32_t *d_hist, cudaStream_t s, int *where) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        B3C_CUDA(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 8));
+        attr_done = true;
+    }
+    int cur = 0;
+    for (int shift = bit_lo; shift < bit_hi; shift += RS_BITS) {
+        const int w = (bit_hi - shift) < RS_BITS ? (bit_hi - shift) : RS_BITS;
+        const unsigned mask = (1u << w) - 1u;
+        const uint64_t *src = cur ? b : a;
+        uint64_t *dst = cur ? a : b;
+        k_rs_hist<<<RS_BLOCKS, RS_THREADS, 0, s>>>(src, d_n, shift, mask, d_hist);
+        B3C_LAUNCH_CHECK();
+        k_scan_u32_single<<<1, 1024, 0, s>>>(d_hist, (int64_t)RS_BINS * RS_BLOCKS);
+        B3C_LAUNCH_CHECK();
+        k_rs_scatter<<<RS_BLOCKS, RS_THREADS, RS_TILE * 8, s>>>(src, dst, d_n, shift, mask, d_hist);
+        B3C_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+    *where = cur;
+    return B3C_OK;
+}
+
+// ---- run-length reduce ----------------------------------------------------------------------
+__global__ void __launch_bounds__(RS_THREADS) k_rle_count(const uint64_t *__restrict__ keys,
+                                                          const unsigned long long *__restrict__ d_n,
+                                                          int64_t *__restrict__ heads) {
+    __shared__ unsigned s_c;
+    if (threadIdx.x == 0) s_c = 0;
+    __syncthreads();
+    int64_t lo, hi, t0, t1;
+    rs_segment((int64_t)*d_n, &lo, &hi, &t0, &t1);
+    unsigned c = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RS_THREADS) c += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    c = warp_sum(c);
+    if (lane_id() == 0 && c) atomicAdd(&s_c, c);
+    __syncthreads();
+    if (threadIdx.x == 0) heads[blockIdx.x] = s_c;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rle_write(const uint64_t *__restrict__ keys,
+                                                          const unsigned long long *__restrict__ d_n,
+                                                          const int64_t *__restrict__ heads_ex,
+                                                          uint64_t *__restrict__ uniq, uint32_t *__restrict__ pos) {
+    __shared__ uint32_t s_w[33];
+    int64_t lo, hi, t0, t1;
+    rs_segment((int64_t)*d_n, &lo, &hi, &t0, &t1);
+    int64_t run = heads_ex[blockIdx.x];
+    for (int64_t base = lo; base < hi; base += RS_THREADS) {
+        const int64_t i = base + threadIdx.x;
+        uint64_t k = 0;
+        uint32_t h = 0;
+        if (i < hi) {
+            k = keys[i];
+            h = (i == 0 || k != keys[i - 1]) ? 1u : 0u;
+        }
+        uint32_t tot;
+        const uint32_t ex = block_scan_excl<uint32_t>(h, s_w, &tot);
+        if (h) {
+            uniq[run + ex] = k;
+            pos[run + ex] = (uint32_t)i;
+        }
+        run += tot;
+    }
+}
+
+__global__ void k_rle_finish(const int64_t *__restrict__ heads_ex, int nblk, const unsigned long long *d_n,
+                             uint32_t *__restrict__ pos, unsigned long long *__restrict__ ctr) {
+    const int64_t nnz = heads_ex[nblk];
+    ctr[C_NNZ_UO] = (unsigned long long)nnz;
+    pos[nnz] = (uint32_t)*d_n;
+}
+
+__global__ void k_rle_counts(const uint32_t *__restrict__ pos, const unsigned long long *__restrict__ ctr,
+                             uint32_t *__restrict__ cnt, int b, const uint64_t *__restrict__ uniq,
+                             uint64_t *__restrict__ comp) {
+    const int64_t nnz = (int64_t)ctr[C_NNZ_UO];
+    const uint64_t jmask = (1ull << b) - 1ull;
+    unsigned long long w = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = pos[e + 1] - pos[e];
+        cnt[e] = c;
+        w += c;
+        comp[e] = ((uint64_t)(uniq[e] & jmask) << 32) | (uint64_t)e;    // (column, entry id)
+    }
+    w = warp_sum(w);
+    if (lane_id() == 0 && w) atomicAdd((unsigned long long *)&ctr[C_WEIGHT], 2ull * w);   // mirrored entries (Q7)
+}
+
+__global__ void k_diag_stats(const uint32_t *__restrict__ diag, int32_t n, unsigned long long *__restrict__ ctr) {
+    unsigned long long nz = 0, w = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = diag[i];
+        nz += c ? 1ull : 0ull;
+        w += c;
+    }
+    nz = warp_sum(nz);
+    w = warp_sum(w);
+    if (lane_id() == 0) {
+        if (nz) atomicAdd(&ctr[C_NNZ_DIAG], nz);
+        if (w) atomicAdd(&ctr[C_WEIGHT], w);
+    }
+}
+
+// ptr[r] = first entry whose row >= r, ptr[n_seq] = n; rows come from sorted keys >> shift
+__global__ void k_row_ptr(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ d_n, int shift,
+                          int32_t n_seq, int64_t *__restrict__ ptr) {
+    const int64_t n = (int64_t)*d_n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t e = gid; e < n; e += stride) {
+        const int64_t r = (int64_t)(keys[e] >> shift);
+        const int64_t rp = e > 0 ? (int64_t)(keys[e - 1] >> shift) : -1;
+        for (int64_t q = rp + 1; q <= r; ++q) ptr[q] = e;
+    }
+    const int64_t rl = n > 0 ? (int64_t)(keys[n - 1] >> shift) : -1;
+    for (int64_t q = rl + 1 + gid; q <= n_seq; q += stride) ptr[q] = n;
+}
+
+__global__ void k_row_len(const int64_t *__restrict__ up, const int64_t *__restrict__ lo,
+                          const uint32_t *__restrict__ diag, int32_t n, int64_t *__restrict__ len_f,
+                          int64_t *__restrict__ len_u) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = up[r + 1] - up[r], l = lo[r + 1] - lo[r], d = diag[r] ? 1 : 0;
+        len_f[r] = u + l + d;
+        len_u[r] = u + d;
+    }
+}
+
+__global__ void k_emit(int symmetric, int b, int32_t n_seq, const unsigned long long *__restrict__ ctr,
+                       const uint64_t *__restrict__ uniq, const uint32_t *__restrict__ cnt,
+                       const uint64_t *__restrict__ comp, const uint32_t *__restrict__ diag,
+                       const int64_t *__restrict__ up, const int64_t *__restrict__ lo,
+                       const int64_t *__restrict__ indptr, int32_t *__restrict__ indices,
+                       uint32_t *__restrict__ counts) {
+    const int64_t nnz = (int64_t)ctr[C_NNZ_UO];
+    const uint64_t jmask = (1ull << b) - 1ull;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // upper half: entry e sits after the row's lower half and diagonal
+    for (int64_t e = gid; e < nnz; e += stride) {
+        const uint64_t k = uniq[e];
+        const int64_t i = (int64_t)(k >> b);
+        const int64_t lower = symmetric ? (lo[i + 1] - lo[i]) : 0;
+        const int64_t d = indptr[i] + lower + (diag[i] ? 1 : 0) + (e - up[i]);
+        indices[d] = (int32_t)(k & jmask);
+        counts[d] = cnt[e];
+    }
+    // diagonal
+    for (int64_t r = gid; r < n_seq; r += stride) {
+        const uint32_t c = diag[r];
+        if (c) {
+            const int64_t d = indptr[r] + (symmetric ? (lo[r + 1] - lo[r]) : 0);
+            indices[d] = (int32_t)r;
+            counts[d] = c;
+        }
+    }
+    // lower half (mirror): composite t is sorted by (column j, entry id) == (j, i)
+    if (symmetric) {
+        for (int64_t t = gid; t < nnz; t += stride) {
+            const uint64_t c = comp[t];
+            const int64_t j = (int64_t)(c >> 32);
+            const int64_t e = (int64_t)(c & 0xffffffffull);
+            const int64_t d = indptr[j] + (t - lo[j]);
+            indices[d] = (int32_t)(uniq[e] >> b);
+            counts[d] = cnt[e];
+        }
+    }
+}
+
+template <bool A, bool B>
+static int launch_classify(const AccumState &st, const ClsParams &P, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        B3C_CUDA(cudaFuncSetAttribute(k_classify<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        attr_done = true;
+    }
+    k_classify<A, B><<<st.cls_grid, CLS_THREADS, st.cls_smem, s>>>(P);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+static int get_state(void *ws, AccumState *out) {
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = g_states.find(ws);
+    if (it == g_states.end()) {
+        set_error("workspace %p has no accumulator: call b3c_accum_begin first", ws);
+        return B3C_ERR_ARG;
+    }
+    *out = it->second;
+    return B3C_OK;
+}
+
+}  // namespace b3c
+
+using namespace b3c;
+
+extern "C" {
+
+int64_t b3c_accum_workspace_bytes(int64_t pair_capacity, int32_t n_seq, int32_t n_refs) {
+    if (pair_capacity < 0 || n_seq <= 0 || n_refs <= 0) return B3C_ERR_ARG;
+    AccumState st;
+    plan(st, pair_capacity, n_seq, n_refs);
+    return st.total;
+}
+
+int b3c_accum_begin(void *d_ws, int64_t ws_bytes, int64_t pair_capacity, int32_t n_seq,
+                    const int32_t *d_tid2idx, int32_t n_refs, void *stream) {
+    B3C_REQUIRE(d_ws && d_tid2idx, "null pointer");
+    B3C_REQUIRE(n_seq > 0 && n_refs > 0 && pair_capacity >= 0, "invalid sizes N=%d refs=%d cap=%lld", n_seq, n_refs,
+                (long long)pair_capacity);
+    B3C_REQUIRE(pair_capacity < 0xffffffffll, "pair capacity must be below 2^32 per accumulator");
+    AccumState st;
+    plan(st, pair_capacity, n_seq, n_refs);
+    if (ws_bytes < st.total) {
+        set_error("workspace too small: %lld < %lld", (long long)ws_bytes, (long long)st.total);
+        return B3C_ERR_CAPACITY;
+    }
+    st.d_lut = d_tid2idx;
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    B3C_CUDA(cudaMemsetAsync(ws + st.o_ctr, 0, C_COUNT * 8, s));
+    B3C_CUDA(cudaMemsetAsync(ws + st.o_diag, 0, (size_t)n_seq * 4, s));
+    // rank table + on-device check that tid2idx is the dense rank map
+    unsigned long long one = 1;
+    B3C_CUDA(cudaMemcpyAsync(ws + st.o_ctr + C_LUT_OK * 8, &one, 8, cudaMemcpyHostToDevice, s));
+    int64_t *cnt64 = (int64_t *)(ws + st.o_tmp64);
+    int64_t *pref64 = cnt64 + st.rank_words + 1;
+    k_rank_bits<<<(unsigned)ceil_div(st.rank_words, 256), 256, 0, s>>>(d_tid2idx, n_refs, st.rank_words,
+                                                                      (unsigned long long *)(ws + st.o_bits), cnt64);
+    B3C_LAUNCH_CHECK();
+    int rc = scan_exclusive_i64(cnt64, pref64, st.rank_words, (int64_t *)(ws + st.o_scan_tmp), s);
+    if (rc) return rc;
+    const int64_t nver = n_refs > st.rank_words ? n_refs : st.rank_words;
+    k_rank_verify<<<(unsigned)ceil_div(nver, 256), 256, 0, s>>>(d_tid2idx, n_refs, n_seq,
+                                                               (const unsigned long long *)(ws + st.o_bits), pref64,
+                                                               (uint32_t *)(ws + st.o_pref), st.rank_words,
+                                                               (unsigned long long *)(ws + st.o_ctr));
+    B3C_LAUNCH_CHECK();
+    std::lock_guard<std::mutex> g(g_mu);
+    g_states[d_ws] = st;
+    return B3C_OK;
+}
+
+int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    B3C_REQUIRE(n_records >= 0, "negative record count");
+    if (n_records == 0) return B3C_OK;
+    B3C_REQUIRE(d_records != nullptr, "null records");
+    B3C_REQUIRE(((uintptr_t)d_records & 15) == 0, "records must be 16-byte aligned");
+    B3C_REQUIRE(!st.reduced, "accumulator already reduced: call b3c_accum_begin to start a new map");
+    char *ws = (char *)d_ws;
+    ClsParams P;
+    P.rec = d_records;
+    P.n_rec = n_records;
+    P.lut = st.d_lut;
+    P.n_refs = st.n_refs;
+    P.n_seq = st.n_seq;
+    P.b = st.b;
+    P.rank_words = st.rank_words;
+    P.g_bits = (const unsigned long long *)(ws + st.o_bits);
+    P.g_pref = (const uint32_t *)(ws + st.o_pref);
+    P.diag = (uint32_t *)(ws + st.o_diag);
+    P.keys = (uint64_t *)(ws + st.o_keys_a);
+    P.cap = st.cap;
+    P.ctr = (unsigned long long *)(ws + st.o_ctr);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (st.smem_diag && st.smem_rank) return launch_classify<true, true>(st, P, s);
+    if (st.smem_diag) return launch_classify<true, false>(st, P, s);
+    if (st.smem_rank) return launch_classify<false, true>(st, P, s);
+    return launch_classify<false, false>(st, P, s);
+}
+
+int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    B3C_REQUIRE(h_sizes != nullptr, "null h_sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    unsigned long long *ctr = (unsigned long long *)(ws + st.o_ctr);
+    uint64_t *ka = (uint64_t *)(ws + st.o_keys_a), *kb = (uint64_t *)(ws + st.o_keys_b);
+    uint64_t *uniq = (uint64_t *)(ws + st.o_uniq);
+    uint32_t *pos = (uint32_t *)(ws + st.o_pos), *cnt = (uint32_t *)(ws + st.o_cnt);
+    uint32_t *hist = (uint32_t *)(ws + st.o_hist);
+    int64_t *heads = (int64_t *)(ws + st.o_heads), *heads_ex = heads + RS_BLOCKS + 2;
+    int64_t *scan_tmp = (int64_t *)(ws + st.o_scan_tmp);
+    uint32_t *diag = (uint32_t *)(ws + st.o_diag);
+    int64_t *up = (int64_t *)(ws + st.o_up_ptr), *lo = (int64_t *)(ws + st.o_lo_ptr), *len = (int64_t *)(ws + st.o_len);
+    int64_t *ip_f = (int64_t *)(ws + st.o_indptr_f), *ip_u = (int64_t *)(ws + st.o_indptr_u);
+
+    // 1. sort the off-diagonal keys on their 2b significant bits
+    int where = 0;
+    rc = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
+    if (rc) return rc;
+    uint64_t *sorted = where ? kb : ka, *other = where ? ka : kb;
+    // 2. run-length reduce -> unique keys + counts, composite (j, e) for the mirror half
+    k_rle_count<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(heads, heads_ex, RS_BLOCKS, scan_tmp, s);
+    if (rc) return rc;
+    k_rle_write<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads_ex, uniq, pos);
+    B3C_LAUNCH_CHECK();
+    k_rle_finish<<<1, 1, 0, s>>>(heads_ex, RS_BLOCKS, ctr + C_NKEYS, pos, ctr);
+    B3C_LAUNCH_CHECK();
+    k_rle_counts<<<kNumSMs * 8, 256, 0, s>>>(pos, ctr, cnt, st.b, uniq, sorted);   // composite overwrites the sorted keys
+    B3C_LAUNCH_CHECK();
+    k_diag_stats<<<kNumSMs * 2, 256, 0, s>>>(diag, st.n_seq, ctr);
+    B3C_LAUNCH_CHECK();
+    // 3. stable sort of the composite on the column bits only -> (j, i) order
+    int where2 = 0;
+    rc = radix_sort(sorted, other, ctr + C_NNZ_UO, 32, 32 + st.b, hist, s, &where2);
+    if (rc) return rc;
+    uint64_t *comp = where2 ? other : sorted;
+    st.comp_in_a = (comp == ka) ? 1 : 0;
+    // 4. row pointers of both halves, row lengths, indptr of both output forms
+    k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(uniq, ctr + C_NNZ_UO, st.b, st.n_seq, up);
+    B3C_LAUNCH_CHECK();
+    k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(comp, ctr + C_NNZ_UO, 32, st.n_seq, lo);
+    B3C_LAUNCH_CHECK();
+    k_row_len<<<kNumSMs * 4, 256, 0, s>>>(up, lo, diag, st.n_seq, len, ip_u /* scratch: upper lengths */);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(len, ip_f, st.n_seq, scan_tmp, s);
+    if (rc) return rc;
+    B3C_CUDA(cudaMemcpyAsync(len, ip_u, (size_t)st.n_seq * 8, cudaMemcpyDeviceToDevice, s));
+    rc = scan_exclusive_i64(len, ip_u, st.n_seq, scan_tmp, s);
+    if (rc) return rc;
+
+    unsigned long long h[C_COUNT];
+    B3C_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaStreamSynchronize(s));
+    if (h[C_OVERFLOW]) {
+        set_error("pair capacity %lld exceeded (%llu off-diagonal keys)", (long long)st.cap, h[C_NKEYS]);
+        return B3C_ERR_CAPACITY;
+    }
+    st.reduced = true;
+    st.nnz_uo = (int64_t)h[C_NNZ_UO];
+    st.nnz_diag = (int64_t)h[C_NNZ_DIAG];
+    h_sizes[0] = st.nnz_uo + st.nnz_diag;
+    h_sizes[1] = 2 * st.nnz_uo + st.nnz_diag;
+    h_sizes[2] = (int64_t)h[C_ACCEPT];
+    h_sizes[3] = (int64_t)h[C_EXCL];
+    h_sizes[4] = (int64_t)h[C_POOR];
+    h_sizes[5] = (int64_t)h[C_WEIGHT];
+    std::lock_guard<std::mutex> g(g_mu);
+    g_states[d_ws] = st;
+    return B3C_OK;
+}
+
+int b3c_accum_emit_csr(void *d_ws, int symmetric, int64_t *d_indptr, int32_t *d_indices, uint32_t *d_counts,
+                       void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    B3C_REQUIRE(st.reduced, "call b3c_accum_reduce before b3c_accum_emit_csr");
+    B3C_REQUIRE(d_indptr != nullptr, "null indptr");
+    const int64_t nnz_out = symmetric ? 2 * st.nnz_uo + st.nnz_diag : st.nnz_uo + st.nnz_diag;
+    B3C_REQUIRE(nnz_out == 0 || (d_indices && d_counts), "null output arrays");
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    const int64_t *ip = (const int64_t *)(ws + (symmetric ? st.o_indptr_f : st.o_indptr_u));
+    B3C_CUDA(cudaMemcpyAsync(d_indptr, ip, ((size_t)st.n_seq + 1) * 8, cudaMemcpyDeviceToDevice, s));
+    k_emit<<<kNumSMs * 8, 256, 0, s>>>(symmetric ? 1 : 0, st.b, st.n_seq, (const unsigned long long *)(ws + st.o_ctr),
+                                       (const uint64_t *)(ws + st.o_uniq), (const uint32_t *)(ws + st.o_cnt),
+                                       (const uint64_t *)(ws + (st.comp_in_a ? st.o_keys_a : st.o_keys_b)),
+                                       (const uint32_t *)(ws + st.o_diag), (const int64_t *)(ws + st.o_up_ptr),
+                                       (const int64_t *)(ws + st.o_lo_ptr), ip, d_indices, d_counts);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+"""
+Device-resident stages of the contact-map hot path.
+
+Thin host-side wrappers over the C ABI (include/bin3c_b200.h).  PyTorch tensors are used
+only as device buffers and for the current CUDA stream; every operation here is a call
+into hand-written sm_100a kernels -- there is no torch arithmetic on the data path and no
+CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import lib, check
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('bin3c_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _empty(n, dtype, device=None):
+    return torch.empty(max(int(n), 0), dtype=dtype, device=device or 'cuda')
+
+
+def to_device(a, dtype=None, non_blocking=False):
+    """numpy array / torch tensor -> contiguous CUDA tensor (H2D copy when needed)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.uint64:
+            a = a.view(np.int64)
+        elif a.dtype == np.uint32:
+            a = a.view(np.int32)
+        t = torch.from_numpy(a)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to('cuda', non_blocking=non_blocking).contiguous()
+
+
+class DeviceCSR(object):
+    """CSR on the device: int64 indptr[n+1], int32 indices[nnz], data[nnz] (int32 bits of uint32 counts, or float64)."""
+
+    def __init__(self, n, indptr, indices, data, counts=False):
+        self.n = int(n)
+        self.indptr = indptr
+        self.indices = indices
+        self.data = data
+        self.counts = counts           # True: data holds uint32 counts (stored in an int32 tensor)
+
+    @property
+    def nnz(self):
+        return int(self.indices.numel())
+
+    @classmethod
+    def from_scipy(cls, m, dtype=np.float64):
+        """Canonical CSR (duplicates summed, sorted columns) of a scipy matrix, copied to the device."""
+        import scipy.sparse as sp
+        c = sp.csr_matrix(m, copy=True)
+        c.sum_duplicates()
+        c.sort_indices()
+        counts = np.dtype(dtype) == np.uint32
+        return cls(c.shape[0], to_device(c.indptr.astype(np.int64)), to_device(c.indices.astype(np.int32)),
+                   to_device(c.data.astype(dtype)), counts=counts)
+
+    def host_arrays(self):
+        indptr = self.indptr.cpu().numpy()
+        indices = self.indices.cpu().numpy()
+        data = self.data.cpu().numpy()
+        if self.counts:
+            data = data.view(np.uint32)
+        return indptr, indices, data
+
+    def to_scipy_csr(self):
+        import scipy.sparse as sp
+        indptr, indices, data = self.host_arrays()
+        return sp.csr_matrix((data, indices, indptr), shape=(self.n, self.n))
+
+    def to_scipy_coo(self):
+        import scipy.sparse as sp
+        indptr, indices, data = self.host_arrays()
+        row = np.repeat(np.arange(self.n, dtype=np.int32), np.diff(indptr))
+        return sp.coo_matrix((data, (row, indices)), shape=(self.n, self.n))
+
+
+# --------------------------------------------------------------------------------------
+# pair accumulation
+# --------------------------------------------------------------------------------------
+
+class Accumulator(object):
+    """
+    Device accumulator for packed pair records (include/bin3c_b200.h, "Pair accumulation").
+    Usage: add(records) any number of times, then finish().
+    """
+
+    def __init__(self, n_seq, tid2idx, pair_capacity):
+        require_cuda()
+        self.n_seq = int(n_seq)
+        self.tid2idx = to_device(tid2idx, torch.int32)
+        self.n_refs = int(self.tid2idx.numel())
+        self.capacity = int(pair_capacity)
+        nbytes = lib.b3c_accum_workspace_bytes(self.capacity, self.n_seq, self.n_refs)
+        if nbytes < 0:
+            raise AssertionError('invalid accumulator sizes')
+        self.ws = _empty(nbytes, torch.uint8)
+        self.begin()
+
+    def begin(self):
+        check(lib.b3c_accum_begin(_ptr(self.ws), self.ws.numel(), self.capacity, self.n_seq,
+                                  _ptr(self.tid2idx), self.n_refs, _stream()))
+        self.info = None
+
+    def add(self, records):
+        """records: CUDA int64/uint64-bit tensor of packed pair records (16-byte aligned)."""
+        assert records.is_cuda and records.element_size() == 8 and records.is_contiguous()
+        check(lib.b3c_accum_add_pairs(_ptr(self.ws), _ptr(records), records.numel(), _stream()))
+
+    def finish(self, symmetric=True):
+        """Sort-reduce and emit the canonical CSR.  Returns (DeviceCSR[uint32 counts], info dict)."""
+        sizes = (C.c_int64 * 8)()
+        check(lib.b3c_accum_reduce(_ptr(self.ws), sizes, _stream()))
+        nnz = int(sizes[1] if symmetric else sizes[0])
+        indptr = _empty(self.n_seq + 1, torch.int64)
+        indices = _empty(nnz, torch.int32)
+        counts = _empty(nnz, torch.int32)
+        check(lib.b3c_accum_emit_csr(_ptr(self.ws), 1 if symmetric else 0, _ptr(indptr), _ptr(indices),
+                                     _ptr(counts), _stream()))
+        self.info = dict(nnz_upper=int(sizes[0]), nnz_full=int(sizes[1]), accepted=int(sizes[2]),
+                         ref_excluded=int(sizes[3]), poor_match=int(sizes[4]), map_weight=int(sizes[5]))
+        return DeviceCSR(self.n_seq, indptr, indices, counts, counts=True), self.info
+
+
+# --------------------------------------------------------------------------------------
+# mask + normalisation
+# --------------------------------------------------------------------------------------
+
+def max_offdiag(csr):
+    out = _empty(csr.n, csr.data.dtype)
+    fn = lib.b3c_max_offdiag_u32 if csr.counts else lib.b3c_max_offdiag_f64
+    if not csr.counts:
+        assert csr.data.dtype == torch.float64
+    check(fn(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(out), _stream()))
+    return out
+
+
+def acceptance_mask(lengths, signal, min_len, min_sig):
+    n = int(lengths.numel())
+    mask = _empty(n, torch.uint8)
+    check(lib.b3c_acceptance_mask(n, _ptr(lengths), _ptr(signal), int(min_len), int(min_sig), _ptr(mask), _stream()))
+    return mask
+
+
+def site_norm(csr, sites):
+    """counts (uint32) or float64 matrix -> float64 matrix scaled by 1/(s_i*s_j); float input is scaled in place."""
+    if csr.counts:
+        out = _empty(csr.nnz, torch.float64)
+        check(lib.b3c_site_norm(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites), _ptr(out),
+                                _stream()))
+        return DeviceCSR(csr.n, csr.indptr, csr.indices, out)
+    check(lib.b3c_site_norm_f64(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites), _stream()))
+    return csr
+
+
+# --------------------------------------------------------------------------------------
+# Knight-Ruiz
+# --------------------------------------------------------------------------------------
+
+_KR_WS = {}
+
+
+def _kr_workspace(n, nnz):
+    nbytes = lib.b3c_kr_workspace_bytes(n, nnz)
+    dev = torch.cuda.current_device()
+    ws = _KR_WS.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = _empty(nbytes, torch.uint8)
+        _KR_WS[dev] = ws
+    return ws
+
+
+def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000):
+    """Returns (x CUDA float64[n], info dict) for a symmetric float64 DeviceCSR."""
+    assert csr.data.dtype == torch.float64
+    ws = _kr_workspace(csr.n, csr.nnz)
+    x = _empty(csr.n, torch.float64)
+    info = (C.c_int64 * 8)()
+    rc = lib.b3c_kr_run(csr.n, csr.nnz, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), float(tol),
+                        float(delta), float(Delta), int(max_iter), 0, _ptr(x), _ptr(ws), ws.numel(), info, _stream())
+    out = dict(n_iter=int(info[0]), zero_diag=int(info[1]), outer=int(info[2]), n_spmv=int(info[3]))
+    check(rc)
+    return x, out
+
+
+def kr_apply(csr, x):
+    """diag(x) . A . diag(x) entry-wise (sparse_utils.py:223-224)."""
+    out = _empty(csr.nnz, torch.float64)
+    check(lib.b3c_kr_scale(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(x), _ptr(out), _stream()))
+    return DeviceCSR(csr.n, csr.indptr, csr.indices, out)
+
+
+def asymmetry_count(csr, tol):
+    scratch = _empty(1, torch.int64)
+    cnt = (C.c_int64 * 1)()
+    check(lib.b3c_asymmetry_count(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), float(tol),
+                                  _ptr(scratch), cnt, _stream()))
+    return int(cnt[0])
+
+
+def spmv(csr, u, y=None, ws=None, prepared=False):
+    """y = A.u with KR's SpMV kernels.  Pass the same ws with prepared=True to reuse the tile plan."""
+    if ws is None:
+        ws = _kr_workspace(csr.n, csr.nnz)
+    if y is None:
+        y = _empty(csr.n, torch.float64)
+    check(lib.b3c_spmv(csr.n, csr.nnz, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(u), _ptr(y),
+                       _ptr(ws), ws.numel(), 1 if prepared else 0, _stream()))
+    return y
+
+
+# --------------------------------------------------------------------------------------
+# compress + edge weighting
+# --------------------------------------------------------------------------------------
+
+def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True):
+    """
+    Drop rejected contigs and produce the compressed matrix and/or the weighted edge list.
+    Returns dict(n_accepted, sub=DeviceCSR|None, u, v, w, scl) with CUDA tensors.
+    """
+    assert csr.data.dtype == torch.float64
+    n = csr.n
+    nbytes = lib.b3c_compress_workspace_bytes(n)
+    ws = _empty(nbytes, torch.uint8)
+    newidx = _empty(n, torch.int32)
+    h = (C.c_int64 * 4)()
+    check(lib.b3c_compress_count(n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask), _ptr(newidx),
+                                 _ptr(ws), ws.numel(), h, _stream()))
+    n_acc, n_kept, n_edges = int(h[0]), int(h[1]), int(h[2])
+    sub_indptr = sub_indices = sub_data = eu = ev = ew = None
+    if want_sub:
+        sub_indptr = _empty(n_acc + 1, torch.int64)
+        sub_indices = _empty(n_kept, torch.int32)
+        sub_data = _empty(n_kept, torch.float64)
+    if want_edges:
+        eu = _empty(n_edges, torch.int32)
+        ev = _empty(n_edges, torch.int32)
+        ew = _empty(n_edges, torch.float64)
+    scl = _empty(1, torch.float64)
+    check(lib.b3c_compress_fill(n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask), _ptr(newidx),
+                                _ptr(ws), 1 if scale else 0, _ptr(sub_indptr), _ptr(sub_indices), _ptr(sub_data),
+                                _ptr(eu), _ptr(ev), _ptr(ew), _ptr(scl), _stream()))
+    sub = DeviceCSR(n_acc, sub_indptr, sub_indices, sub_data) if want_sub else None
+    return dict(n_accepted=n_acc, n_kept=n_kept, n_edges=n_edges, sub=sub, u=eu, v=ev, w=ew, scl=scl, newidx=newidx)
+
+
+def launch_count():
+    return _cabi.launch_count()

@@ -1,0 +1,18 @@
+"""The exception types the hot path can raise, named as in the reference's mzd/exceptions.py."""
+
+
+class ApplicationException(Exception):
+    def __init__(self, message):
+        super(ApplicationException, self).__init__(message)
+
+
+class NoneAcceptedException(ApplicationException):
+    """All sequences were excluded during filtering (raised at contact_map.py:926-927)"""
+    def __init__(self):
+        super(NoneAcceptedException, self).__init__('all sequences were excluded')
+
+
+class ParsingError(ApplicationException):
+    """An error during input parsing (raised at contact_map.py:571-573)"""
+    def __init__(self, msg):
+        super(ParsingError, self).__init__(msg)

@@ -1,0 +1,157 @@
+/*
+ * bin3c_b200 -- C ABI of the B200-native bin3C contact-map hot path.
+ *
+ * The reference (cerebis/bin3C @ 76ad2a9) is pure Python and has no FFI layer; the
+ * functions below are what a ctypes binding inside mzd/sparse_utils.py and
+ * mzd/contact_map.py would call in place of the cited Python code (see INTEGRATION.md
+ * for that binding).  Every entry point takes plain pointers and sizes.
+ *
+ * Conventions
+ *   - Pointers named d_* are DEVICE pointers (e.g. torch.Tensor.data_ptr()); h_* are host
+ *     pointers.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - All functions return 0 on success or a negative b3c_status; b3c_last_error()
+ *     returns a thread-local message for the last failure.
+ *   - No function allocates device memory: callers supply outputs and a workspace whose
+ *     size comes from the matching *_workspace_bytes() query.  Entry points that hand a
+ *     size back to the host (b3c_accum_reduce, b3c_kr_run, b3c_compress_count)
+ *     synchronise the stream; the rest only enqueue work.
+ *   - Sparse matrices are CSR: int64 indptr[n+1], int32 indices[nnz], values.
+ *
+ * Packed pair record (uint64, little endian) -- the input of the path, one per usable
+ * read pair of the name-sorted BAM (contact_map.py:720-731):
+ *     bits  0..30  BAM reference id of mate 1      (r1.reference_id)
+ *     bit   31     pass flag: both mates satisfy the matcher (contact_map.py:612-622,737)
+ *     bits 32..62  BAM reference id of mate 2      (r2.reference_id)
+ *     bit   63     reserved, must be 0
+ */
+#ifndef BIN3C_B200_H
+#define BIN3C_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B3C_OK = 0,
+    B3C_ERR_ARG = -1,        /* bad argument (AssertionError in the reference)          */
+    B3C_ERR_CUDA = -2,       /* CUDA runtime failure                                    */
+    B3C_ERR_CAPACITY = -3,   /* caller-supplied buffer or workspace too small           */
+    B3C_ERR_NOCONV = -4,     /* KR: n_iter > max_iter (RuntimeError, sparse_utils.py:213) */
+    B3C_ERR_NAN = -5,        /* KR: scale vector developed NaNs (sparse_utils.py:192)   */
+    B3C_ERR_TIE = -6         /* KR: max(ynew) == Delta exactly (ValueError, Q13, sparse_utils.py:179-181) */
+} b3c_status;
+
+int b3c_version(void);
+const char *b3c_last_error(void);
+/* number of kernels this library has launched in the calling process (bench "gpu_launches") */
+int64_t b3c_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Pair accumulation.  Replaces the per-pair loop of ContactMap._bin_map
+ * (contact_map.py:720-798), ContactMap.make_reverse_index (contact_map.py:818-832, as the
+ * dense table d_tid2idx) and Sparse2DAccumulator + get_coo (sparse_utils.py:227-266).
+ *
+ *   begin      zero the accumulator state held in the workspace
+ *   add_pairs  classify a chunk of packed records: reference-exclusion test, then the
+ *              matcher bit (filter order Q12), canonicalise i<=j, count diagonal pairs
+ *              directly and append off-diagonal keys (i<<32|j).  May be called many
+ *              times (streaming chunks, overlapping H2D copies).
+ *   reduce     radix sort the keys + run-length reduce; returns sizes to the host:
+ *              h_sizes[0] = nnz of the upper triangle incl. diagonal
+ *              h_sizes[1] = nnz of the full symmetric matrix
+ *              h_sizes[2..4] = accepted, ref_excluded, poor_match (contact_map.py:709-716)
+ *              h_sizes[5] = map weight = sum of the symmetric matrix (contact_map.py:834-838)
+ *   emit       write the canonical CSR (sorted columns, exact uint32 counts):
+ *              symmetric != 0 -> full symmetric matrix as get_coo(symm=True) returns it
+ *              (diagonal once, off-diagonals mirrored, Q7); else the upper triangle.
+ * ------------------------------------------------------------------------------------ */
+int64_t b3c_accum_workspace_bytes(int64_t pair_capacity, int32_t n_seq, int32_t n_refs);
+int b3c_accum_begin(void *d_ws, int64_t ws_bytes, int64_t pair_capacity, int32_t n_seq,
+                    const int32_t *d_tid2idx, int32_t n_refs, void *stream);
+int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records, void *stream);
+int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream);
+int b3c_accum_emit_csr(void *d_ws, int symmetric, int64_t *d_indptr, int32_t *d_indices,
+                       uint32_t *d_counts, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Filter mask.  max_offdiag (sparse_utils.py:269-281) and the two threshold tests of
+ * ContactMap.set_primary_acceptance_mask (contact_map.py:888-905).
+ * d_signal (uint32[n]) and d_mask (uint8[n]) are outputs; either may be NULL.
+ * ------------------------------------------------------------------------------------ */
+int b3c_max_offdiag_u32(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
+                        const uint32_t *d_counts, uint32_t *d_signal, void *stream);
+int b3c_max_offdiag_f64(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
+                        const double *d_data, double *d_signal, void *stream);
+int b3c_acceptance_mask(int32_t n, const int32_t *d_lengths, const uint32_t *d_signal,
+                        int64_t min_len, int64_t min_sig, uint8_t *d_mask, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Site normalisation.  ContactMap._get_sites + fast_norm_fullseq_bysite
+ * (contact_map.py:1103-1108, 100-113): out[e] = count[e] * (1.0 / (s_i * s_j)), zero sites
+ * counted as one (Q6).  d_sites is the raw int32 site count per contig.
+ * ------------------------------------------------------------------------------------ */
+int b3c_site_norm(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
+                  const uint32_t *d_counts, const int32_t *d_sites, double *d_out, void *stream);
+/* same on an already-float matrix, in place (ContactMap._norm_seq called on a float map) */
+int b3c_site_norm_f64(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
+                      double *d_data, const int32_t *d_sites, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Knight-Ruiz balancing.  kr_biostochastic (sparse_utils.py:90-224).
+ *
+ *   b3c_kr_run    computes the scale vector x (float64[n]) of the symmetric CSR matrix;
+ *                 zero diagonals are treated as one on the working matrix only (Q2).
+ *                 h_info[0] = n_iter, [1] = zero diagonals patched, [2] = outer Newton
+ *                 steps, [3] = number of SpMV launches/phases executed.
+ *                 mode 0 = one persistent cooperative kernel (device-side control flow).
+ *   b3c_kr_scale  out[e] = x_i * (a_ij * x_j), the entries of X.T.dot(orig.dot(X))
+ *                 (sparse_utils.py:223-224, Q9) on the ORIGINAL matrix.
+ *   b3c_spmv      y = A.u with the same kernel KR uses (microbench, config C5).
+ * ------------------------------------------------------------------------------------ */
+int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz);
+int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices,
+               const double *d_data, double tol, double delta, double Delta, int32_t max_iter,
+               int32_t mode, double *d_x, void *d_ws, int64_t ws_bytes, int64_t *h_info,
+               void *stream);
+int b3c_kr_scale(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
+                 const double *d_data, const double *d_x, double *d_out, void *stream);
+/* is_hermitian (sparse_utils.py:10-18) without the dense N x N temporary (Q11): counts the
+ * entries with |a_ij - a_ji| >= tol (a missing mirror entry counts as zero).  Columns must be
+ * sorted within rows.  h_count[0] receives the count (the stream is synchronised). */
+int b3c_asymmetry_count(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
+                        const double *d_data, double tol, uint64_t *d_scratch, int64_t *h_count,
+                        void *stream);
+int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices,
+             const double *d_data, const double *d_u, double *d_y, void *d_ws, int64_t ws_bytes,
+             int32_t prepared, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Compress + edge weighting.  compress (sparse_utils.py:284-314), get_subspace
+ * (contact_map.py:966-982) and the edge loop of to_graph (cluster.py:314-321).
+ *
+ *   count   d_newidx[i] = index of contig i among the accepted ones (or -1);
+ *           h_out[0] = accepted contigs, [1] = nnz kept, [2] = undirected edges (u<=v kept
+ *           entries, self-loops included, Q8)
+ *   fill    compressed CSR of the kept entries (sub_* may be NULL) and/or the edge list
+ *           (u, v, w) with w = value * scl, scl = 1/max over the kept entries incl. the
+ *           diagonal when scale != 0 (Q8); one value per undirected edge, taken from the
+ *           upper-triangle entry (Q9).  d_scl receives scl (float64[1]).
+ * ------------------------------------------------------------------------------------ */
+int64_t b3c_compress_workspace_bytes(int32_t n);
+int b3c_compress_count(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
+                       const double *d_data, const uint8_t *d_mask, int32_t *d_newidx, void *d_ws,
+                       int64_t ws_bytes, int64_t *h_out, void *stream);
+int b3c_compress_fill(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
+                      const double *d_data, const uint8_t *d_mask, const int32_t *d_newidx,
+                      void *d_ws, int scale,
+                      int64_t *d_sub_indptr, int32_t *d_sub_indices, double *d_sub_data,
+                      int32_t *d_edge_u, int32_t *d_edge_v, double *d_edge_w, double *d_scl,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIN3C_B200_H */

@@ -1,0 +1,404 @@
+"""
+GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the golden vectors
+produced by the reference's own functions and against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): contact matrix, counters and acceptance mask bit-exact;
+KR scale vector and edge weights within 1e-9 max relative error, identical iteration count.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import golden_lut
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9          # north_star tolerance for KR scale vector and edge weights
+
+
+@pytest.fixture(scope='module')
+def dev():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from bin3c_b200 import device
+    return device
+
+
+def _accumulate(dev, records, lut, n, symmetric=True, chunks=1, capacity=None):
+    import torch
+    rec = dev.to_device(np.ascontiguousarray(records, dtype=np.uint64))
+    acc = dev.Accumulator(n, lut, capacity if capacity is not None else max(len(records), 1))
+    if len(records):
+        step = -(-len(records) // chunks)
+        step += step & 1                      # keep chunk starts 16-byte aligned
+        for lo in range(0, len(records), step):
+            acc.add(rec[lo:lo + step])
+    csr, info = acc.finish(symmetric=symmetric)
+    torch.cuda.synchronize()
+    return csr, info
+
+
+def _relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+# ---------------------------------------------------------------------------------------------
+# accumulation
+# ---------------------------------------------------------------------------------------------
+
+def test_accumulate_golden(dev, golden):
+    g = golden
+    n = len(g['lengths'])
+    csr, info = _accumulate(dev, g['records'], golden_lut(g), n)
+    coo = csr.to_scipy_coo()
+    assert coo.dtype == np.uint32
+    assert np.array_equal(coo.row, g['map_row'])
+    assert np.array_equal(coo.col, g['map_col'])
+    assert np.array_equal(coo.data, g['map_data'])
+    assert [info['accepted'], info['ref_excluded'], info['poor_match']] == g['counts'].tolist()
+    assert info['map_weight'] == int(g['map_weight'])
+
+
+def test_accumulate_chunked_and_upper(dev, golden):
+    from oracle import oracle
+    from bin3c_b200 import synth
+    g = golden
+    n = len(g['lengths'])
+    ti, tj, ok = synth.unpack_pairs(g['records'])
+    up, counts = oracle.bin_pairs_fast(ti, tj, ok, golden_lut(g), n)
+    up = up.tocsr()
+    up.sort_indices()
+    csr, info = _accumulate(dev, g['records'], golden_lut(g), n, symmetric=False, chunks=3)
+    got = csr.to_scipy_csr()
+    assert np.array_equal(got.indptr, up.indptr)
+    assert np.array_equal(got.indices, up.indices)
+    assert np.array_equal(got.data, up.data)
+    assert info['nnz_upper'] == up.nnz
+
+
+def _oracle_full(records, lut, n):
+    from oracle import oracle
+    from bin3c_b200 import synth
+    ti, tj, ok = synth.unpack_pairs(records)
+    up, counts = oracle.bin_pairs_fast(ti, tj, ok, lut, n)
+    return oracle.symmetrise(up), counts
+
+
+@pytest.mark.parametrize('case', ['empty', 'all_excluded', 'all_poor', 'all_diag', 'single', 'one_cell'])
+def test_accumulate_edge_cases(dev, case):
+    from bin3c_b200 import synth
+    n, n_refs = 37, 45
+    lut = np.full(n_refs, -1, dtype=np.int32)
+    keep = np.sort(np.random.default_rng(5).choice(n_refs, n, replace=False))
+    lut[keep] = np.arange(n, dtype=np.int32)
+    excl = np.setdiff1d(np.arange(n_refs), keep)
+    rng = np.random.default_rng(7)
+    if case == 'empty':
+        rec = np.zeros(0, dtype=np.uint64)
+    elif case == 'all_excluded':
+        rec = synth.pack_pairs(rng.choice(excl, 999), rng.choice(keep, 999), np.ones(999, bool))
+    elif case == 'all_poor':
+        rec = synth.pack_pairs(rng.choice(keep, 1001), rng.choice(keep, 1001), np.zeros(1001, bool))
+    elif case == 'all_diag':
+        a = rng.choice(keep, 5000)
+        rec = synth.pack_pairs(a, a, np.ones(5000, bool))
+    elif case == 'single':
+        rec = synth.pack_pairs([keep[3]], [keep[1]], [True])
+    else:
+        rec = synth.pack_pairs(np.full(70000, keep[2]), np.full(70000, keep[30]), np.ones(70000, bool))
+    csr, info = _accumulate(dev, rec, lut, n)
+    want, counts = _oracle_full(rec, lut, n)
+    got = csr.to_scipy_coo()
+    assert np.array_equal(got.row, want.row) and np.array_equal(got.col, want.col)
+    assert np.array_equal(got.data, want.data)
+    assert {k: info[k] for k in counts} == counts
+
+
+@pytest.mark.parametrize('n,n_refs,p,rank_lut', [
+    (1000, 1200, 200_000, True),          # shared-memory diagonal + rank table
+    (1000, 1200, 200_000, False),         # arbitrary tid->index map: gather fallback
+    (70_000, 80_000, 400_000, True),      # 17-bit indices: global diagonal, 64-bit staging
+    (70_000, 80_000, 400_000, False),
+    (300_000, 2_400_000, 300_000, True),  # rank table too large for shared memory
+    (257, 257, 50_001, True),             # odd sizes, no excluded refs
+])
+def test_accumulate_random(dev, n, n_refs, p, rank_lut):
+    from bin3c_b200 import synth
+    rng = np.random.default_rng(n + p + int(rank_lut))
+    keep = np.sort(rng.choice(n_refs, n, replace=False))
+    lut = np.full(n_refs, -1, dtype=np.int32)
+    lut[keep] = np.arange(n, dtype=np.int32) if rank_lut else rng.permutation(n).astype(np.int32)
+    # heavy duplicates + a tid beyond the table (must count as excluded)
+    a = rng.integers(0, n_refs, p)
+    b = np.where(rng.random(p) < 0.6, a, rng.integers(0, min(n_refs, 3000), p))
+    a[:5] = n_refs + 11
+    rec = synth.pack_pairs(a, b, rng.random(p) < 0.9)
+    csr, info = _accumulate(dev, rec, lut, n, chunks=2)
+    want, counts = _oracle_full(rec, lut, n)
+    got = csr.to_scipy_coo()
+    assert got.nnz == want.nnz
+    assert np.array_equal(got.row, want.row) and np.array_equal(got.col, want.col)
+    assert np.array_equal(got.data, want.data)
+    assert {k: info[k] for k in counts} == counts
+    assert info['map_weight'] == int(want.sum(dtype=np.uint64))
+
+
+def test_accumulate_capacity_error(dev):
+    from bin3c_b200 import synth
+    from bin3c_b200._cabi import B3CError
+    lut = np.arange(64, dtype=np.int32)
+    rng = np.random.default_rng(3)
+    rec = synth.pack_pairs(rng.integers(0, 64, 10000), rng.integers(0, 64, 10000), np.ones(10000, bool))
+    with pytest.raises(B3CError):
+        _accumulate(dev, rec, lut, 64, capacity=100)
+
+
+# ---------------------------------------------------------------------------------------------
+# mask, normalisation
+# ---------------------------------------------------------------------------------------------
+
+def _golden_map_dev(dev, g):
+    n = len(g['lengths'])
+    m = sp.coo_matrix((g['map_data'], (g['map_row'], g['map_col'])), shape=(n, n), dtype=np.uint32)
+    return dev.DeviceCSR.from_scipy(m, np.uint32), m
+
+
+def test_mask_golden(dev, golden):
+    import torch
+    g = golden
+    csr, _ = _golden_map_dev(dev, g)
+    sig = dev.max_offdiag(csr)
+    assert np.array_equal(sig.cpu().numpy().view(np.uint32), g['signal'])
+    mask = dev.acceptance_mask(dev.to_device(g['lengths'], torch.int32), sig, int(g['min_len']), int(g['min_sig']))
+    assert np.array_equal(mask.cpu().numpy().astype(bool), g['mask'])
+
+
+def test_site_norm_exact(dev, golden):
+    import torch
+    from oracle import oracle
+    g = golden
+    csr, m = _golden_map_dev(dev, g)
+    sites = g['sites'].copy()
+    sites[::7] = 0                                  # exercise the zero -> one rule (Q6)
+    out = dev.site_norm(csr, dev.to_device(sites, torch.int32))
+    want = oracle.norm_by_sites(m.row, m.col, m.data.astype(np.float64), oracle.get_sites(sites))
+    assert np.array_equal(out.data.cpu().numpy(), want)       # same operations, same rounding
+
+
+# ---------------------------------------------------------------------------------------------
+# Knight-Ruiz
+# ---------------------------------------------------------------------------------------------
+
+def _normed_dev(dev, g):
+    import torch
+    csr, _ = _golden_map_dev(dev, g)
+    return dev.site_norm(csr, dev.to_device(g['sites'], torch.int32))
+
+
+def test_kr_golden(dev, golden):
+    g = golden
+    a = _normed_dev(dev, g)
+    x, info = dev.kr_scale_vector(a)
+    assert info['n_iter'] == int(g['kr_n_iter'])
+    assert info['zero_diag'] == int(g['kr_zero_diag'])
+    assert _relerr(x.cpu().numpy(), g['kr_x']) <= REL_TOL
+    bal = dev.kr_apply(a, x).to_scipy_csr()
+    assert np.array_equal(bal.indptr, g['bal_indptr']) and np.array_equal(bal.indices, g['bal_indices'])
+    assert _relerr(bal.data, g['bal_data']) <= REL_TOL
+
+
+def test_kr_deterministic(dev):
+    from conftest import load_golden
+    g = load_golden('c1mini')
+    a = _normed_dev(dev, g)
+    x1, _ = dev.kr_scale_vector(a)
+    x2, _ = dev.kr_scale_vector(a)
+    assert np.array_equal(x1.cpu().numpy(), x2.cpu().numpy())
+
+
+@pytest.mark.parametrize('n,density,seed', [(3000, 0.01, 1), (20000, 0.002, 2), (1500, 0.2, 3), (5, 0.9, 4)])
+def test_kr_random_vs_oracle(dev, n, density, seed):
+    from oracle import oracle
+    rng = np.random.default_rng(seed)
+    up = sp.random(n, n, density=density, random_state=rng, data_rvs=lambda k: rng.uniform(0.1, 5.0, k))
+    up = sp.triu(up, k=1)
+    d = rng.uniform(0.5, 2.0, n)
+    d[rng.random(n) < 0.1] = 0.0                      # zero diagonals (Q2)
+    m = (up + up.T + sp.diags(d)).tocsr()
+    m.eliminate_zeros()
+    res = oracle.kr_scale_vector(m)
+    x, info = dev.kr_scale_vector(dev.DeviceCSR.from_scipy(m))
+    assert info['n_iter'] == res.n_iter
+    assert info['zero_diag'] == res.n_zero_diag
+    assert _relerr(x.cpu().numpy(), res.x) <= REL_TOL
+
+
+def test_kr_long_rows_and_empty_rows(dev):
+    """Rows far longer than an SpMV tile, rows straddling tiles, and completely empty rows (Q3)."""
+    from oracle import oracle
+    rng = np.random.default_rng(9)
+    n = 9000
+    rows = [np.full(7000, 0), np.full(5000, 1), rng.integers(2, n // 2, 60000)]
+    cols = [rng.choice(n // 2, 7000, replace=False), rng.choice(n // 2, 5000, replace=False),
+            rng.integers(2, n // 2, 60000)]
+    r = np.concatenate(rows)
+    c = np.concatenate(cols)
+    up = sp.coo_matrix((rng.uniform(0.2, 3.0, len(r)), (np.minimum(r, c), np.maximum(r, c))), shape=(n, n)).tocsr()
+    up = sp.triu(up, k=1)
+    m = (up + up.T + sp.diags(np.r_[rng.uniform(1, 2, n // 2), np.zeros(n - n // 2)])).tocsr()
+    m.eliminate_zeros()
+    assert (np.diff(m.indptr) == 0).sum() > 1000 and np.diff(m.indptr).max() > 4096
+    res = oracle.kr_scale_vector(m)
+    x, info = dev.kr_scale_vector(dev.DeviceCSR.from_scipy(m))
+    assert info['n_iter'] == res.n_iter
+    assert _relerr(x.cpu().numpy(), res.x) <= REL_TOL
+
+
+@pytest.mark.parametrize('n,nnz_row', [(1, 1), (100, 1), (5000, 3), (4097, 40), (3000, 900)])
+def test_spmv_vs_scipy(dev, n, nnz_row):
+    rng = np.random.default_rng(n)
+    m = sp.random(n, n, density=min(1.0, nnz_row / n), random_state=rng, format='csr')
+    m.sort_indices()
+    u = rng.standard_normal(n)
+    y = dev.spmv(dev.DeviceCSR.from_scipy(m), dev.to_device(u)).cpu().numpy()
+    want = m.dot(u)
+    assert np.max(np.abs(y - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+
+
+# ---------------------------------------------------------------------------------------------
+# compress + edges, whole path
+# ---------------------------------------------------------------------------------------------
+
+def test_compress_edges_golden(dev, golden):
+    import torch
+    from oracle import oracle
+    g = golden
+    n = len(g['lengths'])
+    bal = sp.csr_matrix((g['bal_data'], g['bal_indices'], g['bal_indptr']), shape=(n, n))
+    res = dev.compress_edges(dev.DeviceCSR.from_scipy(bal), dev.to_device(g['mask'].astype(np.uint8), torch.uint8))
+    assert res['n_accepted'] == int(g['sub_n']) and res['n_kept'] == int(g['sub_nnz'])
+    want = oracle.compress(bal.tocoo(), g['mask']).tocsr()
+    want.sort_indices()
+    got = res['sub'].to_scipy_csr()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert np.array_equal(got.data, want.data)
+    assert float(res['scl'].cpu()[0]) == float(g['scl'])
+    assert np.array_equal(res['u'].cpu().numpy(), g['edge_u'])
+    assert np.array_equal(res['v'].cpu().numpy(), g['edge_v'])
+    assert _relerr(res['w'].cpu().numpy(), g['edge_w']) <= REL_TOL
+
+
+def _contact_map(g):
+    from bin3c_b200.contact_map import ContactMap, PairRecords
+    lengths = np.full(int(g['n_refs']), 500, dtype=np.int64)
+    sites = np.ones(int(g['n_refs']), dtype=np.int64)
+    lengths[g['ref_index']] = g['lengths']
+    sites[g['ref_index']] = g['sites']
+    pr = PairRecords(lengths, sites, g['records'])
+    return ContactMap(pr, ['synthetic'], None, None, min_mapq=60, min_len=int(g['min_len']),
+                      min_sig=int(g['min_sig']), random_seed=1)
+
+
+def test_contact_map_end_to_end(dev, golden):
+    import pickle
+    from bin3c_b200 import cluster
+    g = golden
+    # the golden cases use min_len thresholds at or above the 1000 bp floor of their contigs
+    if int(g['min_len']) > 1000:
+        pytest.skip('constructor-level length filter changes N for this case')
+    cm = _contact_map(g)
+    assert cm.total_seq == len(g['lengths'])
+    assert [cm.pair_counts[k] for k in ('accepted', 'ref_excluded', 'poor_match')] == g['counts'].tolist()
+    assert cm.map_weight() == int(g['map_weight'])
+    assert np.array_equal(cm.get_primary_acceptance_mask(), g['mask'])
+    sm = cm.seq_map
+    assert sp.isspmatrix_coo(sm) and sm.dtype == np.uint32
+    assert np.array_equal(sm.row, g['map_row']) and np.array_equal(sm.col, g['map_col'])
+    assert np.array_equal(sm.data, g['map_data'])
+
+    u, v, w, scl = cluster.to_edges(cm, norm=True, bisto=True, scale=True)
+    assert cm.kr_info['n_iter'] == int(g['kr_n_iter'])
+    assert _relerr(cm.bisto_scale, g['kr_x']) <= REL_TOL
+    assert np.array_equal(u, g['edge_u']) and np.array_equal(v, g['edge_v'])
+    assert _relerr(w, g['edge_w']) <= REL_TOL
+    assert abs(scl - float(g['scl'])) <= REL_TOL * float(g['scl'])
+
+    sub = cm.get_subspace(marginalise=True, flatten=False)
+    assert sp.isspmatrix_coo(sub) and sub.shape == (int(g['sub_n']),) * 2 and sub.nnz == int(g['sub_nnz'])
+
+    gph = cluster.to_graph(cm, norm=True, bisto=True, scale=True)
+    assert gph.number_of_edges() == len(g['edge_u'])
+
+    # the whole object pickles with host containers only (bin3C.py:165)
+    cm2 = pickle.loads(pickle.dumps(cm))
+    assert cm2._dev == {} and np.array_equal(cm2.seq_map.data, g['map_data'])
+    assert _relerr(cm2.processed_map.tocsr().data, g['bal_data']) <= REL_TOL
+
+
+def test_none_accepted(dev):
+    from conftest import load_golden
+    from bin3c_b200.exceptions import NoneAcceptedException
+    g = load_golden('dups')
+    g['min_sig'] = np.int64(10 ** 9)
+    cm = _contact_map(g)
+    assert cm.get_primary_acceptance_mask().sum() == 0
+    with pytest.raises(NoneAcceptedException):
+        cm.prepare_seq_map(norm=True, bisto=True)
+
+
+def test_sparse_utils_dropin(dev, golden):
+    from bin3c_b200 import sparse_utils as su
+    from oracle import oracle
+    g = golden
+    n = len(g['lengths'])
+    m = sp.coo_matrix((g['map_data'], (g['map_row'], g['map_col'])), shape=(n, n), dtype=np.uint32)
+    assert np.array_equal(su.max_offdiag(m), g['signal'])
+    s = oracle.get_sites(g['sites'])
+    fm = sp.coo_matrix((oracle.norm_by_sites(m.row, m.col, m.data.astype(float), s), (m.row, m.col)), shape=m.shape)
+    assert su.is_hermitian(fm)
+    bal, x = su.kr_biostochastic(fm)
+    assert su.kr_biostochastic.last_info['n_iter'] == int(g['kr_n_iter'])
+    assert _relerr(x, g['kr_x']) <= REL_TOL
+    sub = su.compress(bal, g['mask'])
+    assert sp.isspmatrix_coo(sub) and sub.shape[0] == int(g['sub_n']) and sub.nnz == int(g['sub_nnz'])
+    # the per-pair protocol and the bulk entry agree
+    acc = su.Sparse2DAccumulator(n, tid2idx=golden_lut(g))
+    acc.add_pairs(records=g['records'])
+    coo = acc.get_coo()
+    assert np.array_equal(coo.row, g['map_row']) and np.array_equal(coo.data, g['map_data'])
+    acc2 = su.Sparse2DAccumulator(4)
+    acc2[0, 1] += 3
+    acc2[2, 2] += 1
+    assert acc2[0, 1] == 3 and acc2[1, 0] == 0
+    assert np.array_equal(acc2.get_coo().toarray(), np.array([[0, 3, 0, 0], [3, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 0]]))
+    asym = sp.csr_matrix(np.array([[1.0, 2.0], [2.5, 1.0]]))
+    assert not su.is_hermitian(asym)
+
+
+def test_medium_config_properties(dev):
+    """A mid-size community (N=20k, P=4M): exact counts vs the vectorised oracle, KR bistochastic."""
+    import torch
+    from bin3c_b200 import synth
+    from oracle import oracle
+    com = synth.make_community(n_genomes=40, n_contigs=20_000, n_pairs=4_000_000, seed=77)
+    lut = com.tid2idx()
+    csr, info = _accumulate(dev, com.records, lut, com.n_contigs, chunks=4)
+    want, counts = _oracle_full(com.records, lut, com.n_contigs)
+    got = csr.to_scipy_coo()
+    assert np.array_equal(got.row, want.row) and np.array_equal(got.col, want.col)
+    assert np.array_equal(got.data, want.data)
+    assert {k: info[k] for k in counts} == counts
+    normed = dev.site_norm(csr, dev.to_device(com.sites, torch.int32))
+    x, kinfo = dev.kr_scale_vector(normed)
+    a = normed.to_scipy_csr()
+    work = a + sp.diags((a.diagonal() == 0).astype(float))
+    xx = x.cpu().numpy()
+    assert np.max(np.abs(xx * work.dot(xx) - 1)) < 1e-5
+    res = oracle.kr_scale_vector(a)
+    assert kinfo['n_iter'] == res.n_iter
+    assert _relerr(xx, res.x) <= REL_TOL
