@@ -262,32 +262,11 @@ class ContactMap(object):
         lut[np.fromiter(idx.keys(), dtype=np.int64, count=len(idx))] = \
             np.fromiter(idx.values(), dtype=np.int32, count=len(idx))
 
-        records = bam.records
-        n_rec = int(records.numel()) if isinstance(records, torch.Tensor) else len(records)
-        acc = dev.Accumulator(self.total_seq, lut, max(n_rec, 1))
-
-        if isinstance(records, torch.Tensor) and records.is_cuda:
-            acc.add(records)
-        else:
-            host = records if isinstance(records, torch.Tensor) else \
-                torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint64).view(np.int64))
-            main = torch.cuda.current_stream()
-            copy_stream = torch.cuda.Stream()
-            copy_stream.wait_stream(main)
-            pending = []
-            for lo in range(0, n_rec, chunk_records):
-                hi = min(lo + chunk_records, n_rec)
-                with torch.cuda.stream(copy_stream):
-                    d = host[lo:hi].to('cuda', non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                main.wait_event(ev)
-                d.record_stream(main)
-                acc.add(d)
-                pending.append(d)
-            del pending
-
-        csr, info = acc.finish(symmetric=True)
+        from .pipeline import HotPath
+        hp = HotPath(lut, self.order.lengths(), np.array([si.sites for si in self.seq_info], dtype=np.int32),
+                     min_len=self.min_len or 1, min_sig=self.min_sig or 1)
+        csr = hp.accumulate(bam.records, chunk_records=chunk_records)
+        info = hp.acc_info
         self._host['seq_map'] = None
         self._dev['seq_map'] = csr
         counts['accepted'] = info['accepted']

@@ -75,7 +75,7 @@ static void layout(AccumState &st) {
     st.o_uniq = c.take(cap * 8);
     st.o_pos = c.take((cap + 1) * 4);
     st.o_cnt = c.take(cap * 4);
-    st.o_hist = c.take((int64_t)RS_BINS * RS_BLOCKS * 4);
+    st.o_hist = c.take(((int64_t)RS_BINS * RS_BLOCKS + RS_BINS) * 4);
     st.o_heads = c.take((RS_BLOCKS + 2) * 8 * 2);
     st.o_up_ptr = c.take(n1 * 8);
     st.o_lo_ptr = c.take(n1 * 8);
@@ -206,25 +206,37 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
         }
     };
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // two 128-bit streaming loads per thread; the next tile's loads are issued before the current
+    // tile is processed, so their latency hides behind the classification work
+    auto load_tile = [&](int64_t tile, uint4 (&v)[CLS_RPT / 2]) -> unsigned {
         const int64_t base = tile * CLS_TILE;
-        // two 128-bit streaming loads per thread, both issued before use
-        uint4 v[CLS_RPT / 2];
-        bool ok[CLS_RPT];
+        unsigned okm = 0;
 #pragma unroll
         for (int l = 0; l < CLS_RPT / 2; ++l) {
             const int64_t i = base + ((int64_t)l * CLS_THREADS + threadIdx.x) * 2;
-            ok[2 * l] = i < P.n_rec;
-            ok[2 * l + 1] = i + 1 < P.n_rec;
-            if (ok[2 * l + 1]) {
+            if (i + 1 < P.n_rec) {
                 v[l] = ld_stream_u4(P.rec + i);
-            } else if (ok[2 * l]) {
+                okm |= 3u << (2 * l);
+            } else if (i < P.n_rec) {
                 const uint2 t = ld_stream_u2(P.rec + i);
                 v[l] = make_uint4(t.x, t.y, 0u, 0u);
+                okm |= 1u << (2 * l);
             } else {
                 v[l] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
+        return okm;
+    };
+    uint4 v[CLS_RPT / 2];
+    unsigned okm = 0;
+    if ((int64_t)blockIdx.x < n_tiles) okm = load_tile(blockIdx.x, v);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint4 vn[CLS_RPT / 2];
+        unsigned okn = 0;
+        if (tile + gridDim.x < n_tiles) okn = load_tile(tile + gridDim.x, vn);
+        bool ok[CLS_RPT];
+#pragma unroll
+        for (int k = 0; k < CLS_RPT; ++k) ok[k] = (okm >> k) & 1u;
 #pragma unroll
         for (int k = 0; k < CLS_RPT; ++k) {
             const uint32_t lo = (k & 1) ? v[k >> 1].z : v[k >> 1].x;
@@ -274,10 +286,10 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
         }
         __syncthreads();
         if (threadIdx.x == 0) *s_cnt = 0;
-        // the next tile's first staging write happens after its own ballot, and every thread has
-        // passed the barrier above, so the reset is ordered by the barrier at the end of that tile;
-        // an explicit barrier keeps the reset ahead of the next tile's atomics
-        __syncthreads();
+        __syncthreads();            // the reset must precede the next tile's staging atomics
+#pragma unroll
+        for (int l = 0; l < CLS_RPT / 2; ++l) v[l] = vn[l];
+        okm = okn;
     }
 
     if (SMEM_DIAG) {
@@ -306,6 +318,14 @@ __global__ void __launch_bounds__(CLS_THREADS, 1) k_classify(ClsParams P) {
     else classify_tiles<SMEM_DIAG, false>(P, smem);
 }
 
+// an overflowed key buffer must not be sorted: drop the keys, keep the flag (reported by reduce)
+__global__ void k_accum_guard(unsigned long long *__restrict__ ctr, int64_t cap) {
+    if (ctr[C_OVERFLOW] || (int64_t)ctr[C_NKEYS] > cap) {
+        ctr[C_OVERFLOW] = 1;
+        ctr[C_NKEYS] = 0;
+    }
+}
+
 // ---- LSD radix sort --------------------------------------------------------------------
 __device__ __forceinline__ void rs_segment(int64_t n, int64_t *lo, int64_t *hi, int64_t *t0, int64_t *t1) {
     const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
@@ -330,26 +350,31 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restri
     for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) hist[(int64_t)d * gridDim.x + blockIdx.x] = s_h[d];
 }
 
-// single block: exclusive scan of m uint32 values in place
-__global__ void __launch_bounds__(1024) k_scan_u32_single(uint32_t *__restrict__ a, int64_t m) {
+// one CTA per digit: exclusive scan of that digit's per-block counts in place, digit total out.
+// The scatter kernel turns the 256 totals into digit bases itself.
+__global__ void __launch_bounds__(256) k_rs_scan_digit(uint32_t *__restrict__ hist, int nblk,
+                                                      uint32_t *__restrict__ totals) {
     __shared__ uint32_t s_w[33];
-    const int64_t per = (m + 1023) / 1024;
-    const int64_t lo = min(m, (int64_t)threadIdx.x * per), hi = min(m, lo + per);
-    uint32_t s = 0;
-    for (int64_t i = lo; i < hi; ++i) s += a[i];
+    uint32_t *row = hist + (int64_t)blockIdx.x * nblk;
+    const int per = (nblk + 255) / 256;
+    const int lo = min(nblk, (int)threadIdx.x * per), hi = min(nblk, lo + per);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += row[i];
     uint32_t tot;
-    uint32_t ex = block_scan_excl<uint32_t>(s, s_w, &tot);
-    for (int64_t i = lo; i < hi; ++i) {
-        const uint32_t v = a[i];
-        a[i] = ex;
+    uint32_t ex = block_scan_excl<uint32_t>(sum, s_w, &tot);
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t v = row[i];
+        row[i] = ex;
         ex += v;
     }
+    if (threadIdx.x == 0) totals[blockIdx.x] = tot;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__restrict__ in,
                                                            uint64_t *__restrict__ out,
                                                            const unsigned long long *__restrict__ d_n, int shift,
-                                                           unsigned mask, const uint32_t *__restrict__ offs) {
+                                                           unsigned mask, const uint32_t *__restrict__ offs,
+                                                           const uint32_t *__restrict__ totals) {
     __shared__ uint32_t s_wcnt[RS_WARPS][RS_BINS + 1];
     __shared__ uint32_t s_off[RS_BINS];
     __shared__ uint32_t s_tot[RS_BINS];
@@ -362,7 +387,14 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
     int64_t lo, hi, t0, t1;
     rs_segment(n, &lo, &hi, &t0, &t1);
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5, lt = lanemask_lt();
-    if (threadIdx.x < RS_BINS) s_off[threadIdx.x] = offs[(int64_t)threadIdx.x * gridDim.x + blockIdx.x];
+    {
+        // digit base = exclusive scan of the digit totals; plus this block's offset inside the digit
+        const uint32_t v = (threadIdx.x < RS_BINS) ? totals[threadIdx.x] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_scan_excl<uint32_t>(v, s_scan, &tot);
+        if (threadIdx.x < RS_BINS) s_off[threadIdx.x] = ex + offs[(int64_t)threadIdx.x * gridDim.x + blockIdx.x];
+    }
+    __syncthreads();
 
     for (int64_t tile = t0; tile < t1; ++tile) {
         const int64_t base = tile * RS_TILE;
@@ -439,9 +471,10 @@ static int radix_sort(uint64_t *a, uint64_t *b, const unsigned long long *d_n, i
         uint64_t *dst = cur ? a : b;
         k_rs_hist<<<RS_BLOCKS, RS_THREADS, 0, s>>>(src, d_n, shift, mask, d_hist);
         B3C_LAUNCH_CHECK();
-        k_scan_u32_single<<<1, 1024, 0, s>>>(d_hist, (int64_t)RS_BINS * RS_BLOCKS);
+        uint32_t *d_totals = d_hist + (int64_t)RS_BINS * RS_BLOCKS;
+        k_rs_scan_digit<<<RS_BINS, 256, 0, s>>>(d_hist, RS_BLOCKS, d_totals);
         B3C_LAUNCH_CHECK();
-        k_rs_scatter<<<RS_BLOCKS, RS_THREADS, RS_TILE * 8, s>>>(src, dst, d_n, shift, mask, d_hist);
+        k_rs_scatter<<<RS_BLOCKS, RS_THREADS, RS_TILE * 8, s>>>(src, dst, d_n, shift, mask, d_hist, d_totals);
         B3C_LAUNCH_CHECK();
         cur ^= 1;
     }
@@ -670,6 +703,23 @@ int b3c_accum_begin(void *d_ws, int64_t ws_bytes, int64_t pair_capacity, int32_t
     return B3C_OK;
 }
 
+int b3c_accum_reset(void *d_ws, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    // keep C_LUT_OK (the rank-table verdict of begin); clear the per-map counters and the diagonal
+    B3C_CUDA(cudaMemsetAsync(ws + st.o_ctr, 0, C_LUT_OK * 8, s));
+    B3C_CUDA(cudaMemsetAsync(ws + st.o_ctr + (C_LUT_OK + 1) * 8, 0, (C_COUNT - C_LUT_OK - 1) * 8, s));
+    B3C_CUDA(cudaMemsetAsync(ws + st.o_diag, 0, (size_t)st.n_seq * 4, s));
+    st.reduced = false;
+    st.nnz_uo = st.nnz_diag = 0;
+    std::lock_guard<std::mutex> g(g_mu);
+    g_states[d_ws] = st;
+    return B3C_OK;
+}
+
 int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records, void *stream) {
     AccumState st;
     int rc = get_state(d_ws, &st);
@@ -719,6 +769,8 @@ int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream) {
     int64_t *up = (int64_t *)(ws + st.o_up_ptr), *lo = (int64_t *)(ws + st.o_lo_ptr), *len = (int64_t *)(ws + st.o_len);
     int64_t *ip_f = (int64_t *)(ws + st.o_indptr_f), *ip_u = (int64_t *)(ws + st.o_indptr_u);
 
+    k_accum_guard<<<1, 1, 0, s>>>(ctr, st.cap);
+    B3C_LAUNCH_CHECK();
     // 1. sort the off-diagonal keys on their 2b significant bits
     int where = 0;
     rc = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
@@ -760,7 +812,7 @@ int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream) {
     B3C_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaStreamSynchronize(s));
     if (h[C_OVERFLOW]) {
-        set_error("pair capacity %lld exceeded (%llu off-diagonal keys)", (long long)st.cap, h[C_NKEYS]);
+        set_error("pair capacity %lld exceeded by the off-diagonal keys", (long long)st.cap);
         return B3C_ERR_CAPACITY;
     }
     st.reduced = true;

@@ -30,6 +30,9 @@ constexpr int SPMV_NPT = 8;
 constexpr int SPMV_TILE = KR_THREADS * SPMV_NPT;     // 2048 non-zeros = 24 KB of matrix per tile
 constexpr int CHUNK = 1024;                          // rows per reduction chunk
 constexpr int CHUNK_RPT = CHUNK / KR_THREADS;
+constexpr int SPTR_CAP = 1024;                       // row pointers of a tile staged in shared memory
+constexpr int RED_MAX = 8;                           // values reduced together by one block reduction
+constexpr int KR_MIN_CTAS = 4;                       // CTAs per SM the persistent kernel is compiled for
 
 // partial arrays, each n_chunks long
 enum { PA = 0, PB, PC, PMIN, PNEGMAX, PG1, PG2, P_COUNT };
@@ -39,6 +42,12 @@ struct KRScalars {
     double rho_km1, rho_km2, rout, rold, eta, inner_tol, alpha, beta, gamma;
     long long n_iter, max_iter, k, outer, n_spmv, zero_diag;
     int status, ymode, ysel, state;
+};
+
+// per-phase cycle counters of CTA 0 (work = its own phase time, sync = its wait at the grid barrier)
+enum { T_INIT = 0, T_SPMV, T_FIX, T_RESID, T_DIR, T_W, T_STEP, T_UPDATE, T_SCALAR, T_COUNT };
+struct KRTimers {
+    long long work[T_COUNT], sync[T_COUNT], total;
 };
 
 struct KRArgs {
@@ -51,6 +60,7 @@ struct KRArgs {
     // plan
     int64_t n_tiles;
     int32_t *tile_ra;
+    int32_t *chunk_t;          // per local chunk: first tile whose last-starting row lies in the chunk
     double *head_part, *tail_part;
     double *dfix;
     // vectors (global row indexing, length n)
@@ -59,51 +69,59 @@ struct KRArgs {
     double *part;
     int32_t n_chunks;
     KRScalars *ctl;
+    KRTimers *timers;
 };
 
 // ---- deterministic block reductions ---------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double *s_red) {
-    v = warp_sum(v);
+// NS sums followed by NM minima, reduced together: warp xor-tree, then the 8 warp results in warp
+// order.  Every thread gets the results; the shape is fixed, so the value is reproducible.
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce(double (&v)[NS + NM], double *s_red) {
+    constexpr int K = NS + NM;
+    static_assert(K <= RED_MAX, "too many values");
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = (i < NS) ? warp_sum(v[i]) : warp_min(v[i]);
     const unsigned w = threadIdx.x >> 5;
     __syncthreads();
-    if (lane_id() == 0) s_red[w] = v;
-    __syncthreads();
-    double r = 0.0;
+    if (lane_id() == 0) {
 #pragma unroll
-    for (int i = 0; i < KR_WARPS; ++i) r += s_red[i];
-    return r;
-}
-__device__ __forceinline__ double block_min(double v, double *s_red) {
-    v = warp_min(v);
-    const unsigned w = threadIdx.x >> 5;
+        for (int i = 0; i < K; ++i) s_red[w * K + i] = v[i];
+    }
     __syncthreads();
-    if (lane_id() == 0) s_red[w] = v;
-    __syncthreads();
-    double r = s_red[0];
 #pragma unroll
-    for (int i = 1; i < KR_WARPS; ++i) r = fmin(r, s_red[i]);
-    return r;
+    for (int i = 0; i < K; ++i) {
+        double r = s_red[i];
+#pragma unroll
+        for (int j = 1; j < KR_WARPS; ++j) r = (i < NS) ? r + s_red[j * K + i] : fmin(r, s_red[j * K + i]);
+        v[i] = r;
+    }
 }
 
-// every thread of every CTA gets the same value: fixed strided accumulation + fixed tree
-__device__ __forceinline__ double reduce_sum(const double *part, int n, double *s_red) {
-    double a = 0.0;
-    for (int i = threadIdx.x; i < n; i += KR_THREADS) a += part[i];
-    return block_sum(a, s_red);
-}
-__device__ __forceinline__ double reduce_min(const double *part, int n, double *s_red) {
-    double a = INFINITY;
-    for (int i = threadIdx.x; i < n; i += KR_THREADS) a = fmin(a, part[i]);
-    return block_min(a, s_red);
+// the same over per-chunk partial arrays: out[i] = reduce(part[ids[i]][0..nc)); identical in every CTA
+template <int NS, int NM>
+__device__ __forceinline__ void reduce_parts(const double *part, int nc, const int (&ids)[NS + NM],
+                                             double (&out)[NS + NM], double *s_red) {
+#pragma unroll
+    for (int i = 0; i < NS + NM; ++i) out[i] = (i < NS) ? 0.0 : (double)INFINITY;
+    for (int j = threadIdx.x; j < nc; j += KR_THREADS) {
+#pragma unroll
+        for (int i = 0; i < NS + NM; ++i) {
+            const double x = part[(int64_t)ids[i] * nc + j];
+            out[i] = (i < NS) ? out[i] + x : fmin(out[i], x);
+        }
+    }
+    block_reduce<NS, NM>(out, s_red);
 }
 
 // ---- SpMV -------------------------------------------------------------------------------------
 // `u` is rewritten between SpMV phases of the same (persistent) launch, so it is read with
 // ordinary coherent loads -- never ld.global.nc -- and carries no __restrict__.
-__device__ __forceinline__ void spmv_tile(const KRArgs &A, const double *u, int64_t t, double *s_prod) {
+__device__ __forceinline__ void spmv_tile(const KRArgs &A, const double *u, int64_t t, double *s_prod,
+                                          int *s_ptr) {
     const int64_t base = t * SPMV_TILE;
     const int64_t rem = A.nnz - base;
     const int cnt = (int)(rem < SPMV_TILE ? (rem > 0 ? rem : 0) : SPMV_TILE);
+    // 1. stream the tile: all loads are issued before anything is consumed
     double a[SPMV_NPT];
     int c[SPMV_NPT];
 #pragma unroll
@@ -117,74 +135,101 @@ __device__ __forceinline__ void spmv_tile(const KRArgs &A, const double *u, int6
             c[k] = 0;
         }
     }
+    // 2. rows that start inside the tile are [ra, rb); their pointers go to shared memory while the
+    //    matrix loads are in flight, so the reduction below never waits on global memory
+    const int ra = A.tile_ra[t], rb = A.tile_ra[t + 1];
+    const int n_rows = rb - ra;
+    const bool staged = n_rows < SPTR_CAP;
+    if (staged) {
+        for (int i = threadIdx.x; i <= n_rows; i += KR_THREADS) {
+            const int64_t rel = A.indptr[ra + i] - base;
+            s_ptr[i] = (int)(rel > cnt ? cnt + 1 : rel);              // cnt+1 marks "ends beyond this tile"
+        }
+    }
+    // 3. gather u[col], multiply, park the products
 #pragma unroll
     for (int k = 0; k < SPMV_NPT; ++k) {
         const int idx = k * KR_THREADS + threadIdx.x;
         if (idx < cnt) s_prod[idx] = a[k] * u[c[k]];
     }
     __syncthreads();
-    const int ra = A.tile_ra[t], rb = A.tile_ra[t + 1];
-    const int64_t end = base + cnt;
-    const int n_items = (rb - ra) + 1;            // item 0 = head segment of a row begun earlier
+    // 4. segmented reduction: item 0 is the head of a row begun in an earlier tile, item i>0 is row ra+i-1
+    const int n_items = n_rows + 1;
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    auto bounds = [&](int it, int &lo, int &hi, bool &complete) {
+        int p0, p1;
+        if (staged) {
+            p0 = (it == 0) ? 0 : s_ptr[it - 1];
+            p1 = s_ptr[it == 0 ? 0 : it];
+        } else {
+            const int64_t r0 = (it == 0) ? 0 : A.indptr[ra + it - 1] - base;
+            const int64_t r1 = A.indptr[ra + (it == 0 ? 0 : it)] - base;
+            p0 = (int)r0;
+            p1 = (int)(r1 > cnt ? cnt + 1 : r1);
+        }
+        lo = p0;
+        hi = p1 > cnt ? cnt : p1;
+        complete = p1 <= cnt;
+    };
     if (n_items <= 8 * KR_WARPS) {
         for (int it = warp; it < n_items; it += KR_WARPS) {
-            int64_t lo, hi, rend = 0;
-            if (it == 0) {
-                lo = base;
-                hi = min(A.indptr[ra], end);
-            } else {
-                lo = A.indptr[ra + it - 1];
-                rend = A.indptr[ra + it];
-                hi = min(rend, end);
-            }
+            int lo, hi;
+            bool complete;
+            bounds(it, lo, hi, complete);
             double s = 0.0;
-            for (int64_t e = lo + lane; e < hi; e += 32) s += s_prod[(int)(e - base)];
+            for (int e = lo + (int)lane; e < hi; e += 32) s += s_prod[e];
             s = warp_sum(s);
             if (lane == 0) {
                 if (it == 0) A.head_part[t] = s;
-                else if (rend <= end) A.q[A.row_lo + ra + it - 1] = s;
+                else if (complete) A.q[A.row_lo + ra + it - 1] = s;
                 else A.tail_part[t] = s;
             }
         }
     } else {
         for (int it = threadIdx.x; it < n_items; it += KR_THREADS) {
-            int64_t lo, hi, rend = 0;
-            if (it == 0) {
-                lo = base;
-                hi = min(A.indptr[ra], end);
-            } else {
-                lo = A.indptr[ra + it - 1];
-                rend = A.indptr[ra + it];
-                hi = min(rend, end);
-            }
+            int lo, hi;
+            bool complete;
+            bounds(it, lo, hi, complete);
             double s = 0.0;
-            for (int64_t e = lo; e < hi; ++e) s += s_prod[(int)(e - base)];
+            for (int e = lo; e < hi; ++e) s += s_prod[e];
             if (it == 0) A.head_part[t] = s;
-            else if (rend <= end) A.q[A.row_lo + ra + it - 1] = s;
+            else if (complete) A.q[A.row_lo + ra + it - 1] = s;
             else A.tail_part[t] = s;
         }
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ void phase_spmv(const KRArgs &A, double *s_prod) {
-    for (int64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) spmv_tile(A, A.u, t, s_prod);
+__device__ __forceinline__ void phase_spmv(const KRArgs &A, double *s_prod, int *s_ptr) {
+    for (int64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) spmv_tile(A, A.u, t, s_prod, s_ptr);
 }
 
-// rows that straddle tiles: tail of the first tile + heads of the following ones, in tile order
+// A row that straddles tiles leaves tail_part in its first tile and head_part in the following
+// ones; its value is their sum in tile order.  The straddling row of tile t, if any, is rb-1.
+__device__ __forceinline__ void fix_tile(const KRArgs &A, int64_t t) {
+    const int ra = A.tile_ra[t], rb = A.tile_ra[t + 1];
+    if (rb <= ra) return;
+    const int64_t rend = A.indptr[rb];
+    if (rend <= (t + 1) * SPMV_TILE) return;
+    const int64_t t_last = (rend - 1) / SPMV_TILE;
+    double s = A.tail_part[t];
+    for (int64_t t2 = t + 1; t2 <= t_last; ++t2) s += A.head_part[t2];
+    A.q[A.row_lo + rb - 1] = s;
+}
+
+// stand-alone form (b3c_spmv): all tiles
 __device__ __forceinline__ void phase_fix(const KRArgs &A) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < A.n_tiles; t += stride) {
-        const int ra = A.tile_ra[t], rb = A.tile_ra[t + 1];
-        if (rb <= ra) continue;
-        const int64_t rend = A.indptr[rb];            // end of the last row that starts in this tile
-        if (rend <= (t + 1) * SPMV_TILE) continue;
-        const int64_t t_last = (rend - 1) / SPMV_TILE;
-        double s = A.tail_part[t];
-        for (int64_t t2 = t + 1; t2 <= t_last; ++t2) s += A.head_part[t2];
-        A.q[A.row_lo + rb - 1] = s;
-    }
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < A.n_tiles; t += stride) fix_tile(A, t);
+}
+
+// fused form: the CTA that owns chunk c patches the straddling rows that fall inside the chunk
+// before it reads q, so no separate pass (and no extra grid barrier) is needed
+__device__ __forceinline__ void chunk_fixup(const KRArgs &A, int c) {
+    const int lc = c - A.row_lo / CHUNK;
+    const int t0 = A.chunk_t[lc], t1 = A.chunk_t[lc + 1];
+    for (int t = t0 + (int)threadIdx.x; t < t1; t += KR_THREADS) fix_tile(A, t);
+    __syncthreads();
 }
 
 // ---- vector phases: one CTA per 1024-row chunk, 4 rows per thread -----------------------------------
@@ -216,6 +261,7 @@ __device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
         if (loc) {
+            chunk_fixup(A, c);
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
@@ -231,8 +277,9 @@ __device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red) {
                 }
             }
         }
-        acc = block_sum(acc, s_red);
-        if (threadIdx.x == 0) A.part[PA * A.n_chunks + c] = loc ? acc : 0.0;
+        double r[1] = {acc};
+        block_reduce<1, 0>(r, s_red);
+        if (threadIdx.x == 0) A.part[PA * A.n_chunks + c] = loc ? r[0] : 0.0;
     }
 }
 
@@ -263,8 +310,9 @@ __device__ __forceinline__ void phase_dir(const KRArgs &A, bool first, double be
             }
         }
         if (first) {
-            acc = block_sum(acc, s_red);
-            if (threadIdx.x == 0) A.part[PB * A.n_chunks + c] = loc ? acc : 0.0;
+            double r[1] = {acc};
+            block_reduce<1, 0>(r, s_red);
+            if (threadIdx.x == 0) A.part[PB * A.n_chunks + c] = loc ? r[0] : 0.0;
         }
     }
 }
@@ -275,6 +323,7 @@ __device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
         if (loc) {
+            chunk_fixup(A, c);
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
@@ -288,8 +337,9 @@ __device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red) {
                 }
             }
         }
-        acc = block_sum(acc, s_red);
-        if (threadIdx.x == 0) A.part[PA * A.n_chunks + c] = loc ? acc : 0.0;
+        double r[1] = {acc};
+        block_reduce<1, 0>(r, s_red);
+        if (threadIdx.x == 0) A.part[PA * A.n_chunks + c] = loc ? r[0] : 0.0;
     }
 }
 
@@ -321,18 +371,15 @@ __device__ __forceinline__ void phase_step(const KRArgs &A, double alpha, double
                 }
             }
         }
-        rho = block_sum(rho, s_red);
-        mn = block_min(mn, s_red);
-        nmx = block_min(nmx, s_red);
-        g1 = block_min(g1, s_red);
-        g2 = block_min(g2, s_red);
+        double r[5] = {rho, mn, nmx, g1, g2};
+        block_reduce<1, 4>(r, s_red);
         if (threadIdx.x == 0) {
             const int nc = A.n_chunks;
-            A.part[PC * nc + c] = loc ? rho : 0.0;
-            A.part[PMIN * nc + c] = mn;
-            A.part[PNEGMAX * nc + c] = nmx;
-            A.part[PG1 * nc + c] = g1;
-            A.part[PG2 * nc + c] = g2;
+            A.part[PC * nc + c] = loc ? r[0] : 0.0;
+            A.part[PMIN * nc + c] = r[1];
+            A.part[PNEGMAX * nc + c] = r[2];
+            A.part[PG1 * nc + c] = r[3];
+            A.part[PG2 * nc + c] = r[4];
         }
     }
 }
@@ -399,24 +446,41 @@ __device__ __forceinline__ bool scalar_decide(KRScalars &S, double ymin, double 
 }
 
 // ---- the persistent kernel ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(KR_THREADS) k_kr_persistent(KRArgs A) {
+#define KR_PHASE(id, call)                                                     \
+    do {                                                                       \
+        const long long t0_ = clock64();                                       \
+        call;                                                                  \
+        const long long t1_ = clock64();                                       \
+        grid.sync();                                                           \
+        if (timing) {                                                          \
+            const long long t2_ = clock64();                                   \
+            A.timers->work[id] += t1_ - t0_;                                   \
+            A.timers->sync[id] += t2_ - t1_;                                   \
+        }                                                                      \
+    } while (0)
+
+__global__ void __launch_bounds__(KR_THREADS, KR_MIN_CTAS) k_kr_persistent(KRArgs A) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double s_prod[SPMV_TILE];
-    __shared__ double s_red[KR_WARPS];
+    __shared__ int s_ptr[SPTR_CAP + 1];
+    __shared__ double s_red[KR_WARPS * RED_MAX];
     KRScalars S = *A.ctl;
     const int nc = A.n_chunks;
     double *ybuf[2] = {A.y0, A.y1};
+    const bool timing = (blockIdx.x == 0 && threadIdx.x == 0);
+    const long long t_begin = clock64();
+    long long ts_ = 0;
 
-    phase_init(A);
-    grid.sync();
-    phase_spmv(A, s_prod);
-    grid.sync();
-    phase_fix(A);
-    grid.sync();
-    phase_resid(A, s_red);
-    grid.sync();
+    KR_PHASE(T_INIT, phase_init(A));
+    KR_PHASE(T_SPMV, phase_spmv(A, s_prod, s_ptr));
+    KR_PHASE(T_RESID, phase_resid(A, s_red));
     S.n_spmv = 1;
-    scalar_outer(S, reduce_sum(A.part + PA * nc, nc, s_red), true);
+    {
+        double r[1];
+        const int ids[1] = {PA};
+        reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
+        scalar_outer(S, r[0], true);
+    }
 
     while (S.rout > S.rt && S.n_iter < S.max_iter) {      // sparse_utils.py:146
         S.outer += 1;
@@ -428,26 +492,28 @@ __global__ void __launch_bounds__(KR_THREADS) k_kr_persistent(KRArgs A) {
             const bool first = (S.k == 1);
             if (!first) S.beta = S.rho_km1 / S.rho_km2;
             double *ycur = ybuf[S.ysel], *ynew = ybuf[S.ysel ^ 1];
-            phase_dir(A, first, S.beta, ycur, s_red);
-            grid.sync();
-            phase_spmv(A, s_prod);
-            grid.sync();
-            phase_fix(A);
-            grid.sync();
-            phase_w(A, s_red);
-            grid.sync();
+            KR_PHASE(T_DIR, phase_dir(A, first, S.beta, ycur, s_red));
+            KR_PHASE(T_SPMV, phase_spmv(A, s_prod, s_ptr));
+            KR_PHASE(T_W, phase_w(A, s_red));
             S.n_spmv += 1;
-            if (first) S.rho_km1 = reduce_sum(A.part + PB * nc, nc, s_red);
-            const double pw = reduce_sum(A.part + PA * nc, nc, s_red);
-            S.alpha = S.rho_km1 / pw;
-            phase_step(A, S.alpha, S.delta, S.Delta, ycur, ynew, s_red);
-            grid.sync();
-            const double ymin = reduce_min(A.part + PMIN * nc, nc, s_red);
-            const double ymax = -reduce_min(A.part + PNEGMAX * nc, nc, s_red);
-            const double g1 = reduce_min(A.part + PG1 * nc, nc, s_red);
-            const double g2 = reduce_min(A.part + PG2 * nc, nc, s_red);
-            const double rho_new = reduce_sum(A.part + PC * nc, nc, s_red);
-            if (scalar_decide(S, ymin, ymax, g1, g2, rho_new)) break;
+            ts_ = clock64();
+            {
+                double r[2];
+                const int ids[2] = {PA, PB};
+                reduce_parts<2, 0>(A.part, nc, ids, r, s_red);
+                if (first) S.rho_km1 = r[1];              // rk.Z of the first step (sparse_utils.py:160)
+                S.alpha = S.rho_km1 / r[0];               // rho / p.w (sparse_utils.py:166)
+            }
+            if (timing) A.timers->work[T_SCALAR] += clock64() - ts_;
+            KR_PHASE(T_STEP, phase_step(A, S.alpha, S.delta, S.Delta, ycur, ynew, s_red));
+            ts_ = clock64();
+            double r[5];
+            {
+                const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
+                reduce_parts<1, 4>(A.part, nc, ids, r, s_red);
+            }
+            if (timing) A.timers->work[T_SCALAR] += clock64() - ts_;
+            if (scalar_decide(S, r[1], -r[2], r[3], r[4], r[0])) break;
             if (S.k >= S.max_iter + 8) {                  // safety net: the reference's inner loop is unbounded
                 S.status = B3C_ERR_NOCONV;
                 break;
@@ -455,18 +521,19 @@ __global__ void __launch_bounds__(KR_THREADS) k_kr_persistent(KRArgs A) {
         }
         if (S.status != 0) break;
         // with ymode 2 the step was not accepted: ycur still holds y; with ymode 1 ysel was flipped
-        phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]);
-        grid.sync();
-        phase_spmv(A, s_prod);
-        grid.sync();
-        phase_fix(A);
-        grid.sync();
-        phase_resid(A, s_red);
-        grid.sync();
+        KR_PHASE(T_UPDATE, phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
+        KR_PHASE(T_SPMV, phase_spmv(A, s_prod, s_ptr));
+        KR_PHASE(T_RESID, phase_resid(A, s_red));
         S.n_spmv += 1;
-        scalar_outer(S, reduce_sum(A.part + PA * nc, nc, s_red), false);
+        double r[1];
+        const int ids[1] = {PA};
+        reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
+        scalar_outer(S, r[0], false);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *A.ctl = S;
+    if (timing) {
+        *A.ctl = S;
+        A.timers->total = clock64() - t_begin;
+    }
 }
 
 // ---- stand-alone kernels (plan, microbench SpMV, host-driven phases) -----------------------------
@@ -513,15 +580,36 @@ __global__ void __launch_bounds__(KR_THREADS) k_diag_fix(int32_t row_lo, int32_t
     if (lane == 0 && nz) atomicAdd((unsigned long long *)&ctl->zero_diag, (unsigned long long)nz);
 }
 
+// chunk_t[lc] = first tile t with tile_ra[t+1] > lc*CHUNK, i.e. whose last-starting row is at or
+// beyond the chunk's first local row; chunk_t[n_local_chunks] = n_tiles
+__global__ void k_chunk_plan(int32_t n_local_chunks, int64_t n_tiles, const int32_t *__restrict__ tile_ra,
+                             int32_t *__restrict__ chunk_t) {
+    const int lc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lc > n_local_chunks) return;
+    if (lc == n_local_chunks) {
+        chunk_t[lc] = (int32_t)n_tiles;
+        return;
+    }
+    const int64_t r0 = (int64_t)lc * CHUNK;
+    int64_t lo = 0, hi = n_tiles;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)tile_ra[mid + 1] > r0) hi = mid;
+        else lo = mid + 1;
+    }
+    chunk_t[lc] = (int32_t)lo;
+}
+
 __global__ void __launch_bounds__(KR_THREADS) k_spmv(KRArgs A) {
     __shared__ double s_prod[SPMV_TILE];
-    phase_spmv(A, s_prod);
+    __shared__ int s_ptr[SPTR_CAP + 1];
+    phase_spmv(A, s_prod, s_ptr);
 }
 __global__ void __launch_bounds__(KR_THREADS) k_spmv_fix(KRArgs A) { phase_fix(A); }
 
 // ---- workspace ---------------------------------------------------------------------------------------
 struct KRLayout {
-    int64_t n_tiles, o_tile_ra, o_head, o_tail, o_dfix, o_vec, o_part, o_ctl, total;
+    int64_t n_tiles, o_tile_ra, o_chunk_t, o_head, o_tail, o_dfix, o_vec, o_part, o_ctl, o_timers, total;
     int32_t n_chunks;
 };
 static KRLayout kr_layout(int32_t n, int64_t nnz) {
@@ -531,12 +619,14 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     if (L.n_tiles < 1) L.n_tiles = 1;
     L.n_chunks = (int32_t)ceil_div(n, CHUNK);
     L.o_tile_ra = c.take((L.n_tiles + 1) * 4);
+    L.o_chunk_t = c.take(((int64_t)L.n_chunks + 2) * 4);
     L.o_head = c.take(L.n_tiles * 8);
     L.o_tail = c.take(L.n_tiles * 8);
     L.o_dfix = c.take((int64_t)n * 8);
     L.o_vec = c.take((int64_t)n * 8 * 10);
     L.o_part = c.take((int64_t)L.n_chunks * 8 * P_COUNT);
     L.o_ctl = c.take(sizeof(KRScalars));
+    L.o_timers = c.take(sizeof(KRTimers));
     L.total = c.cur;
     return L;
 }
@@ -552,6 +642,7 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.data = data;
     A.n_tiles = L.n_tiles;
     A.tile_ra = (int32_t *)(ws + L.o_tile_ra);
+    A.chunk_t = (int32_t *)(ws + L.o_chunk_t);
     A.head_part = (double *)(ws + L.o_head);
     A.tail_part = (double *)(ws + L.o_tail);
     A.dfix = (double *)(ws + L.o_dfix);
@@ -569,6 +660,7 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.part = (double *)(ws + L.o_part);
     A.n_chunks = L.n_chunks;
     A.ctl = (KRScalars *)(ws + L.o_ctl);
+    A.timers = (KRTimers *)(ws + L.o_timers);
 }
 
 static int persistent_grid(int *grid_out) {
@@ -582,7 +674,7 @@ static int persistent_grid(int *grid_out) {
             set_error("persistent KR kernel does not fit on an SM");
             return B3C_ERR_CUDA;
         }
-        if (per_sm > 4) per_sm = 4;
+        if (per_sm > KR_MIN_CTAS) per_sm = KR_MIN_CTAS;
         cached = sms * per_sm;
     }
     *grid_out = cached;
@@ -631,8 +723,11 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
     S.eta = 0.1;                      // etamax (sparse_utils.py:129-130)
     S.max_iter = max_iter;
     B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
+    B3C_CUDA(cudaMemsetAsync(A.timers, 0, sizeof(KRTimers), s));
 
     k_tile_plan<<<(unsigned)ceil_div(L.n_tiles + 1, 256), 256, 0, s>>>(n, d_indptr, L.n_tiles, A.tile_ra);
+    B3C_LAUNCH_CHECK();
+    k_chunk_plan<<<(unsigned)ceil_div(L.n_chunks + 1, 256), 256, 0, s>>>(L.n_chunks, L.n_tiles, A.tile_ra, A.chunk_t);
     B3C_LAUNCH_CHECK();
     {
         int64_t blocks = ceil_div(n, KR_WARPS);
@@ -648,11 +743,19 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
     count_launch();
     B3C_CUDA(cudaMemcpyAsync(d_x, A.x, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
     B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
+    KRTimers T;
+    B3C_CUDA(cudaMemcpyAsync(&T, A.timers, sizeof(T), cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaStreamSynchronize(s));
     h_info[0] = S.n_iter;
     h_info[1] = S.zero_diag;
     h_info[2] = S.outer;
     h_info[3] = S.n_spmv;
+    h_info[4] = grid;
+    h_info[5] = T.total;
+    for (int i = 0; i < T_COUNT; ++i) {
+        h_info[6 + i] = T.work[i];
+        h_info[6 + T_COUNT + i] = T.sync[i];
+    }
     if (S.status == B3C_ERR_TIE) {
         set_error("KR: max(ynew) == Delta with no element above Delta (reference raises ValueError here)");
         return B3C_ERR_TIE;

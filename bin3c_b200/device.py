@@ -32,6 +32,28 @@ def _empty(n, dtype, device=None):
     return torch.empty(max(int(n), 0), dtype=dtype, device=device or 'cuda')
 
 
+class BufferPool(object):
+    """
+    Grow-only named device buffers, so a pipeline that runs the path repeatedly does not go through
+    the allocator (or cudaMalloc) on every step.  get() returns a view of the first n elements.
+    """
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, n, dtype):
+        n = max(int(n), 0)
+        t = self._bufs.get(name)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(n + n // 4 + 16, dtype=dtype, device='cuda')
+            self._bufs[name] = t
+        return t[:n]
+
+
+def _alloc(pool, name, n, dtype):
+    return _empty(n, dtype) if pool is None else pool.get(name, n, dtype)
+
+
 def to_device(a, dtype=None, non_blocking=False):
     """numpy array / torch tensor -> contiguous CUDA tensor (H2D copy when needed)."""
     if isinstance(a, torch.Tensor):
@@ -113,11 +135,13 @@ class Accumulator(object):
         if nbytes < 0:
             raise AssertionError('invalid accumulator sizes')
         self.ws = _empty(nbytes, torch.uint8)
-        self.begin()
-
-    def begin(self):
         check(lib.b3c_accum_begin(_ptr(self.ws), self.ws.numel(), self.capacity, self.n_seq,
                                   _ptr(self.tid2idx), self.n_refs, _stream()))
+        self.info = None
+
+    def begin(self):
+        """Start another map over the same reference table."""
+        check(lib.b3c_accum_reset(_ptr(self.ws), _stream()))
         self.info = None
 
     def add(self, records):
@@ -125,14 +149,14 @@ class Accumulator(object):
         assert records.is_cuda and records.element_size() == 8 and records.is_contiguous()
         check(lib.b3c_accum_add_pairs(_ptr(self.ws), _ptr(records), records.numel(), _stream()))
 
-    def finish(self, symmetric=True):
+    def finish(self, symmetric=True, pool=None):
         """Sort-reduce and emit the canonical CSR.  Returns (DeviceCSR[uint32 counts], info dict)."""
         sizes = (C.c_int64 * 8)()
         check(lib.b3c_accum_reduce(_ptr(self.ws), sizes, _stream()))
         nnz = int(sizes[1] if symmetric else sizes[0])
-        indptr = _empty(self.n_seq + 1, torch.int64)
-        indices = _empty(nnz, torch.int32)
-        counts = _empty(nnz, torch.int32)
+        indptr = _alloc(pool, 'map_indptr', self.n_seq + 1, torch.int64)
+        indices = _alloc(pool, 'map_indices', nnz, torch.int32)
+        counts = _alloc(pool, 'map_counts', nnz, torch.int32)
         check(lib.b3c_accum_emit_csr(_ptr(self.ws), 1 if symmetric else 0, _ptr(indptr), _ptr(indices),
                                      _ptr(counts), _stream()))
         self.info = dict(nnz_upper=int(sizes[0]), nnz_full=int(sizes[1]), accepted=int(sizes[2]),
@@ -144,8 +168,8 @@ class Accumulator(object):
 # mask + normalisation
 # --------------------------------------------------------------------------------------
 
-def max_offdiag(csr):
-    out = _empty(csr.n, csr.data.dtype)
+def max_offdiag(csr, pool=None):
+    out = _alloc(pool, 'signal', csr.n, csr.data.dtype)
     fn = lib.b3c_max_offdiag_u32 if csr.counts else lib.b3c_max_offdiag_f64
     if not csr.counts:
         assert csr.data.dtype == torch.float64
@@ -153,17 +177,17 @@ def max_offdiag(csr):
     return out
 
 
-def acceptance_mask(lengths, signal, min_len, min_sig):
+def acceptance_mask(lengths, signal, min_len, min_sig, pool=None):
     n = int(lengths.numel())
-    mask = _empty(n, torch.uint8)
+    mask = _alloc(pool, 'mask', n, torch.uint8)
     check(lib.b3c_acceptance_mask(n, _ptr(lengths), _ptr(signal), int(min_len), int(min_sig), _ptr(mask), _stream()))
     return mask
 
 
-def site_norm(csr, sites):
+def site_norm(csr, sites, pool=None):
     """counts (uint32) or float64 matrix -> float64 matrix scaled by 1/(s_i*s_j); float input is scaled in place."""
     if csr.counts:
-        out = _empty(csr.nnz, torch.float64)
+        out = _alloc(pool, 'normed', csr.nnz, torch.float64)
         check(lib.b3c_site_norm(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites), _ptr(out),
                                 _stream()))
         return DeviceCSR(csr.n, csr.indptr, csr.indices, out)
@@ -188,22 +212,26 @@ def _kr_workspace(n, nnz):
     return ws
 
 
-def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000):
+def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000, pool=None):
     """Returns (x CUDA float64[n], info dict) for a symmetric float64 DeviceCSR."""
     assert csr.data.dtype == torch.float64
     ws = _kr_workspace(csr.n, csr.nnz)
-    x = _empty(csr.n, torch.float64)
-    info = (C.c_int64 * 8)()
+    x = _alloc(pool, 'kr_x', csr.n, torch.float64)
+    info = (C.c_int64 * 32)()
     rc = lib.b3c_kr_run(csr.n, csr.nnz, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), float(tol),
                         float(delta), float(Delta), int(max_iter), 0, _ptr(x), _ptr(ws), ws.numel(), info, _stream())
-    out = dict(n_iter=int(info[0]), zero_diag=int(info[1]), outer=int(info[2]), n_spmv=int(info[3]))
+    names = ('init', 'spmv', 'fix', 'resid', 'dir', 'w', 'step', 'update', 'scalar')
+    out = dict(n_iter=int(info[0]), zero_diag=int(info[1]), outer=int(info[2]), n_spmv=int(info[3]),
+               grid=int(info[4]), cycles=int(info[5]),
+               work_cycles={k: int(info[6 + i]) for i, k in enumerate(names)},
+               sync_cycles={k: int(info[15 + i]) for i, k in enumerate(names)})
     check(rc)
     return x, out
 
 
-def kr_apply(csr, x):
+def kr_apply(csr, x, pool=None):
     """diag(x) . A . diag(x) entry-wise (sparse_utils.py:223-224)."""
-    out = _empty(csr.nnz, torch.float64)
+    out = _alloc(pool, 'balanced', csr.nnz, torch.float64)
     check(lib.b3c_kr_scale(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(x), _ptr(out), _stream()))
     return DeviceCSR(csr.n, csr.indptr, csr.indices, out)
 
@@ -231,7 +259,7 @@ def spmv(csr, u, y=None, ws=None, prepared=False):
 # compress + edge weighting
 # --------------------------------------------------------------------------------------
 
-def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True):
+def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True, pool=None):
     """
     Drop rejected contigs and produce the compressed matrix and/or the weighted edge list.
     Returns dict(n_accepted, sub=DeviceCSR|None, u, v, w, scl) with CUDA tensors.
@@ -239,22 +267,22 @@ def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True):
     assert csr.data.dtype == torch.float64
     n = csr.n
     nbytes = lib.b3c_compress_workspace_bytes(n)
-    ws = _empty(nbytes, torch.uint8)
-    newidx = _empty(n, torch.int32)
+    ws = _alloc(pool, 'compress_ws', nbytes, torch.uint8)
+    newidx = _alloc(pool, 'newidx', n, torch.int32)
     h = (C.c_int64 * 4)()
     check(lib.b3c_compress_count(n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask), _ptr(newidx),
                                  _ptr(ws), ws.numel(), h, _stream()))
     n_acc, n_kept, n_edges = int(h[0]), int(h[1]), int(h[2])
     sub_indptr = sub_indices = sub_data = eu = ev = ew = None
     if want_sub:
-        sub_indptr = _empty(n_acc + 1, torch.int64)
-        sub_indices = _empty(n_kept, torch.int32)
-        sub_data = _empty(n_kept, torch.float64)
+        sub_indptr = _alloc(pool, 'sub_indptr', n_acc + 1, torch.int64)
+        sub_indices = _alloc(pool, 'sub_indices', n_kept, torch.int32)
+        sub_data = _alloc(pool, 'sub_data', n_kept, torch.float64)
     if want_edges:
-        eu = _empty(n_edges, torch.int32)
-        ev = _empty(n_edges, torch.int32)
-        ew = _empty(n_edges, torch.float64)
-    scl = _empty(1, torch.float64)
+        eu = _alloc(pool, 'edge_u', n_edges, torch.int32)
+        ev = _alloc(pool, 'edge_v', n_edges, torch.int32)
+        ew = _alloc(pool, 'edge_w', n_edges, torch.float64)
+    scl = _alloc(pool, 'scl', 1, torch.float64)
     check(lib.b3c_compress_fill(n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask), _ptr(newidx),
                                 _ptr(ws), 1 if scale else 0, _ptr(sub_indptr), _ptr(sub_indices), _ptr(sub_data),
                                 _ptr(eu), _ptr(ev), _ptr(ew), _ptr(scl), _stream()))

@@ -1,0 +1,155 @@
+"""
+The hot path as one device-resident pipeline with reusable workspaces:
+
+    packed pair records -> contact matrix (CSR, exact counts) -> acceptance mask ->
+    site normalisation -> Knight-Ruiz balancing -> compressed, scaled edge list
+
+HotPath holds the per-dataset tables (tid->index map, lengths, sites) on the device and is the
+engine behind ContactMap / cluster.to_edges; bench.py drives it directly.  Every stage is a call
+into the C ABI (bin3c_b200.device); nothing here computes on the host.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import device as dev
+
+
+class HotPath(object):
+
+    def __init__(self, tid2idx, lengths, sites, min_len=1000, min_sig=5, tol=1e-6, delta=0.1, Delta=3,
+                 max_iter=1000, pair_capacity=0):
+        dev.require_cuda()
+        self.n_seq = int(len(lengths))
+        self.tid2idx = dev.to_device(np.asarray(tid2idx, dtype=np.int32), torch.int32)
+        self.lengths = dev.to_device(np.asarray(lengths, dtype=np.int32), torch.int32)
+        self.sites = dev.to_device(np.asarray(sites, dtype=np.int32), torch.int32)
+        self.min_len, self.min_sig = int(min_len), int(min_sig)
+        self.kr_params = dict(tol=tol, delta=delta, Delta=Delta, max_iter=max_iter)
+        self._acc = None
+        self._capacity = 0
+        self.pool = dev.BufferPool()      # outputs live in grow-only buffers reused by every run
+        if pair_capacity:
+            self._ensure_accumulator(pair_capacity)
+        self.events = None
+        self.reset()
+
+    def reset(self):
+        self.seq_map = self.signal = self.mask = self.normed = self.x = self.balanced = None
+        self.acc_info = self.kr_info = self.edge_res = None
+
+    # ---- stage events (CUDA events on the current stream, for bench.py) --------------------------
+    def enable_events(self, on=True):
+        self.events = [] if on else None
+
+    def _mark(self, name):
+        if self.events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.events.append((name, ev, time.perf_counter()))
+
+    # ---- accumulation ----------------------------------------------------------------------------
+    def _ensure_accumulator(self, n_records):
+        if self._acc is None or self._capacity < n_records:
+            self._acc = None
+            self._capacity = max(int(n_records), 1)
+            self._acc = dev.Accumulator(self.n_seq, self.tid2idx, self._capacity)
+        else:
+            self._acc.begin()
+        return self._acc
+
+    def accumulate(self, records, chunk_records=1 << 24):
+        """
+        records: CUDA tensor (used in place) or host tensor / NumPy array of packed uint64 records.
+        Host records are streamed in chunks on a side stream so the H2D copy of chunk k+1 overlaps
+        the classification of chunk k (use pinned memory for a truly asynchronous copy).
+        """
+        if not isinstance(records, torch.Tensor):
+            records = torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint64).view(np.int64))
+        n_rec = int(records.numel())
+        acc = self._ensure_accumulator(n_rec)
+        self.h2d_bytes = 0
+        self._mark('start')
+        if records.is_cuda:
+            acc.add(records)
+        else:
+            main = torch.cuda.current_stream()
+            copy_stream = torch.cuda.Stream()
+            copy_stream.wait_stream(main)
+            for lo in range(0, n_rec, chunk_records):
+                hi = min(lo + chunk_records, n_rec)
+                with torch.cuda.stream(copy_stream):
+                    d = records[lo:hi].to('cuda', non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                main.wait_event(ev)
+                d.record_stream(main)
+                acc.add(d)
+                self.h2d_bytes += (hi - lo) * 8
+        self._mark('classify')
+        self.seq_map, self.acc_info = acc.finish(symmetric=True, pool=self.pool)
+        self._mark('sort_reduce_emit')
+        return self.seq_map
+
+    # ---- mask, normalisation, balancing --------------------------------------------------------
+    def compute_mask(self, min_len=None, min_sig=None):
+        self.signal = dev.max_offdiag(self.seq_map, pool=self.pool)
+        self.mask = dev.acceptance_mask(self.lengths, self.signal, min_len or self.min_len, min_sig or self.min_sig,
+                                        pool=self.pool)
+        self._mark('mask')
+        return self.mask
+
+    def normalise(self):
+        self.normed = dev.site_norm(self.seq_map, self.sites, pool=self.pool)
+        self._mark('site_norm')
+        return self.normed
+
+    def balance(self):
+        self.x, self.kr_info = dev.kr_scale_vector(self.normed, pool=self.pool, **self.kr_params)
+        self._mark('kr')
+        self.balanced = dev.kr_apply(self.normed, self.x, pool=self.pool)
+        self._mark('kr_apply')
+        return self.balanced
+
+    def edges(self, scale=True, want_sub=False):
+        self.edge_res = dev.compress_edges(self.balanced, self.mask, want_sub=want_sub, want_edges=True, scale=scale,
+                                           pool=self.pool)
+        self._mark('compress_edges')
+        return self.edge_res
+
+    def run(self, records, to_host=False):
+        """
+        The whole path.  Returns the edge result dict (CUDA tensors, or NumPy arrays if to_host).
+        The CUDA tensors are views of the pipeline's reusable buffers: they are overwritten by the
+        next run(), so clone what must outlive it.
+        """
+        self.reset()
+        if self.events is not None:
+            self.events = []
+        self.accumulate(records)
+        self.compute_mask()
+        self.normalise()
+        self.balance()
+        res = self.edges()
+        if to_host:
+            packed = (res['u'].cpu(), res['v'].cpu(), res['w'].cpu(), res['scl'].cpu())
+            self.d2h_bytes = sum(int(t.numel()) * t.element_size() for t in packed)
+            self._mark('d2h')
+            return dict(u=packed[0].numpy(), v=packed[1].numpy(), w=packed[2].numpy(), scl=float(packed[3][0]),
+                        n_accepted=res['n_accepted'])
+        return res
+
+    def stage_ms(self):
+        """Elapsed ms per stage from the recorded events (call after a synchronize)."""
+        out = {}
+        for (_, a, _t), (name, b, _u) in zip(self.events[:-1], self.events[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+    def stage_host_ms(self):
+        """Host wall-clock ms between the same marks (launch + Python overhead, not device time)."""
+        out = {}
+        for (_, _a, t0), (name, _b, t1) in zip(self.events[:-1], self.events[1:]):
+            out[name] = out.get(name, 0.0) + (t1 - t0) * 1e3
+        return out

@@ -54,7 +54,9 @@ int64_t b3c_launch_count(void);
  * (contact_map.py:720-798), ContactMap.make_reverse_index (contact_map.py:818-832, as the
  * dense table d_tid2idx) and Sparse2DAccumulator + get_coo (sparse_utils.py:227-266).
  *
- *   begin      zero the accumulator state held in the workspace
+ *   begin      once per reference table: lay out the workspace, build the tid->index rank table
+ *              and zero the accumulator
+ *   reset      zero the accumulator for another map over the same reference table
  *   add_pairs  classify a chunk of packed records: reference-exclusion test, then the
  *              matcher bit (filter order Q12), canonicalise i<=j, count diagonal pairs
  *              directly and append off-diagonal keys (i<<32|j).  May be called many
@@ -71,6 +73,7 @@ int64_t b3c_launch_count(void);
 int64_t b3c_accum_workspace_bytes(int64_t pair_capacity, int32_t n_seq, int32_t n_refs);
 int b3c_accum_begin(void *d_ws, int64_t ws_bytes, int64_t pair_capacity, int32_t n_seq,
                     const int32_t *d_tid2idx, int32_t n_refs, void *stream);
+int b3c_accum_reset(void *d_ws, void *stream);
 int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records, void *stream);
 int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream);
 int b3c_accum_emit_csr(void *d_ws, int symmetric, int64_t *d_indptr, int32_t *d_indices,
@@ -104,8 +107,11 @@ int b3c_site_norm_f64(int32_t n, const int64_t *d_indptr, const int32_t *d_indic
  *
  *   b3c_kr_run    computes the scale vector x (float64[n]) of the symmetric CSR matrix;
  *                 zero diagonals are treated as one on the working matrix only (Q2).
- *                 h_info[0] = n_iter, [1] = zero diagonals patched, [2] = outer Newton
- *                 steps, [3] = number of SpMV launches/phases executed.
+ *                 h_info (int64[32]): [0] = n_iter, [1] = zero diagonals patched, [2] = outer
+ *                 Newton steps, [3] = SpMV phases executed, [4] = CTAs of the persistent grid,
+ *                 [5] = SM cycles of the whole kernel, [6..14] = cycles CTA 0 spent working in
+ *                 each phase (init, spmv, fix-up, residual, direction, w, step, update, scalar
+ *                 reductions), [15..23] = cycles it waited at the grid barrier after each.
  *                 mode 0 = one persistent cooperative kernel (device-side control flow).
  *   b3c_kr_scale  out[e] = x_i * (a_ij * x_j), the entries of X.T.dot(orig.dot(X))
  *                 (sparse_utils.py:223-224, Q9) on the ORIGINAL matrix.

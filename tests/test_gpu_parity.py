@@ -242,7 +242,7 @@ def test_kr_long_rows_and_empty_rows(dev):
     """Rows far longer than an SpMV tile, rows straddling tiles, and completely empty rows (Q3)."""
     from oracle import oracle
     rng = np.random.default_rng(9)
-    n = 9000
+    n = 20000
     rows = [np.full(7000, 0), np.full(5000, 1), rng.integers(2, n // 2, 60000)]
     cols = [rng.choice(n // 2, 7000, replace=False), rng.choice(n // 2, 5000, replace=False),
             rng.integers(2, n // 2, 60000)]
