@@ -46,19 +46,30 @@ SIGNATURES = {
     'b3c_accum_add_pairs': (C.c_int, [_p, _p, _i64, _p]),
     'b3c_accum_reduce': (C.c_int, [_p, _pi64, _p]),
     'b3c_accum_emit_csr': (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
-    'b3c_max_offdiag_u32': (C.c_int, [_i32, _p, _p, _p, _p, _p]),
-    'b3c_max_offdiag_f64': (C.c_int, [_i32, _p, _p, _p, _p, _p]),
+    'b3c_accum_offsets': (C.c_int, [_p, _pi64]),
+    'b3c_accum_row_hist': (C.c_int, [_p, _p, _p]),
+    'b3c_accum_route': (C.c_int, [_p, _p, _i32, _p, _i64, _p, _pi64, _p]),
+    'b3c_accum_reduce_block': (C.c_int, [_p, _p, _i64, _i32, _i32, _pi64, _p]),
+    'b3c_accum_emit_block': (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
+    'b3c_max_offdiag_u32': (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p]),
+    'b3c_max_offdiag_f64': (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p]),
     'b3c_acceptance_mask': (C.c_int, [_i32, _p, _p, _i64, _i64, _p, _p]),
-    'b3c_site_norm': (C.c_int, [_i32, _p, _p, _p, _p, _p, _p]),
-    'b3c_site_norm_f64': (C.c_int, [_i32, _p, _p, _p, _p, _p]),
+    'b3c_site_norm': (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p]),
+    'b3c_site_norm_f64': (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p]),
     'b3c_kr_workspace_bytes': (_i64, [_i32, _i64]),
     'b3c_kr_run': (C.c_int, [_i32, _i64, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _p, _p, _i64, _pi64, _p]),
-    'b3c_kr_scale': (C.c_int, [_i32, _p, _p, _p, _p, _p, _p]),
+    'b3c_krp_workspace_bytes': (_i64, [_i32, _i64]),
+    'b3c_krp_setup': (C.c_int, [_i32, _i32, _i32, _i64, _p, _p, _p, _f64, _f64, _f64, _i32, _p, _i64, _pi64, _p]),
+    'b3c_krp_phase': (C.c_int, [_p, _i32, _p]),
+    'b3c_krp_scalar': (C.c_int, [_p, _i32, _p]),
+    'b3c_krp_state': (C.c_int, [_p, _pi64, _p]),
+    'b3c_kr_scale': (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p]),
     'b3c_asymmetry_count': (C.c_int, [_i32, _p, _p, _p, _f64, _p, _pi64, _p]),
     'b3c_spmv': (C.c_int, [_i32, _i64, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]),
     'b3c_compress_workspace_bytes': (_i64, [_i32]),
-    'b3c_compress_count': (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _i64, _pi64, _p]),
-    'b3c_compress_fill': (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'b3c_compress_count': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _pi64, _p]),
+    'b3c_compress_fill': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p,
+                                    _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -629,6 +629,153 @@ __global__ void k_emit(int symmetric, int b, int32_t n_seq, const unsigned long 
     }
 }
 
+// ==== sharded accumulation (multi-GPU): route keys to the rank that owns their row ================
+// Canonical key (i<j) -> two directed keys: (i,j) for the owner of row i, (j,i) for the owner of
+// row j.  Each rank then sorts and run-length reduces the directed keys of its own row block, which
+// yields the full symmetric rows of that block directly (no mirror sort).
+constexpr int ROUTE_MAX_RANKS = 64;
+
+__device__ __forceinline__ int owner_of(int32_t row, const int32_t *s_splits, int G) {
+    int g = 0;
+    while (g + 1 < G && row >= s_splits[g + 1]) ++g;
+    return g;
+}
+
+// rowcnt[r] += number of directed keys with row r (int64 so the host side can all-reduce it)
+__global__ void k_row_hist(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ d_n, int b,
+                           unsigned long long *__restrict__ rowcnt) {
+    const int64_t n = (int64_t)*d_n;
+    const uint64_t jmask = (1ull << b) - 1ull;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[e];
+        atomicAdd(&rowcnt[k >> b], 1ull);
+        atomicAdd(&rowcnt[k & jmask], 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_route_count(const uint64_t *__restrict__ keys,
+                                                     const unsigned long long *__restrict__ d_n, int b,
+                                                     const int32_t *__restrict__ splits, int G,
+                                                     unsigned long long *__restrict__ cnt) {
+    __shared__ int32_t s_splits[ROUTE_MAX_RANKS + 1];
+    __shared__ unsigned s_cnt[ROUTE_MAX_RANKS];
+    if (threadIdx.x <= (unsigned)G) s_splits[threadIdx.x] = splits[threadIdx.x];
+    if (threadIdx.x < (unsigned)G) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t n = (int64_t)*d_n;
+    const uint64_t jmask = (1ull << b) - 1ull;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[e];
+        atomicAdd(&s_cnt[owner_of((int32_t)(k >> b), s_splits, G)], 1u);
+        atomicAdd(&s_cnt[owner_of((int32_t)(k & jmask), s_splits, G)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < (unsigned)G && s_cnt[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// base[g] = exclusive scan of cnt; cursor[g] starts at base[g]
+__global__ void k_route_bases(const unsigned long long *__restrict__ cnt, int G, unsigned long long *__restrict__ base,
+                              unsigned long long *__restrict__ cursor) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int g = 0; g < G; ++g) {
+            base[g] = run;
+            cursor[g] = run;
+            run += cnt[g];
+        }
+        base[G] = run;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_route_scatter(const uint64_t *__restrict__ keys,
+                                                       const unsigned long long *__restrict__ d_n, int b,
+                                                       const int32_t *__restrict__ splits, int G,
+                                                       unsigned long long *__restrict__ cursor,
+                                                       uint64_t *__restrict__ out) {
+    __shared__ int32_t s_splits[ROUTE_MAX_RANKS + 1];
+    __shared__ unsigned s_cnt[ROUTE_MAX_RANKS];
+    __shared__ unsigned long long s_base[ROUTE_MAX_RANKS];
+    if (threadIdx.x <= (unsigned)G) s_splits[threadIdx.x] = splits[threadIdx.x];
+    __syncthreads();
+    const int64_t n = (int64_t)*d_n;
+    const uint64_t jmask = (1ull << b) - 1ull;
+    const int64_t per_block = 256 * 8;
+    for (int64_t base = (int64_t)blockIdx.x * per_block; base < n; base += (int64_t)gridDim.x * per_block) {
+        if (threadIdx.x < (unsigned)G) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint64_t dk[16];
+        int own[16];
+        unsigned slot[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t e = base + q * 256 + threadIdx.x;
+            if (e < n) {
+                const uint64_t k = keys[e];
+                const uint64_t i = k >> b, j = k & jmask;
+                dk[2 * q] = k;
+                dk[2 * q + 1] = (j << b) | i;
+                own[2 * q] = owner_of((int32_t)i, s_splits, G);
+                own[2 * q + 1] = owner_of((int32_t)j, s_splits, G);
+                slot[2 * q] = atomicAdd(&s_cnt[own[2 * q]], 1u);
+                slot[2 * q + 1] = atomicAdd(&s_cnt[own[2 * q + 1]], 1u);
+            } else {
+                own[2 * q] = own[2 * q + 1] = -1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < (unsigned)G && s_cnt[threadIdx.x])
+            s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (own[q] >= 0) out[s_base[own[q]] + slot[q]] = dk[q];
+        __syncthreads();
+    }
+}
+
+// row block emit: unique directed keys (row in [row_lo,row_hi), col != row) + diagonal -> local CSR.
+// ptr[] is the row pointer over GLOBAL rows (k_row_ptr); indptr is local (row_hi - row_lo + 1).
+__global__ void k_block_row_len(const int64_t *__restrict__ ptr, const uint32_t *__restrict__ diag, int32_t row_lo,
+                                int32_t n_local, int64_t *__restrict__ len) {
+    for (int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; lr < n_local; lr += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = row_lo + lr;
+        len[lr] = (ptr[r + 1] - ptr[r]) + (diag[r] ? 1 : 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_emit_block(int b, int32_t row_lo, int32_t n_local,
+                                                    const uint64_t *__restrict__ uniq, const uint32_t *__restrict__ cnt,
+                                                    const uint32_t *__restrict__ diag, const int64_t *__restrict__ ptr,
+                                                    const int64_t *__restrict__ indptr, int32_t *__restrict__ indices,
+                                                    uint32_t *__restrict__ counts) {
+    const unsigned lane = lane_id();
+    const uint64_t jmask = (1ull << b) - 1ull;
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < n_local; lr += nw) {
+        const int64_t r = row_lo + lr;
+        const int64_t lo = ptr[r], hi = ptr[r + 1];
+        const uint32_t d = diag[r];
+        const int64_t out0 = indptr[lr];
+        unsigned below = 0;          // entries with col < r, counted as they stream by
+        for (int64_t e0 = lo; e0 < hi; e0 += 32) {
+            const int64_t e = e0 + lane;
+            int32_t c = 0x7fffffff;
+            if (e < hi) c = (int32_t)(uniq[e] & jmask);
+            const bool lower = c < (int32_t)r;
+            if (e < hi) {
+                const int64_t dst = out0 + (e - lo) + ((!lower && d) ? 1 : 0);
+                indices[dst] = c;
+                counts[dst] = cnt[e];
+            }
+            below += __popc(__ballot_sync(kFullMask, lower));
+        }
+        if (lane == 0 && d) {
+            indices[out0 + below] = (int32_t)r;
+            counts[out0 + below] = d;
+        }
+    }
+}
+
 template <bool A, bool B>
 static int launch_classify(const AccumState &st, const ClsParams &P, cudaStream_t s) {
     static bool attr_done = false;
@@ -847,6 +994,160 @@ int b3c_accum_emit_csr(void *d_ws, int symmetric, int64_t *d_indptr, int32_t *d_
                                        (const uint64_t *)(ws + (st.comp_in_a ? st.o_keys_a : st.o_keys_b)),
                                        (const uint32_t *)(ws + st.o_diag), (const int64_t *)(ws + st.o_up_ptr),
                                        (const int64_t *)(ws + st.o_lo_ptr), ip, d_indices, d_counts);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+// ---- sharded accumulation entry points (see bin3c_b200/dist.py) ---------------------------------------
+
+int b3c_accum_offsets(void *d_ws, int64_t *h_offsets) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    B3C_REQUIRE(h_offsets != nullptr, "null h_offsets");
+    h_offsets[0] = st.o_ctr;       // uint64[16] counters
+    h_offsets[1] = st.o_diag;      // uint32[n_seq] diagonal counts
+    h_offsets[2] = st.o_keys_a;    // uint64[cap] canonical keys after add_pairs
+    h_offsets[3] = st.cap;
+    return B3C_OK;
+}
+
+int b3c_accum_row_hist(void *d_ws, uint64_t *d_rowcnt, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    B3C_REQUIRE(d_rowcnt != nullptr, "null rowcnt");
+    char *ws = (char *)d_ws;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *ctr = (unsigned long long *)(ws + st.o_ctr);
+    k_accum_guard<<<1, 1, 0, s>>>(ctr, st.cap);
+    B3C_LAUNCH_CHECK();
+    k_row_hist<<<kNumSMs * 8, 256, 0, s>>>((const uint64_t *)(ws + st.o_keys_a), ctr + C_NKEYS, st.b,
+                                           (unsigned long long *)d_rowcnt);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_accum_route(void *d_ws, const int32_t *d_splits, int32_t n_ranks, uint64_t *d_out, int64_t out_capacity,
+                    uint64_t *d_scratch, int64_t *h_counts, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    B3C_REQUIRE(d_splits && d_out && d_scratch && h_counts, "null pointer");
+    B3C_REQUIRE(n_ranks >= 1 && n_ranks <= ROUTE_MAX_RANKS, "unsupported rank count %d", n_ranks);
+    char *ws = (char *)d_ws;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *ctr = (unsigned long long *)(ws + st.o_ctr);
+    const uint64_t *keys = (const uint64_t *)(ws + st.o_keys_a);
+    unsigned long long *cnt = (unsigned long long *)d_scratch;              // [G]
+    unsigned long long *base = cnt + ROUTE_MAX_RANKS;                       // [G+1]
+    unsigned long long *cursor = base + ROUTE_MAX_RANKS + 1;                // [G]
+    B3C_CUDA(cudaMemsetAsync(d_scratch, 0, (3 * ROUTE_MAX_RANKS + 2) * 8, s));
+    k_accum_guard<<<1, 1, 0, s>>>(ctr, st.cap);
+    B3C_LAUNCH_CHECK();
+    k_route_count<<<kNumSMs * 4, 256, 0, s>>>(keys, ctr + C_NKEYS, st.b, d_splits, n_ranks, cnt);
+    B3C_LAUNCH_CHECK();
+    k_route_bases<<<1, 32, 0, s>>>(cnt, n_ranks, base, cursor);
+    B3C_LAUNCH_CHECK();
+    unsigned long long h[ROUTE_MAX_RANKS + 1 + C_COUNT];
+    B3C_CUDA(cudaMemcpyAsync(h, base, (n_ranks + 1) * 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(h + ROUTE_MAX_RANKS + 1, ctr, C_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaStreamSynchronize(s));
+    if (h[ROUTE_MAX_RANKS + 1 + C_OVERFLOW]) {
+        set_error("pair capacity %lld exceeded by the off-diagonal keys", (long long)st.cap);
+        return B3C_ERR_CAPACITY;
+    }
+    if ((int64_t)h[n_ranks] > out_capacity) {
+        set_error("route buffer too small: %llu > %lld", h[n_ranks], (long long)out_capacity);
+        return B3C_ERR_CAPACITY;
+    }
+    k_route_scatter<<<kNumSMs * 4, 256, 0, s>>>(keys, ctr + C_NKEYS, st.b, d_splits, n_ranks, cursor, d_out);
+    B3C_LAUNCH_CHECK();
+    for (int g = 0; g <= n_ranks; ++g) h_counts[g] = (int64_t)h[g];          // exclusive offsets, [G] = total
+    // local pair counters ride along: accepted, ref_excluded, poor_match
+    h_counts[n_ranks + 1] = (int64_t)h[ROUTE_MAX_RANKS + 1 + C_ACCEPT];
+    h_counts[n_ranks + 2] = (int64_t)h[ROUTE_MAX_RANKS + 1 + C_EXCL];
+    h_counts[n_ranks + 3] = (int64_t)h[ROUTE_MAX_RANKS + 1 + C_POOR];
+    return B3C_OK;
+}
+
+int b3c_accum_reduce_block(void *d_ws, const uint64_t *d_keys, int64_t n_keys, int32_t row_lo, int32_t row_hi,
+                           int64_t *h_sizes, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    B3C_REQUIRE(h_sizes != nullptr && n_keys >= 0, "bad arguments");
+    B3C_REQUIRE(0 <= row_lo && row_lo < row_hi && row_hi <= st.n_seq, "bad row block [%d,%d)", row_lo, row_hi);
+    if (n_keys > st.cap) {
+        set_error("received %lld directed keys, accumulator capacity is %lld", (long long)n_keys, (long long)st.cap);
+        return B3C_ERR_CAPACITY;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    unsigned long long *ctr = (unsigned long long *)(ws + st.o_ctr);
+    uint64_t *ka = (uint64_t *)(ws + st.o_keys_a), *kb = (uint64_t *)(ws + st.o_keys_b);
+    uint64_t *uniq = (uint64_t *)(ws + st.o_uniq);
+    uint32_t *pos = (uint32_t *)(ws + st.o_pos), *cnt = (uint32_t *)(ws + st.o_cnt);
+    uint32_t *hist = (uint32_t *)(ws + st.o_hist);
+    int64_t *heads = (int64_t *)(ws + st.o_heads), *heads_ex = heads + RS_BLOCKS + 2;
+    int64_t *scan_tmp = (int64_t *)(ws + st.o_scan_tmp);
+    uint32_t *diag = (uint32_t *)(ws + st.o_diag);
+    int64_t *ptr = (int64_t *)(ws + st.o_up_ptr), *len = (int64_t *)(ws + st.o_len);
+    int64_t *ip = (int64_t *)(ws + st.o_indptr_f);
+    const int32_t n_local = row_hi - row_lo;
+
+    if (n_keys) B3C_CUDA(cudaMemcpyAsync(ka, d_keys, (size_t)n_keys * 8, cudaMemcpyDeviceToDevice, s));
+    const unsigned long long nk = (unsigned long long)n_keys;
+    B3C_CUDA(cudaMemcpyAsync(ctr + C_NKEYS, &nk, 8, cudaMemcpyHostToDevice, s));
+    B3C_CUDA(cudaMemsetAsync(ctr + C_NNZ_UO, 0, 3 * 8, s));       // nnz_uo, nnz_diag, weight
+    int where = 0;
+    rc = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
+    if (rc) return rc;
+    uint64_t *sorted = where ? kb : ka;
+    k_rle_count<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(heads, heads_ex, RS_BLOCKS, scan_tmp, s);
+    if (rc) return rc;
+    k_rle_write<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads_ex, uniq, pos);
+    B3C_LAUNCH_CHECK();
+    k_rle_finish<<<1, 1, 0, s>>>(heads_ex, RS_BLOCKS, ctr + C_NKEYS, pos, ctr);
+    B3C_LAUNCH_CHECK();
+    k_rle_counts<<<kNumSMs * 8, 256, 0, s>>>(pos, ctr, cnt, st.b, uniq, sorted);
+    B3C_LAUNCH_CHECK();
+    k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(uniq, ctr + C_NNZ_UO, st.b, st.n_seq, ptr);
+    B3C_LAUNCH_CHECK();
+    k_block_row_len<<<(unsigned)ceil_div(n_local, 256), 256, 0, s>>>(ptr, diag, row_lo, n_local, len);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(len, ip, n_local, scan_tmp, s);
+    if (rc) return rc;
+    int64_t nnz_local = 0;
+    B3C_CUDA(cudaMemcpyAsync(&nnz_local, ip + n_local, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaStreamSynchronize(s));
+    st.reduced = true;
+    st.nnz_uo = nnz_local;
+    h_sizes[0] = nnz_local;
+    std::lock_guard<std::mutex> g(g_mu);
+    g_states[d_ws] = st;
+    return B3C_OK;
+}
+
+int b3c_accum_emit_block(void *d_ws, int32_t row_lo, int32_t row_hi, int64_t *d_indptr, int32_t *d_indices,
+                         uint32_t *d_counts, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    B3C_REQUIRE(st.reduced, "call b3c_accum_reduce_block first");
+    B3C_REQUIRE(d_indptr != nullptr && 0 <= row_lo && row_lo < row_hi && row_hi <= st.n_seq, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    const int32_t n_local = row_hi - row_lo;
+    const int64_t *ip = (const int64_t *)(ws + st.o_indptr_f);
+    B3C_CUDA(cudaMemcpyAsync(d_indptr, ip, ((size_t)n_local + 1) * 8, cudaMemcpyDeviceToDevice, s));
+    int64_t blocks = ceil_div(n_local, 8);
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    k_emit_block<<<(unsigned)blocks, 256, 0, s>>>(st.b, row_lo, n_local, (const uint64_t *)(ws + st.o_uniq),
+                                                  (const uint32_t *)(ws + st.o_cnt), (const uint32_t *)(ws + st.o_diag),
+                                                  (const int64_t *)(ws + st.o_up_ptr), ip, d_indices, d_counts);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }

@@ -313,6 +313,8 @@ __device__ __forceinline__ void phase_dir(const KRArgs &A, bool first, double be
             double r[1] = {acc};
             block_reduce<1, 0>(r, s_red);
             if (threadIdx.x == 0) A.part[PB * A.n_chunks + c] = loc ? r[0] : 0.0;
+        } else if (threadIdx.x == 0) {
+            A.part[PB * A.n_chunks + c] = 0.0;
         }
     }
 }
@@ -607,6 +609,119 @@ __global__ void __launch_bounds__(KR_THREADS) k_spmv(KRArgs A) {
 }
 __global__ void __launch_bounds__(KR_THREADS) k_spmv_fix(KRArgs A) { phase_fix(A); }
 
+// ---- phase-at-a-time form (multi-GPU row-block driver) ------------------------------------------
+// The driver all-reduces u with SUM, so the slices a rank does not own must hold zeros.
+__device__ __forceinline__ void zero_nonlocal_u(const KRArgs &A) {
+    if (A.row_lo == 0 && A.row_hi == A.n) return;
+    KR_FOR_CHUNKS(c) {
+        if (chunk_local(A, c)) continue;
+#pragma unroll
+        for (int i = 0; i < CHUNK_RPT; ++i) {
+            const int64_t r = KR_ROW(c, i);
+            if (r < A.n) A.u[r] = 0.0;
+        }
+    }
+}
+
+enum { KRP_INIT = 0, KRP_SPMV, KRP_RESID, KRP_DIR, KRP_W, KRP_STEP, KRP_UPDATE };
+enum { KRS_OUTER_FIRST = 0, KRS_OUTER, KRS_ALPHA, KRS_DECIDE };
+enum { KR_STATE_DONE = 0, KR_STATE_INNER = 1, KR_STATE_UPDATE = 2 };
+
+__global__ void __launch_bounds__(KR_THREADS) k_krp_phase(KRArgs A, int phase) {
+    __shared__ double s_prod[SPMV_TILE];
+    __shared__ int s_ptr[SPTR_CAP + 1];
+    __shared__ double s_red[KR_WARPS * RED_MAX];
+    const KRScalars S = *A.ctl;                 // only k_krp_scalar writes the control block
+    double *ybuf[2] = {A.y0, A.y1};
+    switch (phase) {
+        case KRP_INIT:
+            phase_init(A);
+            zero_nonlocal_u(A);
+            break;
+        case KRP_SPMV:
+            phase_spmv(A, s_prod, s_ptr);
+            break;
+        case KRP_RESID:
+            phase_resid(A, s_red);
+            break;
+        case KRP_DIR:
+            phase_dir(A, S.k == 1, S.beta, ybuf[S.ysel], s_red);
+            zero_nonlocal_u(A);
+            break;
+        case KRP_W:
+            phase_w(A, s_red);
+            break;
+        case KRP_STEP:
+            phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red);
+            break;
+        case KRP_UPDATE:
+            phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]);
+            zero_nonlocal_u(A);
+            break;
+        default:
+            break;
+    }
+}
+
+// the loop control of k_kr_persistent, one decision at a time, on the (all-reduced) partials
+__global__ void __launch_bounds__(KR_THREADS) k_krp_scalar(KRArgs A, int which) {
+    __shared__ double s_red[KR_WARPS * RED_MAX];
+    KRScalars S = *A.ctl;
+    const int nc = A.n_chunks;
+    if (which == KRS_OUTER_FIRST || which == KRS_OUTER) {
+        double r[1];
+        const int ids[1] = {PA};
+        reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
+        scalar_outer(S, r[0], which == KRS_OUTER_FIRST);
+        S.n_spmv += 1;
+        if (S.rout > S.rt && S.n_iter < S.max_iter) {          // sparse_utils.py:146
+            S.outer += 1;
+            S.k = 0;
+            S.ymode = 0;
+            S.inner_tol = fmax(S.rout * S.eta * S.eta, S.rt);
+            if (S.rho_km1 > S.inner_tol) {                     // sparse_utils.py:154
+                S.k = 1;
+                S.state = KR_STATE_INNER;
+            } else {
+                S.state = KR_STATE_UPDATE;
+            }
+        } else {
+            S.state = KR_STATE_DONE;
+        }
+    } else if (which == KRS_ALPHA) {
+        double r[2];
+        const int ids[2] = {PA, PB};
+        reduce_parts<2, 0>(A.part, nc, ids, r, s_red);
+        if (S.k == 1) S.rho_km1 = r[1];
+        S.alpha = S.rho_km1 / r[0];
+        S.n_spmv += 1;
+    } else if (which == KRS_DECIDE) {
+        double r[5];
+        const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
+        reduce_parts<1, 4>(A.part, nc, ids, r, s_red);
+        bool stop = scalar_decide(S, r[1], -r[2], r[3], r[4], r[0]);
+        if (!stop && S.k >= S.max_iter + 8) {
+            S.status = B3C_ERR_NOCONV;
+            stop = true;
+        }
+        if (S.status != 0) {
+            S.state = KR_STATE_DONE;
+        } else if (stop) {
+            S.state = KR_STATE_UPDATE;
+        } else if (S.rho_km1 > S.inner_tol) {
+            S.k += 1;
+            S.beta = S.rho_km1 / S.rho_km2;
+            S.state = KR_STATE_INNER;
+        } else {
+            S.state = KR_STATE_UPDATE;
+        }
+    }
+    if (threadIdx.x == 0) *A.ctl = S;
+}
+
+static std::mutex g_krp_mu;
+static std::unordered_map<void *, KRArgs> g_krp;
+
 // ---- workspace ---------------------------------------------------------------------------------------
 struct KRLayout {
     int64_t n_tiles, o_tile_ra, o_chunk_t, o_head, o_tail, o_dfix, o_vec, o_part, o_ctl, o_timers, total;
@@ -788,6 +903,115 @@ int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_i
     B3C_LAUNCH_CHECK();
     k_spmv_fix<<<(unsigned)ceil_div(L.n_tiles, 256), 256, 0, s>>>(A);
     B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+// ---- phase API (multi-GPU row-block driver, bin3c_b200/dist.py) --------------------------------------
+
+int64_t b3c_krp_workspace_bytes(int32_t n, int64_t nnz_local) {
+    if (n <= 0 || nnz_local < 0) return B3C_ERR_ARG;
+    return kr_layout(n, nnz_local).total;
+}
+
+int b3c_krp_setup(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, const int64_t *d_indptr,
+                  const int32_t *d_indices, const double *d_data, double tol, double delta, double Delta,
+                  int32_t max_iter, void *d_ws, int64_t ws_bytes, int64_t *h_offsets, void *stream) {
+    B3C_REQUIRE(n > 0 && 0 <= row_lo && row_lo < row_hi && row_hi <= n, "bad row block [%d,%d) of %d", row_lo, row_hi, n);
+    B3C_REQUIRE(row_lo % CHUNK == 0 && (row_hi % CHUNK == 0 || row_hi == n), "row blocks must be %d-row aligned", CHUNK);
+    B3C_REQUIRE(d_indptr && d_ws && h_offsets && nnz_local >= 0, "bad arguments");
+    const KRLayout L = kr_layout(n, nnz_local);
+    if (ws_bytes < L.total) {
+        set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
+        return B3C_ERR_CAPACITY;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    KRArgs A;
+    kr_bind(A, L, (char *)d_ws, n, row_lo, row_hi, nnz_local, d_indptr, d_indices, d_data);
+    KRScalars S;
+    memset(&S, 0, sizeof(S));
+    S.tol = tol;
+    S.delta = delta;
+    S.Delta = Delta;
+    S.rt = tol * tol;
+    S.stop_tol = tol * 0.5;
+    S.eta = 0.1;
+    S.max_iter = max_iter;
+    S.state = KR_STATE_INNER;
+    B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
+    B3C_CUDA(cudaMemsetAsync(A.timers, 0, sizeof(KRTimers), s));
+    B3C_CUDA(cudaMemsetAsync(A.part, 0, (size_t)L.n_chunks * 8 * P_COUNT, s));
+    const int32_t n_local = row_hi - row_lo;
+    const int32_t n_local_chunks = (int32_t)ceil_div(n_local, CHUNK);
+    k_tile_plan<<<(unsigned)ceil_div(L.n_tiles + 1, 256), 256, 0, s>>>(n_local, d_indptr, L.n_tiles, A.tile_ra);
+    B3C_LAUNCH_CHECK();
+    k_chunk_plan<<<(unsigned)ceil_div(n_local_chunks + 1, 256), 256, 0, s>>>(n_local_chunks, L.n_tiles, A.tile_ra,
+                                                                            A.chunk_t);
+    B3C_LAUNCH_CHECK();
+    {
+        int64_t blocks = ceil_div(n_local, KR_WARPS);
+        if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+        k_diag_fix<<<(unsigned)blocks, KR_THREADS, 0, s>>>(row_lo, row_hi, d_indptr, d_indices, d_data, A.dfix, A.ctl);
+        B3C_LAUNCH_CHECK();
+    }
+    h_offsets[0] = L.o_vec + (int64_t)n * 8 * 8;        // u: float64[n]
+    h_offsets[1] = L.o_vec;                             // x: float64[n]
+    h_offsets[2] = L.o_part;                            // partials: float64[7][n_chunks]
+    h_offsets[3] = L.n_chunks;
+    h_offsets[4] = L.o_ctl;
+    std::lock_guard<std::mutex> g(g_krp_mu);
+    g_krp[d_ws] = A;
+    return B3C_OK;
+}
+
+static int krp_get(void *ws, KRArgs *A) {
+    std::lock_guard<std::mutex> g(g_krp_mu);
+    auto it = g_krp.find(ws);
+    if (it == g_krp.end()) {
+        set_error("workspace %p has no KR plan: call b3c_krp_setup first", ws);
+        return B3C_ERR_ARG;
+    }
+    *A = it->second;
+    return B3C_OK;
+}
+
+int b3c_krp_phase(void *d_ws, int32_t phase, void *stream) {
+    KRArgs A;
+    int rc = krp_get(d_ws, &A);
+    if (rc) return rc;
+    B3C_REQUIRE(phase >= KRP_INIT && phase <= KRP_UPDATE, "unknown phase %d", phase);
+    unsigned grid;
+    if (phase == KRP_SPMV) grid = spmv_grid(A.n_tiles);
+    else grid = (unsigned)(A.n_chunks < kNumSMs * 4 ? A.n_chunks : kNumSMs * 4);
+    k_krp_phase<<<grid, KR_THREADS, 0, (cudaStream_t)stream>>>(A, phase);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_krp_scalar(void *d_ws, int32_t which, void *stream) {
+    KRArgs A;
+    int rc = krp_get(d_ws, &A);
+    if (rc) return rc;
+    B3C_REQUIRE(which >= KRS_OUTER_FIRST && which <= KRS_DECIDE, "unknown scalar step %d", which);
+    k_krp_scalar<<<1, KR_THREADS, 0, (cudaStream_t)stream>>>(A, which);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_krp_state(void *d_ws, int64_t *h_state, void *stream) {
+    KRArgs A;
+    int rc = krp_get(d_ws, &A);
+    if (rc) return rc;
+    B3C_REQUIRE(h_state != nullptr, "null h_state");
+    KRScalars S;
+    B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    B3C_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    h_state[0] = S.state;
+    h_state[1] = S.status;
+    h_state[2] = S.n_iter;
+    h_state[3] = S.k;
+    h_state[4] = S.outer;
+    h_state[5] = S.n_spmv;
+    h_state[6] = S.zero_diag;
     return B3C_OK;
 }
 

@@ -16,7 +16,8 @@ static inline unsigned row_grid(int32_t n) {
 
 // ---- max_offdiag (sparse_utils.py:269-281) ----------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(ROW_THREADS) k_max_offdiag(int32_t n, const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(ROW_THREADS) k_max_offdiag(int32_t n, int32_t row_lo,
+                                                             const int64_t *__restrict__ indptr,
                                                              const int32_t *__restrict__ indices,
                                                              const T *__restrict__ val, T *__restrict__ out) {
     const unsigned lane = lane_id();
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_max_offdiag(int32_t n, const in
         T m = T(0);     // the zeroed diagonal is always a member of the column
         for (int64_t e = lo + lane; e < hi; e += 32) {
             const T v = val[e];
-            if (indices[e] != (int32_t)r && v > m) m = v;
+            if (indices[e] != (int32_t)r + row_lo && v > m) m = v;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -46,7 +47,8 @@ __global__ void k_accept_mask(int32_t n, const int32_t *__restrict__ len, const 
 
 // ---- site normalisation (contact_map.py:1103-1108, 110-113) ---------------------------------
 template <typename T>
-__global__ void __launch_bounds__(ROW_THREADS) k_site_norm(int32_t n, const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(ROW_THREADS) k_site_norm(int32_t n, int32_t row_lo,
+                                                           const int64_t *__restrict__ indptr,
                                                            const int32_t *__restrict__ indices,
                                                            const T *in, const int32_t *__restrict__ sites,
                                                            double *out) {   // in may alias out (in-place f64 form)
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_site_norm(int32_t n, const int6
     const int64_t nw = (int64_t)gridDim.x * ROW_WARPS;
     for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
         const int64_t lo = indptr[r], hi = indptr[r + 1];
-        const int32_t sr = sites[r];
+        const int32_t sr = sites[r + row_lo];
         const double si = sr == 0 ? 1.0 : (double)sr;                 // zero sites count as one (Q6)
         for (int64_t e = lo + lane; e < hi; e += 32) {
             const int32_t sc = __ldg(sites + indices[e]);
@@ -67,7 +69,8 @@ __global__ void __launch_bounds__(ROW_THREADS) k_site_norm(int32_t n, const int6
 }
 
 // ---- diag(x).A.diag(x) (sparse_utils.py:223-224) ----------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS) k_kr_scale(int32_t n, const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(ROW_THREADS) k_kr_scale(int32_t n, int32_t row_lo,
+                                                          const int64_t *__restrict__ indptr,
                                                           const int32_t *__restrict__ indices,
                                                           const double *__restrict__ a, const double *__restrict__ x,
                                                           double *__restrict__ out) {
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_kr_scale(int32_t n, const int64
     const int64_t nw = (int64_t)gridDim.x * ROW_WARPS;
     for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
         const int64_t lo = indptr[r], hi = indptr[r + 1];
-        const double xi = x[r];
+        const double xi = x[r + row_lo];
         for (int64_t e = lo + lane; e < hi; e += 32)
             out[e] = __dmul_rn(xi, __dmul_rn(a[e], __ldg(x + indices[e])));     // x_i * (a_ij * x_j), Q9
     }
@@ -140,7 +143,8 @@ __global__ void k_newidx(int32_t n, const uint8_t *__restrict__ mask, const int6
 }
 
 // per OLD row: kept entries, kept upper-triangle entries (edges), running max of kept values
-__global__ void __launch_bounds__(ROW_THREADS) k_compress_count(int32_t n, const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(ROW_THREADS) k_compress_count(int32_t n, int32_t row_lo,
+                                                                const int64_t *__restrict__ indptr,
                                                                 const int32_t *__restrict__ indices,
                                                                 const double *__restrict__ data,
                                                                 const uint8_t *__restrict__ mask,
@@ -151,13 +155,13 @@ __global__ void __launch_bounds__(ROW_THREADS) k_compress_count(int32_t n, const
     double wmax = 0.0;
     for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
         unsigned k = 0, ed = 0;
-        if (mask[r]) {
+        if (mask[r + row_lo]) {
             const int64_t lo = indptr[r], hi = indptr[r + 1];
             for (int64_t e = lo + lane; e < hi; e += 32) {
                 const int32_t c = indices[e];
                 if (__ldg(mask + c)) {
                     ++k;
-                    ed += (c >= (int32_t)r) ? 1u : 0u;
+                    ed += (c >= (int32_t)r + row_lo) ? 1u : 0u;
                     if (data) wmax = fmax(wmax, data[e]);
                 }
             }
@@ -175,16 +179,16 @@ __global__ void __launch_bounds__(ROW_THREADS) k_compress_count(int32_t n, const
 }
 
 __global__ void __launch_bounds__(ROW_THREADS) k_compress_fill(
-    int32_t n, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+    int32_t n, int32_t row_lo, const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
     const double *__restrict__ data, const uint8_t *__restrict__ mask, const int32_t *__restrict__ newidx,
     const int64_t *__restrict__ kept_ex, const int64_t *__restrict__ edge_ex,
-    const int64_t *__restrict__ n_accepted, const unsigned long long *__restrict__ vmax, int scale,
+    const int64_t *__restrict__ n_accepted, const double *__restrict__ vmax, int scale,
     int64_t *__restrict__ sub_indptr,
     int32_t *__restrict__ sub_indices, double *__restrict__ sub_data, int32_t *__restrict__ eu,
     int32_t *__restrict__ ev, double *__restrict__ ew, double *__restrict__ scl_out) {
     const unsigned lane = lane_id(), lt = lanemask_lt();
     const int64_t nw = (int64_t)gridDim.x * ROW_WARPS;
-    const double vm = __longlong_as_double((long long)*vmax);
+    const double vm = *vmax;
     const double scl = scale ? __ddiv_rn(1.0, vm) : 1.0;                 // cluster.py:316
     if (blockIdx.x == 0 && threadIdx.x == 0 && scl_out) *scl_out = scl;
     for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r <= n; r += nw) {
@@ -193,8 +197,8 @@ __global__ void __launch_bounds__(ROW_THREADS) k_compress_fill(
             if (lane == 0 && sub_indptr) sub_indptr[*n_accepted] = kept_ex[n];
             continue;
         }
-        if (!mask[r]) continue;
-        const int32_t nr = newidx[r];
+        if (!mask[r + row_lo]) continue;
+        const int32_t nr = newidx[r + row_lo];
         const int64_t lo = indptr[r], hi = indptr[r + 1];
         int64_t kbase = kept_ex[r], ebase = edge_ex[r];
         if (lane == 0 && sub_indptr) sub_indptr[nr] = kbase;
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_compress_fill(
                 c = indices[e];
                 keep = __ldg(mask + c) != 0;
             }
-            const bool is_edge = keep && c >= (int32_t)r;
+            const bool is_edge = keep && c >= (int32_t)r + row_lo;
             const unsigned mk = __ballot_sync(kFullMask, keep);
             const unsigned me = __ballot_sync(kFullMask, is_edge);
             if (keep) {
@@ -236,20 +240,20 @@ using namespace b3c;
 
 extern "C" {
 
-int b3c_max_offdiag_u32(int32_t n, const int64_t *d_indptr, const int32_t *d_indices, const uint32_t *d_counts,
-                        uint32_t *d_signal, void *stream) {
-    B3C_REQUIRE(n > 0 && d_indptr && d_signal, "bad arguments");
-    k_max_offdiag<uint32_t><<<row_grid(n), ROW_THREADS, 0, (cudaStream_t)stream>>>(n, d_indptr, d_indices, d_counts,
-                                                                                  d_signal);
+int b3c_max_offdiag_u32(int32_t n_local, int32_t row_lo, const int64_t *d_indptr, const int32_t *d_indices,
+                        const uint32_t *d_counts, uint32_t *d_signal, void *stream) {
+    B3C_REQUIRE(n_local > 0 && row_lo >= 0 && d_indptr && d_signal, "bad arguments");
+    k_max_offdiag<uint32_t><<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        n_local, row_lo, d_indptr, d_indices, d_counts, d_signal);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }
 
-int b3c_max_offdiag_f64(int32_t n, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
-                        double *d_signal, void *stream) {
-    B3C_REQUIRE(n > 0 && d_indptr && d_signal, "bad arguments");
-    k_max_offdiag<double><<<row_grid(n), ROW_THREADS, 0, (cudaStream_t)stream>>>(n, d_indptr, d_indices, d_data,
-                                                                                d_signal);
+int b3c_max_offdiag_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr, const int32_t *d_indices,
+                        const double *d_data, double *d_signal, void *stream) {
+    B3C_REQUIRE(n_local > 0 && row_lo >= 0 && d_indptr && d_signal, "bad arguments");
+    k_max_offdiag<double><<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        n_local, row_lo, d_indptr, d_indices, d_data, d_signal);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }
@@ -263,28 +267,29 @@ int b3c_acceptance_mask(int32_t n, const int32_t *d_lengths, const uint32_t *d_s
     return B3C_OK;
 }
 
-int b3c_site_norm(int32_t n, const int64_t *d_indptr, const int32_t *d_indices, const uint32_t *d_counts,
-                  const int32_t *d_sites, double *d_out, void *stream) {
-    B3C_REQUIRE(n > 0 && d_indptr && d_sites && d_out, "bad arguments");
-    k_site_norm<uint32_t><<<row_grid(n), ROW_THREADS, 0, (cudaStream_t)stream>>>(n, d_indptr, d_indices, d_counts,
-                                                                                d_sites, d_out);
+int b3c_site_norm(int32_t n_local, int32_t row_lo, const int64_t *d_indptr, const int32_t *d_indices,
+                  const uint32_t *d_counts, const int32_t *d_sites, double *d_out, void *stream) {
+    B3C_REQUIRE(n_local > 0 && row_lo >= 0 && d_indptr && d_sites && d_out, "bad arguments");
+    k_site_norm<uint32_t><<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        n_local, row_lo, d_indptr, d_indices, d_counts, d_sites, d_out);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }
 
-int b3c_site_norm_f64(int32_t n, const int64_t *d_indptr, const int32_t *d_indices, double *d_data,
-                      const int32_t *d_sites, void *stream) {
-    B3C_REQUIRE(n > 0 && d_indptr && d_sites && d_data, "bad arguments");
-    k_site_norm<double><<<row_grid(n), ROW_THREADS, 0, (cudaStream_t)stream>>>(n, d_indptr, d_indices, d_data,
-                                                                              d_sites, d_data);
+int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr, const int32_t *d_indices,
+                      double *d_data, const int32_t *d_sites, void *stream) {
+    B3C_REQUIRE(n_local > 0 && row_lo >= 0 && d_indptr && d_sites && d_data, "bad arguments");
+    k_site_norm<double><<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        n_local, row_lo, d_indptr, d_indices, d_data, d_sites, d_data);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }
 
-int b3c_kr_scale(int32_t n, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
-                 const double *d_x, double *d_out, void *stream) {
-    B3C_REQUIRE(n > 0 && d_indptr && d_x && d_out, "bad arguments");
-    k_kr_scale<<<row_grid(n), ROW_THREADS, 0, (cudaStream_t)stream>>>(n, d_indptr, d_indices, d_data, d_x, d_out);
+int b3c_kr_scale(int32_t n_local, int32_t row_lo, const int64_t *d_indptr, const int32_t *d_indices,
+                 const double *d_data, const double *d_x, double *d_out, void *stream) {
+    B3C_REQUIRE(n_local > 0 && row_lo >= 0 && d_indptr && d_x && d_out, "bad arguments");
+    k_kr_scale<<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(n_local, row_lo, d_indptr, d_indices,
+                                                                            d_data, d_x, d_out);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }
@@ -307,10 +312,11 @@ int64_t b3c_compress_workspace_bytes(int32_t n) {
     return compress_layout(n).total;
 }
 
-int b3c_compress_count(int32_t n, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
-                       const uint8_t *d_mask, int32_t *d_newidx, void *d_ws, int64_t ws_bytes, int64_t *h_out,
-                       void *stream) {
-    B3C_REQUIRE(n > 0 && d_indptr && d_mask && d_newidx && d_ws && h_out, "bad arguments");
+int b3c_compress_count(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_indptr,
+                       const int32_t *d_indices, const double *d_data, const uint8_t *d_mask, int32_t *d_newidx,
+                       void *d_ws, int64_t ws_bytes, double *d_vmax, int64_t *h_out, void *stream) {
+    B3C_REQUIRE(n > 0 && n_local > 0 && row_lo >= 0 && row_lo + n_local <= n, "bad row block");
+    B3C_REQUIRE(d_indptr && d_mask && d_newidx && d_ws && d_vmax && h_out, "null pointer");
     const CompressWs w = compress_layout(n);
     if (ws_bytes < w.total) {
         set_error("compress workspace too small: %lld < %lld", (long long)ws_bytes, (long long)w.total);
@@ -322,42 +328,47 @@ int b3c_compress_count(int32_t n, const int64_t *d_indptr, const int32_t *d_indi
     int64_t *kept = (int64_t *)(ws + w.o_kept), *kept_ex = (int64_t *)(ws + w.o_kept_ex);
     int64_t *edge = (int64_t *)(ws + w.o_edge), *edge_ex = (int64_t *)(ws + w.o_edge_ex);
     int64_t *scan = (int64_t *)(ws + w.o_scan);
-    unsigned long long *vmax = (unsigned long long *)(ws + w.o_max);
-    B3C_CUDA(cudaMemsetAsync(vmax, 0, 64, s));
+    B3C_CUDA(cudaMemsetAsync(d_vmax, 0, 8, s));
     const unsigned g = (unsigned)ceil_div(n, 256);
+    // gapless ids over the WHOLE mask (every rank computes the same table)
     k_mask_flags<<<g, 256, 0, s>>>(n, d_mask, flag);
     B3C_LAUNCH_CHECK();
     int rc = scan_exclusive_i64(flag, nidx, n, scan, s);
     if (rc) return rc;
     k_newidx<<<g, 256, 0, s>>>(n, d_mask, nidx, d_newidx);
     B3C_LAUNCH_CHECK();
-    k_compress_count<<<row_grid(n), ROW_THREADS, 0, s>>>(n, d_indptr, d_indices, d_data, d_mask, kept, edge, vmax);
+    // non-negative doubles order like their bit patterns, so the running maximum is kept as bits
+    k_compress_count<<<row_grid(n_local), ROW_THREADS, 0, s>>>(n_local, row_lo, d_indptr, d_indices, d_data, d_mask,
+                                                               kept, edge, (unsigned long long *)d_vmax);
     B3C_LAUNCH_CHECK();
-    rc = scan_exclusive_i64(kept, kept_ex, n, scan, s);
+    rc = scan_exclusive_i64(kept, kept_ex, n_local, scan, s);
     if (rc) return rc;
-    rc = scan_exclusive_i64(edge, edge_ex, n, scan, s);
+    rc = scan_exclusive_i64(edge, edge_ex, n_local, scan, s);
     if (rc) return rc;
     B3C_CUDA(cudaMemcpyAsync(&h_out[0], nidx + n, 8, cudaMemcpyDeviceToHost, s));
-    B3C_CUDA(cudaMemcpyAsync(&h_out[1], kept_ex + n, 8, cudaMemcpyDeviceToHost, s));
-    B3C_CUDA(cudaMemcpyAsync(&h_out[2], edge_ex + n, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(&h_out[1], kept_ex + n_local, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(&h_out[2], edge_ex + n_local, 8, cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaStreamSynchronize(s));
     return B3C_OK;
 }
 
-int b3c_compress_fill(int32_t n, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
-                      const uint8_t *d_mask, const int32_t *d_newidx, void *d_ws, int scale,
+int b3c_compress_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_indptr,
+                      const int32_t *d_indices, const double *d_data, const uint8_t *d_mask,
+                      const int32_t *d_newidx, void *d_ws, const double *d_vmax, int scale,
                       int64_t *d_sub_indptr, int32_t *d_sub_indices, double *d_sub_data, int32_t *d_edge_u,
                       int32_t *d_edge_v, double *d_edge_w, double *d_scl, void *stream) {
-    B3C_REQUIRE(n > 0 && d_indptr && d_data && d_mask && d_newidx && d_ws, "bad arguments");
+    B3C_REQUIRE(n > 0 && n_local > 0 && row_lo >= 0 && row_lo + n_local <= n, "bad row block");
+    B3C_REQUIRE(d_indptr && d_data && d_mask && d_newidx && d_ws && d_vmax, "null pointer");
     B3C_REQUIRE((d_sub_indices == nullptr) == (d_sub_data == nullptr), "sub_indices/sub_data must come together");
+    B3C_REQUIRE(d_sub_indptr == nullptr || (row_lo == 0 && n_local == n),
+                "the compressed matrix is only produced for a whole matrix, not a row block");
     B3C_REQUIRE((d_edge_u == nullptr) == (d_edge_v == nullptr) && (d_edge_u == nullptr) == (d_edge_w == nullptr),
                 "edge arrays must come together");
     const CompressWs w = compress_layout(n);
     char *ws = (char *)d_ws;
-    k_compress_fill<<<row_grid(n + 1), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-        n, d_indptr, d_indices, d_data, d_mask, d_newidx, (const int64_t *)(ws + w.o_kept_ex),
-        (const int64_t *)(ws + w.o_edge_ex), (const int64_t *)(ws + w.o_newidx64) + n,
-        (const unsigned long long *)(ws + w.o_max), scale, d_sub_indptr,
+    k_compress_fill<<<row_grid(n_local + 1), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        n_local, row_lo, d_indptr, d_indices, d_data, d_mask, d_newidx, (const int64_t *)(ws + w.o_kept_ex),
+        (const int64_t *)(ws + w.o_edge_ex), (const int64_t *)(ws + w.o_newidx64) + n, d_vmax, scale, d_sub_indptr,
         d_sub_indices, d_sub_data, d_edge_u, d_edge_v, d_edge_w, d_scl);
     B3C_LAUNCH_CHECK();
     return B3C_OK;

@@ -73,12 +73,19 @@ def to_device(a, dtype=None, non_blocking=False):
 class DeviceCSR(object):
     """CSR on the device: int64 indptr[n+1], int32 indices[nnz], data[nnz] (int32 bits of uint32 counts, or float64)."""
 
-    def __init__(self, n, indptr, indices, data, counts=False):
-        self.n = int(n)
+    def __init__(self, n, indptr, indices, data, counts=False, row_lo=0, n_total=None):
+        self.n = int(n)                # rows held here (a whole matrix, or a row block of one)
         self.indptr = indptr
         self.indices = indices
         self.data = data
         self.counts = counts           # True: data holds uint32 counts (stored in an int32 tensor)
+        self.row_lo = int(row_lo)      # global index of the first row
+        self.n_total = int(n_total) if n_total is not None else self.n     # columns / global rows
+
+    def like(self, data, counts=False):
+        """Same structure, other values."""
+        return DeviceCSR(self.n, self.indptr, self.indices, data, counts=counts, row_lo=self.row_lo,
+                         n_total=self.n_total)
 
     @property
     def nnz(self):
@@ -173,7 +180,7 @@ def max_offdiag(csr, pool=None):
     fn = lib.b3c_max_offdiag_u32 if csr.counts else lib.b3c_max_offdiag_f64
     if not csr.counts:
         assert csr.data.dtype == torch.float64
-    check(fn(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(out), _stream()))
+    check(fn(csr.n, csr.row_lo, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(out), _stream()))
     return out
 
 
@@ -188,10 +195,11 @@ def site_norm(csr, sites, pool=None):
     """counts (uint32) or float64 matrix -> float64 matrix scaled by 1/(s_i*s_j); float input is scaled in place."""
     if csr.counts:
         out = _alloc(pool, 'normed', csr.nnz, torch.float64)
-        check(lib.b3c_site_norm(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites), _ptr(out),
+        check(lib.b3c_site_norm(csr.n, csr.row_lo, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites),
+                                _ptr(out), _stream()))
+        return csr.like(out)
+    check(lib.b3c_site_norm_f64(csr.n, csr.row_lo, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites),
                                 _stream()))
-        return DeviceCSR(csr.n, csr.indptr, csr.indices, out)
-    check(lib.b3c_site_norm_f64(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites), _stream()))
     return csr
 
 
@@ -232,8 +240,9 @@ def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000, pool=None)
 def kr_apply(csr, x, pool=None):
     """diag(x) . A . diag(x) entry-wise (sparse_utils.py:223-224)."""
     out = _alloc(pool, 'balanced', csr.nnz, torch.float64)
-    check(lib.b3c_kr_scale(csr.n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(x), _ptr(out), _stream()))
-    return DeviceCSR(csr.n, csr.indptr, csr.indices, out)
+    check(lib.b3c_kr_scale(csr.n, csr.row_lo, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(x), _ptr(out),
+                           _stream()))
+    return csr.like(out)
 
 
 def asymmetry_count(csr, tol):
@@ -259,19 +268,26 @@ def spmv(csr, u, y=None, ws=None, prepared=False):
 # compress + edge weighting
 # --------------------------------------------------------------------------------------
 
-def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True, pool=None):
+def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True, pool=None, reduce_max=None):
     """
-    Drop rejected contigs and produce the compressed matrix and/or the weighted edge list.
+    Drop rejected contigs and produce the compressed matrix and/or the weighted edge list of a
+    matrix or row block.  `mask` covers all csr.n_total contigs.  `reduce_max(tensor)` lets a
+    multi-GPU driver all-reduce the block maximum before the weights are scaled.
     Returns dict(n_accepted, sub=DeviceCSR|None, u, v, w, scl) with CUDA tensors.
     """
     assert csr.data.dtype == torch.float64
-    n = csr.n
+    n, nl = csr.n_total, csr.n
+    whole = (csr.row_lo == 0 and nl == n)
+    assert whole or not want_sub, 'the compressed matrix is only produced for a whole matrix'
     nbytes = lib.b3c_compress_workspace_bytes(n)
     ws = _alloc(pool, 'compress_ws', nbytes, torch.uint8)
     newidx = _alloc(pool, 'newidx', n, torch.int32)
+    vmax = _alloc(pool, 'vmax', 1, torch.float64)
     h = (C.c_int64 * 4)()
-    check(lib.b3c_compress_count(n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask), _ptr(newidx),
-                                 _ptr(ws), ws.numel(), h, _stream()))
+    check(lib.b3c_compress_count(n, csr.row_lo, nl, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask),
+                                 _ptr(newidx), _ptr(ws), ws.numel(), _ptr(vmax), h, _stream()))
+    if reduce_max is not None:
+        reduce_max(vmax)
     n_acc, n_kept, n_edges = int(h[0]), int(h[1]), int(h[2])
     sub_indptr = sub_indices = sub_data = eu = ev = ew = None
     if want_sub:
@@ -283,9 +299,9 @@ def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True, pool=N
         ev = _alloc(pool, 'edge_v', n_edges, torch.int32)
         ew = _alloc(pool, 'edge_w', n_edges, torch.float64)
     scl = _alloc(pool, 'scl', 1, torch.float64)
-    check(lib.b3c_compress_fill(n, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask), _ptr(newidx),
-                                _ptr(ws), 1 if scale else 0, _ptr(sub_indptr), _ptr(sub_indices), _ptr(sub_data),
-                                _ptr(eu), _ptr(ev), _ptr(ew), _ptr(scl), _stream()))
+    check(lib.b3c_compress_fill(n, csr.row_lo, nl, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask),
+                                _ptr(newidx), _ptr(ws), _ptr(vmax), 1 if scale else 0, _ptr(sub_indptr),
+                                _ptr(sub_indices), _ptr(sub_data), _ptr(eu), _ptr(ev), _ptr(ew), _ptr(scl), _stream()))
     sub = DeviceCSR(n_acc, sub_indptr, sub_indices, sub_data) if want_sub else None
     return dict(n_accepted=n_acc, n_kept=n_kept, n_edges=n_edges, sub=sub, u=eu, v=ev, w=ew, scl=scl, newidx=newidx)
 

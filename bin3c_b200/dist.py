@@ -1,0 +1,426 @@
+"""
+Multi-GPU driver of the hot path: one process per GPU, torch.distributed
+(NCCL over NVLink / NVSwitch) for the exchanges, the C-ABI kernels for all arithmetic.
+
+  accumulation   pair records are sharded by chunk (each rank classifies its own records).  Row
+                 ranges are cut so that every rank owns about the same number of matrix entries
+                 (all-reduced row histogram, 1024-row aligned).  Every canonical key (i<j) becomes
+                 the directed keys (i,j) and (j,i), each routed to the owner of its row with ONE
+                 all-to-all; the diagonal counts are all-reduced.  Each rank then sorts and
+                 run-length reduces what it received: the result is its row block of the full
+                 symmetric matrix, with exact integer counts whatever the number of ranks.
+  mask / norm    per row block; the mask slices are combined with an all-reduce.
+  KR             row block per rank; per SpMV the vector u is assembled with an all-reduce (the
+                 slices a rank does not own are zero, so SUM is exact), the fixed-shape chunk
+                 partials of the dot products / minima are all-reduced, and the loop control runs
+                 on the device from those partials (b3c_krp_*): every rank takes the same branches.
+  compress/edges per row block; the scale 1/max needs one all-reduce(MAX).
+
+The collective layer (`Comm`) and the per-rank compute layer (`engine`) are separate so the host
+logic can be exercised on CPU with the gloo backend (tests/test_dist_gloo.py injects a NumPy
+engine); the product engine is CudaEngine and has no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+CHUNK = 1024          # row alignment of KR row blocks (kr.cu: CHUNK)
+
+KRP_INIT, KRP_SPMV, KRP_RESID, KRP_DIR, KRP_W, KRP_STEP, KRP_UPDATE = range(7)
+KRS_OUTER_FIRST, KRS_OUTER, KRS_ALPHA, KRS_DECIDE = range(4)
+STATE_DONE, STATE_INNER, STATE_UPDATE = 0, 1, 2
+PA, PB, PC, PMIN, PNEGMAX, PG1, PG2 = range(7)
+
+
+# ------------------------------------------------------------------------------------------------
+# pure host logic
+# ------------------------------------------------------------------------------------------------
+
+def balanced_row_splits(row_weight, n_ranks, align=CHUNK):
+    """
+    Cut [0, n) into n_ranks contiguous row ranges of about equal total weight, boundaries rounded
+    to multiples of `align` (the last boundary is n).  Ranges may be empty when n is small.
+    Returns int32[n_ranks + 1].
+    """
+    w = np.asarray(row_weight, dtype=np.float64)
+    n = len(w)
+    cum = np.concatenate([[0.0], np.cumsum(w + 1e-9)])          # strictly increasing
+    targets = cum[-1] * np.arange(1, n_ranks) / n_ranks
+    cuts = np.searchsorted(cum, targets, side='left')
+    cuts = (np.round(cuts / float(align)) * align).astype(np.int64)
+    cuts = np.clip(cuts, 0, (n // align) * align)
+    splits = np.concatenate([[0], np.maximum.accumulate(cuts), [n]]).astype(np.int32)
+    return splits
+
+
+class Comm(object):
+    """The collectives the driver needs; world size 1 short-circuits everything."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.world = dist.get_world_size(group) if self.on else 1
+
+    def all_reduce(self, t, op='sum'):
+        if self.world > 1:
+            ops = {'sum': dist.ReduceOp.SUM, 'min': dist.ReduceOp.MIN, 'max': dist.ReduceOp.MAX}
+            dist.all_reduce(t, op=ops[op], group=self.group)
+        return t
+
+    def exchange_counts(self, send_counts):
+        """send_counts[g] = elements this rank sends to g  ->  elements it receives from each g."""
+        if self.world == 1:
+            return list(send_counts)
+        dev = 'cuda' if dist.get_backend(self.group) == 'nccl' else 'cpu'
+        s = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        r = torch.empty_like(s)
+        dist.all_to_all_single(r, s, group=self.group)
+        return [int(v) for v in r.cpu()]
+
+    def all_to_all_v(self, send, send_counts, recv_counts):
+        if self.world == 1:
+            return send[:send_counts[0]]
+        recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send[:int(sum(send_counts))], output_split_sizes=list(recv_counts),
+                               input_split_sizes=list(send_counts), group=self.group)
+        return recv
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+
+# ------------------------------------------------------------------------------------------------
+# the product engine: everything a rank computes, through the C ABI
+# ------------------------------------------------------------------------------------------------
+
+class CudaEngine(object):
+
+    def __init__(self, tid2idx, lengths, sites, pair_capacity):
+        from . import device as dev
+        self.dev = dev
+        dev.require_cuda()
+        self.lib, self.check = dev.lib, dev.check
+        self.n = int(len(lengths))
+        self.tid2idx = dev.to_device(np.asarray(tid2idx, dtype=np.int32), torch.int32)
+        self.lengths = dev.to_device(np.asarray(lengths, dtype=np.int32), torch.int32)
+        self.sites = dev.to_device(np.asarray(sites, dtype=np.int32), torch.int32)
+        self.acc = dev.Accumulator(self.n, self.tid2idx, pair_capacity)
+        offs = (C.c_int64 * 4)()
+        self.check(self.lib.b3c_accum_offsets(dev._ptr(self.acc.ws), offs))
+        self._o_diag = int(offs[1])
+        self.pool = dev.BufferPool()
+        self.scratch = torch.zeros(256, dtype=torch.int64, device='cuda')
+        self.kr_ws = None
+
+    # ---- accumulation ------------------------------------------------------------------------
+    def classify(self, records):
+        self.acc.begin()
+        self.acc.add(records)
+
+    def row_hist(self):
+        dev = self.dev
+        h = self.pool.get('rowcnt', self.n, torch.int64)
+        h.zero_()
+        self.check(self.lib.b3c_accum_row_hist(dev._ptr(self.acc.ws), dev._ptr(h), dev._stream()))
+        return h
+
+    def diag_counts(self):
+        """int32 view of the accumulator's diagonal counts (to be all-reduced in place)."""
+        return self.acc.ws[self._o_diag:self._o_diag + 4 * self.n].view(torch.int32)
+
+    def route(self, splits):
+        dev = self.dev
+        G = len(splits) - 1
+        d_splits = dev.to_device(np.asarray(splits, dtype=np.int32), torch.int32)
+        out = self.pool.get('route_out', 2 * self.acc.capacity, torch.int64)
+        h = (C.c_int64 * (G + 8))()
+        self.check(self.lib.b3c_accum_route(dev._ptr(self.acc.ws), dev._ptr(d_splits), G, dev._ptr(out), out.numel(),
+                                            dev._ptr(self.scratch), h, dev._stream()))
+        offs = [int(h[g]) for g in range(G + 1)]
+        counters = dict(accepted=int(h[G + 1]), ref_excluded=int(h[G + 2]), poor_match=int(h[G + 3]))
+        return out, [offs[g + 1] - offs[g] for g in range(G)], counters
+
+    def build_block(self, keys, row_lo, row_hi):
+        dev = self.dev
+        sizes = (C.c_int64 * 8)()
+        n_keys = int(keys.numel())
+        self.check(self.lib.b3c_accum_reduce_block(dev._ptr(self.acc.ws), dev._ptr(keys) if n_keys else None, n_keys,
+                                                   row_lo, row_hi, sizes, dev._stream()))
+        nnz = int(sizes[0])
+        nl = row_hi - row_lo
+        indptr = self.pool.get('blk_indptr', nl + 1, torch.int64)
+        indices = self.pool.get('blk_indices', nnz, torch.int32)
+        counts = self.pool.get('blk_counts', nnz, torch.int32)
+        self.check(self.lib.b3c_accum_emit_block(dev._ptr(self.acc.ws), row_lo, row_hi, dev._ptr(indptr),
+                                                 dev._ptr(indices), dev._ptr(counts), dev._stream()))
+        return dev.DeviceCSR(nl, indptr, indices, counts, counts=True, row_lo=row_lo, n_total=self.n)
+
+    # ---- mask / norm ---------------------------------------------------------------------------
+    def block_mask(self, csr, min_len, min_sig):
+        dev = self.dev
+        sig = dev.max_offdiag(csr, pool=self.pool)
+        return dev.acceptance_mask(self.lengths[csr.row_lo:csr.row_lo + csr.n], sig, min_len, min_sig, pool=self.pool)
+
+    def new_mask(self):
+        m = self.pool.get('mask_full', self.n, torch.uint8)
+        m.zero_()
+        return m
+
+    def site_norm(self, csr):
+        return self.dev.site_norm(csr, self.sites, pool=self.pool)
+
+    # ---- KR phases -------------------------------------------------------------------------------
+    def kr_setup(self, csr, tol, delta, Delta, max_iter):
+        dev, lib = self.dev, self.lib
+        nbytes = lib.b3c_krp_workspace_bytes(self.n, csr.nnz)
+        if self.kr_ws is None or self.kr_ws.numel() < nbytes:
+            self.kr_ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+        offs = (C.c_int64 * 8)()
+        self.check(lib.b3c_krp_setup(self.n, csr.row_lo, csr.row_lo + csr.n, csr.nnz, dev._ptr(csr.indptr),
+                                     dev._ptr(csr.indices), dev._ptr(csr.data), float(tol), float(delta), float(Delta),
+                                     int(max_iter), dev._ptr(self.kr_ws), self.kr_ws.numel(), offs, dev._stream()))
+        n, nc = self.n, int(offs[3])
+        ws = self.kr_ws
+        self.u = ws[int(offs[0]):int(offs[0]) + 8 * n].view(torch.float64)
+        self.x = ws[int(offs[1]):int(offs[1]) + 8 * n].view(torch.float64)
+        self.part = ws[int(offs[2]):int(offs[2]) + 8 * 7 * nc].view(torch.float64).view(7, nc)
+
+    def kr_phase(self, phase):
+        self.check(self.lib.b3c_krp_phase(self.dev._ptr(self.kr_ws), phase, self.dev._stream()))
+
+    def kr_scalar(self, which):
+        self.check(self.lib.b3c_krp_scalar(self.dev._ptr(self.kr_ws), which, self.dev._stream()))
+
+    def kr_state(self):
+        h = (C.c_int64 * 8)()
+        self.check(self.lib.b3c_krp_state(self.dev._ptr(self.kr_ws), h, self.dev._stream()))
+        return dict(state=int(h[0]), status=int(h[1]), n_iter=int(h[2]), k=int(h[3]), outer=int(h[4]),
+                    n_spmv=int(h[5]), zero_diag=int(h[6]))
+
+    # ---- scaling + edges ----------------------------------------------------------------------------
+    def kr_apply(self, csr, x):
+        return self.dev.kr_apply(csr, x, pool=self.pool)
+
+    def compress_edges(self, csr, mask, reduce_max, scale=True):
+        return self.dev.compress_edges(csr, mask, want_sub=False, want_edges=True, scale=scale, pool=self.pool,
+                                       reduce_max=reduce_max)
+
+    def synchronize(self):
+        torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------
+# the driver
+# ------------------------------------------------------------------------------------------------
+
+def kr_block_loop(eng, comm, max_phases=1_000_000):
+    """
+    The Knight-Ruiz iteration over row blocks (sparse_utils.py:123-221): phases on the engine,
+    collectives in between, loop control on the device (see include/bin3c_b200.h, "Row-block
+    phase API").  Returns the final state dict.
+    """
+    def spmv():
+        comm.all_reduce(eng.u, 'sum')
+        eng.kr_phase(KRP_SPMV)
+
+    eng.kr_phase(KRP_INIT)
+    spmv()
+    eng.kr_phase(KRP_RESID)
+    comm.all_reduce(eng.part[PA], 'sum')
+    eng.kr_scalar(KRS_OUTER_FIRST)
+    st = eng.kr_state()
+    n = 0
+    while st['state'] != STATE_DONE and n < max_phases:
+        n += 1
+        if st['state'] == STATE_INNER:
+            eng.kr_phase(KRP_DIR)
+            spmv()
+            eng.kr_phase(KRP_W)
+            comm.all_reduce(eng.part[PA:PB + 1], 'sum')
+            eng.kr_scalar(KRS_ALPHA)
+            eng.kr_phase(KRP_STEP)
+            comm.all_reduce(eng.part[PC], 'sum')
+            comm.all_reduce(eng.part[PMIN:PG2 + 1], 'min')
+            eng.kr_scalar(KRS_DECIDE)
+        else:
+            eng.kr_phase(KRP_UPDATE)
+            spmv()
+            eng.kr_phase(KRP_RESID)
+            comm.all_reduce(eng.part[PA], 'sum')
+            eng.kr_scalar(KRS_OUTER)
+        st = eng.kr_state()
+    return st
+
+
+class ShardedHotPath(object):
+    """The whole path over `comm.world` ranks.  Each rank passes its own chunk of pair records."""
+
+    def __init__(self, tid2idx, lengths, sites, pair_capacity, min_len=1000, min_sig=5, tol=1e-6, delta=0.1,
+                 Delta=3, max_iter=1000, comm=None, engine=None):
+        self.comm = comm or Comm()
+        self.n = int(len(lengths))
+        self.min_len, self.min_sig = int(min_len), int(min_sig)
+        self.kr_params = (tol, delta, Delta, max_iter)
+        # every rank may receive up to both directions of every key: size the buffers for the
+        # directed keys of a balanced split with head-room
+        self.engine = engine or CudaEngine(tid2idx, lengths, sites, pair_capacity)
+        self.info = {}
+
+    def accumulate(self, records):
+        eng, comm = self.engine, self.comm
+        eng.classify(records)
+        rowcnt = comm.all_reduce(eng.row_hist(), 'sum')
+        weight = rowcnt.cpu().numpy().astype(np.float64) + 1.0        # +1: the diagonal entry
+        self.splits = balanced_row_splits(weight, comm.world)
+        send, send_counts, counters = eng.route(self.splits)
+        recv_counts = comm.exchange_counts(send_counts)
+        keys = comm.all_to_all_v(send, send_counts, recv_counts)
+        comm.all_reduce(eng.diag_counts(), 'sum')
+        self.row_lo, self.row_hi = int(self.splits[comm.rank]), int(self.splits[comm.rank + 1])
+        dev = keys.device
+        c = torch.tensor([counters['accepted'], counters['ref_excluded'], counters['poor_match']],
+                         dtype=torch.int64, device=dev)
+        comm.all_reduce(c, 'sum')
+        c = c.cpu().tolist()
+        self.info.update(accepted=c[0], ref_excluded=c[1], poor_match=c[2], splits=self.splits.tolist(),
+                         keys_received=int(keys.numel()))
+        if self.row_hi > self.row_lo:
+            self.block = eng.build_block(keys, self.row_lo, self.row_hi)
+        else:
+            self.block = None
+        return self.block
+
+    def compute_mask(self):
+        eng, comm = self.engine, self.comm
+        mask = eng.new_mask()
+        if self.block is not None:
+            mask[self.row_lo:self.row_hi].copy_(eng.block_mask(self.block, self.min_len, self.min_sig))
+        self.mask = comm.all_reduce(mask, 'sum')
+        return self.mask
+
+    def balance(self):
+        eng, comm = self.engine, self.comm
+        assert self.block is not None, 'a rank without rows is not supported by the KR driver'
+        self.normed = eng.site_norm(self.block)
+        eng.kr_setup(self.normed, *self.kr_params)
+        st = kr_block_loop(eng, comm)
+        z = torch.tensor([st['zero_diag']], dtype=torch.int64, device=eng.x.device)
+        st['zero_diag'] = int(comm.all_reduce(z, 'sum').cpu()[0])
+        self.kr_info = st
+        if st['status'] == -6:
+            raise ValueError('KR: max(ynew) == Delta with no element above Delta (Q13)')
+        if st['status'] != 0 or st['n_iter'] > self.kr_params[3]:
+            raise RuntimeError('matrix balancing failed to converge in {} iterations'.format(st['n_iter']))
+        # x: every rank wrote its own slice; assemble the whole vector
+        xs = eng.x
+        if comm.world > 1:
+            full = torch.zeros_like(xs)
+            full[self.row_lo:self.row_hi].copy_(xs[self.row_lo:self.row_hi])
+            xs = comm.all_reduce(full, 'sum')
+        self.x = xs
+        self.balanced = eng.kr_apply(self.normed, self.x)
+        return self.balanced
+
+    def edges(self, scale=True):
+        eng, comm = self.engine, self.comm
+        self.edge_res = eng.compress_edges(self.balanced, self.mask, lambda t: comm.all_reduce(t, 'max'), scale=scale)
+        return self.edge_res
+
+    def run(self, records):
+        self.accumulate(records)
+        self.compute_mask()
+        self.balance()
+        return self.edges()
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py entry for N > 1 (one process per GPU, launched by torchrun)
+# ------------------------------------------------------------------------------------------------
+
+def bench_main(args, rank, local_rank, world):
+    """Weak scaling: every rank brings a C2-sized shard (50M pairs) of a community whose contig and
+    genome counts grow with the number of ranks (world=1 would be exactly C2)."""
+    import json
+    import os
+    import time
+    from . import synth, device as dev
+    from bench import METRIC, UNIT, MIN_LEN, MIN_SIG, ClockSampler, measured_peak
+
+    scale = args.scale
+    n_genomes, n_contigs = 100 * world, 50_000 * world
+    pairs_local = max(1, int(50_000_000 * scale))
+    t0 = time.time()
+    com = synth.make_shard(n_genomes, n_contigs, pairs_local, seed=1002, rank=rank)
+    gen_s = time.time() - t0
+    comm = Comm()
+    rec_dev = dev.to_device(com.records)
+    hp = ShardedHotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=int(2.5 * pairs_local) + 1024,
+                        min_len=MIN_LEN, min_sig=MIN_SIG, comm=comm)
+
+    def sync():
+        torch.cuda.synchronize()
+        comm.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        hp.run(rec_dev)
+    sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = dev.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {'accumulate': 0.0, 'mask': 0.0, 'kr': 0.0, 'edges': 0.0}
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        marks[0].record()
+        hp.accumulate(rec_dev)
+        marks[1].record()
+        hp.compute_mask()
+        marks[2].record()
+        hp.balance()
+        marks[3].record()
+        res = hp.edges()
+        marks[4].record()
+        torch.cuda.synchronize()
+        for k, (a, b) in zip(stage, zip(marks[:-1], marks[1:])):
+            stage[k] += a.elapsed_time(b)
+    e1.record()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device='cuda')
+    comm.all_reduce(ms, 'max')
+    clocks = sampler.stop()
+    launches = dev.launch_count() - launches0
+    tot = torch.tensor([pairs_local, int(hp.block.nnz), int(res['n_edges'])], dtype=torch.int64, device='cuda')
+    comm.all_reduce(tot, 'sum')
+    if rank != 0:
+        return
+    ms_per_step = float(ms.cpu()[0])
+    total_pairs, nnz_full, n_edges = [int(v) for v in tot.cpu()]
+    peak, peak_src = measured_peak()
+    kr = hp.kr_info
+    line = {
+        'metric': METRIC, 'value': total_pairs / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u32 counts / f64 balancing', 'data': 'synthetic',
+        'config': {'workload': 'weak scaling of C2: {} genomes, {} contigs, {} pairs = {} per GPU (seed 1002)'.format(
+            n_genomes, n_contigs, total_pairs, pairs_local),
+            'l2': 'input records {} MB per GPU > 126 MB L2, no explicit flush'.format(8 * pairs_local // 1000000),
+            'nnz_full': nnz_full, 'edges': n_edges, 'row_splits': hp.info['splits'], 'generator_s': round(gen_s, 1)},
+        'clocks': clocks,
+        'e2e': None,
+        'gpu_launches': int(launches),
+        'stages_ms_rank0': {k: round(v / args.steps, 4) for k, v in stage.items()},
+        'kr': {'n_iter': kr['n_iter'], 'n_spmv': kr['n_spmv'], 'outer': kr['outer'], 'zero_diag': kr['zero_diag']},
+        'pair_counts': {k: hp.info[k] for k in ('accepted', 'ref_excluded', 'poor_match')},
+        'roofline': {'kernel': 'k_krp_phase(SPMV)', 'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s',
+                     'frac': None, 'traffic': None, 'peak_source': peak_src,
+                     'note': 'per-kernel roofline is reported by the N=1 run'},
+        'cpu_baseline': None,
+    }
+    print(json.dumps(line))

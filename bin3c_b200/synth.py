@@ -111,6 +111,88 @@ def _contig_lengths(rng, n, profile):
     return np.clip(ln, 1000, 1_000_000).astype(np.int64)
 
 
+class CommunityTables(object):
+    """The contig / genome / reference tables of a community, without any pairs."""
+
+    def __init__(self, n_genomes, n_contigs, seed, profile='lognormal', excl_ref_frac=0.10):
+        rng = np.random.default_rng(seed)
+        G, N = int(n_genomes), int(n_contigs)
+        assert G >= 1 and N >= G
+        self.G, self.N, self.seed, self.profile = G, N, seed, profile
+        # genomes: relative size and abundance
+        g_size = rng.lognormal(0.0, 1.0, size=G)
+        g_abund = rng.lognormal(0.0, 1.0, size=G)
+        # every genome gets at least one contig, the remainder by size
+        genome_sorted = np.concatenate([np.arange(G), rng.choice(G, size=N - G, p=g_size / g_size.sum())])
+        genome_sorted.sort()
+        lengths_sorted = _contig_lengths(rng, N, profile)
+        # genome-sorted working order "s"; internal (assembly) order is a shuffle of it
+        self.genome_sorted = genome_sorted
+        self.g_start = np.searchsorted(genome_sorted, np.arange(G), side='left')
+        self.g_end = np.searchsorted(genome_sorted, np.arange(G), side='right')
+        self.cum_len = np.concatenate([[0.0], np.cumsum(lengths_sorted.astype(np.float64))])
+        w1 = lengths_sorted * g_abund[genome_sorted]
+        cum_w1 = np.cumsum(w1)
+        self.cum_w1 = cum_w1 / cum_w1[-1]
+        self.perm = rng.permutation(N)            # s -> internal index
+        self.lengths = np.empty(N, dtype=np.int32)
+        self.lengths[self.perm] = lengths_sorted
+        self.genome_of = np.empty(N, dtype=np.int32)
+        self.genome_of[self.perm] = genome_sorted
+        self.sites = np.maximum(1, self.lengths // 256).astype(np.int32)
+        # BAM references: usable contigs interleaved with excluded (short) references
+        n_excl = max(1, int(round(N * excl_ref_frac)))
+        self.n_refs = N + n_excl
+        is_excl = np.zeros(self.n_refs, dtype=bool)
+        is_excl[rng.choice(self.n_refs, size=n_excl, replace=False)] = True
+        self.ref_index = np.flatnonzero(~is_excl).astype(np.int64)     # internal k -> tid (ascending)
+        self.excl_tids = np.flatnonzero(is_excl).astype(np.int64)
+        self.rng = rng                                                 # continues into the pair stream
+
+    def sample_pairs(self, n_pairs, rng=None, p_same=0.80, p_genome=0.18, p_pass=0.85, excl_end_frac=0.01,
+                     chunk=1 << 24):
+        """Packed pair records drawn from this community (rng defaults to the table stream)."""
+        rng = self.rng if rng is None else rng
+        N, P = self.N, int(n_pairs)
+        n_excl = len(self.excl_tids)
+        records = np.empty(P, dtype=np.uint64)
+        for lo in range(0, P, chunk):
+            m = min(chunk, P - lo)
+            s1 = np.searchsorted(self.cum_w1, rng.random(m), side='right')
+            np.minimum(s1, N - 1, out=s1)
+            kind = rng.random(m)
+            s2 = s1.copy()
+            # same genome, contig ~ L
+            sel = np.flatnonzero((kind >= p_same) & (kind < p_same + p_genome))
+            g = self.genome_sorted[s1[sel]]
+            u = self.cum_len[self.g_start[g]] + rng.random(len(sel)) * \
+                (self.cum_len[self.g_end[g]] - self.cum_len[self.g_start[g]])
+            s2[sel] = np.clip(np.searchsorted(self.cum_len, u, side='right') - 1, self.g_start[g], self.g_end[g] - 1)
+            # any contig ~ L
+            sel = np.flatnonzero(kind >= p_same + p_genome)
+            u = rng.random(len(sel)) * self.cum_len[-1]
+            s2[sel] = np.clip(np.searchsorted(self.cum_len, u, side='right') - 1, 0, N - 1)
+
+            t1 = self.ref_index[self.perm[s1]]
+            t2 = self.ref_index[self.perm[s2]]
+            # a few ends land on excluded references
+            e = rng.random(m)
+            sel = np.flatnonzero(e < excl_end_frac)
+            t1[sel] = self.excl_tids[rng.integers(0, n_excl, size=len(sel))]
+            sel = np.flatnonzero((e >= excl_end_frac) & (e < 2 * excl_end_frac))
+            t2[sel] = self.excl_tids[rng.integers(0, n_excl, size=len(sel))]
+            # mate order is arbitrary in a BAM
+            swap = rng.random(m) < 0.5
+            a = np.where(swap, t2, t1)
+            b = np.where(swap, t1, t2)
+            records[lo:lo + m] = pack_pairs(a, b, rng.random(m) < p_pass)
+        return records
+
+    def community(self, records):
+        return Community(self.n_refs, self.ref_index, self.lengths, self.sites, self.genome_of, records, self.seed,
+                         self.profile)
+
+
 def make_community(n_genomes, n_contigs, n_pairs, seed, profile='lognormal',
                    p_same=0.80, p_genome=0.18, p_pass=0.85, excl_ref_frac=0.10,
                    excl_end_frac=0.01, chunk=1 << 24):
@@ -118,74 +200,20 @@ def make_community(n_genomes, n_contigs, n_pairs, seed, profile='lognormal',
     Build a deterministic synthetic community.  All randomness comes from
     numpy.random.default_rng(seed); the same arrays feed the oracle and the GPU path.
     """
-    rng = np.random.default_rng(seed)
-    G, N, P = int(n_genomes), int(n_contigs), int(n_pairs)
-    assert G >= 1 and N >= G
+    tab = CommunityTables(n_genomes, n_contigs, seed, profile=profile, excl_ref_frac=excl_ref_frac)
+    rec = tab.sample_pairs(n_pairs, p_same=p_same, p_genome=p_genome, p_pass=p_pass, excl_end_frac=excl_end_frac,
+                           chunk=chunk)
+    return tab.community(rec)
 
-    # genomes: relative size and abundance
-    g_size = rng.lognormal(0.0, 1.0, size=G)
-    g_abund = rng.lognormal(0.0, 1.0, size=G)
 
-    # every genome gets at least one contig, the remainder by size
-    genome_sorted = np.concatenate([np.arange(G), rng.choice(G, size=N - G, p=g_size / g_size.sum())])
-    genome_sorted.sort()
-    lengths_sorted = _contig_lengths(rng, N, profile)
-
-    # genome-sorted working order "s"; internal (assembly) order is a shuffle of it
-    g_start = np.searchsorted(genome_sorted, np.arange(G), side='left')
-    g_end = np.searchsorted(genome_sorted, np.arange(G), side='right')
-    cum_len = np.concatenate([[0.0], np.cumsum(lengths_sorted.astype(np.float64))])
-    w1 = lengths_sorted * g_abund[genome_sorted]
-    cum_w1 = np.cumsum(w1)
-    cum_w1 /= cum_w1[-1]
-
-    perm = rng.permutation(N)            # s -> internal index
-    lengths = np.empty(N, dtype=np.int32)
-    lengths[perm] = lengths_sorted
-    genome_of = np.empty(N, dtype=np.int32)
-    genome_of[perm] = genome_sorted
-    sites = np.maximum(1, lengths // 256).astype(np.int32)
-
-    # BAM references: usable contigs interleaved with excluded (short) references
-    n_excl = max(1, int(round(N * excl_ref_frac)))
-    n_refs = N + n_excl
-    is_excl = np.zeros(n_refs, dtype=bool)
-    is_excl[rng.choice(n_refs, size=n_excl, replace=False)] = True
-    ref_index = np.flatnonzero(~is_excl).astype(np.int64)     # internal k -> tid (ascending)
-    excl_tids = np.flatnonzero(is_excl).astype(np.int64)
-
-    records = np.empty(P, dtype=np.uint64)
-    for lo in range(0, P, chunk):
-        m = min(chunk, P - lo)
-        s1 = np.searchsorted(cum_w1, rng.random(m), side='right')
-        np.minimum(s1, N - 1, out=s1)
-        kind = rng.random(m)
-        s2 = s1.copy()
-        # same genome, contig ~ L
-        sel = np.flatnonzero((kind >= p_same) & (kind < p_same + p_genome))
-        g = genome_sorted[s1[sel]]
-        u = cum_len[g_start[g]] + rng.random(len(sel)) * (cum_len[g_end[g]] - cum_len[g_start[g]])
-        s2[sel] = np.clip(np.searchsorted(cum_len, u, side='right') - 1, g_start[g], g_end[g] - 1)
-        # any contig ~ L
-        sel = np.flatnonzero(kind >= p_same + p_genome)
-        u = rng.random(len(sel)) * cum_len[-1]
-        s2[sel] = np.clip(np.searchsorted(cum_len, u, side='right') - 1, 0, N - 1)
-
-        t1 = ref_index[perm[s1]]
-        t2 = ref_index[perm[s2]]
-        # a few ends land on excluded references
-        e = rng.random(m)
-        sel = np.flatnonzero(e < excl_end_frac)
-        t1[sel] = excl_tids[rng.integers(0, n_excl, size=len(sel))]
-        sel = np.flatnonzero((e >= excl_end_frac) & (e < 2 * excl_end_frac))
-        t2[sel] = excl_tids[rng.integers(0, n_excl, size=len(sel))]
-        # mate order is arbitrary in a BAM
-        swap = rng.random(m) < 0.5
-        a = np.where(swap, t2, t1)
-        b = np.where(swap, t1, t2)
-        records[lo:lo + m] = pack_pairs(a, b, rng.random(m) < p_pass)
-
-    return Community(n_refs, ref_index, lengths, sites, genome_of, records, seed, profile)
+def make_shard(n_genomes, n_contigs, n_pairs_local, seed, rank, profile='lognormal'):
+    """
+    One rank's shard of a community for the multi-GPU runs: every rank builds the same tables from
+    `seed` and draws its own n_pairs_local records from the stream default_rng([seed, rank]).
+    """
+    tab = CommunityTables(n_genomes, n_contigs, seed, profile=profile)
+    rec = tab.sample_pairs(n_pairs_local, rng=np.random.default_rng([seed, 7919 + rank]))
+    return tab.community(rec)
 
 
 # the BASELINE.json configs, made concrete (BASELINE.md section 5)

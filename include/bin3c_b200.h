@@ -80,27 +80,63 @@ int b3c_accum_emit_csr(void *d_ws, int symmetric, int64_t *d_indptr, int32_t *d_
                        uint32_t *d_counts, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Sharded accumulation (multi-GPU; driver: bin3c_b200/dist.py).  Each rank
+ * classifies its own chunk of the pair records (begin / add_pairs as above), then:
+ *
+ *   row_hist      d_rowcnt[r] (uint64[n_seq], zeroed by the caller) += directed keys of row r,
+ *                 all-reduced by the driver to cut nnz-balanced row ranges
+ *   route         turns every canonical key (i<j) into the directed keys (i,j) and (j,i) and
+ *                 buckets them by the rank that owns their row: d_splits (int32[n_ranks+1]) are
+ *                 the row-range boundaries; d_out receives the buckets back to back;
+ *                 h_counts[0..n_ranks] = bucket offsets (exclusive scan, last = total) followed
+ *                 by this rank's accepted / ref_excluded / poor_match counters.
+ *                 d_scratch needs 1600 bytes.
+ *   reduce_block  after the all-to-all: sort + run-length reduce the directed keys received for
+ *                 rows [row_lo, row_hi) (the diagonal counts in the workspace must already be
+ *                 all-reduced: b3c_accum_offsets gives their location); h_sizes[0] = nnz of the
+ *                 row block of the full symmetric matrix
+ *   emit_block    local CSR of the row block: local indptr, global sorted columns, exact counts
+ * ------------------------------------------------------------------------------------ */
+int b3c_accum_offsets(void *d_ws, int64_t *h_offsets /* [4]: counters, diagonal, keys, capacity */);
+int b3c_accum_row_hist(void *d_ws, uint64_t *d_rowcnt, void *stream);
+int b3c_accum_route(void *d_ws, const int32_t *d_splits, int32_t n_ranks, uint64_t *d_out,
+                    int64_t out_capacity, uint64_t *d_scratch, int64_t *h_counts, void *stream);
+int b3c_accum_reduce_block(void *d_ws, const uint64_t *d_keys, int64_t n_keys, int32_t row_lo,
+                           int32_t row_hi, int64_t *h_sizes, void *stream);
+int b3c_accum_emit_block(void *d_ws, int32_t row_lo, int32_t row_hi, int64_t *d_indptr,
+                         int32_t *d_indices, uint32_t *d_counts, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Row blocks.  The row-wise entry points below take a block of n_local rows whose first row is
+ * global row `row_lo`: d_indptr is local (n_local + 1 entries, starting at 0), column indices are
+ * global, and per-contig vectors (sites, x, mask, newidx) are indexed globally.  A whole matrix
+ * is the block row_lo = 0, n_local = n.  This is what the multi-GPU driver shards on.
+ *
  * Filter mask.  max_offdiag (sparse_utils.py:269-281) and the two threshold tests of
  * ContactMap.set_primary_acceptance_mask (contact_map.py:888-905).
- * d_signal (uint32[n]) and d_mask (uint8[n]) are outputs; either may be NULL.
+ * d_signal has n_local entries; b3c_acceptance_mask works on whole vectors of length n.
  * ------------------------------------------------------------------------------------ */
-int b3c_max_offdiag_u32(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
-                        const uint32_t *d_counts, uint32_t *d_signal, void *stream);
-int b3c_max_offdiag_f64(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
-                        const double *d_data, double *d_signal, void *stream);
+int b3c_max_offdiag_u32(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
+                        const int32_t *d_indices, const uint32_t *d_counts, uint32_t *d_signal,
+                        void *stream);
+int b3c_max_offdiag_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
+                        const int32_t *d_indices, const double *d_data, double *d_signal,
+                        void *stream);
 int b3c_acceptance_mask(int32_t n, const int32_t *d_lengths, const uint32_t *d_signal,
                         int64_t min_len, int64_t min_sig, uint8_t *d_mask, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Site normalisation.  ContactMap._get_sites + fast_norm_fullseq_bysite
  * (contact_map.py:1103-1108, 100-113): out[e] = count[e] * (1.0 / (s_i * s_j)), zero sites
- * counted as one (Q6).  d_sites is the raw int32 site count per contig.
+ * counted as one (Q6).  d_sites is the raw int32 site count per contig (global).
  * ------------------------------------------------------------------------------------ */
-int b3c_site_norm(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
-                  const uint32_t *d_counts, const int32_t *d_sites, double *d_out, void *stream);
+int b3c_site_norm(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
+                  const int32_t *d_indices, const uint32_t *d_counts, const int32_t *d_sites,
+                  double *d_out, void *stream);
 /* same on an already-float matrix, in place (ContactMap._norm_seq called on a float map) */
-int b3c_site_norm_f64(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
-                      double *d_data, const int32_t *d_sites, void *stream);
+int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
+                      const int32_t *d_indices, double *d_data, const int32_t *d_sites,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Knight-Ruiz balancing.  kr_biostochastic (sparse_utils.py:90-224).
@@ -122,8 +158,9 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
                const double *d_data, double tol, double delta, double Delta, int32_t max_iter,
                int32_t mode, double *d_x, void *d_ws, int64_t ws_bytes, int64_t *h_info,
                void *stream);
-int b3c_kr_scale(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
-                 const double *d_data, const double *d_x, double *d_out, void *stream);
+int b3c_kr_scale(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
+                 const int32_t *d_indices, const double *d_data, const double *d_x, double *d_out,
+                 void *stream);
 /* is_hermitian (sparse_utils.py:10-18) without the dense N x N temporary (Q11): counts the
  * entries with |a_ij - a_ji| >= tol (a missing mirror entry counts as zero).  Columns must be
  * sorted within rows.  h_count[0] receives the count (the stream is synchronised). */
@@ -135,24 +172,58 @@ int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_i
              int32_t prepared, void *stream);
 
 /* ------------------------------------------------------------------------------------
- * Compress + edge weighting.  compress (sparse_utils.py:284-314), get_subspace
- * (contact_map.py:966-982) and the edge loop of to_graph (cluster.py:314-321).
+ * Row-block phase API of KR (multi-GPU driver).  Each
+ * rank owns rows [row_lo, row_hi) (1024-row aligned) of the matrix as a local CSR with global
+ * columns, and the matching slices of all vectors.  The arithmetic is that of b3c_kr_run; the
+ * driver puts collectives between the phases:
  *
- *   count   d_newidx[i] = index of contig i among the accepted ones (or -1);
- *           h_out[0] = accepted contigs, [1] = nnz kept, [2] = undirected edges (u<=v kept
- *           entries, self-loops included, Q8)
- *   fill    compressed CSR of the kept entries (sub_* may be NULL) and/or the edge list
- *           (u, v, w) with w = value * scl, scl = 1/max over the kept entries incl. the
- *           diagonal when scale != 0 (Q8); one value per undirected edge, taken from the
- *           upper-triangle entry (Q9).  d_scl receives scl (float64[1]).
+ *     phase INIT | all-reduce u | SPMV | RESID | all-reduce partials | scalar OUTER_FIRST
+ *     while state != DONE:
+ *       INNER : DIR | all-reduce u | SPMV | W | all-reduce PA,PB | scalar ALPHA |
+ *               STEP | all-reduce PC (sum), PMIN..PG2 (min) | scalar DECIDE
+ *       UPDATE: UPDATE | all-reduce u | SPMV | RESID | all-reduce PA | scalar OUTER
+ *
+ * u slices a rank does not own are zero, so a SUM all-reduce assembles the vector exactly; the
+ * partial arrays hold the identity (0 / +inf) for chunks a rank does not own.
+ * setup returns byte offsets into the workspace: h_offsets[0] = u (float64[n]), [1] = x
+ * (float64[n]), [2] = partials (float64[7][n_chunks]: sums PA PB PC, then minima), [3] = n_chunks.
+ * b3c_krp_state synchronises and returns state (0 done, 1 inner, 2 update), status, n_iter, k,
+ * outer steps, SpMV count, zero diagonals of this block.
+ * ------------------------------------------------------------------------------------ */
+int64_t b3c_krp_workspace_bytes(int32_t n, int64_t nnz_local);
+int b3c_krp_setup(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local,
+                  const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
+                  double tol, double delta, double Delta, int32_t max_iter,
+                  void *d_ws, int64_t ws_bytes, int64_t *h_offsets, void *stream);
+int b3c_krp_phase(void *d_ws, int32_t phase, void *stream);   /* 0 INIT 1 SPMV 2 RESID 3 DIR 4 W 5 STEP 6 UPDATE */
+int b3c_krp_scalar(void *d_ws, int32_t which, void *stream);  /* 0 OUTER_FIRST 1 OUTER 2 ALPHA 3 DECIDE */
+int b3c_krp_state(void *d_ws, int64_t *h_state /* [8] */, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Compress + edge weighting.  compress (sparse_utils.py:284-314), get_subspace
+ * (contact_map.py:966-982) and the edge loop of to_graph (cluster.py:314-321), on a row block
+ * (see "Row blocks"); d_mask and d_newidx have n entries.
+ *
+ *   count   d_newidx[i] = index of contig i among the accepted ones (or -1), over the whole
+ *           mask; d_vmax (float64[1]) = largest kept value of this block (the multi-GPU driver
+ *           all-reduces it with MAX before fill);
+ *           h_out[0] = accepted contigs (whole mask), [1] = entries kept in this block,
+ *           [2] = undirected edges of this block (kept entries with u<=v, self-loops
+ *           included, Q8)
+ *   fill    the edge list (u, v, w) with w = value * scl, scl = 1/d_vmax when scale != 0
+ *           (cluster.py:316, maximum over the kept entries incl. the diagonal, Q8); one value
+ *           per undirected edge, taken from the upper-triangle entry (Q9); d_scl receives scl.
+ *           For a whole matrix (row_lo = 0, n_local = n) the compressed CSR can be written as
+ *           well (d_sub_*; NULL to skip).
  * ------------------------------------------------------------------------------------ */
 int64_t b3c_compress_workspace_bytes(int32_t n);
-int b3c_compress_count(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
-                       const double *d_data, const uint8_t *d_mask, int32_t *d_newidx, void *d_ws,
-                       int64_t ws_bytes, int64_t *h_out, void *stream);
-int b3c_compress_fill(int32_t n, const int64_t *d_indptr, const int32_t *d_indices,
-                      const double *d_data, const uint8_t *d_mask, const int32_t *d_newidx,
-                      void *d_ws, int scale,
+int b3c_compress_count(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_indptr,
+                       const int32_t *d_indices, const double *d_data, const uint8_t *d_mask,
+                       int32_t *d_newidx, void *d_ws, int64_t ws_bytes, double *d_vmax,
+                       int64_t *h_out, void *stream);
+int b3c_compress_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_indptr,
+                      const int32_t *d_indices, const double *d_data, const uint8_t *d_mask,
+                      const int32_t *d_newidx, void *d_ws, const double *d_vmax, int scale,
                       int64_t *d_sub_indptr, int32_t *d_sub_indices, double *d_sub_data,
                       int32_t *d_edge_u, int32_t *d_edge_v, double *d_edge_w, double *d_scl,
                       void *stream);

@@ -1,0 +1,96 @@
+"""
+GPU tests of the sharded (multi-GPU) path through the C ABI.  With one GPU the driver runs with
+world size 1 (same kernels: key routing, block reduce/emit, KR phase API); with two or more GPUs
+two NCCL ranks are spawned.  Bars as in test_gpu_parity.py.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(n_genomes=12, n_contigs=9000, n_pairs=1_500_000, seed=654)
+
+
+def _check(parts, com, min_sig):
+    from bin3c_b200 import synth
+    from oracle import oracle
+    ti, tj, ok = synth.unpack_pairs(com.records)
+    ref = oracle.run_path(ti, tj, ok, com.tid2idx(), com.lengths, com.sites, min_len=1000, min_sig=min_sig)
+    row = np.concatenate([p['row'] for p in parts])
+    col = np.concatenate([p['col'] for p in parts])
+    data = np.concatenate([p['data'] for p in parts])
+    o = np.lexsort((col, row))
+    sm = ref['seq_map']
+    assert len(row) == sm.nnz
+    assert np.array_equal(row[o], sm.row) and np.array_equal(col[o], sm.col) and np.array_equal(data[o], sm.data)
+    for p in parts:
+        assert p['counts'].tolist() == [ref['counts'][k] for k in ('accepted', 'ref_excluded', 'poor_match')]
+        assert np.array_equal(p['mask'].astype(bool), ref['mask'])
+        assert int(p['n_iter']) == ref['n_iter']
+        assert np.max(np.abs(p['x'] - ref['x']) / np.abs(ref['x'])) <= 1e-9
+    u = np.concatenate([p['u'] for p in parts])
+    v = np.concatenate([p['v'] for p in parts])
+    w = np.concatenate([p['w'] for p in parts])
+    o = np.lexsort((v, u))
+    assert np.array_equal(u[o], ref['u']) and np.array_equal(v[o], ref['v'])
+    assert np.max(np.abs(w[o] - ref['w']) / np.abs(ref['w'])) <= 1e-9
+
+
+def _run_rank(rank, world, com, min_sig):
+    import torch
+    from bin3c_b200 import device as dev
+    from bin3c_b200.dist import ShardedHotPath, Comm
+    per = -(-com.n_pairs // world)
+    per += per & 1
+    mine = com.records[rank * per:(rank + 1) * per]
+    hp = ShardedHotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=int(2.5 * len(mine)) + 1024,
+                        min_len=1000, min_sig=min_sig, comm=Comm())
+    res = hp.run(dev.to_device(mine))
+    torch.cuda.synchronize()
+    indptr, indices, data = hp.block.host_arrays()
+    row = np.repeat(np.arange(hp.block.n), np.diff(indptr)) + hp.row_lo
+    return dict(row=row, col=indices, data=data, mask=hp.mask.cpu().numpy(), x=hp.x.cpu().numpy(),
+                n_iter=hp.kr_info['n_iter'], u=res['u'].cpu().numpy(), v=res['v'].cpu().numpy(),
+                w=res['w'].cpu().numpy(),
+                counts=np.array([hp.info[k] for k in ('accepted', 'ref_excluded', 'poor_match')]))
+
+
+def test_sharded_path_world1():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from bin3c_b200 import synth
+    com = synth.make_community(**CFG)
+    _check([_run_rank(0, 1, com, 3)], com, 3)
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from bin3c_b200 import synth
+    com = synth.make_community(**CFG)
+    np.savez(os.path.join(out_dir, 'rank{}.npz'.format(rank)), **_run_rank(rank, world, com, 3))
+    dist.destroy_process_group()
+
+
+def test_sharded_path_two_ranks(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from bin3c_b200 import synth
+    mp.spawn(_nccl_worker, args=(2, 29655, str(tmp_path)), nprocs=2, join=True)
+    com = synth.make_community(**CFG)
+    parts = [dict(np.load(os.path.join(str(tmp_path), 'rank{}.npz'.format(r)))) for r in range(2)]
+    _check(parts, com, 3)
