@@ -66,6 +66,7 @@ SIGNATURES = {
     'b3c_kr_scale': (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p]),
     'b3c_asymmetry_count': (C.c_int, [_i32, _p, _p, _p, _f64, _p, _pi64, _p]),
     'b3c_spmv': (C.c_int, [_i32, _i64, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]),
+    'b3c_set_option': (C.c_int, [_i32, _i64]),
     'b3c_compress_workspace_bytes': (_i64, [_i32]),
     'b3c_compress_count': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _pi64, _p]),
     'b3c_compress_fill': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p,

@@ -1,16 +1,29 @@
-// Knight-Ruiz balancing (sparse_utils.py:90-224) as fp64 CSR SpMV + fused vector phases.
+// Knight-Ruiz balancing (sparse_utils.py:90-224) as fp64 sparse matrix-vector products + fused
+// vector phases.
 //
 // One persistent cooperative kernel runs the whole Newton/CG iteration with device-side
-// control flow: every CTA derives the loop scalars from the same per-chunk partial sums in
-// the same order, so all CTAs take identical branches and the host is not involved until the
-// scale vector is final.  The same phase functions are exposed one-by-one (b3c_krp_*) for
+// control flow: every CTA reads the same loop scalars, derived from the same per-chunk partial
+// sums in the same order, so all CTAs take identical branches and the host is not involved until
+// the scale vector is final.  The same phase functions are exposed one-by-one (b3c_krp_*) for
 // the multi-GPU row-block driver, which puts NCCL collectives between them.
 //
-// SpMV: the non-zeros are cut into fixed tiles of SPMV_TILE entries regardless of row
-// boundaries (nnz-balanced, so heavy-tailed contig rows cost nothing extra).  A CTA streams
-// a tile's values and column indices with coalesced loads, gathers u[col], parks the products
-// in shared memory and reduces them per row.  Rows that straddle tiles leave partial sums that
-// a tiny fix-up pass adds in tile order, so the result is deterministic.
+// SpMV operand.  A scattered fp64 gather through L1 costs one L1 wavefront per distinct 128-byte
+// line (32 per warp load when the contig order is shuffled), which caps a CSR SpMV at ~1/3 of HBM
+// speed on this part.  So u is gathered from SHARED memory: the columns are cut into S slabs of
+// W <= 28672 entries (224 KB of fp64) and the matrix is re-laid once per balancing run as a
+// slab-major STREAM: all entries of slab 0 row by row, then slab 1, ...  An entry is its fp64 value
+// plus a 16-bit slab-local column whose top bit marks the first entry of a (row, slab) segment:
+// 10 B per non-zero instead of CSR's 12, and no row pointers are read by the SpMV at all.  A CTA --
+// one per SM -- owns a contiguous range of 2048-entry tiles, brings the slab of u into shared
+// memory with TMA bulk copies (cp.async.bulk + mbarrier) and streams its tiles with 256-bit loads
+// issued two tiles ahead (register ring).  Every warp reduces its own 128 entries with a
+// segmented scan in registers (start flags -> ballots -> 5 shuffle steps), writes the sums of the
+// segments that end inside its chunk, and leaves (head, tail) partials; one warp per tile stitches
+// the 16 chunks together and carries the open segment into the next tile, so the cost per entry
+// does not depend on the row lengths (heavy-tailed contig rows, empty rows).  A segment that
+// crosses a CTA's range is finished by the vector phase that consumes it, from one boundary record
+// per CTA.  Matrices wider than SLAB_S_MAX slabs use the same stream with 32-bit columns and gather
+// u through L1/L2 ("gather form").
 //
 // Reductions (dot products, min, max) use fixed 1024-row chunks with a fixed tree inside the
 // chunk and an in-order sum over chunks: the value does not depend on the grid size or on how
@@ -24,15 +37,17 @@ namespace cg = cooperative_groups;
 
 namespace b3c {
 
-constexpr int KR_THREADS = 256;
+constexpr int KR_THREADS = 512;
 constexpr int KR_WARPS = KR_THREADS / 32;
-constexpr int SPMV_NPT = 8;
-constexpr int SPMV_TILE = KR_THREADS * SPMV_NPT;     // 2048 non-zeros = 24 KB of matrix per tile
+constexpr int SPMV_EPP = 8;                          // entries per lane per piece (one 64-byte load of values)
+constexpr int SPMV_CHUNK = 32 * SPMV_EPP * 2;        // 512 entries per warp step: two pieces, 16 consecutive per lane
+constexpr int SPMV_TILE = 2048;                      // every slab is padded to a multiple of this many entries
 constexpr int CHUNK = 1024;                          // rows per reduction chunk
 constexpr int CHUNK_RPT = CHUNK / KR_THREADS;
-constexpr int SPTR_CAP = 1024;                       // row pointers of a tile staged in shared memory
 constexpr int RED_MAX = 8;                           // values reduced together by one block reduction
-constexpr int KR_MIN_CTAS = 4;                       // CTAs per SM the persistent kernel is compiled for
+constexpr int SLAB_W_MAX = 28672;                    // fp64 entries of u held in shared memory (15-bit columns)
+constexpr int SLAB_S_MAX = 16;                       // more slabs than this: gather form
+static_assert(KR_WARPS <= 32 && SLAB_W_MAX <= 65536, "warp records are stitched by one warp; 16-bit columns");
 
 // partial arrays, each n_chunks long
 enum { PA = 0, PB, PC, PMIN, PNEGMAX, PG1, PG2, P_COUNT };
@@ -50,6 +65,28 @@ struct KRTimers {
     long long work[T_COUNT], sync[T_COUNT], total;
 };
 
+// what each warp leaves for the stitching warp after its run of chunks
+struct WarpRecs {
+    double head[KR_WARPS];     // sum of the entries before the run's first flag (all of them if it has none)
+    double tail[KR_WARPS];     // sum of the segment still open at the end of the run
+    int seen[KR_WARPS];        // the run contains a segment start
+    int first[KR_WARPS];       // ordinal of the first segment that starts inside the run
+    int last[KR_WARPS];        // ordinal of the last one
+};
+
+// dynamic shared memory carve (bytes)
+constexpr int SM_RED = 0;
+constexpr int SM_REC = SM_RED + KR_WARPS * RED_MAX * 8;
+constexpr int SM_CTL = SM_REC + 2 * (int)sizeof(WarpRecs);
+constexpr int SM_STATE = SM_CTL + ((int)sizeof(KRScalars) + 15) / 16 * 16;
+constexpr int SM_SLAB = SM_STATE + 32;
+constexpr int SM_MBAR = (SM_SLAB + (SLAB_S_MAX + 2) * 4 + 7) / 8 * 8;
+constexpr int SM_U = (SM_MBAR + 8 + 127) / 128 * 128;
+constexpr int SM_BYTES_GATHER = SM_U;
+constexpr int SM_BYTES_SLAB = SM_U + SLAB_W_MAX * 8;
+static_assert(SM_REC % 8 == 0 && SM_CTL % 8 == 0 && SM_STATE % 8 == 0 && SM_MBAR % 8 == 0, "shared memory carve alignment");
+static_assert(SM_BYTES_SLAB <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+
 struct KRArgs {
     // local row block [row_lo, row_hi) of an n x n matrix; indptr is local (0-based), columns global
     int32_t n, row_lo, row_hi;
@@ -57,14 +94,30 @@ struct KRArgs {
     const int64_t *indptr;
     const int32_t *indices;
     const double *data;
-    // plan
-    int64_t n_tiles;
-    int32_t *tile_ra;
-    int32_t *chunk_t;          // per local chunk: first tile whose last-starting row lies in the chunk
-    double *head_part, *tail_part;
+    // the stream
+    int32_t slab;              // 1: 16-bit columns, u gathered from shared memory; 0: 32-bit columns, gather form
+    int32_t S, W, npad;        // slabs (1 in gather form), slab width, local rows padded to CHUNK
+    int64_t nv;                // S * npad (row, slab) cells
+    int64_t nnzv;              // entries incl. slab padding (multiple of SPMV_TILE)
+    int64_t n_sch;             // stream chunks = nnzv / SPMV_CHUNK
+    int32_t n_seg;             // non-empty cells = segments
+    const double *sval;
+    const void *scol;          // uint16[nnzv] or uint32[nnzv]
+    const uint16_t *sflag;     // [n_sch * 32] start flags of each lane's 16 entries
+    const int32_t *chunk_seg0; // [n_sch] ordinal of the first segment starting at or after the chunk
+    const int32_t *seg_of;     // [nv] ordinal of cell (s * npad + r), -1 if empty
+    const int32_t *seg_row;    // [n_seg] cell of a segment
+    const int32_t *slab_c0;    // [S+1] first chunk of each slab
+    double *qs;                // [n_seg] segment sums
+    // one boundary record per SpMV CTA
+    int32_t n_bnd;
+    double *bnd_head, *bnd_tail;
+    int32_t *bnd_flag, *bnd_ord, *bnd_lr;
+    // build scratch
+    int64_t *cnt, *vp, *ord, *scan_tmp;
     double *dfix;
-    // vectors (global row indexing, length n)
-    double *x, *v, *rk, *y0, *y1, *p, *Z, *w, *u, *q;
+    // vectors (global row indexing, length n, each 256-byte aligned)
+    double *x, *v, *rk, *y0, *y1, *p, *Z, *w, *u;
     // partials [P_COUNT][n_chunks]
     double *part;
     int32_t n_chunks;
@@ -72,8 +125,66 @@ struct KRArgs {
     KRTimers *timers;
 };
 
+struct SpmvState {             // carried from tile to tile by the stitching warps
+    double open;               // sum so far of the segment open at the end of the last tile
+    int seen, last_ord;        // a segment start was seen in this CTA's range; ordinal of the latest one
+};
+
+struct Smem {
+    double *red, *u;
+    WarpRecs *rec;
+    KRScalars *ctl;
+    SpmvState *st;
+    int *slab;
+    uint64_t *mbar;
+    unsigned u_phase;          // parity of the next completion of mbar
+};
+
+__device__ __forceinline__ Smem carve_smem(unsigned char *base) {
+    Smem s;
+    s.red = (double *)(base + SM_RED);
+    s.rec = (WarpRecs *)(base + SM_REC);
+    s.ctl = (KRScalars *)(base + SM_CTL);
+    s.st = (SpmvState *)(base + SM_STATE);
+    s.slab = (int *)(base + SM_SLAB);
+    s.mbar = (uint64_t *)(base + SM_MBAR);
+    s.u = (double *)(base + SM_U);
+    s.u_phase = 0;
+    return s;
+}
+
+// ---- TMA bulk copy + mbarrier (the u slab) ------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *mbar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "B3C_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra B3C_DONE;\n\t"
+        "bra B3C_WAIT;\n\t"
+        "B3C_DONE:\n\t"
+        "}" ::"r"(smem_addr(mbar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_addr(mbar))
+                 : "memory");
+}
+
 // ---- deterministic block reductions ---------------------------------------------------------
-// NS sums followed by NM minima, reduced together: warp xor-tree, then the 8 warp results in warp
+// NS sums followed by NM minima, reduced together: warp xor-tree, then the warp results in warp
 // order.  Every thread gets the results; the shape is fixed, so the value is reproducible.
 template <int NS, int NM>
 __device__ __forceinline__ void block_reduce(double (&v)[NS + NM], double *s_red) {
@@ -106,7 +217,7 @@ __device__ __forceinline__ void reduce_parts(const double *part, int nc, const i
     for (int j = threadIdx.x; j < nc; j += KR_THREADS) {
 #pragma unroll
         for (int i = 0; i < NS + NM; ++i) {
-            const double x = part[(int64_t)ids[i] * nc + j];
+            const double x = __ldcg(part + (int64_t)ids[i] * nc + j);
             out[i] = (i < NS) ? out[i] + x : fmin(out[i], x);
         }
     }
@@ -114,125 +225,340 @@ __device__ __forceinline__ void reduce_parts(const double *part, int nc, const i
 }
 
 // ---- SpMV -------------------------------------------------------------------------------------
-// `u` is rewritten between SpMV phases of the same (persistent) launch, so it is read with
-// ordinary coherent loads -- never ld.global.nc -- and carries no __restrict__.
-__device__ __forceinline__ void spmv_tile(const KRArgs &A, const double *u, int64_t t, double *s_prod,
-                                          int *s_ptr) {
-    const int64_t base = t * SPMV_TILE;
-    const int64_t rem = A.nnz - base;
-    const int cnt = (int)(rem < SPMV_TILE ? (rem > 0 ? rem : 0) : SPMV_TILE);
-    // 1. stream the tile: all loads are issued before anything is consumed
-    double a[SPMV_NPT];
-    int c[SPMV_NPT];
+// Inside a 512-entry chunk lane l owns the 16 consecutive entries [16 l, 16 l + 16), and the chunk is STORED
+// piece-major -- physical position k * 256 + 8 l + i holds logical entry 16 l + 8 k + i -- so the two
+// pieces (k = 0, 1) of a chunk are each read with fully coalesced 64-byte-per-lane loads.
+__host__ __device__ __forceinline__ int64_t stream_phys(int64_t logical) {
+    const int64_t r = logical & (SPMV_CHUNK - 1);
+    return (logical - r) + ((r >> 3) & 1) * (SPMV_CHUNK / 2) + (r >> 4) * SPMV_EPP + (r & 7);
+}
+
+// What a lane holds for one piece, loaded SPMV_DEPTH pieces ahead of its use.
+struct PieceRegs {
+    double a[SPMV_EPP];
+    unsigned c[SPMV_EPP];      // slab form: c[0..3] hold the 8 columns, 16 bit each; gather form: one column each
+    unsigned fw;               // first piece of a chunk only: start flags of the lane's 16 entries
+    int seg0;                  // first piece only: ordinal of the first segment that starts inside the chunk
+};
+
+template <bool SLAB>
+__device__ __forceinline__ void piece_load(const KRArgs &A, int64_t p, int64_t p_hi, PieceRegs &R) {
+    if (p >= p_hi) return;
+    const int64_t chunk = p >> 1;
+    const int64_t e = chunk * SPMV_CHUNK + (p & 1) * (SPMV_CHUNK / 2) + SPMV_EPP * lane_id();
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(R.a[0]), "=d"(R.a[1]), "=d"(R.a[2]), "=d"(R.a[3])
+                 : "l"(A.sval + e));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(R.a[4]), "=d"(R.a[5]), "=d"(R.a[6]), "=d"(R.a[7])
+                 : "l"(A.sval + e + 4));
+    if (SLAB) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(R.c[0]), "=r"(R.c[1]), "=r"(R.c[2]), "=r"(R.c[3])
+                     : "l"((const uint16_t *)A.scol + e));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(R.c[0]), "=r"(R.c[1]), "=r"(R.c[2]), "=r"(R.c[3])
+                     : "l"((const uint32_t *)A.scol + e));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(R.c[4]), "=r"(R.c[5]), "=r"(R.c[6]), "=r"(R.c[7])
+                     : "l"((const uint32_t *)A.scol + e + 4));
+    }
+    if ((p & 1) == 0) {
+        unsigned short fw;
+        asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(fw) : "l"(A.sflag + chunk * 32 + lane_id()));
+        R.fw = fw;
+        R.seg0 = __ldg(A.chunk_seg0 + chunk);
+    }
+}
+
+// bring slab `slab` of u into shared memory: one thread issues TMA bulk copies, everybody waits on the mbarrier
+__device__ __forceinline__ void slab_fetch(const KRArgs &A, const double *u, int slab, Smem &sm) {
+    const int col0 = slab * A.W;
+    int cnt = A.n - col0;
+    if (cnt > A.W) cnt = A.W;
+    const unsigned bytes = (unsigned)((cnt + 1) & ~1) * 8u;          // whole 16-byte units (the vectors are padded)
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");             // u was written through the generic proxy
+        mbar_expect_tx(sm.mbar, bytes);
+        constexpr unsigned PIECE = 32768;
+        for (unsigned off = 0; off < bytes; off += PIECE)
+            bulk_g2s((char *)sm.u + off, (const char *)(u + col0) + off, bytes - off < PIECE ? bytes - off : PIECE,
+                     sm.mbar);
+    }
+    mbar_wait(sm.mbar, sm.u_phase);
+    sm.u_phase ^= 1u;
+}
+
+// what a warp carries along its run of chunks (identical in all lanes)
+struct WarpRun {
+    double open;               // sum so far of the segment open at the end of the last chunk
+    double head;               // sum of the entries before the run's first flag
+    int seen, last;            // a segment start was seen; ordinal of the latest one
+};
+// what a lane carries through the pieces of a chunk
+struct LaneRun {
+    double cur, head;          // sum of the segment open at this point of the lane's run; sum before its first flag
+    unsigned fw;               // flags not yet consumed
+    int base, nseen;           // ordinal of the first segment starting in the lane's run; starts seen so far
+    int lower, total, seg0;    // flags in lower lanes / in the whole chunk; the chunk's first ordinal
+};
+
+// One piece: 8 products per lane, added to the lane's running segment; a start flag closes the open segment.
+template <bool SLAB>
+__device__ __forceinline__ void piece_process(const KRArgs &A, const double *u, const PieceRegs &R, const Smem &sm,
+                                              bool first_piece, LaneRun &L) {
+    const unsigned lane = lane_id();
+    if (first_piece) {
+        const int pc = __popc(R.fw);
+        int inc = pc;
 #pragma unroll
-    for (int k = 0; k < SPMV_NPT; ++k) {
-        const int idx = k * KR_THREADS + threadIdx.x;
-        if (idx < cnt) {
-            a[k] = ld_stream_f64(A.data + base + idx);
-            c[k] = ld_stream_s32(A.indices + base + idx);
-        } else {
-            a[k] = 0.0;
-            c[k] = 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, inc, o);
+            if ((int)lane >= o) inc += t;
         }
+        L.lower = inc - pc;
+        L.total = __shfl_sync(kFullMask, inc, 31);
+        L.seg0 = R.seg0;
+        L.base = R.seg0 + L.lower;
+        L.fw = R.fw;
+        L.cur = 0.0;
+        L.head = 0.0;
+        L.nseen = 0;
     }
-    // 2. rows that start inside the tile are [ra, rb); their pointers go to shared memory while the
-    //    matrix loads are in flight, so the reduction below never waits on global memory
-    const int ra = A.tile_ra[t], rb = A.tile_ra[t + 1];
-    const int n_rows = rb - ra;
-    const bool staged = n_rows < SPTR_CAP;
-    if (staged) {
-        for (int i = threadIdx.x; i <= n_rows; i += KR_THREADS) {
-            const int64_t rel = A.indptr[ra + i] - base;
-            s_ptr[i] = (int)(rel > cnt ? cnt + 1 : rel);              // cnt+1 marks "ends beyond this tile"
-        }
-    }
-    // 3. gather u[col], multiply, park the products
+    double x[SPMV_EPP];
+    if (SLAB) {
+        const double *su = sm.u;
 #pragma unroll
-    for (int k = 0; k < SPMV_NPT; ++k) {
-        const int idx = k * KR_THREADS + threadIdx.x;
-        if (idx < cnt) s_prod[idx] = a[k] * u[c[k]];
-    }
-    __syncthreads();
-    // 4. segmented reduction: item 0 is the head of a row begun in an earlier tile, item i>0 is row ra+i-1
-    const int n_items = n_rows + 1;
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    auto bounds = [&](int it, int &lo, int &hi, bool &complete) {
-        int p0, p1;
-        if (staged) {
-            p0 = (it == 0) ? 0 : s_ptr[it - 1];
-            p1 = s_ptr[it == 0 ? 0 : it];
-        } else {
-            const int64_t r0 = (it == 0) ? 0 : A.indptr[ra + it - 1] - base;
-            const int64_t r1 = A.indptr[ra + (it == 0 ? 0 : it)] - base;
-            p0 = (int)r0;
-            p1 = (int)(r1 > cnt ? cnt + 1 : r1);
-        }
-        lo = p0;
-        hi = p1 > cnt ? cnt : p1;
-        complete = p1 <= cnt;
-    };
-    if (n_items <= 8 * KR_WARPS) {
-        for (int it = warp; it < n_items; it += KR_WARPS) {
-            int lo, hi;
-            bool complete;
-            bounds(it, lo, hi, complete);
-            double s = 0.0;
-            for (int e = lo + (int)lane; e < hi; e += 32) s += s_prod[e];
-            s = warp_sum(s);
-            if (lane == 0) {
-                if (it == 0) A.head_part[t] = s;
-                else if (complete) A.q[A.row_lo + ra + it - 1] = s;
-                else A.tail_part[t] = s;
-            }
+        for (int i = 0; i < SPMV_EPP / 2; ++i) {
+            x[2 * i] = __dmul_rn(R.a[2 * i], su[R.c[i] & 0xffffu]);
+            x[2 * i + 1] = __dmul_rn(R.a[2 * i + 1], su[R.c[i] >> 16]);
         }
     } else {
-        for (int it = threadIdx.x; it < n_items; it += KR_THREADS) {
-            int lo, hi;
-            bool complete;
-            bounds(it, lo, hi, complete);
-            double s = 0.0;
-            for (int e = lo; e < hi; ++e) s += s_prod[e];
-            if (it == 0) A.head_part[t] = s;
-            else if (complete) A.q[A.row_lo + ra + it - 1] = s;
-            else A.tail_part[t] = s;
+#pragma unroll
+        for (int i = 0; i < SPMV_EPP; ++i) x[i] = __dmul_rn(R.a[i], u[R.c[i]]);
+    }
+    const unsigned bits = L.fw & 0xffu;
+    L.fw >>= 8;
+    if (bits == 0) {
+#pragma unroll
+        for (int i = 0; i < SPMV_EPP; ++i) L.cur = __dadd_rn(L.cur, x[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SPMV_EPP; ++i) {
+            if (bits & (1u << i)) {
+                if (L.nseen == 0) L.head = L.cur;
+                else A.qs[L.base + L.nseen - 1] = L.cur;
+                L.nseen += 1;
+                L.cur = x[i];
+            } else {
+                L.cur = __dadd_rn(L.cur, x[i]);
+            }
         }
+    }
+}
+
+// End of a chunk: stitch the 32 lane runs together (one segmented scan) and carry the open segment on.
+__device__ __forceinline__ void chunk_finish(const KRArgs &A, const LaneRun &L, WarpRun &run) {
+    const unsigned lane = lane_id();
+    if (L.total == 0) {                                // the whole chunk continues the open segment
+        run.open = __dadd_rn(run.open, warp_sum(L.cur));
+        return;
+    }
+    const bool seen = L.nseen > 0;
+    const unsigned any = __ballot_sync(kFullMask, seen);
+    const unsigned lt = lanemask_lt();
+    const unsigned le = any & (lt | (1u << lane));
+    const int start = le ? 31 - __clz(le) : 0;         // nearest lane at or below me holding a flag
+    double V = L.cur;                                  // lane sum since its last flag (all 16 entries if it has none)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFullMask, V, o);
+        if ((int)lane - o >= start) V = __dadd_rn(t, V);
+    }
+    double Oprev = __shfl_up_sync(kFullMask, V, 1);    // sum of the segment open at the end of the lane below
+    if (lane == 0) Oprev = 0.0;
+    const double closing = __dadd_rn(Oprev, L.head);   // the segment open at my start ends at my first flag
+    if (seen && L.lower > 0) A.qs[L.base - 1] = closing;
+    // the lane holding the chunk's first flag closes the run's open segment
+    const double chead = __shfl_sync(kFullMask, closing, __ffs(any) - 1);
+    const double rclose = __dadd_rn(run.open, chead);
+    if (!run.seen) run.head = rclose;
+    else if (lane == 0) A.qs[L.seg0 - 1] = rclose;
+    run.open = __shfl_sync(kFullMask, V, 31);
+    run.seen = 1;
+    run.last = L.seg0 + L.total - 1;
+}
+
+// One warp stitches the runs of the 16 warps over a part of the CTA's range: closes the segment that was
+// open when a run with flags began, carries the open segment forward, and writes the CTA's boundary
+// record after the last part.
+__device__ __forceinline__ void part_stitch(const KRArgs &A, const Smem &sm, int buf, bool last_part) {
+    const unsigned lane = lane_id();
+    const bool act = lane < KR_WARPS;
+    const WarpRecs &rec = sm.rec[buf];
+    const double head = act ? rec.head[lane] : 0.0;
+    const double tail = act ? rec.tail[lane] : 0.0;
+    const int seen = act ? rec.seen[lane] : 0;
+    const int first = act ? rec.first[lane] : 0;
+    const int lastv = act ? rec.last[lane] : 0;
+    const double open_in = sm.st->open;
+    const int seen_in = sm.st->seen;
+    int last_ord = sm.st->last_ord;
+    __syncwarp();
+    const unsigned fm = __ballot_sync(kFullMask, seen != 0);
+    const unsigned lt = lanemask_lt();
+    const unsigned le = fm & (lt | (1u << lane));
+    const int start = le ? 31 - __clz(le) : 0;
+    double V = seen ? tail : head;
+#pragma unroll
+    for (int o = 1; o < KR_WARPS; o <<= 1) {
+        const double t = __shfl_up_sync(kFullMask, V, o);
+        if ((int)lane - o >= start) V = __dadd_rn(t, V);
+    }
+    const double O = le ? V : __dadd_rn(open_in, V);               // open sum after warp `lane`'s run
+    double Oprev = __shfl_up_sync(kFullMask, O, 1);
+    if (lane == 0) Oprev = open_in;
+    if (act && seen) {
+        const double closing = __dadd_rn(Oprev, head);
+        if (!seen_in && !(fm & lt)) A.bnd_head[blockIdx.x] = closing;  // the CTA's first flag: closes its head
+        else A.qs[first - 1] = closing;
+    }
+    const double open_out = __shfl_sync(kFullMask, O, KR_WARPS - 1);
+    if (fm) last_ord = __shfl_sync(kFullMask, lastv, 31 - __clz(fm));
+    if (lane == 0) {
+        sm.st->open = open_out;
+        sm.st->seen = seen_in | (fm != 0);
+        sm.st->last_ord = last_ord;
+        if (last_part) {
+            const int b = blockIdx.x;
+            if (seen_in | (fm != 0)) {
+                A.bnd_tail[b] = open_out;
+                A.bnd_ord[b] = last_ord;
+                A.bnd_lr[b] = __ldg(A.seg_row + last_ord) % A.npad;
+                A.bnd_flag[b] = 1;
+            } else {
+                A.bnd_head[b] = open_out;
+                A.bnd_flag[b] = 0;
+            }
+        }
+    }
+}
+
+// The SpMV phase.  The CTA owns a contiguous range of chunks; it is cut into parts at slab boundaries
+// (almost always one part), and inside a part every warp streams its own contiguous run of chunks with no
+// block-wide synchronisation; the runs are stitched once per part.
+template <bool SLAB>
+__device__ __forceinline__ void phase_spmv(const KRArgs &A, const double *u, Smem &sm) {
+    const int64_t c_lo = A.n_sch * blockIdx.x / gridDim.x, c_hi = A.n_sch * (blockIdx.x + 1) / gridDim.x;
+    if (c_lo >= c_hi) {
+        if (threadIdx.x == 0) {
+            A.bnd_head[blockIdx.x] = 0.0;
+            A.bnd_flag[blockIdx.x] = 0;
+        }
+        return;
+    }
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        sm.st->open = 0.0;
+        sm.st->seen = 0;
+        sm.st->last_ord = -1;
+    }
+    for (int i = threadIdx.x; i <= A.S; i += KR_THREADS) sm.slab[i] = A.slab_c0[i];
+    __syncthreads();
+    int slab = 0, part = 0;
+    for (int64_t p_lo = c_lo; p_lo < c_hi; ++part) {
+        while (p_lo >= sm.slab[slab + 1]) ++slab;
+        const int64_t slab_end = sm.slab[slab + 1];
+        const int64_t p_hi = slab_end < c_hi ? slab_end : c_hi;
+        const int64_t n = p_hi - p_lo;
+        const int64_t w_lo = p_lo + n * warp / KR_WARPS, w_hi = p_lo + n * (warp + 1) / KR_WARPS;
+        const int64_t q_lo = 2 * w_lo, q_hi = 2 * w_hi;            // pieces
+        PieceRegs R0, R1, R2;
+        piece_load<SLAB>(A, q_lo, q_hi, R0);
+        piece_load<SLAB>(A, q_lo + 1, q_hi, R1);
+        piece_load<SLAB>(A, q_lo + 2, q_hi, R2);
+        // every gather of the previous part is behind that part's barrier, so the slab can be replaced
+        if (SLAB) slab_fetch(A, u, slab, sm);
+        WarpRun run;
+        run.open = 0.0;
+        run.head = 0.0;
+        run.seen = 0;
+        run.last = -1;
+        LaneRun L;
+        L.cur = L.head = 0.0;
+        L.fw = 0;
+        L.base = L.nseen = L.lower = L.total = L.seg0 = 0;
+        int first = 0;
+        if (q_lo < q_hi) first = R0.seg0;
+        // the ring has three stages and a chunk two pieces: six pieces (three chunks) per trip keep every index static
+        for (int64_t q = q_lo; q < q_hi; q += 6) {
+            piece_process<SLAB>(A, u, R0, sm, true, L);
+            piece_load<SLAB>(A, q + 3, q_hi, R0);
+            piece_process<SLAB>(A, u, R1, sm, false, L);
+            piece_load<SLAB>(A, q + 4, q_hi, R1);
+            chunk_finish(A, L, run);
+            if (q + 2 < q_hi) {
+                piece_process<SLAB>(A, u, R2, sm, true, L);
+                piece_load<SLAB>(A, q + 5, q_hi, R2);
+                piece_process<SLAB>(A, u, R0, sm, false, L);
+                piece_load<SLAB>(A, q + 6, q_hi, R0);
+                chunk_finish(A, L, run);
+            }
+            if (q + 4 < q_hi) {
+                piece_process<SLAB>(A, u, R1, sm, true, L);
+                piece_load<SLAB>(A, q + 7, q_hi, R1);
+                piece_process<SLAB>(A, u, R2, sm, false, L);
+                piece_load<SLAB>(A, q + 8, q_hi, R2);
+                chunk_finish(A, L, run);
+            }
+        }
+        if (lane_id() == 0) {
+            WarpRecs &rec = sm.rec[part & 1];
+            rec.head[warp] = run.seen ? run.head : run.open;
+            rec.tail[warp] = run.open;
+            rec.seen[warp] = run.seen;
+            rec.first[warp] = first;
+            rec.last[warp] = run.last;
+        }
+        __syncthreads();
+        if (warp == part % KR_WARPS) part_stitch(A, sm, part & 1, p_hi == c_hi);
+        p_lo = p_hi;
+    }
+    __syncthreads();                   // the next phase reuses the shared-memory reduction scratch
+}
+
+// Finish the segments that cross SpMV CTA ranges: the segment open at the end of CTA g's range is
+// its tail plus the heads of the following CTAs up to (and including) the first one that saw a flag.
+// The CTA that owns reduction chunk c does this for the rows of the chunk before it reads their sums.
+__device__ __forceinline__ void boundary_fix(const KRArgs &A, int c) {
+    const int64_t r0 = (int64_t)c * CHUNK - A.row_lo;              // local rows [r0, r0 + CHUNK)
+    for (int g = threadIdx.x; g < A.n_bnd; g += KR_THREADS) {
+        if (!__ldcg(A.bnd_flag + g)) continue;
+        const int lr = __ldcg(A.bnd_lr + g);
+        if (lr < r0 || lr >= r0 + CHUNK) continue;
+        double s = __ldcg(A.bnd_tail + g);
+        for (int g2 = g + 1; g2 < A.n_bnd; ++g2) {
+            s = __dadd_rn(s, __ldcg(A.bnd_head + g2));
+            if (__ldcg(A.bnd_flag + g2)) break;
+        }
+        A.qs[__ldcg(A.bnd_ord + g)] = s;
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ void phase_spmv(const KRArgs &A, double *s_prod, int *s_ptr) {
-    for (int64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) spmv_tile(A, A.u, t, s_prod, s_ptr);
+// (A u)[r]: the segment sums of global row r, added in slab order
+__device__ __forceinline__ double row_q(const KRArgs &A, int64_t r) {
+    const int64_t lr = r - A.row_lo;
+    double s = 0.0;
+    for (int k = 0; k < A.S; ++k) {
+        const int o = __ldg(A.seg_of + (int64_t)k * A.npad + lr);
+        if (o >= 0) s = __dadd_rn(s, __ldcg(A.qs + o));
+    }
+    return s;
 }
 
-// A row that straddles tiles leaves tail_part in its first tile and head_part in the following
-// ones; its value is their sum in tile order.  The straddling row of tile t, if any, is rb-1.
-__device__ __forceinline__ void fix_tile(const KRArgs &A, int64_t t) {
-    const int ra = A.tile_ra[t], rb = A.tile_ra[t + 1];
-    if (rb <= ra) return;
-    const int64_t rend = A.indptr[rb];
-    if (rend <= (t + 1) * SPMV_TILE) return;
-    const int64_t t_last = (rend - 1) / SPMV_TILE;
-    double s = A.tail_part[t];
-    for (int64_t t2 = t + 1; t2 <= t_last; ++t2) s += A.head_part[t2];
-    A.q[A.row_lo + rb - 1] = s;
-}
-
-// stand-alone form (b3c_spmv): all tiles
-__device__ __forceinline__ void phase_fix(const KRArgs &A) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < A.n_tiles; t += stride) fix_tile(A, t);
-}
-
-// fused form: the CTA that owns chunk c patches the straddling rows that fall inside the chunk
-// before it reads q, so no separate pass (and no extra grid barrier) is needed
-__device__ __forceinline__ void chunk_fixup(const KRArgs &A, int c) {
-    const int lc = c - A.row_lo / CHUNK;
-    const int t0 = A.chunk_t[lc], t1 = A.chunk_t[lc + 1];
-    for (int t = t0 + (int)threadIdx.x; t < t1; t += KR_THREADS) fix_tile(A, t);
-    __syncthreads();
-}
-
-// ---- vector phases: one CTA per 1024-row chunk, 4 rows per thread -----------------------------------
+// ---- vector phases: one CTA per 1024-row chunk, CHUNK_RPT rows per thread ------------------------
 #define KR_FOR_CHUNKS(c) for (int c = blockIdx.x; c < A.n_chunks; c += gridDim.x)
 #define KR_ROW(c, i) ((int64_t)(c) * CHUNK + (i) * KR_THREADS + threadIdx.x)
 
@@ -261,13 +587,13 @@ __device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
         if (loc) {
-            chunk_fixup(A, c);
+            boundary_fix(A, c);
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
                 if (r < A.row_hi) {
                     const double xx = A.x[r];
-                    double qq = A.q[r];
+                    double qq = row_q(A, r);
                     if (A.dfix[r] != 0.0) qq = __dadd_rn(qq, A.u[r]);          // zero diagonal counted as one (Q2)
                     const double vv = __dmul_rn(xx, qq);
                     const double rr = __dsub_rn(1.0, vv);
@@ -325,12 +651,12 @@ __device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
         if (loc) {
-            chunk_fixup(A, c);
+            boundary_fix(A, c);
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
                 if (r < A.row_hi) {
-                    double qq = A.q[r];
+                    double qq = row_q(A, r);
                     if (A.dfix[r] != 0.0) qq = __dadd_rn(qq, A.u[r]);
                     const double pp = A.p[r];
                     const double ww = __dadd_rn(__dmul_rn(A.x[r], qq), __dmul_rn(A.v[r], pp));
@@ -406,7 +732,7 @@ __device__ __forceinline__ void phase_update(const KRArgs &A, int ymode, double 
     }
 }
 
-// ---- scalar logic (identical in every thread) -----------------------------------------------------
+// ---- scalar logic ------------------------------------------------------------------------------------
 // after a residual phase: rho = rk.rk; first call initialises, later calls close an outer step
 __device__ __forceinline__ void scalar_outer(KRScalars &S, double rho, bool first) {
     const double g = 0.9, etamax = 0.1;
@@ -447,7 +773,59 @@ __device__ __forceinline__ bool scalar_decide(KRScalars &S, double ymin, double 
     return false;
 }
 
+// ---- loop control ------------------------------------------------------------------------------------
+// One decision at a time on the reduced partials r[]; leaves the next thing to do in S.state.  Shared by the
+// persistent kernel and the phase-at-a-time form (k_krp_scalar), so both take exactly the same branches.
+enum { KRP_INIT = 0, KRP_SPMV, KRP_RESID, KRP_DIR, KRP_W, KRP_STEP, KRP_UPDATE };
+enum { KRS_OUTER_FIRST = 0, KRS_OUTER, KRS_ALPHA, KRS_DECIDE };
+enum { KR_STATE_DONE = 0, KR_STATE_INNER = 1, KR_STATE_UPDATE = 2 };
+
+__device__ __forceinline__ void scalar_step(KRScalars &S, int which, const double *r) {
+    if (which == KRS_OUTER_FIRST || which == KRS_OUTER) {          // r[0] = rk.rk
+        scalar_outer(S, r[0], which == KRS_OUTER_FIRST);
+        S.n_spmv += 1;
+        if (S.rout > S.rt && S.n_iter < S.max_iter) {              // sparse_utils.py:146
+            S.outer += 1;
+            S.k = 0;
+            S.ymode = 0;
+            S.inner_tol = fmax(S.rout * S.eta * S.eta, S.rt);
+            if (S.rho_km1 > S.inner_tol) {                         // sparse_utils.py:154
+                S.k = 1;
+                S.state = KR_STATE_INNER;
+            } else {
+                S.state = KR_STATE_UPDATE;
+            }
+        } else {
+            S.state = KR_STATE_DONE;
+        }
+    } else if (which == KRS_ALPHA) {                               // r[0] = p.w, r[1] = rk.Z of the first step
+        if (S.k == 1) S.rho_km1 = r[1];                            // sparse_utils.py:160
+        S.alpha = S.rho_km1 / r[0];                                // sparse_utils.py:166
+        S.n_spmv += 1;
+    } else if (which == KRS_DECIDE) {                              // r = rk.Z, min y, -max y, both clamp factors
+        bool stop = scalar_decide(S, r[1], -r[2], r[3], r[4], r[0]);
+        if (!stop && S.k >= S.max_iter + 8) {                      // safety net: the reference's inner loop is unbounded
+            S.status = B3C_ERR_NOCONV;
+            stop = true;
+        }
+        if (S.status != 0) {
+            S.state = KR_STATE_DONE;
+        } else if (stop) {
+            S.state = KR_STATE_UPDATE;
+        } else if (S.rho_km1 > S.inner_tol) {
+            S.k += 1;
+            S.beta = S.rho_km1 / S.rho_km2;
+            S.state = KR_STATE_INNER;
+        } else {
+            S.state = KR_STATE_UPDATE;
+        }
+    }
+}
+
 // ---- the persistent kernel ---------------------------------------------------------------------------
+// The loop scalars live in shared memory: thread 0 updates them between block barriers, everybody reads
+// them; all CTAs compute identical values from the same partials.  One trip of the loop is
+// "make u | SpMV | consume": init or update -> residual (an outer Newton step), direction -> w, step (a CG step).
 #define KR_PHASE(id, call)                                                     \
     do {                                                                       \
         const long long t0_ = clock64();                                       \
@@ -460,77 +838,63 @@ __device__ __forceinline__ bool scalar_decide(KRScalars &S, double ymin, double 
             A.timers->sync[id] += t2_ - t1_;                                   \
         }                                                                      \
     } while (0)
+// a decision taken by thread 0 on the shared scalars, then published to the CTA
+#define KR_SCALAR(which, r)                                                    \
+    do {                                                                       \
+        const long long ts_ = clock64();                                       \
+        if (threadIdx.x == 0) scalar_step(S, which, r);                        \
+        __syncthreads();                                                       \
+        if (timing) A.timers->work[T_SCALAR] += clock64() - ts_;               \
+    } while (0)
 
-__global__ void __launch_bounds__(KR_THREADS, KR_MIN_CTAS) k_kr_persistent(KRArgs A) {
+template <bool SLAB>
+__global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double s_prod[SPMV_TILE];
-    __shared__ int s_ptr[SPTR_CAP + 1];
-    __shared__ double s_red[KR_WARPS * RED_MAX];
-    KRScalars S = *A.ctl;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem sm = carve_smem(smem_raw);
+    double *s_red = sm.red;
+    KRScalars &S = *sm.ctl;
+    if (threadIdx.x == 0) {
+        S = *A.ctl;
+        if (SLAB) mbar_init(sm.mbar, 1);
+    }
+    __syncthreads();
     const int nc = A.n_chunks;
     double *ybuf[2] = {A.y0, A.y1};
     const bool timing = (blockIdx.x == 0 && threadIdx.x == 0);
     const long long t_begin = clock64();
-    long long ts_ = 0;
 
-    KR_PHASE(T_INIT, phase_init(A));
-    KR_PHASE(T_SPMV, phase_spmv(A, s_prod, s_ptr));
-    KR_PHASE(T_RESID, phase_resid(A, s_red));
-    S.n_spmv = 1;
-    {
-        double r[1];
-        const int ids[1] = {PA};
-        reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
-        scalar_outer(S, r[0], true);
-    }
-
-    while (S.rout > S.rt && S.n_iter < S.max_iter) {      // sparse_utils.py:146
-        S.outer += 1;
-        S.k = 0;
-        S.ymode = 0;
-        S.inner_tol = fmax(S.rout * S.eta * S.eta, S.rt);
-        while (S.rho_km1 > S.inner_tol) {                 // sparse_utils.py:154
-            S.k += 1;
-            const bool first = (S.k == 1);
-            if (!first) S.beta = S.rho_km1 / S.rho_km2;
-            double *ycur = ybuf[S.ysel], *ynew = ybuf[S.ysel ^ 1];
-            KR_PHASE(T_DIR, phase_dir(A, first, S.beta, ycur, s_red));
-            KR_PHASE(T_SPMV, phase_spmv(A, s_prod, s_ptr));
+    int mode = -1;                                        // -1: first trip (x = 1)
+    for (;;) {
+        if (mode < 0) KR_PHASE(T_INIT, phase_init(A));
+        else if (mode == KR_STATE_INNER) KR_PHASE(T_DIR, phase_dir(A, S.k == 1, S.beta, ybuf[S.ysel], s_red));
+        else KR_PHASE(T_UPDATE, phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
+        KR_PHASE(T_SPMV, phase_spmv<SLAB>(A, A.u, sm));
+        if (mode == KR_STATE_INNER) {
             KR_PHASE(T_W, phase_w(A, s_red));
-            S.n_spmv += 1;
-            ts_ = clock64();
             {
                 double r[2];
                 const int ids[2] = {PA, PB};
                 reduce_parts<2, 0>(A.part, nc, ids, r, s_red);
-                if (first) S.rho_km1 = r[1];              // rk.Z of the first step (sparse_utils.py:160)
-                S.alpha = S.rho_km1 / r[0];               // rho / p.w (sparse_utils.py:166)
+                KR_SCALAR(KRS_ALPHA, r);
             }
-            if (timing) A.timers->work[T_SCALAR] += clock64() - ts_;
-            KR_PHASE(T_STEP, phase_step(A, S.alpha, S.delta, S.Delta, ycur, ynew, s_red));
-            ts_ = clock64();
-            double r[5];
+            KR_PHASE(T_STEP, phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red));
             {
+                double r[5];
                 const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
                 reduce_parts<1, 4>(A.part, nc, ids, r, s_red);
+                KR_SCALAR(KRS_DECIDE, r);
             }
-            if (timing) A.timers->work[T_SCALAR] += clock64() - ts_;
-            if (scalar_decide(S, r[1], -r[2], r[3], r[4], r[0])) break;
-            if (S.k >= S.max_iter + 8) {                  // safety net: the reference's inner loop is unbounded
-                S.status = B3C_ERR_NOCONV;
-                break;
-            }
+        } else {
+            KR_PHASE(T_RESID, phase_resid(A, s_red));
+            double r[1];
+            const int ids[1] = {PA};
+            reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
+            KR_SCALAR(mode < 0 ? KRS_OUTER_FIRST : KRS_OUTER, r);
         }
-        if (S.status != 0) break;
-        // with ymode 2 the step was not accepted: ycur still holds y; with ymode 1 ysel was flipped
-        KR_PHASE(T_UPDATE, phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
-        KR_PHASE(T_SPMV, phase_spmv(A, s_prod, s_ptr));
-        KR_PHASE(T_RESID, phase_resid(A, s_red));
-        S.n_spmv += 1;
-        double r[1];
-        const int ids[1] = {PA};
-        reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
-        scalar_outer(S, r[0], false);
+        mode = S.state;
+        if (mode == KR_STATE_DONE) break;
+        __syncthreads();                                  // everybody has read the state before thread 0 moves on
     }
     if (timing) {
         *A.ctl = S;
@@ -538,35 +902,150 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MIN_CTAS) k_kr_persistent(KRArg
     }
 }
 
-// ---- stand-alone kernels (plan, microbench SpMV, host-driven phases) -----------------------------
-__global__ void k_tile_plan(int32_t n_local, const int64_t *__restrict__ indptr, int64_t n_tiles,
-                            int32_t *__restrict__ tile_ra) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    if (t == n_tiles) {
-        tile_ra[t] = n_local;
+// ---- building the stream (once per balancing run) ---------------------------------------------------
+// Columns are sorted within a row, so the entries of row r that fall in slab s are one contiguous
+// segment.  Pass 1 counts the segment lengths into cnt[s * npad + r]; the slab totals are padded to
+// whole tiles; an exclusive scan gives the position vp of every cell; a second scan numbers the
+// non-empty cells; pass 2 copies the segments.  A warp walks one row in 32-entry windows; a lane whose
+// slab differs from its left neighbour's starts a segment.
+// set the start flag of logical stream position `pos` (bit pos % 16 of the lane's 16-bit word)
+__device__ __forceinline__ void stream_set_flag(uint16_t *sflag, int64_t pos) {
+    const int64_t w16 = pos >> 4;                      // chunk * 32 + lane
+    atomicOr((unsigned *)sflag + (w16 >> 1), (1u << (pos & 15)) << ((w16 & 1) * 16));
+}
+
+template <bool FILL, bool SLAB>
+__global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restrict__ cnt, double *__restrict__ sval,
+                                                     void *__restrict__ scol_v, uint16_t *__restrict__ sflag) {
+    const unsigned lane = lane_id();
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    const int n_local = A.row_hi - A.row_lo;
+    const int W = A.W;
+    bool bad = false;
+    for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < n_local; lr += nw) {
+        const int64_t lo = A.indptr[lr], hi = A.indptr[lr + 1];
+        int carry_s = -1;
+        int64_t carry_start = lo;
+        for (int64_t e0 = lo; e0 < hi; e0 += 32) {
+            const int64_t e = e0 + lane;
+            const bool valid = e < hi;
+            int col = valid ? A.indices[e] : 0;
+            if (col < 0 || col >= A.n) {           // reported through ctl->status; clamped to stay in bounds
+                bad = true;
+                col = col < 0 ? 0 : A.n - 1;
+            }
+            const int s = valid ? col / W : 0x7fffffff;
+            int sp = __shfl_up_sync(kFullMask, s, 1);
+            if (lane == 0) sp = carry_s;
+            const bool flag = valid && (s != sp);
+            bad |= valid && s < sp;
+            const unsigned fm = __ballot_sync(kFullMask, flag);
+            const unsigned below = fm & lanemask_lt();
+            if (!FILL) {
+                if (flag && sp >= 0) {             // this entry closes the segment of slab sp
+                    const int64_t prev_start = below ? e0 + (31 - __clz(below)) : carry_start;
+                    cnt[(int64_t)sp * A.npad + lr] = e - prev_start;
+                }
+            } else if (valid) {
+                const unsigned upto = fm & (lanemask_lt() | (1u << lane));
+                const int64_t seg_start = upto ? e0 + (31 - __clz(upto)) : carry_start;
+                const int64_t dst = A.vp[(int64_t)s * A.npad + lr] + (e - seg_start);
+                const int64_t ph = stream_phys(dst);
+                sval[ph] = A.data[e];
+                const unsigned lc = (unsigned)(col - s * W);
+                if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
+                else ((uint32_t *)scol_v)[ph] = lc;
+                if (e == seg_start) stream_set_flag(sflag, dst);
+            }
+            if (fm) carry_start = e0 + (31 - __clz(fm));
+            const int last = (int)((hi - 1 - e0) < 31 ? (hi - 1 - e0) : 31);
+            carry_s = __shfl_sync(kFullMask, s, last);
+        }
+        if (!FILL && hi > lo && lane == 0) cnt[(int64_t)carry_s * A.npad + lr] = hi - carry_start;
+    }
+    if (!FILL && bad) A.ctl->status = B3C_ERR_ARG;     // unsorted or out-of-range columns
+}
+
+// one CTA per slab: pad the slab's entry count to whole tiles (the padding belongs to its last cell)
+__global__ void __launch_bounds__(256) k_slab_pad(KRArgs A, int64_t *__restrict__ cnt) {
+    __shared__ int64_t s_w[33];
+    const int s = blockIdx.x;
+    int64_t v = 0;
+    for (int64_t i = threadIdx.x; i < A.npad; i += 256) v += cnt[(int64_t)s * A.npad + i];
+    int64_t tot;
+    block_scan_excl<int64_t>(v, s_w, &tot);
+    if (threadIdx.x == 0) {
+        const int64_t pad = (SPMV_TILE - tot % SPMV_TILE) % SPMV_TILE;
+        cnt[(int64_t)s * A.npad + A.npad - 1] += pad;
+    }
+}
+
+// flag[v] = 1 if cell v has entries (a second scan numbers the segments)
+__global__ void __launch_bounds__(256) k_cell_flags(int64_t nv, const int64_t *__restrict__ vp, int64_t *__restrict__ flag) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nv) flag[v] = vp[v + 1] > vp[v] ? 1 : 0;
+}
+
+// seg_of / seg_row from the numbering
+__global__ void __launch_bounds__(256) k_cell_index(int64_t nv, const int64_t *__restrict__ vp,
+                                                    const int64_t *__restrict__ ord, int32_t *__restrict__ seg_of,
+                                                    int32_t *__restrict__ seg_row) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    if (vp[v + 1] > vp[v]) {
+        seg_of[v] = (int32_t)ord[v];
+        seg_row[ord[v]] = (int32_t)v;
+    } else {
+        seg_of[v] = -1;
+    }
+}
+
+// first chunk of every slab; zero the last tile of every slab (its padding; the fill overwrites the real part);
+// flag the first entry of the slab's last cell in case it consists of padding only
+template <bool SLAB>
+__global__ void __launch_bounds__(256) k_slab_finish(KRArgs A, double *__restrict__ sval, void *__restrict__ scol_v,
+                                                     uint16_t *__restrict__ sflag, int32_t *__restrict__ slab_t0) {
+    const int s = blockIdx.x;
+    if (s == A.S) {
+        if (threadIdx.x == 0) slab_t0[s] = (int32_t)(A.vp[A.nv] / SPMV_CHUNK);
         return;
     }
-    const int64_t base = t * SPMV_TILE;
-    int lo = 0, hi = n_local;                 // first r in [0, n_local] with indptr[r] >= base
+    const int64_t begin = A.vp[(int64_t)s * A.npad], end = A.vp[(int64_t)(s + 1) * A.npad];
+    if (threadIdx.x == 0) slab_t0[s] = (int32_t)(begin / SPMV_CHUNK);
+    const int64_t z0 = end - begin >= SPMV_TILE ? end - SPMV_TILE : begin;
+    for (int64_t i = z0 + threadIdx.x; i < end; i += 256) {
+        sval[i] = 0.0;
+        if (SLAB) ((uint16_t *)scol_v)[i] = 0;
+        else ((uint32_t *)scol_v)[i] = 0;
+    }
+    __syncthreads();
+    const int64_t last = A.vp[(int64_t)(s + 1) * A.npad - 1];
+    if (threadIdx.x == 0 && last < end) stream_set_flag(sflag, last);
+}
+
+// chunk_seg0[c] = ordinal of the first segment that starts at or after entry c * 128
+__global__ void __launch_bounds__(256) k_chunk_seg0(int64_t n_chunks, int64_t nv, const int64_t *__restrict__ vp,
+                                                    const int64_t *__restrict__ ord, int32_t *__restrict__ chunk_seg0) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const int64_t pos = c * SPMV_CHUNK;
+    int64_t lo = 0, hi = nv;                  // first cell in [0, nv] with vp[cell] >= pos
     while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (indptr[mid] >= base) hi = mid;
+        const int64_t mid = (lo + hi) >> 1;
+        if (vp[mid] >= pos) hi = mid;
         else lo = mid + 1;
     }
-    tile_ra[t] = lo;
+    chunk_seg0[c] = (int32_t)ord[lo];
 }
 
 // dfix[r] = 1 where the diagonal entry of (global) row r is absent or zero (sparse_utils.py:110-115)
-__global__ void __launch_bounds__(KR_THREADS) k_diag_fix(int32_t row_lo, int32_t row_hi,
-                                                         const int64_t *__restrict__ indptr,
-                                                         const int32_t *__restrict__ indices,
-                                                         const double *__restrict__ data, double *__restrict__ dfix,
-                                                         KRScalars *ctl) {
+__global__ void __launch_bounds__(256) k_diag_fix(int32_t row_lo, int32_t row_hi, const int64_t *__restrict__ indptr,
+                                                  const int32_t *__restrict__ indices, const double *__restrict__ data,
+                                                  double *__restrict__ dfix, KRScalars *ctl) {
     const unsigned lane = lane_id();
-    const int64_t nw = (int64_t)gridDim.x * KR_WARPS;
+    const int64_t nw = (int64_t)gridDim.x * 8;
     unsigned nz = 0;
-    for (int64_t lr = (int64_t)blockIdx.x * KR_WARPS + (threadIdx.x >> 5); lr < row_hi - row_lo; lr += nw) {
+    for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < row_hi - row_lo; lr += nw) {
         const int64_t lo = indptr[lr], hi = indptr[lr + 1];
         const int32_t gr = row_lo + (int32_t)lr;
         double d = 0.0;           // duplicates of the diagonal would be summed by scipy's diagonal()
@@ -582,32 +1061,27 @@ __global__ void __launch_bounds__(KR_THREADS) k_diag_fix(int32_t row_lo, int32_t
     if (lane == 0 && nz) atomicAdd((unsigned long long *)&ctl->zero_diag, (unsigned long long)nz);
 }
 
-// chunk_t[lc] = first tile t with tile_ra[t+1] > lc*CHUNK, i.e. whose last-starting row is at or
-// beyond the chunk's first local row; chunk_t[n_local_chunks] = n_tiles
-__global__ void k_chunk_plan(int32_t n_local_chunks, int64_t n_tiles, const int32_t *__restrict__ tile_ra,
-                             int32_t *__restrict__ chunk_t) {
-    const int lc = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lc > n_local_chunks) return;
-    if (lc == n_local_chunks) {
-        chunk_t[lc] = (int32_t)n_tiles;
-        return;
+// ---- stand-alone kernels (microbench SpMV, host-driven phases) ------------------------------------
+template <bool SLAB>
+__global__ void __launch_bounds__(KR_THREADS, 1) k_spmv(KRArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem sm = carve_smem(smem_raw);
+    if (SLAB) {
+        if (threadIdx.x == 0) mbar_init(sm.mbar, 1);
+        __syncthreads();
     }
-    const int64_t r0 = (int64_t)lc * CHUNK;
-    int64_t lo = 0, hi = n_tiles;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t)tile_ra[mid + 1] > r0) hi = mid;
-        else lo = mid + 1;
+    phase_spmv<SLAB>(A, A.u, sm);
+}
+// y[r] = (A u)[r] (b3c_spmv): one CTA per reduction chunk
+__global__ void __launch_bounds__(KR_THREADS) k_spmv_collect(KRArgs A, double *__restrict__ y) {
+    const int c = blockIdx.x;
+    boundary_fix(A, c);
+#pragma unroll
+    for (int i = 0; i < CHUNK_RPT; ++i) {
+        const int64_t r = KR_ROW(c, i);
+        if (r >= A.row_lo && r < A.row_hi) y[r] = row_q(A, r);
     }
-    chunk_t[lc] = (int32_t)lo;
 }
-
-__global__ void __launch_bounds__(KR_THREADS) k_spmv(KRArgs A) {
-    __shared__ double s_prod[SPMV_TILE];
-    __shared__ int s_ptr[SPTR_CAP + 1];
-    phase_spmv(A, s_prod, s_ptr);
-}
-__global__ void __launch_bounds__(KR_THREADS) k_spmv_fix(KRArgs A) { phase_fix(A); }
 
 // ---- phase-at-a-time form (multi-GPU row-block driver) ------------------------------------------
 // The driver all-reduces u with SUM, so the slices a rank does not own must hold zeros.
@@ -623,13 +1097,7 @@ __device__ __forceinline__ void zero_nonlocal_u(const KRArgs &A) {
     }
 }
 
-enum { KRP_INIT = 0, KRP_SPMV, KRP_RESID, KRP_DIR, KRP_W, KRP_STEP, KRP_UPDATE };
-enum { KRS_OUTER_FIRST = 0, KRS_OUTER, KRS_ALPHA, KRS_DECIDE };
-enum { KR_STATE_DONE = 0, KR_STATE_INNER = 1, KR_STATE_UPDATE = 2 };
-
 __global__ void __launch_bounds__(KR_THREADS) k_krp_phase(KRArgs A, int phase) {
-    __shared__ double s_prod[SPMV_TILE];
-    __shared__ int s_ptr[SPTR_CAP + 1];
     __shared__ double s_red[KR_WARPS * RED_MAX];
     const KRScalars S = *A.ctl;                 // only k_krp_scalar writes the control block
     double *ybuf[2] = {A.y0, A.y1};
@@ -637,9 +1105,6 @@ __global__ void __launch_bounds__(KR_THREADS) k_krp_phase(KRArgs A, int phase) {
         case KRP_INIT:
             phase_init(A);
             zero_nonlocal_u(A);
-            break;
-        case KRP_SPMV:
-            phase_spmv(A, s_prod, s_ptr);
             break;
         case KRP_RESID:
             phase_resid(A, s_red);
@@ -668,54 +1133,23 @@ __global__ void __launch_bounds__(KR_THREADS) k_krp_scalar(KRArgs A, int which) 
     __shared__ double s_red[KR_WARPS * RED_MAX];
     KRScalars S = *A.ctl;
     const int nc = A.n_chunks;
+    double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (which == KRS_OUTER_FIRST || which == KRS_OUTER) {
-        double r[1];
+        double t[1];
         const int ids[1] = {PA};
-        reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
-        scalar_outer(S, r[0], which == KRS_OUTER_FIRST);
-        S.n_spmv += 1;
-        if (S.rout > S.rt && S.n_iter < S.max_iter) {          // sparse_utils.py:146
-            S.outer += 1;
-            S.k = 0;
-            S.ymode = 0;
-            S.inner_tol = fmax(S.rout * S.eta * S.eta, S.rt);
-            if (S.rho_km1 > S.inner_tol) {                     // sparse_utils.py:154
-                S.k = 1;
-                S.state = KR_STATE_INNER;
-            } else {
-                S.state = KR_STATE_UPDATE;
-            }
-        } else {
-            S.state = KR_STATE_DONE;
-        }
+        reduce_parts<1, 0>(A.part, nc, ids, t, s_red);
+        r[0] = t[0];
     } else if (which == KRS_ALPHA) {
-        double r[2];
+        double t[2];
         const int ids[2] = {PA, PB};
-        reduce_parts<2, 0>(A.part, nc, ids, r, s_red);
-        if (S.k == 1) S.rho_km1 = r[1];
-        S.alpha = S.rho_km1 / r[0];
-        S.n_spmv += 1;
-    } else if (which == KRS_DECIDE) {
-        double r[5];
+        reduce_parts<2, 0>(A.part, nc, ids, t, s_red);
+        r[0] = t[0];
+        r[1] = t[1];
+    } else {
         const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
         reduce_parts<1, 4>(A.part, nc, ids, r, s_red);
-        bool stop = scalar_decide(S, r[1], -r[2], r[3], r[4], r[0]);
-        if (!stop && S.k >= S.max_iter + 8) {
-            S.status = B3C_ERR_NOCONV;
-            stop = true;
-        }
-        if (S.status != 0) {
-            S.state = KR_STATE_DONE;
-        } else if (stop) {
-            S.state = KR_STATE_UPDATE;
-        } else if (S.rho_km1 > S.inner_tol) {
-            S.k += 1;
-            S.beta = S.rho_km1 / S.rho_km2;
-            S.state = KR_STATE_INNER;
-        } else {
-            S.state = KR_STATE_UPDATE;
-        }
     }
+    scalar_step(S, which, r);
     if (threadIdx.x == 0) *A.ctl = S;
 }
 
@@ -723,31 +1157,57 @@ static std::mutex g_krp_mu;
 static std::unordered_map<void *, KRArgs> g_krp;
 
 // ---- workspace ---------------------------------------------------------------------------------------
+// tuning / test hooks (b3c_set_option): slab width cap and slab count cap of the SpMV operand
+static std::atomic<int> g_slab_w_max{SLAB_W_MAX};
+static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
+constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
+
 struct KRLayout {
-    int64_t n_tiles, o_tile_ra, o_chunk_t, o_head, o_tail, o_dfix, o_vec, o_part, o_ctl, o_timers, total;
-    int32_t n_chunks;
+    int32_t slab, S, W, n_chunks;
+    int64_t nvec;                       // elements per (padded) vector
+    int64_t nv_max, nnzv_max, nseg_max;
+    int64_t o_dfix, o_vec, o_qs, o_part, o_ctl, o_timers, o_bnd;
+    int64_t o_cnt, o_vp, o_ord, o_scan, o_slab_t0, o_sval, o_scol, o_sflag, o_seg0, o_seg_of, o_seg_row, total;
 };
+
 static KRLayout kr_layout(int32_t n, int64_t nnz) {
     KRLayout L;
     Carver c;
-    L.n_tiles = ceil_div(nnz, SPMV_TILE);
-    if (L.n_tiles < 1) L.n_tiles = 1;
+    const int64_t s_need = ceil_div(n, g_slab_w_max.load());
+    L.slab = s_need <= g_slab_s_max.load() ? 1 : 0;
+    L.S = L.slab ? (int32_t)s_need : 1;
+    L.W = L.slab ? (int32_t)align_up(ceil_div(n, L.S), 2) : n;
+    const int64_t npad_max = align_up(n, CHUNK);
+    L.nv_max = (int64_t)L.S * npad_max;
+    L.nnzv_max = align_up(nnz, SPMV_TILE) + (int64_t)L.S * SPMV_TILE;
+    L.nseg_max = (nnz + L.S < L.nv_max ? nnz + L.S : L.nv_max) + 1;
     L.n_chunks = (int32_t)ceil_div(n, CHUNK);
-    L.o_tile_ra = c.take((L.n_tiles + 1) * 4);
-    L.o_chunk_t = c.take(((int64_t)L.n_chunks + 2) * 4);
-    L.o_head = c.take(L.n_tiles * 8);
-    L.o_tail = c.take(L.n_tiles * 8);
+    L.nvec = align_up(n, 32);
     L.o_dfix = c.take((int64_t)n * 8);
-    L.o_vec = c.take((int64_t)n * 8 * 10);
+    L.o_vec = c.take(L.nvec * 8 * 9);
+    L.o_qs = c.take(L.nseg_max * 8);
     L.o_part = c.take((int64_t)L.n_chunks * 8 * P_COUNT);
     L.o_ctl = c.take(sizeof(KRScalars));
     L.o_timers = c.take(sizeof(KRTimers));
+    L.o_bnd = c.take((int64_t)BND_MAX * (8 + 8 + 4 + 4 + 4));
+    L.o_cnt = c.take((L.nv_max + 1) * 8);
+    L.o_vp = c.take((L.nv_max + 1) * 8);
+    L.o_ord = c.take((L.nv_max + 1) * 8);
+    L.o_scan = c.take(scan_tmp_elems(L.nv_max) * 8);
+    L.o_slab_t0 = c.take((SLAB_S_MAX + 2) * 4);
+    L.o_sval = c.take(L.nnzv_max * 8);
+    L.o_scol = c.take(L.nnzv_max * (L.slab ? 2 : 4));
+    L.o_sflag = c.take(L.nnzv_max / 8 + 64);
+    L.o_seg0 = c.take((L.nnzv_max / SPMV_CHUNK + 1) * 4);
+    L.o_seg_of = c.take(L.nv_max * 4);
+    L.o_seg_row = c.take(L.nseg_max * 4);
     L.total = c.cur;
     return L;
 }
 
 static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz,
                     const int64_t *indptr, const int32_t *indices, const double *data) {
+    const int32_t n_local = row_hi - row_lo;
     A.n = n;
     A.row_lo = row_lo;
     A.row_hi = row_hi;
@@ -755,50 +1215,162 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.indptr = indptr;
     A.indices = indices;
     A.data = data;
-    A.n_tiles = L.n_tiles;
-    A.tile_ra = (int32_t *)(ws + L.o_tile_ra);
-    A.chunk_t = (int32_t *)(ws + L.o_chunk_t);
-    A.head_part = (double *)(ws + L.o_head);
-    A.tail_part = (double *)(ws + L.o_tail);
+    A.slab = L.slab;
+    A.S = L.S;
+    A.W = L.W;
+    A.npad = (int32_t)align_up(n_local, CHUNK);
+    A.nv = (int64_t)L.S * A.npad;
+    A.nnzv = 0;                                        // known after the scan (kr_prepare)
+    A.n_sch = 0;
+    A.n_seg = 0;
+    A.sval = (const double *)(ws + L.o_sval);
+    A.scol = (const void *)(ws + L.o_scol);
+    A.sflag = (const uint16_t *)(ws + L.o_sflag);
+    A.chunk_seg0 = (const int32_t *)(ws + L.o_seg0);
+    A.seg_of = (const int32_t *)(ws + L.o_seg_of);
+    A.seg_row = (const int32_t *)(ws + L.o_seg_row);
+    A.slab_c0 = (const int32_t *)(ws + L.o_slab_t0);
+    A.qs = (double *)(ws + L.o_qs);
+    A.n_bnd = 0;
+    char *b = ws + L.o_bnd;
+    A.bnd_head = (double *)b;
+    A.bnd_tail = (double *)(b + (int64_t)BND_MAX * 8);
+    A.bnd_flag = (int32_t *)(b + (int64_t)BND_MAX * 16);
+    A.bnd_ord = (int32_t *)(b + (int64_t)BND_MAX * 20);
+    A.bnd_lr = (int32_t *)(b + (int64_t)BND_MAX * 24);
+    A.cnt = (int64_t *)(ws + L.o_cnt);
+    A.vp = (int64_t *)(ws + L.o_vp);
+    A.ord = (int64_t *)(ws + L.o_ord);
+    A.scan_tmp = (int64_t *)(ws + L.o_scan);
     A.dfix = (double *)(ws + L.o_dfix);
     double *vec = (double *)(ws + L.o_vec);
     A.x = vec;
-    A.v = vec + (int64_t)n * 1;
-    A.rk = vec + (int64_t)n * 2;
-    A.y0 = vec + (int64_t)n * 3;
-    A.y1 = vec + (int64_t)n * 4;
-    A.p = vec + (int64_t)n * 5;
-    A.Z = vec + (int64_t)n * 6;
-    A.w = vec + (int64_t)n * 7;
-    A.u = vec + (int64_t)n * 8;
-    A.q = vec + (int64_t)n * 9;
+    A.v = vec + L.nvec * 1;
+    A.rk = vec + L.nvec * 2;
+    A.y0 = vec + L.nvec * 3;
+    A.y1 = vec + L.nvec * 4;
+    A.p = vec + L.nvec * 5;
+    A.Z = vec + L.nvec * 6;
+    A.w = vec + L.nvec * 7;
+    A.u = vec + L.nvec * 8;
     A.part = (double *)(ws + L.o_part);
     A.n_chunks = L.n_chunks;
     A.ctl = (KRScalars *)(ws + L.o_ctl);
     A.timers = (KRTimers *)(ws + L.o_timers);
 }
 
-static int persistent_grid(int *grid_out) {
+static unsigned row_warp_grid(int64_t n_rows) {
+    int64_t blocks = ceil_div(n_rows > 0 ? n_rows : 1, 8);
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    return (unsigned)blocks;
+}
+
+template <bool SLAB>
+static int persistent_grid_of(int *grid_out) {
     static int cached = 0;
     if (!cached) {
         int per_sm = 0, dev = 0, sms = 0;
+        const int smem = SLAB ? SM_BYTES_SLAB : SM_BYTES_GATHER;
         B3C_CUDA(cudaGetDevice(&dev));
         B3C_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kr_persistent, KR_THREADS, 0));
+        B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        B3C_CUDA(cudaFuncSetAttribute(k_spmv<SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kr_persistent<SLAB>, KR_THREADS, smem));
         if (per_sm < 1) {
             set_error("persistent KR kernel does not fit on an SM");
             return B3C_ERR_CUDA;
         }
-        if (per_sm > KR_MIN_CTAS) per_sm = KR_MIN_CTAS;
+        const int want = 1;
+        if (per_sm > want) per_sm = want;
         cached = sms * per_sm;
+        if (cached > BND_MAX) cached = BND_MAX;
     }
     *grid_out = cached;
     return B3C_OK;
 }
+static int persistent_grid(bool slab, int *grid_out) {
+    return slab ? persistent_grid_of<true>(grid_out) : persistent_grid_of<false>(grid_out);
+}
 
-static unsigned spmv_grid(int64_t n_tiles) {
-    const int64_t cap = (int64_t)kNumSMs * 8;
-    return (unsigned)(n_tiles < cap ? n_tiles : cap);
+// Build the stream, its segment numbering and the zero-diagonal vector.  Needs the control block already
+// uploaded (k_stream_rows / k_diag_fix write into it).  The entry and segment counts are needed on the host
+// to size things: one small D2H copy + sync.
+template <bool SLAB>
+static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
+    const int32_t n_local = A.row_hi - A.row_lo;
+    double *sval = const_cast<double *>(A.sval);
+    void *scol = const_cast<void *>(A.scol);
+    uint16_t *sflag = const_cast<uint16_t *>(A.sflag);
+    B3C_CUDA(cudaMemsetAsync(A.cnt, 0, (size_t)(A.nv + 1) * 8, s));
+    B3C_CUDA(cudaMemsetAsync(sflag, 0, (size_t)(L.nnzv_max / 8 + 64), s));
+    k_stream_rows<false, SLAB><<<row_warp_grid(n_local), 256, 0, s>>>(A, A.cnt, nullptr, nullptr, nullptr);
+    B3C_LAUNCH_CHECK();
+    k_slab_pad<<<(unsigned)A.S, 256, 0, s>>>(A, A.cnt);
+    B3C_LAUNCH_CHECK();
+    int rc = scan_exclusive_i64(A.cnt, A.vp, A.nv, A.scan_tmp, s);
+    if (rc) return rc;
+    k_slab_finish<SLAB><<<(unsigned)A.S + 1, 256, 0, s>>>(A, sval, scol, sflag, const_cast<int32_t *>(A.slab_c0));
+    B3C_LAUNCH_CHECK();
+    // number the non-empty cells: cnt is reused for the 0/1 flags, ord receives their exclusive scan
+    k_cell_flags<<<(unsigned)ceil_div(A.nv, 256), 256, 0, s>>>(A.nv, A.vp, A.cnt);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(A.cnt, A.ord, A.nv, A.scan_tmp, s);
+    if (rc) return rc;
+    int64_t totals[2] = {0, 0};
+    KRScalars S;
+    B3C_CUDA(cudaMemcpyAsync(&totals[0], A.vp + A.nv, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(&totals[1], A.ord + A.nv, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaStreamSynchronize(s));
+    if (S.status == B3C_ERR_ARG) {
+        set_error("KR: column indices must be sorted within rows and lie in [0, n)");
+        return B3C_ERR_ARG;
+    }
+    if (totals[0] > L.nnzv_max || totals[0] % SPMV_TILE != 0 || totals[1] > L.nseg_max) {
+        set_error("stream layout: %lld entries, %lld segments (capacity %lld, %lld)", (long long)totals[0],
+                  (long long)totals[1], (long long)L.nnzv_max, (long long)L.nseg_max);
+        return B3C_ERR_CAPACITY;
+    }
+    A.nnzv = totals[0];
+    A.n_sch = A.nnzv / SPMV_CHUNK;
+    A.n_seg = (int32_t)totals[1];
+    k_stream_rows<true, SLAB><<<row_warp_grid(n_local), 256, 0, s>>>(A, nullptr, sval, scol, sflag);
+    B3C_LAUNCH_CHECK();
+    k_cell_index<<<(unsigned)ceil_div(A.nv, 256), 256, 0, s>>>(A.nv, A.vp, A.ord, const_cast<int32_t *>(A.seg_of),
+                                                               const_cast<int32_t *>(A.seg_row));
+    B3C_LAUNCH_CHECK();
+    const int64_t n_c = A.nnzv / SPMV_CHUNK;
+    if (n_c > 0) {
+        k_chunk_seg0<<<(unsigned)ceil_div(n_c, 256), 256, 0, s>>>(n_c, A.nv, A.vp, A.ord,
+                                                                  const_cast<int32_t *>(A.chunk_seg0));
+        B3C_LAUNCH_CHECK();
+    }
+    B3C_CUDA(cudaMemsetAsync(A.qs, 0, (size_t)(A.n_seg + 1) * 8, s));
+    k_diag_fix<<<row_warp_grid(n_local), 256, 0, s>>>(A.row_lo, A.row_hi, A.indptr, A.indices, A.data, A.dfix, A.ctl);
+    B3C_LAUNCH_CHECK();
+    rc = persistent_grid(SLAB, &A.n_bnd);
+    return rc;
+}
+static int kr_prepare(KRArgs &A, const KRLayout &L, cudaStream_t s) {
+    return A.slab ? kr_prepare_t<true>(A, L, s) : kr_prepare_t<false>(A, L, s);
+}
+
+static int launch_spmv(const KRArgs &A, cudaStream_t s) {
+    if (A.slab) k_spmv<true><<<A.n_bnd, KR_THREADS, SM_BYTES_SLAB, s>>>(A);
+    else k_spmv<false><<<A.n_bnd, KR_THREADS, SM_BYTES_GATHER, s>>>(A);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+static void kr_scalars_init(KRScalars &S, double tol, double delta, double Delta, int32_t max_iter) {
+    memset(&S, 0, sizeof(S));
+    S.tol = tol;
+    S.delta = delta;
+    S.Delta = Delta;
+    S.rt = tol * tol;                 // sparse_utils.py:135
+    S.stop_tol = tol * 0.5;           // sparse_utils.py:131
+    S.eta = 0.1;                      // etamax (sparse_utils.py:129-130)
+    S.max_iter = max_iter;
 }
 
 }  // namespace b3c
@@ -806,6 +1378,22 @@ static unsigned spmv_grid(int64_t n_tiles) {
 using namespace b3c;
 
 extern "C" {
+
+int b3c_set_option(int32_t key, int64_t value) {
+    switch (key) {
+        case B3C_OPT_KR_SLAB_WIDTH:
+            B3C_REQUIRE(value >= 2 && value <= SLAB_W_MAX, "slab width must be in [2, %d]", SLAB_W_MAX);
+            g_slab_w_max.store((int)value & ~1);
+            return B3C_OK;
+        case B3C_OPT_KR_MAX_SLABS:
+            B3C_REQUIRE(value >= 0 && value <= SLAB_S_MAX, "slab count cap must be in [0, %d]", SLAB_S_MAX);
+            g_slab_s_max.store((int)value);
+            return B3C_OK;
+        default:
+            set_error("unknown option %d", key);
+            return B3C_ERR_ARG;
+    }
+}
 
 int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz) {
     if (n <= 0 || nnz < 0) return B3C_ERR_ARG;
@@ -829,32 +1417,19 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
     kr_bind(A, L, ws, n, 0, n, nnz, d_indptr, d_indices, d_data);
 
     KRScalars S;
-    memset(&S, 0, sizeof(S));
-    S.tol = tol;
-    S.delta = delta;
-    S.Delta = Delta;
-    S.rt = tol * tol;                 // sparse_utils.py:135
-    S.stop_tol = tol * 0.5;           // sparse_utils.py:131
-    S.eta = 0.1;                      // etamax (sparse_utils.py:129-130)
-    S.max_iter = max_iter;
+    kr_scalars_init(S, tol, delta, Delta, max_iter);
     B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
     B3C_CUDA(cudaMemsetAsync(A.timers, 0, sizeof(KRTimers), s));
-
-    k_tile_plan<<<(unsigned)ceil_div(L.n_tiles + 1, 256), 256, 0, s>>>(n, d_indptr, L.n_tiles, A.tile_ra);
-    B3C_LAUNCH_CHECK();
-    k_chunk_plan<<<(unsigned)ceil_div(L.n_chunks + 1, 256), 256, 0, s>>>(L.n_chunks, L.n_tiles, A.tile_ra, A.chunk_t);
-    B3C_LAUNCH_CHECK();
-    {
-        int64_t blocks = ceil_div(n, KR_WARPS);
-        if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
-        k_diag_fix<<<(unsigned)blocks, KR_THREADS, 0, s>>>(0, n, d_indptr, d_indices, d_data, A.dfix, A.ctl);
-        B3C_LAUNCH_CHECK();
-    }
-    int grid = 0;
-    int rc = persistent_grid(&grid);
+    int rc = kr_prepare(A, L, s);
     if (rc) return rc;
+    const int grid = A.n_bnd;
     void *args[] = {&A};
-    B3C_CUDA(cudaLaunchCooperativeKernel((void *)k_kr_persistent, dim3(grid), dim3(KR_THREADS), args, 0, s));
+    if (A.slab)
+        B3C_CUDA(cudaLaunchCooperativeKernel((void *)k_kr_persistent<true>, dim3(grid), dim3(KR_THREADS), args,
+                                             SM_BYTES_SLAB, s));
+    else
+        B3C_CUDA(cudaLaunchCooperativeKernel((void *)k_kr_persistent<false>, dim3(grid), dim3(KR_THREADS), args,
+                                             SM_BYTES_GATHER, s));
     count_launch();
     B3C_CUDA(cudaMemcpyAsync(d_x, A.x, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
     B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
@@ -871,6 +1446,9 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
         h_info[6 + i] = T.work[i];
         h_info[6 + T_COUNT + i] = T.sync[i];
     }
+    h_info[24] = A.slab ? A.S : 0;
+    h_info[25] = A.nnzv;
+    h_info[26] = A.n_seg;
     if (S.status == B3C_ERR_TIE) {
         set_error("KR: max(ynew) == Delta with no element above Delta (reference raises ValueError here)");
         return B3C_ERR_TIE;
@@ -892,16 +1470,29 @@ int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_i
     }
     cudaStream_t s = (cudaStream_t)stream;
     KRArgs A;
-    kr_bind(A, L, (char *)d_ws, n, 0, n, nnz, d_indptr, d_indices, d_data);
-    A.u = const_cast<double *>(d_u);
-    A.q = d_y;
-    if (!prepared) {
-        k_tile_plan<<<(unsigned)ceil_div(L.n_tiles + 1, 256), 256, 0, s>>>(n, d_indptr, L.n_tiles, A.tile_ra);
-        B3C_LAUNCH_CHECK();
+    if (prepared) {
+        std::lock_guard<std::mutex> g(g_krp_mu);
+        auto it = g_krp.find(d_ws);
+        B3C_REQUIRE(it != g_krp.end(), "b3c_spmv: workspace %p was not prepared", d_ws);
+        A = it->second;
+        B3C_REQUIRE(A.n == n && A.nnz == nnz && A.indptr == d_indptr, "b3c_spmv: workspace prepared for another matrix");
+    } else {
+        kr_bind(A, L, (char *)d_ws, n, 0, n, nnz, d_indptr, d_indices, d_data);
+        B3C_CUDA(cudaMemsetAsync(A.ctl, 0, sizeof(KRScalars), s));
+        int rc = kr_prepare(A, L, s);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> g(g_krp_mu);
+        g_krp[d_ws] = A;
     }
-    k_spmv<<<spmv_grid(L.n_tiles), KR_THREADS, 0, s>>>(A);
-    B3C_LAUNCH_CHECK();
-    k_spmv_fix<<<(unsigned)ceil_div(L.n_tiles, 256), 256, 0, s>>>(A);
+    if (A.slab) {
+        // the TMA copy of a slab needs a 16-byte aligned, padded operand: stage it in the workspace
+        B3C_CUDA(cudaMemcpyAsync(A.u, d_u, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    } else {
+        A.u = const_cast<double *>(d_u);
+    }
+    int rc = launch_spmv(A, s);
+    if (rc) return rc;
+    k_spmv_collect<<<(unsigned)A.n_chunks, KR_THREADS, 0, s>>>(A, d_y);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }
@@ -928,32 +1519,15 @@ int b3c_krp_setup(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, 
     KRArgs A;
     kr_bind(A, L, (char *)d_ws, n, row_lo, row_hi, nnz_local, d_indptr, d_indices, d_data);
     KRScalars S;
-    memset(&S, 0, sizeof(S));
-    S.tol = tol;
-    S.delta = delta;
-    S.Delta = Delta;
-    S.rt = tol * tol;
-    S.stop_tol = tol * 0.5;
-    S.eta = 0.1;
-    S.max_iter = max_iter;
+    kr_scalars_init(S, tol, delta, Delta, max_iter);
     S.state = KR_STATE_INNER;
     B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
     B3C_CUDA(cudaMemsetAsync(A.timers, 0, sizeof(KRTimers), s));
     B3C_CUDA(cudaMemsetAsync(A.part, 0, (size_t)L.n_chunks * 8 * P_COUNT, s));
-    const int32_t n_local = row_hi - row_lo;
-    const int32_t n_local_chunks = (int32_t)ceil_div(n_local, CHUNK);
-    k_tile_plan<<<(unsigned)ceil_div(L.n_tiles + 1, 256), 256, 0, s>>>(n_local, d_indptr, L.n_tiles, A.tile_ra);
-    B3C_LAUNCH_CHECK();
-    k_chunk_plan<<<(unsigned)ceil_div(n_local_chunks + 1, 256), 256, 0, s>>>(n_local_chunks, L.n_tiles, A.tile_ra,
-                                                                            A.chunk_t);
-    B3C_LAUNCH_CHECK();
-    {
-        int64_t blocks = ceil_div(n_local, KR_WARPS);
-        if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
-        k_diag_fix<<<(unsigned)blocks, KR_THREADS, 0, s>>>(row_lo, row_hi, d_indptr, d_indices, d_data, A.dfix, A.ctl);
-        B3C_LAUNCH_CHECK();
-    }
-    h_offsets[0] = L.o_vec + (int64_t)n * 8 * 8;        // u: float64[n]
+    B3C_CUDA(cudaMemsetAsync(A.u, 0, (size_t)L.nvec * 8, s));
+    int rc = kr_prepare(A, L, s);
+    if (rc) return rc;
+    h_offsets[0] = L.o_vec + L.nvec * 8 * 8;            // u: float64[n]
     h_offsets[1] = L.o_vec;                             // x: float64[n]
     h_offsets[2] = L.o_part;                            // partials: float64[7][n_chunks]
     h_offsets[3] = L.n_chunks;
@@ -979,9 +1553,8 @@ int b3c_krp_phase(void *d_ws, int32_t phase, void *stream) {
     int rc = krp_get(d_ws, &A);
     if (rc) return rc;
     B3C_REQUIRE(phase >= KRP_INIT && phase <= KRP_UPDATE, "unknown phase %d", phase);
-    unsigned grid;
-    if (phase == KRP_SPMV) grid = spmv_grid(A.n_tiles);
-    else grid = (unsigned)(A.n_chunks < kNumSMs * 4 ? A.n_chunks : kNumSMs * 4);
+    if (phase == KRP_SPMV) return launch_spmv(A, (cudaStream_t)stream);
+    const unsigned grid = (unsigned)(A.n_chunks < kNumSMs * 4 ? A.n_chunks : kNumSMs * 4);
     k_krp_phase<<<grid, KR_THREADS, 0, (cudaStream_t)stream>>>(A, phase);
     B3C_LAUNCH_CHECK();
     return B3C_OK;

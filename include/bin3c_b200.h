@@ -147,12 +147,22 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  *                 Newton steps, [3] = SpMV phases executed, [4] = CTAs of the persistent grid,
  *                 [5] = SM cycles of the whole kernel, [6..14] = cycles CTA 0 spent working in
  *                 each phase (init, spmv, fix-up, residual, direction, w, step, update, scalar
- *                 reductions), [15..23] = cycles it waited at the grid barrier after each.
+ *                 reductions), [15..23] = cycles it waited at the grid barrier after each,
+ *                 [24] = column slabs of the SpMV operand (0 = gather form), [25] = entries of the
+ *                 SpMV stream including slab padding.
  *                 mode 0 = one persistent cooperative kernel (device-side control flow).
  *   b3c_kr_scale  out[e] = x_i * (a_ij * x_j), the entries of X.T.dot(orig.dot(X))
  *                 (sparse_utils.py:223-224, Q9) on the ORIGINAL matrix.
  *   b3c_spmv      y = A.u with the same kernel KR uses (microbench, config C5).
  * ------------------------------------------------------------------------------------ */
+/* Tuning / test hooks.  KR's SpMV gathers its operand vector from shared memory, one column slab at
+ * a time (see csrc/kr.cu); B3C_OPT_KR_SLAB_WIDTH caps the slab width (default 26112 columns, the most
+ * that fits in a CTA's shared memory), B3C_OPT_KR_MAX_SLABS the slab count (default 16; wider matrices,
+ * or 0, select the form that gathers through L1/L2).  Results are identical up to fp64 summation
+ * order.  Workspace sizes depend on these, so set them before the *_workspace_bytes() query. */
+enum { B3C_OPT_KR_SLAB_WIDTH = 1, B3C_OPT_KR_MAX_SLABS = 2 };
+int b3c_set_option(int32_t key, int64_t value);
+
 int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz);
 int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices,
                const double *d_data, double tol, double delta, double Delta, int32_t max_iter,
@@ -170,6 +180,8 @@ int b3c_asymmetry_count(int32_t n, const int64_t *d_indptr, const int32_t *d_ind
 int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices,
              const double *d_data, const double *d_u, double *d_y, void *d_ws, int64_t ws_bytes,
              int32_t prepared, void *stream);
+/* b3c_spmv: prepared = 0 builds the SpMV operand and plan for this matrix in d_ws (and synchronises);
+ * prepared != 0 reuses what the last prepared = 0 call on the same d_ws built. */
 
 /* ------------------------------------------------------------------------------------
  * Row-block phase API of KR (multi-GPU driver).  Each

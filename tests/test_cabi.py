@@ -72,7 +72,14 @@ def test_workspace_sizes_scale(cabi):
     a = cabi.lib.b3c_accum_workspace_bytes(1_000_000, 50_000, 55_000)
     b = cabi.lib.b3c_accum_workspace_bytes(2_000_000, 50_000, 55_000)
     assert 31_000_000 < b - a < 33_000_000          # 32 bytes per pair of capacity
-    assert cabi.lib.b3c_kr_workspace_bytes(1_000_000, 10 ** 8) < 200_000_000
+    # KR holds its own copy of the matrix as the SpMV stream: 10 B per entry with column slabs (n <= 16 * 28672),
+    # 12 B per entry in the gather form, plus O(n) vectors and cell tables
+    k1 = cabi.lib.b3c_kr_workspace_bytes(50_000, 10 ** 7)
+    k2 = cabi.lib.b3c_kr_workspace_bytes(50_000, 2 * 10 ** 7)
+    assert 99_000_000 < k2 - k1 < 120_000_000
+    g1 = cabi.lib.b3c_kr_workspace_bytes(1_000_000, 10 ** 8)
+    g2 = cabi.lib.b3c_kr_workspace_bytes(1_000_000, 2 * 10 ** 8)
+    assert 1_190_000_000 < g2 - g1 < 1_400_000_000
 
 
 def test_product_has_no_oracle_import():

@@ -270,6 +270,101 @@ def test_spmv_vs_scipy(dev, n, nnz_row):
     assert np.max(np.abs(y - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
 
 
+class _kr_options(object):
+    """Temporarily change the slab shape of KR's SpMV operand (b3c_set_option)."""
+
+    def __init__(self, dev, width=None, max_slabs=None):
+        self.dev, self.width, self.max_slabs = dev, width, max_slabs
+
+    def __enter__(self):
+        if self.width is not None:
+            self.dev.check(self.dev.lib.b3c_set_option(1, self.width))
+        if self.max_slabs is not None:
+            self.dev.check(self.dev.lib.b3c_set_option(2, self.max_slabs))
+
+    def __exit__(self, *a):
+        self.dev.check(self.dev.lib.b3c_set_option(1, 26112))
+        self.dev.check(self.dev.lib.b3c_set_option(2, 16))
+
+
+def _sym_matrix(n, nnz_row, seed, zero_diag_frac=0.1):
+    rng = np.random.default_rng(seed)
+    k = int(n * nnz_row / 2)
+    r, c = rng.integers(0, n, k), rng.integers(0, n, k)
+    up = sp.coo_matrix((rng.uniform(0.1, 5.0, k), (np.minimum(r, c), np.maximum(r, c))), shape=(n, n)).tocsr()
+    up = sp.triu(up, k=1)
+    d = rng.uniform(0.5, 2.0, n)
+    d[rng.random(n) < zero_diag_frac] = 0.0
+    m = (up + up.T + sp.diags(d)).tocsr()
+    m.eliminate_zeros()
+    m.sort_indices()
+    return m
+
+
+# slab shapes: (width cap, slab cap).  None = defaults; (1000, 16) forces several narrow slabs on small matrices;
+# (None, 0) forces the form that gathers through L1/L2
+SLAB_SHAPES = [(None, None), (1000, 16), (334, 16), (None, 0)]
+
+
+@pytest.mark.parametrize('shape', SLAB_SHAPES)
+@pytest.mark.parametrize('n,nnz_row', [(1, 1), (100, 1), (5000, 3), (4097, 40), (3000, 900)])
+def test_spmv_slab_shapes(dev, n, nnz_row, shape):
+    rng = np.random.default_rng(n)
+    m = sp.random(n, n, density=min(1.0, nnz_row / n), random_state=rng, format='csr')
+    m.sort_indices()
+    u = rng.standard_normal(n)
+    with _kr_options(dev, *shape):
+        y = dev.spmv(dev.DeviceCSR.from_scipy(m), dev.to_device(u)).cpu().numpy()
+    want = m.dot(u)
+    assert np.max(np.abs(y - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+
+
+@pytest.mark.parametrize('n,nnz_row', [(60000, 20), (130000, 6), (450000, 4)])
+def test_spmv_wide(dev, n, nnz_row):
+    """Default slab shape on matrices that need 3 and 5 slabs, and one too wide for slabs (gather form)."""
+    m = _sym_matrix(n, nnz_row, seed=n)
+    u = np.random.default_rng(1).standard_normal(n)
+    csr = dev.DeviceCSR.from_scipy(m)
+    y = dev.spmv(csr, dev.to_device(u)).cpu().numpy()
+    want = m.dot(u)
+    assert np.max(np.abs(y - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+
+
+@pytest.mark.parametrize('shape', SLAB_SHAPES[1:])
+def test_kr_slab_shapes(dev, shape):
+    """The scale vector must not depend on how the SpMV operand is cut (beyond summation order)."""
+    from oracle import oracle
+    m = _sym_matrix(5000, 30, seed=17)
+    res = oracle.kr_scale_vector(m)
+    with _kr_options(dev, *shape):
+        x, info = dev.kr_scale_vector(dev.DeviceCSR.from_scipy(m))
+    assert info['slabs'] == (0 if shape[1] == 0 else -(-5000 // shape[0]))
+    assert info['n_iter'] == res.n_iter
+    assert info['zero_diag'] == res.n_zero_diag
+    assert _relerr(x.cpu().numpy(), res.x) <= REL_TOL
+
+
+def test_kr_three_slabs_vs_oracle(dev):
+    from oracle import oracle
+    m = _sym_matrix(60000, 12, seed=23)
+    res = oracle.kr_scale_vector(m)
+    x, info = dev.kr_scale_vector(dev.DeviceCSR.from_scipy(m))
+    assert info['slabs'] == 3
+    assert info['n_iter'] == res.n_iter
+    assert _relerr(x.cpu().numpy(), res.x) <= REL_TOL
+
+
+def test_kr_rejects_unsorted_columns(dev):
+    m = _sym_matrix(3000, 10, seed=5)
+    csr = dev.DeviceCSR.from_scipy(m)
+    lo, hi = int(m.indptr[7]), int(m.indptr[8])
+    assert hi - lo >= 2
+    csr.indices[lo], csr.indices[hi - 1] = csr.indices[hi - 1].clone(), csr.indices[lo].clone()
+    with _kr_options(dev, 1000, 16):
+        with pytest.raises(AssertionError):
+            dev.kr_scale_vector(csr)
+
+
 # ---------------------------------------------------------------------------------------------
 # compress + edges, whole path
 # ---------------------------------------------------------------------------------------------
