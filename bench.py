@@ -209,9 +209,11 @@ def main():
     barrier()
     ev0.record()
     per_step_events = []
+    kr_kernel_us = 0.0
     for _ in range(args.steps):
         res = hp.run(rec_dev)
         per_step_events.append(hp.events)
+        kr_kernel_us += hp.kr_info['kernel_us']            # CUDA events around the persistent kernel's launch
     ev1.record()
     barrier()
     launches = dev.launch_count() - launches0
@@ -245,20 +247,22 @@ def main():
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
     peak, peak_src = measured_peak()
-    t_cls, t_kr = stage_ms.get('classify', 0.0), stage_ms.get('kr', 0.0)
+    t_cls = stage_ms.get('classify', 0.0)
+    t_kr = kr_kernel_us / args.steps * 1e-3             # ms per launch of k_kr_persistent (the 'kr' stage adds its set-up)
     spmv_bytes = 12 * nnz_full + 24 * N                 # fp64 value + int32 column, int64 indptr, x read, y written
     kr_bytes = kr['n_spmv'] * spmv_bytes
     cls_bytes = 8 * P
     roof_kr = {'kernel': 'k_kr_persistent', 'bound': 'hbm', 'achieved': kr_bytes / (t_kr * 1e-3) / 1e9, 'peak': peak,
                'unit': 'GB/s', 'frac': kr_bytes / (t_kr * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
                'bytes_per_launch': kr_bytes, 'ms_per_launch': t_kr,
-               'note': '{} SpMV x (12*nnz + 24*N) B, vector phases not counted; matrix {} MB vs 126 MB L2'.format(
-                   kr['n_spmv'], spmv_bytes // 1000000)}
+               'note': '{} SpMV x (12*nnz + 24*N) B per launch (SURVEY 8d formula; the kernel streams 10 B per entry), '
+                       'vector phases and grid barriers are inside the launch but add no counted bytes; '
+                       'matrix {} MB vs 126 MB L2'.format(kr['n_spmv'], spmv_bytes // 1000000)}
     roof_cls = {'kernel': 'k_classify', 'bound': 'hbm', 'achieved': cls_bytes / (t_cls * 1e-3) / 1e9, 'peak': peak,
                 'unit': 'GB/s', 'frac': cls_bytes / (t_cls * 1e-3) / 1e9 / peak, 'traffic': None,
                 'peak_source': peak_src, 'bytes_per_launch': cls_bytes, 'ms_per_launch': t_cls,
                 'note': '8 B per packed pair record read once'}
-    roofline, other = (roof_kr, roof_cls) if t_kr >= t_cls else (roof_cls, roof_kr)
+    roofline, other = (roof_kr, roof_cls) if stage_ms.get('kr', 0.0) >= t_cls else (roof_cls, roof_kr)
 
     # ---- CPU baseline on a bounded sample -------------------------------------------------------------------
     cpu = None
@@ -288,7 +292,11 @@ def main():
                         'total': round(kr['cycles'] / (clocks.get('sm_mhz') or 1965.0), 1), 'grid': kr['grid']},
         'accumulate_pairs_per_s': P / ((stage_ms.get('classify', 0) + stage_ms.get('sort_reduce_emit', 0)) * 1e-3),
         'kr': {'n_iter': kr['n_iter'], 'n_spmv': kr['n_spmv'], 'outer': kr['outer'], 'zero_diag': kr['zero_diag'],
-               'spmv_gbs_by_formula': roof_kr['achieved'], 'ms': t_kr},
+               'spmv_gbs_by_formula': roof_kr['achieved'], 'kernel_ms': t_kr, 'stage_ms': stage_ms.get('kr'),
+               'slabs': kr['slabs'], 'stream_entries': kr['nnz_stream'], 'segments': kr['segments'],
+               'spmv_phase_gbs': (spmv_bytes * kr['n_spmv'] / 1e9) /
+                                 ((kr['work_cycles']['spmv'] + kr['sync_cycles']['spmv']) /
+                                  ((clocks.get('sm_mhz') or 1965.0) * 1e6))},
         'pair_counts': {k: info[k] for k in ('accepted', 'ref_excluded', 'poor_match')},
     }
     print(json.dumps(line))

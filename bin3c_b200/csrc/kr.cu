@@ -47,6 +47,7 @@ constexpr int CHUNK_RPT = CHUNK / KR_THREADS;
 constexpr int RED_MAX = 8;                           // values reduced together by one block reduction
 constexpr int SLAB_W_MAX = 28672;                    // fp64 entries of u held in shared memory (15-bit columns)
 constexpr int SLAB_S_MAX = 16;                       // more slabs than this: gather form
+constexpr int KR_MAX_RANKS = 8;                      // GPUs of one node in peer mode
 static_assert(KR_WARPS <= 32 && SLAB_W_MAX <= 65536, "warp records are stitched by one warp; 16-bit columns");
 
 // partial arrays, each n_chunks long
@@ -123,7 +124,32 @@ struct KRArgs {
     int32_t n_chunks;
     KRScalars *ctl;
     KRTimers *timers;
+    // peer mode (one persistent kernel per GPU of a node, exchange buffers mapped over NVLink): u and the
+    // partials live in the exchange buffer of every rank and are written into all of them directly
+    int32_t n_rank, rank;                       // n_rank <= 1: single GPU / host-driven phases
+    double *xu[KR_MAX_RANKS];                   // u of every rank (own included)
+    double *xpart[KR_MAX_RANKS];                // partials of every rank
+    unsigned long long *xflag[KR_MAX_RANKS];    // barrier flags of every rank: xflag[g][r] = epoch rank r has reached
+    unsigned long long *epoch;                  // this rank's epoch counter (persists across runs)
+    unsigned *bar_count, *bar_gen;              // grid barrier of the persistent kernel (zeroed per run)
 };
+
+// publish u[r] / a partial: to this rank and, in peer mode, straight into every other rank's copy
+__device__ __forceinline__ void put_u(const KRArgs &A, int64_t r, double v) {
+    A.u[r] = v;
+    for (int g = 0; g < A.n_rank; ++g)
+        if (g != A.rank) A.xu[g][r] = v;
+}
+// `loc`: the chunk belongs to this rank.  Without peers the other chunks get the identity (the host
+// driver all-reduces the arrays); with peers their owners write them.
+__device__ __forceinline__ void put_part(const KRArgs &A, int which, int c, double v, bool loc, double identity) {
+    const int64_t i = (int64_t)which * A.n_chunks + c;
+    if (A.n_rank <= 1) {
+        A.part[i] = loc ? v : identity;
+    } else if (loc) {
+        for (int g = 0; g < A.n_rank; ++g) A.xpart[g][i] = v;
+    }
+}
 
 struct SpmvState {             // carried from tile to tile by the stitching warps
     double open;               // sum so far of the segment open at the end of the last tile
@@ -575,7 +601,7 @@ __device__ __forceinline__ void phase_init(const KRArgs &A) {
             const int64_t r = KR_ROW(c, i);
             if (r < A.row_hi) {
                 A.x[r] = 1.0;
-                A.u[r] = 1.0;
+                put_u(A, r, 1.0);
             }
         }
     }
@@ -605,7 +631,7 @@ __device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red) {
         }
         double r[1] = {acc};
         block_reduce<1, 0>(r, s_red);
-        if (threadIdx.x == 0) A.part[PA * A.n_chunks + c] = loc ? r[0] : 0.0;
+        if (threadIdx.x == 0) put_part(A, PA, c, r[0], loc, 0.0);
     }
 }
 
@@ -631,16 +657,16 @@ __device__ __forceinline__ void phase_dir(const KRArgs &A, bool first, double be
                         pp = __dadd_rn(A.Z[r], __dmul_rn(beta, A.p[r]));    // sparse_utils.py:163
                     }
                     A.p[r] = pp;
-                    A.u[r] = __dmul_rn(A.x[r], pp);
+                    put_u(A, r, __dmul_rn(A.x[r], pp));
                 }
             }
         }
         if (first) {
             double r[1] = {acc};
             block_reduce<1, 0>(r, s_red);
-            if (threadIdx.x == 0) A.part[PB * A.n_chunks + c] = loc ? r[0] : 0.0;
+            if (threadIdx.x == 0) put_part(A, PB, c, r[0], loc, 0.0);
         } else if (threadIdx.x == 0) {
-            A.part[PB * A.n_chunks + c] = 0.0;
+            put_part(A, PB, c, 0.0, loc, 0.0);
         }
     }
 }
@@ -667,7 +693,7 @@ __device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red) {
         }
         double r[1] = {acc};
         block_reduce<1, 0>(r, s_red);
-        if (threadIdx.x == 0) A.part[PA * A.n_chunks + c] = loc ? r[0] : 0.0;
+        if (threadIdx.x == 0) put_part(A, PA, c, r[0], loc, 0.0);
     }
 }
 
@@ -702,12 +728,11 @@ __device__ __forceinline__ void phase_step(const KRArgs &A, double alpha, double
         double r[5] = {rho, mn, nmx, g1, g2};
         block_reduce<1, 4>(r, s_red);
         if (threadIdx.x == 0) {
-            const int nc = A.n_chunks;
-            A.part[PC * nc + c] = loc ? r[0] : 0.0;
-            A.part[PMIN * nc + c] = r[1];
-            A.part[PNEGMAX * nc + c] = r[2];
-            A.part[PG1 * nc + c] = r[3];
-            A.part[PG2 * nc + c] = r[4];
+            put_part(A, PC, c, r[0], loc, 0.0);
+            put_part(A, PMIN, c, r[1], loc, (double)INFINITY);
+            put_part(A, PNEGMAX, c, r[2], loc, (double)INFINITY);
+            put_part(A, PG1, c, r[3], loc, (double)INFINITY);
+            put_part(A, PG2, c, r[4], loc, (double)INFINITY);
         }
     }
 }
@@ -726,7 +751,7 @@ __device__ __forceinline__ void phase_update(const KRArgs &A, int ymode, double 
                 if (ymode == 2) yy = __dadd_rn(yy, __dmul_rn(gamma, __dmul_rn(alpha, A.p[r])));
                 const double xx = __dmul_rn(A.x[r], yy);
                 A.x[r] = xx;
-                A.u[r] = xx;
+                put_u(A, r, xx);
             }
         }
     }
@@ -784,6 +809,7 @@ __device__ __forceinline__ void scalar_step(KRScalars &S, int which, const doubl
     if (which == KRS_OUTER_FIRST || which == KRS_OUTER) {          // r[0] = rk.rk
         scalar_outer(S, r[0], which == KRS_OUTER_FIRST);
         S.n_spmv += 1;
+        if (isnan(S.rout)) S.status = B3C_ERR_NAN;                 // sparse_utils.py:192-193
         if (S.rout > S.rt && S.n_iter < S.max_iter) {              // sparse_utils.py:146
             S.outer += 1;
             S.k = 0;
@@ -826,12 +852,65 @@ __device__ __forceinline__ void scalar_step(KRScalars &S, int which, const doubl
 // The loop scalars live in shared memory: thread 0 updates them between block barriers, everybody reads
 // them; all CTAs compute identical values from the same partials.  One trip of the loop is
 // "make u | SpMV | consume": init or update -> residual (an outer Newton step), direction -> w, step (a CG step).
-#define KR_PHASE(id, call)                                                     \
+// Barrier after a phase: one arrive counter + one generation word in global memory (the kernel is launched
+// cooperatively, so all CTAs are resident).  Thread 0 of every CTA fences and arrives; the last CTA to
+// arrive opens the next generation.  `cross`: the phase published data to the other GPUs -- the fences are
+// system-wide, and before opening the generation the last CTA tells every rank this one has arrived
+// (release store into its flag array over NVLink) and waits until all ranks have (acquire loads of the local
+// flags).  A rank that never arrives (it failed before its launch) would hang the node, so that wait gives
+// up after ~4 s and poisons the local partials with NaN: every CTA then derives NaN scalars, the loop
+// conditions fail, the kernel ends and the host reports the time-out.
+__device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned long long &epoch, unsigned &gen) {
+    cross = cross && A.n_rank > 1;
+    if (cross) epoch += 1;
+    gen += 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (cross) __threadfence_system();
+        else __threadfence();
+        const unsigned arrived = atomicAdd(A.bar_count, 1u) + 1u;
+        if (arrived == gen * gridDim.x) {
+            if (cross) {
+                // every CTA's system fence completed before it arrived, so this rank's peer stores have been
+                // performed: relaxed flag stores and a relaxed spin are enough (a system-scope fence costs
+                // microseconds, so there is exactly one per CTA per barrier)
+                for (int g = 0; g < A.n_rank; ++g)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(A.xflag[g] + A.rank), "l"(epoch) : "memory");
+                const long long t0 = clock64();
+                for (int g = 0; g < A.n_rank; ++g) {
+                    const unsigned long long *mine = A.xflag[A.rank] + g;
+                    unsigned long long seen;
+                    do {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+                        if (seen < epoch && clock64() - t0 > 8000000000LL) {
+                            for (int i = 0; i < P_COUNT; ++i)
+                                A.part[(int64_t)i * A.n_chunks] = __longlong_as_double(0x7ff8000000000000LL);
+                            A.timers->sync[T_FIX] = -1;
+                            seen = epoch;
+                        }
+                    } while (seen < epoch);
+                }
+            }
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.bar_gen), "r"(gen) : "memory");
+            __threadfence();                           // this CTA reads what the others (and the peers) wrote, too
+        } else {
+            unsigned g2;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(A.bar_gen) : "memory");
+            } while (g2 < gen);
+        }
+        // what the peers wrote lies in this GPU's own memory: the gpu-scope acquire above (L1 invalidation) is
+        // all a reader needs
+    }
+    __syncthreads();
+}
+
+#define KR_PHASE(id, cross, call)                                              \
     do {                                                                       \
         const long long t0_ = clock64();                                       \
         call;                                                                  \
         const long long t1_ = clock64();                                       \
-        grid.sync();                                                           \
+        kr_barrier(A, cross, epoch, gen);                                      \
         if (timing) {                                                          \
             const long long t2_ = clock64();                                   \
             A.timers->work[id] += t1_ - t0_;                                   \
@@ -849,7 +928,6 @@ __device__ __forceinline__ void scalar_step(KRScalars &S, int which, const doubl
 
 template <bool SLAB>
 __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
-    cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem sm = carve_smem(smem_raw);
     double *s_red = sm.red;
@@ -863,22 +941,24 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
     double *ybuf[2] = {A.y0, A.y1};
     const bool timing = (blockIdx.x == 0 && threadIdx.x == 0);
     const long long t_begin = clock64();
+    unsigned long long epoch = A.n_rank > 1 ? *A.epoch : 0ull;
+    unsigned gen = 0;
 
     int mode = -1;                                        // -1: first trip (x = 1)
     for (;;) {
-        if (mode < 0) KR_PHASE(T_INIT, phase_init(A));
-        else if (mode == KR_STATE_INNER) KR_PHASE(T_DIR, phase_dir(A, S.k == 1, S.beta, ybuf[S.ysel], s_red));
-        else KR_PHASE(T_UPDATE, phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
-        KR_PHASE(T_SPMV, phase_spmv<SLAB>(A, A.u, sm));
+        if (mode < 0) KR_PHASE(T_INIT, true, phase_init(A));
+        else if (mode == KR_STATE_INNER) KR_PHASE(T_DIR, true, phase_dir(A, S.k == 1, S.beta, ybuf[S.ysel], s_red));
+        else KR_PHASE(T_UPDATE, true, phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
+        KR_PHASE(T_SPMV, false, phase_spmv<SLAB>(A, A.u, sm));
         if (mode == KR_STATE_INNER) {
-            KR_PHASE(T_W, phase_w(A, s_red));
+            KR_PHASE(T_W, true, phase_w(A, s_red));
             {
                 double r[2];
                 const int ids[2] = {PA, PB};
                 reduce_parts<2, 0>(A.part, nc, ids, r, s_red);
                 KR_SCALAR(KRS_ALPHA, r);
             }
-            KR_PHASE(T_STEP, phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red));
+            KR_PHASE(T_STEP, true, phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red));
             {
                 double r[5];
                 const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
@@ -886,7 +966,7 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
                 KR_SCALAR(KRS_DECIDE, r);
             }
         } else {
-            KR_PHASE(T_RESID, phase_resid(A, s_red));
+            KR_PHASE(T_RESID, true, phase_resid(A, s_red));
             double r[1];
             const int ids[1] = {PA};
             reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
@@ -899,6 +979,7 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
     if (timing) {
         *A.ctl = S;
         A.timers->total = clock64() - t_begin;
+        if (A.n_rank > 1) *A.epoch = epoch;
     }
 }
 
@@ -1166,7 +1247,7 @@ struct KRLayout {
     int32_t slab, S, W, n_chunks;
     int64_t nvec;                       // elements per (padded) vector
     int64_t nv_max, nnzv_max, nseg_max;
-    int64_t o_dfix, o_vec, o_qs, o_part, o_ctl, o_timers, o_bnd;
+    int64_t o_dfix, o_vec, o_qs, o_part, o_ctl, o_timers, o_bar, o_bnd;
     int64_t o_cnt, o_vp, o_ord, o_scan, o_slab_t0, o_sval, o_scol, o_sflag, o_seg0, o_seg_of, o_seg_row, total;
 };
 
@@ -1189,6 +1270,7 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     L.o_part = c.take((int64_t)L.n_chunks * 8 * P_COUNT);
     L.o_ctl = c.take(sizeof(KRScalars));
     L.o_timers = c.take(sizeof(KRTimers));
+    L.o_bar = c.take(256);
     L.o_bnd = c.take((int64_t)BND_MAX * (8 + 8 + 4 + 4 + 4));
     L.o_cnt = c.take((L.nv_max + 1) * 8);
     L.o_vp = c.take((L.nv_max + 1) * 8);
@@ -1257,6 +1339,16 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.n_chunks = L.n_chunks;
     A.ctl = (KRScalars *)(ws + L.o_ctl);
     A.timers = (KRTimers *)(ws + L.o_timers);
+    A.bar_count = (unsigned *)(ws + L.o_bar);
+    A.bar_gen = (unsigned *)(ws + L.o_bar + 128);
+    A.n_rank = 0;
+    A.rank = 0;
+    A.epoch = nullptr;
+    for (int g = 0; g < KR_MAX_RANKS; ++g) {
+        A.xu[g] = nullptr;
+        A.xpart[g] = nullptr;
+        A.xflag[g] = nullptr;
+    }
 }
 
 static unsigned row_warp_grid(int64_t n_rows) {
@@ -1400,42 +1492,33 @@ int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz) {
     return kr_layout(n, nnz).total;
 }
 
-int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
-               double tol, double delta, double Delta, int32_t max_iter, int32_t mode, double *d_x, void *d_ws,
-               int64_t ws_bytes, int64_t *h_info, void *stream) {
-    B3C_REQUIRE(n > 0 && nnz >= 0 && d_indptr && d_x && d_ws && h_info, "bad arguments");
-    B3C_REQUIRE(nnz == 0 || (d_indices && d_data), "null matrix arrays");
-    B3C_REQUIRE(mode == 0, "b3c_kr_run: only mode 0 (persistent kernel) is implemented; use b3c_krp_* for phases");
-    const KRLayout L = kr_layout(n, nnz);
-    if (ws_bytes < L.total) {
-        set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
-        return B3C_ERR_CAPACITY;
+// launch the persistent kernel on a prepared operand, wait, and report
+static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *h_info, cudaStream_t s) {
+    static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!ev[0]) {
+        B3C_CUDA(cudaEventCreate(&ev[0]));
+        B3C_CUDA(cudaEventCreate(&ev[1]));
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    char *ws = (char *)d_ws;
-    KRArgs A;
-    kr_bind(A, L, ws, n, 0, n, nnz, d_indptr, d_indices, d_data);
-
-    KRScalars S;
-    kr_scalars_init(S, tol, delta, Delta, max_iter);
-    B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
-    B3C_CUDA(cudaMemsetAsync(A.timers, 0, sizeof(KRTimers), s));
-    int rc = kr_prepare(A, L, s);
-    if (rc) return rc;
     const int grid = A.n_bnd;
     void *args[] = {&A};
+    B3C_CUDA(cudaMemsetAsync(A.bar_count, 0, 256, s));
+    B3C_CUDA(cudaEventRecord(ev[0], s));
     if (A.slab)
         B3C_CUDA(cudaLaunchCooperativeKernel((void *)k_kr_persistent<true>, dim3(grid), dim3(KR_THREADS), args,
                                              SM_BYTES_SLAB, s));
     else
         B3C_CUDA(cudaLaunchCooperativeKernel((void *)k_kr_persistent<false>, dim3(grid), dim3(KR_THREADS), args,
                                              SM_BYTES_GATHER, s));
+    B3C_CUDA(cudaEventRecord(ev[1], s));
     count_launch();
-    B3C_CUDA(cudaMemcpyAsync(d_x, A.x, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
-    B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
+    KRScalars S;
     KRTimers T;
+    B3C_CUDA(cudaMemcpyAsync(d_x, A.x, (size_t)A.n * 8, cudaMemcpyDeviceToDevice, s));
+    B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaMemcpyAsync(&T, A.timers, sizeof(T), cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    B3C_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1]));
     h_info[0] = S.n_iter;
     h_info[1] = S.zero_diag;
     h_info[2] = S.outer;
@@ -1449,15 +1532,135 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
     h_info[24] = A.slab ? A.S : 0;
     h_info[25] = A.nnzv;
     h_info[26] = A.n_seg;
+    h_info[27] = (int64_t)(ms * 1000.0f + 0.5f);       // the persistent kernel alone, microseconds (CUDA events)
+    if (T.sync[T_FIX] < 0) {
+        set_error("KR: a rank did not reach a cross-GPU barrier within the time-out");
+        return B3C_ERR_CUDA;
+    }
     if (S.status == B3C_ERR_TIE) {
         set_error("KR: max(ynew) == Delta with no element above Delta (reference raises ValueError here)");
         return B3C_ERR_TIE;
+    }
+    if (S.status == B3C_ERR_NAN) {
+        set_error("scale vector has developed invalid values (NANs)!");
+        return B3C_ERR_NAN;
     }
     if (S.status == B3C_ERR_NOCONV || S.n_iter > max_iter) {
         set_error("matrix balancing failed to converge in %lld iterations", (long long)S.n_iter);
         return B3C_ERR_NOCONV;
     }
     return B3C_OK;
+}
+
+int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
+               double tol, double delta, double Delta, int32_t max_iter, int32_t mode, double *d_x, void *d_ws,
+               int64_t ws_bytes, int64_t *h_info, void *stream) {
+    B3C_REQUIRE(n > 0 && nnz >= 0 && d_indptr && d_x && d_ws && h_info, "bad arguments");
+    B3C_REQUIRE(nnz == 0 || (d_indices && d_data), "null matrix arrays");
+    B3C_REQUIRE(mode == 0, "b3c_kr_run: only mode 0 (persistent kernel) is implemented; use b3c_krp_* for phases");
+    const KRLayout L = kr_layout(n, nnz);
+    if (ws_bytes < L.total) {
+        set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
+        return B3C_ERR_CAPACITY;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    KRArgs A;
+    kr_bind(A, L, (char *)d_ws, n, 0, n, nnz, d_indptr, d_indices, d_data);
+    KRScalars S;
+    kr_scalars_init(S, tol, delta, Delta, max_iter);
+    B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
+    B3C_CUDA(cudaMemsetAsync(A.timers, 0, sizeof(KRTimers), s));
+    int rc = kr_prepare(A, L, s);
+    if (rc) return rc;
+    return kr_launch_collect(A, max_iter, d_x, h_info, s);
+}
+
+// ---- peer mode: one persistent kernel per GPU of a node, exchange buffers mapped over NVLink ------------
+// exchange buffer of a rank: [flags: KR_MAX_RANKS x u64 | epoch u64 | pad to 256 B][u: nvec x f64][partials]
+struct XLayout {
+    int64_t o_flag, o_epoch, o_u, o_part, total;
+};
+static XLayout x_layout(int32_t n) {
+    XLayout X;
+    Carver c;
+    X.o_flag = c.take(KR_MAX_RANKS * 8);
+    X.o_epoch = c.take(8);
+    X.o_u = c.take(align_up(n, 32) * 8);
+    X.o_part = c.take(ceil_div(n, CHUNK) * 8 * P_COUNT);
+    X.total = c.cur;
+    return X;
+}
+
+int64_t b3c_kr_exchange_bytes(int32_t n) {
+    if (n <= 0) return B3C_ERR_ARG;
+    return x_layout(n).total;
+}
+
+int b3c_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *h_handle) {
+    B3C_REQUIRE(bytes > 0 && d_ptr && h_handle, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    B3C_CUDA(cudaMalloc(&p, (size_t)bytes));
+    B3C_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    B3C_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(h_handle, &h, sizeof(h));
+    *d_ptr = p;
+    return B3C_OK;
+}
+int b3c_peer_open(const uint8_t *h_handle, void **d_ptr) {
+    B3C_REQUIRE(h_handle && d_ptr, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle, sizeof(h));
+    B3C_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B3C_OK;
+}
+int b3c_peer_close(void *d_ptr) {
+    B3C_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return B3C_OK;
+}
+int b3c_peer_free(void *d_ptr) {
+    B3C_CUDA(cudaFree(d_ptr));
+    return B3C_OK;
+}
+
+int b3c_kr_run_peer(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, const int64_t *d_indptr,
+                    const int32_t *d_indices, const double *d_data, double tol, double delta, double Delta,
+                    int32_t max_iter, int32_t rank, int32_t n_ranks, void *const *h_exchange, double *d_x, void *d_ws,
+                    int64_t ws_bytes, int64_t *h_info, void *stream) {
+    B3C_REQUIRE(n > 0 && 0 <= row_lo && row_lo < row_hi && row_hi <= n, "bad row block [%d,%d) of %d", row_lo, row_hi, n);
+    B3C_REQUIRE(row_lo % CHUNK == 0 && (row_hi % CHUNK == 0 || row_hi == n), "row blocks must be %d-row aligned", CHUNK);
+    B3C_REQUIRE(d_indptr && d_x && d_ws && h_info && h_exchange && nnz_local >= 0, "bad arguments");
+    B3C_REQUIRE(n_ranks >= 1 && n_ranks <= KR_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank %d of %d (at most %d)",
+                rank, n_ranks, KR_MAX_RANKS);
+    const KRLayout L = kr_layout(n, nnz_local);
+    if (ws_bytes < L.total) {
+        set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
+        return B3C_ERR_CAPACITY;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    KRArgs A;
+    kr_bind(A, L, (char *)d_ws, n, row_lo, row_hi, nnz_local, d_indptr, d_indices, d_data);
+    const XLayout X = x_layout(n);
+    for (int g = 0; g < n_ranks; ++g) {
+        B3C_REQUIRE(h_exchange[g] != nullptr, "null exchange buffer of rank %d", g);
+        char *b = (char *)h_exchange[g];
+        A.xflag[g] = (unsigned long long *)(b + X.o_flag);
+        A.xu[g] = (double *)(b + X.o_u);
+        A.xpart[g] = (double *)(b + X.o_part);
+    }
+    A.n_rank = n_ranks;
+    A.rank = rank;
+    A.epoch = (unsigned long long *)((char *)h_exchange[rank] + X.o_epoch);
+    A.u = A.xu[rank];
+    A.part = A.xpart[rank];
+    KRScalars S;
+    kr_scalars_init(S, tol, delta, Delta, max_iter);
+    B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
+    B3C_CUDA(cudaMemsetAsync(A.timers, 0, sizeof(KRTimers), s));
+    int rc = kr_prepare(A, L, s);
+    if (rc) return rc;
+    return kr_launch_collect(A, max_iter, d_x, h_info, s);
 }
 
 int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,

@@ -10,10 +10,15 @@ Multi-GPU driver of the hot path: one process per GPU, to
                  run-length reduces what it received: the result is its row block of the full
                  symmetric matrix, with exact integer counts whatever the number of ranks.
   mask / norm    per row block; the mask slices are combined with an all-reduce.
-  KR             row block per rank; per SpMV the vector u is assembled with an all-reduce (the
-                 slices a rank does not own are zero, so SUM is exact), the fixed-shape chunk
-                 partials of the dot products / minima are all-reduced, and the loop control runs
-                 on the device from those partials (b3c_krp_*): every rank takes the same branches.
+  KR             row block per rank.  Product path (CudaEngine.kr_run_peer): every rank runs the
+                 persistent KR kernel on its block; u and the fixed-shape chunk partials live in
+                 exchange buffers that all ranks of the node map over NVLink (CUDA IPC) and write
+                 into directly, with flag barriers in the same buffers -- no host round trip and no
+                 collective call inside the iteration.  Host-driven form (kr_block_loop, used by the
+                 gloo tests and as the reference for the peer form): per SpMV the vector u is
+                 assembled with an all-reduce (the slices a rank does not own are zero, so SUM is
+                 exact), the partials are all-reduced, and the loop control runs on the device
+                 from those partials (b3c_krp_*).  Every rank takes the same branches either way.
   compress/edges per row block; the scale 1/max needs one all-reduce(MAX).
 
 The collective layer (`Comm`) and the per-rank compute layer (`engine`) are separate so the host
@@ -21,6 +26,7 @@ logic can be exercised on CPU with the gloo backend (tests/test_dist_gloo.py inj
 engine); the product engine is CudaEngine and has no CPU fallback.
 """
 import ctypes as C
+import time
 
 import numpy as np
 import torch
@@ -91,6 +97,13 @@ class Comm(object):
     def barrier(self):
         if self.world > 1:
             dist.barrier(group=self.group)
+
+    def all_gather_object(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,6 +214,68 @@ class CudaEngine(object):
         return dict(state=int(h[0]), status=int(h[1]), n_iter=int(h[2]), k=int(h[3]), outer=int(h[4]),
                     n_spmv=int(h[5]), zero_diag=int(h[6]))
 
+    # ---- KR, peer form ---------------------------------------------------------------------------------
+    def _peer_buffers(self, comm):
+        """This rank's exchange buffer plus the mapped buffers of all other ranks (made once)."""
+        if getattr(self, '_xbuf', None) is not None:
+            return self._xbuf
+        lib = self.lib
+        assert comm.world <= 8, 'peer-mode KR handles the GPUs of one node (at most 8 ranks)'
+        nbytes = lib.b3c_kr_exchange_bytes(self.n)
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self.check(lib.b3c_peer_alloc(nbytes, C.byref(own), handle))
+        handles = comm.all_gather_object(handle.raw)
+        ptrs = (C.c_void_p * comm.world)()
+        self._x_opened = []
+        for g, h in enumerate(handles):
+            if g == comm.rank:
+                ptrs[g] = own.value
+            else:
+                p = C.c_void_p()
+                self.check(lib.b3c_peer_open(h, C.byref(p)))
+                ptrs[g] = p.value
+                self._x_opened.append(p.value)
+        self._x_own = own.value
+        self._xbuf = ptrs
+        comm.barrier()
+        return ptrs
+
+    def close_peers(self):
+        if getattr(self, '_xbuf', None) is None:
+            return
+        torch.cuda.synchronize()
+        for p in self._x_opened:
+            self.lib.b3c_peer_close(C.c_void_p(p))
+        self.lib.b3c_peer_free(C.c_void_p(self._x_own))
+        self._xbuf = None
+
+    def kr_run_peer(self, csr, tol, delta, Delta, max_iter, comm):
+        """The whole KR iteration of this rank's row block in one persistent kernel (see module docstring)."""
+        dev, lib = self.dev, self.lib
+        ptrs = self._peer_buffers(comm)
+        nbytes = lib.b3c_krp_workspace_bytes(self.n, csr.nnz)
+        if self.kr_ws is None or self.kr_ws.numel() < nbytes:
+            self.kr_ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+        x = self.pool.get('kr_x', self.n, torch.float64)
+        info = (C.c_int64 * 32)()
+        rc = lib.b3c_kr_run_peer(self.n, csr.row_lo, csr.row_lo + csr.n, csr.nnz, dev._ptr(csr.indptr),
+                                 dev._ptr(csr.indices), dev._ptr(csr.data), float(tol), float(delta), float(Delta),
+                                 int(max_iter), comm.rank, comm.world, ptrs, dev._ptr(x), dev._ptr(self.kr_ws),
+                                 self.kr_ws.numel(), info, dev._stream())
+        self.x = x
+        st = dict(state=0, status=0, n_iter=int(info[0]), zero_diag=int(info[1]), outer=int(info[2]),
+                  n_spmv=int(info[3]), kernel_us=int(info[27]), slabs=int(info[24]), nnz_stream=int(info[25]),
+                  cycles=int(info[5]))
+        names = ('init', 'spmv', 'fix', 'resid', 'dir', 'w', 'step', 'update', 'scalar')
+        st['work_cycles'] = {k: int(info[6 + i]) for i, k in enumerate(names)}
+        st['sync_cycles'] = {k: int(info[15 + i]) for i, k in enumerate(names)}
+        if rc == -6:
+            st['status'] = -6
+        else:
+            self.check(rc)
+        return st
+
     # ---- scaling + edges ----------------------------------------------------------------------------
     def kr_apply(self, csr, x):
         return self.dev.kr_apply(csr, x, pool=self.pool)
@@ -256,12 +331,33 @@ def kr_block_loop(eng, comm, max_phases=1_000_000):
     return st
 
 
+class _Trace(object):
+    """Optional wall-clock trace of the driver's sub-steps (device-synchronised; for tuning, never in timed runs)."""
+
+    def __init__(self):
+        self.on, self.t, self.out = False, 0.0, {}
+
+    def start(self):
+        self.on, self.out = True, {}
+        torch.cuda.synchronize()
+        self.t = time.perf_counter()
+
+    def mark(self, name):
+        if self.on:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.out[name] = self.out.get(name, 0.0) + (now - self.t) * 1e3
+            self.t = now
+
+
 class ShardedHotPath(object):
     """The whole path over `comm.world` ranks.  Each rank passes its own chunk of pair records."""
 
     def __init__(self, tid2idx, lengths, sites, pair_capacity, min_len=1000, min_sig=5, tol=1e-6, delta=0.1,
-                 Delta=3, max_iter=1000, comm=None, engine=None):
+                 Delta=3, max_iter=1000, comm=None, engine=None, host_driven_kr=False):
         self.comm = comm or Comm()
+        self.host_driven_kr = host_driven_kr          # True: kr_block_loop (collectives between phases)
+        self.trace = _Trace()
         self.n = int(len(lengths))
         self.min_len, self.min_sig = int(min_len), int(min_sig)
         self.kr_params = (tol, delta, Delta, max_iter)
@@ -272,14 +368,21 @@ class ShardedHotPath(object):
 
     def accumulate(self, records):
         eng, comm = self.engine, self.comm
+        tr = self.trace
         eng.classify(records)
+        tr.mark('classify')
         rowcnt = comm.all_reduce(eng.row_hist(), 'sum')
+        tr.mark('row_hist+allreduce')
         weight = rowcnt.cpu().numpy().astype(np.float64) + 1.0        # +1: the diagonal entry
         self.splits = balanced_row_splits(weight, comm.world)
+        tr.mark('splits(host)')
         send, send_counts, counters = eng.route(self.splits)
+        tr.mark('route')
         recv_counts = comm.exchange_counts(send_counts)
         keys = comm.all_to_all_v(send, send_counts, recv_counts)
+        tr.mark('all_to_all')
         comm.all_reduce(eng.diag_counts(), 'sum')
+        tr.mark('diag allreduce')
         self.row_lo, self.row_hi = int(self.splits[comm.rank]), int(self.splits[comm.rank + 1])
         dev = keys.device
         c = torch.tensor([counters['accepted'], counters['ref_excluded'], counters['poor_match']],
@@ -288,10 +391,12 @@ class ShardedHotPath(object):
         c = c.cpu().tolist()
         self.info.update(accepted=c[0], ref_excluded=c[1], poor_match=c[2], splits=self.splits.tolist(),
                          keys_received=int(keys.numel()))
+        tr.mark('counters')
         if self.row_hi > self.row_lo:
             self.block = eng.build_block(keys, self.row_lo, self.row_hi)
         else:
             self.block = None
+        tr.mark('build_block')
         return self.block
 
     def compute_mask(self):
@@ -300,14 +405,20 @@ class ShardedHotPath(object):
         if self.block is not None:
             mask[self.row_lo:self.row_hi].copy_(eng.block_mask(self.block, self.min_len, self.min_sig))
         self.mask = comm.all_reduce(mask, 'sum')
+        self.trace.mark('mask')
         return self.mask
 
     def balance(self):
         eng, comm = self.engine, self.comm
         assert self.block is not None, 'a rank without rows is not supported by the KR driver'
         self.normed = eng.site_norm(self.block)
-        eng.kr_setup(self.normed, *self.kr_params)
-        st = kr_block_loop(eng, comm)
+        self.trace.mark('site_norm')
+        if hasattr(eng, 'kr_run_peer') and not self.host_driven_kr:
+            st = eng.kr_run_peer(self.normed, *self.kr_params, comm=comm)
+        else:
+            eng.kr_setup(self.normed, *self.kr_params)
+            st = kr_block_loop(eng, comm)
+        self.trace.mark('kr')
         z = torch.tensor([st['zero_diag']], dtype=torch.int64, device=eng.x.device)
         st['zero_diag'] = int(comm.all_reduce(z, 'sum').cpu()[0])
         self.kr_info = st
@@ -322,13 +433,23 @@ class ShardedHotPath(object):
             full[self.row_lo:self.row_hi].copy_(xs[self.row_lo:self.row_hi])
             xs = comm.all_reduce(full, 'sum')
         self.x = xs
+        self.trace.mark('x allreduce')
         self.balanced = eng.kr_apply(self.normed, self.x)
+        self.trace.mark('kr_apply')
         return self.balanced
 
     def edges(self, scale=True):
         eng, comm = self.engine, self.comm
         self.edge_res = eng.compress_edges(self.balanced, self.mask, lambda t: comm.all_reduce(t, 'max'), scale=scale)
+        self.trace.mark('edges')
         return self.edge_res
+
+    def traced_run(self, records):
+        """One run with a device sync after every sub-step; returns {sub-step: ms}."""
+        self.trace.start()
+        self.run(records)
+        self.trace.on = False
+        return dict(self.trace.out)
 
     def run(self, records):
         self.accumulate(records)
@@ -394,8 +515,30 @@ def bench_main(args, rank, local_rank, world):
     sync()
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device='cuda')
     comm.all_reduce(ms, 'max')
-    clocks = sampler.stop()
     launches = dev.launch_count() - launches0
+    trace = hp.traced_run(rec_dev)
+
+    # ---- end to end: this rank's records start in pinned HOST memory, its edge list ends on the host ----
+    rec_host = torch.from_numpy(com.records.view(np.int64)).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        d = rec_host.to('cuda', non_blocking=True)
+        r = hp.run(d)
+        out = (r['u'].cpu(), r['v'].cpu(), r['w'].cpu(), r['scl'].cpu())
+        return sum(int(t.numel()) * t.element_size() for t in out)
+
+    e2e_step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        d2h = e2e_step()
+    sync()
+    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device='cuda')
+    comm.all_reduce(e2e_t, 'max')
+    d2h_t = torch.tensor([d2h], dtype=torch.int64, device='cuda')
+    comm.all_reduce(d2h_t, 'sum')
+    clocks = sampler.stop()
     tot = torch.tensor([pairs_local, int(hp.block.nnz), int(res['n_edges'])], dtype=torch.int64, device='cuda')
     comm.all_reduce(tot, 'sum')
     if rank != 0:
@@ -413,10 +556,15 @@ def bench_main(args, rank, local_rank, world):
             'l2': 'input records {} MB per GPU > 126 MB L2, no explicit flush'.format(8 * pairs_local // 1000000),
             'nnz_full': nnz_full, 'edges': n_edges, 'row_splits': hp.info['splits'], 'generator_s': round(gen_s, 1)},
         'clocks': clocks,
-        'e2e': None,
+        'e2e': {'value': total_pairs / float(e2e_t.cpu()[0]), 'unit': UNIT, 'h2d_bytes_per_step': 8 * total_pairs,
+                'd2h_bytes_per_step': int(d2h_t.cpu()[0]), 'ms_per_step': float(e2e_t.cpu()[0]) * 1e3, 'steps': e2e_steps},
         'gpu_launches': int(launches),
         'stages_ms_rank0': {k: round(v / args.steps, 4) for k, v in stage.items()},
-        'kr': {'n_iter': kr['n_iter'], 'n_spmv': kr['n_spmv'], 'outer': kr['outer'], 'zero_diag': kr['zero_diag']},
+        'kr': {'n_iter': kr['n_iter'], 'n_spmv': kr['n_spmv'], 'outer': kr['outer'], 'zero_diag': kr['zero_diag'],
+               'kernel_us': kr.get('kernel_us'), 'slabs': kr.get('slabs'),
+               'phase_us_work': {k: round(v / 1965.0, 1) for k, v in kr.get('work_cycles', {}).items()},
+               'phase_us_sync': {k: round(v / 1965.0, 1) for k, v in kr.get('sync_cycles', {}).items()}},
+        'substeps_ms_rank0_synced': {k: round(v, 3) for k, v in trace.items()},
         'pair_counts': {k: hp.info[k] for k in ('accepted', 'ref_excluded', 'poor_match')},
         'roofline': {'kernel': 'k_krp_phase(SPMV)', 'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s',
                      'frac': None, 'traffic': None, 'peak_source': peak_src,

@@ -149,7 +149,8 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  *                 each phase (init, spmv, fix-up, residual, direction, w, step, update, scalar
  *                 reductions), [15..23] = cycles it waited at the grid barrier after each,
  *                 [24] = column slabs of the SpMV operand (0 = gather form), [25] = entries of the
- *                 SpMV stream including slab padding.
+ *                 SpMV stream including slab padding, [26] = (row, slab) segments, [27] = duration
+ *                 of the persistent kernel alone in microseconds (CUDA events on `stream`).
  *                 mode 0 = one persistent cooperative kernel (device-side control flow).
  *   b3c_kr_scale  out[e] = x_i * (a_ij * x_j), the entries of X.T.dot(orig.dot(X))
  *                 (sparse_utils.py:223-224, Q9) on the ORIGINAL matrix.
@@ -210,6 +211,37 @@ int b3c_krp_setup(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local,
 int b3c_krp_phase(void *d_ws, int32_t phase, void *stream);   /* 0 INIT 1 SPMV 2 RESID 3 DIR 4 W 5 STEP 6 UPDATE */
 int b3c_krp_scalar(void *d_ws, int32_t which, void *stream);  /* 0 OUTER_FIRST 1 OUTER 2 ALPHA 3 DECIDE */
 int b3c_krp_state(void *d_ws, int64_t *h_state /* [8] */, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Peer mode of KR (multi-GPU, one process per GPU of ONE node).  Every rank runs the same persistent
+ * kernel as b3c_kr_run on its row block; the operand vector u and the fixed-shape partials live in
+ * an "exchange buffer" per rank that every other rank maps over NVLink (CUDA IPC), and each rank
+ * writes its slice of u and its partials straight into all of them (peer stores).  Cross-GPU
+ * barriers are release/acquire flags in the same buffers, so an iteration needs no host round
+ * trip and no collective call; results are those of the phase API.
+ *
+ *   b3c_peer_alloc   cudaMalloc + zero `bytes` on the current device; h_handle64 receives the 64-byte
+ *                    IPC handle to hand to the other ranks (e.g. with an all-gather)
+ *   b3c_peer_open    map another rank's buffer from its handle (peer access is enabled lazily)
+ *   b3c_peer_close / b3c_peer_free   undo open / alloc
+ *   b3c_kr_exchange_bytes            size of the exchange buffer for an n x n matrix
+ *   b3c_kr_run_peer  as b3c_kr_run on rows [row_lo, row_hi); h_exchange (HOST array of n_ranks DEVICE
+ *                    pointers) lists the exchange buffer of every rank as seen from this process,
+ *                    its own at [rank].  All ranks must call it together (the kernels wait for each
+ *                    other); a missing rank ends in B3C_ERR_CUDA after a time-out instead of a hang.
+ *                    d_x receives the whole workspace vector x: only rows [row_lo, row_hi) are
+ *                    meaningful.  h_info as b3c_kr_run; [27] = microseconds of the persistent kernel.
+ * ------------------------------------------------------------------------------------ */
+int b3c_peer_alloc(int64_t bytes, void **d_ptr, uint8_t *h_handle64);
+int b3c_peer_open(const uint8_t *h_handle64, void **d_ptr);
+int b3c_peer_close(void *d_ptr);
+int b3c_peer_free(void *d_ptr);
+int64_t b3c_kr_exchange_bytes(int32_t n);
+int b3c_kr_run_peer(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local,
+                    const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
+                    double tol, double delta, double Delta, int32_t max_iter, int32_t rank,
+                    int32_t n_ranks, void *const *h_exchange, double *d_x, void *d_ws,
+                    int64_t ws_bytes, int64_t *h_info, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Compress + edge weighting.  compress (sparse_utils.py:284-314), get_subspace

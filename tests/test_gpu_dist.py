@@ -43,7 +43,7 @@ def _check(parts, com, min_sig):
     assert np.max(np.abs(w[o] - ref['w']) / np.abs(ref['w'])) <= 1e-9
 
 
-def _run_rank(rank, world, com, min_sig):
+def _run_rank(rank, world, com, min_sig, host_driven_kr=False):
     import torch
     from bin3c_b200 import device as dev
     from bin3c_b200.dist import ShardedHotPath, Comm
@@ -51,24 +51,27 @@ def _run_rank(rank, world, com, min_sig):
     per += per & 1
     mine = com.records[rank * per:(rank + 1) * per]
     hp = ShardedHotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=int(2.5 * len(mine)) + 1024,
-                        min_len=1000, min_sig=min_sig, comm=Comm())
+                        min_len=1000, min_sig=min_sig, comm=Comm(), host_driven_kr=host_driven_kr)
     res = hp.run(dev.to_device(mine))
     torch.cuda.synchronize()
     indptr, indices, data = hp.block.host_arrays()
     row = np.repeat(np.arange(hp.block.n), np.diff(indptr)) + hp.row_lo
+    hp.engine.close_peers()
     return dict(row=row, col=indices, data=data, mask=hp.mask.cpu().numpy(), x=hp.x.cpu().numpy(),
                 n_iter=hp.kr_info['n_iter'], u=res['u'].cpu().numpy(), v=res['v'].cpu().numpy(),
                 w=res['w'].cpu().numpy(),
                 counts=np.array([hp.info[k] for k in ('accepted', 'ref_excluded', 'poor_match')]))
 
 
-def test_sharded_path_world1():
+@pytest.mark.parametrize('host_driven_kr', [False, True])
+def test_sharded_path_world1(host_driven_kr):
+    """World size 1: peer-mode KR (persistent kernel on the exchange buffer) and the host-driven phase loop."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     from bin3c_b200 import synth
     com = synth.make_community(**CFG)
-    _check([_run_rank(0, 1, com, 3)], com, 3)
+    _check([_run_rank(0, 1, com, 3, host_driven_kr)], com, 3)
 
 
 def _nccl_worker(rank, world, port, out_dir):
@@ -80,7 +83,8 @@ def _nccl_worker(rank, world, port, out_dir):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     from bin3c_b200 import synth
     com = synth.make_community(**CFG)
-    np.savez(os.path.join(out_dir, 'rank{}.npz'.format(rank)), **_run_rank(rank, world, com, 3))
+    for tag, host_driven in (('peer', False), ('host', True)):
+        np.savez(os.path.join(out_dir, '{}{}.npz'.format(tag, rank)), **_run_rank(rank, world, com, 3, host_driven))
     dist.destroy_process_group()
 
 
@@ -92,5 +96,6 @@ def test_sharded_path_two_ranks(tmp_path):
     from bin3c_b200 import synth
     mp.spawn(_nccl_worker, args=(2, 29655, str(tmp_path)), nprocs=2, join=True)
     com = synth.make_community(**CFG)
-    parts = [dict(np.load(os.path.join(str(tmp_path), 'rank{}.npz'.format(r)))) for r in range(2)]
-    _check(parts, com, 3)
+    for tag in ('peer', 'host'):
+        parts = [dict(np.load(os.path.join(str(tmp_path), '{}{}.npz'.format(tag, r)))) for r in range(2)]
+        _check(parts, com, 3)
