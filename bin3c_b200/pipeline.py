@@ -33,6 +33,9 @@ class HotPath(object):
         if pair_capacity:
             self._ensure_accumulator(pair_capacity)
         self.events = None
+        self._copy_stream = None
+        self._host = {}
+        self.h2d_bytes = self.d2h_bytes = 0
         self.reset()
 
     def reset(self):
@@ -63,7 +66,8 @@ class HotPath(object):
         """
         records: CUDA tensor (used in place) or host tensor / NumPy array of packed uint64 records.
         Host records are streamed in chunks on a side stream so the H2D copy of chunk k+1 overlaps
-        the classification of chunk k (use pinned memory for a truly asynchronous copy).
+        the classification of chunk k (use pinned memory for a truly asynchronous copy).  The chunk
+        is large on purpose: every classify launch flushes its per-CTA diagonal histograms.
         """
         if not isinstance(records, torch.Tensor):
             records = torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint64).view(np.int64))
@@ -74,18 +78,27 @@ class HotPath(object):
         if records.is_cuda:
             acc.add(records)
         else:
+            # Ring of two device staging buffers owned by the pipeline (no allocator traffic per
+            # chunk): the copy of chunk k+1 runs on the side stream while chunk k is classified.
             main = torch.cuda.current_stream()
-            copy_stream = torch.cuda.Stream()
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+                self._ring_ev = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
+            copy_stream = self._copy_stream
+            chunk = int(min(chunk_records, max(n_rec, 1)))
+            ring = [self.pool.get('stage%d' % k, chunk, torch.int64) for k in range(2)]
             copy_stream.wait_stream(main)
-            for lo in range(0, n_rec, chunk_records):
-                hi = min(lo + chunk_records, n_rec)
+            for k, lo in enumerate(range(0, n_rec, chunk)):
+                hi = min(lo + chunk, n_rec)
+                buf, (copied, consumed) = ring[k & 1][:hi - lo], self._ring_ev[k & 1]
+                if k >= 2:
+                    copy_stream.wait_event(consumed)
                 with torch.cuda.stream(copy_stream):
-                    d = records[lo:hi].to('cuda', non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                main.wait_event(ev)
-                d.record_stream(main)
-                acc.add(d)
+                    buf.copy_(records[lo:hi], non_blocking=True)
+                    copied.record(copy_stream)
+                main.wait_event(copied)
+                acc.add(buf)
+                consumed.record(main)
                 self.h2d_bytes += (hi - lo) * 8
         self._mark('classify')
         self.seq_map, self.acc_info = acc.finish(symmetric=True, pool=self.pool)
@@ -121,8 +134,8 @@ class HotPath(object):
     def run(self, records, to_host=False):
         """
         The whole path.  Returns the edge result dict (CUDA tensors, or NumPy arrays if to_host).
-        The CUDA tensors are views of the pipeline's reusable buffers: they are overwritten by the
-        next run(), so clone what must outlive it.
+        Both are views of the pipeline's reusable buffers (device buffers, or pinned host buffers
+        with to_host): they are overwritten by the next run(), so copy what must outlive it.
         """
         self.reset()
         if self.events is not None:
@@ -133,12 +146,26 @@ class HotPath(object):
         self.balance()
         res = self.edges()
         if to_host:
-            packed = (res['u'].cpu(), res['v'].cpu(), res['w'].cpu(), res['scl'].cpu())
-            self.d2h_bytes = sum(int(t.numel()) * t.element_size() for t in packed)
+            # one asynchronous D2H per array into pinned, grow-only host buffers, then one sync
+            n_edges = int(res['n_edges'])
+            host = {k: self._pinned(k, n, res[k].dtype) for k, n in (('u', n_edges), ('v', n_edges), ('w', n_edges),
+                                                                    ('scl', 1))}
+            for k, h in host.items():
+                h.copy_(res[k][:h.numel()], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.d2h_bytes = sum(int(h.numel()) * h.element_size() for h in host.values())
             self._mark('d2h')
-            return dict(u=packed[0].numpy(), v=packed[1].numpy(), w=packed[2].numpy(), scl=float(packed[3][0]),
-                        n_accepted=res['n_accepted'])
+            return dict(u=host['u'].numpy(), v=host['v'].numpy(), w=host['w'].numpy(), scl=float(host['scl'][0]),
+                        n_accepted=res['n_accepted'], n_edges=n_edges)
         return res
+
+    def _pinned(self, name, n, dtype):
+        """Grow-only pinned host buffer; returns a view of the first n elements."""
+        t = self._host.get(name)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(n + n // 4 + 16, dtype=dtype, pin_memory=True)
+            self._host[name] = t
+        return t[:n]
 
     def stage_ms(self):
         """Elapsed ms per stage from the recorded events (call after a synchronize)."""

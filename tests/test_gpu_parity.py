@@ -497,3 +497,31 @@ def test_medium_config_properties(dev):
     res = oracle.kr_scale_vector(a)
     assert kinfo['n_iter'] == res.n_iter
     assert _relerr(xx, res.x) <= REL_TOL
+
+
+def test_hotpath_host_records_match_device_records(dev):
+    """HotPath.run with (pinned / pageable) HOST records streamed through the staging ring and the
+    edge list read back into pinned host buffers == the same run with device-resident records."""
+    import torch
+    from bin3c_b200 import synth
+    from bin3c_b200.pipeline import HotPath
+    com = synth.make_community(n_genomes=12, n_contigs=3000, n_pairs=700_001, seed=99)
+    hp = HotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=com.n_pairs)
+    rec = torch.from_numpy(com.records.view(np.int64))
+    r0 = hp.run(rec.to('cuda'))
+    n = int(r0['n_edges'])
+    want = [r0[k][:n].cpu().numpy().copy() for k in ('u', 'v', 'w')] + [float(r0['scl'].cpu()[0])]
+    for host, chunk in ((rec.pin_memory(), 100_000), (rec, 1 << 24), (rec.pin_memory(), 233_334)):
+        hp.reset()
+        hp.accumulate(host, chunk_records=chunk)          # 8, 1 and 4 chunks (ragged tail)
+        assert hp.h2d_bytes == 8 * com.n_pairs
+        hp.compute_mask(); hp.normalise(); hp.balance(); hp.edges()
+        got = hp.edge_res
+        assert int(got['n_edges']) == n
+        for k, w in zip(('u', 'v', 'w'), want):
+            assert np.array_equal(got[k][:n].cpu().numpy(), w)
+    out = hp.run(rec.pin_memory(), to_host=True)
+    assert out['n_edges'] == n and hp.d2h_bytes == 16 * n + 8
+    for k, w in zip(('u', 'v', 'w'), want):
+        assert np.array_equal(out[k], w)
+    assert out['scl'] == want[3]

@@ -55,6 +55,18 @@ def test_loop_equals_vectorised(golden):
     assert np.array_equal(m1.row, m2.row) and np.array_equal(m1.col, m2.col) and np.array_equal(m1.data, m2.data)
 
 
+def test_threaded_accumulation_equals_vectorised():
+    """The multi-threaded CPU-baseline accumulation is the same integer sort-reduce."""
+    com = synth.make_community(n_genomes=6, n_contigs=1200, n_pairs=600_000, seed=31)
+    ti, tj, ok = synth.unpack_pairs(com.records)
+    up1, c1 = oracle.bin_pairs_fast(ti, tj, ok, com.tid2idx(), com.n_contigs)
+    for threads in (2, 5):
+        up2, c2 = oracle.bin_pairs_threads(ti, tj, ok, com.tid2idx(), com.n_contigs, threads)
+        assert c1 == c2
+        assert np.array_equal(up1.row, up2.row) and np.array_equal(up1.col, up2.col)
+        assert np.array_equal(up1.data, up2.data) and up2.dtype == np.uint32
+
+
 def test_mask_bit_exact(golden):
     g = golden
     m = _seq_map(g)
