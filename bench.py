@@ -51,6 +51,15 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic(cfg, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            return int(json.load(fh)[cfg][kernel]['bytes'])
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -272,6 +281,9 @@ def main():
                 'unit': 'GB/s', 'frac': cls_bytes / (t_cls * 1e-3) / 1e9 / peak, 'traffic': None,
                 'peak_source': peak_src, 'bytes_per_launch': cls_bytes, 'ms_per_launch': t_cls,
                 'note': '8 B per packed pair record read once'}
+    if args.scale == 1.0:
+        roof_kr['traffic'] = ncu_traffic(cfg, 'k_kr_persistent')
+        roof_cls['traffic'] = ncu_traffic(cfg, 'k_classify')
     roofline, other = (roof_kr, roof_cls) if stage_ms.get('kr', 0.0) >= t_cls else (roof_cls, roof_kr)
 
     # ---- CPU baseline on a bounded sample -------------------------------------------------------------------
