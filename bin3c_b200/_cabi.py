@@ -58,6 +58,7 @@ SIGNATURES = {
     'b3c_site_norm_f64': (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p]),
     'b3c_kr_workspace_bytes': (_i64, [_i32, _i64]),
     'b3c_kr_run': (C.c_int, [_i32, _i64, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _p, _p, _i64, _pi64, _p]),
+    'b3c_kr_run_counts': (C.c_int, [_i32, _i64, _p, _p, _p, _p, _f64, _f64, _f64, _i32, _p, _p, _i64, _pi64, _p]),
     'b3c_krp_workspace_bytes': (_i64, [_i32, _i64]),
     'b3c_krp_setup': (C.c_int, [_i32, _i32, _i32, _i64, _p, _p, _p, _f64, _f64, _f64, _i32, _p, _i64, _pi64, _p]),
     'b3c_krp_phase': (C.c_int, [_p, _i32, _p]),
@@ -74,10 +75,14 @@ SIGNATURES = {
     'b3c_kr_exchange_bytes': (_i64, [_i32]),
     'b3c_kr_run_peer': (C.c_int, [_i32, _i32, _i32, _i64, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _i32,
                                   C.POINTER(C.c_void_p), _p, _p, _i64, _pi64, _p]),
+    'b3c_kr_run_peer_counts': (C.c_int, [_i32, _i32, _i32, _i64, _p, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _i32,
+                                         C.POINTER(C.c_void_p), _p, _p, _i64, _pi64, _p]),
     'b3c_compress_workspace_bytes': (_i64, [_i32]),
     'b3c_compress_count': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _pi64, _p]),
     'b3c_compress_fill': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p,
                                     _p]),
+    'b3c_edges_count': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _pi64, _p]),
+    'b3c_edges_fill': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

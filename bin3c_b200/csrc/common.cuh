@@ -113,6 +113,14 @@ __device__ __forceinline__ unsigned warp_max_u32(unsigned v) {
     return v;
 }
 
+// count / (s_i * s_j) with the reference's operation order (contact_map.py:110-113: t = s_i*s_j; r = 1.0/t;
+// d = d*r) and zero site counts taken as one (contact_map.py:1103-1108, Q6): the value k_site_norm writes.
+__device__ __forceinline__ double site_scaled(uint32_t count, int32_t s_row, int32_t s_col) {
+    const double si = s_row == 0 ? 1.0 : (double)s_row;
+    const double sj = s_col == 0 ? 1.0 : (double)s_col;
+    return __dmul_rn((double)count, __ddiv_rn(1.0, __dmul_rn(si, sj)));
+}
+
 // inclusive warp scan
 template <typename T>
 __device__ __forceinline__ T warp_scan_incl(T v) {

@@ -95,6 +95,9 @@ struct KRArgs {
     const int64_t *indptr;
     const int32_t *indices;
     const double *data;
+    // counts form: data == nullptr, the value of an entry is count / (s_i * s_j) computed on the fly
+    const uint32_t *cnt32;
+    const int32_t *sites;
     // the stream
     int32_t slab;              // 1: 16-bit columns, u gathered from shared memory; 0: 32-bit columns, gather form
     int32_t S, W, npad;        // slabs (1 in gather form), slab width, local rows padded to CHUNK
@@ -1005,6 +1008,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
     bool bad = false;
     for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < n_local; lr += nw) {
         const int64_t lo = A.indptr[lr], hi = A.indptr[lr + 1];
+        const int32_t s_row = (FILL && A.cnt32) ? A.sites[A.row_lo + lr] : 1;
         int carry_s = -1;
         int64_t carry_start = lo;
         for (int64_t e0 = lo; e0 < hi; e0 += 32) {
@@ -1032,7 +1036,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 const int64_t seg_start = upto ? e0 + (31 - __clz(upto)) : carry_start;
                 const int64_t dst = A.vp[(int64_t)s * A.npad + lr] + (e - seg_start);
                 const int64_t ph = stream_phys(dst);
-                sval[ph] = A.data[e];
+                sval[ph] = A.cnt32 ? site_scaled(A.cnt32[e], s_row, __ldg(A.sites + col)) : A.data[e];
                 const unsigned lc = (unsigned)(col - s * W);
                 if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
                 else ((uint32_t *)scol_v)[ph] = lc;
@@ -1122,6 +1126,7 @@ __global__ void __launch_bounds__(256) k_chunk_seg0(int64_t n_chunks, int64_t nv
 // dfix[r] = 1 where the diagonal entry of (global) row r is absent or zero (sparse_utils.py:110-115)
 __global__ void __launch_bounds__(256) k_diag_fix(int32_t row_lo, int32_t row_hi, const int64_t *__restrict__ indptr,
                                                   const int32_t *__restrict__ indices, const double *__restrict__ data,
+                                                  const uint32_t *__restrict__ cnt32, const int32_t *__restrict__ sites,
                                                   double *__restrict__ dfix, KRScalars *ctl) {
     const unsigned lane = lane_id();
     const int64_t nw = (int64_t)gridDim.x * 8;
@@ -1131,7 +1136,7 @@ __global__ void __launch_bounds__(256) k_diag_fix(int32_t row_lo, int32_t row_hi
         const int32_t gr = row_lo + (int32_t)lr;
         double d = 0.0;           // duplicates of the diagonal would be summed by scipy's diagonal()
         for (int64_t e = lo + lane; e < hi; e += 32)
-            if (indices[e] == gr) d += data[e];
+            if (indices[e] == gr) d += cnt32 ? site_scaled(cnt32[e], sites[gr], sites[gr]) : data[e];
         d = warp_sum(d);
         if (lane == 0) {
             const bool z = (d == 0.0);
@@ -1297,6 +1302,8 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.indptr = indptr;
     A.indices = indices;
     A.data = data;
+    A.cnt32 = nullptr;
+    A.sites = nullptr;
     A.slab = L.slab;
     A.S = L.S;
     A.W = L.W;
@@ -1438,7 +1445,8 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
         B3C_LAUNCH_CHECK();
     }
     B3C_CUDA(cudaMemsetAsync(A.qs, 0, (size_t)(A.n_seg + 1) * 8, s));
-    k_diag_fix<<<row_warp_grid(n_local), 256, 0, s>>>(A.row_lo, A.row_hi, A.indptr, A.indices, A.data, A.dfix, A.ctl);
+    k_diag_fix<<<row_warp_grid(n_local), 256, 0, s>>>(A.row_lo, A.row_hi, A.indptr, A.indices, A.data, A.cnt32, A.sites,
+                                                              A.dfix, A.ctl);
     B3C_LAUNCH_CHECK();
     rc = persistent_grid(SLAB, &A.n_bnd);
     return rc;
@@ -1552,12 +1560,11 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     return B3C_OK;
 }
 
-int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
-               double tol, double delta, double Delta, int32_t max_iter, int32_t mode, double *d_x, void *d_ws,
-               int64_t ws_bytes, int64_t *h_info, void *stream) {
+static int kr_run_impl(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
+                       const uint32_t *d_counts, const int32_t *d_sites, double tol, double delta, double Delta,
+                       int32_t max_iter, double *d_x, void *d_ws, int64_t ws_bytes, int64_t *h_info, void *stream) {
     B3C_REQUIRE(n > 0 && nnz >= 0 && d_indptr && d_x && d_ws && h_info, "bad arguments");
-    B3C_REQUIRE(nnz == 0 || (d_indices && d_data), "null matrix arrays");
-    B3C_REQUIRE(mode == 0, "b3c_kr_run: only mode 0 (persistent kernel) is implemented; use b3c_krp_* for phases");
+    B3C_REQUIRE(nnz == 0 || (d_indices && (d_data || (d_counts && d_sites))), "null matrix arrays");
     const KRLayout L = kr_layout(n, nnz);
     if (ws_bytes < L.total) {
         set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
@@ -1566,6 +1573,8 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
     cudaStream_t s = (cudaStream_t)stream;
     KRArgs A;
     kr_bind(A, L, (char *)d_ws, n, 0, n, nnz, d_indptr, d_indices, d_data);
+    A.cnt32 = d_data ? nullptr : d_counts;
+    A.sites = d_data ? nullptr : d_sites;
     KRScalars S;
     kr_scalars_init(S, tol, delta, Delta, max_iter);
     B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
@@ -1573,6 +1582,23 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
     int rc = kr_prepare(A, L, s);
     if (rc) return rc;
     return kr_launch_collect(A, max_iter, d_x, h_info, s);
+}
+
+int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
+               double tol, double delta, double Delta, int32_t max_iter, int32_t mode, double *d_x, void *d_ws,
+               int64_t ws_bytes, int64_t *h_info, void *stream) {
+    B3C_REQUIRE(mode == 0, "b3c_kr_run: only mode 0 (persistent kernel) is implemented; use b3c_krp_* for phases");
+    B3C_REQUIRE(nnz == 0 || d_data, "null matrix values");
+    return kr_run_impl(n, nnz, d_indptr, d_indices, d_data, nullptr, nullptr, tol, delta, Delta, max_iter, d_x, d_ws,
+                       ws_bytes, h_info, stream);
+}
+
+int b3c_kr_run_counts(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices,
+                      const uint32_t *d_counts, const int32_t *d_sites, double tol, double delta, double Delta,
+                      int32_t max_iter, double *d_x, void *d_ws, int64_t ws_bytes, int64_t *h_info, void *stream) {
+    B3C_REQUIRE(d_sites && (nnz == 0 || d_counts), "null counts / sites");
+    return kr_run_impl(n, nnz, d_indptr, d_indices, nullptr, d_counts, d_sites, tol, delta, Delta, max_iter, d_x, d_ws,
+                       ws_bytes, h_info, stream);
 }
 
 // ---- peer mode: one persistent kernel per GPU of a node, exchange buffers mapped over NVLink ------------
@@ -1624,10 +1650,11 @@ int b3c_peer_free(void *d_ptr) {
     return B3C_OK;
 }
 
-int b3c_kr_run_peer(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, const int64_t *d_indptr,
-                    const int32_t *d_indices, const double *d_data, double tol, double delta, double Delta,
-                    int32_t max_iter, int32_t rank, int32_t n_ranks, void *const *h_exchange, double *d_x, void *d_ws,
-                    int64_t ws_bytes, int64_t *h_info, void *stream) {
+static int kr_run_peer_impl(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, const int64_t *d_indptr,
+                            const int32_t *d_indices, const double *d_data, const uint32_t *d_counts,
+                            const int32_t *d_sites, double tol, double delta, double Delta, int32_t max_iter,
+                            int32_t rank, int32_t n_ranks, void *const *h_exchange, double *d_x, void *d_ws,
+                            int64_t ws_bytes, int64_t *h_info, void *stream) {
     B3C_REQUIRE(n > 0 && 0 <= row_lo && row_lo < row_hi && row_hi <= n, "bad row block [%d,%d) of %d", row_lo, row_hi, n);
     B3C_REQUIRE(row_lo % CHUNK == 0 && (row_hi % CHUNK == 0 || row_hi == n), "row blocks must be %d-row aligned", CHUNK);
     B3C_REQUIRE(d_indptr && d_x && d_ws && h_info && h_exchange && nnz_local >= 0, "bad arguments");
@@ -1641,6 +1668,8 @@ int b3c_kr_run_peer(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local
     cudaStream_t s = (cudaStream_t)stream;
     KRArgs A;
     kr_bind(A, L, (char *)d_ws, n, row_lo, row_hi, nnz_local, d_indptr, d_indices, d_data);
+    A.cnt32 = d_data ? nullptr : d_counts;
+    A.sites = d_data ? nullptr : d_sites;
     const XLayout X = x_layout(n);
     for (int g = 0; g < n_ranks; ++g) {
         B3C_REQUIRE(h_exchange[g] != nullptr, "null exchange buffer of rank %d", g);
@@ -1661,6 +1690,25 @@ int b3c_kr_run_peer(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local
     int rc = kr_prepare(A, L, s);
     if (rc) return rc;
     return kr_launch_collect(A, max_iter, d_x, h_info, s);
+}
+
+int b3c_kr_run_peer(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, const int64_t *d_indptr,
+                    const int32_t *d_indices, const double *d_data, double tol, double delta, double Delta,
+                    int32_t max_iter, int32_t rank, int32_t n_ranks, void *const *h_exchange, double *d_x, void *d_ws,
+                    int64_t ws_bytes, int64_t *h_info, void *stream) {
+    B3C_REQUIRE(nnz_local == 0 || d_data, "null matrix values");
+    return kr_run_peer_impl(n, row_lo, row_hi, nnz_local, d_indptr, d_indices, d_data, nullptr, nullptr, tol, delta, Delta,
+                            max_iter, rank, n_ranks, h_exchange, d_x, d_ws, ws_bytes, h_info, stream);
+}
+
+int b3c_kr_run_peer_counts(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, const int64_t *d_indptr,
+                           const int32_t *d_indices, const uint32_t *d_counts, const int32_t *d_sites, double tol,
+                           double delta, double Delta, int32_t max_iter, int32_t rank, int32_t n_ranks,
+                           void *const *h_exchange, double *d_x, void *d_ws, int64_t ws_bytes, int64_t *h_info,
+                           void *stream) {
+    B3C_REQUIRE(d_sites && (nnz_local == 0 || d_counts), "null counts / sites");
+    return kr_run_peer_impl(n, row_lo, row_hi, nnz_local, d_indptr, d_indices, nullptr, d_counts, d_sites, tol, delta,
+                            Delta, max_iter, rank, n_ranks, h_exchange, d_x, d_ws, ws_bytes, h_info, stream);
 }
 
 int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,

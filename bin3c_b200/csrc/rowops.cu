@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_asym_count(int32_t n, const int
 // ---- compress + edge weighting ------------------------------------------------------------------
 // workspace layout (int64 elements unless noted)
 struct CompressWs {
-    int64_t o_flag, o_newidx64, o_kept, o_kept_ex, o_edge, o_edge_ex, o_scan, o_max, total;
+    int64_t o_flag, o_newidx64, o_kept, o_kept_ex, o_edge, o_edge_ex, o_scan, o_max, o_attr, total;
 };
 static CompressWs compress_layout(int32_t n) {
     Carver c;
@@ -127,6 +127,7 @@ static CompressWs compress_layout(int32_t n) {
     w.o_edge_ex = c.take(n1 * 8);
     w.o_scan = c.take(scan_tmp_elems(n) * 8);
     w.o_max = c.take(64);
+    w.o_attr = c.take((int64_t)n * 16);
     w.total = c.cur;
     return w;
 }
@@ -229,6 +230,124 @@ __global__ void __launch_bounds__(ROW_THREADS) k_compress_fill(
                 }
             }
             kbase += __popc(mk);
+            ebase += __popc(me);
+        }
+    }
+}
+
+// ---- fused form: edge list straight from counts, sites and the KR scale vector -----------------------
+// The value of an entry is recomputed where it is consumed, x_i * ((count / (s_i s_j)) * x_j) -- what
+// k_site_norm followed by k_kr_scale would have stored -- so neither intermediate matrix exists.  What a
+// column needs (gapless id or -1, site count, x) is packed into one 16-byte record per contig, so an
+// entry costs ONE scattered 128-bit gather instead of four scalar ones (a scattered warp load costs one
+// L1 wavefront per distinct line whatever its width).
+struct __align__(16) ContigAttr {
+    int32_t newidx;          // index among the accepted contigs, -1 if rejected
+    int32_t site;
+    double x;
+};
+static_assert(sizeof(ContigAttr) == 16, "one 128-bit gather per entry");
+
+__device__ __forceinline__ ContigAttr ld_attr(const ContigAttr *p) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    ContigAttr a;
+    a.newidx = (int32_t)v.x;
+    a.site = (int32_t)v.y;
+    a.x = __hiloint2double((int)v.w, (int)v.z);
+    return a;
+}
+
+__global__ void k_edge_attr(int32_t n, const uint8_t *__restrict__ mask, const int64_t *__restrict__ ex,
+                            const int32_t *__restrict__ sites, const double *__restrict__ x,
+                            ContigAttr *__restrict__ attr, int32_t *__restrict__ newidx) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        ContigAttr a;
+        a.newidx = mask[i] ? (int32_t)ex[i] : -1;
+        a.site = sites[i];
+        a.x = x[i];
+        attr[i] = a;
+        newidx[i] = a.newidx;
+    }
+}
+
+__device__ __forceinline__ double edge_value(uint32_t count, const ContigAttr &ar, const ContigAttr &ac) {
+    return __dmul_rn(ar.x, __dmul_rn(site_scaled(count, ar.site, ac.site), ac.x));
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) k_edges_count(int32_t n, int32_t row_lo,
+                                                             const int64_t *__restrict__ indptr,
+                                                             const int32_t *__restrict__ indices,
+                                                             const uint32_t *__restrict__ counts,
+                                                             const ContigAttr *__restrict__ attr,
+                                                             int64_t *__restrict__ kept, int64_t *__restrict__ edge,
+                                                             unsigned long long *__restrict__ vmax) {
+    const unsigned lane = lane_id();
+    const int64_t nw = (int64_t)gridDim.x * ROW_WARPS;
+    double wmax = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
+        unsigned k = 0, ed = 0;
+        const int32_t gr = (int32_t)r + row_lo;
+        const ContigAttr ar = ld_attr(attr + gr);
+        if (ar.newidx >= 0) {
+            const int64_t lo = indptr[r], hi = indptr[r + 1];
+            for (int64_t e = lo + lane; e < hi; e += 32) {
+                const int32_t c = indices[e];
+                const ContigAttr ac = ld_attr(attr + c);
+                if (ac.newidx >= 0) {
+                    ++k;
+                    ed += (c >= gr) ? 1u : 0u;
+                    wmax = fmax(wmax, edge_value(counts[e], ar, ac));
+                }
+            }
+        }
+        k = warp_sum(k);
+        ed = warp_sum(ed);
+        if (lane == 0) {
+            kept[r] = k;
+            edge[r] = ed;
+        }
+    }
+    wmax = warp_max(wmax);
+    if (lane == 0 && wmax > 0.0) atomicMax(vmax, (unsigned long long)__double_as_longlong(wmax));
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) k_edges_fill(int32_t n, int32_t row_lo,
+                                                            const int64_t *__restrict__ indptr,
+                                                            const int32_t *__restrict__ indices,
+                                                            const uint32_t *__restrict__ counts,
+                                                            const ContigAttr *__restrict__ attr,
+                                                            const int64_t *__restrict__ edge_ex,
+                                                            const double *__restrict__ vmax, int scale,
+                                                            int32_t *__restrict__ eu, int32_t *__restrict__ ev,
+                                                            double *__restrict__ ew, double *__restrict__ scl_out) {
+    const unsigned lane = lane_id(), lt = lanemask_lt();
+    const int64_t nw = (int64_t)gridDim.x * ROW_WARPS;
+    const double scl = scale ? __ddiv_rn(1.0, *vmax) : 1.0;                 // cluster.py:316
+    if (blockIdx.x == 0 && threadIdx.x == 0 && scl_out) *scl_out = scl;
+    for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
+        const int32_t gr = (int32_t)r + row_lo;
+        const ContigAttr ar = ld_attr(attr + gr);
+        if (ar.newidx < 0) continue;
+        const int64_t lo = indptr[r], hi = indptr[r + 1];
+        int64_t ebase = edge_ex[r];
+        // columns are sorted: the upper-triangle entries (c >= row) are the tail of the row
+        for (int64_t e0 = lo; e0 < hi; e0 += 32) {
+            const int64_t e = e0 + lane;
+            int32_t c = -1;
+            ContigAttr ac;
+            ac.newidx = -1;
+            if (e < hi) {
+                c = indices[e];
+                if (c >= gr) ac = ld_attr(attr + c);
+            }
+            const bool is_edge = ac.newidx >= 0;
+            const unsigned me = __ballot_sync(kFullMask, is_edge);
+            if (is_edge) {
+                const int64_t d = ebase + __popc(me & lt);
+                eu[d] = ar.newidx;
+                ev[d] = ac.newidx;
+                ew[d] = __dmul_rn(edge_value(counts[e], ar, ac), scl);      // cluster.py:321
+            }
             ebase += __popc(me);
         }
     }
@@ -370,6 +489,60 @@ int b3c_compress_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t 
         n_local, row_lo, d_indptr, d_indices, d_data, d_mask, d_newidx, (const int64_t *)(ws + w.o_kept_ex),
         (const int64_t *)(ws + w.o_edge_ex), (const int64_t *)(ws + w.o_newidx64) + n, d_vmax, scale, d_sub_indptr,
         d_sub_indices, d_sub_data, d_edge_u, d_edge_v, d_edge_w, d_scl);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_edges_count(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_indptr, const int32_t *d_indices,
+                    const uint32_t *d_counts, const int32_t *d_sites, const double *d_x, const uint8_t *d_mask,
+                    int32_t *d_newidx, void *d_ws, int64_t ws_bytes, double *d_vmax, int64_t *h_out, void *stream) {
+    B3C_REQUIRE(n > 0 && n_local > 0 && row_lo >= 0 && row_lo + n_local <= n, "bad row block");
+    B3C_REQUIRE(d_indptr && d_counts && d_sites && d_x && d_mask && d_newidx && d_ws && d_vmax && h_out, "null pointer");
+    const CompressWs w = compress_layout(n);
+    if (ws_bytes < w.total) {
+        set_error("compress workspace too small: %lld < %lld", (long long)ws_bytes, (long long)w.total);
+        return B3C_ERR_CAPACITY;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    int64_t *flag = (int64_t *)(ws + w.o_flag), *nidx = (int64_t *)(ws + w.o_newidx64);
+    int64_t *kept = (int64_t *)(ws + w.o_kept), *kept_ex = (int64_t *)(ws + w.o_kept_ex);
+    int64_t *edge = (int64_t *)(ws + w.o_edge), *edge_ex = (int64_t *)(ws + w.o_edge_ex);
+    int64_t *scan = (int64_t *)(ws + w.o_scan);
+    ContigAttr *attr = (ContigAttr *)(ws + w.o_attr);
+    B3C_CUDA(cudaMemsetAsync(d_vmax, 0, 8, s));
+    const unsigned g = (unsigned)ceil_div(n, 256);
+    k_mask_flags<<<g, 256, 0, s>>>(n, d_mask, flag);
+    B3C_LAUNCH_CHECK();
+    int rc = scan_exclusive_i64(flag, nidx, n, scan, s);
+    if (rc) return rc;
+    k_edge_attr<<<g, 256, 0, s>>>(n, d_mask, nidx, d_sites, d_x, attr, d_newidx);
+    B3C_LAUNCH_CHECK();
+    k_edges_count<<<row_grid(n_local), ROW_THREADS, 0, s>>>(n_local, row_lo, d_indptr, d_indices, d_counts, attr, kept,
+                                                            edge, (unsigned long long *)d_vmax);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(kept, kept_ex, n_local, scan, s);
+    if (rc) return rc;
+    rc = scan_exclusive_i64(edge, edge_ex, n_local, scan, s);
+    if (rc) return rc;
+    B3C_CUDA(cudaMemcpyAsync(&h_out[0], nidx + n, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(&h_out[1], kept_ex + n_local, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(&h_out[2], edge_ex + n_local, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaStreamSynchronize(s));
+    return B3C_OK;
+}
+
+int b3c_edges_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_indptr, const int32_t *d_indices,
+                   const uint32_t *d_counts, void *d_ws, const double *d_vmax, int scale, int32_t *d_edge_u,
+                   int32_t *d_edge_v, double *d_edge_w, double *d_scl, void *stream) {
+    B3C_REQUIRE(n > 0 && n_local > 0 && row_lo >= 0 && row_lo + n_local <= n, "bad row block");
+    B3C_REQUIRE(d_indptr && d_counts && d_ws && d_vmax && d_edge_u && d_edge_v && d_edge_w, "null pointer");
+    // the per-contig records b3c_edges_count left in d_ws hold the site counts, x and the gapless ids
+    const CompressWs w = compress_layout(n);
+    char *ws = (char *)d_ws;
+    k_edges_fill<<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        n_local, row_lo, d_indptr, d_indices, d_counts, (const ContigAttr *)(ws + w.o_attr),
+        (const int64_t *)(ws + w.o_edge_ex), d_vmax, scale, d_edge_u, d_edge_v, d_edge_w, d_scl);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }

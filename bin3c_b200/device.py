@@ -220,14 +220,24 @@ def _kr_workspace(n, nnz):
     return ws
 
 
-def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000, pool=None):
-    """Returns (x CUDA float64[n], info dict) for a symmetric float64 DeviceCSR."""
-    assert csr.data.dtype == torch.float64
+def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000, pool=None, sites=None):
+    """
+    Returns (x CUDA float64[n], info dict) for a symmetric float64 DeviceCSR -- or, with `sites`, for a
+    uint32 count matrix that is site-normalised on the fly (the normalised matrix is never written).
+    """
     ws = _kr_workspace(csr.n, csr.nnz)
     x = _alloc(pool, 'kr_x', csr.n, torch.float64)
     info = (C.c_int64 * 32)()
-    rc = lib.b3c_kr_run(csr.n, csr.nnz, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), float(tol),
-                        float(delta), float(Delta), int(max_iter), 0, _ptr(x), _ptr(ws), ws.numel(), info, _stream())
+    if sites is not None:
+        assert csr.counts, 'the counts form takes the raw uint32 contact matrix'
+        rc = lib.b3c_kr_run_counts(csr.n, csr.nnz, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites),
+                                   float(tol), float(delta), float(Delta), int(max_iter), _ptr(x), _ptr(ws),
+                                   ws.numel(), info, _stream())
+    else:
+        assert csr.data.dtype == torch.float64
+        rc = lib.b3c_kr_run(csr.n, csr.nnz, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), float(tol),
+                            float(delta), float(Delta), int(max_iter), 0, _ptr(x), _ptr(ws), ws.numel(), info,
+                            _stream())
     names = ('init', 'spmv', 'fix', 'resid', 'dir', 'w', 'step', 'update', 'scalar')
     out = dict(n_iter=int(info[0]), zero_diag=int(info[1]), outer=int(info[2]), n_spmv=int(info[3]),
                grid=int(info[4]), cycles=int(info[5]),
@@ -269,14 +279,21 @@ def spmv(csr, u, y=None, ws=None, prepared=False):
 # compress + edge weighting
 # --------------------------------------------------------------------------------------
 
-def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True, pool=None, reduce_max=None):
+def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True, pool=None, reduce_max=None, sites=None,
+                   x=None):
     """
     Drop rejected contigs and produce the compressed matrix and/or the weighted edge list of a
     matrix or row block.  `mask` covers all csr.n_total contigs.  `reduce_max(tensor)` lets a
     multi-GPU driver all-reduce the block maximum before the weights are scaled.
+    Fused form: csr holds the raw uint32 counts and `sites`, `x` (site counts, KR scale vector) are
+    given -- the edge weights are normalised and balanced on the fly (edge list only).
     Returns dict(n_accepted, sub=DeviceCSR|None, u, v, w, scl) with CUDA tensors.
     """
-    assert csr.data.dtype == torch.float64
+    fused = sites is not None
+    if fused:
+        assert csr.counts and x is not None and not want_sub and want_edges
+    else:
+        assert csr.data.dtype == torch.float64
     n, nl = csr.n_total, csr.n
     whole = (csr.row_lo == 0 and nl == n)
     assert whole or not want_sub, 'the compressed matrix is only produced for a whole matrix'
@@ -285,8 +302,12 @@ def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True, pool=N
     newidx = _alloc(pool, 'newidx', n, torch.int32)
     vmax = _alloc(pool, 'vmax', 1, torch.float64)
     h = (C.c_int64 * 4)()
-    check(lib.b3c_compress_count(n, csr.row_lo, nl, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask),
-                                 _ptr(newidx), _ptr(ws), ws.numel(), _ptr(vmax), h, _stream()))
+    if fused:
+        check(lib.b3c_edges_count(n, csr.row_lo, nl, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(sites),
+                                  _ptr(x), _ptr(mask), _ptr(newidx), _ptr(ws), ws.numel(), _ptr(vmax), h, _stream()))
+    else:
+        check(lib.b3c_compress_count(n, csr.row_lo, nl, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data),
+                                     _ptr(mask), _ptr(newidx), _ptr(ws), ws.numel(), _ptr(vmax), h, _stream()))
     if reduce_max is not None:
         reduce_max(vmax)
     n_acc, n_kept, n_edges = int(h[0]), int(h[1]), int(h[2])
@@ -300,9 +321,14 @@ def compress_edges(csr, mask, want_sub=True, want_edges=True, scale=True, pool=N
         ev = _alloc(pool, 'edge_v', n_edges, torch.int32)
         ew = _alloc(pool, 'edge_w', n_edges, torch.float64)
     scl = _alloc(pool, 'scl', 1, torch.float64)
-    check(lib.b3c_compress_fill(n, csr.row_lo, nl, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(mask),
-                                _ptr(newidx), _ptr(ws), _ptr(vmax), 1 if scale else 0, _ptr(sub_indptr),
-                                _ptr(sub_indices), _ptr(sub_data), _ptr(eu), _ptr(ev), _ptr(ew), _ptr(scl), _stream()))
+    if fused:
+        check(lib.b3c_edges_fill(n, csr.row_lo, nl, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(ws),
+                                 _ptr(vmax), 1 if scale else 0, _ptr(eu), _ptr(ev), _ptr(ew), _ptr(scl), _stream()))
+    else:
+        check(lib.b3c_compress_fill(n, csr.row_lo, nl, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data),
+                                    _ptr(mask), _ptr(newidx), _ptr(ws), _ptr(vmax), 1 if scale else 0,
+                                    _ptr(sub_indptr), _ptr(sub_indices), _ptr(sub_data), _ptr(eu), _ptr(ev), _ptr(ew),
+                                    _ptr(scl), _stream()))
     sub = DeviceCSR(n_acc, sub_indptr, sub_indices, sub_data) if want_sub else None
     return dict(n_accepted=n_acc, n_kept=n_kept, n_edges=n_edges, sub=sub, u=eu, v=ev, w=ew, scl=scl, newidx=newidx)
 

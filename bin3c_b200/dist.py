@@ -250,8 +250,11 @@ class CudaEngine(object):
         self.lib.b3c_peer_free(C.c_void_p(self._x_own))
         self._xbuf = None
 
+    fused = True      # KR and the edge emission take the raw counts (normalised / balanced on the fly)
+
     def kr_run_peer(self, csr, tol, delta, Delta, max_iter, comm):
-        """The whole KR iteration of this rank's row block in one persistent kernel (see module docstring)."""
+        """The whole KR iteration of this rank's row block in one persistent kernel (see module docstring).
+        csr: float64 normalised block, or the raw uint32 count block (site-normalised on the fly)."""
         dev, lib = self.dev, self.lib
         ptrs = self._peer_buffers(comm)
         nbytes = lib.b3c_krp_workspace_bytes(self.n, csr.nnz)
@@ -259,10 +262,16 @@ class CudaEngine(object):
             self.kr_ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
         x = self.pool.get('kr_x', self.n, torch.float64)
         info = (C.c_int64 * 32)()
-        rc = lib.b3c_kr_run_peer(self.n, csr.row_lo, csr.row_lo + csr.n, csr.nnz, dev._ptr(csr.indptr),
-                                 dev._ptr(csr.indices), dev._ptr(csr.data), float(tol), float(delta), float(Delta),
-                                 int(max_iter), comm.rank, comm.world, ptrs, dev._ptr(x), dev._ptr(self.kr_ws),
-                                 self.kr_ws.numel(), info, dev._stream())
+        if csr.counts:
+            rc = lib.b3c_kr_run_peer_counts(self.n, csr.row_lo, csr.row_lo + csr.n, csr.nnz, dev._ptr(csr.indptr),
+                                            dev._ptr(csr.indices), dev._ptr(csr.data), dev._ptr(self.sites), float(tol),
+                                            float(delta), float(Delta), int(max_iter), comm.rank, comm.world, ptrs,
+                                            dev._ptr(x), dev._ptr(self.kr_ws), self.kr_ws.numel(), info, dev._stream())
+        else:
+            rc = lib.b3c_kr_run_peer(self.n, csr.row_lo, csr.row_lo + csr.n, csr.nnz, dev._ptr(csr.indptr),
+                                     dev._ptr(csr.indices), dev._ptr(csr.data), float(tol), float(delta), float(Delta),
+                                     int(max_iter), comm.rank, comm.world, ptrs, dev._ptr(x), dev._ptr(self.kr_ws),
+                                     self.kr_ws.numel(), info, dev._stream())
         self.x = x
         st = dict(state=0, status=0, n_iter=int(info[0]), zero_diag=int(info[1]), outer=int(info[2]),
                   n_spmv=int(info[3]), kernel_us=int(info[27]), slabs=int(info[24]), nnz_stream=int(info[25]),
@@ -280,9 +289,10 @@ class CudaEngine(object):
     def kr_apply(self, csr, x):
         return self.dev.kr_apply(csr, x, pool=self.pool)
 
-    def compress_edges(self, csr, mask, reduce_max, scale=True):
+    def compress_edges(self, csr, mask, reduce_max, scale=True, x=None):
+        """csr: the balanced float64 block, or (with x) the raw count block -- fused form."""
         return self.dev.compress_edges(csr, mask, want_sub=False, want_edges=True, scale=scale, pool=self.pool,
-                                       reduce_max=reduce_max)
+                                       reduce_max=reduce_max, sites=self.sites if x is not None else None, x=x)
 
     def synchronize(self):
         torch.cuda.synchronize()
@@ -411,11 +421,18 @@ class ShardedHotPath(object):
     def balance(self):
         eng, comm = self.engine, self.comm
         assert self.block is not None, 'a rank without rows is not supported by the KR driver'
-        self.normed = eng.site_norm(self.block)
-        self.trace.mark('site_norm')
-        if hasattr(eng, 'kr_run_peer') and not self.host_driven_kr:
+        peer = hasattr(eng, 'kr_run_peer') and not self.host_driven_kr
+        self.fused = peer and getattr(eng, 'fused', False)
+        if self.fused:
+            self.normed = None
+            st = eng.kr_run_peer(self.block, *self.kr_params, comm=comm)
+        elif peer:
+            self.normed = eng.site_norm(self.block)
+            self.trace.mark('site_norm')
             st = eng.kr_run_peer(self.normed, *self.kr_params, comm=comm)
         else:
+            self.normed = eng.site_norm(self.block)
+            self.trace.mark('site_norm')
             eng.kr_setup(self.normed, *self.kr_params)
             st = kr_block_loop(eng, comm)
         self.trace.mark('kr')
@@ -434,13 +451,20 @@ class ShardedHotPath(object):
             xs = comm.all_reduce(full, 'sum')
         self.x = xs
         self.trace.mark('x allreduce')
-        self.balanced = eng.kr_apply(self.normed, self.x)
-        self.trace.mark('kr_apply')
+        if self.fused:
+            self.balanced = None
+        else:
+            self.balanced = eng.kr_apply(self.normed, self.x)
+            self.trace.mark('kr_apply')
         return self.balanced
 
     def edges(self, scale=True):
         eng, comm = self.engine, self.comm
-        self.edge_res = eng.compress_edges(self.balanced, self.mask, lambda t: comm.all_reduce(t, 'max'), scale=scale)
+        reduce_max = lambda t: comm.all_reduce(t, 'max')                      # noqa: E731
+        if self.fused:
+            self.edge_res = eng.compress_edges(self.block, self.mask, reduce_max, scale=scale, x=self.x)
+        else:
+            self.edge_res = eng.compress_edges(self.balanced, self.mask, reduce_max, scale=scale)
         self.trace.mark('edges')
         return self.edge_res
 

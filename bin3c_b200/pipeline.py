@@ -131,9 +131,25 @@ class HotPath(object):
         self._mark('compress_edges')
         return self.edge_res
 
-    def run(self, records, to_host=False):
+    def balance_fused(self):
+        """KR on the raw counts, site-normalised while the SpMV operand is built (no `normed` matrix)."""
+        self.x, self.kr_info = dev.kr_scale_vector(self.seq_map, pool=self.pool, sites=self.sites, **self.kr_params)
+        self._mark('kr')
+        return self.x
+
+    def edges_fused(self, scale=True):
+        """Edge list straight from counts, sites and x (no normalised / balanced matrix in memory)."""
+        self.edge_res = dev.compress_edges(self.seq_map, self.mask, want_sub=False, want_edges=True, scale=scale,
+                                           pool=self.pool, sites=self.sites, x=self.x)
+        self._mark('compress_edges')
+        return self.edge_res
+
+    def run(self, records, to_host=False, fused=True):
         """
-        The whole path.  Returns the edge result dict (CUDA tensors, or NumPy arrays if to_host).
+        The whole path.  fused=True (default) never materialises the normalised and the balanced matrix:
+        their entries are recomputed where they are consumed, with the same operations in the same
+        order, so the edge list is bit-identical to the staged form (fused=False: site_norm -> KR ->
+        kr_apply -> compress, the stages ContactMap exposes).  Returns the edge result dict (CUDA tensors, or NumPy arrays if to_host).
         Both are views of the pipeline's reusable buffers (device buffers, or pinned host buffers
         with to_host): they are overwritten by the next run(), so copy what must outlive it.
         """
@@ -142,9 +158,13 @@ class HotPath(object):
             self.events = []
         self.accumulate(records)
         self.compute_mask()
-        self.normalise()
-        self.balance()
-        res = self.edges()
+        if fused:
+            self.balance_fused()
+            res = self.edges_fused()
+        else:
+            self.normalise()
+            self.balance()
+            res = self.edges()
         if to_host:
             # one asynchronous D2H per array into pinned, grow-only host buffers, then one sync
             n_edges = int(res['n_edges'])

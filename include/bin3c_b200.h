@@ -169,6 +169,15 @@ int b3c_kr_run(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d
                const double *d_data, double tol, double delta, double Delta, int32_t max_iter,
                int32_t mode, double *d_x, void *d_ws, int64_t ws_bytes, int64_t *h_info,
                void *stream);
+/* Counts form of b3c_kr_run: the matrix is given as the raw uint32 contact counts plus the int32 site
+ * count per contig, and every entry is normalised while the SpMV operand is built --
+ * a_ij = count_ij * (1.0 / (s_i * s_j)), bit for bit what b3c_site_norm writes
+ * (prepare_seq_map's astype(float) + _norm_seq, contact_map.py:929-933, 110-113) -- so the normalised
+ * matrix is never materialised.  Same result, same h_info as b3c_kr_run on b3c_site_norm's output. */
+int b3c_kr_run_counts(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices,
+                      const uint32_t *d_counts, const int32_t *d_sites, double tol, double delta,
+                      double Delta, int32_t max_iter, double *d_x, void *d_ws, int64_t ws_bytes,
+                      int64_t *h_info, void *stream);
 int b3c_kr_scale(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
                  const int32_t *d_indices, const double *d_data, const double *d_x, double *d_out,
                  void *stream);
@@ -243,6 +252,14 @@ int b3c_kr_run_peer(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local
                     int32_t n_ranks, void *const *h_exchange, double *d_x, void *d_ws,
                     int64_t ws_bytes, int64_t *h_info, void *stream);
 
+/* counts form of b3c_kr_run_peer (see b3c_kr_run_counts) */
+int b3c_kr_run_peer_counts(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local,
+                           const int64_t *d_indptr, const int32_t *d_indices,
+                           const uint32_t *d_counts, const int32_t *d_sites, double tol,
+                           double delta, double Delta, int32_t max_iter, int32_t rank,
+                           int32_t n_ranks, void *const *h_exchange, double *d_x, void *d_ws,
+                           int64_t ws_bytes, int64_t *h_info, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Compress + edge weighting.  compress (sparse_utils.py:284-314), get_subspace
  * (contact_map.py:966-982) and the edge loop of to_graph (cluster.py:314-321), on a row block
@@ -271,6 +288,22 @@ int b3c_compress_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t 
                       int64_t *d_sub_indptr, int32_t *d_sub_indices, double *d_sub_data,
                       int32_t *d_edge_u, int32_t *d_edge_v, double *d_edge_w, double *d_scl,
                       void *stream);
+
+/* Fused form for the graph hand-off (to_graph with norm=True, bisto=True, cluster.py:301-321): the
+ * edge list straight from the raw counts, the site counts and the KR scale vector.  The value of an
+ * entry is x_i * ((count_ij * (1.0 / (s_i * s_j))) * x_j) -- exactly what b3c_site_norm followed by
+ * b3c_kr_scale would have stored (contact_map.py:110-113, sparse_utils.py:223-224) -- so neither the
+ * normalised nor the balanced matrix is written to memory.  Arguments and outputs as
+ * b3c_compress_count / b3c_compress_fill (edge list only); b3c_edges_count leaves one packed record
+ * per contig (gapless id, site count, x) in d_ws, which b3c_edges_fill gathers from. */
+int b3c_edges_count(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_indptr,
+                    const int32_t *d_indices, const uint32_t *d_counts, const int32_t *d_sites,
+                    const double *d_x, const uint8_t *d_mask, int32_t *d_newidx, void *d_ws,
+                    int64_t ws_bytes, double *d_vmax, int64_t *h_out, void *stream);
+int b3c_edges_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_indptr,
+                   const int32_t *d_indices, const uint32_t *d_counts, void *d_ws,
+                   const double *d_vmax, int scale, int32_t *d_edge_u, int32_t *d_edge_v,
+                   double *d_edge_w, double *d_scl, void *stream);
 
 #ifdef __cplusplus
 }

@@ -525,3 +525,26 @@ def test_hotpath_host_records_match_device_records(dev):
     for k, w in zip(('u', 'v', 'w'), want):
         assert np.array_equal(out[k], w)
     assert out['scl'] == want[3]
+
+
+def test_fused_counts_form_is_bit_identical(dev):
+    """KR on raw counts (normalised on the fly) and the fused edge emission give exactly the staged
+    results: same x, same n_iter, same (u, v, w, scl) -- including zero site counts (Q6)."""
+    import torch
+    from bin3c_b200 import synth
+    from bin3c_b200.pipeline import HotPath
+    com = synth.make_community(n_genomes=10, n_contigs=4000, n_pairs=900_000, seed=123)
+    sites = com.sites.copy()
+    sites[::17] = 0
+    hp = HotPath(com.tid2idx(), com.lengths, sites, pair_capacity=com.n_pairs, min_sig=3)
+    rec = dev.to_device(com.records)
+    r_staged = hp.run(rec, fused=False)
+    n = int(r_staged['n_edges'])
+    staged = [r_staged[k][:n].cpu().numpy().copy() for k in ('u', 'v', 'w')] + [r_staged['scl'].cpu().numpy().copy()]
+    x_staged, it_staged = hp.x.cpu().numpy().copy(), hp.kr_info['n_iter']
+    r_fused = hp.run(rec, fused=True)
+    assert int(r_fused['n_edges']) == n and hp.kr_info['n_iter'] == it_staged
+    assert np.array_equal(hp.x.cpu().numpy(), x_staged)
+    for k, w in zip(('u', 'v', 'w'), staged):
+        assert np.array_equal(r_fused[k][:n].cpu().numpy(), w)
+    assert np.array_equal(r_fused['scl'].cpu().numpy(), staged[3])
