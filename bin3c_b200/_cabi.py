@@ -77,6 +77,14 @@ SIGNATURES = {
                                   C.POINTER(C.c_void_p), _p, _p, _i64, _pi64, _p]),
     'b3c_kr_run_peer_counts': (C.c_int, [_i32, _i32, _i32, _i64, _p, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _i32,
                                          C.POINTER(C.c_void_p), _p, _p, _i64, _pi64, _p]),
+    'b3c_xa_bytes': (_i64, [_i32, _i64]),
+    'b3c_xa_offsets': (C.c_int, [_i32, _i64, _pi64]),
+    'b3c_peer_barrier': (C.c_int, [C.POINTER(C.c_void_p), _i32, _i32, _i32, _i64, C.c_uint64, _p]),
+    'b3c_peer_put': (C.c_int, [C.POINTER(C.c_void_p), _i32, _i64, _p, _i64, _p]),
+    'b3c_peer_allreduce_f64': (C.c_int, [C.POINTER(C.c_void_p), _i32, _i32, _i32, _i64, C.c_uint64, _i32, _p, _i32, _p]),
+    'b3c_shard_publish': (C.c_int, [_p, C.POINTER(C.c_void_p), _i32, _i32, _p]),
+    'b3c_shard_scatter': (C.c_int, [_p, C.POINTER(C.c_void_p), _i32, _i32, _p, _p]),
+    'b3c_shard_reduce_block': (C.c_int, [_p, C.POINTER(C.c_void_p), _i32, _i32, _p, _pi64, _p]),
     'b3c_compress_workspace_bytes': (_i64, [_i32]),
     'b3c_compress_count': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p, _pi64, _p]),
     'b3c_compress_fill': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p,

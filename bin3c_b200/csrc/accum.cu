@@ -776,6 +776,298 @@ __global__ void __launch_bounds__(256) k_emit_block(int b, int32_t row_lo, int32
     }
 }
 
+
+// ---- peer exchange arena (multi-GPU, one process per GPU of a node) ------------------------------------
+// Every rank owns one arena, allocated with b3c_peer_alloc and mapped by all other ranks over NVLink
+// (CUDA IPC).  Ranks write into each other's arenas directly from kernels -- routed keys, mask and x
+// slices, small reduction operands -- and synchronise with flag barriers kept in the same arenas, so
+// the data path of the sharded accumulation has no collective-library call and no host round trip.
+constexpr int XA_MAX_RANKS = 8;
+constexpr int XA_SCAL = 8;                       // doubles per small all-reduce
+constexpr int XA_CHUNK = 1024;                   // rows per weight chunk = KR's reduction chunk (row-block alignment)
+constexpr int XA_MAX_CHUNKS = 4096;              // weight chunks the split kernel keeps in shared memory
+
+struct XaLayout {
+    int64_t o_flag, o_ctl, o_scal, o_cw, o_cnt3, o_diag, o_mask, o_x, o_keys, total;
+    int32_t n_chunks;
+};
+static XaLayout xa_layout(int32_t n_seq, int64_t key_cap) {
+    XaLayout X;
+    Carver c;
+    X.n_chunks = (int32_t)ceil_div(n_seq, XA_CHUNK);
+    X.o_flag = c.take(XA_MAX_RANKS * 8);
+    X.o_ctl = c.take(4 * 8);                                     // [0] keys received, [1] overflow, [2] time-out
+    X.o_scal = c.take(2 * XA_MAX_RANKS * XA_SCAL * 8);           // two sets, alternated by barrier epoch
+    X.o_cw = c.take((int64_t)XA_MAX_RANKS * X.n_chunks * 8);
+    X.o_cnt3 = c.take(XA_MAX_RANKS * 4 * 8);
+    X.o_diag = c.take((int64_t)n_seq * 4);
+    X.o_mask = c.take((int64_t)n_seq);
+    X.o_x = c.take((int64_t)n_seq * 8);
+    X.o_keys = c.take((key_cap > 0 ? key_cap : 1) * 8);
+    X.total = c.cur;
+    return X;
+}
+
+struct Peers {
+    char *a[XA_MAX_RANKS];
+};
+
+// Flag barrier between the ranks' streams: everything this rank enqueued before it is complete (stream
+// order), thread g tells rank g "rank `rank` reached `epoch`" and waits until rank g has told us the same.
+// A rank that never arrives would hang the node, so the wait gives up after ~4 s and raises the arena's
+// time-out word (reported by the next call that synchronises).
+__global__ void k_peer_barrier(Peers P, int rank, int G, unsigned long long epoch, int64_t o_flag, int64_t o_ctl) {
+    const int g = threadIdx.x;
+    if (g >= G) return;
+    __threadfence_system();
+    unsigned long long *theirs = (unsigned long long *)(P.a[g] + o_flag) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long *mine = (const unsigned long long *)(P.a[rank] + o_flag) + g;
+    const long long t0 = clock64();
+    unsigned long long seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        if (seen < epoch && clock64() - t0 > 8000000000LL) {
+            ((unsigned long long *)(P.a[rank] + o_ctl))[2] = 1ull;
+            break;
+        }
+    } while (seen < epoch);
+}
+
+// copy `bytes` (a multiple of 1; 16-byte aligned fast path) from src into every rank's arena at `offset`
+__global__ void k_peer_put(Peers P, int G, int64_t offset, const unsigned char *__restrict__ src, int64_t bytes) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((offset | (int64_t)(uintptr_t)src) & 15) == 0;
+    const int64_t nv = vec ? bytes / 16 : 0;
+    for (int g = 0; g < G; ++g) {
+        unsigned char *dst = (unsigned char *)(P.a[g] + offset);
+        for (int64_t i = gid; i < nv; i += stride) ((uint4 *)dst)[i] = ((const uint4 *)src)[i];
+        for (int64_t i = nv * 16 + gid; i < bytes; i += stride) dst[i] = src[i];
+    }
+}
+
+// all-reduce of up to XA_SCAL doubles: put this rank's values into slot `rank` of every arena, flag barrier,
+// reduce the G slots in rank order (the same order on every rank: bit-identical results).  One CTA.
+__global__ void k_peer_allreduce(Peers P, int rank, int G, unsigned long long epoch, int op, double *__restrict__ val,
+                                 int count, int64_t o_flag, int64_t o_ctl, int64_t o_scal) {
+    const int64_t set = o_scal + (int64_t)(epoch & 1ull) * XA_MAX_RANKS * XA_SCAL * 8;
+    const int t = threadIdx.x;
+    if (t < G * count) {
+        const int g = t / count, i = t % count;
+        ((double *)(P.a[g] + set))[rank * XA_SCAL + i] = val[i];
+    }
+    __syncthreads();
+    if (t < G) {
+        __threadfence_system();
+        unsigned long long *theirs = (unsigned long long *)(P.a[t] + o_flag) + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+        const unsigned long long *mine = (const unsigned long long *)(P.a[rank] + o_flag) + t;
+        const long long t0 = clock64();
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+            if (seen < epoch && clock64() - t0 > 8000000000LL) {
+                ((unsigned long long *)(P.a[rank] + o_ctl))[2] = 1ull;
+                break;
+            }
+        } while (seen < epoch);
+    }
+    __syncthreads();
+    if (t < count) {
+        const volatile double *slots = (const volatile double *)(P.a[rank] + set);
+        double r = slots[t];
+        for (int g = 1; g < G; ++g) {
+            const double v = slots[g * XA_SCAL + t];
+            r = op == 0 ? r + v : fmax(r, v);
+        }
+        val[t] = r;
+    }
+}
+
+// cw[c] += directed keys whose row lies in 1024-row chunk c (both directions of every canonical key)
+__global__ void __launch_bounds__(256) k_chunk_weights(const uint64_t *__restrict__ keys,
+                                                       const unsigned long long *__restrict__ d_n, int b, int n_chunks,
+                                                       unsigned long long *__restrict__ cw) {
+    extern __shared__ unsigned s_cw[];
+    const bool sm = n_chunks <= XA_MAX_CHUNKS;
+    if (sm) {
+        for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) s_cw[i] = 0;
+        __syncthreads();
+    }
+    const int64_t n = (int64_t)*d_n;
+    const uint64_t jmask = (1ull << b) - 1ull;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[e];
+        const int ci = (int)((k >> b) / XA_CHUNK), cj = (int)((k & jmask) / XA_CHUNK);
+        if (sm) {
+            atomicAdd(&s_cw[ci], 1u);
+            atomicAdd(&s_cw[cj], 1u);
+        } else {
+            atomicAdd(&cw[ci], 1ull);
+            atomicAdd(&cw[cj], 1ull);
+        }
+    }
+    if (sm) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_chunks; i += blockDim.x)
+            if (s_cw[i]) atomicAdd(&cw[i], (unsigned long long)s_cw[i]);
+    }
+}
+
+// this rank's pair counters into slot `rank` of every arena
+__global__ void k_publish_counters(Peers P, int rank, int G, const unsigned long long *__restrict__ ctr, int64_t o_cnt3) {
+    const int t = threadIdx.x;
+    if (t < G * 3) {
+        const int g = t / 3, i = t % 3;
+        ((unsigned long long *)(P.a[g] + o_cnt3))[rank * 4 + i] = ctr[C_ACCEPT + i];
+    }
+}
+
+// Row splits from the summed chunk weights: G contiguous row ranges of about equal weight (directed keys
+// + one diagonal entry per row), cut at chunk boundaries; splits[G] = n_seq.  Every rank computes the same
+// table from the same numbers.  One CTA.
+__global__ void __launch_bounds__(1024) k_shard_splits(Peers P, int rank, int G, int32_t n_seq, int n_chunks,
+                                                       int64_t o_cw, int32_t *__restrict__ splits) {
+    __shared__ long long s_cum[XA_MAX_CHUNKS];
+    const unsigned long long *cw = (const unsigned long long *)(P.a[rank] + o_cw);
+    for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+        long long w = 0;
+        for (int g = 0; g < G; ++g) w += (long long)cw[(int64_t)g * n_chunks + c];
+        const int64_t rows = (int64_t)n_seq - (int64_t)c * XA_CHUNK;
+        s_cum[c] = w + (rows < XA_CHUNK ? rows : XA_CHUNK);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            run += s_cum[c];
+            s_cum[c] = run;                                  // inclusive
+        }
+        const long long total = run;
+        const int full = n_seq / XA_CHUNK;                   // cuts lie on whole-chunk boundaries below n_seq
+        int prev = 0, c = 0;
+        splits[0] = 0;
+        for (int k = 1; k < G; ++k) {
+            const long long target = total * k / G;
+            while (c < n_chunks && s_cum[c] < target) ++c;   // first chunk whose inclusive sum reaches the target
+            int bnd = c;                                     // boundary before chunk c ...
+            if (c < n_chunks) {
+                const long long before = c > 0 ? s_cum[c - 1] : 0;
+                if (s_cum[c] - target <= target - before) bnd = c + 1;      // ... or after it, whichever is nearer
+            }
+            if (bnd > full) bnd = full;
+            if (bnd < prev) bnd = prev;
+            prev = bnd;
+            splits[k] = bnd * XA_CHUNK;
+        }
+        splits[G] = n_seq;
+    }
+}
+
+// Route + scatter over NVLink: every canonical key (i<j) becomes the directed keys (i,j) and (j,i); each goes
+// straight into the receive buffer of the rank that owns its row.  Per tile the keys are grouped by owner in
+// shared memory, one system-scope atomic per owner reserves the range in that rank's buffer, and the tile is
+// written out in owner-contiguous, coalesced runs.
+constexpr int RT_THREADS = 256;
+constexpr int RT_KPT = 8;
+constexpr int RT_TILE = RT_THREADS * RT_KPT;
+__global__ void __launch_bounds__(RT_THREADS) k_route_peer(const uint64_t *__restrict__ keys,
+                                                           const unsigned long long *__restrict__ d_n, int b,
+                                                           const int32_t *__restrict__ splits, Peers P, int G,
+                                                           int64_t o_ctl, int64_t o_keys, int64_t cap) {
+    __shared__ int32_t s_splits[XA_MAX_RANKS + 1];
+    __shared__ unsigned s_cnt[XA_MAX_RANKS], s_off[XA_MAX_RANKS + 1];
+    __shared__ unsigned long long s_base[XA_MAX_RANKS];
+    __shared__ uint64_t s_stage[2 * RT_TILE];
+    if (threadIdx.x <= (unsigned)G) s_splits[threadIdx.x] = splits[threadIdx.x];
+    __syncthreads();
+    const int64_t n = (int64_t)*d_n;
+    const uint64_t jmask = (1ull << b) - 1ull;
+    for (int64_t base = (int64_t)blockIdx.x * RT_TILE; base < n; base += (int64_t)gridDim.x * RT_TILE) {
+        if (threadIdx.x < (unsigned)G) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint64_t dk[2 * RT_KPT];
+        int own[2 * RT_KPT];
+        unsigned slot[2 * RT_KPT];
+#pragma unroll
+        for (int q = 0; q < RT_KPT; ++q) {
+            const int64_t e = base + q * RT_THREADS + threadIdx.x;
+            if (e < n) {
+                const uint64_t k = keys[e];
+                const uint64_t i = k >> b, j = k & jmask;
+                dk[2 * q] = k;
+                dk[2 * q + 1] = (j << b) | i;
+                own[2 * q] = owner_of((int32_t)i, s_splits, G);
+                own[2 * q + 1] = owner_of((int32_t)j, s_splits, G);
+                slot[2 * q] = atomicAdd(&s_cnt[own[2 * q]], 1u);
+                slot[2 * q + 1] = atomicAdd(&s_cnt[own[2 * q + 1]], 1u);
+            } else {
+                own[2 * q] = own[2 * q + 1] = -1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned run = 0;
+            for (int g = 0; g < G; ++g) {
+                s_off[g] = run;
+                run += s_cnt[g];
+            }
+            s_off[G] = run;
+        }
+        if (threadIdx.x < (unsigned)G && s_cnt[threadIdx.x]) {
+            unsigned long long *ctl = (unsigned long long *)(P.a[threadIdx.x] + o_ctl);
+            const unsigned long long at = atomicAdd_system(&ctl[0], (unsigned long long)s_cnt[threadIdx.x]);
+            if ((int64_t)(at + s_cnt[threadIdx.x]) > cap) {
+                ctl[1] = 1ull;                               // receive buffer overflow: drop, the owner reports it
+                s_base[threadIdx.x] = ~0ull;
+            } else {
+                s_base[threadIdx.x] = at;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2 * RT_KPT; ++q)
+            if (own[q] >= 0) s_stage[s_off[own[q]] + slot[q]] = dk[q];
+        __syncthreads();
+        const unsigned total = s_off[G];
+        for (unsigned i = threadIdx.x; i < total; i += RT_THREADS) {
+            int g = 0;
+            while (i >= s_off[g + 1]) ++g;
+            const unsigned long long at = s_base[g];
+            if (at != ~0ull) ((uint64_t *)(P.a[g] + o_keys))[at + (i - s_off[g])] = s_stage[i];
+        }
+        __syncthreads();
+    }
+}
+
+// diag[r] = sum over ranks of their diagonal histograms, for this rank's rows (peer reads)
+__global__ void k_diag_gather(Peers P, int G, int32_t row_lo, int32_t row_hi, int64_t o_diag, uint32_t *__restrict__ diag) {
+    for (int64_t r = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < row_hi; r += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t s = 0;
+        for (int g = 0; g < G; ++g) s += ((const uint32_t *)(P.a[g] + o_diag))[r];
+        diag[r] = s;
+    }
+}
+
+// received-key count -> the sort's counter; summed pair counters; flags
+__global__ void k_shard_collect(Peers P, int rank, int G, int64_t o_ctl, int64_t o_cnt3, int64_t cap,
+                                unsigned long long *__restrict__ ctr, unsigned long long *__restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long *ctl = (const unsigned long long *)(P.a[rank] + o_ctl);
+    const unsigned long long *c3 = (const unsigned long long *)(P.a[rank] + o_cnt3);
+    const bool bad = ctl[1] != 0 || (int64_t)ctl[0] > cap;
+    ctr[C_NKEYS] = bad ? 0ull : ctl[0];
+    ctr[C_NNZ_UO] = ctr[C_NNZ_DIAG] = ctr[C_WEIGHT] = 0ull;
+    out[0] = ctl[0];
+    out[1] = bad ? 1ull : 0ull;
+    out[2] = ctl[2];
+    for (int i = 0; i < 3; ++i) {
+        unsigned long long s = 0;
+        for (int g = 0; g < G; ++g) s += c3[g * 4 + i];
+        out[3 + i] = s;
+    }
+}
+
 template <bool A, bool B>
 static int launch_classify(const AccumState &st, const ClsParams &P, cudaStream_t s) {
     static bool attr_done = false;
@@ -1149,6 +1441,219 @@ int b3c_accum_emit_block(void *d_ws, int32_t row_lo, int32_t row_hi, int64_t *d_
                                                   (const uint32_t *)(ws + st.o_cnt), (const uint32_t *)(ws + st.o_diag),
                                                   (const int64_t *)(ws + st.o_up_ptr), ip, d_indices, d_counts);
     B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+// ---- peer exchange arena entry points -----------------------------------------------------------------
+
+static int peers_of(void *const *h_arena, int32_t rank, int32_t n_ranks, Peers *P) {
+    B3C_REQUIRE(h_arena != nullptr && n_ranks >= 1 && n_ranks <= XA_MAX_RANKS && rank >= 0 && rank < n_ranks,
+                "bad rank %d of %d (at most %d)", rank, n_ranks, XA_MAX_RANKS);
+    for (int g = 0; g < XA_MAX_RANKS; ++g) P->a[g] = nullptr;
+    for (int g = 0; g < n_ranks; ++g) {
+        B3C_REQUIRE(h_arena[g] != nullptr, "null arena of rank %d", g);
+        P->a[g] = (char *)h_arena[g];
+    }
+    return B3C_OK;
+}
+
+int64_t b3c_xa_bytes(int32_t n_seq, int64_t key_capacity) {
+    if (n_seq <= 0 || key_capacity < 0) return B3C_ERR_ARG;
+    return xa_layout(n_seq, key_capacity).total;
+}
+
+int b3c_xa_offsets(int32_t n_seq, int64_t key_capacity, int64_t *h_offsets) {
+    B3C_REQUIRE(n_seq > 0 && key_capacity >= 0 && h_offsets, "bad arguments");
+    const XaLayout X = xa_layout(n_seq, key_capacity);
+    h_offsets[0] = X.o_mask;
+    h_offsets[1] = X.o_x;
+    h_offsets[2] = X.o_keys;
+    h_offsets[3] = X.o_diag;
+    return B3C_OK;
+}
+
+int b3c_peer_barrier(void *const *h_arena, int32_t rank, int32_t n_ranks, int32_t n_seq, int64_t key_capacity,
+                     uint64_t epoch, void *stream) {
+    Peers P;
+    int rc = peers_of(h_arena, rank, n_ranks, &P);
+    if (rc) return rc;
+    const XaLayout X = xa_layout(n_seq, key_capacity);
+    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(P, rank, n_ranks, epoch, X.o_flag, X.o_ctl);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_peer_put(void *const *h_arena, int32_t n_ranks, int64_t offset, const void *d_src, int64_t bytes, void *stream) {
+    Peers P;
+    int rc = peers_of(h_arena, 0, n_ranks, &P);
+    if (rc) return rc;
+    B3C_REQUIRE(offset >= 0 && bytes >= 0 && (bytes == 0 || d_src), "bad arguments");
+    if (bytes == 0) return B3C_OK;
+    int64_t blocks = ceil_div(bytes, 16 * 256);
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    k_peer_put<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, n_ranks, offset, (const unsigned char *)d_src, bytes);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_peer_allreduce_f64(void *const *h_arena, int32_t rank, int32_t n_ranks, int32_t n_seq, int64_t key_capacity,
+                           uint64_t epoch, int32_t op, double *d_val, int32_t count, void *stream) {
+    Peers P;
+    int rc = peers_of(h_arena, rank, n_ranks, &P);
+    if (rc) return rc;
+    B3C_REQUIRE(d_val && count >= 1 && count <= XA_SCAL && (op == 0 || op == 1), "bad arguments");
+    const XaLayout X = xa_layout(n_seq, key_capacity);
+    k_peer_allreduce<<<1, 64, 0, (cudaStream_t)stream>>>(P, rank, n_ranks, epoch, op, d_val, count, X.o_flag, X.o_ctl,
+                                                         X.o_scal);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_shard_publish(void *d_ws, void *const *h_arena, int32_t rank, int32_t n_ranks, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    Peers P;
+    rc = peers_of(h_arena, rank, n_ranks, &P);
+    if (rc) return rc;
+    const XaLayout X = xa_layout(st.n_seq, st.cap);
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    unsigned long long *ctr = (unsigned long long *)(ws + st.o_ctr);
+    char *mine = P.a[rank];
+    k_accum_guard<<<1, 1, 0, s>>>(ctr, st.cap);
+    B3C_LAUNCH_CHECK();
+    // receive cursor + overflow word of this rank (nobody scatters to it before the next barrier)
+    B3C_CUDA(cudaMemsetAsync(mine + X.o_ctl, 0, 16, s));
+    // chunk weights of the local keys, accumulated in this rank's own slot, then copied to every other arena
+    unsigned long long *cw = (unsigned long long *)(mine + X.o_cw) + (int64_t)rank * X.n_chunks;
+    B3C_CUDA(cudaMemsetAsync(cw, 0, (size_t)X.n_chunks * 8, s));
+    const int smem = X.n_chunks <= XA_MAX_CHUNKS ? X.n_chunks * 4 : 0;
+    static bool attr_done = false;
+    if (!attr_done) {
+        B3C_CUDA(cudaFuncSetAttribute(k_chunk_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_MAX_CHUNKS * 4));
+        attr_done = true;
+    }
+    k_chunk_weights<<<kNumSMs * 4, 256, smem, s>>>((const uint64_t *)(ws + st.o_keys_a), ctr + C_NKEYS, st.b, X.n_chunks, cw);
+    B3C_LAUNCH_CHECK();
+    if (n_ranks > 1) {
+        Peers others = P;
+        k_peer_put<<<8, 256, 0, s>>>(others, n_ranks, X.o_cw + (int64_t)rank * X.n_chunks * 8, (const unsigned char *)cw,
+                                     (int64_t)X.n_chunks * 8);
+        B3C_LAUNCH_CHECK();
+    }
+    k_publish_counters<<<1, 32, 0, s>>>(P, rank, n_ranks, ctr, X.o_cnt3);
+    B3C_LAUNCH_CHECK();
+    // the local diagonal histogram, where the owners of the rows can read it
+    B3C_CUDA(cudaMemcpyAsync(mine + X.o_diag, ws + st.o_diag, (size_t)st.n_seq * 4, cudaMemcpyDeviceToDevice, s));
+    return B3C_OK;
+}
+
+int b3c_shard_scatter(void *d_ws, void *const *h_arena, int32_t rank, int32_t n_ranks, int32_t *d_splits, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    Peers P;
+    rc = peers_of(h_arena, rank, n_ranks, &P);
+    if (rc) return rc;
+    B3C_REQUIRE(d_splits != nullptr, "null splits");
+    const XaLayout X = xa_layout(st.n_seq, st.cap);
+    if (X.n_chunks > XA_MAX_CHUNKS) {
+        set_error("sharded accumulation supports at most %d row chunks (%d contigs)", XA_MAX_CHUNKS, XA_MAX_CHUNKS * XA_CHUNK);
+        return B3C_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    unsigned long long *ctr = (unsigned long long *)(ws + st.o_ctr);
+    k_shard_splits<<<1, 1024, 0, s>>>(P, rank, n_ranks, st.n_seq, X.n_chunks, X.o_cw, d_splits);
+    B3C_LAUNCH_CHECK();
+    k_route_peer<<<kNumSMs * 4, RT_THREADS, 0, s>>>((const uint64_t *)(ws + st.o_keys_a), ctr + C_NKEYS, st.b, d_splits, P,
+                                                    n_ranks, X.o_ctl, X.o_keys, st.cap);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_shard_reduce_block(void *d_ws, void *const *h_arena, int32_t rank, int32_t n_ranks, const int32_t *d_splits,
+                           int64_t *h_sizes, void *stream) {
+    AccumState st;
+    int rc = get_state(d_ws, &st);
+    if (rc) return rc;
+    Peers P;
+    rc = peers_of(h_arena, rank, n_ranks, &P);
+    if (rc) return rc;
+    B3C_REQUIRE(d_splits && h_sizes, "null pointer");
+    const XaLayout X = xa_layout(st.n_seq, st.cap);
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    unsigned long long *ctr = (unsigned long long *)(ws + st.o_ctr);
+    uint64_t *ka = (uint64_t *)(P.a[rank] + X.o_keys), *kb = (uint64_t *)(ws + st.o_keys_b);
+    uint64_t *uniq = (uint64_t *)(ws + st.o_uniq);
+    uint32_t *pos = (uint32_t *)(ws + st.o_pos), *cnt = (uint32_t *)(ws + st.o_cnt);
+    uint32_t *hist = (uint32_t *)(ws + st.o_hist);
+    int64_t *heads = (int64_t *)(ws + st.o_heads), *heads_ex = heads + RS_BLOCKS + 2;
+    int64_t *scan_tmp = (int64_t *)(ws + st.o_scan_tmp);
+    uint32_t *diag = (uint32_t *)(ws + st.o_diag);
+    int64_t *ptr = (int64_t *)(ws + st.o_up_ptr), *len = (int64_t *)(ws + st.o_len);
+    int64_t *ip = (int64_t *)(ws + st.o_indptr_f);
+    unsigned long long *d_out = (unsigned long long *)(ws + st.o_tmp64);      // [6] scratch (the rank table is final)
+
+    // the splits decide the row block: they are needed on the host to size the launches below
+    int32_t h_splits[XA_MAX_RANKS + 1];
+    B3C_CUDA(cudaMemcpyAsync(h_splits, d_splits, (size_t)(n_ranks + 1) * 4, cudaMemcpyDeviceToHost, s));
+    k_shard_collect<<<1, 32, 0, s>>>(P, rank, n_ranks, X.o_ctl, X.o_cnt3, st.cap, ctr, d_out);
+    B3C_LAUNCH_CHECK();
+    int where = 0;
+    rc = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
+    if (rc) return rc;
+    uint64_t *sorted = where ? kb : ka;
+    k_rle_count<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(heads, heads_ex, RS_BLOCKS, scan_tmp, s);
+    if (rc) return rc;
+    k_rle_write<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads_ex, uniq, pos);
+    B3C_LAUNCH_CHECK();
+    k_rle_finish<<<1, 1, 0, s>>>(heads_ex, RS_BLOCKS, ctr + C_NKEYS, pos, ctr);
+    B3C_LAUNCH_CHECK();
+    k_rle_counts<<<kNumSMs * 8, 256, 0, s>>>(pos, ctr, cnt, st.b, uniq, sorted);
+    B3C_LAUNCH_CHECK();
+    k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(uniq, ctr + C_NNZ_UO, st.b, st.n_seq, ptr);
+    B3C_LAUNCH_CHECK();
+    B3C_CUDA(cudaStreamSynchronize(s));                       // h_splits
+    const int32_t row_lo = h_splits[rank], row_hi = h_splits[rank + 1];
+    const int32_t n_local = row_hi - row_lo;
+    int64_t nnz_local = 0;
+    unsigned long long h_out[6] = {0, 0, 0, 0, 0, 0};
+    if (n_local > 0) {
+        k_diag_gather<<<(unsigned)ceil_div(n_local, 256), 256, 0, s>>>(P, n_ranks, row_lo, row_hi, X.o_diag, diag);
+        B3C_LAUNCH_CHECK();
+        k_block_row_len<<<(unsigned)ceil_div(n_local, 256), 256, 0, s>>>(ptr, diag, row_lo, n_local, len);
+        B3C_LAUNCH_CHECK();
+        rc = scan_exclusive_i64(len, ip, n_local, scan_tmp, s);
+        if (rc) return rc;
+        B3C_CUDA(cudaMemcpyAsync(&nnz_local, ip + n_local, 8, cudaMemcpyDeviceToHost, s));
+    }
+    B3C_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaStreamSynchronize(s));
+    if (h_out[2]) {
+        set_error("sharded accumulation: a rank did not reach a barrier within the time-out");
+        return B3C_ERR_CUDA;
+    }
+    if (h_out[1]) {
+        set_error("received %llu directed keys, accumulator capacity is %lld", h_out[0], (long long)st.cap);
+        return B3C_ERR_CAPACITY;
+    }
+    st.reduced = true;
+    st.nnz_uo = nnz_local;
+    h_sizes[0] = nnz_local;
+    h_sizes[1] = row_lo;
+    h_sizes[2] = row_hi;
+    h_sizes[3] = (int64_t)h_out[3];
+    h_sizes[4] = (int64_t)h_out[4];
+    h_sizes[5] = (int64_t)h_out[5];
+    h_sizes[6] = (int64_t)h_out[0];
+    for (int g = 0; g <= n_ranks; ++g) h_sizes[8 + g] = h_splits[g];
+    std::lock_guard<std::mutex> g(g_mu);
+    g_states[d_ws] = st;
     return B3C_OK;
 }
 

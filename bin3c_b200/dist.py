@@ -110,6 +110,19 @@ class Comm(object):
 # the product engine: everything a rank computes, through the C ABI
 # ------------------------------------------------------------------------------------------------
 
+class _CAI(object):
+    """Raw device memory as a __cuda_array_interface__ object (for torch.as_tensor)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def _device_view(ptr, n, dtype):
+    """A torch tensor over n elements of device memory this process did not allocate through torch."""
+    typestr = {torch.uint8: '|u1', torch.float64: '<f8', torch.int64: '<i8', torch.int32: '<i4'}[dtype]
+    return torch.as_tensor(_CAI(ptr, n, typestr), device='cuda')
+
+
 class CudaEngine(object):
 
     def __init__(self, tid2idx, lengths, sites, pair_capacity):
@@ -128,6 +141,105 @@ class CudaEngine(object):
         self.pool = dev.BufferPool()
         self.scratch = torch.zeros(256, dtype=torch.int64, device='cuda')
         self.kr_ws = None
+
+    # ---- peer exchange arena (NVLink-mapped; see include/bin3c_b200.h, "Peer exchange arena") --------
+    def open_arena(self, comm):
+        """Allocate this rank's arena, map everybody else's (once); views of the mask and x regions."""
+        if getattr(self, '_arena', None) is not None:
+            return self._arena
+        lib, dev = self.lib, self.dev
+        assert comm.world <= 8, 'the peer arena spans the GPUs of one node (at most 8 ranks)'
+        self._xa_cap = int(self.acc.capacity)
+        nbytes = lib.b3c_xa_bytes(self.n, self._xa_cap)
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self.check(lib.b3c_peer_alloc(nbytes, C.byref(own), handle))
+        handles = comm.all_gather_object(handle.raw)
+        ptrs = (C.c_void_p * comm.world)()
+        self._a_opened = []
+        for g, h in enumerate(handles):
+            if g == comm.rank:
+                ptrs[g] = own.value
+            else:
+                q = C.c_void_p()
+                self.check(lib.b3c_peer_open(h, C.byref(q)))
+                ptrs[g] = q.value
+                self._a_opened.append(q.value)
+        offs = (C.c_int64 * 4)()
+        self.check(lib.b3c_xa_offsets(self.n, self._xa_cap, offs))
+        self._a_off = dict(mask=int(offs[0]), x=int(offs[1]))
+        self._a_own = own.value
+        self._arena = ptrs
+        self._epoch = 0
+        self.mask_view = _device_view(own.value + self._a_off['mask'], self.n, torch.uint8)
+        self.x_view = _device_view(own.value + self._a_off['x'], self.n, torch.float64)
+        self._scal = torch.zeros(8, dtype=torch.float64, device='cuda')
+        self._splits_dev = torch.zeros(16, dtype=torch.int32, device='cuda')
+        comm.barrier()
+        return ptrs
+
+    def close_arena(self):
+        if getattr(self, '_arena', None) is None:
+            return
+        torch.cuda.synchronize()
+        self.mask_view = self.x_view = None
+        for q in self._a_opened:
+            self.lib.b3c_peer_close(C.c_void_p(q))
+        self.lib.b3c_peer_free(C.c_void_p(self._a_own))
+        self._arena = None
+
+    def peer_barrier(self, comm):
+        self._epoch += 1
+        self.check(self.lib.b3c_peer_barrier(self._arena, comm.rank, comm.world, self.n, self._xa_cap, self._epoch,
+                                             self.dev._stream()))
+
+    def peer_put(self, comm, region, elem_offset, src):
+        """src (CUDA tensor) -> every rank's arena, `elem_offset` elements into the named region."""
+        off = self._a_off[region] + int(elem_offset) * src.element_size()
+        self.check(self.lib.b3c_peer_put(self._arena, comm.world, off, self.dev._ptr(src),
+                                         src.numel() * src.element_size(), self.dev._stream()))
+
+    def peer_allreduce(self, comm, t, op='sum'):
+        """In-place all-reduce of a small float64 CUDA tensor (<= 8 values) through the arenas."""
+        assert t.dtype == torch.float64 and t.numel() <= 8 and t.is_contiguous()
+        self._epoch += 1
+        self.check(self.lib.b3c_peer_allreduce_f64(self._arena, comm.rank, comm.world, self.n, self._xa_cap, self._epoch,
+                                                   0 if op == 'sum' else 1, self.dev._ptr(t), t.numel(),
+                                                   self.dev._stream()))
+        return t
+
+    def accumulate_peer(self, records, comm):
+        """
+        The sharded accumulation with every exchange done by kernels over the peer arenas: classify ->
+        publish chunk weights | barrier | splits + route/scatter into the owners' buffers | barrier |
+        sort + reduce the received keys -> this rank's row block.  One host synchronisation (the sizes).
+        Returns (block DeviceCSR or None, info dict).
+        """
+        dev, lib = self.dev, self.lib
+        ptrs = self.open_arena(comm)
+        self.acc.begin()
+        self.acc.add(records)
+        ws = dev._ptr(self.acc.ws)
+        self.check(lib.b3c_shard_publish(ws, ptrs, comm.rank, comm.world, dev._stream()))
+        self.peer_barrier(comm)
+        self.check(lib.b3c_shard_scatter(ws, ptrs, comm.rank, comm.world, dev._ptr(self._splits_dev), dev._stream()))
+        self.peer_barrier(comm)
+        sizes = (C.c_int64 * 24)()
+        self.check(lib.b3c_shard_reduce_block(ws, ptrs, comm.rank, comm.world, dev._ptr(self._splits_dev), sizes,
+                                              dev._stream()))
+        nnz, row_lo, row_hi = int(sizes[0]), int(sizes[1]), int(sizes[2])
+        info = dict(accepted=int(sizes[3]), ref_excluded=int(sizes[4]), poor_match=int(sizes[5]),
+                    keys_received=int(sizes[6]), splits=[int(sizes[8 + g]) for g in range(comm.world + 1)])
+        block = None
+        if row_hi > row_lo:
+            nl = row_hi - row_lo
+            indptr = self.pool.get('blk_indptr', nl + 1, torch.int64)
+            indices = self.pool.get('blk_indices', nnz, torch.int32)
+            counts = self.pool.get('blk_counts', nnz, torch.int32)
+            self.check(lib.b3c_accum_emit_block(ws, row_lo, row_hi, dev._ptr(indptr), dev._ptr(indices),
+                                                dev._ptr(counts), dev._stream()))
+            block = dev.DeviceCSR(nl, indptr, indices, counts, counts=True, row_lo=row_lo, n_total=self.n)
+        return block, info
 
     # ---- accumulation ------------------------------------------------------------------------
     def classify(self, records):
@@ -242,6 +354,7 @@ class CudaEngine(object):
         return ptrs
 
     def close_peers(self):
+        self.close_arena()
         if getattr(self, '_xbuf', None) is None:
             return
         torch.cuda.synchronize()
@@ -364,7 +477,7 @@ class ShardedHotPath(object):
     """The whole path over `comm.world` ranks.  Each rank passes its own chunk of pair records."""
 
     def __init__(self, tid2idx, lengths, sites, pair_capacity, min_len=1000, min_sig=5, tol=1e-6, delta=0.1,
-                 Delta=3, max_iter=1000, comm=None, engine=None, host_driven_kr=False):
+                 Delta=3, max_iter=1000, comm=None, engine=None, host_driven_kr=False, peer_exchange=None):
         self.comm = comm or Comm()
         self.host_driven_kr = host_driven_kr          # True: kr_block_loop (collectives between phases)
         self.trace = _Trace()
@@ -374,11 +487,22 @@ class ShardedHotPath(object):
         # every rank may receive up to both directions of every key: size the buffers for the
         # directed keys of a balanced split with head-room
         self.engine = engine or CudaEngine(tid2idx, lengths, sites, pair_capacity)
+        # peer exchange: keys, mask / x slices and the small reductions move through NVLink-mapped arenas
+        # written by our own kernels; otherwise (CPU engines, host-driven form) through torch.distributed
+        self.peer = (hasattr(self.engine, 'accumulate_peer') and not host_driven_kr) if peer_exchange is None \
+            else bool(peer_exchange)
         self.info = {}
 
     def accumulate(self, records):
         eng, comm = self.engine, self.comm
         tr = self.trace
+        if self.peer:
+            self.block, info = eng.accumulate_peer(records, comm)
+            self.splits = np.asarray(info['splits'], dtype=np.int32)
+            self.row_lo, self.row_hi = int(self.splits[comm.rank]), int(self.splits[comm.rank + 1])
+            self.info.update(info)
+            tr.mark('accumulate(peer)')
+            return self.block
         eng.classify(records)
         tr.mark('classify')
         rowcnt = comm.all_reduce(eng.row_hist(), 'sum')
@@ -411,6 +535,13 @@ class ShardedHotPath(object):
 
     def compute_mask(self):
         eng, comm = self.engine, self.comm
+        if self.peer:
+            if self.block is not None:
+                eng.peer_put(comm, 'mask', self.row_lo, eng.block_mask(self.block, self.min_len, self.min_sig))
+            eng.peer_barrier(comm)
+            self.mask = eng.mask_view
+            self.trace.mark('mask')
+            return self.mask
         mask = eng.new_mask()
         if self.block is not None:
             mask[self.row_lo:self.row_hi].copy_(eng.block_mask(self.block, self.min_len, self.min_sig))
@@ -436,8 +567,15 @@ class ShardedHotPath(object):
             eng.kr_setup(self.normed, *self.kr_params)
             st = kr_block_loop(eng, comm)
         self.trace.mark('kr')
-        z = torch.tensor([st['zero_diag']], dtype=torch.int64, device=eng.x.device)
-        st['zero_diag'] = int(comm.all_reduce(z, 'sum').cpu()[0])
+        if self.peer:
+            # x: every rank puts its slice into all arenas; zero-diagonal count summed through the arenas
+            eng.peer_put(comm, 'x', self.row_lo, eng.x[self.row_lo:self.row_hi])
+            eng._scal[0] = float(st['zero_diag'])
+            z = eng.peer_allreduce(comm, eng._scal[:1], 'sum')           # also the barrier behind the x slices
+            st['zero_diag'] = int(z.cpu()[0])
+        else:
+            z = torch.tensor([st['zero_diag']], dtype=torch.int64, device=eng.x.device)
+            st['zero_diag'] = int(comm.all_reduce(z, 'sum').cpu()[0])
         self.kr_info = st
         if st['status'] == -6:
             raise ValueError('KR: max(ynew) == Delta with no element above Delta (Q13)')
@@ -445,7 +583,9 @@ class ShardedHotPath(object):
             raise RuntimeError('matrix balancing failed to converge in {} iterations'.format(st['n_iter']))
         # x: every rank wrote its own slice; assemble the whole vector
         xs = eng.x
-        if comm.world > 1:
+        if self.peer:
+            xs = eng.x_view
+        elif comm.world > 1:
             full = torch.zeros_like(xs)
             full[self.row_lo:self.row_hi].copy_(xs[self.row_lo:self.row_hi])
             xs = comm.all_reduce(full, 'sum')
@@ -460,7 +600,10 @@ class ShardedHotPath(object):
 
     def edges(self, scale=True):
         eng, comm = self.engine, self.comm
-        reduce_max = lambda t: comm.all_reduce(t, 'max')                      # noqa: E731
+        if self.peer:
+            reduce_max = lambda t: eng.peer_allreduce(comm, t, 'max')         # noqa: E731
+        else:
+            reduce_max = lambda t: comm.all_reduce(t, 'max')                  # noqa: E731
         if self.fused:
             self.edge_res = eng.compress_edges(self.block, self.mask, reduce_max, scale=scale, x=self.x)
         else:

@@ -261,6 +261,56 @@ int b3c_kr_run_peer_counts(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nn
                            int64_t ws_bytes, int64_t *h_info, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Peer exchange arena: the sharded accumulation without a collective library in the data path
+ * (the reference has no multi-process form -- this is the partitioned
+ * equivalent of Sparse2DAccumulator.get_coo, sparse_utils.py:246-266, one row block per GPU).
+ * Every rank allocates one arena (b3c_peer_alloc, b3c_xa_bytes) and maps the others' (b3c_peer_open);
+ * h_arena is the HOST array of n_ranks DEVICE pointers as seen from this process, its own at [rank].
+ * All calls only enqueue work on `stream` unless stated.  `epoch` is a counter the callers advance
+ * together: every barrier / all-reduce call of a rank uses the next value (1, 2, 3, ...).
+ *
+ *   b3c_peer_barrier        flag barrier between the ranks' streams: work enqueued after it starts
+ *                           once every rank has completed what it enqueued before it
+ *   b3c_peer_put            copy bytes from d_src into EVERY rank's arena at `offset` (peer stores)
+ *   b3c_peer_allreduce_f64  in-place all-reduce of count <= 8 doubles (op 0 = sum, 1 = max), slots
+ *                           reduced in rank order: one kernel = put + barrier + reduce
+ *   b3c_xa_offsets          h_offsets[0] = mask (uint8[n_seq]), [1] = x (float64[n_seq]), [2] = key
+ *                           receive buffer, [3] = diagonal histogram: regions callers put into / view
+ *
+ *   Sharded accumulation, after b3c_accum_add_pairs on every rank's own records:
+ *     b3c_shard_publish       1024-row chunk weights of the local keys, the pair counters and the local
+ *                             diagonal histogram into the arenas; resets this rank's receive cursor
+ *     (barrier)
+ *     b3c_shard_scatter       d_splits (int32[n_ranks+1], device) = row ranges of about equal weight, cut
+ *                             at chunk boundaries, identical on every rank; then every canonical key
+ *                             (i<j) is written as (i,j) and (j,i) straight into the receive buffer of
+ *                             the rank owning its row (one system-scope atomic per owner and tile
+ *                             reserves the range; owner-contiguous coalesced peer stores)
+ *     (barrier)
+ *     b3c_shard_reduce_block  sort + run-length reduce what was received, gather the diagonal counts
+ *                             of the own rows from all ranks, build the row pointers; synchronises.
+ *                             h_sizes (int64[24]): [0] = entries of this rank's block, [1] = row_lo,
+ *                             [2] = row_hi, [3..5] = accepted / ref_excluded / poor_match summed over
+ *                             ranks, [6] = directed keys received, [8..8+n_ranks] = the splits.
+ *                             Follow with b3c_accum_emit_block(row_lo, row_hi).
+ * Counts are integer sums, so the block is bit-identical whatever the number of ranks.
+ * ------------------------------------------------------------------------------------ */
+int64_t b3c_xa_bytes(int32_t n_seq, int64_t key_capacity);
+int b3c_xa_offsets(int32_t n_seq, int64_t key_capacity, int64_t *h_offsets /* [4] */);
+int b3c_peer_barrier(void *const *h_arena, int32_t rank, int32_t n_ranks, int32_t n_seq,
+                     int64_t key_capacity, uint64_t epoch, void *stream);
+int b3c_peer_put(void *const *h_arena, int32_t n_ranks, int64_t offset, const void *d_src,
+                 int64_t bytes, void *stream);
+int b3c_peer_allreduce_f64(void *const *h_arena, int32_t rank, int32_t n_ranks, int32_t n_seq,
+                           int64_t key_capacity, uint64_t epoch, int32_t op, double *d_val,
+                           int32_t count, void *stream);
+int b3c_shard_publish(void *d_ws, void *const *h_arena, int32_t rank, int32_t n_ranks, void *stream);
+int b3c_shard_scatter(void *d_ws, void *const *h_arena, int32_t rank, int32_t n_ranks,
+                      int32_t *d_splits, void *stream);
+int b3c_shard_reduce_block(void *d_ws, void *const *h_arena, int32_t rank, int32_t n_ranks,
+                           const int32_t *d_splits, int64_t *h_sizes, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Compress + edge weighting.  compress (sparse_utils.py:284-314), get_subspace
  * (contact_map.py:966-982) and the edge loop of to_graph (cluster.py:314-321), on a row block
  * (see "Row blocks"); d_mask and d_newidx have n entries.

@@ -56,11 +56,15 @@ def _run_rank(rank, world, com, min_sig, host_driven_kr=False):
     torch.cuda.synchronize()
     indptr, indices, data = hp.block.host_arrays()
     row = np.repeat(np.arange(hp.block.n), np.diff(indptr)) + hp.row_lo
-    hp.engine.close_peers()
-    return dict(row=row, col=indices, data=data, mask=hp.mask.cpu().numpy(), x=hp.x.cpu().numpy(),
-                n_iter=hp.kr_info['n_iter'], u=res['u'].cpu().numpy(), v=res['v'].cpu().numpy(),
-                w=res['w'].cpu().numpy(),
-                counts=np.array([hp.info[k] for k in ('accepted', 'ref_excluded', 'poor_match')]))
+    out = dict(row=row, col=indices, data=data, mask=hp.mask.cpu().numpy(), x=hp.x.cpu().numpy(),
+               n_iter=hp.kr_info['n_iter'], u=res['u'].cpu().numpy(), v=res['v'].cpu().numpy(),
+               w=res['w'].cpu().numpy(),
+               counts=np.array([hp.info[k] for k in ('accepted', 'ref_excluded', 'poor_match')]))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()                      # nobody unmaps an arena another rank may still be reading
+    hp.engine.close_peers()                 # the mask / x views above were copied before the arenas go away
+    return out
 
 
 @pytest.mark.parametrize('host_driven_kr', [False, True])
