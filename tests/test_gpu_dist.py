@@ -78,7 +78,7 @@ def test_sharded_path_world1(host_driven_kr):
     _check([_run_rank(0, 1, com, 3, host_driven_kr)], com, 3)
 
 
-def _nccl_worker(rank, world, port, out_dir):
+def _nccl_worker(rank, world, port, out_dir, cfg):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -86,20 +86,26 @@ def _nccl_worker(rank, world, port, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     from bin3c_b200 import synth
-    com = synth.make_community(**CFG)
+    com = synth.make_community(**cfg)
     for tag, host_driven in (('peer', False), ('host', True)):
         np.savez(os.path.join(out_dir, '{}{}.npz'.format(tag, rank)), **_run_rank(rank, world, com, 3, host_driven))
     dist.destroy_process_group()
 
 
-def test_sharded_path_two_ranks(tmp_path):
+BIG = dict(n_genomes=30, n_contigs=40_000, n_pairs=3_000_000, seed=655)     # >= 4 row chunks per rank at 8 ranks
+
+
+@pytest.mark.parametrize('world,cfg', [(2, CFG), (4, BIG), (8, BIG)])
+def test_sharded_path_ranks(tmp_path, world, cfg):
+    """2 / 4 / 8 NCCL ranks, both exchange forms (peer arenas + persistent KR, host-driven collectives):
+    the assembled result equals the single-process oracle (counts, mask, n_iter exact; x, w <= 1e-9)."""
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs two GPUs')
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs {} GPUs'.format(world))
     from bin3c_b200 import synth
-    mp.spawn(_nccl_worker, args=(2, 29655, str(tmp_path)), nprocs=2, join=True)
-    com = synth.make_community(**CFG)
+    mp.spawn(_nccl_worker, args=(world, 29655 + world, str(tmp_path), cfg), nprocs=world, join=True)
+    com = synth.make_community(**cfg)
     for tag in ('peer', 'host'):
-        parts = [dict(np.load(os.path.join(str(tmp_path), '{}{}.npz'.format(tag, r)))) for r in range(2)]
+        parts = [dict(np.load(os.path.join(str(tmp_path), '{}{}.npz'.format(tag, r)))) for r in range(world)]
         _check(parts, com, 3)
