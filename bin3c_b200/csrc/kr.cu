@@ -80,7 +80,7 @@ constexpr int SM_RED = 0;
 constexpr int SM_REC = SM_RED + KR_WARPS * RED_MAX * 8;
 constexpr int SM_CTL = SM_REC + 2 * (int)sizeof(WarpRecs);
 constexpr int SM_STATE = SM_CTL + ((int)sizeof(KRScalars) + 15) / 16 * 16;
-constexpr int SM_SLAB = SM_STATE + 32;
+constexpr int SM_SLAB = SM_STATE + 32;          // SpmvState (16 B) + the CTA's SpMV cycle counter
 constexpr int SM_MBAR = (SM_SLAB + (SLAB_S_MAX + 2) * 4 + 7) / 8 * 8;
 constexpr int SM_U = (SM_MBAR + 8 + 127) / 128 * 128;
 constexpr int SM_BYTES_GATHER = SM_U;
@@ -135,7 +135,10 @@ struct KRArgs {
     unsigned long long *xflag[KR_MAX_RANKS];    // barrier flags of every rank: xflag[g][r] = epoch rank r has reached
     unsigned long long *epoch;                  // this rank's epoch counter (persists across runs)
     unsigned *bar_count, *bar_gen;              // grid barrier of the persistent kernel (zeroed per run)
+    int32_t opts;                               // KR_OPT_* bits (b3c_set_option)
+    long long *cta_spmv;                        // [n_bnd] cycles every CTA spent inside its SpMV phases
 };
+enum { KR_OPT_BANK_ORDER = 1, KR_OPT_SLAB_ALIGN = 2, KR_OPT_FAST_BARRIER = 4 };
 
 // publish u[r] / a partial: to this rank and, in peer mode, straight into every other rank's copy
 __device__ __forceinline__ void put_u(const KRArgs &A, int64_t r, double v) {
@@ -158,6 +161,8 @@ struct SpmvState {             // carried from tile to tile by the stitching war
     double open;               // sum so far of the segment open at the end of the last tile
     int seen, last_ord;        // a segment start was seen in this CTA's range; ordinal of the latest one
 };
+
+static_assert(sizeof(SpmvState) == 16, "SM_STATE holds SpmvState followed by the CTA's 8-byte SpMV cycle counter");
 
 struct Smem {
     double *red, *u;
@@ -479,22 +484,46 @@ __device__ __forceinline__ void part_stitch(const KRArgs &A, const Smem &sm, int
 // block-wide synchronisation; the runs are stitched once per part.
 template <bool SLAB>
 __device__ __forceinline__ void phase_spmv(const KRArgs &A, const double *u, Smem &sm) {
-    const int64_t c_lo = A.n_sch * blockIdx.x / gridDim.x, c_hi = A.n_sch * (blockIdx.x + 1) / gridDim.x;
-    if (c_lo >= c_hi) {
-        if (threadIdx.x == 0) {
-            A.bnd_head[blockIdx.x] = 0.0;
-            A.bnd_flag[blockIdx.x] = 0;
-        }
-        return;
-    }
-    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i <= A.S; i += KR_THREADS) sm.slab[i] = A.slab_c0[i];
     if (threadIdx.x == 0) {
         sm.st->open = 0.0;
         sm.st->seen = 0;
         sm.st->last_ord = -1;
     }
-    for (int i = threadIdx.x; i <= A.S; i += KR_THREADS) sm.slab[i] = A.slab_c0[i];
     __syncthreads();
+    int64_t c_lo = A.n_sch * blockIdx.x / gridDim.x, c_hi = A.n_sch * (blockIdx.x + 1) / gridDim.x;
+    if (SLAB && (A.opts & KR_OPT_SLAB_ALIGN) && A.S > 1 && (int)gridDim.x >= 2 * A.S) {
+        // CTA ranges follow the slabs: every slab gets a share of the grid proportional to its chunks, so no
+        // CTA fetches two slabs of u (a range straddling a slab boundary would, and hold the grid barrier up)
+        const int G = gridDim.x, g = blockIdx.x;
+        int b_lo = 0, b_hi = G, s_mine = 0, prev = 0;
+        for (int k = 0; k < A.S; ++k) {
+            int nxt = G;
+            if (k + 1 < A.S) {
+                nxt = (int)(((int64_t)sm.slab[k + 1] * G + A.n_sch / 2) / A.n_sch);
+                if (nxt < prev + 1) nxt = prev + 1;
+                if (nxt > G - (A.S - 1 - k)) nxt = G - (A.S - 1 - k);
+            }
+            if (g >= prev && g < nxt) {
+                s_mine = k;
+                b_lo = prev;
+                b_hi = nxt;
+            }
+            prev = nxt;
+        }
+        const int64_t s0 = sm.slab[s_mine], len = sm.slab[s_mine + 1] - s0;
+        c_lo = s0 + len * (g - b_lo) / (b_hi - b_lo);
+        c_hi = s0 + len * (g - b_lo + 1) / (b_hi - b_lo);
+    }
+    if (c_lo >= c_hi) {
+        if (threadIdx.x == 0) {
+            A.bnd_head[blockIdx.x] = 0.0;
+            A.bnd_flag[blockIdx.x] = 0;
+        }
+        __syncthreads();
+        return;
+    }
+    const int warp = threadIdx.x >> 5;
     int slab = 0, part = 0;
     for (int64_t p_lo = c_lo; p_lo < c_hi; ++part) {
         while (p_lo >= sm.slab[slab + 1]) ++slab;
@@ -868,7 +897,15 @@ __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned
     if (cross) epoch += 1;
     gen += 1;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !cross && (A.opts & KR_OPT_FAST_BARRIER)) {
+        // one word: a release-add to arrive (nothing comes back), then acquire-poll the same count
+        const unsigned target = gen * gridDim.x;
+        unsigned seen;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(A.bar_count) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.bar_count) : "memory");
+        } while (seen < target);
+    } else if (threadIdx.x == 0) {
         if (cross) __threadfence_system();
         else __threadfence();
         const unsigned arrived = atomicAdd(A.bar_count, 1u) + 1u;
@@ -914,6 +951,7 @@ __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned
         call;                                                                  \
         const long long t1_ = clock64();                                       \
         kr_barrier(A, cross, epoch, gen);                                      \
+        if (id == T_SPMV && threadIdx.x == 0) *my_spmv += t1_ - t0_;           \
         if (timing) {                                                          \
             const long long t2_ = clock64();                                   \
             A.timers->work[id] += t1_ - t0_;                                   \
@@ -946,6 +984,8 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
     const long long t_begin = clock64();
     unsigned long long epoch = A.n_rank > 1 ? *A.epoch : 0ull;
     unsigned gen = 0;
+    long long *my_spmv = (long long *)(smem_raw + SM_STATE + 16);      // this CTA's own SpMV time (diagnostics)
+    if (threadIdx.x == 0) *my_spmv = 0;
 
     int mode = -1;                                        // -1: first trip (x = 1)
     for (;;) {
@@ -979,6 +1019,7 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
         if (mode == KR_STATE_DONE) break;
         __syncthreads();                                  // everybody has read the state before thread 0 moves on
     }
+    if (threadIdx.x == 0) A.cta_spmv[blockIdx.x] = *my_spmv;
     if (timing) {
         *A.ctl = S;
         A.timers->total = clock64() - t_begin;
@@ -1106,6 +1147,61 @@ __global__ void __launch_bounds__(256) k_slab_finish(KRArgs A, double *__restric
     __syncthreads();
     const int64_t last = A.vp[(int64_t)(s + 1) * A.npad - 1];
     if (threadIdx.x == 0 && last < end) stream_set_flag(sflag, last);
+}
+
+// Bank order (slab form).  At step i of a chunk the 32 lanes of a warp gather u[col] for the i-th entry of their
+// own 16-entry runs at once; u sits in shared memory as fp64, so an entry's bank pair is col % 16 and a
+// half-warp whose 16 columns were drawn at random needs ~3 passes.  The order of the entries INSIDE a segment
+// is free (the row sum is the only thing that depends on it, and it is fixed once per stream), so every lane
+// orders each piece of a segment inside its run by (bank - lane) mod 16: lane l then tends to touch bank
+// l + i at step i and the half-warp's banks are (nearly) distinct.  One thread per lane run, in place: the
+// 16 entries of a run are touched by nobody else; flags belong to positions and do not move.
+__global__ void __launch_bounds__(256) k_stream_bank_order(int64_t n_runs, double *__restrict__ sval,
+                                                           uint16_t *__restrict__ scol, const uint16_t *__restrict__ sflag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_runs) return;
+    const int64_t chunk = t >> 5;
+    const unsigned lane = (unsigned)(t & 31);
+    const int64_t base = chunk * SPMV_CHUNK + SPMV_EPP * lane;          // piece 0; piece 1 is SPMV_CHUNK / 2 further
+    double a[16];
+    unsigned c[16];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double4 *pv = (const double4 *)(sval + base + k * (SPMV_CHUNK / 2));
+        const double4 v0 = pv[0], v1 = pv[1];
+        a[8 * k + 0] = v0.x; a[8 * k + 1] = v0.y; a[8 * k + 2] = v0.z; a[8 * k + 3] = v0.w;
+        a[8 * k + 4] = v1.x; a[8 * k + 5] = v1.y; a[8 * k + 6] = v1.z; a[8 * k + 7] = v1.w;
+        const uint4 cc = *(const uint4 *)(scol + base + k * (SPMV_CHUNK / 2));
+        c[8 * k + 0] = cc.x & 0xffffu; c[8 * k + 1] = cc.x >> 16; c[8 * k + 2] = cc.y & 0xffffu; c[8 * k + 3] = cc.y >> 16;
+        c[8 * k + 4] = cc.z & 0xffffu; c[8 * k + 5] = cc.z >> 16; c[8 * k + 6] = cc.w & 0xffffu; c[8 * k + 7] = cc.w >> 16;
+    }
+    const unsigned fw = sflag[t];
+    // sort key: pieces of different segments keep their order (segment ordinal inside the run), then the bank
+    // rotated by the lane, then the position (a strict order, so the ranks are a permutation)
+    unsigned key[16];
+    unsigned seg = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        seg += (fw >> i) & 1u;
+        key[i] = (seg << 8) | (((c[i] - lane) & 15u) << 4) | (unsigned)i;
+    }
+    bool moved = false;
+    unsigned rank[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        unsigned r = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r += key[j] < key[i] ? 1u : 0u;
+        rank[i] = r;
+        moved |= r != (unsigned)i;
+    }
+    if (!moved) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int64_t dst = base + (rank[i] >> 3) * (SPMV_CHUNK / 2) + (rank[i] & 7);
+        sval[dst] = a[i];
+        scol[dst] = (uint16_t)c[i];
+    }
 }
 
 // chunk_seg0[c] = ordinal of the first segment that starts at or after entry c * 128
@@ -1246,13 +1342,14 @@ static std::unordered_map<void *, KRArgs> g_krp;
 // tuning / test hooks (b3c_set_option): slab width cap and slab count cap of the SpMV operand
 static std::atomic<int> g_slab_w_max{SLAB_W_MAX};
 static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
+static std::atomic<int> g_kr_opts{KR_OPT_BANK_ORDER | KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER};
 constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
 
 struct KRLayout {
     int32_t slab, S, W, n_chunks;
     int64_t nvec;                       // elements per (padded) vector
     int64_t nv_max, nnzv_max, nseg_max;
-    int64_t o_dfix, o_vec, o_qs, o_part, o_ctl, o_timers, o_bar, o_bnd;
+    int64_t o_dfix, o_vec, o_qs, o_part, o_ctl, o_timers, o_bar, o_bnd, o_cta;
     int64_t o_cnt, o_vp, o_ord, o_scan, o_slab_t0, o_sval, o_scol, o_sflag, o_seg0, o_seg_of, o_seg_row, total;
 };
 
@@ -1277,6 +1374,7 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     L.o_timers = c.take(sizeof(KRTimers));
     L.o_bar = c.take(256);
     L.o_bnd = c.take((int64_t)BND_MAX * (8 + 8 + 4 + 4 + 4));
+    L.o_cta = c.take((int64_t)BND_MAX * 8);
     L.o_cnt = c.take((L.nv_max + 1) * 8);
     L.o_vp = c.take((L.nv_max + 1) * 8);
     L.o_ord = c.take((L.nv_max + 1) * 8);
@@ -1348,6 +1446,8 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.timers = (KRTimers *)(ws + L.o_timers);
     A.bar_count = (unsigned *)(ws + L.o_bar);
     A.bar_gen = (unsigned *)(ws + L.o_bar + 128);
+    A.opts = g_kr_opts.load();
+    A.cta_spmv = (long long *)(ws + L.o_cta);
     A.n_rank = 0;
     A.rank = 0;
     A.epoch = nullptr;
@@ -1435,6 +1535,10 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     A.n_seg = (int32_t)totals[1];
     k_stream_rows<true, SLAB><<<row_warp_grid(n_local), 256, 0, s>>>(A, nullptr, sval, scol, sflag);
     B3C_LAUNCH_CHECK();
+    if (SLAB && (A.opts & KR_OPT_BANK_ORDER) && A.n_sch > 0) {
+        k_stream_bank_order<<<(unsigned)ceil_div(A.n_sch * 32, 256), 256, 0, s>>>(A.n_sch * 32, sval, (uint16_t *)scol, sflag);
+        B3C_LAUNCH_CHECK();
+    }
     k_cell_index<<<(unsigned)ceil_div(A.nv, 256), 256, 0, s>>>(A.nv, A.vp, A.ord, const_cast<int32_t *>(A.seg_of),
                                                                const_cast<int32_t *>(A.seg_row));
     B3C_LAUNCH_CHECK();
@@ -1489,6 +1593,10 @@ int b3c_set_option(int32_t key, int64_t value) {
             B3C_REQUIRE(value >= 0 && value <= SLAB_S_MAX, "slab count cap must be in [0, %d]", SLAB_S_MAX);
             g_slab_s_max.store((int)value);
             return B3C_OK;
+        case B3C_OPT_KR_FLAGS:
+            B3C_REQUIRE(value >= 0 && value <= 7, "KR option flags must be in [0, 7]");
+            g_kr_opts.store((int)value);
+            return B3C_OK;
         default:
             set_error("unknown option %d", key);
             return B3C_ERR_ARG;
@@ -1541,6 +1649,19 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     h_info[25] = A.nnzv;
     h_info[26] = A.n_seg;
     h_info[27] = (int64_t)(ms * 1000.0f + 0.5f);       // the persistent kernel alone, microseconds (CUDA events)
+    {
+        long long cta[BND_MAX];
+        B3C_CUDA(cudaMemcpy(cta, A.cta_spmv, (size_t)grid * 8, cudaMemcpyDeviceToHost));
+        long long mn = cta[0], mx = cta[0], sum = 0;
+        for (int i = 0; i < grid; ++i) {
+            mn = cta[i] < mn ? cta[i] : mn;
+            mx = cta[i] > mx ? cta[i] : mx;
+            sum += cta[i];
+        }
+        h_info[28] = mn;                               // SpMV cycles of the fastest / slowest CTA and the mean
+        h_info[29] = mx;
+        h_info[30] = sum / grid;
+    }
     if (T.sync[T_FIX] < 0) {
         set_error("KR: a rank did not reach a cross-GPU barrier within the time-out");
         return B3C_ERR_CUDA;

@@ -243,7 +243,8 @@ def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000, pool=None,
                grid=int(info[4]), cycles=int(info[5]),
                work_cycles={k: int(info[6 + i]) for i, k in enumerate(names)},
                sync_cycles={k: int(info[15 + i]) for i, k in enumerate(names)},
-               slabs=int(info[24]), nnz_stream=int(info[25]), segments=int(info[26]), kernel_us=int(info[27]))
+               slabs=int(info[24]), nnz_stream=int(info[25]), segments=int(info[26]), kernel_us=int(info[27]),
+               cta_spmv_cycles=dict(min=int(info[28]), max=int(info[29]), mean=int(info[30])))
     check(rc)
     return x, out
 

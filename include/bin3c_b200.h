@@ -150,7 +150,8 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  *                 reductions), [15..23] = cycles it waited at the grid barrier after each,
  *                 [24] = column slabs of the SpMV operand (0 = gather form), [25] = entries of the
  *                 SpMV stream including slab padding, [26] = (row, slab) segments, [27] = duration
- *                 of the persistent kernel alone in microseconds (CUDA events on `stream`).
+ *                 of the persistent kernel alone in microseconds (CUDA events on `stream`),
+ *                 [28..30] = SpMV cycles of the fastest CTA, the slowest CTA and the mean.
  *                 mode 0 = one persistent cooperative kernel (device-side control flow).
  *   b3c_kr_scale  out[e] = x_i * (a_ij * x_j), the entries of X.T.dot(orig.dot(X))
  *                 (sparse_utils.py:223-224, Q9) on the ORIGINAL matrix.
@@ -160,8 +161,11 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  * a time (see csrc/kr.cu); B3C_OPT_KR_SLAB_WIDTH caps the slab width (default 26112 columns, the most
  * that fits in a CTA's shared memory), B3C_OPT_KR_MAX_SLABS the slab count (default 16; wider matrices,
  * or 0, select the form that gathers through L1/L2).  Results are identical up to fp64 summation
- * order.  Workspace sizes depend on these, so set them before the *_workspace_bytes() query. */
-enum { B3C_OPT_KR_SLAB_WIDTH = 1, B3C_OPT_KR_MAX_SLABS = 2 };
+ * order.  Workspace sizes depend on these, so set them before the *_workspace_bytes() query.
+ * B3C_OPT_KR_FLAGS (default 7) is a bit set for A/B measurements: 1 = order every lane's run of the
+ * stream by shared-memory bank, 2 = align the SpMV CTA ranges with the slabs, 4 = single-word grid
+ * barrier (release-add + acquire-poll). */
+enum { B3C_OPT_KR_SLAB_WIDTH = 1, B3C_OPT_KR_MAX_SLABS = 2, B3C_OPT_KR_FLAGS = 3 };
 int b3c_set_option(int32_t key, int64_t value);
 
 int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz);
