@@ -372,23 +372,20 @@ __device__ __forceinline__ void piece_process(const KRArgs &A, const double *u, 
 #pragma unroll
         for (int i = 0; i < SPMV_EPP; ++i) x[i] = __dmul_rn(R.a[i], u[R.c[i]]);
     }
-    const unsigned bits = L.fw & 0xffu;
+    // segments are padded to whole pieces (seg_padded), so only the piece's first entry can carry a flag:
+    // add the piece up as a fixed tree, then either extend the open segment or close it and open the next
+    static_assert(SPMV_EPP == 8, "piece sum tree");
+    const double s8 = __dadd_rn(__dadd_rn(__dadd_rn(x[0], x[1]), __dadd_rn(x[2], x[3])),
+                                __dadd_rn(__dadd_rn(x[4], x[5]), __dadd_rn(x[6], x[7])));
+    const unsigned bits = L.fw & 1u;
     L.fw >>= 8;
-    if (bits == 0) {
-#pragma unroll
-        for (int i = 0; i < SPMV_EPP; ++i) L.cur = __dadd_rn(L.cur, x[i]);
+    if (bits) {
+        if (L.nseen == 0) L.head = L.cur;
+        else A.qs[L.base + L.nseen - 1] = L.cur;
+        L.nseen += 1;
+        L.cur = s8;
     } else {
-#pragma unroll
-        for (int i = 0; i < SPMV_EPP; ++i) {
-            if (bits & (1u << i)) {
-                if (L.nseen == 0) L.head = L.cur;
-                else A.qs[L.base + L.nseen - 1] = L.cur;
-                L.nseen += 1;
-                L.cur = x[i];
-            } else {
-                L.cur = __dadd_rn(L.cur, x[i]);
-            }
-        }
+        L.cur = __dadd_rn(L.cur, s8);
     }
 }
 
@@ -1033,6 +1030,10 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
 // whole tiles; an exclusive scan gives the position vp of every cell; a second scan numbers the
 // non-empty cells; pass 2 copies the segments.  A warp walks one row in 32-entry windows; a lane whose
 // slab differs from its left neighbour's starts a segment.
+// Every segment is padded with zero entries to a whole number of 8-entry pieces, so a segment can only start at
+// the first entry of a lane's piece: the SpMV adds a piece up unconditionally and looks at ONE flag per piece.
+__host__ __device__ __forceinline__ int64_t seg_padded(int64_t len) { return (len + SPMV_EPP - 1) & ~(int64_t)(SPMV_EPP - 1); }
+
 // set the start flag of logical stream position `pos` (bit pos % 16 of the lane's 16-bit word)
 __device__ __forceinline__ void stream_set_flag(uint16_t *sflag, int64_t pos) {
     const int64_t w16 = pos >> 4;                      // chunk * 32 + lane
@@ -1070,7 +1071,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
             if (!FILL) {
                 if (flag && sp >= 0) {             // this entry closes the segment of slab sp
                     const int64_t prev_start = below ? e0 + (31 - __clz(below)) : carry_start;
-                    cnt[(int64_t)sp * A.npad + lr] = e - prev_start;
+                    cnt[(int64_t)sp * A.npad + lr] = seg_padded(e - prev_start);
                 }
             } else if (valid) {
                 const unsigned upto = fm & (lanemask_lt() | (1u << lane));
@@ -1082,12 +1083,28 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
                 else ((uint32_t *)scol_v)[ph] = lc;
                 if (e == seg_start) stream_set_flag(sflag, dst);
+                // the segment's last entry also writes its padding (zero value, column 0) up to a whole piece
+                int s_next = -1;
+                if (e + 1 < hi) {
+                    int cn = A.indices[e + 1];
+                    cn = cn < 0 ? 0 : (cn >= A.n ? A.n - 1 : cn);
+                    s_next = cn / W;
+                }
+                if (s_next != s) {
+                    const int64_t len = e - seg_start + 1, seg0 = dst - (e - seg_start);
+                    for (int64_t k = len; k < seg_padded(len); ++k) {
+                        const int64_t pp = stream_phys(seg0 + k);
+                        sval[pp] = 0.0;
+                        if (SLAB) ((uint16_t *)scol_v)[pp] = 0;
+                        else ((uint32_t *)scol_v)[pp] = 0;
+                    }
+                }
             }
             if (fm) carry_start = e0 + (31 - __clz(fm));
             const int last = (int)((hi - 1 - e0) < 31 ? (hi - 1 - e0) : 31);
             carry_s = __shfl_sync(kFullMask, s, last);
         }
-        if (!FILL && hi > lo && lane == 0) cnt[(int64_t)carry_s * A.npad + lr] = hi - carry_start;
+        if (!FILL && hi > lo && lane == 0) cnt[(int64_t)carry_s * A.npad + lr] = seg_padded(hi - carry_start);
     }
     if (!FILL && bad) A.ctl->status = B3C_ERR_ARG;     // unsorted or out-of-range columns
 }
@@ -1362,8 +1379,9 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     L.W = L.slab ? (int32_t)align_up(ceil_div(n, L.S), 2) : n;
     const int64_t npad_max = align_up(n, CHUNK);
     L.nv_max = (int64_t)L.S * npad_max;
-    L.nnzv_max = align_up(nnz, SPMV_TILE) + (int64_t)L.S * SPMV_TILE;
     L.nseg_max = (nnz + L.S < L.nv_max ? nnz + L.S : L.nv_max) + 1;
+    // every segment is padded to a whole piece (< SPMV_EPP extra entries each), every slab to a whole tile
+    L.nnzv_max = align_up(nnz + (SPMV_EPP - 1) * L.nseg_max, SPMV_TILE) + (int64_t)L.S * SPMV_TILE;
     L.n_chunks = (int32_t)ceil_div(n, CHUNK);
     L.nvec = align_up(n, 32);
     L.o_dfix = c.take((int64_t)n * 8);
