@@ -1,0 +1,97 @@
+/*
+ * bin3c_io -- host-side C ABI of the two steps either side of the contact-map hot path
+ * (SURVEY.md section 8f, ranks 1 and 2).  Built as bin3c_b200/libbin3c_io.so (g++ + zlib +
+ * pthreads; no CUDA, no htslib).  The device path itself is include/bin3c_b200.h.
+ *
+ *   b3c_bam_*         name-sorted BAM -> reference table + packed pair records.  Replaces the
+ *                     pysam side of the reference: AlignmentFile / header checks
+ *                     (contact_map.py:534-545), next_informative (:624-629), the pairing loop
+ *                     (:720-731), the matchers (:612-622) and the min_insert filter (:761-766).
+ *                     BGZF blocks are inflated on a pool of threads, two batches ahead of the
+ *                     parser; the parser is the reference's sequential state machine.
+ *   b3c_edges_write   edge arrays -> the text file nx.write_edgelist(g, path, data=['weight'],
+ *                     delimiter=' ') produces (cluster.py:139-151): one "u v weight" line per
+ *                     undirected edge, weight printed as the shortest round-trip decimal in
+ *                     Python's float repr layout.  Formatted on a pool of threads.
+ *
+ * All pointers are HOST pointers.  Functions return 0 (or a non-negative count) on success and a
+ * negative b3c_io_status on failure; b3c_io_last_error() returns a thread-local message.
+ *
+ * Packed pair record (uint64, little endian), identical to include/bin3c_b200.h:
+ *     bits  0..30  BAM reference id of the first record of the pair   (r1.reference_id)
+ *     bit   31     pass flag: both mates satisfy the matcher          (contact_map.py:737)
+ *     bits 32..62  BAM reference id of the second record              (r2.reference_id)
+ *     bit   63     0
+ * A reference id outside [0, n_refs) is stored as 0x7fffffff (never in the index table, so the
+ * pair is counted ref_excluded like `r.reference_id not in _idx`, contact_map.py:733).
+ */
+#ifndef BIN3C_IO_H
+#define BIN3C_IO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B3C_IO_OK = 0,
+    B3C_IO_ERR_ARG = -1,      /* bad argument                                                   */
+    B3C_IO_ERR_OPEN = -2,     /* file cannot be opened / written                                */
+    B3C_IO_ERR_FORMAT = -3,   /* not BGZF / not BAM / truncated / CRC mismatch                   */
+    B3C_IO_ERR_SORT = -4      /* @HD SO is not 'queryname' (IOError, contact_map.py:537-538)     */
+} b3c_io_status;
+
+int b3c_io_version(void);
+const char *b3c_io_last_error(void);
+
+typedef struct b3c_bam b3c_bam;
+
+/* Open a BAM file and parse its header (magic, SAM text, reference table).  n_threads <= 0: one
+ * inflate thread per online core.  require_queryname != 0 enforces contact_map.py:537-538. */
+int b3c_bam_open(const char *path, int32_t n_threads, int32_t require_queryname, b3c_bam **out);
+void b3c_bam_close(b3c_bam *bam);
+
+/* header: bam.references / bam.lengths (contact_map.py:545) and the raw SAM text */
+int32_t b3c_bam_n_refs(const b3c_bam *bam);
+const char *b3c_bam_ref_name(const b3c_bam *bam, int32_t tid);
+int64_t b3c_bam_ref_lengths(const b3c_bam *bam, int64_t *h_lengths, int32_t capacity);
+int64_t b3c_bam_header_text(const b3c_bam *bam, char *h_text, int64_t capacity);   /* returns the full length */
+
+/* Matcher and insert filter; call before the first read.
+ *   min_mapq     r.mapping_quality >= min_mapq                         (_simple_match, :612-613)
+ *   strong       > 0: also the 5'-end CIGAR op must be M with length >= strong; a record without
+ *                CIGAR fails                                           (_strong_match, :615-619)
+ *   min_insert   > 0 (needs h_tid2idx): a pair that passes the exclusion and matcher tests, whose
+ *                read-1 mate is flagged proper-pair and has r2.pos - r1.pos < min_insert, is
+ *                dropped here and counted short_insert                 (:744-745, :761-766)
+ *   h_tid2idx    BAM reference id -> internal index or -1 (make_reverse_index('refid'), :703);
+ *                copied; may be NULL when min_insert == 0 */
+int b3c_bam_set_filter(b3c_bam *bam, int32_t min_mapq, int32_t strong, int32_t min_insert,
+                       const int32_t *h_tid2idx, int32_t n_refs);
+
+/* Decode until `capacity` records are written or the file ends.  Returns the number of records
+ * written (0 = end of file) or a negative status.  Consecutive calls continue the stream. */
+int64_t b3c_bam_read_pairs(b3c_bam *bam, uint64_t *h_records, int64_t capacity);
+
+/* h_stats[0] alignments read (what bam.count(until_eof=True) returns once the file is exhausted)
+ * h_stats[1] informative alignments (mapped, primary, not supplementary; :628)
+ * h_stats[2] pairs found (records written + short_insert)
+ * h_stats[3] short_insert (:765)
+ * h_stats[4] informative alignments left without a mate
+ * h_stats[5] BGZF blocks inflated
+ * h_stats[6] compressed bytes consumed
+ * h_stats[7] uncompressed bytes produced */
+int b3c_bam_stats(const b3c_bam *bam, int64_t *h_stats, int32_t n_stats);
+
+/* Write `n_edges` lines "u<sep>v<sep>weight\n" to `path` (truncating).  Returns bytes written. */
+int64_t b3c_edges_write(const char *path, const int32_t *h_u, const int32_t *h_v, const double *h_w,
+                        int64_t n_edges, char sep, int32_t n_threads);
+/* Format one weight as Python's repr(float) would; returns the length (buffer of >= 32 bytes). */
+int32_t b3c_format_weight(double w, char *h_buf, int32_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIN3C_IO_H */
