@@ -80,12 +80,13 @@ constexpr int SM_RED = 0;
 constexpr int SM_REC = SM_RED + KR_WARPS * RED_MAX * 8;
 constexpr int SM_CTL = SM_REC + 2 * (int)sizeof(WarpRecs);
 constexpr int SM_STATE = SM_CTL + ((int)sizeof(KRScalars) + 15) / 16 * 16;
-constexpr int SM_SLAB = SM_STATE + 32;          // SpmvState (16 B) + the CTA's SpMV cycle counter
+constexpr int SM_TIM = SM_STATE + 32;           // SpmvState (16 B) + the CTA's SpMV cycle counter, then the phase timers
+constexpr int SM_SLAB = SM_TIM + 2 * 9 * 8;     // work[T_COUNT], sync[T_COUNT]: accumulated in shared memory, written out once
 constexpr int SM_MBAR = (SM_SLAB + (SLAB_S_MAX + 2) * 4 + 7) / 8 * 8;
 constexpr int SM_U = (SM_MBAR + 8 + 127) / 128 * 128;
 constexpr int SM_BYTES_GATHER = SM_U;
 constexpr int SM_BYTES_SLAB = SM_U + SLAB_W_MAX * 8;
-static_assert(SM_REC % 8 == 0 && SM_CTL % 8 == 0 && SM_STATE % 8 == 0 && SM_MBAR % 8 == 0, "shared memory carve alignment");
+static_assert(SM_REC % 8 == 0 && SM_CTL % 8 == 0 && SM_STATE % 8 == 0 && SM_TIM % 8 == 0 && SM_MBAR % 8 == 0, "shared memory carve alignment");
 static_assert(SM_BYTES_SLAB <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
 struct KRArgs {
@@ -586,18 +587,29 @@ __device__ __forceinline__ void phase_spmv(const KRArgs &A, const double *u, Sme
 // Finish the segments that cross SpMV CTA ranges: the segment open at the end of CTA g's range is
 // its tail plus the heads of the following CTAs up to (and including) the first one that saw a flag.
 // The CTA that owns reduction chunk c does this for the rows of the chunk before it reads their sums.
+// Everything a record can need in the common case (its own fields and the next CTA's head and flag) is
+// loaded up front, so the fix costs one trip to L2 instead of a chain of three or four.
 __device__ __forceinline__ void boundary_fix(const KRArgs &A, int c) {
     const int64_t r0 = (int64_t)c * CHUNK - A.row_lo;              // local rows [r0, r0 + CHUNK)
     for (int g = threadIdx.x; g < A.n_bnd; g += KR_THREADS) {
-        if (!__ldcg(A.bnd_flag + g)) continue;
+        const bool nxt = g + 1 < A.n_bnd;
+        const int flag = __ldcg(A.bnd_flag + g);
         const int lr = __ldcg(A.bnd_lr + g);
-        if (lr < r0 || lr >= r0 + CHUNK) continue;
+        const int ord = __ldcg(A.bnd_ord + g);
         double s = __ldcg(A.bnd_tail + g);
-        for (int g2 = g + 1; g2 < A.n_bnd; ++g2) {
-            s = __dadd_rn(s, __ldcg(A.bnd_head + g2));
-            if (__ldcg(A.bnd_flag + g2)) break;
+        const double h1 = nxt ? __ldcg(A.bnd_head + g + 1) : 0.0;
+        const int f1 = nxt ? __ldcg(A.bnd_flag + g + 1) : 1;
+        if (!flag || lr < r0 || lr >= r0 + CHUNK) continue;
+        if (nxt) {
+            s = __dadd_rn(s, h1);
+            if (!f1) {
+                for (int g2 = g + 2; g2 < A.n_bnd; ++g2) {
+                    s = __dadd_rn(s, __ldcg(A.bnd_head + g2));
+                    if (__ldcg(A.bnd_flag + g2)) break;
+                }
+            }
         }
-        A.qs[__ldcg(A.bnd_ord + g)] = s;
+        A.qs[ord] = s;
     }
     __syncthreads();
 }
@@ -614,12 +626,57 @@ __device__ __forceinline__ double row_q(const KRArgs &A, int64_t r) {
 }
 
 // ---- vector phases: one CTA per 1024-row chunk, CHUNK_RPT rows per thread ------------------------
+// Every phase first LOADS what its CHUNK_RPT rows need (independent L2 reads, issued back to back), then computes
+// and stores: the vectors are rewritten from phase to phase, so they are read with ld.global.cg (L2) and a
+// store can never force a later load to wait.
 #define KR_FOR_CHUNKS(c) for (int c = blockIdx.x; c < A.n_chunks; c += gridDim.x)
 #define KR_ROW(c, i) ((int64_t)(c) * CHUNK + (i) * KR_THREADS + threadIdx.x)
+constexpr int ROWQ_S = 4;                      // slabs handled by the batched row_q; more fall back to the loop
 
 __device__ __forceinline__ bool chunk_local(const KRArgs &A, int c) {
     const int64_t r0 = (int64_t)c * CHUNK;
     return r0 >= A.row_lo && r0 < A.row_hi;
+}
+
+// q = A u plus the zero-diagonal term (Q2) for the CHUNK_RPT rows of this thread, loads batched
+__device__ __forceinline__ void rows_q(const KRArgs &A, int c, double (&qq)[CHUNK_RPT]) {
+    if (A.S > ROWQ_S) {
+#pragma unroll
+        for (int i = 0; i < CHUNK_RPT; ++i) {
+            const int64_t r = KR_ROW(c, i);
+            qq[i] = 0.0;
+            if (r < A.row_hi) {
+                qq[i] = row_q(A, r);
+                if (__ldcg(A.dfix + r) != 0.0) qq[i] = __dadd_rn(qq[i], __ldcg(A.u + r));
+            }
+        }
+        return;
+    }
+    int o[CHUNK_RPT][ROWQ_S];
+    double df[CHUNK_RPT], uu[CHUNK_RPT], t[CHUNK_RPT][ROWQ_S];
+#pragma unroll
+    for (int i = 0; i < CHUNK_RPT; ++i) {
+        const int64_t r = KR_ROW(c, i);
+        const bool ok = r < A.row_hi;
+#pragma unroll
+        for (int k = 0; k < ROWQ_S; ++k)
+            o[i][k] = (ok && k < A.S) ? __ldg(A.seg_of + (int64_t)k * A.npad + (r - A.row_lo)) : -1;
+        df[i] = ok ? __ldcg(A.dfix + r) : 0.0;
+        uu[i] = ok ? __ldcg(A.u + r) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < CHUNK_RPT; ++i)
+#pragma unroll
+        for (int k = 0; k < ROWQ_S; ++k) t[i][k] = o[i][k] >= 0 ? __ldcg(A.qs + o[i][k]) : 0.0;
+#pragma unroll
+    for (int i = 0; i < CHUNK_RPT; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < ROWQ_S; ++k)
+            if (o[i][k] >= 0) s = __dadd_rn(s, t[i][k]);
+        if (df[i] != 0.0) s = __dadd_rn(s, uu[i]);                 // zero diagonal counted as one (Q2)
+        qq[i] = s;
+    }
 }
 
 __device__ __forceinline__ void phase_init(const KRArgs &A) {
@@ -642,15 +699,19 @@ __device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
         if (loc) {
+            double xx[CHUNK_RPT], qq[CHUNK_RPT];
+#pragma unroll
+            for (int i = 0; i < CHUNK_RPT; ++i) {
+                const int64_t r = KR_ROW(c, i);
+                xx[i] = r < A.row_hi ? __ldcg(A.x + r) : 0.0;
+            }
             boundary_fix(A, c);
+            rows_q(A, c, qq);
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
                 if (r < A.row_hi) {
-                    const double xx = A.x[r];
-                    double qq = row_q(A, r);
-                    if (A.dfix[r] != 0.0) qq = __dadd_rn(qq, A.u[r]);          // zero diagonal counted as one (Q2)
-                    const double vv = __dmul_rn(xx, qq);
+                    const double vv = __dmul_rn(xx[i], qq[i]);
                     const double rr = __dsub_rn(1.0, vv);
                     A.v[r] = vv;
                     A.rk[r] = rr;
@@ -670,23 +731,31 @@ __device__ __forceinline__ void phase_dir(const KRArgs &A, bool first, double be
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
         if (loc) {
+            double a0[CHUNK_RPT], a1[CHUNK_RPT], xx[CHUNK_RPT];
+#pragma unroll
+            for (int i = 0; i < CHUNK_RPT; ++i) {
+                const int64_t r = KR_ROW(c, i);
+                const bool ok = r < A.row_hi;
+                a0[i] = ok ? __ldcg((first ? A.rk : A.Z) + r) : 0.0;
+                a1[i] = ok ? __ldcg((first ? A.v : A.p) + r) : 1.0;
+                xx[i] = ok ? __ldcg(A.x + r) : 0.0;
+            }
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
                 if (r < A.row_hi) {
                     double pp;
                     if (first) {
-                        const double rr = A.rk[r];
-                        const double z = __ddiv_rn(rr, A.v[r]);             // sparse_utils.py:158
+                        const double z = __ddiv_rn(a0[i], a1[i]);           // sparse_utils.py:158
                         A.Z[r] = z;
                         pp = z;
-                        acc = __dadd_rn(acc, __dmul_rn(rr, z));
+                        acc = __dadd_rn(acc, __dmul_rn(a0[i], z));
                         ycur[r] = 1.0;                                      // y[:] = e (sparse_utils.py:150)
                     } else {
-                        pp = __dadd_rn(A.Z[r], __dmul_rn(beta, A.p[r]));    // sparse_utils.py:163
+                        pp = __dadd_rn(a0[i], __dmul_rn(beta, a1[i]));      // sparse_utils.py:163
                     }
                     A.p[r] = pp;
-                    put_u(A, r, __dmul_rn(A.x[r], pp));
+                    put_u(A, r, __dmul_rn(xx[i], pp));
                 }
             }
         }
@@ -706,17 +775,24 @@ __device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
         if (loc) {
+            double xx[CHUNK_RPT], vv[CHUNK_RPT], pp[CHUNK_RPT], qq[CHUNK_RPT];
+#pragma unroll
+            for (int i = 0; i < CHUNK_RPT; ++i) {
+                const int64_t r = KR_ROW(c, i);
+                const bool ok = r < A.row_hi;
+                xx[i] = ok ? __ldcg(A.x + r) : 0.0;
+                vv[i] = ok ? __ldcg(A.v + r) : 0.0;
+                pp[i] = ok ? __ldcg(A.p + r) : 0.0;
+            }
             boundary_fix(A, c);
+            rows_q(A, c, qq);
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
                 if (r < A.row_hi) {
-                    double qq = row_q(A, r);
-                    if (A.dfix[r] != 0.0) qq = __dadd_rn(qq, A.u[r]);
-                    const double pp = A.p[r];
-                    const double ww = __dadd_rn(__dmul_rn(A.x[r], qq), __dmul_rn(A.v[r], pp));
+                    const double ww = __dadd_rn(__dmul_rn(xx[i], qq[i]), __dmul_rn(vv[i], pp[i]));
                     A.w[r] = ww;
-                    acc = __dadd_rn(acc, __dmul_rn(pp, ww));
+                    acc = __dadd_rn(acc, __dmul_rn(pp[i], ww));
                 }
             }
         }
@@ -734,20 +810,31 @@ __device__ __forceinline__ void phase_step(const KRArgs &A, double alpha, double
         double rho = 0.0, mn = INFINITY, nmx = INFINITY, g1 = INFINITY, g2 = INFINITY;
         const bool loc = chunk_local(A, c);
         if (loc) {
+            double pp[CHUNK_RPT], yv[CHUNK_RPT], rk[CHUNK_RPT], ww[CHUNK_RPT], vv[CHUNK_RPT];
+#pragma unroll
+            for (int i = 0; i < CHUNK_RPT; ++i) {
+                const int64_t r = KR_ROW(c, i);
+                const bool ok = r < A.row_hi;
+                pp[i] = ok ? __ldcg(A.p + r) : 0.0;
+                yv[i] = ok ? __ldcg(ycur + r) : 0.0;
+                rk[i] = ok ? __ldcg(A.rk + r) : 0.0;
+                ww[i] = ok ? __ldcg(A.w + r) : 0.0;
+                vv[i] = ok ? __ldcg(A.v + r) : 0.0;
+            }
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
                 if (r < A.row_hi) {
-                    const double ap = __dmul_rn(alpha, A.p[r]);
-                    const double yy = ycur[r];
+                    const double ap = __dmul_rn(alpha, pp[i]);
+                    const double yy = yv[i];
                     const double yn = __dadd_rn(yy, ap);
                     ynew[r] = yn;
                     mn = fmin(mn, yn);
                     nmx = fmin(nmx, -yn);
                     if (ap < 0.0) g1 = fmin(g1, __ddiv_rn(__dsub_rn(delta, yy), ap));      // :174-175
                     if (yn > Delta) g2 = fmin(g2, __ddiv_rn(__dsub_rn(Delta, yy), ap));    // :180-181
-                    const double rr = __dsub_rn(A.rk[r], __dmul_rn(alpha, A.w[r]));       // :186
-                    const double z = __dmul_rn(rr, A.v[r]);                               // :189
+                    const double rr = __dsub_rn(rk[i], __dmul_rn(alpha, ww[i]));          // :186
+                    const double z = __dmul_rn(rr, vv[i]);                                // :189
                     A.rk[r] = rr;
                     A.Z[r] = z;
                     rho = __dadd_rn(rho, __dmul_rn(rr, z));
@@ -771,16 +858,24 @@ __device__ __forceinline__ void phase_update(const KRArgs &A, int ymode, double 
                                              const double *ycur) {
     KR_FOR_CHUNKS(c) {
         if (!chunk_local(A, c)) continue;
+        double xx[CHUNK_RPT], yv[CHUNK_RPT], pp[CHUNK_RPT];
+#pragma unroll
+        for (int i = 0; i < CHUNK_RPT; ++i) {
+            const int64_t r = KR_ROW(c, i);
+            const bool ok = r < A.row_hi;
+            xx[i] = ok ? __ldcg(A.x + r) : 0.0;
+            yv[i] = (ok && ymode >= 1) ? __ldcg(ycur + r) : 1.0;
+            pp[i] = (ok && ymode == 2) ? __ldcg(A.p + r) : 0.0;
+        }
 #pragma unroll
         for (int i = 0; i < CHUNK_RPT; ++i) {
             const int64_t r = KR_ROW(c, i);
             if (r < A.row_hi) {
-                double yy = 1.0;
-                if (ymode >= 1) yy = ycur[r];
-                if (ymode == 2) yy = __dadd_rn(yy, __dmul_rn(gamma, __dmul_rn(alpha, A.p[r])));
-                const double xx = __dmul_rn(A.x[r], yy);
-                A.x[r] = xx;
-                put_u(A, r, xx);
+                double yy = yv[i];
+                if (ymode == 2) yy = __dadd_rn(yy, __dmul_rn(gamma, __dmul_rn(alpha, pp[i])));
+                const double xn = __dmul_rn(xx[i], yy);
+                A.x[r] = xn;
+                put_u(A, r, xn);
             }
         }
     }
@@ -951,9 +1046,16 @@ __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned
         if (id == T_SPMV && threadIdx.x == 0) *my_spmv += t1_ - t0_;           \
         if (timing) {                                                          \
             const long long t2_ = clock64();                                   \
-            A.timers->work[id] += t1_ - t0_;                                   \
-            A.timers->sync[id] += t2_ - t1_;                                   \
+            tim_work[id] += t1_ - t0_;                                         \
+            tim_sync[id] += t2_ - t1_;                                         \
         }                                                                      \
+    } while (0)
+// the reduction of the per-chunk partials every CTA repeats after a barrier (timed in the T_FIX slot)
+#define KR_REDUCE(call)                                                        \
+    do {                                                                       \
+        const long long tr_ = clock64();                                       \
+        call;                                                                  \
+        if (timing) tim_work[T_FIX] += clock64() - tr_;                        \
     } while (0)
 // a decision taken by thread 0 on the shared scalars, then published to the CTA
 #define KR_SCALAR(which, r)                                                    \
@@ -961,7 +1063,7 @@ __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned
         const long long ts_ = clock64();                                       \
         if (threadIdx.x == 0) scalar_step(S, which, r);                        \
         __syncthreads();                                                       \
-        if (timing) A.timers->work[T_SCALAR] += clock64() - ts_;               \
+        if (timing) tim_work[T_SCALAR] += clock64() - ts_;                     \
     } while (0)
 
 template <bool SLAB>
@@ -982,7 +1084,13 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
     unsigned long long epoch = A.n_rank > 1 ? *A.epoch : 0ull;
     unsigned gen = 0;
     long long *my_spmv = (long long *)(smem_raw + SM_STATE + 16);      // this CTA's own SpMV time (diagnostics)
-    if (threadIdx.x == 0) *my_spmv = 0;
+    // CTA 0's phase timers live in shared memory while the loop runs (a global read-modify-write per phase
+    // would sit on the critical path of every grid barrier)
+    long long *tim_work = (long long *)(smem_raw + SM_TIM), *tim_sync = tim_work + T_COUNT;
+    if (threadIdx.x == 0) {
+        *my_spmv = 0;
+        for (int i = 0; i < 2 * T_COUNT; ++i) tim_work[i] = 0;
+    }
 
     int mode = -1;                                        // -1: first trip (x = 1)
     for (;;) {
@@ -995,21 +1103,21 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
             {
                 double r[2];
                 const int ids[2] = {PA, PB};
-                reduce_parts<2, 0>(A.part, nc, ids, r, s_red);
+                KR_REDUCE((reduce_parts<2, 0>(A.part, nc, ids, r, s_red)));
                 KR_SCALAR(KRS_ALPHA, r);
             }
             KR_PHASE(T_STEP, true, phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red));
             {
                 double r[5];
                 const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
-                reduce_parts<1, 4>(A.part, nc, ids, r, s_red);
+                KR_REDUCE((reduce_parts<1, 4>(A.part, nc, ids, r, s_red)));
                 KR_SCALAR(KRS_DECIDE, r);
             }
         } else {
             KR_PHASE(T_RESID, true, phase_resid(A, s_red));
             double r[1];
             const int ids[1] = {PA};
-            reduce_parts<1, 0>(A.part, nc, ids, r, s_red);
+            KR_REDUCE((reduce_parts<1, 0>(A.part, nc, ids, r, s_red)));
             KR_SCALAR(mode < 0 ? KRS_OUTER_FIRST : KRS_OUTER, r);
         }
         mode = S.state;
@@ -1019,6 +1127,10 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
     if (threadIdx.x == 0) A.cta_spmv[blockIdx.x] = *my_spmv;
     if (timing) {
         *A.ctl = S;
+        for (int i = 0; i < T_COUNT; ++i) {
+            A.timers->work[i] += tim_work[i];
+            A.timers->sync[i] += tim_sync[i];
+        }
         A.timers->total = clock64() - t_begin;
         if (A.n_rank > 1) *A.epoch = epoch;
     }

@@ -238,7 +238,7 @@ def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000, pool=None,
         rc = lib.b3c_kr_run(csr.n, csr.nnz, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), float(tol),
                             float(delta), float(Delta), int(max_iter), 0, _ptr(x), _ptr(ws), ws.numel(), info,
                             _stream())
-    names = ('init', 'spmv', 'fix', 'resid', 'dir', 'w', 'step', 'update', 'scalar')
+    names = ('init', 'spmv', 'reduce', 'resid', 'dir', 'w', 'step', 'update', 'scalar')
     out = dict(n_iter=int(info[0]), zero_diag=int(info[1]), outer=int(info[2]), n_spmv=int(info[3]),
                grid=int(info[4]), cycles=int(info[5]),
                work_cycles={k: int(info[6 + i]) for i, k in enumerate(names)},

@@ -389,7 +389,7 @@ class CudaEngine(object):
         st = dict(state=0, status=0, n_iter=int(info[0]), zero_diag=int(info[1]), outer=int(info[2]),
                   n_spmv=int(info[3]), kernel_us=int(info[27]), slabs=int(info[24]), nnz_stream=int(info[25]),
                   cycles=int(info[5]))
-        names = ('init', 'spmv', 'fix', 'resid', 'dir', 'w', 'step', 'update', 'scalar')
+        names = ('init', 'spmv', 'reduce', 'resid', 'dir', 'w', 'step', 'update', 'scalar')
         st['work_cycles'] = {k: int(info[6 + i]) for i, k in enumerate(names)}
         st['sync_cycles'] = {k: int(info[15 + i]) for i, k in enumerate(names)}
         if rc == -6:

@@ -11,8 +11,9 @@
  *                     parser; the parser is the reference's sequential state machine.
  *   b3c_edges_write   edge arrays -> the text file nx.write_edgelist(g, path, data=['weight'],
  *                     delimiter=' ') produces (cluster.py:139-151): one "u v weight" line per
- *                     undirected edge, weight printed as the shortest round-trip decimal in
- *                     Python's float repr layout.  Formatted on a pool of threads.
+ *                     undirected edge, weight printed as Python's str(float) prints it (Python 3: the
+ *                     shortest round-trip decimal; Python 2.7: 12 significant digits).  Formatted on a
+ *                     pool of threads.
  *
  * All pointers are HOST pointers.  Functions return 0 (or a non-negative count) on success and a
  * negative b3c_io_status on failure; b3c_io_last_error() returns a thread-local message.
@@ -85,11 +86,22 @@ int64_t b3c_bam_read_pairs(b3c_bam *bam, uint64_t *h_records, int64_t capacity);
  * h_stats[7] uncompressed bytes produced */
 int b3c_bam_stats(const b3c_bam *bam, int64_t *h_stats, int32_t n_stats);
 
-/* Write `n_edges` lines "u<sep>v<sep>weight\n" to `path` (truncating).  Returns bytes written. */
+/* How a weight is printed.  networkx prints it with str(): the shortest round-trip decimal on Python 3
+ * (== repr), '%.12g' plus '.0' on integer-looking values on the Python 2.7 the reference pins. */
+typedef enum {
+    B3C_FLOAT_REPR = 0,       /* Python 3 str(float) / repr(float)                               */
+    B3C_FLOAT_STR12 = 1       /* Python 2.7 str(float): 12 significant digits                    */
+} b3c_float_style;
+
+/* Write `n_edges` lines "u<sep>v<sep>weight\n" to `path` (truncating).  Returns bytes written.
+ * b3c_edges_write prints B3C_FLOAT_REPR. */
 int64_t b3c_edges_write(const char *path, const int32_t *h_u, const int32_t *h_v, const double *h_w,
                         int64_t n_edges, char sep, int32_t n_threads);
-/* Format one weight as Python's repr(float) would; returns the length (buffer of >= 32 bytes). */
+int64_t b3c_edges_write_fmt(const char *path, const int32_t *h_u, const int32_t *h_v, const double *h_w,
+                            int64_t n_edges, char sep, int32_t float_style, int32_t n_threads);
+/* Format one weight; returns the length (buffer of >= 32 bytes, NUL terminated). */
 int32_t b3c_format_weight(double w, char *h_buf, int32_t capacity);
+int32_t b3c_format_weight_fmt(double w, int32_t float_style, char *h_buf, int32_t capacity);
 
 #ifdef __cplusplus
 }
