@@ -69,12 +69,16 @@ def to_graph(contact_map, norm=True, bisto=False, scale=False, extern_ids=False,
     return g
 
 
-def write_edges(u, v, w, parent_dir, base_name='cm_graph', sep=' '):
+def write_edges(u, v, w, parent_dir, base_name='cm_graph', sep=' ', py2_str=False, threads=0):
     """
     The file nx.write_edgelist(g, path, data=['weight'], delimiter=' ') produces (cluster.py:139-151):
-    one 'u v weight' line per undirected edge, weight formatted as Python repr(float).
+    one 'u v weight' line per undirected edge.  networkx prints the weight with str(): repr(float) on
+    Python 3 (the default here); `py2_str=True` gives what the Python 2.7 the reference pins prints
+    ('%.12g', '.0' appended to integer-looking values).  Written by the native writer of libbin3c_io.so
+    (include/bin3c_io.h: b3c_edges_write_fmt), formatted on a pool of threads.
     """
+    from . import bam_io
     edge_file = os.path.join(parent_dir, '{}.edges'.format(base_name))
-    with open(edge_file, 'w') as out:
-        out.writelines('{}{}{}{}{}\n'.format(a, sep, b, sep, repr(c)) for a, b, c in zip(u.tolist(), v.tolist(), w.tolist()))
+    bam_io.write_edges(u, v, w, edge_file, sep=sep,
+                       float_style=bam_io.FLOAT_STR12 if py2_str else bam_io.FLOAT_REPR, threads=threads)
     return edge_file

@@ -1,6 +1,8 @@
 """
-Build libbin3c_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
-    python -m bin3c_b200.csrc.build [--force]
+Build the two in-tree libraries:
+  libbin3c_b200.so  the device path, nvcc for sm_100a (cross-compiles without a GPU)
+  libbin3c_io.so    the host-side BAM pair reader and edge-list writer, g++ + zlib + pthreads
+    python -m bin3c_b200.csrc.build [--force] [-v]
 """
 import os
 import subprocess
@@ -13,6 +15,23 @@ SOURCES = ['core.cu', 'accum.cu', 'rowops.cu', 'kr.cu']
 HEADERS = ['common.cuh', os.path.join('..', '..', 'include', 'bin3c_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--shared']
+
+
+IO_LIB = os.path.join(PKG, 'libbin3c_io.so')
+IO_SOURCES = ['io_bam.cpp', 'io_edges.cpp']
+IO_HEADERS = ['io_common.h', os.path.join('..', '..', 'include', 'bin3c_io.h')]
+IO_FLAGS = ['-O2', '-std=c++17', '-Wall', '-fPIC', '-shared', '-pthread']
+
+
+def build_io(force=False):
+    deps = [os.path.join(HERE, f) for f in IO_SOURCES + IO_HEADERS] + [os.path.abspath(__file__)]
+    if not force and os.path.exists(IO_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(IO_LIB) for d in deps):
+        return IO_LIB
+    cmd = [os.environ.get('CXX', 'g++')] + IO_FLAGS + [os.path.join(HERE, f) for f in IO_SOURCES] + ['-o', IO_LIB, '-lz']
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('g++ failed:\n' + res.stdout)
+    return IO_LIB
 
 
 def _nvcc():
@@ -31,6 +50,7 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    build_io(force)
     if not force and not stale():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \

@@ -537,7 +537,7 @@ int64_t b3c_bam_read_pairs(b3c_bam *h, uint64_t *h_records, int64_t capacity) {
     const int32_t n_refs = (int32_t)h->ref_names.size();
     int64_t n = 0;
     while (n < capacity) {
-        Aln a;
+        Aln a = {0, 0, 0, false, nullptr, 0};
         const int rc = next_alignment(h, &a);
         if (rc < 0) return rc;
         if (rc == 0) {

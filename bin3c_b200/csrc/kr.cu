@@ -220,7 +220,8 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
 
 // ---- deterministic block reductions ---------------------------------------------------------
 // NS sums followed by NM minima, reduced together: warp xor-tree, then the warp results in warp
-// order.  Every thread gets the results; the shape is fixed, so the value is reproducible.
+// order.  The results are valid in THREAD 0 only (every caller hands them to thread 0: a partial to
+// publish, or the loop scalars); the shape is fixed, so the value is reproducible.
 template <int NS, int NM>
 __device__ __forceinline__ void block_reduce(double (&v)[NS + NM], double *s_red) {
     constexpr int K = NS + NM;
@@ -234,16 +235,18 @@ __device__ __forceinline__ void block_reduce(double (&v)[NS + NM], double *s_red
         for (int i = 0; i < K; ++i) s_red[w * K + i] = v[i];
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-        double r = s_red[i];
+        for (int i = 0; i < K; ++i) {
+            double r = s_red[i];
 #pragma unroll
-        for (int j = 1; j < KR_WARPS; ++j) r = (i < NS) ? r + s_red[j * K + i] : fmin(r, s_red[j * K + i]);
-        v[i] = r;
+            for (int j = 1; j < KR_WARPS; ++j) r = (i < NS) ? r + s_red[j * K + i] : fmin(r, s_red[j * K + i]);
+            v[i] = r;
+        }
     }
 }
 
-// the same over per-chunk partial arrays: out[i] = reduce(part[ids[i]][0..nc)); identical in every CTA
+// the same over per-chunk partial arrays: out[i] = reduce(part[ids[i]][0..nc)) in thread 0; identical in every CTA
 template <int NS, int NM>
 __device__ __forceinline__ void reduce_parts(const double *part, int nc, const int (&ids)[NS + NM],
                                              double (&out)[NS + NM], double *s_red) {
@@ -1460,8 +1463,10 @@ __global__ void __launch_bounds__(KR_THREADS) k_krp_scalar(KRArgs A, int which) 
         const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
         reduce_parts<1, 4>(A.part, nc, ids, r, s_red);
     }
-    scalar_step(S, which, r);
-    if (threadIdx.x == 0) *A.ctl = S;
+    if (threadIdx.x == 0) {
+        scalar_step(S, which, r);
+        *A.ctl = S;
+    }
 }
 
 static std::mutex g_krp_mu;

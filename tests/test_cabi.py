@@ -1,6 +1,6 @@
 """
-CPU tests of the drop-in boundary: the shared library loads, exports every symbol that
-include/bin3c_b200.h declares, and the ctypes table covers exactly that set.  No compute
+CPU tests of the drop-in boundary: the shared libraries load, export every symbol that
+include/bin3c_b200.h and include/bin3c_io.h declare, and the ctypes tables cover exactly those sets.  No compute
 calls are made (no GPU here); argument validation that happens before any CUDA call is checked.
 """
 import ctypes
@@ -15,8 +15,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, 'include', 'bin3c_b200.h')
 
 
-def _declared():
-    src = open(HEADER).read()
+IO_HEADER = os.path.join(ROOT, 'include', 'bin3c_io.h')
+
+
+def _declared(header=HEADER):
+    src = open(header).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     return sorted(set(re.findall(r'\b(b3c_[a-z0-9_]+)\s*\(', src)))
 
@@ -39,6 +42,20 @@ def test_library_exports_every_declared_symbol(cabi):
 
 def test_ctypes_table_matches_header(cabi):
     assert sorted(cabi.SIGNATURES) == _declared()
+
+
+def test_io_library_exports_every_declared_symbol(cabi):
+    from bin3c_b200 import bam_io
+    names = _declared(IO_HEADER)
+    assert len(names) >= 15
+    lib = ctypes.CDLL(bam_io.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), 'missing export: ' + n
+    assert sorted(bam_io.SIGNATURES) == names
+    assert bam_io.lib.b3c_io_version() >= 100
+    # every include/*.h is covered by one of the two tables
+    assert sorted(f for f in os.listdir(os.path.join(ROOT, 'include')) if f.endswith('.h')) == \
+        ['bin3c_b200.h', 'bin3c_io.h']
 
 
 def test_no_torch_types_in_abi():

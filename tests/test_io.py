@@ -1,0 +1,255 @@
+"""
+Host IO library (include/bin3c_io.h): BAM -> packed pair records against the
+oracle's restatement of the reference pairing loop (contact_map.py:612-629, :720-766), and the edge-list
+writer against what nx.write_edgelist prints (cluster.py:139-151).  CPU only.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import bam_writer                                   # noqa: E402
+from bin3c_b200 import bam_io                       # noqa: E402
+from oracle import oracle                           # noqa: E402
+
+
+def random_alignments(rng, n_refs, n_templates, weird=True):
+    """A name-sorted alignment stream with everything the pairing loop looks at."""
+    alns = []
+    for t in range(n_templates):
+        name = 'read{:07d}'.format(t) if rng.random() < 0.9 else 'r{}'.format(t)
+        kind = rng.random()
+        n_rec = 2 if kind < 0.75 else rng.choice([1, 1, 3, 4])
+        for k in range(n_rec):
+            flag = 0x1 | (0x40 if k % 2 == 0 else 0x80)
+            if rng.random() < 0.5:
+                flag |= 0x10
+            if rng.random() < 0.6:
+                flag |= 0x2
+            if weird and rng.random() < 0.08:
+                flag |= rng.choice([0x4, 0x100, 0x800])
+            tid = rng.randrange(n_refs)
+            if weird and rng.random() < 0.01:
+                tid = n_refs + 3                               # out of the header's table
+            if rng.random() < 0.1:
+                cigar = []
+            else:
+                m = rng.randrange(1, 150)
+                cigar = [(0, m)]
+                if rng.random() < 0.3:
+                    cigar = [(4, rng.randrange(1, 30))] + cigar
+                if rng.random() < 0.3:
+                    cigar = cigar + [(4, rng.randrange(1, 30))]
+            alns.append(dict(name=name, flag=flag, tid=tid, pos=rng.randrange(0, 5000), mapq=rng.randrange(0, 61),
+                             cigar=cigar))
+    return alns
+
+
+def lut_for(lengths, min_len):
+    keep = np.asarray(lengths) >= min_len
+    return np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+
+
+@pytest.mark.parametrize('block_bytes,threads', [(65280, 0), (997, 3), (64, 1)])
+@pytest.mark.parametrize('mode', ['mapq', 'strong', 'insert'])
+def test_bam_pairs_match_oracle(tmp_path, block_bytes, threads, mode):
+    rng = random.Random(block_bytes * 7 + len(mode))
+    n_refs = 40
+    refs = ['contig_{}'.format(i) for i in range(n_refs)]
+    lengths = [rng.choice([300, 800, 1500, 20000]) for _ in range(n_refs)]
+    alns = random_alignments(rng, n_refs, 3000 if block_bytes > 100 else 300)
+    path = str(tmp_path / 'x.bam')
+    bam_writer.write_bam(path, refs, lengths, alns, block_bytes=block_bytes)
+    kw = dict(min_mapq=30)
+    if mode == 'strong':
+        kw['strong'] = 40
+    lut = None
+    if mode == 'insert':
+        kw['min_insert'] = 1200
+        lut = lut_for(lengths, 1000)
+    want, st = oracle.pair_alignments(alns, n_refs, idx_of=lut, **kw)
+    with bam_io.BamPairReader(path, threads=threads) as bam:
+        assert bam.references == refs
+        assert bam.lengths.tolist() == lengths
+        assert '@HD' in bam.header_text and 'SO:queryname' in bam.header_text
+        bam.set_filter(tid2idx=lut, **kw)
+        parts = []
+        while True:                                            # odd chunk size: records continue across calls
+            r = bam.read_pairs(701)
+            if len(r) == 0:
+                break
+            parts.append(r.copy())
+        got = np.concatenate(parts) if parts else np.empty(0, np.uint64)
+        stats = bam.stats()
+    assert np.array_equal(got, want)
+    for k in ('alignments', 'informative', 'pairs', 'short_insert', 'unpaired'):
+        assert stats[k] == st[k], k
+    assert stats['uncompressed_bytes'] > 0 and stats['bgzf_blocks'] >= 2
+    if mode == 'insert':
+        assert st['short_insert'] > 0
+
+
+def test_bam_large_multibatch(tmp_path):
+    """More than one batch of BGZF blocks (256 blocks each) and many threads."""
+    rng = random.Random(7)
+    n_refs = 500
+    refs = ['c{}'.format(i) for i in range(n_refs)]
+    lengths = [1000 + i for i in range(n_refs)]
+    alns = random_alignments(rng, n_refs, 60000, weird=True)
+    path = str(tmp_path / 'big.bam')
+    bam_writer.write_bam(path, refs, lengths, alns, block_bytes=8000, level=1)
+    want, st = oracle.pair_alignments(alns, n_refs, min_mapq=20)
+    with bam_io.BamPairReader(path, threads=8) as bam:
+        bam.set_filter(min_mapq=20)
+        got = bam.read_all(chunk=10000)
+        stats = bam.stats()
+    assert stats['bgzf_blocks'] > 600
+    assert np.array_equal(got, want)
+    assert stats['pairs'] == st['pairs'] and stats['unpaired'] == st['unpaired']
+
+
+def test_pair_records_from_bam_feeds_the_oracle_path(tmp_path):
+    """BAM -> PairRecords -> the same (tid_i, tid_j, pass) arrays the accumulation oracle takes."""
+    rng = random.Random(11)
+    n_refs = 30
+    refs = ['s{}'.format(i) for i in range(n_refs)]
+    lengths = [rng.choice([500, 5000]) for _ in range(n_refs)]
+    alns = random_alignments(rng, n_refs, 2000, weird=False)
+    path = str(tmp_path / 'p.bam')
+    bam_writer.write_bam(path, refs, lengths, alns)
+    pr, stats = bam_io.pair_records_from_bam(path, min_mapq=10)
+    assert pr.references == refs and pr.lengths.tolist() == lengths
+    rec = pr.records
+    ti = (rec & np.uint64(0x7fffffff)).astype(np.int64)
+    tj = ((rec >> np.uint64(32)) & np.uint64(0x7fffffff)).astype(np.int64)
+    ok = ((rec >> np.uint64(31)) & np.uint64(1)).astype(bool)
+    lut = lut_for(lengths, 1000)
+    n_seq = int((lut >= 0).sum())
+    want, _ = oracle.pair_alignments(alns, n_refs, min_mapq=10)
+    assert np.array_equal(rec, want) and stats['pairs'] == len(rec)
+    # the records drive the accumulation oracle exactly as records from the synthetic generator do
+    dok, counts = oracle.bin_pairs_loop(ti, tj, ok, {t: int(i) for t, i in enumerate(lut) if i >= 0}, n_seq)
+    assert counts['accepted'] > 100
+    assert counts['accepted'] + counts['ref_excluded'] + counts['poor_match'] == len(rec)
+    assert sum(dok.values()) == counts['accepted']
+
+
+def test_bam_errors(tmp_path):
+    refs, lengths = ['a', 'b'], [1000, 2000]
+    alns = [dict(name='q', flag=0x41, tid=0, pos=1, mapq=60, cigar=[(0, 50)]),
+            dict(name='q', flag=0x81, tid=1, pos=9, mapq=60, cigar=[(0, 50)])]
+    p1 = str(tmp_path / 'coord.bam')
+    bam_writer.write_bam(p1, refs, lengths, alns, sort_order='coordinate')
+    with pytest.raises(IOError, match='sorted by read name'):
+        bam_io.BamPairReader(p1)
+    with bam_io.BamPairReader(p1, require_queryname=False) as bam:       # the check is the caller's choice
+        assert len(bam.read_all()) == 1
+    p2 = str(tmp_path / 'nohd.bam')
+    bam_writer.write_bam(p2, refs, lengths, alns, hd=False)
+    with pytest.raises(IOError):
+        bam_io.BamPairReader(p2)
+    with pytest.raises(IOError):
+        bam_io.BamPairReader(str(tmp_path / 'missing.bam'))
+    p3 = str(tmp_path / 'garbage.bam')
+    with open(p3, 'wb') as out:
+        out.write(b'this is not a BGZF file at all' * 10)
+    with pytest.raises(ValueError):
+        bam_io.BamPairReader(p3)
+    # truncated in the middle of the alignment section
+    p4 = str(tmp_path / 'full.bam')
+    many = []
+    for t in range(500):
+        many += [dict(name='t{}'.format(t), flag=0x41, tid=0, pos=1, mapq=60, cigar=[(0, 50)]),
+                 dict(name='t{}'.format(t), flag=0x81, tid=1, pos=9, mapq=60, cigar=[(0, 50)])]
+    bam_writer.write_bam(p4, refs, lengths, many, block_bytes=4096)
+    raw = open(p4, 'rb').read()
+    p5 = str(tmp_path / 'trunc.bam')
+    with open(p5, 'wb') as out:
+        out.write(raw[:len(raw) * 2 // 3])
+    with pytest.raises(ValueError):
+        with bam_io.BamPairReader(p5) as bam:
+            bam.read_all()
+    # a flipped payload byte fails the CRC / inflate
+    p6 = str(tmp_path / 'corrupt.bam')
+    bad = bytearray(raw)
+    bad[len(bad) // 2] ^= 0x55
+    with open(p6, 'wb') as out:
+        out.write(bytes(bad))
+    with pytest.raises(ValueError):
+        with bam_io.BamPairReader(p6) as bam:
+            bam.read_all()
+    # empty alignment section, no EOF marker
+    p7 = str(tmp_path / 'empty.bam')
+    bam_writer.write_bam(p7, refs, lengths, [], eof_marker=False)
+    with bam_io.BamPairReader(p7) as bam:
+        assert len(bam.read_all()) == 0 and bam.stats()['alignments'] == 0
+    # min_insert without the index table
+    with bam_io.BamPairReader(p4) as bam:
+        with pytest.raises(AssertionError):
+            bam.set_filter(min_insert=100)
+        bam.read_pairs(10)
+        with pytest.raises(AssertionError):
+            bam.set_filter(min_mapq=5)                                   # too late
+
+
+WEIGHTS = [1.0, 0.1, 1.0 / 3.0, 2.0 / 3.0, 1e-5, 1.5e-5, 9.999e-5, 0.0001, 0.00012345678901234567, 1e15, 1e16,
+           123456789012345678.0, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 0.0, -2.5, 100.0,
+           0.30000000000000004, 1e22, 1e-7, 0.999999999999, 0.9999999999999999, 0.5, 1e12, 1e13, 999999999999.5,
+           123456789012.0, 1234567890123.0, 7.0e-10, float('inf'), float('-inf'), float('nan'), -0.0]
+
+
+def test_format_weight_matches_python():
+    rng = np.random.default_rng(3)
+    ws = list(WEIGHTS) + rng.random(2000).tolist() + (10.0 ** rng.uniform(-12, 20, 2000)).tolist() + \
+        np.frombuffer(rng.bytes(8 * 2000), dtype=np.float64).tolist()
+    for w in ws:
+        assert bam_io.format_weight(w) == repr(float(w)), w
+        t = '%.12g' % w
+        if not ('.' in t or 'e' in t or 'n' in t):
+            t += '.0'
+        assert bam_io.format_weight(w, bam_io.FLOAT_STR12) == t, w
+
+
+@pytest.mark.parametrize('n,threads', [(0, 0), (1, 1), (1000, 2), (300000, 0), (300000, 5)])
+def test_write_edges_matches_networkx_text(tmp_path, n, threads):
+    rng = np.random.default_rng(n + 1)
+    u = rng.integers(0, 50000, n).astype(np.int32)
+    v = rng.integers(0, 50000, n).astype(np.int32)
+    w = rng.random(n) * 10.0 ** rng.integers(-8, 1, n)
+    if n:
+        w[0] = 1.0
+    for style, py2 in ((bam_io.FLOAT_REPR, False), (bam_io.FLOAT_STR12, True)):
+        path = str(tmp_path / 'e{}.edges'.format(style))
+        nbytes = bam_io.write_edges(u, v, w, path, float_style=style, threads=threads)
+        text = open(path).read()
+        assert nbytes == len(text)
+        assert text == oracle.edge_lines(u, v, w, py2=py2)
+    if n == 1000:
+        nx = pytest.importorskip('networkx')
+        g = nx.Graph()
+        uu, idx = np.unique(np.stack([np.minimum(u, v), np.maximum(u, v)]), axis=1, return_index=True)
+        for a, b, c in zip(uu[0], uu[1], w[idx]):
+            g.add_edge(int(a), int(b), weight=float(c))
+        p_nx, p_b3 = str(tmp_path / 'nx.edges'), str(tmp_path / 'b3.edges')
+        nx.write_edgelist(g, p_nx, data=['weight'], delimiter=' ')
+        e = list(g.edges(data='weight'))
+        bam_io.write_edges([a for a, _, _ in e], [b for _, b, _ in e], [c for _, _, c in e], p_b3)
+        assert open(p_nx).read() == open(p_b3).read()
+
+
+def test_cluster_write_edges_uses_the_native_writer(tmp_path):
+    from bin3c_b200 import cluster
+    u = np.array([0, 0, 1], dtype=np.int32)
+    v = np.array([0, 2, 2], dtype=np.int32)
+    w = np.array([1.0, 0.25, 1.0 / 3.0])
+    f = cluster.write_edges(u, v, w, str(tmp_path))
+    assert os.path.basename(f) == 'cm_graph.edges'
+    assert open(f).read() == '0 0 1.0\n0 2 0.25\n1 2 0.3333333333333333\n'
+    f = cluster.write_edges(u, v, w, str(tmp_path), base_name='py2', py2_str=True)
+    assert open(f).read() == '0 0 1.0\n0 2 0.25\n1 2 0.333333333333\n'
