@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the pair count (debugging only)')
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-microbench', action='store_true', help='skip the C5 KR SpMV microbench (HBM-resident matrix)')
     return ap.parse_args()
 
 
@@ -180,6 +181,32 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def spmv_microbench(dev, torch, peak, rows=250_000, nnz=100_000_000, reps=20):
+    """BASELINE config 5 (one point of it): the KR SpMV kernel alone on a random block-structured symmetric CSR
+    that does not fit in L2, GB/s by SURVEY 8d's 12*nnz + 24*N formula against the measured HBM peak."""
+    from bin3c_b200 import synth
+    indptr, indices, data = synth.make_block_csr(rows, nnz, seed=1005)
+    csr = dev.DeviceCSR(rows, dev.to_device(indptr), dev.to_device(indices), dev.to_device(data))
+    u = dev.to_device(np.random.default_rng(0).uniform(0.5, 1.5, csr.n))
+    ws = torch.empty(dev.lib.b3c_kr_workspace_bytes(csr.n, csr.nnz), dtype=torch.uint8, device='cuda')
+    y = dev.spmv(csr, u, ws=ws, prepared=False)
+    for _ in range(3):
+        dev.spmv(csr, u, y=y, ws=ws, prepared=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dev.spmv(csr, u, y=y, ws=ws, prepared=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = 12 * csr.nnz + 24 * csr.n
+    return {'workload': 'C5 point: block-structured symmetric CSR, {} rows, {} nnz (seed 1005), {} MB by formula'.format(
+                csr.n, csr.nnz, nbytes // 1000000),
+            'kernels': 'k_spmv + k_spmv_collect (the SpMV phase of k_kr_persistent as a stand-alone launch)',
+            'ms_per_spmv': ms, 'gbs': nbytes / ms / 1e6, 'peak': peak, 'frac': nbytes / ms / 1e6 / peak, 'reps': reps}
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -296,6 +323,11 @@ def main():
                          'threads, SciPy KR single-threaded; box has {} cores'.format(sample, t, cpu_threads(),
                                                                                      os.cpu_count())}
 
+    # ---- C5 flavour: KR's SpMV on a block-structured matrix too large for L2 (HBM-bound) -----------------------
+    micro = None
+    if not args.no_microbench and args.scale == 1.0:
+        micro = spmv_microbench(dev, torch, peak)
+
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -321,6 +353,7 @@ def main():
                                  ((kr['work_cycles']['spmv'] + kr['sync_cycles']['spmv']) /
                                   ((clocks.get('sm_mhz') or 1965.0) * 1e6))},
         'pair_counts': {k: info[k] for k in ('accepted', 'ref_excluded', 'poor_match')},
+        'kr_spmv_microbench': micro,
     }
     print(json.dumps(line))
 

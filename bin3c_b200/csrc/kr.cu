@@ -23,7 +23,7 @@
 // does not depend on the row lengths (heavy-tailed contig rows, empty rows).  A segment that
 // crosses a CTA's range is finished by the vector phase that consumes it, from one boundary record
 // per CTA.  Matrices wider than SLAB_S_MAX slabs use the same stream with 32-bit columns and gather
-// u through L1/L2 ("gather form").
+// u through L1/L2 ("gather form"), unless their (row, slab) cells hold SLAB_DENSE_CELL entries or more on average.
 //
 // Reductions (dot products, min, max) use fixed 1024-row chunks with a fixed tree inside the
 // chunk and an in-order sum over chunks: the value does not depend on the grid size or on how
@@ -46,7 +46,9 @@ constexpr int CHUNK = 1024;                          // rows per reduction chunk
 constexpr int CHUNK_RPT = CHUNK / KR_THREADS;
 constexpr int RED_MAX = 8;                           // values reduced together by one block reduction
 constexpr int SLAB_W_MAX = 28672;                    // fp64 entries of u held in shared memory (15-bit columns)
-constexpr int SLAB_S_MAX = 16;                       // more slabs than this: gather form
+constexpr int SLAB_S_MAX = 16;                       // more slabs than this: gather form (default; B3C_OPT_KR_MAX_SLABS)
+constexpr int SLAB_S_CAP = 48;                       // the most slabs the tables are sized for
+constexpr int SLAB_DENSE_CELL = 6;                   // mean entries per (row, slab) cell from which slabs beyond SLAB_S_MAX pay
 constexpr int KR_MAX_RANKS = 8;                      // GPUs of one node in peer mode
 static_assert(KR_WARPS <= 32 && SLAB_W_MAX <= 65536, "warp records are stitched by one warp; 16-bit columns");
 
@@ -82,7 +84,7 @@ constexpr int SM_CTL = SM_REC + 2 * (int)sizeof(WarpRecs);
 constexpr int SM_STATE = SM_CTL + ((int)sizeof(KRScalars) + 15) / 16 * 16;
 constexpr int SM_TIM = SM_STATE + 32;           // SpmvState (16 B) + the CTA's SpMV cycle counter, then the phase timers
 constexpr int SM_SLAB = SM_TIM + 2 * 9 * 8;     // work[T_COUNT], sync[T_COUNT]: accumulated in shared memory, written out once
-constexpr int SM_MBAR = (SM_SLAB + (SLAB_S_MAX + 2) * 4 + 7) / 8 * 8;
+constexpr int SM_MBAR = (SM_SLAB + (SLAB_S_CAP + 2) * 4 + 7) / 8 * 8;
 constexpr int SM_U = (SM_MBAR + 8 + 127) / 128 * 128;
 constexpr int SM_BYTES_GATHER = SM_U;
 constexpr int SM_BYTES_SLAB = SM_U + SLAB_W_MAX * 8;
@@ -617,13 +619,20 @@ __device__ __forceinline__ void boundary_fix(const KRArgs &A, int c) {
     __syncthreads();
 }
 
-// (A u)[r]: the segment sums of global row r, added in slab order
+// (A u)[r]: the segment sums of global row r, added in slab order (loads batched eight slabs at a time)
 __device__ __forceinline__ double row_q(const KRArgs &A, int64_t r) {
     const int64_t lr = r - A.row_lo;
     double s = 0.0;
-    for (int k = 0; k < A.S; ++k) {
-        const int o = __ldg(A.seg_of + (int64_t)k * A.npad + lr);
-        if (o >= 0) s = __dadd_rn(s, __ldcg(A.qs + o));
+    for (int k0 = 0; k0 < A.S; k0 += 8) {
+        int o[8];
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = k0 + k < A.S ? __ldg(A.seg_of + (int64_t)(k0 + k) * A.npad + lr) : -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = o[k] >= 0 ? __ldcg(A.qs + o[k]) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (o[k] >= 0) s = __dadd_rn(s, t[k]);
     }
     return s;
 }
@@ -1490,8 +1499,14 @@ struct KRLayout {
 static KRLayout kr_layout(int32_t n, int64_t nnz) {
     KRLayout L;
     Carver c;
+    // Slab form whenever the matrix is at most B3C_OPT_KR_MAX_SLABS (16) slabs wide.  Wider matrices cut every row
+    // into more (row, slab) segments, each padded to whole 8-entry pieces: that pays only while the segments are
+    // long enough.  Measured on 1 M rows / 35 slabs (profiles/r1_spmv_sizes.md): 2.7 entries per cell -> gather
+    // form 0.42 ms, slab form 0.69 ms; 9.2 per cell -> gather 1.37 ms, slab 1.06 ms; break-even near 5.
     const int64_t s_need = ceil_div(n, g_slab_w_max.load());
-    L.slab = s_need <= g_slab_s_max.load() ? 1 : 0;
+    const int s_max = g_slab_s_max.load();
+    const bool dense_cells = s_max >= SLAB_S_MAX && s_need <= SLAB_S_CAP && nnz >= SLAB_DENSE_CELL * (int64_t)n * s_need;
+    L.slab = (s_need <= s_max || dense_cells) ? 1 : 0;
     L.S = L.slab ? (int32_t)s_need : 1;
     L.W = L.slab ? (int32_t)align_up(ceil_div(n, L.S), 2) : n;
     const int64_t npad_max = align_up(n, CHUNK);
@@ -1514,7 +1529,7 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     L.o_vp = c.take((L.nv_max + 1) * 8);
     L.o_ord = c.take((L.nv_max + 1) * 8);
     L.o_scan = c.take(scan_tmp_elems(L.nv_max) * 8);
-    L.o_slab_t0 = c.take((SLAB_S_MAX + 2) * 4);
+    L.o_slab_t0 = c.take((SLAB_S_CAP + 2) * 4);
     L.o_sval = c.take(L.nnzv_max * 8);
     L.o_scol = c.take(L.nnzv_max * (L.slab ? 2 : 4));
     L.o_sflag = c.take(L.nnzv_max / 8 + 64);
@@ -1725,7 +1740,7 @@ int b3c_set_option(int32_t key, int64_t value) {
             g_slab_w_max.store((int)value & ~1);
             return B3C_OK;
         case B3C_OPT_KR_MAX_SLABS:
-            B3C_REQUIRE(value >= 0 && value <= SLAB_S_MAX, "slab count cap must be in [0, %d]", SLAB_S_MAX);
+            B3C_REQUIRE(value >= 0 && value <= SLAB_S_CAP, "slab count cap must be in [0, %d]", SLAB_S_CAP);
             g_slab_s_max.store((int)value);
             return B3C_OK;
         case B3C_OPT_KR_FLAGS:

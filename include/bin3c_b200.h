@@ -158,10 +158,11 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  *   b3c_spmv      y = A.u with the same kernel KR uses (microbench, config C5).
  * ------------------------------------------------------------------------------------ */
 /* Tuning / test hooks.  KR's SpMV gathers its operand vector from shared memory, one column slab at
- * a time (see csrc/kr.cu); B3C_OPT_KR_SLAB_WIDTH caps the slab width (default 26112 columns, the most
- * that fits in a CTA's shared memory), B3C_OPT_KR_MAX_SLABS the slab count (default 16; wider matrices,
- * or 0, select the form that gathers through L1/L2).  Results are identical up to fp64 summation
- * order.  Workspace sizes depend on these, so set them before the *_workspace_bytes() query.
+ * a time (see csrc/kr.cu); B3C_OPT_KR_SLAB_WIDTH caps the slab width (default 28672 columns, the most
+ * that fits in a CTA's shared memory), B3C_OPT_KR_MAX_SLABS the slab count (default 16, at most 48; wider
+ * matrices, or 0, select the form that gathers through L1/L2 -- except that at the default, matrices of up
+ * to 48 slabs whose (row, slab) cells hold 6 or more entries on average stay in the slab form).  Results are
+ * identical up to fp64 summation order.  Workspace sizes depend on these, so set them before the *_workspace_bytes() query.
  * B3C_OPT_KR_FLAGS (default 7) is a bit set for A/B measurements: 1 = order every lane's run of the
  * stream by shared-memory bank, 2 = align the SpMV CTA ranges with the slabs, 4 = single-word grid
  * barrier (release-add + acquire-poll). */

@@ -283,7 +283,7 @@ class _kr_options(object):
             self.dev.check(self.dev.lib.b3c_set_option(2, self.max_slabs))
 
     def __exit__(self, *a):
-        self.dev.check(self.dev.lib.b3c_set_option(1, 26112))
+        self.dev.check(self.dev.lib.b3c_set_option(1, 28672))
         self.dev.check(self.dev.lib.b3c_set_option(2, 16))
 
 
@@ -302,8 +302,8 @@ def _sym_matrix(n, nnz_row, seed, zero_diag_frac=0.1):
 
 
 # slab shapes: (width cap, slab cap).  None = defaults; (1000, 16) forces several narrow slabs on small matrices;
-# (None, 0) forces the form that gathers through L1/L2
-SLAB_SHAPES = [(None, None), (1000, 16), (334, 16), (None, 0)]
+# (126, 48) many narrow slabs (up to the table cap); (None, 0) forces the form that gathers through L1/L2
+SLAB_SHAPES = [(None, None), (1000, 16), (334, 16), (126, 48), (None, 0)]
 
 
 @pytest.mark.parametrize('shape', SLAB_SHAPES)
@@ -341,6 +341,19 @@ def test_kr_slab_shapes(dev, shape):
     assert info['slabs'] == (0 if shape[1] == 0 else -(-5000 // shape[0]))
     assert info['n_iter'] == res.n_iter
     assert info['zero_diag'] == res.n_zero_diag
+    assert _relerr(x.cpu().numpy(), res.x) <= REL_TOL
+
+
+@pytest.mark.parametrize('nnz_row,slabs', [(300, 40), (30, 0)])
+def test_kr_wide_matrix_form_follows_cell_density(dev, nnz_row, slabs):
+    """Beyond 16 slabs the slab form is kept only while the (row, slab) cells hold >= 6 entries on average."""
+    from oracle import oracle
+    m = _sym_matrix(5000, nnz_row, seed=29)
+    res = oracle.kr_scale_vector(m)
+    with _kr_options(dev, 126, None):                      # 40 slabs needed, slab cap left at its default
+        x, info = dev.kr_scale_vector(dev.DeviceCSR.from_scipy(m))
+    assert info['slabs'] == slabs
+    assert info['n_iter'] == res.n_iter
     assert _relerr(x.cpu().numpy(), res.x) <= REL_TOL
 
 
@@ -497,6 +510,69 @@ def test_medium_config_properties(dev):
     res = oracle.kr_scale_vector(a)
     assert kinfo['n_iter'] == res.n_iter
     assert _relerr(xx, res.x) <= REL_TOL
+
+
+def test_full_size_c2_properties(dev):
+    """
+    BASELINE config C2 at full size (50k contigs, 50M pairs), through properties that do not need the oracle's
+    minutes: the three counters and every row marginal against vectorised NumPy over the records (a checksum of
+    checksums), canonical + symmetric CSR, the bistochastic property of x, a sorted edge list with weights in
+    (0, 1] and max 1, and a second run that is bit-identical (idempotence).
+    """
+    import torch
+    from bin3c_b200 import synth
+    from bin3c_b200.pipeline import HotPath
+    com = synth.make_config('C2')
+    P, N = com.n_pairs, com.n_contigs
+    hp = HotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=P)
+    rec = dev.to_device(com.records)
+    r1 = hp.run(rec, fused=False)
+    n = int(r1['n_edges'])
+    first = [r1[k][:n].cpu().numpy().copy() for k in ('u', 'v', 'w')]
+    x = hp.x.cpu().numpy().copy()
+
+    # counters and marginals from the records themselves
+    ti, tj, ok = synth.unpack_pairs(com.records)
+    lut = com.tid2idx().astype(np.int64)
+    safe = lambda t: np.where(t < len(lut), lut[np.minimum(t, len(lut) - 1)], -1)
+    ii, jj = safe(ti.astype(np.int64)), safe(tj.astype(np.int64))
+    excl = (ii < 0) | (jj < 0)
+    poor = ~excl & ~ok.astype(bool)
+    acc = ~excl & ~poor
+    assert hp.acc_info['ref_excluded'] == int(excl.sum())
+    assert hp.acc_info['poor_match'] == int(poor.sum())
+    assert hp.acc_info['accepted'] == int(acc.sum())
+    a, b = ii[acc], jj[acc]
+    marg = np.bincount(a, minlength=N) + np.bincount(b, minlength=N) - np.bincount(a[a == b], minlength=N)
+    m = hp.seq_map.to_scipy_csr()
+    assert m.dtype == np.uint32 and m.has_sorted_indices
+    assert np.array_equal(np.asarray(m.sum(axis=1, dtype=np.int64)).ravel(), marg)
+    assert int(m.sum(dtype=np.int64)) == 2 * int(acc.sum()) - int((a == b).sum())      # map_weight (Q7)
+    assert (m != m.T).nnz == 0
+    assert np.all(np.diff(m.indptr) >= 0) and m.nnz == hp.acc_info['nnz_full']
+
+    # bistochastic on the working matrix (zero diagonals -> 1, Q2)
+    w = hp.normed.to_scipy_csr()
+    work = w + sp.diags((w.diagonal() == 0).astype(float))
+    assert np.max(np.abs(x * work.dot(x) - 1)) < 1e-4
+    assert hp.kr_info['n_iter'] < 100
+
+    # the edge list: upper triangle of the accepted sub-matrix, sorted, scaled by 1/max (Q8)
+    u, v, wts = first
+    assert np.all(u <= v) and np.all(np.diff(u.astype(np.int64) * N + v) > 0)
+    assert wts.max() == 1.0 and wts.min() > 0.0
+    mask = hp.mask.cpu().numpy().astype(bool)
+    assert int(r1['n_accepted']) == int(mask.sum()) and u.max() < mask.sum() and v.max() < mask.sum()
+    sub = sp.triu(m[mask][:, mask].tocsr(), k=0)
+    assert n == sub.nnz
+
+    # idempotence, and the fused form gives the same bits
+    for fused in (False, True):
+        r2 = hp.run(rec, fused=fused)
+        assert int(r2['n_edges']) == n
+        for k, want in zip(('u', 'v', 'w'), first):
+            assert np.array_equal(r2[k][:n].cpu().numpy(), want)
+        assert np.array_equal(hp.x.cpu().numpy(), x)
 
 
 def test_hotpath_host_records_match_device_records(dev):

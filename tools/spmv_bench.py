@@ -39,6 +39,8 @@ def main():
     ap.add_argument('--reps', type=int, default=20)
     ap.add_argument('--c2-scale', type=float, default=1.0)
     ap.add_argument('--skip-block', action='store_true')
+    ap.add_argument('--skip-c2', action='store_true')
+    ap.add_argument('--max-slabs', default='', help='comma list: B3C_OPT_KR_MAX_SLABS values to run the block matrix with')
     args = ap.parse_args()
     import torch
     import __graft_entry__
@@ -46,17 +48,25 @@ def main():
     from bin3c_b200 import device as dev, synth
     from bin3c_b200.pipeline import HotPath
     out = {}
-    com = synth.make_config('C2', scale=args.c2_scale)
-    hp = HotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=com.n_pairs)
-    hp.accumulate(dev.to_device(com.records))
-    hp.normalise()
-    out['c2_matrix'] = time_spmv(dev, torch, hp.normed, args.reps)
+    if not args.skip_c2:
+        com = synth.make_config('C2', scale=args.c2_scale)
+        hp = HotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=com.n_pairs)
+        hp.accumulate(dev.to_device(com.records))
+        hp.normalise()
+        out['c2_matrix'] = time_spmv(dev, torch, hp.normed, args.reps)
     if not args.skip_block:
         t0 = time.time()
         indptr, indices, data = synth.make_block_csr(args.rows, args.nnz, seed=1005)
         csr = dev.DeviceCSR(args.rows, dev.to_device(indptr), dev.to_device(indices), dev.to_device(data))
-        out['block_matrix'] = time_spmv(dev, torch, csr, args.reps)
-        out['block_matrix']['gen_s'] = round(time.time() - t0, 1)
+        gen_s = round(time.time() - t0, 1)
+        caps = [int(v) for v in args.max_slabs.split(',') if v] or [None]
+        for cap in caps:
+            if cap is not None:
+                dev.check(dev.lib.b3c_set_option(2, cap))
+            key = 'block_matrix' if cap is None else 'block_matrix_max_slabs_{}'.format(cap)
+            out[key] = time_spmv(dev, torch, csr, args.reps)
+            out[key]['gen_s'] = gen_s
+            out[key]['ws_mb'] = dev.lib.b3c_kr_workspace_bytes(csr.n, csr.nnz) / 1e6
     print(json.dumps(out))
 
 
