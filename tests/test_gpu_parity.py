@@ -560,7 +560,7 @@ def test_full_size_c2_properties(dev):
     # the edge list: upper triangle of the accepted sub-matrix, sorted, scaled by 1/max (Q8)
     u, v, wts = first
     assert np.all(u <= v) and np.all(np.diff(u.astype(np.int64) * N + v) > 0)
-    assert wts.max() == 1.0 and wts.min() > 0.0
+    assert 1.0 - 4e-16 <= wts.max() <= 1.0 and wts.min() > 0.0          # max * (1.0 / max), as the reference scales
     mask = hp.mask.cpu().numpy().astype(bool)
     assert int(r1['n_accepted']) == int(mask.sum()) and u.max() < mask.sum() and v.max() < mask.sum()
     sub = sp.triu(m[mask][:, mask].tocsr(), k=0)
