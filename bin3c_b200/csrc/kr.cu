@@ -350,15 +350,13 @@ __device__ __forceinline__ void piece_process(const KRArgs &A, const double *u, 
                                               bool first_piece, LaneRun &L) {
     const unsigned lane = lane_id();
     if (first_piece) {
-        const int pc = __popc(R.fw);
-        int inc = pc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(kFullMask, inc, o);
-            if ((int)lane >= o) inc += t;
-        }
-        L.lower = inc - pc;
-        L.total = __shfl_sync(kFullMask, inc, 31);
+        // segments start only at piece boundaries (seg_padded), so a lane's 16 entries carry at most two flags,
+        // bits 0 and 8: the prefix count over the lanes is two ballots instead of a shuffle scan
+        const unsigned f0 = __ballot_sync(kFullMask, (R.fw & 1u) != 0);
+        const unsigned f1 = __ballot_sync(kFullMask, (R.fw & 0x100u) != 0);
+        const unsigned lt = lanemask_lt();
+        L.lower = __popc(f0 & lt) + __popc(f1 & lt);
+        L.total = __popc(f0) + __popc(f1);
         L.seg0 = R.seg0;
         L.base = R.seg0 + L.lower;
         L.fw = R.fw;
