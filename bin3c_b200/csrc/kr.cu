@@ -140,8 +140,9 @@ struct KRArgs {
     unsigned *bar_count, *bar_gen;              // grid barrier of the persistent kernel (zeroed per run)
     int32_t opts;                               // KR_OPT_* bits (b3c_set_option)
     long long *cta_spmv;                        // [n_bnd] cycles every CTA spent inside its SpMV phases
+    unsigned long long *ll;                     // [P_COUNT][n_chunks][2] flagged words: partials exchanged without a barrier
 };
-enum { KR_OPT_BANK_ORDER = 1, KR_OPT_SLAB_ALIGN = 2, KR_OPT_FAST_BARRIER = 4 };
+enum { KR_OPT_BANK_ORDER = 1, KR_OPT_SLAB_ALIGN = 2, KR_OPT_FAST_BARRIER = 4, KR_OPT_LL_PARTIALS = 8 };
 
 // publish u[r] / a partial: to this rank and, in peer mode, straight into every other rank's copy
 __device__ __forceinline__ void put_u(const KRArgs &A, int64_t r, double v) {
@@ -151,13 +152,50 @@ __device__ __forceinline__ void put_u(const KRArgs &A, int64_t r, double v) {
 }
 // `loc`: the chunk belongs to this rank.  Without peers the other chunks get the identity (the host
 // driver all-reduces the arrays); with peers their owners write them.
-__device__ __forceinline__ void put_part(const KRArgs &A, int which, int c, double v, bool loc, double identity) {
+// `ll_epoch` != 0 (single GPU, KR_OPT_LL_PARTIALS): the partial is published as two flagged 8-byte words -- (low
+// half, epoch) and (high half, epoch) -- that a reader polls until both carry the epoch it expects.  An aligned
+// 8-byte store is single-copy atomic, so the value needs no fence and the phase no grid barrier: the phases that
+// only produce partials (resid, w, step) hand over through these words alone, because every vector they touch is
+// private to the thread that owns the row.
+__device__ __forceinline__ void put_part(const KRArgs &A, int which, int c, double v, bool loc, double identity,
+                                         unsigned ll_epoch = 0) {
     const int64_t i = (int64_t)which * A.n_chunks + c;
-    if (A.n_rank <= 1) {
+    if (ll_epoch) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v), e = (unsigned long long)ll_epoch << 32;
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.ll + 2 * i), "l"((b & 0xffffffffull) | e),
+                     "l"((b >> 32) | e)
+                     : "memory");
+    } else if (A.n_rank <= 1) {
         A.part[i] = loc ? v : identity;
     } else if (loc) {
         for (int g = 0; g < A.n_rank; ++g) A.xpart[g][i] = v;
     }
+}
+// The flagged words carry the data; WAITING for them is done on one counter polled by one thread per CTA (thousands
+// of threads polling the words themselves queue up in front of the writers at the L2 slices that hold them).  The
+// counter is only a hint -- its relaxed add is not ordered after the words -- so readers still check the epochs.
+__device__ __forceinline__ unsigned *ll_counter(const KRArgs &A) {
+    return (unsigned *)(A.ll + 2 * (int64_t)P_COUNT * A.n_chunks);
+}
+__device__ __forceinline__ void ll_arrive(const KRArgs &A) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ll_counter(A)) : "memory");
+}
+__device__ __forceinline__ void ll_wait(const KRArgs &A, unsigned target) {
+    if (threadIdx.x == 0) {
+        unsigned seen;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ll_counter(A)) : "memory");
+        } while ((int)(seen - target) < 0);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ double get_part_ll(const KRArgs &A, int which, int c, unsigned ll_epoch) {
+    const unsigned long long *p = A.ll + 2 * ((int64_t)which * A.n_chunks + c);
+    unsigned long long a, b;
+    do {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    } while ((unsigned)(a >> 32) != ll_epoch || (unsigned)(b >> 32) != ll_epoch);
+    return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
 }
 
 struct SpmvState {             // carried from tile to tile by the stitching warps
@@ -237,27 +275,37 @@ __device__ __forceinline__ void block_reduce(double (&v)[NS + NM], double *s_red
         for (int i = 0; i < K; ++i) s_red[w * K + i] = v[i];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // lane i folds value i over the warps, in warp order (the K chains run side by side), then hands it to thread 0
+        const int i = (int)lane_id() < K ? (int)lane_id() : 0;
+        const bool is_sum = i < NS;
+        double r = s_red[i];
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-            double r = s_red[i];
-#pragma unroll
-            for (int j = 1; j < KR_WARPS; ++j) r = (i < NS) ? r + s_red[j * K + i] : fmin(r, s_red[j * K + i]);
-            v[i] = r;
+        for (int j = 1; j < KR_WARPS; ++j) {
+            const double x = s_red[j * K + i];
+            const double a = r + x, m = fmin(r, x);
+            r = is_sum ? a : m;
         }
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = __shfl_sync(kFullMask, r, k);
     }
 }
 
-// the same over per-chunk partial arrays: out[i] = reduce(part[ids[i]][0..nc)) in thread 0; identical in every CTA
+// the same over per-chunk partial arrays: out[i] = reduce(part[ids[i]][0..nc)) in thread 0; identical in every CTA.
+// Bit i of `ll_mask` set: partial ids[i] comes through the flagged words of epoch `ll_epoch` (see put_part).
 template <int NS, int NM>
-__device__ __forceinline__ void reduce_parts(const double *part, int nc, const int (&ids)[NS + NM],
-                                             double (&out)[NS + NM], double *s_red) {
+__device__ __forceinline__ void reduce_parts(const KRArgs &A, int nc, const int (&ids)[NS + NM],
+                                             double (&out)[NS + NM], double *s_red, unsigned ll_mask = 0,
+                                             unsigned ll_epoch = 0) {
+    const double *part = A.part;
+    if (ll_mask) ll_wait(A, ll_epoch * (unsigned)nc);         // every chunk arrives once per hand-over
 #pragma unroll
     for (int i = 0; i < NS + NM; ++i) out[i] = (i < NS) ? 0.0 : (double)INFINITY;
     for (int j = threadIdx.x; j < nc; j += KR_THREADS) {
 #pragma unroll
         for (int i = 0; i < NS + NM; ++i) {
-            const double x = __ldcg(part + (int64_t)ids[i] * nc + j);
+            const double x = ((ll_mask >> i) & 1u) ? get_part_ll(A, ids[i], j, ll_epoch)
+                                                   : __ldcg(part + (int64_t)ids[i] * nc + j);
             out[i] = (i < NS) ? out[i] + x : fmin(out[i], x);
         }
     }
@@ -704,7 +752,7 @@ __device__ __forceinline__ void phase_init(const KRArgs &A) {
 }
 
 // v = x * (A x), rk = 1 - v, partial rk.rk           (sparse_utils.py:136-139, 196-199)
-__device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red) {
+__device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red, unsigned ll = 0) {
     KR_FOR_CHUNKS(c) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
@@ -731,7 +779,10 @@ __device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red) {
         }
         double r[1] = {acc};
         block_reduce<1, 0>(r, s_red);
-        if (threadIdx.x == 0) put_part(A, PA, c, r[0], loc, 0.0);
+        if (threadIdx.x == 0) {
+            put_part(A, PA, c, r[0], loc, 0.0, ll);
+            if (ll) ll_arrive(A);
+        }
     }
 }
 
@@ -780,7 +831,7 @@ __device__ __forceinline__ void phase_dir(const KRArgs &A, bool first, double be
 }
 
 // w = x * (A (x p)) + v * p, partial p.w              (sparse_utils.py:165-166)
-__device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red) {
+__device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red, unsigned ll = 0) {
     KR_FOR_CHUNKS(c) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
@@ -808,14 +859,17 @@ __device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red) {
         }
         double r[1] = {acc};
         block_reduce<1, 0>(r, s_red);
-        if (threadIdx.x == 0) put_part(A, PA, c, r[0], loc, 0.0);
+        if (threadIdx.x == 0) {
+            put_part(A, PA, c, r[0], loc, 0.0, ll);
+            if (ll) ll_arrive(A);
+        }
     }
 }
 
 // ap = alpha p, ynew = y + ap, min/max and both clamp factors, and -- speculatively, used only if
 // the step is accepted -- rk -= alpha w, Z = rk * v (Q1), partial rk.Z   (sparse_utils.py:167-190)
 __device__ __forceinline__ void phase_step(const KRArgs &A, double alpha, double delta, double Delta,
-                                           const double *ycur, double *ynew, double *s_red) {
+                                           const double *ycur, double *ynew, double *s_red, unsigned ll = 0) {
     KR_FOR_CHUNKS(c) {
         double rho = 0.0, mn = INFINITY, nmx = INFINITY, g1 = INFINITY, g2 = INFINITY;
         const bool loc = chunk_local(A, c);
@@ -854,11 +908,12 @@ __device__ __forceinline__ void phase_step(const KRArgs &A, double alpha, double
         double r[5] = {rho, mn, nmx, g1, g2};
         block_reduce<1, 4>(r, s_red);
         if (threadIdx.x == 0) {
-            put_part(A, PC, c, r[0], loc, 0.0);
-            put_part(A, PMIN, c, r[1], loc, (double)INFINITY);
-            put_part(A, PNEGMAX, c, r[2], loc, (double)INFINITY);
-            put_part(A, PG1, c, r[3], loc, (double)INFINITY);
-            put_part(A, PG2, c, r[4], loc, (double)INFINITY);
+            put_part(A, PC, c, r[0], loc, 0.0, ll);
+            put_part(A, PMIN, c, r[1], loc, (double)INFINITY, ll);
+            put_part(A, PNEGMAX, c, r[2], loc, (double)INFINITY, ll);
+            put_part(A, PG1, c, r[3], loc, (double)INFINITY, ll);
+            put_part(A, PG2, c, r[4], loc, (double)INFINITY, ll);
+            if (ll) ll_arrive(A);
         }
     }
 }
@@ -1060,6 +1115,19 @@ __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned
             tim_sync[id] += t2_ - t1_;                                         \
         }                                                                      \
     } while (0)
+// a phase that may hand over through flagged partials: without the barrier the wait is inside the reduction that follows
+#define KR_PHASE_B(id, barrier, call)                                          \
+    do {                                                                       \
+        const long long t0_ = clock64();                                       \
+        call;                                                                  \
+        const long long t1_ = clock64();                                       \
+        if (barrier) kr_barrier(A, true, epoch, gen);                          \
+        if (timing) {                                                          \
+            const long long t2_ = clock64();                                   \
+            tim_work[id] += t1_ - t0_;                                         \
+            tim_sync[id] += t2_ - t1_;                                         \
+        }                                                                      \
+    } while (0)
 // the reduction of the per-chunk partials every CTA repeats after a barrier (timed in the T_FIX slot)
 #define KR_REDUCE(call)                                                        \
     do {                                                                       \
@@ -1102,32 +1170,39 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
         for (int i = 0; i < 2 * T_COUNT; ++i) tim_work[i] = 0;
     }
 
+    // single GPU: the phases that only produce partials hand over through flagged words instead of a grid barrier
+    const bool use_ll = A.n_rank <= 1 && (A.opts & KR_OPT_LL_PARTIALS);
+    unsigned ll_epoch = 0;
+
     int mode = -1;                                        // -1: first trip (x = 1)
     for (;;) {
         if (mode < 0) KR_PHASE(T_INIT, true, phase_init(A));
         else if (mode == KR_STATE_INNER) KR_PHASE(T_DIR, true, phase_dir(A, S.k == 1, S.beta, ybuf[S.ysel], s_red));
         else KR_PHASE(T_UPDATE, true, phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
         KR_PHASE(T_SPMV, false, phase_spmv<SLAB>(A, A.u, sm));
+        const unsigned ll = use_ll ? ++ll_epoch : 0u;      // epoch of this trip's first partial hand-over
         if (mode == KR_STATE_INNER) {
-            KR_PHASE(T_W, true, phase_w(A, s_red));
             {
                 double r[2];
                 const int ids[2] = {PA, PB};
-                KR_REDUCE((reduce_parts<2, 0>(A.part, nc, ids, r, s_red)));
+                KR_PHASE_B(T_W, !use_ll, phase_w(A, s_red, ll));
+                KR_REDUCE((reduce_parts<2, 0>(A, nc, ids, r, s_red, use_ll ? 1u : 0u, ll)));   // PB dates from the dir phase
                 KR_SCALAR(KRS_ALPHA, r);
             }
-            KR_PHASE(T_STEP, true, phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red));
             {
                 double r[5];
                 const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
-                KR_REDUCE((reduce_parts<1, 4>(A.part, nc, ids, r, s_red)));
+                const unsigned ll2 = use_ll ? ++ll_epoch : 0u;
+                KR_PHASE_B(T_STEP, !use_ll,
+                           phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red, ll2));
+                KR_REDUCE((reduce_parts<1, 4>(A, nc, ids, r, s_red, use_ll ? 31u : 0u, ll2)));
                 KR_SCALAR(KRS_DECIDE, r);
             }
         } else {
-            KR_PHASE(T_RESID, true, phase_resid(A, s_red));
             double r[1];
             const int ids[1] = {PA};
-            KR_REDUCE((reduce_parts<1, 0>(A.part, nc, ids, r, s_red)));
+            KR_PHASE_B(T_RESID, !use_ll, phase_resid(A, s_red, ll));
+            KR_REDUCE((reduce_parts<1, 0>(A, nc, ids, r, s_red, use_ll ? 1u : 0u, ll)));
             KR_SCALAR(mode < 0 ? KRS_OUTER_FIRST : KRS_OUTER, r);
         }
         mode = S.state;
@@ -1458,17 +1533,17 @@ __global__ void __launch_bounds__(KR_THREADS) k_krp_scalar(KRArgs A, int which) 
     if (which == KRS_OUTER_FIRST || which == KRS_OUTER) {
         double t[1];
         const int ids[1] = {PA};
-        reduce_parts<1, 0>(A.part, nc, ids, t, s_red);
+        reduce_parts<1, 0>(A, nc, ids, t, s_red);
         r[0] = t[0];
     } else if (which == KRS_ALPHA) {
         double t[2];
         const int ids[2] = {PA, PB};
-        reduce_parts<2, 0>(A.part, nc, ids, t, s_red);
+        reduce_parts<2, 0>(A, nc, ids, t, s_red);
         r[0] = t[0];
         r[1] = t[1];
     } else {
         const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
-        reduce_parts<1, 4>(A.part, nc, ids, r, s_red);
+        reduce_parts<1, 4>(A, nc, ids, r, s_red);
     }
     if (threadIdx.x == 0) {
         scalar_step(S, which, r);
@@ -1483,6 +1558,7 @@ static std::unordered_map<void *, KRArgs> g_krp;
 // tuning / test hooks (b3c_set_option): slab width cap and slab count cap of the SpMV operand
 static std::atomic<int> g_slab_w_max{SLAB_W_MAX};
 static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
+// KR_OPT_LL_PARTIALS stays off: measured slower than the barrier it replaces (profiles/r1_kr_phases.md)
 static std::atomic<int> g_kr_opts{KR_OPT_BANK_ORDER | KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER};
 constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
 
@@ -1490,7 +1566,7 @@ struct KRLayout {
     int32_t slab, S, W, n_chunks;
     int64_t nvec;                       // elements per (padded) vector
     int64_t nv_max, nnzv_max, nseg_max;
-    int64_t o_dfix, o_vec, o_qs, o_part, o_ctl, o_timers, o_bar, o_bnd, o_cta;
+    int64_t o_dfix, o_vec, o_qs, o_part, o_ll, o_ctl, o_timers, o_bar, o_bnd, o_cta;
     int64_t o_cnt, o_vp, o_ord, o_scan, o_slab_t0, o_sval, o_scol, o_sflag, o_seg0, o_seg_of, o_seg_row, total;
 };
 
@@ -1518,6 +1594,7 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     L.o_vec = c.take(L.nvec * 8 * 9);
     L.o_qs = c.take(L.nseg_max * 8);
     L.o_part = c.take((int64_t)L.n_chunks * 8 * P_COUNT);
+    L.o_ll = c.take((int64_t)L.n_chunks * 16 * P_COUNT + 128);       // + the arrival counter of the hand-overs
     L.o_ctl = c.take(sizeof(KRScalars));
     L.o_timers = c.take(sizeof(KRTimers));
     L.o_bar = c.take(256);
@@ -1589,6 +1666,7 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.w = vec + L.nvec * 7;
     A.u = vec + L.nvec * 8;
     A.part = (double *)(ws + L.o_part);
+    A.ll = (unsigned long long *)(ws + L.o_ll);
     A.n_chunks = L.n_chunks;
     A.ctl = (KRScalars *)(ws + L.o_ctl);
     A.timers = (KRTimers *)(ws + L.o_timers);
@@ -1742,7 +1820,7 @@ int b3c_set_option(int32_t key, int64_t value) {
             g_slab_s_max.store((int)value);
             return B3C_OK;
         case B3C_OPT_KR_FLAGS:
-            B3C_REQUIRE(value >= 0 && value <= 7, "KR option flags must be in [0, 7]");
+            B3C_REQUIRE(value >= 0 && value <= 15, "KR option flags must be in [0, 15]");
             g_kr_opts.store((int)value);
             return B3C_OK;
         default:
@@ -1766,6 +1844,7 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     const int grid = A.n_bnd;
     void *args[] = {&A};
     B3C_CUDA(cudaMemsetAsync(A.bar_count, 0, 256, s));
+    B3C_CUDA(cudaMemsetAsync(A.ll, 0, (size_t)A.n_chunks * 16 * P_COUNT + 128, s));      // epoch 0 = never written
     B3C_CUDA(cudaEventRecord(ev[0], s));
     if (A.slab)
         B3C_CUDA(cudaLaunchCooperativeKernel((void *)k_kr_persistent<true>, dim3(grid), dim3(KR_THREADS), args,

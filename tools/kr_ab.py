@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--flags', default='0,1,2,4,7')
+    ap.add_argument('--flags', default='7,15')
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--scale', type=float, default=1.0)
     ap.add_argument('--slab-width', default='')
