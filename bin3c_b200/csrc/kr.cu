@@ -1244,6 +1244,9 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
     const int64_t nw = (int64_t)gridDim.x * 8;
     const int n_local = A.row_hi - A.row_lo;
     const int W = A.W;
+    // col / W as a multiplication: with Wm = ceil(2^40 / W) the quotient is exact while col * W < 2^40 (col < 2^21, W < 2^15)
+    // (slab form); with a single slab (the gather form, W = n) the multiplier is 0 and every column is in slab 0
+    const uint64_t Wm = A.S == 1 ? 0ull : ((1ull << 40) + (uint64_t)W - 1) / (uint64_t)W;
     bool bad = false;
     for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < n_local; lr += nw) {
         const int64_t lo = A.indptr[lr], hi = A.indptr[lr + 1];
@@ -1258,7 +1261,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 bad = true;
                 col = col < 0 ? 0 : A.n - 1;
             }
-            const int s = valid ? col / W : 0x7fffffff;
+            const int s = valid ? (int)(((uint64_t)col * Wm) >> 40) : 0x7fffffff;      // col / W
             int sp = __shfl_up_sync(kFullMask, s, 1);
             if (lane == 0) sp = carry_s;
             const bool flag = valid && (s != sp);
@@ -1285,7 +1288,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 if (e + 1 < hi) {
                     int cn = A.indices[e + 1];
                     cn = cn < 0 ? 0 : (cn >= A.n ? A.n - 1 : cn);
-                    s_next = cn / W;
+                    s_next = (int)(((uint64_t)cn * Wm) >> 40);
                 }
                 if (s_next != s) {
                     const int64_t len = e - seg_start + 1, seg0 = dst - (e - seg_start);
@@ -1438,23 +1441,28 @@ __global__ void __launch_bounds__(256) k_diag_fix(int32_t row_lo, int32_t row_hi
                                                   const int32_t *__restrict__ indices, const double *__restrict__ data,
                                                   const uint32_t *__restrict__ cnt32, const int32_t *__restrict__ sites,
                                                   double *__restrict__ dfix, KRScalars *ctl) {
-    const unsigned lane = lane_id();
-    const int64_t nw = (int64_t)gridDim.x * 8;
-    unsigned nz = 0;
-    for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < row_hi - row_lo; lr += nw) {
-        const int64_t lo = indptr[lr], hi = indptr[lr + 1];
+    // One thread per row: the columns of a row are sorted (k_stream_rows rejects the matrix otherwise), so the
+    // diagonal is found by bisection instead of walking the row.
+    const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool z = false;
+    if (lr < row_hi - row_lo) {
+        int64_t lo = indptr[lr];
+        const int64_t end = indptr[lr + 1];
+        int64_t hi = end;
         const int32_t gr = row_lo + (int32_t)lr;
-        double d = 0.0;           // duplicates of the diagonal would be summed by scipy's diagonal()
-        for (int64_t e = lo + lane; e < hi; e += 32)
-            if (indices[e] == gr) d += cnt32 ? site_scaled(cnt32[e], sites[gr], sites[gr]) : data[e];
-        d = warp_sum(d);
-        if (lane == 0) {
-            const bool z = (d == 0.0);
-            dfix[gr] = z ? 1.0 : 0.0;
-            nz += z ? 1u : 0u;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (indices[mid] < gr) lo = mid + 1;
+            else hi = mid;
         }
+        double d = 0.0;           // duplicates of the diagonal would be summed by scipy's diagonal()
+        for (int64_t e = lo; e < end && indices[e] == gr; ++e)
+            d += cnt32 ? site_scaled(cnt32[e], sites[gr], sites[gr]) : data[e];
+        z = (d == 0.0);
+        dfix[gr] = z ? 1.0 : 0.0;
     }
-    if (lane == 0 && nz) atomicAdd((unsigned long long *)&ctl->zero_diag, (unsigned long long)nz);
+    const unsigned nz = __popc(__ballot_sync(kFullMask, z));
+    if (lane_id() == 0 && nz) atomicAdd((unsigned long long *)&ctl->zero_diag, (unsigned long long)nz);
 }
 
 // ---- stand-alone kernels (microbench SpMV, host-driven phases) ------------------------------------
@@ -1775,7 +1783,7 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
         B3C_LAUNCH_CHECK();
     }
     B3C_CUDA(cudaMemsetAsync(A.qs, 0, (size_t)(A.n_seg + 1) * 8, s));
-    k_diag_fix<<<row_warp_grid(n_local), 256, 0, s>>>(A.row_lo, A.row_hi, A.indptr, A.indices, A.data, A.cnt32, A.sites,
+    k_diag_fix<<<(unsigned)ceil_div(n_local > 0 ? n_local : 1, 256), 256, 0, s>>>(A.row_lo, A.row_hi, A.indptr, A.indices, A.data, A.cnt32, A.sites,
                                                               A.dfix, A.ctl);
     B3C_LAUNCH_CHECK();
     rc = persistent_grid(SLAB, &A.n_bnd);
