@@ -253,3 +253,41 @@ def test_cluster_write_edges_uses_the_native_writer(tmp_path):
     assert open(f).read() == '0 0 1.0\n0 2 0.25\n1 2 0.3333333333333333\n'
     f = cluster.write_edges(u, v, w, str(tmp_path), base_name='py2', py2_str=True)
     assert open(f).read() == '0 0 1.0\n0 2 0.25\n1 2 0.333333333333\n'
+
+
+INFOMAP = '/root/reference/external/Infomap'
+
+
+@pytest.mark.skipif(not os.access(INFOMAP, os.X_OK), reason='the reference tree (and its Infomap binary) is not present')
+def test_infomap_partition_from_native_edge_file(tmp_path):
+    """
+    The hand-off itself: the reference's own Infomap binary, run with the reference's flags (cluster.py:182-185) on
+    the edge file the native writer produces from the golden edge list, accepts it and returns a partition of all
+    nodes; the file the oracle's restatement of nx.write_edgelist writes gives the identical tree (same graph file
+    -> same clustering), and so do the Python-2 ('%.12g') and Python-3 (repr) weight layouts on this community.
+    """
+    import subprocess
+    d = np.load(os.path.join(ROOT, 'tests', 'golden', 'c1mini.npz'))
+    u, v, w = d['edge_u'], d['edge_v'], d['edge_w']
+    parts = {}
+    for name, style, writer in (('native_repr', bam_io.FLOAT_REPR, 'native'), ('native_py2', bam_io.FLOAT_STR12, 'native'),
+                                ('oracle_py2', None, 'oracle')):
+        work = tmp_path / name
+        work.mkdir()
+        f = str(work / 'cm_graph.edges')
+        if writer == 'native':
+            bam_io.write_edges(u, v, w, f, float_style=style)
+        else:
+            with open(f, 'w') as out:
+                out.write(oracle.edge_lines(u, v, w, py2=True))
+        subprocess.check_call([INFOMAP, '-u', '-v', '-z', '-i', 'link-list', '-s', '1234', '-N', '10', f, str(work)],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+        parts[name] = oracle.read_tree(str(work / 'cm_graph.tree'))
+    n_nodes = int(d['sub_n'])
+    for p in parts.values():
+        members = sorted(m for cl in p for m in cl)
+        assert members == list(range(n_nodes))                      # zero-based, gapless ids (-z)
+    assert open(str(tmp_path / 'native_py2' / 'cm_graph.edges')).read() == \
+        open(str(tmp_path / 'oracle_py2' / 'cm_graph.edges')).read()
+    assert parts['native_py2'] == parts['oracle_py2'] == parts['native_repr']
+    assert len(parts['native_py2']) > 1
