@@ -689,35 +689,25 @@ __device__ __forceinline__ double row_q(const KRArgs &A, int64_t r) {
 // store can never force a later load to wait.
 #define KR_FOR_CHUNKS(c) for (int c = blockIdx.x; c < A.n_chunks; c += gridDim.x)
 #define KR_ROW(c, i) ((int64_t)(c) * CHUNK + (i) * KR_THREADS + threadIdx.x)
-constexpr int ROWQ_S = 4;                      // slabs handled by the batched row_q; more fall back to the loop
+constexpr int ROWQ_S = 12;                     // slabs handled by the fully batched rows_q; more fall back to the loop
 
 __device__ __forceinline__ bool chunk_local(const KRArgs &A, int c) {
     const int64_t r0 = (int64_t)c * CHUNK;
     return r0 >= A.row_lo && r0 < A.row_hi;
 }
 
-// q = A u plus the zero-diagonal term (Q2) for the CHUNK_RPT rows of this thread, loads batched
-__device__ __forceinline__ void rows_q(const KRArgs &A, int c, double (&qq)[CHUNK_RPT]) {
-    if (A.S > ROWQ_S) {
-#pragma unroll
-        for (int i = 0; i < CHUNK_RPT; ++i) {
-            const int64_t r = KR_ROW(c, i);
-            qq[i] = 0.0;
-            if (r < A.row_hi) {
-                qq[i] = row_q(A, r);
-                if (__ldcg(A.dfix + r) != 0.0) qq[i] = __dadd_rn(qq[i], __ldcg(A.u + r));
-            }
-        }
-        return;
-    }
-    int o[CHUNK_RPT][ROWQ_S];
-    double df[CHUNK_RPT], uu[CHUNK_RPT], t[CHUNK_RPT][ROWQ_S];
+// q = A u plus the zero-diagonal term (Q2) for the CHUNK_RPT rows of this thread, loads batched: every cell
+// ordinal of up to NB slabs first, then every segment sum, then the adds in slab order
+template <int NB>
+__device__ __forceinline__ void rows_q_batched(const KRArgs &A, int c, double (&qq)[CHUNK_RPT]) {
+    int o[CHUNK_RPT][NB];
+    double df[CHUNK_RPT], uu[CHUNK_RPT], t[CHUNK_RPT][NB];
 #pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i) {
         const int64_t r = KR_ROW(c, i);
         const bool ok = r < A.row_hi;
 #pragma unroll
-        for (int k = 0; k < ROWQ_S; ++k)
+        for (int k = 0; k < NB; ++k)
             o[i][k] = (ok && k < A.S) ? __ldg(A.seg_of + (int64_t)k * A.npad + (r - A.row_lo)) : -1;
         df[i] = ok ? __ldcg(A.dfix + r) : 0.0;
         uu[i] = ok ? __ldcg(A.u + r) : 0.0;
@@ -725,15 +715,29 @@ __device__ __forceinline__ void rows_q(const KRArgs &A, int c, double (&qq)[CHUN
 #pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i)
 #pragma unroll
-        for (int k = 0; k < ROWQ_S; ++k) t[i][k] = o[i][k] >= 0 ? __ldcg(A.qs + o[i][k]) : 0.0;
+        for (int k = 0; k < NB; ++k) t[i][k] = o[i][k] >= 0 ? __ldcg(A.qs + o[i][k]) : 0.0;
 #pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i) {
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < ROWQ_S; ++k)
+        for (int k = 0; k < NB; ++k)
             if (o[i][k] >= 0) s = __dadd_rn(s, t[i][k]);
         if (df[i] != 0.0) s = __dadd_rn(s, uu[i]);                 // zero diagonal counted as one (Q2)
         qq[i] = s;
+    }
+}
+
+__device__ __forceinline__ void rows_q(const KRArgs &A, int c, double (&qq)[CHUNK_RPT]) {
+    if (A.S <= 4) return rows_q_batched<4>(A, c, qq);
+    if (A.S <= ROWQ_S) return rows_q_batched<ROWQ_S>(A, c, qq);
+#pragma unroll
+    for (int i = 0; i < CHUNK_RPT; ++i) {
+        const int64_t r = KR_ROW(c, i);
+        qq[i] = 0.0;
+        if (r < A.row_hi) {
+            qq[i] = row_q(A, r);
+            if (__ldcg(A.dfix + r) != 0.0) qq[i] = __dadd_rn(qq[i], __ldcg(A.u + r));
+        }
     }
 }
 
