@@ -410,16 +410,22 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
             dg[k] = valid ? ((unsigned)(key[k] >> shift) & mask) : (unsigned)RS_BINS;
         }
         __syncthreads();
-        // stable rank inside the warp, one item row at a time
+        // stable rank inside the warp, one item row at a time.  The match masks do not depend on the counters, so
+        // they are all taken first; then the leader of every match group bumps the warp's digit counter with ONE
+        // shared-memory atomic that returns the count of the earlier rows (the rows' atomics are issued back to
+        // back: nothing waits for a value until the shuffles below), and the group reads it from the leader.
+        unsigned mm[RS_KPT];
+#pragma unroll
+        for (int k = 0; k < RS_KPT; ++k) mm[k] = __match_any_sync(kFullMask, dg[k]);
 #pragma unroll
         for (int k = 0; k < RS_KPT; ++k) {
-            const unsigned m = __match_any_sync(kFullMask, dg[k]);
-            const uint32_t prior = s_wcnt[warp][dg[k]];
-            rk[k] = prior + __popc(m & lt);
-            __syncwarp();
-            if ((int)lane == __ffs(m) - 1) s_wcnt[warp][dg[k]] = prior + __popc(m);
-            __syncwarp();
+            rk[k] = 0;
+            if ((int)lane == __ffs(mm[k]) - 1) rk[k] = atomicAdd(&s_wcnt[warp][dg[k]], (uint32_t)__popc(mm[k]));
+            __syncwarp();                          // row k's additions are ordered before row k + 1's
         }
+#pragma unroll
+        for (int k = 0; k < RS_KPT; ++k)
+            rk[k] = __shfl_sync(kFullMask, rk[k], __ffs(mm[k]) - 1) + __popc(mm[k] & lt);
         __syncthreads();
         // per digit: exclusive scan over warps, tile total
         if (threadIdx.x < RS_BINS) {

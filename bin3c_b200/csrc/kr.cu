@@ -1257,10 +1257,20 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
         const int32_t s_row = (FILL && A.cnt32) ? A.sites[A.row_lo + lr] : 1;
         int carry_s = -1;
         int64_t carry_start = lo;
+        // the next window's columns (and counts) are loaded before this window is processed
+        int col_nx = (lo + lane < hi) ? A.indices[lo + lane] : 0;
+        uint32_t cnt_nx = (FILL && A.cnt32 && lo + lane < hi) ? A.cnt32[lo + lane] : 0u;
         for (int64_t e0 = lo; e0 < hi; e0 += 32) {
             const int64_t e = e0 + lane;
             const bool valid = e < hi;
-            int col = valid ? A.indices[e] : 0;
+            int col = col_nx;
+            const uint32_t cnt_e = cnt_nx;
+            if (e + 32 < hi) {
+                col_nx = A.indices[e + 32];
+                if (FILL && A.cnt32) cnt_nx = A.cnt32[e + 32];
+            } else {
+                col_nx = 0;
+            }
             if (col < 0 || col >= A.n) {           // reported through ctl->status; clamped to stay in bounds
                 bad = true;
                 col = col < 0 ? 0 : A.n - 1;
@@ -1272,6 +1282,15 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
             bad |= valid && s < sp;
             const unsigned fm = __ballot_sync(kFullMask, flag);
             const unsigned below = fm & lanemask_lt();
+            // slab of the entry after mine: my right neighbour's, or (lane 31) the first of the prefetched window
+            int s_nb = 0;
+            if (FILL) {
+                int c0 = __shfl_sync(kFullMask, col_nx, 0);
+                c0 = c0 < 0 ? 0 : (c0 >= A.n ? A.n - 1 : c0);
+                const int s_first_nx = (int)(((uint64_t)c0 * Wm) >> 40);
+                s_nb = __shfl_down_sync(kFullMask, s, 1);
+                if (lane == 31) s_nb = s_first_nx;
+            }
             if (!FILL) {
                 if (flag && sp >= 0) {             // this entry closes the segment of slab sp
                     const int64_t prev_start = below ? e0 + (31 - __clz(below)) : carry_start;
@@ -1282,18 +1301,13 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 const int64_t seg_start = upto ? e0 + (31 - __clz(upto)) : carry_start;
                 const int64_t dst = A.vp[(int64_t)s * A.npad + lr] + (e - seg_start);
                 const int64_t ph = stream_phys(dst);
-                sval[ph] = A.cnt32 ? site_scaled(A.cnt32[e], s_row, __ldg(A.sites + col)) : A.data[e];
+                sval[ph] = A.cnt32 ? site_scaled(cnt_e, s_row, __ldg(A.sites + col)) : A.data[e];
                 const unsigned lc = (unsigned)(col - s * W);
                 if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
                 else ((uint32_t *)scol_v)[ph] = lc;
                 if (e == seg_start) stream_set_flag(sflag, dst);
                 // the segment's last entry also writes its padding (zero value, column 0) up to a whole piece
-                int s_next = -1;
-                if (e + 1 < hi) {
-                    int cn = A.indices[e + 1];
-                    cn = cn < 0 ? 0 : (cn >= A.n ? A.n - 1 : cn);
-                    s_next = (int)(((uint64_t)cn * Wm) >> 40);
-                }
+                const int s_next = (e + 1 < hi) ? s_nb : -1;
                 if (s_next != s) {
                     const int64_t len = e - seg_start + 1, seg0 = dst - (e - seg_start);
                     for (int64_t k = len; k < seg_padded(len); ++k) {
