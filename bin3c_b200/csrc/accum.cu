@@ -410,13 +410,26 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
             dg[k] = valid ? ((unsigned)(key[k] >> shift) & mask) : (unsigned)RS_BINS;
         }
         __syncthreads();
-        // stable rank inside the warp, one item row at a time.  The match masks do not depend on the counters, so
+        // stable rank inside the warp, one item row at a time.  The peer masks do not depend on the counters, so
         // they are all taken first; then the leader of every match group bumps the warp's digit counter with ONE
         // shared-memory atomic that returns the count of the earlier rows (the rows' atomics are issued back to
         // back: nothing waits for a value until the shuffles below), and the group reads it from the leader.
         unsigned mm[RS_KPT];
 #pragma unroll
-        for (int k = 0; k < RS_KPT; ++k) mm[k] = __match_any_sync(kFullMask, dg[k]);
+        for (int k = 0; k < RS_KPT; ++k) {
+            // lanes holding the same digit: one ballot per digit bit (match.any is a slow MIO operation here --
+            // it was 24 % of this kernel's stall samples); invalid lanes (digit RS_BINS) form their own group
+            const bool valid = dg[k] < (unsigned)RS_BINS;
+            unsigned m = __ballot_sync(kFullMask, valid);
+            if (!valid) m = ~m;
+#pragma unroll
+            for (int b = 0; b < RS_BITS; ++b) {
+                const bool bit = (dg[k] >> b) & 1u;
+                const unsigned bal = __ballot_sync(kFullMask, bit);
+                m &= bit ? bal : ~bal;
+            }
+            mm[k] = m;
+        }
 #pragma unroll
         for (int k = 0; k < RS_KPT; ++k) {
             rk[k] = 0;

@@ -1328,11 +1328,21 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
 }
 
 // one CTA per slab: pad the slab's entry count to whole tiles (the padding belongs to its last cell)
-__global__ void __launch_bounds__(256) k_slab_pad(KRArgs A, int64_t *__restrict__ cnt) {
+__global__ void __launch_bounds__(1024) k_slab_pad(KRArgs A, int64_t *__restrict__ cnt) {
     __shared__ int64_t s_w[33];
     const int s = blockIdx.x;
     int64_t v = 0;
-    for (int64_t i = threadIdx.x; i < A.npad; i += 256) v += cnt[(int64_t)s * A.npad + i];
+    const int64_t *row = cnt + (int64_t)s * A.npad;
+    int64_t v1 = 0, v2 = 0, v3 = 0;                     // four independent loads in flight per thread
+    int64_t i = threadIdx.x;
+    for (; i + 3 * 1024 < A.npad; i += 4 * 1024) {
+        v += row[i];
+        v1 += row[i + 1024];
+        v2 += row[i + 2 * 1024];
+        v3 += row[i + 3 * 1024];
+    }
+    for (; i < A.npad; i += 1024) v += row[i];
+    v += v1 + v2 + v3;
     int64_t tot;
     block_scan_excl<int64_t>(v, s_w, &tot);
     if (threadIdx.x == 0) {
@@ -1756,7 +1766,7 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     B3C_CUDA(cudaMemsetAsync(sflag, 0, (size_t)(L.nnzv_max / 8 + 64), s));
     k_stream_rows<false, SLAB><<<row_warp_grid(n_local), 256, 0, s>>>(A, A.cnt, nullptr, nullptr, nullptr);
     B3C_LAUNCH_CHECK();
-    k_slab_pad<<<(unsigned)A.S, 256, 0, s>>>(A, A.cnt);
+    k_slab_pad<<<(unsigned)A.S, 1024, 0, s>>>(A, A.cnt);
     B3C_LAUNCH_CHECK();
     int rc = scan_exclusive_i64(A.cnt, A.vp, A.nv, A.scan_tmp, s);
     if (rc) return rc;

@@ -290,13 +290,21 @@ __global__ void __launch_bounds__(ROW_THREADS) k_edges_count(int32_t n, int32_t 
         const ContigAttr ar = ld_attr(attr + gr);
         if (ar.newidx >= 0) {
             const int64_t lo = indptr[r], hi = indptr[r + 1];
+            // the next window's column and count are loaded before this window's scattered gather is consumed
+            int32_t c_nx = (lo + lane < hi) ? indices[lo + lane] : 0;
+            uint32_t n_nx = (lo + lane < hi) ? counts[lo + lane] : 0u;
             for (int64_t e = lo + lane; e < hi; e += 32) {
-                const int32_t c = indices[e];
+                const int32_t c = c_nx;
+                const uint32_t cnt = n_nx;
+                if (e + 32 < hi) {
+                    c_nx = indices[e + 32];
+                    n_nx = counts[e + 32];
+                }
                 const ContigAttr ac = ld_attr(attr + c);
                 if (ac.newidx >= 0) {
                     ++k;
                     ed += (c >= gr) ? 1u : 0u;
-                    wmax = fmax(wmax, edge_value(counts[e], ar, ac));
+                    wmax = fmax(wmax, edge_value(cnt, ar, ac));
                 }
             }
         }
@@ -331,22 +339,26 @@ __global__ void __launch_bounds__(ROW_THREADS) k_edges_fill(int32_t n, int32_t r
         const int64_t lo = indptr[r], hi = indptr[r + 1];
         int64_t ebase = edge_ex[r];
         // columns are sorted: the upper-triangle entries (c >= row) are the tail of the row
+        int32_t c_nx = (lo + lane < hi) ? indices[lo + lane] : -1;
+        uint32_t n_nx = (lo + lane < hi) ? counts[lo + lane] : 0u;
         for (int64_t e0 = lo; e0 < hi; e0 += 32) {
             const int64_t e = e0 + lane;
-            int32_t c = -1;
+            const int32_t c = (e < hi) ? c_nx : -1;
+            const uint32_t cnt = n_nx;
+            if (e + 32 < hi) {                                              // next window, ahead of this one's gather
+                c_nx = indices[e + 32];
+                n_nx = counts[e + 32];
+            }
             ContigAttr ac;
             ac.newidx = -1;
-            if (e < hi) {
-                c = indices[e];
-                if (c >= gr) ac = ld_attr(attr + c);
-            }
+            if (c >= gr) ac = ld_attr(attr + c);
             const bool is_edge = ac.newidx >= 0;
             const unsigned me = __ballot_sync(kFullMask, is_edge);
             if (is_edge) {
                 const int64_t d = ebase + __popc(me & lt);
                 eu[d] = ar.newidx;
                 ev[d] = ac.newidx;
-                ew[d] = __dmul_rn(edge_value(counts[e], ar, ac), scl);      // cluster.py:321
+                ew[d] = __dmul_rn(edge_value(cnt, ar, ac), scl);            // cluster.py:321
             }
             ebase += __popc(me);
         }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Aggregate an ncu source page (cuda,sass) per CUDA source line: stall samples and executed instructions.
-    python tools/ncu_lines.py prof.ncu-rep [top_n]
+    python tools/ncu_lines.py prof.ncu-rep [top_n [kernel-name-regex]]
 """
 import csv
 import subprocess
@@ -10,7 +10,7 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv'],
+    out = subprocess.run(['ncu', '-i', rep] + (['--kernel-name', 'regex:' + sys.argv[3]] if len(sys.argv) > 3 else []) + ['--page', 'source', '--print-source', 'cuda,sass', '--csv'],
                          stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     agg = {}
