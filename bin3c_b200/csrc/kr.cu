@@ -1257,20 +1257,28 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
         const int32_t s_row = (FILL && A.cnt32) ? A.sites[A.row_lo + lr] : 1;
         int carry_s = -1;
         int64_t carry_start = lo;
-        // the next window's columns (and counts) are loaded before this window is processed
-        int col_nx = (lo + lane < hi) ? A.indices[lo + lane] : 0;
-        uint32_t cnt_nx = (FILL && A.cnt32 && lo + lane < hi) ? A.cnt32[lo + lane] : 0u;
+        // software pipeline over the 32-entry windows: columns and counts are loaded two windows ahead, the site
+        // count of a column (a scattered gather that needs the column first) one window ahead
+        const bool want_cnt = FILL && A.cnt32 != nullptr;
+        int col_a = (lo + lane < hi) ? A.indices[lo + lane] : 0;
+        int col_b = (lo + 32 + lane < hi) ? A.indices[lo + 32 + lane] : 0;
+        uint32_t cnt_a = (want_cnt && lo + lane < hi) ? A.cnt32[lo + lane] : 0u;
+        uint32_t cnt_b = (want_cnt && lo + 32 + lane < hi) ? A.cnt32[lo + 32 + lane] : 0u;
+        int32_t site_a = want_cnt ? __ldg(A.sites + min(max(col_a, 0), A.n - 1)) : 1;
         for (int64_t e0 = lo; e0 < hi; e0 += 32) {
             const int64_t e = e0 + lane;
             const bool valid = e < hi;
-            int col = col_nx;
-            const uint32_t cnt_e = cnt_nx;
-            if (e + 32 < hi) {
-                col_nx = A.indices[e + 32];
-                if (FILL && A.cnt32) cnt_nx = A.cnt32[e + 32];
-            } else {
-                col_nx = 0;
+            int col = col_a;
+            const uint32_t cnt_e = cnt_a;
+            const int32_t site_e = site_a;
+            col_a = col_b;
+            cnt_a = cnt_b;
+            col_b = 0;
+            if (e + 64 < hi) {
+                col_b = A.indices[e + 64];
+                if (want_cnt) cnt_b = A.cnt32[e + 64];
             }
+            if (want_cnt && e0 + 32 < hi) site_a = __ldg(A.sites + min(max(col_a, 0), A.n - 1));
             if (col < 0 || col >= A.n) {           // reported through ctl->status; clamped to stay in bounds
                 bad = true;
                 col = col < 0 ? 0 : A.n - 1;
@@ -1282,14 +1290,21 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
             bad |= valid && s < sp;
             const unsigned fm = __ballot_sync(kFullMask, flag);
             const unsigned below = fm & lanemask_lt();
-            // slab of the entry after mine: my right neighbour's, or (lane 31) the first of the prefetched window
+            // slab of the entry after mine: my right neighbour's.  Lane 31 cannot know yet (the next window is still
+            // in flight) and assumes its segment goes on; if it did end there, lane 0 of the next window pads it.
             int s_nb = 0;
             if (FILL) {
-                int c0 = __shfl_sync(kFullMask, col_nx, 0);
-                c0 = c0 < 0 ? 0 : (c0 >= A.n ? A.n - 1 : c0);
-                const int s_first_nx = (int)(((uint64_t)c0 * Wm) >> 40);
                 s_nb = __shfl_down_sync(kFullMask, s, 1);
-                if (lane == 31) s_nb = s_first_nx;
+                if (lane == 31) s_nb = s;
+                if (lane == 0 && flag && sp >= 0) {
+                    const int64_t len = e0 - carry_start, seg0 = A.vp[(int64_t)sp * A.npad + lr];
+                    for (int64_t k = len; k < seg_padded(len); ++k) {
+                        const int64_t pp = stream_phys(seg0 + k);
+                        sval[pp] = 0.0;
+                        if (SLAB) ((uint16_t *)scol_v)[pp] = 0;
+                        else ((uint32_t *)scol_v)[pp] = 0;
+                    }
+                }
             }
             if (!FILL) {
                 if (flag && sp >= 0) {             // this entry closes the segment of slab sp
@@ -1301,7 +1316,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 const int64_t seg_start = upto ? e0 + (31 - __clz(upto)) : carry_start;
                 const int64_t dst = A.vp[(int64_t)s * A.npad + lr] + (e - seg_start);
                 const int64_t ph = stream_phys(dst);
-                sval[ph] = A.cnt32 ? site_scaled(cnt_e, s_row, __ldg(A.sites + col)) : A.data[e];
+                sval[ph] = A.cnt32 ? site_scaled(cnt_e, s_row, site_e) : A.data[e];
                 const unsigned lc = (unsigned)(col - s * W);
                 if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
                 else ((uint32_t *)scol_v)[ph] = lc;
@@ -1595,7 +1610,9 @@ static std::unordered_map<void *, KRArgs> g_krp;
 static std::atomic<int> g_slab_w_max{SLAB_W_MAX};
 static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
 // KR_OPT_LL_PARTIALS stays off: measured slower than the barrier it replaces (profiles/r1_kr_phases.md)
-static std::atomic<int> g_kr_opts{KR_OPT_BANK_ORDER | KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER};
+// KR_OPT_BANK_ORDER stays off too: the reordering pass costs 91 us at C2 and saves 0.5 us per SpMV, so it would
+// only pay for solves of more than ~180 SpMV (typical: 24-40)
+static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER};
 constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
 
 struct KRLayout {

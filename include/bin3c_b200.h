@@ -163,8 +163,8 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  * matrices, or 0, select the form that gathers through L1/L2 -- except that at the default, matrices of up
  * to 48 slabs whose (row, slab) cells hold 6 or more entries on average stay in the slab form).  Results are
  * identical up to fp64 summation order.  Workspace sizes depend on these, so set them before the *_workspace_bytes() query.
- * B3C_OPT_KR_FLAGS (default 7) is a bit set for A/B measurements: 1 = order every lane's run of the
- * stream by shared-memory bank, 2 = align the SpMV CTA ranges with the slabs, 4 = single-word grid
+ * B3C_OPT_KR_FLAGS (default 6) is a bit set for A/B measurements: 1 = order every lane's run of the
+ * stream by shared-memory bank (off: the pass costs more than it saves below ~180 SpMV per solve), 2 = align the SpMV CTA ranges with the slabs, 4 = single-word grid
  * barrier (release-add + acquire-poll), 8 = on one GPU the phases that only produce reduction partials
  * hand them over as flagged 8-byte words instead of passing a grid barrier (off: measured slower). */
 enum { B3C_OPT_KR_SLAB_WIDTH = 1, B3C_OPT_KR_MAX_SLABS = 2, B3C_OPT_KR_FLAGS = 3 };

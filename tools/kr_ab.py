@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--flags', default='7,15')
+    ap.add_argument('--flags', default='6,7')
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--scale', type=float, default=1.0)
     ap.add_argument('--slab-width', default='')
@@ -53,7 +53,7 @@ def main():
                        sync_us={n: round(v / mhz, 1) for n, v in k['sync_cycles'].items() if v},
                        cta_spmv_us={n: round(v / mhz, 1) for n, v in k['cta_spmv_cycles'].items()})
             print(json.dumps(out), flush=True)
-    dev.check(dev.lib.b3c_set_option(3, 7))
+    dev.check(dev.lib.b3c_set_option(3, 6))
 
 
 if __name__ == '__main__':
