@@ -96,7 +96,8 @@ static void plan(AccumState &st, int64_t cap, int32_t n_seq, int32_t n_refs) {
     st.rank_words = ceil_div(n_refs > 0 ? n_refs : 1, 64);
     // shared-memory plan of k_classify: header | staging | rank table | diagonal histogram
     const int64_t hdr = 32;
-    const int64_t rank_bytes = align_up(st.rank_words * 8, 16) + align_up(st.rank_words * 4, 16);
+    // in shared memory the table is held as 32-bit words with one prefix per word (cheaper look-ups than 64-bit)
+    const int64_t rank_bytes = align_up(st.rank_words * 8, 16) + align_up(st.rank_words * 8, 16);
     const int64_t diag_bytes = align_up((int64_t)n_seq * 4, 16);
     const int64_t stage32 = (int64_t)CLS_TILE * 4, stage64 = (int64_t)CLS_TILE * 8;
     st.smem_diag = st.smem_rank = false;
@@ -168,16 +169,22 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + 8);
     stage_t *s_stage = reinterpret_cast<stage_t *>(smem + 32);
     unsigned char *cur = smem + 32 + sizeof(stage_t) * CLS_TILE;
-    const unsigned long long *s_bits = nullptr;
+    const uint32_t *s_bits = nullptr;
     const uint32_t *s_pref = nullptr;
     if (RANK) {
-        unsigned long long *wb = reinterpret_cast<unsigned long long *>(cur);
+        // the global table has 64-bit words with one prefix each; here it is re-cut into 32-bit words (the halves of a
+        // little-endian 64-bit word, in place) with a prefix per half, so a look-up is 32-bit shifts and one POPC
+        uint32_t *wb = reinterpret_cast<uint32_t *>(cur);
         cur += (P.rank_words * 8 + 15) / 16 * 16;
         uint32_t *wp = reinterpret_cast<uint32_t *>(cur);
-        cur += (P.rank_words * 4 + 15) / 16 * 16;
+        cur += (P.rank_words * 8 + 15) / 16 * 16;
         for (int64_t i = threadIdx.x; i < P.rank_words; i += CLS_THREADS) {
-            wb[i] = P.g_bits[i];
-            wp[i] = P.g_pref[i];
+            const unsigned long long m = P.g_bits[i];
+            const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32), pf = P.g_pref[i];
+            wb[2 * i] = lo;
+            wb[2 * i + 1] = hi;
+            wp[2 * i] = pf;
+            wp[2 * i + 1] = pf + __popc(lo);
         }
         s_bits = wb;
         s_pref = wp;
@@ -196,10 +203,10 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
     auto lookup = [&](uint32_t t) -> int32_t {
         if (t >= (uint32_t)P.n_refs) return -1;
         if (RANK) {
-            const unsigned long long m = s_bits[t >> 6];
-            const unsigned bit = t & 63u;
-            if (!((m >> bit) & 1ull)) return -1;
-            return (int32_t)(s_pref[t >> 6] + __popcll(m & ((1ull << bit) - 1ull)));
+            const uint32_t m = s_bits[t >> 5];
+            const unsigned bit = t & 31u;
+            if (!((m >> bit) & 1u)) return -1;
+            return (int32_t)(s_pref[t >> 5] + __popc(m & ((1u << bit) - 1u)));
         } else {
             const int32_t v = __ldg(P.lut + t);
             return v < P.n_seq ? v : -1;
@@ -227,13 +234,15 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
         }
         return okm;
     };
-    uint4 v[CLS_RPT / 2];
-    unsigned okm = 0;
+    // register ring of three tiles: the loads of the tile after next are issued before this tile is processed
+    uint4 v[CLS_RPT / 2], vn[CLS_RPT / 2];
+    unsigned okm = 0, okn = 0;
     if ((int64_t)blockIdx.x < n_tiles) okm = load_tile(blockIdx.x, v);
+    if ((int64_t)blockIdx.x + gridDim.x < n_tiles) okn = load_tile(blockIdx.x + gridDim.x, vn);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint4 vn[CLS_RPT / 2];
-        unsigned okn = 0;
-        if (tile + gridDim.x < n_tiles) okn = load_tile(tile + gridDim.x, vn);
+        uint4 vnn[CLS_RPT / 2];
+        unsigned oknn = 0;
+        if (tile + 2 * (int64_t)gridDim.x < n_tiles) oknn = load_tile(tile + 2 * (int64_t)gridDim.x, vnn);
         bool ok[CLS_RPT];
 #pragma unroll
         for (int k = 0; k < CLS_RPT; ++k) ok[k] = (okm >> k) & 1u;
@@ -288,8 +297,12 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
         if (threadIdx.x == 0) *s_cnt = 0;
         __syncthreads();            // the reset must precede the next tile's staging atomics
 #pragma unroll
-        for (int l = 0; l < CLS_RPT / 2; ++l) v[l] = vn[l];
+        for (int l = 0; l < CLS_RPT / 2; ++l) {
+            v[l] = vn[l];
+            vn[l] = vnn[l];
+        }
         okm = okn;
+        okn = oknn;
     }
 
     if (SMEM_DIAG) {
