@@ -154,13 +154,24 @@ def run_reference(args, rank):
     """The reference arm: the CPU port of the reference path on the host cores, rank 0 only."""
     if rank != 0:
         return
-    cfg = args.config or ('C2' if args.gpus == 1 else 'C3')
     scale = min(1.0, args.scale)
     from bin3c_b200 import synth
-    kw = dict(synth.CONFIGS[cfg])
-    sample = int(min(kw['n_pairs'] * scale, CPU_SAMPLE_PAIRS))
-    kw['n_pairs'] = sample              # the first `sample` pairs of the config's stream (same seed)
-    com = synth.make_community(**kw)
+    if args.gpus > 1 and not args.config:
+        # the workload of our arm at N GPUs (dist.bench_main): a community of 100 N genomes / 50k N contigs with a
+        # C2-sized shard of pairs per GPU; the bounded sample is rank 0's shard
+        sample = int(min(50_000_000 * scale, CPU_SAMPLE_PAIRS))
+        n_genomes, n_contigs, seed = 100 * args.gpus, 50_000 * args.gpus, 1002
+        com = synth.make_shard(n_genomes, n_contigs, sample, seed=seed, rank=0)
+        workload = 'weak scaling of C2: {} genomes, {} contigs, {} pairs = 50000000 per GPU (seed {}); sample: the ' \
+                   '{} pairs of rank 0\'s shard'.format(n_genomes, n_contigs, 50_000_000 * args.gpus, seed, sample)
+    else:
+        cfg = args.config or 'C2'
+        kw = dict(synth.CONFIGS[cfg])
+        sample = int(min(kw['n_pairs'] * scale, CPU_SAMPLE_PAIRS))
+        kw['n_pairs'] = sample              # the first `sample` pairs of the config's stream (same seed)
+        com = synth.make_community(**kw)
+        workload = '{}: {} contigs, first {} pairs of the synthetic community (seed {})'.format(
+            cfg, kw['n_contigs'], sample, kw['seed'])
     for _ in range(min(args.warmup, 1)):
         cpu_oracle_run(com, sample)
     times = [cpu_oracle_run(com, sample) for _ in range(max(args.steps, 1))]
@@ -170,8 +181,7 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': t * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u32 counts / f64 balancing', 'data': 'synthetic',
-        'config': {'workload': '{}: {} contigs, first {} pairs of the synthetic community (seed {})'.format(
-            cfg, kw['n_contigs'], sample, kw['seed'])},
+        'config': {'workload': workload},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
                          'sample': '{} pairs per step, NumPy/SciPy port of the reference path; accumulation on {} '
                                    'threads, SciPy KR single-threaded; box has {} cores'.format(
