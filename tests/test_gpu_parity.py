@@ -448,6 +448,61 @@ def test_contact_map_end_to_end(dev, golden):
     assert _relerr(cm2.processed_map.tocsr().data, g['bal_data']) <= REL_TOL
 
 
+def test_bam_file_to_edge_file(dev, tmp_path):
+    """
+    The path with the steps either side of it: a name-sorted BAM written from the golden community's records (plus
+    unmapped / secondary / supplementary / unpaired records the pairing loop must skip) -> native BAM reader ->
+    ContactMap -> edge list -> native edge writer; matrix, counters, mask and edges against the golden vector.
+    """
+    import bam_writer
+    from conftest import load_golden
+    from bin3c_b200 import bam_io, cluster
+    from bin3c_b200.contact_map import ContactMap
+    g = load_golden('c1mini')
+    rec = g['records']
+    ti = (rec & np.uint64(0x7fffffff)).astype(np.int64)
+    tj = ((rec >> np.uint64(32)) & np.uint64(0x7fffffff)).astype(np.int64)
+    ok = ((rec >> np.uint64(31)) & np.uint64(1)).astype(bool)
+    n_refs = int(g['n_refs'])
+    lengths = np.full(n_refs, 500, dtype=np.int64)
+    sites = np.ones(n_refs, dtype=np.int64)
+    lengths[g['ref_index']] = g['lengths']
+    sites[g['ref_index']] = g['sites']
+    rng = np.random.default_rng(5)
+    alns = []
+    for k, (a, b, p) in enumerate(zip(ti.tolist(), tj.tolist(), ok.tolist())):
+        name = 'pair%07d' % k
+        q1, q2 = (60, 60) if p else ((60, 3) if k & 1 else (7, 60))            # a failed pair has one poor mate
+        alns.append(dict(name=name, flag=0x41, tid=a, pos=10, mapq=q1, cigar=[(0, 100)]))
+        if k % 97 == 0:                                                         # a supplementary record between the mates
+            alns.append(dict(name=name, flag=0x841, tid=int(rng.integers(n_refs)), pos=5, mapq=60, cigar=[(0, 30)]))
+        alns.append(dict(name=name, flag=0x81, tid=b, pos=50, mapq=q2, cigar=[(0, 100)]))
+        if k % 131 == 0:                                                        # an unpaired informative read
+            alns.append(dict(name='single%d' % k, flag=0x41, tid=a, pos=1, mapq=60, cigar=[(0, 50)]))
+        if k % 173 == 0:                                                        # an unmapped pair
+            alns.append(dict(name='unm%d' % k, flag=0x4d, tid=-1, pos=-1, mapq=0, cigar=[]))
+            alns.append(dict(name='unm%d' % k, flag=0x8d, tid=-1, pos=-1, mapq=0, cigar=[]))
+    path = str(tmp_path / 'hic.bam')
+    bam_writer.write_bam(path, ['ref%05d' % i for i in range(n_refs)], lengths.tolist(), alns, block_bytes=30000, level=1)
+    pr, stats = bam_io.pair_records_from_bam(path, sites=sites, min_mapq=60)
+    assert stats['pairs'] == len(rec) and np.array_equal(pr.records, rec)
+    cm = ContactMap(pr, ['synthetic'], None, None, min_mapq=60, min_len=int(g['min_len']), min_sig=int(g['min_sig']),
+                    random_seed=1)
+    assert [cm.pair_counts[k] for k in ('accepted', 'ref_excluded', 'poor_match')] == g['counts'].tolist()
+    sm = cm.seq_map
+    assert np.array_equal(sm.row, g['map_row']) and np.array_equal(sm.col, g['map_col'])
+    assert np.array_equal(sm.data, g['map_data'])
+    assert np.array_equal(cm.get_primary_acceptance_mask(), g['mask'])
+    u, v, w, scl = cluster.to_edges(cm, norm=True, bisto=True, scale=True)
+    assert np.array_equal(u, g['edge_u']) and np.array_equal(v, g['edge_v'])
+    assert _relerr(w, g['edge_w']) <= REL_TOL
+    f = cluster.write_edges(u, v, w, str(tmp_path))
+    lines = open(f).read().splitlines()
+    assert len(lines) == len(u)
+    a, b, c = lines[0].split(' ')
+    assert (int(a), int(b)) == (int(u[0]), int(v[0])) and float(c) == float(w[0])       # repr round-trips
+
+
 def test_none_accepted(dev):
     from conftest import load_golden
     from bin3c_b200.exceptions import NoneAcceptedException
