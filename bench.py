@@ -211,7 +211,19 @@ def spmv_microbench(dev, torch, peak, rows=250_000, nnz=100_000_000, reps=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     nbytes = 12 * csr.nnz + 24 * csr.n
-    return {'workload': 'C5 point: block-structured symmetric CSR, {} rows, {} nnz (seed 1005), {} MB by formula'.format(
+    # the same product on the host: SciPy's csr_matvec, single-threaded, as kr_biostochastic calls it (sparse_utils.py:136)
+    import scipy.sparse as sp
+    m_host = sp.csr_matrix((data, indices, indptr), shape=(rows, rows))
+    u_host = np.random.default_rng(0).uniform(0.5, 1.5, rows)
+    m_host.dot(u_host)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        y_host = m_host.dot(u_host)
+    scipy_ms = (time.perf_counter() - t0) / 3 * 1e3
+    err = float(np.max(np.abs(y.cpu().numpy() - y_host)) / np.max(np.abs(y_host)))
+    assert err < 1e-12, 'SpMV differs from SciPy: {}'.format(err)
+    return {'scipy_csr_matvec_ms': scipy_ms, 'speedup_vs_scipy_1_core': scipy_ms / ms, 'max_rel_diff_vs_scipy': err,
+            'workload': 'C5 point: block-structured symmetric CSR, {} rows, {} nnz (seed 1005), {} MB by formula'.format(
                 csr.n, csr.nnz, nbytes // 1000000),
             'kernels': 'k_spmv + k_spmv_collect (the SpMV phase of k_kr_persistent as a stand-alone launch)',
             'ms_per_spmv': ms, 'gbs': nbytes / ms / 1e6, 'peak': peak, 'frac': nbytes / ms / 1e6 / peak, 'reps': reps}
