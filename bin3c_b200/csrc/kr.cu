@@ -12,18 +12,27 @@
 // speed on this part.  So u is gathered from SHARED memory: the columns are cut into S slabs of
 // W <= 28672 entries (224 KB of fp64) and the matrix is re-laid once per balancing run as a
 // slab-major STREAM: all entries of slab 0 row by row, then slab 1, ...  An entry is its fp64 value
-// plus a 16-bit slab-local column whose top bit marks the first entry of a (row, slab) segment:
-// 10 B per non-zero instead of CSR's 12, and no row pointers are read by the SpMV at all.  A CTA --
-// one per SM -- owns a contiguous range of 2048-entry tiles, brings the slab of u into shared
-// memory with TMA bulk copies (cp.async.bulk + mbarrier) and streams its tiles with 256-bit loads
-// issued two tiles ahead (register ring).  Every warp reduces its own 128 entries with a
-// segmented scan in registers (start flags -> ballots -> 5 shuffle steps), writes the sums of the
-// segments that end inside its chunk, and leaves (head, tail) partials; one warp per tile stitches
-// the 16 chunks together and carries the open segment into the next tile, so the cost per entry
-// does not depend on the row lengths (heavy-tailed contig rows, empty rows).  A segment that
-// crosses a CTA's range is finished by the vector phase that consumes it, from one boundary record
-// per CTA.  Matrices wider than SLAB_S_MAX slabs use the same stream with 32-bit columns and gather
-// u through L1/L2 ("gather form"), unless their (row, slab) cells hold SLAB_DENSE_CELL entries or more on average.
+// plus a 16-bit slab-local column: 10 B per non-zero instead of CSR's 12, and no row pointers are
+// read by the SpMV at all.  Every (row, slab) segment is padded with zero entries to whole 8-entry
+// PIECES, so a segment can only start at the first entry of a piece: one start flag per piece.
+// The stream is cut into CHUNKS of 512 entries (two pieces per lane, stored piece-major so that a
+// piece is one coalesced 64-byte-per-lane load).  A CTA -- one per SM -- owns a contiguous range
+// of chunks inside ONE slab, brings that slab of u into shared memory with TMA bulk copies
+// (cp.async.bulk + mbarrier), and each of its 16 warps streams its own contiguous run of chunks
+// with 256-bit loads issued three pieces ahead (register ring), with no block-wide synchronisation
+// inside the run.  A piece is added up as a fixed tree; a lane's pieces extend or close its open
+// segment; at the end of a chunk the 32 lane runs are stitched by one segmented scan (flag counts
+// from two ballots, sums by 5 shuffle steps), the warp's runs by one warp per CTA, and a segment
+// that crosses a CTA's range is finished by the vector phase that consumes it, from one boundary
+// record per CTA -- so the cost per entry does not depend on the row lengths (heavy-tailed contig
+// rows, empty rows) and nothing is accumulated with atomics.  Matrices wider than SLAB_S_MAX slabs
+// use the same stream with 32-bit columns and gather u through L1/L2 ("gather form"), unless their
+// (row, slab) cells hold SLAB_DENSE_CELL entries or more on average.
+//
+// Vector phases.  One CTA per 1024-row chunk, two rows per thread, always the same rows in the same
+// thread; every phase issues all of its L2 loads first, then computes and stores.  Four grid
+// barriers per CG step (dir | SpMV | w | step); a barrier is one word: red.release to arrive (the
+// release fence costs ~0.9 us: it drains the CTA's stores), ld.acquire to poll.
 //
 // Reductions (dot products, min, max) use fixed 1024-row chunks with a fixed tree inside the
 // chunk and an in-order sum over chunks: the value does not depend on the grid size or on how
