@@ -52,6 +52,9 @@ SIGNATURES = {
     'b3c_bam_stats': (C.c_int, [_p, _p, _i32]),
     'b3c_edges_write': (_i64, [C.c_char_p, _p, _p, _p, _i64, C.c_char, _i32]),
     'b3c_edges_write_fmt': (_i64, [C.c_char_p, _p, _p, _p, _i64, C.c_char, _i32, _i32]),
+    'b3c_records_bytes': (_i32, [_i64]),
+    'b3c_records_pack': (_i64, [_p, _i64, _i32, _p, _i32]),
+    'b3c_records_unpack': (_i64, [_p, _i64, _i32, _p]),
     'b3c_format_weight': (_i32, [C.c_double, _p, _i32]),
     'b3c_format_weight_fmt': (_i32, [C.c_double, _i32, _p, _i32]),
 }
@@ -178,6 +181,29 @@ def pair_records_from_bam(path, sites=None, min_mapq=60, strong=None, min_insert
         bam.set_filter(min_mapq=min_mapq, strong=strong, min_insert=min_insert, tid2idx=tid2idx)
         records = bam.read_all()
         return PairRecords(bam.lengths, s, records, references=bam.references), bam.stats()
+
+
+def records_bytes(n_refs):
+    """The narrowest record (5, 6 or 8 bytes) that holds the reference ids of a table of n_refs entries."""
+    return int(lib.b3c_records_bytes(int(n_refs)))
+
+
+def pack_records(records, bytes_per_record, out=None, threads=0):
+    """uint64 native records -> narrow records (uint8 array, length a multiple of 8) for HotPath / add_pairs_packed."""
+    r = np.ascontiguousarray(records, dtype=np.uint64)
+    nbytes = (len(r) * bytes_per_record + 7) // 8 * 8
+    if out is None:
+        out = np.empty(nbytes, dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.flags.c_contiguous and len(out) >= nbytes
+    check(lib.b3c_records_pack(r.ctypes.data, len(r), int(bytes_per_record), out.ctypes.data, int(threads)))
+    return out[:nbytes]
+
+
+def unpack_records(packed, n, bytes_per_record):
+    b = np.ascontiguousarray(packed, dtype=np.uint8)
+    out = np.empty(int(n), dtype=np.uint64)
+    check(lib.b3c_records_unpack(b.ctypes.data, int(n), int(bytes_per_record), out.ctypes.data))
+    return out
 
 
 def format_weight(w, float_style=FLOAT_REPR):

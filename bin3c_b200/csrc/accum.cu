@@ -150,6 +150,7 @@ __global__ void k_rank_verify(const int32_t *__restrict__ lut, int32_t n_refs, i
 struct ClsParams {
     const uint64_t *rec;
     int64_t n_rec;
+    int32_t rec_bytes;       // 8: native records; 5 or 6: narrow records (b3c_accum_add_pairs_packed)
     const int32_t *lut;
     int32_t n_refs, n_seq;
     int b;
@@ -218,6 +219,33 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
     auto load_tile = [&](int64_t tile, uint4 (&v)[CLS_RPT / 2]) -> unsigned {
         const int64_t base = tile * CLS_TILE;
         unsigned okm = 0;
+        if (P.rec_bytes != 8) {
+            // narrow records: B bytes each, little endian, tid1 in bits [0, tb), the pass flag in bit tb, tid2 in
+            // bits [tb + 1, 2 tb + 1), tb = (8 B - 1) / 2.  A record is cut out of the one or two 8-byte words that
+            // hold it and widened to the native (lo, hi) halves, so the rest of the kernel does not change.
+            const int B = P.rec_bytes, tb = (8 * B - 1) / 2;
+            const uint64_t tmask = (1ull << tb) - 1ull;
+            const int64_t last_word = (P.n_rec * B - 1) >> 3;
+#pragma unroll
+            for (int l = 0; l < CLS_RPT / 2; ++l) {
+                uint32_t h[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int64_t i = base + ((int64_t)l * CLS_THREADS + threadIdx.x) * 2 + q;
+                    if (i < P.n_rec) {
+                        const int64_t o = i * B, w = o >> 3;
+                        const int sh = (int)(o & 7) * 8;
+                        uint64_t r = __ldg(P.rec + w) >> sh;
+                        if (sh + 8 * B > 64) r |= __ldg(P.rec + (w < last_word ? w + 1 : last_word)) << (64 - sh);
+                        h[2 * q] = (uint32_t)(r & tmask) | ((uint32_t)((r >> tb) & 1ull) << 31);
+                        h[2 * q + 1] = (uint32_t)((r >> (tb + 1)) & tmask);
+                        okm |= 1u << (2 * l + q);
+                    }
+                }
+                v[l] = make_uint4(h[0], h[1], h[2], h[3]);
+            }
+            return okm;
+        }
 #pragma unroll
         for (int l = 0; l < CLS_RPT / 2; ++l) {
             const int64_t i = base + ((int64_t)l * CLS_THREADS + threadIdx.x) * 2;
@@ -1191,7 +1219,21 @@ int b3c_accum_reset(void *d_ws, void *stream) {
     return B3C_OK;
 }
 
+static int accum_add(void *d_ws, const void *d_records, int64_t n_records, int32_t rec_bytes, void *stream);
+
 int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records, void *stream) {
+    return accum_add(d_ws, d_records, n_records, 8, stream);
+}
+
+int b3c_accum_add_pairs_packed(void *d_ws, const void *d_bytes, int64_t n_records, int32_t bytes_per_record,
+                               void *stream) {
+    B3C_REQUIRE(bytes_per_record == 5 || bytes_per_record == 6 || bytes_per_record == 8,
+                "bytes_per_record must be 5, 6 or 8");
+    return accum_add(d_ws, d_bytes, n_records, bytes_per_record, stream);
+}
+
+static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int32_t rec_bytes, void *stream) {
+    const uint64_t *d_records = (const uint64_t *)d_records_v;
     AccumState st;
     int rc = get_state(d_ws, &st);
     if (rc) return rc;
@@ -1199,11 +1241,17 @@ int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records
     if (n_records == 0) return B3C_OK;
     B3C_REQUIRE(d_records != nullptr, "null records");
     B3C_REQUIRE(((uintptr_t)d_records & 15) == 0, "records must be 16-byte aligned");
+    if (rec_bytes != 8) {
+        const int tb = (8 * rec_bytes - 1) / 2;
+        B3C_REQUIRE((int64_t)st.n_refs < (1ll << tb) - 1, "%d-byte records hold reference ids below %lld; the table has %d",
+                    rec_bytes, (1ll << tb) - 1, st.n_refs);
+    }
     B3C_REQUIRE(!st.reduced, "accumulator already reduced: call b3c_accum_begin to start a new map");
     char *ws = (char *)d_ws;
     ClsParams P;
     P.rec = d_records;
     P.n_rec = n_records;
+    P.rec_bytes = rec_bytes;
     P.lut = st.d_lut;
     P.n_refs = st.n_refs;
     P.n_seq = st.n_seq;

@@ -197,6 +197,64 @@ int64_t b3c_edges_write_fmt(const char *path, const int32_t *h_u, const int32_t 
     return written;
 }
 
+// ---- narrow pair records (the host side of b3c_accum_add_pairs_packed) ---------------------------------------
+int32_t b3c_records_bytes(int64_t n_refs) {
+    if (n_refs < (1ll << 19) - 1) return 5;
+    if (n_refs < (1ll << 23) - 1) return 6;
+    return 8;
+}
+
+static void pack_range(const uint64_t *in, int64_t lo, int64_t hi, int B, uint8_t *out) {
+    const int tb = (8 * B - 1) / 2;
+    const uint64_t tmask = (1ull << tb) - 1ull;
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint64_t r = in[i];
+        uint64_t t1 = r & 0x7fffffffull, t2 = (r >> 32) & 0x7fffffffull;
+        if (t1 > tmask) t1 = tmask;
+        if (t2 > tmask) t2 = tmask;
+        const uint64_t v = t1 | (((r >> 31) & 1ull) << tb) | (t2 << (tb + 1));
+        uint8_t *o = out + i * B;
+        for (int k = 0; k < B; ++k) o[k] = (uint8_t)(v >> (8 * k));
+    }
+}
+
+int64_t b3c_records_pack(const uint64_t *h_records, int64_t n, int32_t B, uint8_t *h_out, int32_t n_threads) {
+    if (n < 0 || (n > 0 && (!h_records || !h_out)) || (B != 5 && B != 6 && B != 8)) {
+        b3cio::set_err("b3c_records_pack: bad argument");
+        return B3C_IO_ERR_ARG;
+    }
+    const int64_t total = (n * B + 7) / 8 * 8;
+    if (n_threads <= 0) n_threads = (int32_t)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (n < (1 << 16)) n_threads = 1;
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t)
+        th.emplace_back(pack_range, h_records, n * t / n_threads, n * (t + 1) / n_threads, (int)B, h_out);
+    pack_range(h_records, 0, n / n_threads, (int)B, h_out);
+    for (auto &t : th) t.join();
+    for (int64_t k = n * B; k < total; ++k) h_out[k] = 0;
+    return total;
+}
+
+int64_t b3c_records_unpack(const uint8_t *h_bytes, int64_t n, int32_t B, uint64_t *h_records) {
+    if (n < 0 || (n > 0 && (!h_bytes || !h_records)) || (B != 5 && B != 6 && B != 8)) {
+        b3cio::set_err("b3c_records_unpack: bad argument");
+        return B3C_IO_ERR_ARG;
+    }
+    const int tb = (8 * B - 1) / 2;
+    const uint64_t tmask = (1ull << tb) - 1ull;
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t v = 0;
+        for (int k = 0; k < B; ++k) v |= (uint64_t)h_bytes[i * B + k] << (8 * k);
+        uint64_t t1 = v & tmask, t2 = (v >> (tb + 1)) & tmask;
+        if (t1 == tmask) t1 = 0x7fffffffull;
+        if (t2 == tmask) t2 = 0x7fffffffull;
+        h_records[i] = t1 | (((v >> tb) & 1ull) << 31) | (t2 << 32);
+    }
+    return n;
+}
+
 int64_t b3c_edges_write(const char *path, const int32_t *h_u, const int32_t *h_v, const double *h_w, int64_t n_edges,
                         char sep, int32_t n_threads) {
     return b3c_edges_write_fmt(path, h_u, h_v, h_w, n_edges, sep, B3C_FLOAT_REPR, n_threads);

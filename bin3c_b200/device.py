@@ -156,6 +156,13 @@ class Accumulator(object):
         assert records.is_cuda and records.element_size() == 8 and records.is_contiguous()
         check(lib.b3c_accum_add_pairs(_ptr(self.ws), _ptr(records), records.numel(), _stream()))
 
+    def add_packed(self, packed, n_records, bytes_per_record):
+        """packed: CUDA uint8 tensor of narrow records (bam_io.pack_records), 16-byte aligned, padded to 8 bytes."""
+        assert packed.is_cuda and packed.element_size() == 1 and packed.is_contiguous()
+        assert packed.numel() >= (int(n_records) * int(bytes_per_record) + 7) // 8 * 8
+        check(lib.b3c_accum_add_pairs_packed(_ptr(self.ws), _ptr(packed), int(n_records), int(bytes_per_record),
+                                             _stream()))
+
     def finish(self, symmetric=True, pool=None):
         """Sort-reduce and emit the canonical CSR.  Returns (DeviceCSR[uint32 counts], info dict)."""
         sizes = (C.c_int64 * 8)()

@@ -61,6 +61,13 @@ int64_t b3c_launch_count(void);
  *              matcher bit (filter order Q12), canonicalise i<=j, count diagonal pairs
  *              directly and append off-diagonal keys (i<<32|j).  May be called many
  *              times (streaming chunks, overlapping H2D copies).
+ *   add_pairs_packed  the same for NARROW records, which make the host->device copy (what bounds the
+ *              end-to-end rate) 5/8 or 6/8 of the size: bytes_per_record B = 5, 6 or 8, record =
+ *              B little-endian bytes holding tid1 in bits [0, tb), the pass flag in bit tb and tid2 in
+ *              bits [tb+1, 2tb+1), tb = (8B-1)/2 (19, 23, 31 bits: B = 8 is the native layout).  Needs
+ *              n_refs < 2^tb - 1; an id outside the table is stored as 2^tb - 1.  The buffer must be
+ *              16-byte aligned and readable up to the next multiple of 8 bytes; a chunk boundary
+ *              must fall on a multiple of 8 records.  bin3c_io.h: b3c_records_pack packs on the host.
  *   reduce     radix sort the keys + run-length reduce; returns sizes to the host:
  *              h_sizes[0] = nnz of the upper triangle incl. diagonal
  *              h_sizes[1] = nnz of the full symmetric matrix
@@ -75,6 +82,8 @@ int b3c_accum_begin(void *d_ws, int64_t ws_bytes, int64_t pair_capacity, int32_t
                     const int32_t *d_tid2idx, int32_t n_refs, void *stream);
 int b3c_accum_reset(void *d_ws, void *stream);
 int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records, void *stream);
+int b3c_accum_add_pairs_packed(void *d_ws, const void *d_bytes, int64_t n_records, int32_t bytes_per_record,
+                               void *stream);
 int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream);
 int b3c_accum_emit_csr(void *d_ws, int symmetric, int64_t *d_indptr, int32_t *d_indices,
                        uint32_t *d_counts, void *stream);

@@ -86,6 +86,15 @@ int64_t b3c_bam_read_pairs(b3c_bam *bam, uint64_t *h_records, int64_t capacity);
  * h_stats[7] uncompressed bytes produced */
 int b3c_bam_stats(const b3c_bam *bam, int64_t *h_stats, int32_t n_stats);
 
+/* Narrow pair records for the host->device copy (include/bin3c_b200.h: b3c_accum_add_pairs_packed).
+ * b3c_records_bytes: the smallest of 5, 6, 8 bytes per record that holds reference ids of a table of n_refs.
+ * b3c_records_pack: n native records -> n * bytes_per_record bytes (h_out sized to the next multiple of 8 bytes;
+ * the tail is zeroed); ids >= 2^tb - 1 (the native out-of-table marker included) become 2^tb - 1.  Returns the
+ * number of bytes written (a multiple of 8) or a negative status.  b3c_records_unpack is the inverse. */
+int32_t b3c_records_bytes(int64_t n_refs);
+int64_t b3c_records_pack(const uint64_t *h_records, int64_t n, int32_t bytes_per_record, uint8_t *h_out, int32_t n_threads);
+int64_t b3c_records_unpack(const uint8_t *h_bytes, int64_t n, int32_t bytes_per_record, uint64_t *h_records);
+
 /* How a weight is printed.  networkx prints it with str(): the shortest round-trip decimal on Python 3
  * (== repr), '%.12g' plus '.0' on integer-looking values on the Python 2.7 the reference pins. */
 typedef enum {

@@ -148,6 +148,64 @@ def test_accumulate_random(dev, n, n_refs, p, rank_lut):
     assert info['map_weight'] == int(want.sum(dtype=np.uint64))
 
 
+@pytest.mark.parametrize('B', [5, 6, 8])
+@pytest.mark.parametrize('n_pairs', [0, 1, 7, 4099, 300_001])
+def test_accumulate_narrow_records(dev, B, n_pairs):
+    """Narrow (5- and 6-byte) records give exactly the matrix and counters of the native 8-byte records: device-
+    resident in one call and in ragged chunks, and streamed from the host through HotPath's staging ring."""
+    import torch
+    from bin3c_b200 import bam_io, synth
+    from bin3c_b200.pipeline import HotPath
+    com = synth.make_community(n_genomes=6, n_contigs=900, n_pairs=max(n_pairs, 1), seed=31 + B)
+    rec = com.records[:n_pairs].copy()
+    if n_pairs > 20:
+        rec[5] = np.uint64(0x7fffffff) | (rec[5] & np.uint64(0xffffffff80000000))     # out-of-table id in mate 1
+        rec[11] = (rec[11] & np.uint64(0xffffffff)) | (np.uint64(0x7fffffff) << np.uint64(32))
+    lut = com.tid2idx()
+    want, winfo = _accumulate(dev, rec, lut, com.n_contigs)
+    packed = bam_io.pack_records(rec, B)
+    assert np.array_equal(bam_io.unpack_records(packed, n_pairs, B), rec)
+    dpk = torch.from_numpy(packed).cuda()
+    for chunk in (max(n_pairs, 8), 1000):                 # one call; ragged chunks of a multiple of 8 records
+        acc = dev.Accumulator(com.n_contigs, lut, max(n_pairs, 1))
+        for lo in range(0, n_pairs, chunk):
+            hi = min(lo + chunk, n_pairs)
+            nb = ((hi - lo) * B + 7) // 8 * 8
+            piece = dpk[lo * B:lo * B + nb]
+            if piece.data_ptr() % 16:                     # a chunk that does not start on 16 bytes is re-staged
+                piece = piece.clone()
+            acc.add_packed(piece, hi - lo, B)
+        got, ginfo = acc.finish()
+        torch.cuda.synchronize()
+        assert ginfo == winfo
+        assert np.array_equal(got.indptr.cpu().numpy(), want.indptr.cpu().numpy())
+        assert np.array_equal(got.indices.cpu().numpy(), want.indices.cpu().numpy())
+        assert np.array_equal(got.data.cpu().numpy(), want.data.cpu().numpy())
+    if n_pairs >= 4099 and B != 8:
+        hp = HotPath(lut, com.lengths, com.sites, pair_capacity=n_pairs, min_sig=1)
+        r8 = hp.run(dev.to_device(rec))
+        n = int(r8['n_edges'])
+        ref = [r8[k][:n].cpu().numpy().copy() for k in ('u', 'v', 'w')]
+        out = hp.run(torch.from_numpy(packed).pin_memory(), to_host=True, record_bytes=B, n_records=n_pairs)
+        assert hp.h2d_bytes == len(packed) and out['n_edges'] == n
+        for k, w in zip(('u', 'v', 'w'), ref):
+            assert np.array_equal(out[k], w)
+        hp.reset()
+        hp.accumulate(packed, chunk_records=1000, record_bytes=B, n_records=n_pairs)      # pageable, many chunks
+        assert hp.acc_info == winfo
+
+
+def test_accumulate_narrow_records_need_a_small_table(dev):
+    import torch
+    lut = np.arange(600_000, dtype=np.int32)              # more references than 19 bits hold
+    acc = dev.Accumulator(600_000, lut, 16)
+    with pytest.raises(AssertionError):
+        acc.add_packed(torch.zeros(64, dtype=torch.uint8, device='cuda'), 8, 5)
+    acc.add_packed(torch.zeros(64, dtype=torch.uint8, device='cuda'), 8, 6)
+    with pytest.raises(AssertionError):
+        acc.add_packed(torch.zeros(64, dtype=torch.uint8, device='cuda'), 8, 7)
+
+
 def test_accumulate_capacity_error(dev):
     from bin3c_b200 import synth
     from bin3c_b200._cabi import B3CError

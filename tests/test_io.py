@@ -291,3 +291,33 @@ def test_infomap_partition_from_native_edge_file(tmp_path):
         open(str(tmp_path / 'oracle_py2' / 'cm_graph.edges')).read()
     assert parts['native_py2'] == parts['oracle_py2'] == parts['native_repr']
     assert len(parts['native_py2']) > 1
+
+
+@pytest.mark.parametrize('B,n_refs', [(5, 400_000), (6, 5_000_000), (8, 2 ** 31 - 2)])
+def test_narrow_records_round_trip(B, n_refs):
+    """b3c_records_pack / unpack: B-byte little-endian records, tid1 | pass << tb | tid2 << (tb + 1), tb = (8B - 1) / 2;
+    out-of-table ids (the native 0x7fffffff marker) map to the all-ones id of the narrow layout and back."""
+    assert bam_io.records_bytes(n_refs) == B
+    assert bam_io.records_bytes((1 << 19) - 2) == 5 and bam_io.records_bytes((1 << 19) - 1) == 6
+    assert bam_io.records_bytes((1 << 23) - 2) == 6 and bam_io.records_bytes((1 << 23) - 1) == 8
+    rng = np.random.default_rng(B)
+    for n in (0, 1, 5, 100_003):
+        t1 = rng.integers(0, n_refs, n, dtype=np.uint64)
+        t2 = rng.integers(0, n_refs, n, dtype=np.uint64)
+        ok = rng.integers(0, 2, n, dtype=np.uint64)
+        t1[::97] = 0x7fffffff
+        rec = t1 | (ok << np.uint64(31)) | (t2 << np.uint64(32))
+        packed = bam_io.pack_records(rec, B, threads=3)
+        assert packed.dtype == np.uint8 and len(packed) == (n * B + 7) // 8 * 8
+        assert not packed[n * B:].any()
+        assert np.array_equal(bam_io.unpack_records(packed, n, B), rec)
+        if n:                                     # the documented bit layout, checked independently on record 1 (or 0)
+            k = min(1, n - 1)
+            tb = (8 * B - 1) // 2
+            v = int.from_bytes(packed[k * B:(k + 1) * B].tobytes(), 'little')
+            a = int(rec[k]) & 0x7fffffff
+            assert v & ((1 << tb) - 1) == min(a, (1 << tb) - 1)
+            assert (v >> tb) & 1 == (int(rec[k]) >> 31) & 1
+            assert (v >> (tb + 1)) & ((1 << tb) - 1) == (int(rec[k]) >> 32) & 0x7fffffff
+    with pytest.raises(AssertionError):
+        bam_io.pack_records(np.zeros(4, np.uint64), 7)
