@@ -78,7 +78,7 @@ struct b3c_bam {
     std::thread reader;
     bool stop = false;
     int inflating = -1;                    // ring slot the workers draw blocks from, -1 none
-    int64_t n_blocks = 0, c_bytes = 0, u_bytes = 0;
+    std::atomic<int64_t> n_blocks{0}, c_bytes{0}, u_bytes{0};     // written by the reader thread, read by b3c_bam_stats
     // stream cursor of the parser
     int cur = 0;                           // ring slot being parsed
     bool cur_held = false;
@@ -584,7 +584,8 @@ int64_t b3c_bam_read_pairs(b3c_bam *h, uint64_t *h_records, int64_t capacity) {
 
 int b3c_bam_stats(const b3c_bam *h, int64_t *h_stats, int32_t n_stats) {
     if (!h || !h_stats || n_stats < 0) return B3C_IO_ERR_ARG;
-    const int64_t v[8] = {h->n_aln, h->n_inf, h->n_pairs, h->n_short, h->n_orphan, h->n_blocks, h->c_bytes, h->u_bytes};
+    const int64_t v[8] = {h->n_aln, h->n_inf, h->n_pairs, h->n_short, h->n_orphan, h->n_blocks.load(), h->c_bytes.load(),
+                          h->u_bytes.load()};
     for (int i = 0; i < n_stats && i < 8; ++i) h_stats[i] = v[i];
     return 0;
 }

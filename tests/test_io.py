@@ -321,3 +321,50 @@ def test_narrow_records_round_trip(B, n_refs):
             assert (v >> (tb + 1)) & ((1 << tb) - 1) == (int(rec[k]) >> 32) & 0x7fffffff
     with pytest.raises(AssertionError):
         bam_io.pack_records(np.zeros(4, np.uint64), 7)
+
+
+@pytest.mark.parametrize('sanitizer', ['thread', 'address,undefined'])
+def test_io_sources_under_sanitizers(tmp_path, sanitizer):
+    """The library's own sources, instrumented (TSan for the reader / inflate-pool / parser hand-over and the formatter
+    pool, ASan + UBSan for the record parsing), over good, truncated and corrupted BAM files."""
+    import shutil
+    import subprocess
+    if shutil.which('g++') is None:
+        pytest.skip('no g++')
+    src = os.path.join(ROOT, 'bin3c_b200', 'csrc')
+    exe = str(tmp_path / 'io_sanitize')
+    cmd = ['g++', '-O1', '-g', '-std=c++17', '-pthread', '-fsanitize=' + sanitizer, '-fno-omit-frame-pointer',
+           os.path.join(ROOT, 'tests', 'native', 'io_sanitize.cpp'), os.path.join(src, 'io_bam.cpp'),
+           os.path.join(src, 'io_edges.cpp'), '-o', exe, '-lz']
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        pytest.skip('sanitizer build not available here: ' + res.stdout[-300:])
+    rng = random.Random(3)
+    n_refs = 300
+    refs = ['c{}'.format(i) for i in range(n_refs)]
+    lengths = [1000 + i for i in range(n_refs)]
+    alns = random_alignments(rng, n_refs, 40000, weird=True)
+    good = str(tmp_path / 'good.bam')
+    bam_writer.write_bam(good, refs, lengths, alns, block_bytes=6000, level=1)      # ~900 blocks: several batches
+    want, _ = oracle.pair_alignments(alns, n_refs, min_mapq=20, strong=30)
+    raw = open(good, 'rb').read()
+    trunc, corrupt = str(tmp_path / 'trunc.bam'), str(tmp_path / 'corrupt.bam')
+    open(trunc, 'wb').write(raw[:len(raw) * 3 // 5])
+    bad = bytearray(raw)
+    for k in range(5):
+        bad[len(bad) // 7 * (k + 1)] ^= 0xa5
+    open(corrupt, 'wb').write(bytes(bad))
+    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=1 exitcode=66', ASAN_OPTIONS='detect_leaks=1 exitcode=66',
+               UBSAN_OPTIONS='halt_on_error=1 exitcode=66')
+    for path, threads in ((good, 1), (good, 8), (trunc, 4), (corrupt, 4)):
+        out = subprocess.run([exe, path, str(threads), '20', '30', str(tmp_path / 'e.edges')], stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, text=True, env=env, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        status, n, x, nbytes = out.stdout.split()
+        if path == good:
+            h = 0
+            for r in want.tolist():
+                h ^= (r * 0x9e3779b97f4a7c15) & 0xffffffffffffffff
+            assert int(status) == 0 and int(n) == len(want) and int(x) == h and int(nbytes) > 0
+        else:
+            assert int(status) < 0
