@@ -49,6 +49,8 @@ SIGNATURES = {
     'b3c_bam_header_text': (_i64, [_p, _p, _i64]),
     'b3c_bam_set_filter': (C.c_int, [_p, _i32, _i32, _i32, _p, _i32]),
     'b3c_bam_read_pairs': (_i64, [_p, _p, _i64]),
+    'b3c_bam_set_extent': (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32]),
+    'b3c_bam_read_pairs_extent': (_i64, [_p, _p, _p, _i64]),
     'b3c_bam_stats': (C.c_int, [_p, _p, _i32]),
     'b3c_edges_write': (_i64, [C.c_char_p, _p, _p, _p, _i64, C.c_char, _i32]),
     'b3c_edges_write_fmt': (_i64, [C.c_char_p, _p, _p, _p, _i64, C.c_char, _i32, _i32]),
@@ -120,6 +122,22 @@ class BamPairReader(object):
         check(lib.b3c_bam_set_filter(self._h, int(min_mapq), int(strong or 0), int(min_insert or 0),
                                      t.ctypes.data if t is not None else None, len(t) if t is not None else 0))
 
+    def set_extent(self, tid2idx, grouping):
+        """Also emit extent records (contact_map.py:779-788); `grouping` is a contact_map.ExtentGrouping."""
+        t = np.ascontiguousarray(tid2idx, dtype=np.int32)
+        first = np.ascontiguousarray(grouping.first_bin, dtype=np.int64)
+        ptr = np.ascontiguousarray(grouping.edge_ptr, dtype=np.int64)
+        upper = np.ascontiguousarray(grouping.upper_edges, dtype=np.int64)
+        check(lib.b3c_bam_set_extent(self._h, t.ctypes.data, len(t), first.ctypes.data, ptr.ctypes.data,
+                                     upper.ctypes.data, len(first)))
+
+    def read_pairs_extent(self, capacity):
+        """Up to `capacity` further (pair records, extent records); empty arrays at end of file."""
+        rec = np.empty(int(capacity), dtype=np.uint64)
+        ext = np.empty(int(capacity), dtype=np.uint64)
+        n = check(lib.b3c_bam_read_pairs_extent(self._h, rec.ctypes.data, ext.ctypes.data, int(capacity)))
+        return rec[:n], ext[:n]
+
     def read_pairs(self, capacity, out=None):
         """Up to `capacity` further records (an empty array at end of file)."""
         if out is None:
@@ -160,7 +178,8 @@ class BamPairReader(object):
             pass
 
 
-def pair_records_from_bam(path, sites=None, min_mapq=60, strong=None, min_insert=None, min_len=None, threads=0):
+def pair_records_from_bam(path, sites=None, min_mapq=60, strong=None, min_insert=None, min_len=None, threads=0,
+                          bin_size=None):
     """
     BAM file -> (PairRecords, stats): the object `ContactMap(bam_file=...)` takes in this package.
 
@@ -178,7 +197,25 @@ def pair_records_from_bam(path, sites=None, min_mapq=60, strong=None, min_insert
             assert min_len is not None, 'min_insert needs min_len'
             keep = (bam.lengths >= min_len) & (s >= 0)                 # contact_map.py:545-564
             tid2idx = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+        extent = None
+        if bin_size:
+            # the extent map (bin3C mkmap --bin-size): bins over the sequences that pass the length filter
+            from .contact_map import ExtentGrouping
+            assert min_len is not None, 'bin_size needs min_len'
+            keep = (bam.lengths >= min_len) & (s >= 0)
+            tid2idx = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+            bam.set_extent(tid2idx, ExtentGrouping.from_lengths(bam.lengths[keep], bin_size))
         bam.set_filter(min_mapq=min_mapq, strong=strong, min_insert=min_insert, tid2idx=tid2idx)
+        if bin_size:
+            parts = []
+            while True:
+                r, e = bam.read_pairs_extent(1 << 22)
+                if len(r) == 0:
+                    break
+                parts.append((r, e))
+            records = np.concatenate([p[0] for p in parts]) if parts else np.empty(0, dtype=np.uint64)
+            extent = np.concatenate([p[1] for p in parts]) if parts else np.empty(0, dtype=np.uint64)
+            return PairRecords(bam.lengths, s, records, references=bam.references, extent_records=extent), bam.stats()
         records = bam.read_all()
         return PairRecords(bam.lengths, s, records, references=bam.references), bam.stats()
 

@@ -12,6 +12,7 @@ the contig x contig contact matrix, with the same names, arguments and error beh
     ContactMap.get_subspace                      contact_map.py:947-999
     ContactMap._bisto_seq / _get_sites / _norm_seq   contact_map.py:1087-1145
     SeqOrder (the five bookkeeping methods the path uses)   contact_map.py:159-447
+    ExtentGrouping + the extent (binned) map accumulation   contact_map.py:116-156, 779-788, 801-803
 
 The difference from the reference is the input: BAM decoding (pysam) is outside the path
 (SURVEY.md section 8f), so `bam_file` is a PairRecords object -- the BAM header's reference
@@ -42,9 +43,13 @@ class PairRecords(object):
     :param sites: restriction-site count per reference; stands in for the FASTA pass of
                   contact_map.py:520-531.  A negative value marks "not present in the FASTA".
     :param records: uint64 packed pair records, NumPy array (host) or CUDA tensor (device)
+    :param extent_records: optional, same length: the pair's records at BIN level (global bin numbers of the two
+                  5'-end positions in place of reference ids; bam_io.pair_records_from_bam(bin_size=...)),
+                  needed by ContactMap(bin_size=...)
     """
 
-    def __init__(self, lengths, sites, records, references=None):
+    def __init__(self, lengths, sites, records, references=None, extent_records=None):
+        self.extent_records = extent_records      # bin-level records for the extent map (bam_io, bin_size=...)
         self.lengths = np.asarray(lengths, dtype=np.int64)
         self.sites = np.asarray(sites, dtype=np.int64)
         assert self.lengths.shape == self.sites.shape
@@ -66,6 +71,56 @@ class PairRecords(object):
         lengths[com.ref_index] = com.lengths
         sites[com.ref_index] = com.sites
         return cls(lengths, sites, com.records)
+
+
+class ExtentGrouping(object):
+    """
+    The bins of the extent map (contact_map.py:116-156).  A sequence gets length // bin_size bins (the reference is
+    Python 2: `/` on ints), at least one, and one more when the remainder is half a bin or more; the bin edges are
+    np.linspace(0, length, num_bins + 1) truncated to integers.  `map[i]` is the reference's per-sequence array of
+    (upper edge, global bin) pairs; `first_bin`, `edge_ptr` and `upper_edges` are the same thing as flat arrays for
+    the BAM reader (include/bin3c_io.h: b3c_bam_set_extent).
+    """
+
+    def __init__(self, seq_info, bin_size):
+        self._build([s.length for s in seq_info], bin_size)
+
+    @classmethod
+    def from_lengths(cls, lengths, bin_size):
+        g = cls.__new__(cls)
+        g._build(np.asarray(lengths).tolist(), bin_size)
+        return g
+
+    def _build(self, lengths, bin_size):
+        from .exceptions import ZeroLengthException
+        self.bin_size = bin_size
+        self.bins, self.map, self.borders, self.centers = [], [], [], []
+        self.total_bins = 0
+        first, upper = [], []
+        for n, length in enumerate(lengths):
+            length = int(length)
+            if length == 0:
+                raise ZeroLengthException(n)
+            num_bins = length // bin_size
+            if num_bins == 0:
+                num_bins += 1
+            # non-integer discrepancy: contract / expand all bins equally, the threshold being half a bin
+            if length % bin_size != 0 and length / float(bin_size) - num_bins >= 0.5:
+                num_bins += 1
+            edges = np.linspace(0, length, num_bins + 1, endpoint=True).astype(np.int64)
+            self.bins.append(num_bins)
+            first_bin, last_bin = self.total_bins, self.total_bins + num_bins
+            self.map.append(np.vstack((edges[1:], np.arange(first_bin, last_bin))).T)
+            self.borders.append(np.array([first_bin, last_bin], dtype=np.int64))
+            self.total_bins += num_bins
+            c_nk = edges[:-1] + 0.5 * (edges[1] - edges[0]) - 0.5 * length
+            self.centers.append(c_nk.reshape((1, len(c_nk))))
+            first.append(first_bin)
+            upper.append(edges[1:])
+        self.bins = np.array(self.bins)
+        self.first_bin = np.array(first, dtype=np.int64)
+        self.edge_ptr = np.concatenate([[0], np.cumsum(self.bins)]).astype(np.int64)
+        self.upper_edges = np.concatenate(upper).astype(np.int64) if upper else np.empty(0, dtype=np.int64)
 
 
 class SeqOrder(object):
@@ -130,7 +185,8 @@ class ContactMap(object):
         assert isinstance(bam_file, PairRecords), \
             'bam_file must be a PairRecords (BAM decoding is outside the accelerated path)'
         assert tip_size is None, 'tip-based maps are out of scope (unreachable from the bin3C CLI)'
-        assert bin_size is None, 'extent (binned) maps are out of scope (plot-only consumer)'
+        assert not bin_size or bam_file.extent_records is not None, \
+            'bin_size needs extent records: bam_io.pair_records_from_bam(path, bin_size=..., min_len=...)'
         assert not min_insert, 'min_insert needs alignment positions, which packed pair records do not carry'
 
         self.strong = strong
@@ -189,6 +245,9 @@ class ContactMap(object):
         logger.info('References excluded: {}'.format(ref_count))
 
         self.order = SeqOrder(self.seq_info)
+
+        if self.bin_size:
+            self.grouping = ExtentGrouping(self.seq_info, self.bin_size)      # contact_map.py:581-583
 
         # accumulate
         self._bin_map(bam_file)
@@ -274,6 +333,22 @@ class ContactMap(object):
         counts['poor_match'] = info['poor_match']
         self.pair_counts = counts
         self._map_weight = info['map_weight']
+
+        if self.bin_size:
+            # the extent map (contact_map.py:687-691, 779-788, 801-803): the same sort-reduce over the bin-level
+            # records, bins being their own index table; every pair the contig map accepts is tallied
+            logger.info('Initialising contact map of {0}x{0} fragment bins, representing {1} bp over {2} sequences'
+                        .format(self.grouping.total_bins, self.total_len, self.total_seq))
+            nb = self.grouping.total_bins
+            ident = np.arange(nb, dtype=np.int32)
+            ext = bam.extent_records
+            n_ext = int(ext.numel()) if isinstance(ext, torch.Tensor) else len(ext)
+            hx = HotPath(ident, np.ones(nb, dtype=np.int32), np.ones(nb, dtype=np.int32), min_len=1, min_sig=1,
+                         pair_capacity=n_ext)
+            ecsr = hx.accumulate(ext, chunk_records=chunk_records)
+            assert hx.acc_info['accepted'] == info['accepted'], 'extent records disagree with the pair records'
+            self.extent_map = ecsr.to_scipy_coo()
+            hx = None
 
         logger.info('Pair accounting: {}'.format(counts))
         logger.info('Total extent map weight {}'.format(self.map_weight()))

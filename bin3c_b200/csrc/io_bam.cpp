@@ -92,10 +92,14 @@ struct b3c_bam {
     // filter
     int32_t min_mapq = 0, strong = 0, min_insert = 0;
     std::vector<int32_t> tid2idx;
+    // extent map (contact_map.py:779-788): bins per sequence
+    bool extent = false;
+    std::vector<int64_t> ext_first, ext_ptr, ext_edges;
     // pairing state (contact_map.py:720-731): the pending first mate
     bool have_r1 = false;
     std::string r1_name;
     int32_t r1_tid = 0, r1_pos = 0;
+    int64_t r1_pos5 = 0;
     uint16_t r1_flag = 0;
     bool r1_match = false;
     bool started = false;
@@ -394,6 +398,7 @@ int parse_header(b3c_bam *h, int require_queryname) {
 
 struct Aln {
     int32_t tid, pos;
+    int64_t pos5;            // 5'-end position: pos, or pos + reference span for a reverse read (contact_map.py:757-758)
     uint16_t flag;
     bool match;
     const char *name;
@@ -428,6 +433,17 @@ int next_alignment(b3c_bam *h, Aln *a) {
         }
     }
     a->match = m;
+    a->pos5 = a->pos;
+    if (h->extent && (a->flag & 0x10)) {
+        // r.alen = pysam reference_length: the CIGAR operations that consume the reference (M, D, N, =, X)
+        const uint8_t *cg = p + 32 + l_name;
+        int64_t span = 0;
+        for (uint32_t k = 0; k < n_cig; ++k) {
+            const uint32_t op = rd32(cg + 4 * k), t = op & 0xf;
+            if (t == 0 || t == 2 || t == 3 || t == 7 || t == 8) span += op >> 4;
+        }
+        a->pos5 += span;
+    }
     return 1;
 }
 
@@ -523,11 +539,71 @@ int b3c_bam_set_filter(b3c_bam *h, int32_t min_mapq, int32_t strong, int32_t min
     h->strong = strong < 0 ? 0 : strong;
     h->min_insert = min_insert < 0 ? 0 : min_insert;
     if (h_tid2idx) h->tid2idx.assign(h_tid2idx, h_tid2idx + n_refs);
-    else h->tid2idx.clear();
+    else if (!h->extent) h->tid2idx.clear();          // the extent table (b3c_bam_set_extent) is kept
     return 0;
 }
 
+static int64_t read_pairs_impl(b3c_bam *h, uint64_t *h_records, uint64_t *h_extent, int64_t capacity);
+
 int64_t b3c_bam_read_pairs(b3c_bam *h, uint64_t *h_records, int64_t capacity) {
+    return read_pairs_impl(h, h_records, nullptr, capacity);
+}
+
+int64_t b3c_bam_read_pairs_extent(b3c_bam *h, uint64_t *h_records, uint64_t *h_extent_records, int64_t capacity) {
+    if (!h || !h->extent || (!h_extent_records && capacity > 0)) {
+        set_err("b3c_bam_read_pairs_extent: call b3c_bam_set_extent first");
+        return B3C_IO_ERR_ARG;
+    }
+    return read_pairs_impl(h, h_records, h_extent_records, capacity);
+}
+
+int b3c_bam_set_extent(b3c_bam *h, const int32_t *h_tid2idx, int32_t n_refs, const int64_t *h_first_bin,
+                       const int64_t *h_edge_ptr, const int64_t *h_upper_edges, int32_t n_seq) {
+    if (!h || !h_tid2idx || !h_first_bin || !h_edge_ptr || !h_upper_edges || n_seq < 0 ||
+        n_refs != (int32_t)h->ref_names.size()) {
+        set_err("b3c_bam_set_extent: bad argument (the tid -> index table must cover all %d references)",
+                h ? (int)h->ref_names.size() : 0);
+        return B3C_IO_ERR_ARG;
+    }
+    if (h->started) {
+        set_err("b3c_bam_set_extent: records have already been read");
+        return B3C_IO_ERR_ARG;
+    }
+    for (int32_t t = 0; t < n_refs; ++t)
+        if (h_tid2idx[t] >= n_seq) {
+            set_err("b3c_bam_set_extent: index %d of reference %d is outside the %d sequences", h_tid2idx[t], t, n_seq);
+            return B3C_IO_ERR_ARG;
+        }
+    for (int32_t i = 0; i < n_seq; ++i)
+        if (h_edge_ptr[i + 1] <= h_edge_ptr[i] || h_first_bin[i] + (h_edge_ptr[i + 1] - h_edge_ptr[i]) >= 0x7fffffffll) {
+            set_err("b3c_bam_set_extent: sequence %d has no bins, or bin numbers do not fit in 31 bits", i);
+            return B3C_IO_ERR_ARG;
+        }
+    h->tid2idx.assign(h_tid2idx, h_tid2idx + n_refs);
+    h->ext_first.assign(h_first_bin, h_first_bin + n_seq);
+    h->ext_ptr.assign(h_edge_ptr, h_edge_ptr + n_seq + 1);
+    h->ext_edges.assign(h_upper_edges, h_upper_edges + h_edge_ptr[n_seq]);
+    h->extent = true;
+    return 0;
+}
+
+// find_nearest_jit (contact_map.py:49-62): the bin whose upper edge is the first one >= x; past the end, the last
+static uint64_t extent_bin(const b3c_bam *h, int32_t tid, int64_t x, int32_t n_refs) {
+    if (tid < 0 || tid >= n_refs) return BAD_TID;
+    const int32_t ix = h->tid2idx[tid];
+    if (ix < 0) return BAD_TID;
+    const int64_t lo = h->ext_ptr[ix], hi = h->ext_ptr[ix + 1];
+    int64_t a = lo, b = hi;
+    while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        if (h->ext_edges[mid] < x) a = mid + 1;
+        else b = mid;
+    }
+    if (a == hi) a = hi - 1;
+    return (uint64_t)(h->ext_first[ix] + (a - lo));
+}
+
+static int64_t read_pairs_impl(b3c_bam *h, uint64_t *h_records, uint64_t *h_extent, int64_t capacity) {
     if (!h || (!h_records && capacity > 0) || capacity < 0) {
         set_err("b3c_bam_read_pairs: bad argument");
         return B3C_IO_ERR_ARG;
@@ -537,7 +613,7 @@ int64_t b3c_bam_read_pairs(b3c_bam *h, uint64_t *h_records, int64_t capacity) {
     const int32_t n_refs = (int32_t)h->ref_names.size();
     int64_t n = 0;
     while (n < capacity) {
-        Aln a = {0, 0, 0, false, nullptr, 0};
+        Aln a = {0, 0, 0, 0, false, nullptr, 0};
         const int rc = next_alignment(h, &a);
         if (rc < 0) return rc;
         if (rc == 0) {
@@ -556,6 +632,7 @@ int64_t b3c_bam_read_pairs(b3c_bam *h, uint64_t *h_records, int64_t capacity) {
             h->r1_name.assign(a.name, a.name_len);
             h->r1_tid = a.tid;
             h->r1_pos = a.pos;
+            h->r1_pos5 = a.pos5;
             h->r1_flag = a.flag;
             h->r1_match = a.match;
             continue;
@@ -577,6 +654,10 @@ int64_t b3c_bam_read_pairs(b3c_bam *h, uint64_t *h_records, int64_t capacity) {
             }
         }
         const uint64_t t1 = in1 ? (uint32_t)h->r1_tid : BAD_TID, t2 = in2 ? (uint32_t)a.tid : BAD_TID;
+        if (h_extent) {
+            const uint64_t b1 = extent_bin(h, h->r1_tid, h->r1_pos5, n_refs), b2 = extent_bin(h, a.tid, a.pos5, n_refs);
+            h_extent[n] = b1 | ((uint64_t)(pass ? 1u : 0u) << 31) | (b2 << 32);
+        }
         h_records[n++] = t1 | ((uint64_t)(pass ? 1u : 0u) << 31) | (t2 << 32);
     }
     return n;

@@ -16,3 +16,9 @@ class ParsingError(ApplicationException):
     """An error during input parsing (raised at contact_map.py:571-573)"""
     def __init__(self, msg):
         super(ParsingError, self).__init__(msg)
+
+
+class ZeroLengthException(ApplicationException):
+    """Sequence of zero length (raised by ExtentGrouping, contact_map.py:128-129)"""
+    def __init__(self, seq_name):
+        super(ZeroLengthException, self).__init__('Sequence [{}] has zero length'.format(seq_name))

@@ -76,6 +76,20 @@ int b3c_bam_set_filter(b3c_bam *bam, int32_t min_mapq, int32_t strong, int32_t m
  * written (0 = end of file) or a negative status.  Consecutive calls continue the stream. */
 int64_t b3c_bam_read_pairs(b3c_bam *bam, uint64_t *h_records, int64_t capacity);
 
+/* The binned EXTENT map (contact_map.py:779-788; bins from ExtentGrouping, :116-156).  After b3c_bam_set_extent the
+ * 5'-end position of every record is tracked (r.pos, or r.pos + r.alen for a reverse read, :757-758) and
+ * b3c_bam_read_pairs_extent writes, beside each pair record, an EXTENT record of the same layout with global bin
+ * numbers in place of reference ids: find_nearest (:49-62) of the position among the upper bin edges of the mate's
+ * sequence.  A mate on a reference outside the index table gets 0x7fffffff.  Fed to an accumulator over total_bins
+ * bins with the identity index table, the extent records give the extent map and the same three counters.
+ *   h_tid2idx       BAM reference id -> sequence index or -1, all n_refs references
+ *   h_first_bin     [n_seq] global number of the first bin of a sequence
+ *   h_edge_ptr      [n_seq + 1] offsets into h_upper_edges; h_upper_edges[h_edge_ptr[i] .. h_edge_ptr[i+1]) are the
+ *                   ascending upper edges of the bins of sequence i (edges[1:] of ExtentGrouping) */
+int b3c_bam_set_extent(b3c_bam *bam, const int32_t *h_tid2idx, int32_t n_refs, const int64_t *h_first_bin,
+                       const int64_t *h_edge_ptr, const int64_t *h_upper_edges, int32_t n_seq);
+int64_t b3c_bam_read_pairs_extent(b3c_bam *bam, uint64_t *h_records, uint64_t *h_extent_records, int64_t capacity);
+
 /* h_stats[0] alignments read (what bam.count(until_eof=True) returns once the file is exhausted)
  * h_stats[1] informative alignments (mapped, primary, not supplementary; :628)
  * h_stats[2] pairs found (records written + short_insert)

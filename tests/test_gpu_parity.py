@@ -737,3 +737,51 @@ def test_fused_counts_form_is_bit_identical(dev):
     for k, w in zip(('u', 'v', 'w'), staged):
         assert np.array_equal(r_fused[k][:n].cpu().numpy(), w)
     assert np.array_equal(r_fused['scl'].cpu().numpy(), staged[3])
+
+
+def test_extent_map_from_bam(dev, tmp_path):
+    """ContactMap(bin_size=...): the binned extent map (contact_map.py:687-691, 779-788, 801-803) accumulated from the
+    BAM reader's bin-level records with the same sort-reduce kernels, against the oracle's restatement."""
+    import random
+    import bam_writer
+    from bin3c_b200 import bam_io
+    from bin3c_b200.contact_map import ContactMap
+    from oracle import oracle
+    rng = random.Random(9)
+    n_refs = 80
+    refs = ['c{}'.format(i) for i in range(n_refs)]
+    lengths = [rng.choice([400, 1200, 2600, 9000, 30000]) for _ in range(n_refs)]
+    alns = []
+    for t in range(6000):
+        a = rng.randrange(n_refs)
+        b = a if rng.random() < 0.6 else rng.randrange(n_refs)
+        for k, tid in enumerate((a, b)):
+            flag = 0x1 | (0x40 if k == 0 else 0x80) | (0x10 if rng.random() < 0.5 else 0)
+            alns.append(dict(name='r%06d' % t, flag=flag, tid=tid, pos=rng.randrange(0, lengths[tid]),
+                             mapq=rng.choice([0, 20, 60, 60, 60]), cigar=[(0, rng.randrange(20, 150))]))
+    path = str(tmp_path / 'ext.bam')
+    bam_writer.write_bam(path, refs, lengths, alns, level=1)
+    bin_size, min_len = 1000, 1000
+    pr, _ = bam_io.pair_records_from_bam(path, min_mapq=30, min_len=min_len, bin_size=bin_size)
+    cm = ContactMap(pr, ['synthetic'], None, None, min_mapq=30, min_len=min_len, min_sig=1, bin_size=bin_size)
+    keep = np.array(lengths) >= min_len
+    lut = np.where(keep, np.cumsum(keep) - 1, -1)
+    og = oracle.extent_grouping(np.array(lengths)[keep], bin_size)
+    want, want_ext, _ = oracle.pair_alignments(alns, n_refs, min_mapq=30, idx_of=lut, grouping=og)
+    assert np.array_equal(pr.extent_records, want_ext)
+    ok = ((want_ext >> np.uint64(31)) & np.uint64(1)).astype(bool)
+    bi = (want_ext & np.uint64(0x7fffffff)).astype(np.int64)
+    bj = ((want_ext >> np.uint64(32)) & np.uint64(0x7fffffff)).astype(np.int64)
+    nb = og['total_bins']
+    dok, counts = oracle.bin_pairs_loop(bi, bj, ok, {b: b for b in range(nb)}, nb)
+    ref = oracle.dok_to_coo(dok, nb)
+    assert cm.grouping.total_bins == nb and cm.extent_map.shape == (nb, nb)
+    got = cm.extent_map
+    assert got.dtype == np.uint32
+    assert np.array_equal(got.row, ref.row) and np.array_equal(got.col, ref.col) and np.array_equal(got.data, ref.data)
+    assert cm.pair_counts['accepted'] == counts['accepted'] > 1000
+    # without extent records the constructor refuses a bin size
+    from bin3c_b200.contact_map import PairRecords
+    with pytest.raises(AssertionError):
+        ContactMap(PairRecords(pr.lengths, pr.sites, pr.records), ['synthetic'], None, None, min_mapq=30,
+                   min_len=min_len, min_sig=1, bin_size=bin_size)

@@ -368,3 +368,78 @@ def test_io_sources_under_sanitizers(tmp_path, sanitizer):
             assert int(status) == 0 and int(n) == len(want) and int(x) == h and int(nbytes) > 0
         else:
             assert int(status) < 0
+
+
+@pytest.mark.parametrize('bin_size,block_bytes', [(1000, 65280), (2500, 1999), (400, 65280)])
+def test_bam_extent_records_match_oracle(tmp_path, bin_size, block_bytes):
+    """The extent map's bin-level records (contact_map.py:756-788): 5'-end positions (reverse reads: pos + reference
+    span of the CIGAR), find_nearest over the bin edges of ExtentGrouping, excluded references marked; against the
+    oracle's restatement, together with the ordinary pair records of the same pass."""
+    from bin3c_b200.contact_map import ExtentGrouping
+    rng = random.Random(bin_size)
+    n_refs = 60
+    refs = ['contig_{}'.format(i) for i in range(n_refs)]
+    lengths = [rng.choice([300, 800, 1500, 2499, 2500, 7000, 20000]) for _ in range(n_refs)]
+    alns = random_alignments(rng, n_refs, 2500)
+    for a in alns:                                             # richer CIGARs and positions up to the contig end
+        if a['cigar'] and rng.random() < 0.5:
+            a['cigar'] = a['cigar'] + [(2, rng.randrange(1, 9)), (0, rng.randrange(1, 50)), (1, 3), (3, 100)]
+        if 0 <= a['tid'] < n_refs:
+            a['pos'] = rng.randrange(0, lengths[a['tid']])
+    path = str(tmp_path / 'x.bam')
+    bam_writer.write_bam(path, refs, lengths, alns, block_bytes=block_bytes)
+    lut = lut_for(lengths, 1000)
+    kept = [l for l in lengths if l >= 1000]
+    og = oracle.extent_grouping(kept, bin_size)
+    g = ExtentGrouping.from_lengths(kept, bin_size)
+    assert g.total_bins == og['total_bins'] and all(np.array_equal(a, b) for a, b in zip(g.map, og['map']))
+    want, want_ext, st = oracle.pair_alignments(alns, n_refs, min_mapq=30, idx_of=lut, grouping=og)
+    with bam_io.BamPairReader(path, threads=3) as bam:
+        bam.set_extent(lut, g)
+        bam.set_filter(min_mapq=30)                            # keeps the extent table
+        recs, exts = [], []
+        while True:
+            r, e = bam.read_pairs_extent(997)
+            if len(r) == 0:
+                break
+            recs.append(r.copy())
+            exts.append(e.copy())
+        assert bam.stats()['pairs'] == st['pairs']
+    got, got_ext = np.concatenate(recs), np.concatenate(exts)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_ext, want_ext)
+    b1 = got_ext & np.uint64(0x7fffffff)
+    assert (b1[b1 != 0x7fffffff] < g.total_bins).all() and (b1 == 0x7fffffff).any()
+    # through the accumulation oracle: the extent map tallies exactly the pairs the contig map accepts
+    ti, tj, ok = (got & np.uint64(0x7fffffff)).astype(np.int64), ((got >> np.uint64(32)) & np.uint64(0x7fffffff)).astype(np.int64), \
+        ((got >> np.uint64(31)) & np.uint64(1)).astype(bool)
+    _, c_seq = oracle.bin_pairs_loop(ti, tj, ok, {t: int(i) for t, i in enumerate(lut) if i >= 0}, len(kept))
+    bi, bj = (got_ext & np.uint64(0x7fffffff)).astype(np.int64), ((got_ext >> np.uint64(32)) & np.uint64(0x7fffffff)).astype(np.int64)
+    dok, c_ext = oracle.bin_pairs_loop(bi, bj, ok, {b: b for b in range(g.total_bins)}, g.total_bins)
+    assert c_ext == c_seq and sum(dok.values()) == c_seq['accepted']
+    # pair_records_from_bam carries both
+    pr, _ = bam_io.pair_records_from_bam(path, min_mapq=30, min_len=1000, bin_size=bin_size)
+    assert np.array_equal(pr.records, want) and np.array_equal(pr.extent_records, want_ext)
+
+
+def test_bam_extent_argument_errors(tmp_path):
+    from bin3c_b200.contact_map import ExtentGrouping
+    refs, lengths = ['a', 'b', 'c'], [1000, 5000, 400]
+    alns = [dict(name='q', flag=0x41, tid=0, pos=1, mapq=60, cigar=[(0, 50)]),
+            dict(name='q', flag=0x91, tid=1, pos=4000, mapq=60, cigar=[(0, 50), (2, 10), (0, 40)])]
+    path = str(tmp_path / 'e.bam')
+    bam_writer.write_bam(path, refs, lengths, alns)
+    g = ExtentGrouping.from_lengths([1000, 5000], 1000)
+    with bam_io.BamPairReader(path) as bam:
+        with pytest.raises(AssertionError):
+            bam.read_pairs_extent(10)                          # set_extent first
+        with pytest.raises(AssertionError):
+            bam.set_extent(np.array([0, 1], dtype=np.int32), g)            # table must cover all references
+        with pytest.raises(AssertionError):
+            bam.set_extent(np.array([0, 5, -1], dtype=np.int32), g)        # index outside the sequences
+        bam.set_extent(np.array([0, 1, -1], dtype=np.int32), g)
+        r, e = bam.read_pairs_extent(10)
+        # mate 1 forward at 1 -> bin 0 of contig a; mate 2 reverse: 4000 + 100 reference bases = 4100 -> 5th bin of b
+        assert len(r) == 1 and int(e[0]) == 0 | (1 << 31) | ((1 + 4) << 32)
+    with pytest.raises(Exception):
+        ExtentGrouping.from_lengths([1000, 0], 1000)
