@@ -100,3 +100,46 @@ def kr_with_iterations(fns, m, **kw):
     finally:
         fns['logger'].removeHandler(cap)
     return bal, x, cap.n_iter, cap.warnings
+
+
+# ---- the extent map's bins (contact_map.py:116-156) and find_nearest_jit (:49-62) -----------------------------
+class Py2Int(int):
+    """An int whose `/` is Python 2's: integer division when the other operand is an int (contact_map.py:132), true
+    division when it is a float (:137).  Lets ExtentGrouping run verbatim under Python 3."""
+
+    def __truediv__(self, other):
+        if isinstance(other, int):
+            return Py2Int(int(self) // int(other))
+        return int(self) / other
+
+    def __mod__(self, other):
+        return int(self) % other
+
+
+def load_extent():
+    """
+    Exec the reference's ExtentGrouping class and find_nearest_jit body.  Shims: np.int, tqdm.tqdm = identity,
+    the numba decorator dropped (the @jit line is not part of the slice), and sequence lengths wrapped in Py2Int.
+    Returns (make_grouping(lengths, bin_size) -> reference ExtentGrouping instance, find_nearest(group_sites, x)).
+    """
+    if not available():
+        raise RuntimeError('reference tree not found at {}'.format(REFERENCE_ROOT))
+    import collections
+
+    class _Tqdm(object):
+        @staticmethod
+        def tqdm(it, **kw):
+            return it
+
+    ns = {'np': _NpShim(), 'tqdm': _Tqdm, 'ZeroLengthException': ValueError}
+    path = os.path.join(REFERENCE_ROOT, 'mzd', 'contact_map.py')
+    with open(path, 'r') as fh:
+        lines = fh.readlines()
+    for lo, hi in ((50, 62), (116, 156)):              # def find_nearest_jit (without @jit at :49), class ExtentGrouping
+        exec(compile(textwrap.dedent(''.join(lines[lo - 1:hi])), 'mzd/contact_map.py:{}-{}'.format(lo, hi), 'exec'), ns)
+    Seq = collections.namedtuple('Seq', ['length', 'id'])
+
+    def make_grouping(lengths, bin_size):
+        return ns['ExtentGrouping']([Seq(Py2Int(int(l)), n) for n, l in enumerate(lengths)], bin_size)
+
+    return make_grouping, ns['find_nearest_jit']

@@ -136,3 +136,27 @@ def test_compress_edge_cases():
     assert none.shape == (0, 0) and none.nnz == 0
     some = oracle.compress(m, np.array([True, False, True, False]))
     assert np.array_equal(some.toarray(), np.array([[0., 2.], [8., 10.]]))
+
+
+def test_extent_grouping_golden():
+    """ExtentGrouping / find_nearest restatements (oracle and the product's host class) against the vectors the
+    reference's own class produced (tests/golden/make_golden_extent.py)."""
+    import os
+    from bin3c_b200.contact_map import ExtentGrouping
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'extent.npz'))
+    lengths = g['lengths']
+    for bs in g['bin_sizes'].tolist():
+        o = oracle.extent_grouping(lengths, bs)
+        p = ExtentGrouping.from_lengths(lengths, bs)
+        assert np.array_equal(o['bins'], g['bins_%d' % bs]) and np.array_equal(p.bins, g['bins_%d' % bs])
+        assert np.array_equal(np.concatenate([m[:, 0] for m in o['map']]), g['upper_%d' % bs])
+        assert np.array_equal(np.concatenate([m[:, 1] for m in o['map']]), g['binid_%d' % bs])
+        assert np.array_equal(p.upper_edges, g['upper_%d' % bs])
+        assert np.array_equal(np.concatenate([m[:, 1] for m in p.map]), g['binid_%d' % bs])
+        assert p.total_bins == o['total_bins'] == int(g['bins_%d' % bs].sum())
+        for k, x, b in zip(g['q_seq_%d' % bs].tolist(), g['q_pos_%d' % bs].tolist(), g['q_bin_%d' % bs].tolist()):
+            assert oracle.find_nearest(o['map'][k], x) == b
+            # the flat arrays the BAM reader bisects (b3c_bam_set_extent)
+            lo, hi = p.edge_ptr[k], p.edge_ptr[k + 1]
+            j = min(int(np.searchsorted(p.upper_edges[lo:hi], x)), hi - lo - 1)
+            assert p.first_bin[k] + j == b

@@ -51,3 +51,20 @@ def test_reference_functions_vs_oracle(fns, seed, n, p):
         rc = fns['compress'](rb.tocoo(), mask).tocsr()
         oc = oracle.compress(rb.tocoo(), mask).tocsr()
         assert rc.shape == oc.shape and abs(rc - oc).max() == 0
+
+
+def test_reference_extent_grouping_vs_oracle():
+    """The reference's ExtentGrouping class and find_nearest_jit, exec'd live (Python 2 division shimmed)."""
+    import random
+    make_grouping, find_nearest = ref_exec.load_extent()
+    rng = random.Random(77)
+    lengths = [rng.randrange(1, 30000) for _ in range(300)]
+    for bs in (13, 1000, 4096):
+        r = make_grouping(lengths, bs)
+        o = oracle.extent_grouping(lengths, bs)
+        assert r.total_bins == o['total_bins'] and np.array_equal(np.asarray(r.bins), o['bins'])
+        for a, b in zip(r.map, o['map']):
+            assert np.array_equal(np.asarray(a), b)
+        for k in range(0, 300, 11):
+            for x in (0, lengths[k] // 2, lengths[k], lengths[k] + 5):
+                assert int(find_nearest(np.asarray(r.map[k]), x)) == oracle.find_nearest(o['map'][k], x)
