@@ -143,3 +143,98 @@ def load_extent():
         return ns['ExtentGrouping']([Seq(Py2Int(int(l)), n) for n, l in enumerate(lengths)], bin_size)
 
     return make_grouping, ns['find_nearest_jit']
+
+
+# ---- the reference's own _bin_map (contact_map.py:602-809) over duck-typed alignment records ----------------
+class FakeAlignment(object):
+    """The pysam.AlignedSegment attributes _bin_map touches, from an alignment dict (name, flag, tid, pos, mapq, cigar)."""
+    _OPS = 'MIDNSHP=X'
+
+    def __init__(self, a):
+        f = a['flag']
+        self.query_name = a['name']
+        self.reference_id = a['tid']
+        self.mapping_quality = a['mapq']
+        self.pos = self.reference_start = a['pos']
+        cig = a.get('cigar') or None
+        self.cigartuples = list(cig) if cig else None
+        self.cigarstring = ''.join('{}{}'.format(n, self._OPS[op]) for op, n in cig) if cig else None
+        self.alen = sum(n for op, n in cig if op in (0, 2, 3, 7, 8)) if cig else None      # pysam reference_length
+        self.reference_end = self.pos + self.alen if cig else None
+        self.is_unmapped = bool(f & 0x4)
+        self.is_secondary = bool(f & 0x100)
+        self.is_supplementary = bool(f & 0x800)
+        self.is_reverse = bool(f & 0x10)
+        self.is_read2 = bool(f & 0x80)
+        self.is_proper_pair = bool(f & 0x2)
+
+
+class _FakeBam(object):
+    def __init__(self, alignments, lengths):
+        self._alns = alignments
+        self.lengths = list(lengths)
+
+    def reset(self):
+        pass
+
+    def fetch(self, until_eof=True):
+        bam = self
+
+        class It(object):                      # the reference calls _bam_iter.next() (Python 2 protocol)
+            def __init__(self):
+                self._it = iter(bam._alns)
+
+            def next(self):
+                return FakeAlignment(next(self._it))
+        return It()
+
+
+def run_bin_map(alignments, ref_lengths, idx_of, n_seq, min_mapq=0, strong=None, min_insert=None, grouping=None):
+    """
+    Exec the reference's ContactMap._bin_map verbatim (contact_map.py:602-809) on a stub instance and a fake BAM of
+    duck-typed records; Sparse2DAccumulator and find_nearest_jit are the reference's own too.  `grouping` is an
+    exec'd reference ExtentGrouping (load_extent) or None.  A mapped record without CIGAR has alen None, which the
+    reference cannot add to a position: feed such records only as forward reads.
+    Returns dict(seq_map coo, extent_map coo or None, counts dict).
+    """
+    import collections
+    fns = load()
+    _, find_nearest = load_extent()
+    logger = logging.getLogger('mzd.contact_map.exec')
+    captured = {}
+
+    class Cap(logging.Handler):
+        def emit(self, record):
+            msg = record.getMessage()
+            if msg.startswith('Pair accounting: '):
+                captured['counts'] = msg[len('Pair accounting: '):]
+    cap = Cap(level=logging.INFO)
+    logger.addHandler(cap)
+    logger.setLevel(logging.INFO)
+
+    class SU(object):
+        Sparse2DAccumulator = fns['Sparse2DAccumulator']
+
+    ns = {'np': _NpShim(), 'sparse_utils': SU, 'logger': logger, 'OrderedDict': collections.OrderedDict,
+          'find_nearest_jit': find_nearest, 'xrange': range}
+    with open(os.path.join(REFERENCE_ROOT, 'mzd', 'contact_map.py'), 'r') as fh:
+        lines = fh.readlines()[602 - 1:809]
+    exec(compile(textwrap.dedent(''.join(lines)), 'mzd/contact_map.py:602-809', 'exec'), ns)
+
+    class Stub(object):
+        pass
+    me = Stub()
+    me.strong, me.min_insert, me.min_mapq = strong, min_insert, min_mapq
+    me.total_seq, me.total_len, me.total_reads = n_seq, 0, None
+    me.bin_size = grouping.bin_size if grouping is not None else None
+    me.grouping, me.tip_size = grouping, None
+    me.extent_map = me.seq_map = None
+    me.is_tipbased = lambda: False
+    me.make_reverse_index = lambda field: dict(idx_of)
+    me.map_weight = lambda: int(me.seq_map.sum())
+    try:
+        ns['_bin_map'](me, _FakeBam(alignments, ref_lengths))
+    finally:
+        logger.removeHandler(cap)
+    counts = eval(captured['counts'], {'OrderedDict': collections.OrderedDict})
+    return dict(seq_map=me.seq_map, extent_map=me.extent_map, counts=dict(counts))

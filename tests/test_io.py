@@ -443,3 +443,73 @@ def test_bam_extent_argument_errors(tmp_path):
         assert len(r) == 1 and int(e[0]) == 0 | (1 << 31) | ((1 + 4) << 32)
     with pytest.raises(Exception):
         ExtentGrouping.from_lengths([1000, 0], 1000)
+
+
+def _golden_binmap():
+    with np.load(os.path.join(ROOT, 'tests', 'golden', 'binmap.npz')) as z:
+        g = {k: z[k] for k in z.files}            # an NpzFile re-reads an array on every access
+    ptr = g['cig_ptr']
+    alns = []
+    for k in range(len(g['name'])):
+        cig = [(int(o), int(n)) for o, n in zip(g['cig_op'][ptr[k]:ptr[k + 1]], g['cig_len'][ptr[k]:ptr[k + 1]])]
+        alns.append(dict(name='t%d' % g['name'][k], flag=int(g['flag'][k]), tid=int(g['tid'][k]), pos=int(g['pos'][k]),
+                         mapq=int(g['mapq'][k]), cigar=cig))
+    return g, alns
+
+
+def _maps_from_records(rec, ext, lut, n_seq, n_bins):
+    ok = ((rec >> np.uint64(31)) & np.uint64(1)).astype(bool)
+    m31 = np.uint64(0x7fffffff)
+    dok, counts = oracle.bin_pairs_loop((rec & m31).astype(np.int64), ((rec >> np.uint64(32)) & m31).astype(np.int64), ok,
+                                        {t: int(i) for t, i in enumerate(lut) if i >= 0}, n_seq)
+    dx, cx = oracle.bin_pairs_loop((ext & m31).astype(np.int64), ((ext >> np.uint64(32)) & m31).astype(np.int64), ok,
+                                   {b: b for b in range(n_bins)}, n_bins)
+    assert cx == counts
+    return oracle.dok_to_coo(dok, n_seq), oracle.dok_to_coo(dx, n_bins), counts
+
+
+@pytest.mark.parametrize('via', ['oracle', 'native'])
+def test_pair_loop_against_the_reference_bin_map(tmp_path, via):
+    """
+    tests/golden/binmap.npz holds what the REFERENCE'S OWN ContactMap._bin_map (exec'd verbatim on duck-typed records,
+    tests/golden/make_golden_binmap.py) produced: contig map, extent map and counters for three filter settings.
+    'oracle': the oracle's restatement of the loop reproduces them; 'native': so do the records the C++ BAM reader
+    extracts from a real BAM file of the same alignments, accumulated by the oracle.
+    """
+    from bin3c_b200.contact_map import ExtentGrouping
+    g, alns = _golden_binmap()
+    lengths = g['lengths']
+    n_refs = len(lengths)
+    keep = lengths >= int(g['min_len'])
+    lut = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+    n_seq = int(keep.sum())
+    grouping = ExtentGrouping.from_lengths(lengths[keep], int(g['bin_size']))
+    og = oracle.extent_grouping(lengths[keep], int(g['bin_size']))
+    if via == 'native':
+        path = str(tmp_path / 'g.bam')
+        bam_writer.write_bam(path, ['r%d' % i for i in range(n_refs)], lengths.tolist(), alns, block_bytes=20000, level=1)
+    for k in range(int(g['n_params'])):
+        kw = dict(min_mapq=int(g['p%d_min_mapq' % k]), strong=int(g['p%d_strong' % k]) or None,
+                  min_insert=int(g['p%d_min_insert' % k]) or None)
+        if via == 'oracle':
+            rec, ext, st = oracle.pair_alignments(alns, n_refs, idx_of=lut, grouping=og, **kw)
+            short = st['short_insert']
+        else:
+            with bam_io.BamPairReader(path, threads=4) as bam:
+                bam.set_extent(lut, grouping)
+                bam.set_filter(tid2idx=lut, **kw)
+                parts = []
+                while True:
+                    r, e = bam.read_pairs_extent(4099)
+                    if len(r) == 0:
+                        break
+                    parts.append((r.copy(), e.copy()))
+                short = bam.stats()['short_insert']
+            rec, ext = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+        seq_map, ext_map, counts = _maps_from_records(rec, ext, lut, n_seq, grouping.total_bins)
+        want = g['p%d_counts' % k].tolist()
+        assert [counts['accepted'], counts['ref_excluded'], counts['poor_match'], short] == want
+        for nm, m in (('seq_map', seq_map), ('extent_map', ext_map)):
+            assert m.shape[0] == int(g['p%d_%s_n' % (k, nm)])
+            assert np.array_equal(m.row, g['p%d_%s_row' % (k, nm)]) and np.array_equal(m.col, g['p%d_%s_col' % (k, nm)])
+            assert np.array_equal(m.data, g['p%d_%s_data' % (k, nm)])

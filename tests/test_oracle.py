@@ -143,7 +143,8 @@ def test_extent_grouping_golden():
     reference's own class produced (tests/golden/make_golden_extent.py)."""
     import os
     from bin3c_b200.contact_map import ExtentGrouping
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'extent.npz'))
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'extent.npz')) as z:
+        g = {k: z[k] for k in z.files}
     lengths = g['lengths']
     for bs in g['bin_sizes'].tolist():
         o = oracle.extent_grouping(lengths, bs)

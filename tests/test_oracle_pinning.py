@@ -68,3 +68,38 @@ def test_reference_extent_grouping_vs_oracle():
         for k in range(0, 300, 11):
             for x in (0, lengths[k] // 2, lengths[k], lengths[k] + 5):
                 assert int(find_nearest(np.asarray(r.map[k]), x)) == oracle.find_nearest(o['map'][k], x)
+
+
+def test_reference_bin_map_loop_vs_oracle():
+    """The reference's _bin_map, exec'd live on a fresh random alignment stream, against the oracle's loop."""
+    import os
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden_binmap as mg
+    rng = random.Random(5)
+    n_refs = 50
+    lengths = [rng.choice([500, 1000, 2100, 12000]) for _ in range(n_refs)]
+    alns = [dict(a, name='q%d' % a['name']) for a in mg.make_alignments(rng, n_refs, lengths, 3000)]
+    keep = np.array(lengths) >= 1000
+    lut = np.where(keep, np.cumsum(keep) - 1, -1)
+    idx = {t: int(i) for t, i in enumerate(lut) if i >= 0}
+    kept = [l for l in lengths if l >= 1000]
+    make_grouping, _ = ref_exec.load_extent()
+    for kw in (dict(min_mapq=25), dict(min_mapq=25, strong=30), dict(min_mapq=10, min_insert=900)):
+        ref = ref_exec.run_bin_map(alns, lengths, idx, len(kept), grouping=make_grouping(kept, 700), **kw)
+        og = oracle.extent_grouping(kept, 700)
+        rec, ext, st = oracle.pair_alignments(alns, n_refs, idx_of=lut, grouping=og, **kw)
+        m31 = np.uint64(0x7fffffff)
+        ok = ((rec >> np.uint64(31)) & np.uint64(1)).astype(bool)
+        dok, c = oracle.bin_pairs_loop((rec & m31).astype(np.int64), ((rec >> np.uint64(32)) & m31).astype(np.int64), ok,
+                                       idx, len(kept))
+        dx, _ = oracle.bin_pairs_loop((ext & m31).astype(np.int64), ((ext >> np.uint64(32)) & m31).astype(np.int64), ok,
+                                      {b: b for b in range(og['total_bins'])}, og['total_bins'])
+        rc = ref['counts']
+        assert [rc[k] for k in ('accepted', 'ref_excluded', 'poor_match')] == [c[k] for k in ('accepted', 'ref_excluded', 'poor_match')]
+        assert rc['short_insert'] == st['short_insert']
+        for got, want in ((oracle.dok_to_coo(dok, len(kept)), ref['seq_map']),
+                          (oracle.dok_to_coo(dx, og['total_bins']), ref['extent_map'])):
+            assert np.array_equal(got.row, want.row) and np.array_equal(got.col, want.col)
+            assert np.array_equal(got.data, want.data)
