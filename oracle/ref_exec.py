@@ -238,3 +238,53 @@ def run_bin_map(alignments, ref_lengths, idx_of, n_seq, min_mapq=0, strong=None,
         logger.removeHandler(cap)
     counts = eval(captured['counts'], {'OrderedDict': collections.OrderedDict})
     return dict(seq_map=me.seq_map, extent_map=me.extent_map, counts=dict(counts))
+
+
+# ---- the reference's own to_graph (cluster.py:278-325) on a stub contact map -------------------------------------
+def run_to_graph(sub_map, n_accepted, scale=True):
+    """
+    Exec cluster.to_graph verbatim; `sub_map` is what contact_map.get_subspace(marginalise=True, flatten=False) returns
+    (the compressed, balanced map).  Shims: itertools.izip = zip, nx.info (removed in networkx 3) = '', tqdm = identity.
+    Returns the nx.Graph the reference builds.
+    """
+    import networkx
+    import scipy.sparse as sp
+
+    class NX(object):
+        Graph = networkx.Graph
+
+        @staticmethod
+        def info(g):
+            return ''
+
+    class IT(object):
+        izip = zip
+
+    class TQ(object):
+        @staticmethod
+        def tqdm(it, **kw):
+            return it
+
+    class Order(object):
+        @staticmethod
+        def count_accepted():
+            return n_accepted
+
+    class CM(object):
+        processed_map = object()
+        order = Order()
+        seq_info = None
+
+        @staticmethod
+        def set_primary_acceptance_mask(*a, **kw):
+            pass
+
+        @staticmethod
+        def get_subspace(marginalise=False, flatten=True):
+            return sub_map
+
+    ns = {'nx': NX, 'itertools': IT, 'tqdm': TQ, 'sp': sp, 'logger': logging.getLogger('mzd.cluster.exec')}
+    with open(os.path.join(REFERENCE_ROOT, 'mzd', 'cluster.py'), 'r') as fh:
+        lines = fh.readlines()[278 - 1:325]
+    exec(compile(textwrap.dedent(''.join(lines)), 'mzd/cluster.py:278-325', 'exec'), ns)
+    return ns['to_graph'](CM, norm=True, bisto=True, scale=scale)

@@ -103,3 +103,39 @@ def test_reference_bin_map_loop_vs_oracle():
                           (oracle.dok_to_coo(dx, og['total_bins']), ref['extent_map'])):
             assert np.array_equal(got.row, want.row) and np.array_equal(got.col, want.col)
             assert np.array_equal(got.data, want.data)
+
+
+def test_reference_to_graph_vs_oracle_edges(tmp_path):
+    """
+    The reference's to_graph (cluster.py:278-325), exec'd on the compressed balanced map of a synthetic community:
+    same edge set and the same scale 1/max (Q8) as the oracle's edge list; every weight within 2 ulp (the
+    reference keeps the LAST of the two mirrored entries it adds, the oracle and the product the upper one, Q9).
+    The edge file networkx writes from that graph equals the native writer's on the graph's own weights.
+    """
+    pytest.importorskip('networkx')
+    import networkx as nx
+    from bin3c_b200 import bam_io
+    com = synth.make_community(n_genomes=4, n_contigs=300, n_pairs=60000, seed=55)
+    ti, tj, ok = synth.unpack_pairs(com.records)
+    ref = oracle.run_path(ti, tj, ok, com.tid2idx(), com.lengths, com.sites, min_len=1000, min_sig=2)
+    sub = ref['sub_map'] if 'sub_map' in ref else None
+    if sub is None:
+        bal, _x, _n = oracle.kr_biostochastic(sp.coo_matrix(
+            (oracle.norm_by_sites(ref['seq_map'].row, ref['seq_map'].col, ref['seq_map'].data.astype(float),
+                                  oracle.get_sites(com.sites)), (ref['seq_map'].row, ref['seq_map'].col)),
+            shape=ref['seq_map'].shape))
+        sub = oracle.compress(bal.tocoo(), ref['mask'])
+    g = ref_exec.run_to_graph(sub.tocoo(), int(ref['mask'].sum()), scale=True)
+    u, v, w, scl = oracle.graph_edges(sub, scale=True)
+    assert g.number_of_edges() == len(u)
+    gw = np.array([g[int(a)][int(b)]['weight'] for a, b in zip(u, v)])
+    assert np.max(np.abs(gw - w) / w) <= 4.5e-16                       # <= 2 ulp
+    assert gw.max() == w.max()                                           # the scale and the largest entry agree exactly
+    lower = sub.tocsr()
+    k = len(u) // 2
+    assert gw[k] == lower[int(v[k]), int(u[k])] * scl                    # last writer = the mirrored (lower) entry
+    f_nx, f_b3 = str(tmp_path / 'nx.edges'), str(tmp_path / 'b3.edges')
+    nx.write_edgelist(g, f_nx, data=['weight'], delimiter=' ')
+    e = list(g.edges(data='weight'))
+    bam_io.write_edges([a for a, _, _ in e], [b for _, b, _ in e], [c for _, _, c in e], f_b3)
+    assert open(f_nx).read() == open(f_b3).read()
