@@ -241,7 +241,7 @@ def run_bin_map(alignments, ref_lengths, idx_of, n_seq, min_mapq=0, strong=None,
 
 
 # ---- the reference's own to_graph (cluster.py:278-325) on a stub contact map -------------------------------------
-def run_to_graph(sub_map, n_accepted, scale=True):
+def run_to_graph(sub_map, n_accepted, scale=True, contact_map=None):
     """
     Exec cluster.to_graph verbatim; `sub_map` is what contact_map.get_subspace(marginalise=True, flatten=False) returns
     (the compressed, balanced map).  Shims: itertools.izip = zip, nx.info (removed in networkx 3) = '', tqdm = identity.
@@ -287,4 +287,104 @@ def run_to_graph(sub_map, n_accepted, scale=True):
     with open(os.path.join(REFERENCE_ROOT, 'mzd', 'cluster.py'), 'r') as fh:
         lines = fh.readlines()[278 - 1:325]
     exec(compile(textwrap.dedent(''.join(lines)), 'mzd/cluster.py:278-325', 'exec'), ns)
-    return ns['to_graph'](CM, norm=True, bisto=True, scale=scale)
+    return ns['to_graph'](contact_map if contact_map is not None else CM, norm=True, bisto=True, scale=scale)
+
+
+# ---- the whole reference path: SeqOrder + ContactMap classes exec'd, driven as bin3C.py mkmap / cluster do ------------
+def run_reference_path(alignments, ref_lengths, ref_sites, min_len, min_sig, min_mapq=60, strong=None, min_insert=None,
+                       bin_size=None, seed=1):
+    """
+    Exec the reference's SeqOrder and ContactMap classes (contact_map.py:159-485, 486-end), find_nearest_jit,
+    fast_norm_fullseq_bysite (without their numba decorators) and ExtentGrouping, build a ContactMap without its
+    __init__ (which needs pysam and Biopython: the attribute set-up of :492-600 is replayed here from the reference
+    table), then call the reference's own methods in the order bin3C.py mkmap / cluster call them:
+        _bin_map(fake bam) -> set_primary_acceptance_mask() -> to_graph(...) [prepare_seq_map(norm, bisto),
+        get_subspace(marginalise=True, flatten=False)]
+    Returns dict(cm, seq_map, mask, bisto_scale, processed_map, sub_map, graph, counts).
+    """
+    import collections
+    fns = load(skip_hermitian_check=False)
+    _, find_nearest = load_extent()
+    logger = logging.getLogger('mzd.contact_map.exec')
+    captured = {}
+
+    class Cap(logging.Handler):
+        def emit(self, record):
+            msg = record.getMessage()
+            if msg.startswith('Pair accounting: '):
+                captured['counts'] = msg[len('Pair accounting: '):]
+    cap = Cap(level=logging.INFO)
+    logger.addHandler(cap)
+    logger.setLevel(logging.INFO)
+
+    class SU(object):
+        Sparse2DAccumulator = fns['Sparse2DAccumulator']
+        max_offdiag = staticmethod(fns['max_offdiag'])
+        compress = staticmethod(fns['compress'])
+        kr_biostochastic = staticmethod(fns['kr_biostochastic'])
+
+    class NoneAcceptedException(Exception):
+        pass
+
+    class TQ(object):
+        @staticmethod
+        def tqdm(it=None, **kw):
+            class Bar(object):
+                def __enter__(self_):
+                    return self_
+
+                def __exit__(self_, *a):
+                    return False
+
+                def update(self_, n=1):
+                    pass
+            return it if it is not None else Bar()
+
+    SeqInfo = collections.namedtuple('SeqInfo', ['offset', 'refid', 'name', 'length', 'sites'])
+    ns = {'np': _NpShim(), 'sp': scisp, 'sparse_utils': SU, 'logger': logger, 'OrderedDict': collections.OrderedDict,
+          'namedtuple': collections.namedtuple, 'xrange': range, 'tqdm': TQ, 'SeqInfo': SeqInfo,
+          'NoneAcceptedException': NoneAcceptedException, 'find_nearest_jit': find_nearest}
+    with open(os.path.join(REFERENCE_ROOT, 'mzd', 'contact_map.py'), 'r') as fh:
+        lines = fh.readlines()
+    for lo, hi in ((101, 113), (116, 156), (159, 485), (486, len(lines))):
+        exec(compile(textwrap.dedent(''.join(lines[lo - 1:hi])), 'mzd/contact_map.py:{}-{}'.format(lo, hi), 'exec'), ns)
+    # tqdm is imported inside _bin_map ("import tqdm"): give it the stub through sys.modules for the call
+    import sys
+    import types
+    stub = types.ModuleType('tqdm')
+    stub.tqdm = TQ.tqdm
+    saved = sys.modules.get('tqdm')
+    sys.modules['tqdm'] = stub
+
+    CM = ns['ContactMap']
+    cm = CM.__new__(CM)
+    cm.strong, cm.bam_file, cm.bin_size, cm.min_mapq, cm.min_insert = strong, None, bin_size, min_mapq, min_insert
+    cm.min_len, cm.min_sig, cm.min_extent, cm.min_size, cm.max_fold = min_len, min_sig, 0, 0, None
+    cm.random_state = np.random.RandomState(seed)
+    cm.seq_info, cm.seq_map, cm.seq_file, cm.grouping, cm.extent_map, cm.order = [], None, None, None, None, None
+    cm.tip_size, cm.precount, cm.total_reads, cm.cov_info, cm.processed_map = None, False, None, None, None
+    cm.primary_acceptance_mask, cm.bisto_scale, cm.seq_analyzer, cm.enzymes = None, None, None, ['synthetic']
+    offset = 0
+    for n, (rlen, sites) in enumerate(zip(ref_lengths, ref_sites)):                 # contact_map.py:545-564
+        if rlen < min_len or sites < 0:
+            continue
+        cm.seq_info.append(SeqInfo(offset, n, 'ref{:07d}'.format(n), Py2Int(int(rlen)), int(sites)))
+        offset += int(rlen)
+    cm.total_len, cm.total_seq = offset, len(cm.seq_info)
+    cm.current_mask = np.ones(cm.total_seq, dtype=bool)
+    if bin_size:
+        cm.grouping = ns['ExtentGrouping'](cm.seq_info, bin_size)
+    cm.order = ns['SeqOrder'](cm.seq_info)
+    try:
+        cm._bin_map(_FakeBam(alignments, ref_lengths))
+        cm.set_primary_acceptance_mask()
+        graph = run_to_graph(None, None, scale=True, contact_map=cm)
+    finally:
+        logger.removeHandler(cap)
+        if saved is not None:
+            sys.modules['tqdm'] = saved
+        else:
+            del sys.modules['tqdm']
+    counts = dict(eval(captured['counts'], {'OrderedDict': collections.OrderedDict}))
+    return dict(cm=cm, seq_map=cm.seq_map, extent_map=cm.extent_map, mask=cm.get_primary_acceptance_mask(),
+                bisto_scale=cm.bisto_scale, processed_map=cm.processed_map, graph=graph, counts=counts)

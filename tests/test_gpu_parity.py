@@ -785,3 +785,33 @@ def test_extent_map_from_bam(dev, tmp_path):
     with pytest.raises(AssertionError):
         ContactMap(PairRecords(pr.lengths, pr.sites, pr.records), ['synthetic'], None, None, min_mapq=30,
                    min_len=min_len, min_sig=1, bin_size=bin_size)
+
+
+def test_cuda_path_vs_whole_reference_path(dev):
+    """
+    The CUDA path against outputs of the REFERENCE ITSELF: tests/golden/refpath.npz comes from the reference's own
+    ContactMap / SeqOrder / sparse_utils / to_graph code run end to end (tests/golden/make_golden_refpath.py), not
+    from the oracle.  Counts, contact matrix and mask bit-exact; identical KR iteration count; x, the balanced map and
+    the edge weights within 1e-9 (north-star tolerance; zero site counts included, Q6).
+    """
+    import os
+    from bin3c_b200 import cluster
+    from bin3c_b200.contact_map import ContactMap, PairRecords
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'refpath.npz')) as z:
+        g = {k: z[k] for k in z.files}
+    cm = ContactMap(PairRecords(g['lengths'], g['sites'], g['records']), ['synthetic'], None, None, min_mapq=60,
+                    min_len=int(g['min_len']), min_sig=int(g['min_sig']), random_seed=1)
+    assert [cm.pair_counts[k] for k in ('accepted', 'ref_excluded', 'poor_match')] == g['counts'].tolist()
+    sm = cm.seq_map
+    assert np.array_equal(sm.row, g['map_row']) and np.array_equal(sm.col, g['map_col'])
+    assert np.array_equal(sm.data, g['map_data'])
+    assert np.array_equal(cm.get_primary_acceptance_mask(), g['mask'].astype(bool))
+    u, v, w, scl = cluster.to_edges(cm, norm=True, bisto=True, scale=True)
+    assert cm.kr_info['n_iter'] == int(g['kr_n_iter'])
+    assert _relerr(cm.bisto_scale, g['kr_x']) <= REL_TOL
+    assert np.array_equal(u, g['edge_u']) and np.array_equal(v, g['edge_v'])
+    assert _relerr(w, g['edge_w']) <= REL_TOL
+    pm = cm.processed_map.tocoo()
+    o1, o2 = np.lexsort((pm.col, pm.row)), np.lexsort((g['bal_col'], g['bal_row']))
+    assert np.array_equal(pm.row[o1], g['bal_row'][o2]) and np.array_equal(pm.col[o1], g['bal_col'][o2])
+    assert _relerr(pm.data[o1], g['bal_data'][o2]) <= REL_TOL

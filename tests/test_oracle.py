@@ -161,3 +161,31 @@ def test_extent_grouping_golden():
             lo, hi = p.edge_ptr[k], p.edge_ptr[k + 1]
             j = min(int(np.searchsorted(p.upper_edges[lo:hi], x)), hi - lo - 1)
             assert p.first_bin[k] + j == b
+
+
+def _refpath():
+    import os
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'refpath.npz')) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_oracle_vs_whole_reference_path():
+    """tests/golden/refpath.npz was produced by the reference's own ContactMap / SeqOrder / sparse_utils / to_graph code
+    (tests/golden/make_golden_refpath.py); the oracle's run_path must reproduce it: counts, contact matrix and mask
+    bit-exact, identical KR iteration count, x and the balanced map <= 1e-12, edge set identical, weights <= 2 ulp."""
+    from bin3c_b200 import synth
+    g = _refpath()
+    keep = (g['lengths'] >= int(g['min_len'])) & (g['sites'] >= 0)
+    lut = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+    ti, tj, ok = synth.unpack_pairs(g['records'])
+    ref = oracle.run_path(ti, tj, ok, lut, g['lengths'][keep], g['sites'][keep], min_len=int(g['min_len']),
+                          min_sig=int(g['min_sig']))
+    assert [ref['counts'][k] for k in ('accepted', 'ref_excluded', 'poor_match')] == g['counts'].tolist()
+    sm = ref['seq_map']
+    assert np.array_equal(sm.row, g['map_row']) and np.array_equal(sm.col, g['map_col'])
+    assert np.array_equal(sm.data, g['map_data'])
+    assert np.array_equal(ref['mask'], g['mask'].astype(bool))
+    assert ref['n_iter'] == int(g['kr_n_iter'])
+    assert np.max(np.abs(ref['x'] - g['kr_x']) / np.abs(g['kr_x'])) <= 1e-12
+    assert np.array_equal(ref['u'], g['edge_u']) and np.array_equal(ref['v'], g['edge_v'])
+    assert np.max(np.abs(ref['w'] - g['edge_w']) / g['edge_w']) <= 4.5e-16

@@ -139,3 +139,30 @@ def test_reference_to_graph_vs_oracle_edges(tmp_path):
     e = list(g.edges(data='weight'))
     bam_io.write_edges([a for a, _, _ in e], [b for _, b, _ in e], [c for _, _, c in e], f_b3)
     assert open(f_nx).read() == open(f_b3).read()
+
+
+def test_whole_reference_path_vs_oracle():
+    """The reference's ContactMap and SeqOrder classes exec'd live and driven end to end (oracle/ref_exec.py:
+    run_reference_path), against oracle.run_path on a fresh community, with an extent map on the side."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden_refpath as mg
+    com = synth.make_community(n_genomes=3, n_contigs=150, n_pairs=20000, seed=909)
+    lengths = np.full(com.n_refs, 500, dtype=np.int64)
+    sites = np.ones(com.n_refs, dtype=np.int64)
+    lengths[com.ref_index] = com.lengths
+    sites[com.ref_index] = com.sites
+    res = ref_exec.run_reference_path(mg.alignments_of(com.records), lengths, sites, 1000, 2, min_mapq=60, bin_size=3000)
+    ti, tj, ok = synth.unpack_pairs(com.records)
+    ref = oracle.run_path(ti, tj, ok, com.tid2idx(), com.lengths, com.sites, min_len=1000, min_sig=2)
+    assert {k: res['counts'][k] for k in ('accepted', 'ref_excluded', 'poor_match')} == ref['counts']
+    a, b = res['seq_map'], ref['seq_map']
+    assert np.array_equal(a.row, b.row) and np.array_equal(a.col, b.col) and np.array_equal(a.data, b.data)
+    assert np.array_equal(np.asarray(res['mask']), ref['mask'])
+    assert np.max(np.abs(res['bisto_scale'] - ref['x']) / np.abs(ref['x'])) <= 1e-12
+    g = res['graph']
+    assert g.number_of_edges() == len(ref['u'])
+    gw = np.array([g[int(x)][int(y)]['weight'] for x, y in zip(ref['u'], ref['v'])])
+    assert np.max(np.abs(gw - ref['w']) / ref['w']) <= 4.5e-16
+    assert res['extent_map'].shape[0] == res['cm'].grouping.total_bins and res['extent_map'].sum() > 0
