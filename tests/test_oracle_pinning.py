@@ -166,3 +166,51 @@ def test_whole_reference_path_vs_oracle():
     gw = np.array([g[int(x)][int(y)]['weight'] for x, y in zip(ref['u'], ref['v'])])
     assert np.max(np.abs(gw - ref['w']) / ref['w']) <= 4.5e-16
     assert res['extent_map'].shape[0] == res['cm'].grouping.total_bins and res['extent_map'].sum() > 0
+
+
+def test_reference_seqorder_and_mask_rules_vs_product_host_logic():
+    """
+    The product's host-side SeqOrder (pure NumPy, no GPU) beside the reference's SeqOrder class on random masks, and
+    the acceptance-mask rules (contact_map.py:856-909, Q5: falsy thresholds fall back to the instance's, the mask is
+    cached unless `update`) of the reference's ContactMap beside oracle.acceptance_mask.
+    """
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden_refpath as mg
+    from bin3c_b200.contact_map import SeqOrder
+    com = synth.make_community(n_genomes=3, n_contigs=200, n_pairs=30000, seed=4711)
+    lengths = np.full(com.n_refs, 500, dtype=np.int64)
+    sites = np.ones(com.n_refs, dtype=np.int64)
+    lengths[com.ref_index] = com.lengths
+    sites[com.ref_index] = com.sites
+    res = ref_exec.run_reference_path(mg.alignments_of(com.records), lengths, sites, 1000, 3, min_mapq=60)
+    cm = res['cm']
+    mine = SeqOrder(cm.seq_info)
+    mine.set_mask_only(np.asarray(res['mask']))     # positions depend on the history of masks: replay the reference's one
+    assert np.array_equal(np.asarray(cm.order.order['pos']), mine.order['pos'])
+    rng = np.random.default_rng(3)
+    for frac in (1.0, 0.7, 0.2, 0.0):
+        m = rng.random(cm.total_seq) < frac
+        cm.order.set_mask_only(m)
+        mine.set_mask_only(m)
+        assert np.array_equal(np.asarray(cm.order.order['pos']), mine.order['pos'])
+        assert np.array_equal(np.asarray(cm.order.order['mask']), mine.order['mask'])
+        assert np.array_equal(np.asarray(cm.order.mask_vector()), mine.mask_vector())
+        assert cm.order.count_accepted() == mine.count_accepted() == int(m.sum())
+        assert cm.order.count_excluded() == mine.count_excluded()
+        assert np.array_equal(np.asarray(cm.order.accepted()), mine.accepted())
+        assert np.array_equal(np.asarray(cm.order.excluded()), mine.excluded())
+        assert np.array_equal(np.asarray(cm.order.lengths()), mine.lengths())
+        assert np.array_equal(np.asarray(cm.order.lengths(exclude_masked=True)), mine.lengths(exclude_masked=True))
+    sm = res['seq_map']
+    seq_len = np.array([s.length for s in cm.seq_info], dtype=np.int64)
+    first = cm.get_primary_acceptance_mask().copy()
+    assert np.array_equal(first, oracle.acceptance_mask(seq_len, sm, 1000, 3))
+    cm.set_primary_acceptance_mask(min_len=5000, min_sig=20)                 # no update: the cached mask stays
+    assert np.array_equal(cm.get_primary_acceptance_mask(), first)
+    for ml, ms in ((5000, 20), (2000, 1), (1000, 50)):
+        cm.set_primary_acceptance_mask(min_len=ml, min_sig=ms, update=True)
+        assert np.array_equal(cm.get_primary_acceptance_mask(), oracle.acceptance_mask(seq_len, sm, ml, ms))
+    cm.set_primary_acceptance_mask(min_len=0, min_sig=0, update=True)       # falsy -> the instance's 1000 / 3
+    assert np.array_equal(cm.get_primary_acceptance_mask(), first)
