@@ -214,3 +214,53 @@ def test_reference_seqorder_and_mask_rules_vs_product_host_logic():
         assert np.array_equal(cm.get_primary_acceptance_mask(), oracle.acceptance_mask(seq_len, sm, ml, ms))
     cm.set_primary_acceptance_mask(min_len=0, min_sig=0, update=True)       # falsy -> the instance's 1000 / 3
     assert np.array_equal(cm.get_primary_acceptance_mask(), first)
+
+
+def test_infomap_partition_reference_graph_vs_product_edge_list(tmp_path):
+    """
+    North-star: "the resulting Infomap clustering is identical".  The reference's graph (its own to_graph on its own
+    ContactMap) written as its pinned Python 2.7 / networkx 1.11 would write it (12 significant digits), and the
+    oracle's edge list (what the CUDA path is held to within 1e-9) written by the native writer in the same layout:
+    the two files are byte-identical here (1-2 ulp differences vanish in 12 digits), and the reference's Infomap
+    binary returns the same partition for both, and for the full-precision (repr) layout too.
+    """
+    import os
+    import subprocess
+    import sys
+    infomap = os.path.join(ref_exec.REFERENCE_ROOT, 'external', 'Infomap')
+    if not os.access(infomap, os.X_OK):
+        pytest.skip('no Infomap binary in the reference tree')
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden_refpath as mg
+    from bin3c_b200 import bam_io
+    com = synth.make_community(n_genomes=5, n_contigs=400, n_pairs=80000, seed=31337)
+    lengths = np.full(com.n_refs, 500, dtype=np.int64)
+    sites = np.ones(com.n_refs, dtype=np.int64)
+    lengths[com.ref_index] = com.lengths
+    sites[com.ref_index] = com.sites
+    res = ref_exec.run_reference_path(mg.alignments_of(com.records), lengths, sites, 1000, 3, min_mapq=60)
+    ti, tj, ok = synth.unpack_pairs(com.records)
+    ref = oracle.run_path(ti, tj, ok, com.tid2idx(), com.lengths, com.sites, min_len=1000, min_sig=3)
+    g = res['graph']
+    e = sorted((min(a, b), max(a, b), w) for a, b, w in g.edges(data='weight'))
+    parts = {}
+    files = {}
+    for name, (u, v, w), style in (
+            ('reference_py2', ([a for a, _, _ in e], [b for _, b, _ in e], [c for _, _, c in e]), bam_io.FLOAT_STR12),
+            ('product_py2', (ref['u'], ref['v'], ref['w']), bam_io.FLOAT_STR12),
+            ('product_repr', (ref['u'], ref['v'], ref['w']), bam_io.FLOAT_REPR)):
+        work = tmp_path / name
+        work.mkdir()
+        f = str(work / 'cm_graph.edges')
+        if name == 'reference_py2':                      # written independently of the native writer
+            with open(f, 'w') as out:
+                out.write(oracle.edge_lines(u, v, w, py2=True))
+        else:
+            bam_io.write_edges(u, v, w, f, float_style=style)
+        files[name] = open(f).read()
+        subprocess.check_call([infomap, '-u', '-v', '-z', '-i', 'link-list', '-s', '1234', '-N', '10', f, str(work)],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+        parts[name] = oracle.read_tree(str(work / 'cm_graph.tree'))
+    assert files['reference_py2'] == files['product_py2']
+    assert parts['reference_py2'] == parts['product_py2'] == parts['product_repr']
+    assert len(parts['product_py2']) >= 3
