@@ -11,6 +11,11 @@ itertools): the pair loop of contact_map.py:720-798 (driven over packed records 
 the reference accumulator's __getitem__/__setitem__ protocol), the site normalisation of
 contact_map.py:110-113, the mask of :888-905, and the nx.Graph edge loop of
 cluster.py:314-321 (run here with the installed networkx, last-writer-wins included).
+
+Later in the round those pieces were made to execute too -- the pair loop on duck-typed alignment records
+(make_golden_binmap.py), ExtentGrouping with a Python-2 division shim (make_golden_extent.py) and the whole path
+through the reference's own SeqOrder / ContactMap classes and to_graph (make_golden_refpath.py): those vectors
+contain no re-driven glue.  The five cases made by this script are kept as they are.
 """
 import os
 import sys
