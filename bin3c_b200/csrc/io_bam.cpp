@@ -110,20 +110,31 @@ struct b3c_bam {
 namespace {
 
 // ---- inflate pool ----------------------------------------------------------------------------------
-int inflate_block(const Batch &b, const Block &k, uint8_t *out, std::string *msg) {
+// one z_stream per inflate thread, reset for every block (inflateInit2 allocates the window each time otherwise)
+struct Inflater {
     z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, -15) != Z_OK) {
+    bool ok;
+    Inflater() {
+        memset(&zs, 0, sizeof(zs));
+        ok = inflateInit2(&zs, -15) == Z_OK;
+    }
+    ~Inflater() {
+        if (ok) inflateEnd(&zs);
+    }
+};
+
+int inflate_block(Inflater &inf, const Batch &b, const Block &k, uint8_t *out, std::string *msg) {
+    if (!inf.ok || inflateReset(&inf.zs) != Z_OK) {
         *msg = "inflateInit2 failed";
         return B3C_IO_ERR_FORMAT;
     }
+    z_stream &zs = inf.zs;
     zs.next_in = const_cast<Bytef *>(b.comp.data() + k.c_off);
     zs.avail_in = (uInt)k.c_len;
     zs.next_out = out;
     zs.avail_out = k.isize;
     const int rc = inflate(&zs, Z_FINISH);
     const bool ok = (rc == Z_STREAM_END) && zs.total_out == k.isize;
-    inflateEnd(&zs);
     if (!ok) {
         *msg = "corrupt BGZF block (inflate)";
         return B3C_IO_ERR_FORMAT;
@@ -136,6 +147,7 @@ int inflate_block(const Batch &b, const Block &k, uint8_t *out, std::string *msg
 }
 
 void worker_main(b3c_bam *h) {
+    Inflater inf;
     std::unique_lock<std::mutex> lk(h->mu);
     for (;;) {
         h->cv_work.wait(lk, [&] { return h->stop || h->inflating >= 0; });
@@ -151,7 +163,7 @@ void worker_main(b3c_bam *h) {
             const int i = b.next.fetch_add(1);
             if (i >= nb) break;
             const Block &k = b.blocks[i];
-            if (!err && k.isize) err = inflate_block(b, k, b.out.data() + k.u_off, &msg);
+            if (!err && k.isize) err = inflate_block(inf, b, k, b.out.data() + k.u_off, &msg);
             ++mine;
         }
         lk.lock();
