@@ -92,12 +92,19 @@ SIGNATURES = {
                                     _p]),
     'b3c_edges_count': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _pi64, _p]),
     'b3c_edges_fill': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p]),
+    'b3c_synth_pairs': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _f64, _f64, _f64, _f64, C.c_uint64,
+                                  C.c_uint64, _i64, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here == the .so is stale: rebuild
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+# test / debugging hook: a shorter cross-GPU wait than the default 60 s (include/bin3c_b200.h: B3C_OPT_PEER_TIMEOUT_MS)
+if os.environ.get('B3C_PEER_TIMEOUT_MS'):
+    lib.b3c_set_option(4, int(os.environ['B3C_PEER_TIMEOUT_MS']))
 
 
 def last_error():

@@ -874,9 +874,12 @@ struct Peers {
 
 // Flag barrier between the ranks' streams: everything this rank enqueued before it is complete (stream
 // order), thread g tells rank g "rank `rank` reached `epoch`" and waits until rank g has told us the same.
-// A rank that never arrives would hang the node, so the wait gives up after ~4 s and raises the arena's
-// time-out word (reported by the next call that synchronises).
-__global__ void k_peer_barrier(Peers P, int rank, int G, unsigned long long epoch, int64_t o_flag, int64_t o_ctl) {
+// A rank that never arrives would hang the node, so the wait gives up after the peer time-out (60 s unless
+// B3C_OPT_PEER_TIMEOUT_MS says otherwise: ordinary rank skew -- a slower BAM shard, an allocator stall -- must not
+// trip it) and raises the arena's time-out word, reported by the next call that synchronises; the results of a
+// run that timed out are invalid.
+__global__ void k_peer_barrier(Peers P, int rank, int G, unsigned long long epoch, int64_t o_flag, int64_t o_ctl,
+                               long long timeout) {
     const int g = threadIdx.x;
     if (g >= G) return;
     __threadfence_system();
@@ -887,7 +890,7 @@ __global__ void k_peer_barrier(Peers P, int rank, int G, unsigned long long epoc
     unsigned long long seen;
     do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-        if (seen < epoch && clock64() - t0 > 8000000000LL) {
+        if (seen < epoch && clock64() - t0 > timeout) {
             ((unsigned long long *)(P.a[rank] + o_ctl))[2] = 1ull;
             break;
         }
@@ -909,7 +912,7 @@ __global__ void k_peer_put(Peers P, int G, int64_t offset, const unsigned char *
 // all-reduce of up to XA_SCAL doubles: put this rank's values into slot `rank` of every arena, flag barrier,
 // reduce the G slots in rank order (the same order on every rank: bit-identical results).  One CTA.
 __global__ void k_peer_allreduce(Peers P, int rank, int G, unsigned long long epoch, int op, double *__restrict__ val,
-                                 int count, int64_t o_flag, int64_t o_ctl, int64_t o_scal) {
+                                 int count, int64_t o_flag, int64_t o_ctl, int64_t o_scal, long long timeout) {
     const int64_t set = o_scal + (int64_t)(epoch & 1ull) * XA_MAX_RANKS * XA_SCAL * 8;
     const int t = threadIdx.x;
     if (t < G * count) {
@@ -926,7 +929,7 @@ __global__ void k_peer_allreduce(Peers P, int rank, int G, unsigned long long ep
         unsigned long long seen;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-            if (seen < epoch && clock64() - t0 > 8000000000LL) {
+            if (seen < epoch && clock64() - t0 > timeout) {
                 ((unsigned long long *)(P.a[rank] + o_ctl))[2] = 1ull;
                 break;
             }
@@ -1558,7 +1561,8 @@ int b3c_peer_barrier(void *const *h_arena, int32_t rank, int32_t n_ranks, int32_
     int rc = peers_of(h_arena, rank, n_ranks, &P);
     if (rc) return rc;
     const XaLayout X = xa_layout(n_seq, key_capacity);
-    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(P, rank, n_ranks, epoch, X.o_flag, X.o_ctl);
+    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(P, rank, n_ranks, epoch, X.o_flag, X.o_ctl,
+                                                       g_peer_timeout_cycles.load());
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }
@@ -1584,7 +1588,7 @@ int b3c_peer_allreduce_f64(void *const *h_arena, int32_t rank, int32_t n_ranks, 
     B3C_REQUIRE(d_val && count >= 1 && count <= XA_SCAL && (op == 0 || op == 1), "bad arguments");
     const XaLayout X = xa_layout(n_seq, key_capacity);
     k_peer_allreduce<<<1, 64, 0, (cudaStream_t)stream>>>(P, rank, n_ranks, epoch, op, d_val, count, X.o_flag, X.o_ctl,
-                                                         X.o_scal);
+                                                         X.o_scal, g_peer_timeout_cycles.load());
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }
@@ -1603,8 +1607,9 @@ int b3c_shard_publish(void *d_ws, void *const *h_arena, int32_t rank, int32_t n_
     char *mine = P.a[rank];
     k_accum_guard<<<1, 1, 0, s>>>(ctr, st.cap);
     B3C_LAUNCH_CHECK();
-    // receive cursor + overflow word of this rank (nobody scatters to it before the next barrier)
-    B3C_CUDA(cudaMemsetAsync(mine + X.o_ctl, 0, 16, s));
+    // receive cursor, overflow word and time-out word of this rank (nobody scatters to it before the next barrier;
+    // the time-out word is only ever set by this rank's own kernels, so a reported time-out does not outlive a run)
+    B3C_CUDA(cudaMemsetAsync(mine + X.o_ctl, 0, 24, s));
     // chunk weights of the local keys, accumulated in this rank's own slot, then copied to every other arena
     unsigned long long *cw = (unsigned long long *)(mine + X.o_cw) + (int64_t)rank * X.n_chunks;
     B3C_CUDA(cudaMemsetAsync(cw, 0, (size_t)X.n_chunks * 8, s));

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, 'libbin3c_b200.so')
-SOURCES = ['core.cu', 'accum.cu', 'rowops.cu', 'kr.cu']
+SOURCES = ['core.cu', 'accum.cu', 'rowops.cu', 'kr.cu', 'synth.cu']
 HEADERS = ['common.cuh', os.path.join('..', '..', 'include', 'bin3c_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--shared']
@@ -41,25 +41,60 @@ def _nvcc():
     raise RuntimeError('nvcc not found')
 
 
+OBJ_DIR = os.path.join(HERE, '_build')
+
+
+def _deps_common():
+    return [os.path.join(HERE, f) for f in HEADERS] + [os.path.abspath(__file__)]
+
+
+def _obj(src):
+    return os.path.join(OBJ_DIR, os.path.splitext(src)[0] + '.o')
+
+
+def _obj_stale(src):
+    o = _obj(src)
+    if not os.path.exists(o):
+        return True
+    t = os.path.getmtime(o)
+    return any(os.path.getmtime(d) > t for d in [os.path.join(HERE, src)] + _deps_common())
+
+
 def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(HERE, f) for f in SOURCES] + _deps_common()
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
+    """One object per source (compiled in parallel, only when stale), then one link."""
     build_io(force)
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-          [os.path.join(HERE, f) for f in SOURCES] + ['-o', LIB]
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != '--shared']
+
+    def compile_one(src):
+        if not force and not _obj_stale(src):
+            return ''
+        cmd = [_nvcc()] + flags + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(HERE, src), '-o', _obj(src)]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            raise RuntimeError('nvcc failed on {}:\n{}'.format(src, res.stdout))
+        return res.stdout
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        logs = list(ex.map(compile_one, SOURCES))
+    cmd = [_nvcc(), '--shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a'] + \
+          [_obj(f) for f in SOURCES] + ['-o', LIB]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout)
+        raise RuntimeError('nvcc link failed:\n' + res.stdout)
     if verbose:
-        print(res.stdout)
+        print('\n'.join(logs))
     return LIB
 
 

@@ -19,6 +19,8 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 void set_error(const char *fmt, ...);
 extern std::atomic<int64_t> g_launches;
+// cross-GPU flag waits give up after this many SM cycles (b3c_set_option(B3C_OPT_PEER_TIMEOUT_MS); default 60 s)
+extern std::atomic<long long> g_peer_timeout_cycles;
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

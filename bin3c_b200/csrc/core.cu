@@ -7,6 +7,7 @@ namespace b3c {
 
 static thread_local char t_err[1024] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<long long> g_peer_timeout_cycles{60000LL * 2000000LL};
 
 void set_error(const char *fmt, ...) {
     va_list ap;

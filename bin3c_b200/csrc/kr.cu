@@ -148,6 +148,7 @@ struct KRArgs {
     unsigned long long *epoch;                  // this rank's epoch counter (persists across runs)
     unsigned *bar_count, *bar_gen;              // grid barrier of the persistent kernel (zeroed per run)
     int32_t opts;                               // KR_OPT_* bits (b3c_set_option)
+    long long peer_timeout;                     // cycles a cross-GPU wait may last (g_peer_timeout_cycles)
     long long *cta_spmv;                        // [n_bnd] cycles every CTA spent inside its SpMV phases
     unsigned long long *ll;                     // [P_COUNT][n_chunks][2] flagged words: partials exchanged without a barrier
 };
@@ -1060,7 +1061,7 @@ __device__ __forceinline__ void scalar_step(KRScalars &S, int which, const doubl
 // system-wide, and before opening the generation the last CTA tells every rank this one has arrived
 // (release store into its flag array over NVLink) and waits until all ranks have (acquire loads of the local
 // flags).  A rank that never arrives (it failed before its launch) would hang the node, so that wait gives
-// up after ~4 s and poisons the local partials with NaN: every CTA then derives NaN scalars, the loop
+// up after the peer time-out (B3C_OPT_PEER_TIMEOUT_MS, default 60 s) and poisons the local partials with NaN: every CTA then derives NaN scalars, the loop
 // conditions fail, the kernel ends and the host reports the time-out.
 __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned long long &epoch, unsigned &gen) {
     cross = cross && A.n_rank > 1;
@@ -1092,7 +1093,7 @@ __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned
                     unsigned long long seen;
                     do {
                         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-                        if (seen < epoch && clock64() - t0 > 8000000000LL) {
+                        if (seen < epoch && clock64() - t0 > A.peer_timeout) {
                             for (int i = 0; i < P_COUNT; ++i)
                                 A.part[(int64_t)i * A.n_chunks] = __longlong_as_double(0x7ff8000000000000LL);
                             A.timers->sync[T_FIX] = -1;
@@ -1735,6 +1736,7 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.bar_count = (unsigned *)(ws + L.o_bar);
     A.bar_gen = (unsigned *)(ws + L.o_bar + 128);
     A.opts = g_kr_opts.load();
+    A.peer_timeout = g_peer_timeout_cycles.load();
     A.cta_spmv = (long long *)(ws + L.o_cta);
     A.n_rank = 0;
     A.rank = 0;
@@ -1884,6 +1886,10 @@ int b3c_set_option(int32_t key, int64_t value) {
         case B3C_OPT_KR_FLAGS:
             B3C_REQUIRE(value >= 0 && value <= 15, "KR option flags must be in [0, 15]");
             g_kr_opts.store((int)value);
+            return B3C_OK;
+        case B3C_OPT_PEER_TIMEOUT_MS:
+            B3C_REQUIRE(value >= 1 && value <= 3600000, "peer time-out must be between 1 ms and one hour");
+            g_peer_timeout_cycles.store((long long)value * 2000000LL);        // SM cycles at ~2 GHz
             return B3C_OK;
         default:
             set_error("unknown option %d", key);

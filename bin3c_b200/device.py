@@ -178,6 +178,61 @@ class Accumulator(object):
         return DeviceCSR(self.n_seq, indptr, indices, counts, counts=True), self.info
 
 
+class RecordStreamer(object):
+    """
+    Host pair records -> accumulator through a ring of two device staging buffers: the H2D copy of chunk k+1 runs
+    on a side stream while chunk k is classified (use pinned memory for a truly asynchronous copy).  The chunk is
+    large on purpose: every classify launch flushes its per-CTA diagonal histograms.  Used by HotPath (one GPU) and
+    by the sharded driver (every rank streams its own shard).  Returns the bytes copied.
+    """
+
+    def __init__(self, pool):
+        self.pool = pool
+        self._copy_stream = None
+        self._ring_ev = None
+
+    def feed(self, acc, records, n_rec=None, record_bytes=8, chunk_records=1 << 24):
+        B = int(record_bytes)
+        main = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._ring_ev = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
+        copy_stream = self._copy_stream
+        if B == 8:
+            n_rec = int(records.numel())
+            chunk = int(min(chunk_records, max(n_rec, 1)))
+            chunk += chunk & 1                           # chunk starts stay 16-byte aligned
+            ring = [self.pool.get('stage%d' % k, chunk, torch.int64) for k in range(2)]
+        else:
+            n_rec = int(n_rec)
+            assert records.dtype == torch.uint8 and records.numel() >= (n_rec * B + 7) // 8 * 8
+            chunk = max(8, int(min(chunk_records, max(n_rec, 1))) // 8 * 8)
+            ring = [self.pool.get('stage_b%d' % k, chunk * B + 8, torch.uint8) for k in range(2)]
+        copied_bytes = 0
+        copy_stream.wait_stream(main)
+        for k, lo in enumerate(range(0, n_rec, chunk)):
+            hi = min(lo + chunk, n_rec)
+            if B == 8:
+                src, nel = records[lo:hi], hi - lo
+            else:
+                nel = ((hi - lo) * B + 7) // 8 * 8
+                src = records[lo * B:lo * B + nel]
+            buf, (copied, consumed) = ring[k & 1][:nel], self._ring_ev[k & 1]
+            if k >= 2:
+                copy_stream.wait_event(consumed)
+            with torch.cuda.stream(copy_stream):
+                buf.copy_(src, non_blocking=True)
+                copied.record(copy_stream)
+            main.wait_event(copied)
+            if B == 8:
+                acc.add(buf)
+            else:
+                acc.add_packed(buf, hi - lo, B)
+            consumed.record(main)
+            copied_bytes += nel * (8 if B == 8 else 1)
+        return copied_bytes
+
+
 # --------------------------------------------------------------------------------------
 # mask + normalisation
 # --------------------------------------------------------------------------------------

@@ -105,6 +105,14 @@ class Comm(object):
         dist.all_gather_object(out, obj, group=self.group)
         return out
 
+    def gather_object(self, obj, dst=0):
+        """Python objects of all ranks, in rank order, on rank `dst` (None elsewhere)."""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world if self.rank == dst else None
+        dist.gather_object(obj, out, dst=dst, group=self.group)
+        return out
+
 
 # ------------------------------------------------------------------------------------------------
 # the product engine: everything a rank computes, through the C ABI
@@ -208,7 +216,22 @@ class CudaEngine(object):
                                                    self.dev._stream()))
         return t
 
-    def accumulate_peer(self, records, comm):
+    def add_records(self, records, record_bytes=8, n_records=None):
+        """Classify this rank's pair records: a CUDA tensor in place, or HOST records (pinned for an asynchronous
+        copy; native 8-byte or narrow 5/6-byte, bam_io.pack_records) streamed through the staging ring."""
+        B = int(record_bytes)
+        self.h2d_bytes = 0
+        if records.is_cuda:
+            if B == 8:
+                self.acc.add(records)
+            else:
+                self.acc.add_packed(records, int(n_records), B)
+            return
+        if getattr(self, '_streamer', None) is None:
+            self._streamer = self.dev.RecordStreamer(self.pool)
+        self.h2d_bytes = self._streamer.feed(self.acc, records, n_records, B)
+
+    def accumulate_peer(self, records, comm, record_bytes=8, n_records=None):
         """
         The sharded accumulation with every exchange done by kernels over the peer arenas: classify ->
         publish chunk weights | barrier | splits + route/scatter into the owners' buffers | barrier |
@@ -218,7 +241,7 @@ class CudaEngine(object):
         dev, lib = self.dev, self.lib
         ptrs = self.open_arena(comm)
         self.acc.begin()
-        self.acc.add(records)
+        self.add_records(records, record_bytes, n_records)
         ws = dev._ptr(self.acc.ws)
         self.check(lib.b3c_shard_publish(ws, ptrs, comm.rank, comm.world, dev._stream()))
         self.peer_barrier(comm)
@@ -242,9 +265,9 @@ class CudaEngine(object):
         return block, info
 
     # ---- accumulation ------------------------------------------------------------------------
-    def classify(self, records):
+    def classify(self, records, record_bytes=8, n_records=None):
         self.acc.begin()
-        self.acc.add(records)
+        self.add_records(records, record_bytes, n_records)
 
     def row_hist(self):
         dev = self.dev
@@ -493,17 +516,42 @@ class ShardedHotPath(object):
             else bool(peer_exchange)
         self.info = {}
 
-    def accumulate(self, records):
+    def _check_splits(self):
+        """Every rank needs rows: the KR driver and the peer barriers have no form for an idle rank.  The splits are
+        the same on every rank, so all of them raise together (nobody is left spinning at a barrier)."""
+        if np.any(np.diff(self.splits) <= 0):
+            raise ValueError('{} contigs cannot be cut into {} row blocks of whole {}-row chunks (splits {}): run '
+                             'this community on fewer GPUs'.format(self.n, self.comm.world, CHUNK, self.splits.tolist()))
+
+    def stage_barrier(self):
+        """All ranks' streams meet here (a device-side barrier when the peer arenas are open): bench.py puts one in
+        front of every stage it times, so that a stage does not absorb the skew left by its predecessors."""
+        eng, comm = self.engine, self.comm
+        if self.peer and getattr(eng, '_arena', None) is not None:
+            eng.peer_barrier(comm)
+        elif comm.world > 1:
+            eng.synchronize()
+            comm.barrier()
+
+    @property
+    def h2d_bytes(self):
+        return int(getattr(self.engine, 'h2d_bytes', 0))
+
+    def accumulate(self, records, record_bytes=8, n_records=None):
         eng, comm = self.engine, self.comm
         tr = self.trace
         if self.peer:
-            self.block, info = eng.accumulate_peer(records, comm)
+            self.block, info = eng.accumulate_peer(records, comm, record_bytes, n_records)
             self.splits = np.asarray(info['splits'], dtype=np.int32)
             self.row_lo, self.row_hi = int(self.splits[comm.rank]), int(self.splits[comm.rank + 1])
             self.info.update(info)
             tr.mark('accumulate(peer)')
+            self._check_splits()
             return self.block
-        eng.classify(records)
+        if record_bytes != 8:
+            eng.classify(records, record_bytes, n_records)
+        else:
+            eng.classify(records)
         tr.mark('classify')
         rowcnt = comm.all_reduce(eng.row_hist(), 'sum')
         tr.mark('row_hist+allreduce')
@@ -531,6 +579,7 @@ class ShardedHotPath(object):
         else:
             self.block = None
         tr.mark('build_block')
+        self._check_splits()
         return self.block
 
     def compute_mask(self):
@@ -551,7 +600,7 @@ class ShardedHotPath(object):
 
     def balance(self):
         eng, comm = self.engine, self.comm
-        assert self.block is not None, 'a rank without rows is not supported by the KR driver'
+        self._check_splits()
         peer = hasattr(eng, 'kr_run_peer') and not self.host_driven_kr
         self.fused = peer and getattr(eng, 'fused', False)
         if self.fused:
@@ -618,144 +667,8 @@ class ShardedHotPath(object):
         self.trace.on = False
         return dict(self.trace.out)
 
-    def run(self, records):
-        self.accumulate(records)
+    def run(self, records, record_bytes=8, n_records=None):
+        self.accumulate(records, record_bytes, n_records)
         self.compute_mask()
         self.balance()
         return self.edges()
-
-
-# ------------------------------------------------------------------------------------------------
-# bench.py entry for N > 1 (one process per GPU, launched by torchrun)
-# ------------------------------------------------------------------------------------------------
-
-def bench_main(args, rank, local_rank, world):
-    """Weak scaling: every rank brings a C2-sized shard (50M pairs) of a community whose contig and
-    genome counts grow with the number of ranks (world=1 would be exactly C2)."""
-    import json
-    import os
-    import time
-    from . import synth, device as dev
-    from bench import METRIC, UNIT, MIN_LEN, MIN_SIG, ClockSampler, measured_peak
-
-    scale = args.scale
-    n_genomes, n_contigs = 100 * world, 50_000 * world
-    pairs_local = max(1, int(50_000_000 * scale))
-    t0 = time.time()
-    com = synth.make_shard(n_genomes, n_contigs, pairs_local, seed=1002, rank=rank)
-    gen_s = time.time() - t0
-    comm = Comm()
-    rec_dev = dev.to_device(com.records)
-    hp = ShardedHotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=int(2.5 * pairs_local) + 1024,
-                        min_len=MIN_LEN, min_sig=MIN_SIG, comm=comm)
-
-    def sync():
-        torch.cuda.synchronize()
-        comm.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        hp.run(rec_dev)
-    sync()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = dev.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {'accumulate': 0.0, 'mask': 0.0, 'kr': 0.0, 'edges': 0.0}
-    sync()
-    e0.record()
-    for _ in range(args.steps):
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        marks[0].record()
-        hp.accumulate(rec_dev)
-        marks[1].record()
-        hp.compute_mask()
-        marks[2].record()
-        hp.balance()
-        marks[3].record()
-        res = hp.edges()
-        marks[4].record()
-        torch.cuda.synchronize()
-        for k, (a, b) in zip(stage, zip(marks[:-1], marks[1:])):
-            stage[k] += a.elapsed_time(b)
-    e1.record()
-    sync()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device='cuda')
-    comm.all_reduce(ms, 'max')
-    launches = dev.launch_count() - launches0
-    trace = hp.traced_run(rec_dev)
-
-    # ---- end to end: this rank's records start in pinned HOST memory, its edge list ends on the host ----
-    rec_host = torch.from_numpy(com.records.view(np.int64)).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
-
-    stage_dev = torch.empty_like(rec_dev)
-    pinned = {}
-
-    def e2e_step():
-        stage_dev.copy_(rec_host, non_blocking=True)
-        r = hp.run(stage_dev)
-        n = int(r['n_edges'])
-        nbytes = 0
-        for k, m in (('u', n), ('v', n), ('w', n), ('scl', 1)):
-            h = pinned.get(k)
-            if h is None or h.numel() < m:
-                h = pinned[k] = torch.empty(m + m // 4 + 16, dtype=r[k].dtype, pin_memory=True)
-            h[:m].copy_(r[k][:m], non_blocking=True)
-            nbytes += m * h.element_size()
-        torch.cuda.current_stream().synchronize()
-        return nbytes
-
-    e2e_step()
-    sync()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        d2h = e2e_step()
-    sync()
-    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device='cuda')
-    comm.all_reduce(e2e_t, 'max')
-    d2h_t = torch.tensor([d2h], dtype=torch.int64, device='cuda')
-    comm.all_reduce(d2h_t, 'sum')
-    clocks = sampler.stop()
-    tot = torch.tensor([pairs_local, int(hp.block.nnz), int(res['n_edges'])], dtype=torch.int64, device='cuda')
-    comm.all_reduce(tot, 'sum')
-    if rank != 0:
-        return
-    ms_per_step = float(ms.cpu()[0])
-    total_pairs, nnz_full, n_edges = [int(v) for v in tot.cpu()]
-    peak, peak_src = measured_peak()
-    kr = hp.kr_info
-    # rank 0's launch of the persistent KR kernel over its row block: every SpMV streams the block's
-    # entries and reads the whole exchanged vector u
-    blk = hp.block
-    kr_bytes = kr['n_spmv'] * (12 * int(blk.nnz) + 16 * int(blk.n) + 8 * hp.n)
-    kr_s = (kr.get('kernel_us') or 0) * 1e-6
-    ach = kr_bytes / kr_s / 1e9 if kr_s > 0 else None
-    roofline = {'kernel': 'k_kr_persistent (peer mode, rank 0 row block)', 'bound': 'hbm', 'achieved': ach, 'peak': peak,
-                'unit': 'GB/s', 'frac': ach / peak if ach else None, 'traffic': None, 'peak_source': peak_src,
-                'bytes_per_launch': kr_bytes, 'ms_per_launch': kr_s * 1e3,
-                'note': '{} SpMV x (12*nnz_block + 16*rows_block + 8*N) B; the launch also contains the vector phases and '
-                        'the NVLink flag barriers; kernel time from CUDA events around the launch'.format(kr['n_spmv'])}
-    line = {
-        'metric': METRIC, 'value': total_pairs / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u32 counts / f64 balancing', 'data': 'synthetic',
-        'config': {'workload': 'weak scaling of C2: {} genomes, {} contigs, {} pairs = {} per GPU (seed 1002)'.format(
-            n_genomes, n_contigs, total_pairs, pairs_local),
-            'l2': 'input records {} MB per GPU > 126 MB L2, no explicit flush'.format(8 * pairs_local // 1000000),
-            'nnz_full': nnz_full, 'edges': n_edges, 'row_splits': hp.info['splits'], 'generator_s': round(gen_s, 1)},
-        'clocks': clocks,
-        'e2e': {'value': total_pairs / float(e2e_t.cpu()[0]), 'unit': UNIT, 'h2d_bytes_per_step': 8 * total_pairs,
-                'd2h_bytes_per_step': int(d2h_t.cpu()[0]), 'ms_per_step': float(e2e_t.cpu()[0]) * 1e3, 'steps': e2e_steps},
-        'gpu_launches': int(launches),
-        'stages_ms_rank0': {k: round(v / args.steps, 4) for k, v in stage.items()},
-        'kr': {'n_iter': kr['n_iter'], 'n_spmv': kr['n_spmv'], 'outer': kr['outer'], 'zero_diag': kr['zero_diag'],
-               'kernel_us': kr.get('kernel_us'), 'slabs': kr.get('slabs'),
-               'phase_us_work': {k: round(v / 1965.0, 1) for k, v in kr.get('work_cycles', {}).items()},
-               'phase_us_sync': {k: round(v / 1965.0, 1) for k, v in kr.get('sync_cycles', {}).items()}},
-        'substeps_ms_rank0_synced': {k: round(v, 3) for k, v in trace.items()},
-        'pair_counts': {k: hp.info[k] for k in ('accepted', 'ref_excluded', 'poor_match')},
-        'roofline': roofline,
-        'cpu_baseline': None,
-    }
-    print(json.dumps(line))

@@ -33,7 +33,7 @@ class HotPath(object):
         if pair_capacity:
             self._ensure_accumulator(pair_capacity)
         self.events = None
-        self._copy_stream = None
+        self._streamer = None
         self._host = {}
         self.h2d_bytes = self.d2h_bytes = 0
         self.reset()
@@ -64,84 +64,31 @@ class HotPath(object):
 
     def accumulate(self, records, chunk_records=1 << 24, record_bytes=8, n_records=None):
         """
+        records: CUDA tensor (used in place) or host tensor / NumPy array of packed uint64 records.
         record_bytes 5 or 6: `records` is a uint8 tensor / array of NARROW records (bam_io.pack_records) and
         n_records their number; the host->device copy, which bounds the end-to-end rate, shrinks accordingly.
-        records: CUDA tensor (used in place) or host tensor / NumPy array of packed uint64 records.
-        Host records are streamed in chunks on a side stream so the H2D copy of chunk k+1 overlaps
-        the classification of chunk k (use pinned memory for a truly asynchronous copy).  The chunk
-        is large on purpose: every classify launch flushes its per-CTA diagonal histograms.
+        Host records are streamed in chunks through device.RecordStreamer, so the H2D copy of chunk k+1 overlaps
+        the classification of chunk k.
         """
         B = int(record_bytes)
-        if B != 8:
-            return self._accumulate_packed(records, int(n_records), B, chunk_records)
         if not isinstance(records, torch.Tensor):
-            records = torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint64).view(np.int64))
-        n_rec = int(records.numel())
+            if B == 8:
+                records = torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint64).view(np.int64))
+            else:
+                records = torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint8))
+        n_rec = int(records.numel()) if B == 8 else int(n_records)
         acc = self._ensure_accumulator(n_rec)
         self.h2d_bytes = 0
         self._mark('start')
         if records.is_cuda:
-            acc.add(records)
+            if B == 8:
+                acc.add(records)
+            else:
+                acc.add_packed(records, n_rec, B)
         else:
-            # Ring of two device staging buffers owned by the pipeline (no allocator traffic per
-            # chunk): the copy of chunk k+1 runs on the side stream while chunk k is classified.
-            main = torch.cuda.current_stream()
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream()
-                self._ring_ev = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
-            copy_stream = self._copy_stream
-            chunk = int(min(chunk_records, max(n_rec, 1)))
-            ring = [self.pool.get('stage%d' % k, chunk, torch.int64) for k in range(2)]
-            copy_stream.wait_stream(main)
-            for k, lo in enumerate(range(0, n_rec, chunk)):
-                hi = min(lo + chunk, n_rec)
-                buf, (copied, consumed) = ring[k & 1][:hi - lo], self._ring_ev[k & 1]
-                if k >= 2:
-                    copy_stream.wait_event(consumed)
-                with torch.cuda.stream(copy_stream):
-                    buf.copy_(records[lo:hi], non_blocking=True)
-                    copied.record(copy_stream)
-                main.wait_event(copied)
-                acc.add(buf)
-                consumed.record(main)
-                self.h2d_bytes += (hi - lo) * 8
-        self._mark('classify')
-        self.seq_map, self.acc_info = acc.finish(symmetric=True, pool=self.pool)
-        self._mark('sort_reduce_emit')
-        return self.seq_map
-
-    def _accumulate_packed(self, packed, n_rec, B, chunk_records):
-        """accumulate() for narrow records: the same staging ring, over bytes (chunks of a multiple of 8 records)."""
-        if not isinstance(packed, torch.Tensor):
-            packed = torch.from_numpy(np.ascontiguousarray(packed, dtype=np.uint8))
-        assert packed.dtype == torch.uint8 and packed.numel() >= (n_rec * B + 7) // 8 * 8
-        acc = self._ensure_accumulator(n_rec)
-        self.h2d_bytes = 0
-        self._mark('start')
-        if packed.is_cuda:
-            acc.add_packed(packed, n_rec, B)
-        else:
-            main = torch.cuda.current_stream()
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream()
-                self._ring_ev = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
-            copy_stream = self._copy_stream
-            chunk = max(8, int(min(chunk_records, max(n_rec, 1))) // 8 * 8)
-            ring = [self.pool.get('stage_b%d' % k, chunk * B + 8, torch.uint8) for k in range(2)]
-            copy_stream.wait_stream(main)
-            for k, lo in enumerate(range(0, n_rec, chunk)):
-                hi = min(lo + chunk, n_rec)
-                nbytes = ((hi - lo) * B + 7) // 8 * 8
-                buf, (copied, consumed) = ring[k & 1][:nbytes], self._ring_ev[k & 1]
-                if k >= 2:
-                    copy_stream.wait_event(consumed)
-                with torch.cuda.stream(copy_stream):
-                    buf.copy_(packed[lo * B:lo * B + nbytes], non_blocking=True)
-                    copied.record(copy_stream)
-                main.wait_event(copied)
-                acc.add_packed(buf, hi - lo, B)
-                consumed.record(main)
-                self.h2d_bytes += nbytes
+            if self._streamer is None:
+                self._streamer = dev.RecordStreamer(self.pool)
+            self.h2d_bytes = self._streamer.feed(acc, records, n_rec, B, chunk_records)
         self._mark('classify')
         self.seq_map, self.acc_info = acc.finish(symmetric=True, pool=self.pool)
         self._mark('sort_reduce_emit')

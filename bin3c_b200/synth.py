@@ -206,6 +206,128 @@ def make_community(n_genomes, n_contigs, n_pairs, seed, profile='lognormal',
     return tab.community(rec)
 
 
+# ---- counter-based stream ("v2"): record t is a pure function of (seed, t) and the tables -----------------
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+
+
+def _mix64(z):
+    """splitmix64's finaliser over a uint64 array (wrapping arithmetic)."""
+    z = z ^ (z >> np.uint64(30))
+    z = z * np.uint64(0xbf58476d1ce4e5b9)
+    z = z ^ (z >> np.uint64(27))
+    z = z * np.uint64(0x94d049bb133111eb)
+    return z ^ (z >> np.uint64(31))
+
+
+class StreamV2(object):
+    """
+    The pair stream of the large configs (C3, C4): generated on the device by csrc/synth.cu (b3c_synth_pairs) and,
+    bit for bit the same, on the host by host_records() -- the NumPy mirror the CPU oracle is fed from.  Any
+    sub-range [first, first + count) can be produced independently on any rank.
+    """
+
+    def __init__(self, tab, p_same=0.80, p_genome=0.18, p_pass=0.85, excl_end_frac=0.01):
+        self.tab = tab
+        self.p_same, self.p_genome, self.p_pass, self.excl_end_frac = p_same, p_genome, p_pass, excl_end_frac
+        self.seed = int(tab.seed)
+        self.cum_w1 = np.ascontiguousarray(tab.cum_w1, dtype=np.float64)
+        self.cum_len = np.ascontiguousarray(tab.cum_len, dtype=np.float64)
+        self.genome_sorted = np.ascontiguousarray(tab.genome_sorted, dtype=np.int32)
+        self.g_start = np.ascontiguousarray(tab.g_start, dtype=np.int32)
+        self.g_end = np.ascontiguousarray(tab.g_end, dtype=np.int32)
+        self.tid_of_s = np.ascontiguousarray(tab.ref_index[tab.perm], dtype=np.int32)
+        self.excl_tids = np.ascontiguousarray(tab.excl_tids, dtype=np.int32)
+        with np.errstate(over='ignore'):
+            self.key = _mix64(np.array([self.seed], dtype=np.uint64))[0]
+        self._dev = None
+
+    def _draw(self, t, k):
+        with np.errstate(over='ignore'):
+            h = _mix64(self.key + (np.uint64(8) * t + np.uint64(k + 1)) * _GOLD)
+        return (h >> np.uint64(11)).astype(np.float64) * 1.1102230246251565e-16
+
+    def host_records(self, first, count, chunk=1 << 21, threads=None):
+        """Records [first, first + count) of the stream as a uint64 array (NumPy mirror of k_synth_pairs);
+        chunks are independent, so they are spread over a few threads (NumPy releases the GIL)."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        N = self.tab.N
+        out = np.empty(int(count), dtype=np.uint64)
+
+        def one(lo):
+            m = min(chunk, int(count) - lo)
+            t = np.arange(first + lo, first + lo + m, dtype=np.uint64)
+            s1 = np.minimum(np.searchsorted(self.cum_w1, self._draw(t, 0), side='right'), N - 1)
+            kind = self._draw(t, 1)
+            r2 = self._draw(t, 2)
+            s2 = s1.copy()
+            same_g = (kind >= self.p_same) & (kind < self.p_same + self.p_genome)
+            sel = np.flatnonzero(same_g)
+            g = self.genome_sorted[s1[sel]]
+            glo, ghi = self.g_start[g].astype(np.int64), self.g_end[g].astype(np.int64) - 1
+            a, b = self.cum_len[glo], self.cum_len[ghi + 1]
+            u = a + r2[sel] * (b - a)
+            s2[sel] = np.clip(np.searchsorted(self.cum_len, u, side='right') - 1, glo, ghi)
+            sel = np.flatnonzero(kind >= self.p_same + self.p_genome)
+            u = r2[sel] * self.cum_len[N]
+            s2[sel] = np.clip(np.searchsorted(self.cum_len, u, side='right') - 1, 0, N - 1)
+            t1 = self.tid_of_s[s1].astype(np.int64)
+            t2 = self.tid_of_s[s2].astype(np.int64)
+            e = self._draw(t, 3)
+            n_excl = len(self.excl_tids)
+            xt = self.excl_tids[np.minimum((self._draw(t, 4) * float(n_excl)).astype(np.int64), n_excl - 1)]
+            sel = e < self.excl_end_frac
+            t1[sel] = xt[sel]
+            sel = (e >= self.excl_end_frac) & (e < 2.0 * self.excl_end_frac)
+            t2[sel] = xt[sel]
+            swap = self._draw(t, 5) < 0.5
+            out[lo:lo + m] = pack_pairs(np.where(swap, t2, t1), np.where(swap, t1, t2), self._draw(t, 6) < self.p_pass)
+
+        los = list(range(0, int(count), chunk))
+        if threads is None:
+            try:
+                threads = len(os.sched_getaffinity(0))
+            except AttributeError:
+                threads = os.cpu_count() or 1
+        threads = max(1, min(int(threads), len(los), 16))
+        if threads == 1:
+            for lo in los:
+                one(lo)
+        else:
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(one, los))
+        return out
+
+    def device_records(self, first, count, out=None):
+        """The same records generated on the current CUDA device (int64 tensor holding the uint64 bit patterns)."""
+        import ctypes as C
+        import torch
+        from . import device as dev
+        if self._dev is None or self._dev[0] != torch.cuda.current_device():
+            self._dev = (torch.cuda.current_device(),
+                         [dev.to_device(a) for a in (self.cum_w1, self.cum_len, self.genome_sorted, self.g_start,
+                                                     self.g_end, self.tid_of_s, self.excl_tids)])
+        tabs = self._dev[1]
+        if out is None:
+            out = torch.empty(int(count), dtype=torch.int64, device='cuda')
+        assert out.numel() >= count and out.is_cuda and out.element_size() == 8
+        dev.check(dev.lib.b3c_synth_pairs(*[dev._ptr(t) for t in tabs], self.tab.N, self.tab.G, len(self.excl_tids),
+                                          self.p_same, self.p_genome, self.p_pass, self.excl_end_frac,
+                                          C.c_uint64(self.seed), C.c_uint64(int(first)), int(count), dev._ptr(out),
+                                          dev._stream()))
+        return out[:int(count)]
+
+
+def make_stream(name, n_pairs=None):
+    """(CommunityTables, StreamV2, n_pairs) of a named config whose pair stream is counter-based."""
+    kw = dict(CONFIGS[name])
+    P = int(kw.pop('n_pairs') if n_pairs is None else n_pairs)
+    kw.pop('n_pairs', None)
+    assert kw.pop('stream', 'v1') == 'v2', '{} uses the sequential host stream: synth.make_config'.format(name)
+    tab = CommunityTables(**kw)
+    return tab, StreamV2(tab), P
+
+
 def make_shard(n_genomes, n_contigs, n_pairs_local, seed, rank, profile='lognormal'):
     """
     One rank's shard of a community for the multi-GPU runs: every rank builds the same tables from
@@ -220,15 +342,20 @@ def make_shard(n_genomes, n_contigs, n_pairs_local, seed, rank, profile='lognorm
 CONFIGS = {
     'C1': dict(n_genomes=10, n_contigs=2_000, n_pairs=1_000_000, seed=1001),
     'C2': dict(n_genomes=100, n_contigs=50_000, n_pairs=50_000_000, seed=1002),
-    'C3': dict(n_genomes=500, n_contigs=250_000, n_pairs=500_000_000, seed=1003),
-    'C4': dict(n_genomes=2000, n_contigs=1_000_000, n_pairs=2_000_000_000, seed=1004, profile='heavy'),
+    # the pair streams of C3 and C4 are counter-based (StreamV2): generated on the device per shard, mirrored on the host
+    'C3': dict(n_genomes=500, n_contigs=250_000, n_pairs=500_000_000, seed=1003, stream='v2'),
+    'C4': dict(n_genomes=2000, n_contigs=1_000_000, n_pairs=2_000_000_000, seed=1004, profile='heavy', stream='v2'),
 }
 
 
 def make_config(name, scale=1.0):
-    """Community for a named BASELINE config; scale<1 shrinks the pair count only."""
+    """Community for a named BASELINE config with its records on the HOST; scale<1 shrinks the pair count only
+    (for the counter-based configs that is a prefix of the stream)."""
     kw = dict(CONFIGS[name])
     kw['n_pairs'] = max(1, int(kw['n_pairs'] * scale))
+    if kw.pop('stream', 'v1') == 'v2':
+        tab, stream, P = make_stream(name, kw['n_pairs'])
+        return tab.community(stream.host_records(0, P))
     return make_community(**kw)
 
 

@@ -175,8 +175,12 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  * B3C_OPT_KR_FLAGS (default 6) is a bit set for A/B measurements: 1 = order every lane's run of the
  * stream by shared-memory bank (off: the pass costs more than it saves below ~180 SpMV per solve), 2 = align the SpMV CTA ranges with the slabs, 4 = single-word grid
  * barrier (release-add + acquire-poll), 8 = on one GPU the phases that only produce reduction partials
- * hand them over as flagged 8-byte words instead of passing a grid barrier (off: measured slower). */
-enum { B3C_OPT_KR_SLAB_WIDTH = 1, B3C_OPT_KR_MAX_SLABS = 2, B3C_OPT_KR_FLAGS = 3 };
+ * hand them over as flagged 8-byte words instead of passing a grid barrier (off: measured slower).
+ * B3C_OPT_PEER_TIMEOUT_MS (default 60000): how long a cross-GPU flag wait (peer barriers of the sharded
+ * accumulation, hand-overs of peer-mode KR) may last before it gives up.  A time-out is reported as
+ * B3C_ERR_CUDA by the next call that synchronises and the results of that run are invalid; it is cleared
+ * at the start of the next run. */
+enum { B3C_OPT_KR_SLAB_WIDTH = 1, B3C_OPT_KR_MAX_SLABS = 2, B3C_OPT_KR_FLAGS = 3, B3C_OPT_PEER_TIMEOUT_MS = 4 };
 int b3c_set_option(int32_t key, int64_t value);
 
 int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz);
@@ -369,6 +373,23 @@ int b3c_edges_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_
                    const int32_t *d_indices, const uint32_t *d_counts, void *d_ws,
                    const double *d_vmax, int scale, int32_t *d_edge_u, int32_t *d_edge_v,
                    double *d_edge_w, double *d_scl, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Synthetic pair-record stream (bench / test tool -- NOT part of the hot path; the reference has no
+ * counterpart).  SURVEY.md section 8(d): the pair streams of the large BASELINE configs (C3: 4 GB,
+ * C4: 16 GB of packed records) are generated on the device, per shard, by a counter-based generator:
+ * record t is a pure function of (seed, t) and the community tables, so any sub-range is reproducible
+ * on any rank and on the host (bin3c_b200/synth.py: StreamV2.host_records is the bit-exact NumPy
+ * mirror the CPU oracle is fed from).  Tables are in genome-sorted contig order s: d_cum_w1[N]
+ * normalised cumulative end-1 weight, d_cum_len[N+1] cumulative length, d_genome_sorted[N],
+ * d_g_start/d_g_end[G] contig range of a genome, d_tid_of_s[N] BAM reference id, d_excl_tids[n_excl]
+ * excluded references.  Writes records [first, first + count) of the stream to d_records.
+ * ------------------------------------------------------------------------------------ */
+int b3c_synth_pairs(const double *d_cum_w1, const double *d_cum_len, const int32_t *d_genome_sorted,
+                    const int32_t *d_g_start, const int32_t *d_g_end, const int32_t *d_tid_of_s,
+                    const int32_t *d_excl_tids, int32_t n_contigs, int32_t n_genomes, int32_t n_excl,
+                    double p_same, double p_genome, double p_pass, double excl_end_frac, uint64_t seed,
+                    uint64_t first, int64_t count, uint64_t *d_records, void *stream);
 
 #ifdef __cplusplus
 }

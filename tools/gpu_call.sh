@@ -1,18 +1,15 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, the bench line of both arms, the ncu launch list and one full capture of the top kernels.
+# One 1-GPU box visit: parity tests, the bench line of both arms.  Usage: tools/gpu_call.sh [tag]
 set -u
+TAG=${1:-r2}
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-microbench --e2e-steps 1 > gpurun_out/launches_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"k_kr_persistent|k_rs_scatter|k_classify|k_stream_rows|k_edges_count|k_emit" -c 12 -f -o gpurun_out/prof_top \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-microbench --e2e-steps 1 > gpurun_out/prof_top.log 2>&1
-python tools/ncu_summary.py gpurun_out/prof_top.ncu-rep --md > gpurun_out/prof_top_summary.md 2>&1
-python tools/launch_table.py gpurun_out/launches.csv 5 > gpurun_out/launch_table.md 2>&1
-ls -la gpurun_out
-tail -5 gpurun_out/pytest_gpu.log
-cat gpurun_out/bench_n1.json
+export B3C_PEER_TIMEOUT_MS=5000
+( time timeout 1200 python -m pytest tests -m gpu -x -q --durations=12 ) > gpurun_out/pytest_gpu_$TAG.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
+tail -25 gpurun_out/pytest_gpu_$TAG.log
+( time timeout 900 python bench.py ) > gpurun_out/bench_n1_$TAG.json 2> gpurun_out/bench_n1_$TAG.err
+echo "bench rc=$?"; tail -5 gpurun_out/bench_n1_$TAG.err
+( time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
+echo "ref rc=$?"; tail -3 gpurun_out/bench_ref_$TAG.err
+nvidia-smi --query-gpu=name,memory.total --format=csv; nproc; free -g | head -2
+head -c 6000 gpurun_out/bench_n1_$TAG.json
