@@ -264,3 +264,57 @@ def test_infomap_partition_reference_graph_vs_product_edge_list(tmp_path):
     assert files['reference_py2'] == files['product_py2']
     assert parts['reference_py2'] == parts['product_py2'] == parts['product_repr']
     assert len(parts['product_py2']) >= 3
+
+
+def _read_edge_file_gz(path):
+    import gzip
+    u, v, w = [], [], []
+    with gzip.open(path, 'rt') as fh:
+        for line in fh:
+            a, b, c = line.split(' ')
+            u.append(int(a))
+            v.append(int(b))
+            w.append(float(c))
+    return np.array(u), np.array(v), np.array(w)
+
+
+def test_infomap_partition_of_gpu_edge_file(tmp_path):
+    """
+    North-star bar 3 on CUDA OUTPUT: tests/golden/c1_gpu.edges.gz and c1_gpu_py2.edges.gz are the edge files the CUDA
+    path wrote on a B200 for BASELINE config 1 at full size (tests/test_gpu_configs.py::
+    test_c1_full_size_against_the_reference_own_output leaves them in gpurun_out/; committed unchanged, gzip'd).
+    They hold the reference's own edges (c1full.npz: the reference's classes exec'd on the same 1M pairs) to 1e-9,
+    and the reference's Infomap binary, run here with the flags of cluster.py:182-185, returns for both the partition it
+    returns for the reference's own graph file (stored in c1full.npz by make_golden_c1.py).
+    """
+    import gzip
+    import os
+    import shutil
+    import subprocess
+    import sys
+    from conftest import load_golden, GOLDEN_DIR
+    g = load_golden('c1full')
+    u, v, w = _read_edge_file_gz(os.path.join(GOLDEN_DIR, 'c1_gpu.edges.gz'))
+    assert np.array_equal(u, g['edge_u']) and np.array_equal(v, g['edge_v'])
+    assert np.max(np.abs(w - g['edge_w']) / np.abs(g['edge_w'])) <= 1e-9
+    # in the reference's own 12-digit layout the GPU file is the reference's file, byte for byte
+    with gzip.open(os.path.join(GOLDEN_DIR, 'c1_gpu_py2.edges.gz'), 'rt') as fh:
+        gpu_py2 = fh.read()
+    ref_py2 = oracle.edge_lines(g['edge_u'], g['edge_v'], g['edge_w'], py2=True)
+    differing = sum(1 for a, b in zip(gpu_py2.splitlines(), ref_py2.splitlines()) if a != b)
+    assert len(gpu_py2.splitlines()) == len(ref_py2.splitlines()) and differing <= 3, differing
+    infomap = os.path.join(ref_exec.REFERENCE_ROOT, 'external', 'Infomap')
+    if not os.access(infomap, os.X_OK):
+        pytest.skip('no Infomap binary in the reference tree')
+    sys.path.insert(0, GOLDEN_DIR)
+    import make_golden_c1 as mc
+    want = (g['part_node'], g['part_label'])
+    assert want[1].max() + 1 == 10                       # the ten genomes of C1
+    for name in ('c1_gpu.edges.gz', 'c1_gpu_py2.edges.gz'):
+        work = tmp_path / name.replace('.', '_')
+        work.mkdir()
+        f = str(work / 'cm_graph.edges')
+        with gzip.open(os.path.join(GOLDEN_DIR, name), 'rb') as src, open(f, 'wb') as dst:
+            shutil.copyfileobj(src, dst)
+        node, label = mc.partition_arrays(mc.infomap_partition(f, str(work)))
+        assert np.array_equal(node, want[0]) and np.array_equal(label, want[1]), name
