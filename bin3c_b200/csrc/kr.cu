@@ -142,24 +142,37 @@ struct KRArgs {
     // peer mode (one persistent kernel per GPU of a node, exchange buffers mapped over NVLink): u and the
     // partials live in the exchange buffer of every rank and are written into all of them directly
     int32_t n_rank, rank;                       // n_rank <= 1: single GPU / host-driven phases
-    double *xu[KR_MAX_RANKS];                   // u of every rank (own included)
+    double *xx[KR_MAX_RANKS];                   // x of every rank (own included): A.x is xx[rank]
+    double *xz[KR_MAX_RANKS];                   // Z of every rank: A.Z is xz[rank]
     double *xpart[KR_MAX_RANKS];                // partials of every rank
+    unsigned long long *xll[KR_MAX_RANKS];      // flagged partial words (+ arrival counter) of every rank: A.ll is xll[rank]
     unsigned long long *xflag[KR_MAX_RANKS];    // barrier flags of every rank: xflag[g][r] = epoch rank r has reached
     unsigned long long *epoch;                  // this rank's epoch counter (persists across runs)
     unsigned *bar_count, *bar_gen;              // grid barrier of the persistent kernel (zeroed per run)
     int32_t opts;                               // KR_OPT_* bits (b3c_set_option)
     long long peer_timeout;                     // cycles a cross-GPU wait may last (g_peer_timeout_cycles)
+    double *xout;                               // where the persistent kernel leaves the final x (all n entries)
     long long *cta_spmv;                        // [n_bnd] cycles every CTA spent inside its SpMV phases
     unsigned long long *ll;                     // [P_COUNT][n_chunks][2] flagged words: partials exchanged without a barrier
 };
-enum { KR_OPT_BANK_ORDER = 1, KR_OPT_SLAB_ALIGN = 2, KR_OPT_FAST_BARRIER = 4, KR_OPT_LL_PARTIALS = 8 };
+enum { KR_OPT_BANK_ORDER = 1, KR_OPT_SLAB_ALIGN = 2, KR_OPT_FAST_BARRIER = 4, KR_OPT_LL_PARTIALS = 8, KR_OPT_PEER_LL_W = 16 };
 
-// publish u[r] / a partial: to this rank and, in peer mode, straight into every other rank's copy
-__device__ __forceinline__ void put_u(const KRArgs &A, int64_t r, double v) {
-    A.u[r] = v;
+// What crosses the NVLink in peer mode: the owner of row r writes x[r] (once per Newton update) and Z[r] (once per CG
+// step) straight into every rank's copy, and its chunk partials likewise.  Every rank then derives p and u = x * p for
+// ALL columns itself (phase_dir_all), so a CG step needs two cross-GPU hand-overs (after `w`: the p.w partials; after
+// `step`: Z and the remaining partials) instead of the three it took when u was what the ranks exchanged.
+__device__ __forceinline__ void put_x(const KRArgs &A, int64_t r, double v) {
+    A.x[r] = v;
     for (int g = 0; g < A.n_rank; ++g)
-        if (g != A.rank) A.xu[g][r] = v;
+        if (g != A.rank) A.xx[g][r] = v;
 }
+__device__ __forceinline__ void put_z(const KRArgs &A, int64_t r, double v) {
+    A.Z[r] = v;
+    for (int g = 0; g < A.n_rank; ++g)
+        if (g != A.rank) A.xz[g][r] = v;
+}
+// host-driven form (b3c_krp_*): the driver all-reduces u between the phases
+__device__ __forceinline__ void put_u(const KRArgs &A, int64_t r, double v) { A.u[r] = v; }
 // `loc`: the chunk belongs to this rank.  Without peers the other chunks get the identity (the host
 // driver all-reduces the arrays); with peers their owners write them.
 // `ll_epoch` != 0 (single GPU, KR_OPT_LL_PARTIALS): the partial is published as two flagged 8-byte words -- (low
@@ -172,9 +185,16 @@ __device__ __forceinline__ void put_part(const KRArgs &A, int which, int c, doub
     const int64_t i = (int64_t)which * A.n_chunks + c;
     if (ll_epoch) {
         const unsigned long long b = (unsigned long long)__double_as_longlong(v), e = (unsigned long long)ll_epoch << 32;
-        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.ll + 2 * i), "l"((b & 0xffffffffull) | e),
-                     "l"((b >> 32) | e)
-                     : "memory");
+        if (A.n_rank <= 1) {
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.ll + 2 * i), "l"((b & 0xffffffffull) | e),
+                         "l"((b >> 32) | e)
+                         : "memory");
+        } else if (loc) {                              // peer mode: the owner writes the words of every rank
+            for (int g = 0; g < A.n_rank; ++g)
+                asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(A.xll[g] + 2 * i),
+                             "l"((b & 0xffffffffull) | e), "l"((b >> 32) | e)
+                             : "memory");
+        }
     } else if (A.n_rank <= 1) {
         A.part[i] = loc ? v : identity;
     } else if (loc) {
@@ -184,17 +204,31 @@ __device__ __forceinline__ void put_part(const KRArgs &A, int which, int c, doub
 // The flagged words carry the data; WAITING for them is done on one counter polled by one thread per CTA (thousands
 // of threads polling the words themselves queue up in front of the writers at the L2 slices that hold them).  The
 // counter is only a hint -- its relaxed add is not ordered after the words -- so readers still check the epochs.
-__device__ __forceinline__ unsigned *ll_counter(const KRArgs &A) {
-    return (unsigned *)(A.ll + 2 * (int64_t)P_COUNT * A.n_chunks);
+__device__ __forceinline__ unsigned *ll_counter_of(const KRArgs &A, unsigned long long *ll) {
+    return (unsigned *)(ll + 2 * (int64_t)P_COUNT * A.n_chunks);
 }
+__device__ __forceinline__ unsigned *ll_counter(const KRArgs &A) { return ll_counter_of(A, A.ll); }
+// one arrival per chunk and hand-over, at every rank that will read the chunk's words
 __device__ __forceinline__ void ll_arrive(const KRArgs &A) {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ll_counter(A)) : "memory");
+    if (A.n_rank <= 1) {
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ll_counter(A)) : "memory");
+    } else {
+        for (int g = 0; g < A.n_rank; ++g)
+            asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ll_counter_of(A, A.xll[g])) : "memory");
+    }
 }
+// A peer that never writes (it failed) must not hang the node: both waits give up after the peer time-out and poison
+// the result with NaN, as the flag barrier does.
 __device__ __forceinline__ void ll_wait(const KRArgs &A, unsigned target) {
     if (threadIdx.x == 0) {
         unsigned seen;
+        const long long t0 = clock64();
         do {
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ll_counter(A)) : "memory");
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(ll_counter(A)) : "memory");
+            if ((int)(seen - target) < 0 && A.n_rank > 1 && clock64() - t0 > A.peer_timeout) {
+                A.timers->sync[T_FIX] = -1;
+                break;
+            }
         } while ((int)(seen - target) < 0);
     }
     __syncthreads();
@@ -202,8 +236,10 @@ __device__ __forceinline__ void ll_wait(const KRArgs &A, unsigned target) {
 __device__ __forceinline__ double get_part_ll(const KRArgs &A, int which, int c, unsigned ll_epoch) {
     const unsigned long long *p = A.ll + 2 * ((int64_t)which * A.n_chunks + c);
     unsigned long long a, b;
+    const long long t0 = clock64();
     do {
         asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+        if (A.n_rank > 1 && clock64() - t0 > A.peer_timeout) return __longlong_as_double(0x7ff8000000000000LL);
     } while ((unsigned)(a >> 32) != ll_epoch || (unsigned)(b >> 32) != ll_epoch);
     return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
 }
@@ -709,7 +745,7 @@ __device__ __forceinline__ bool chunk_local(const KRArgs &A, int c) {
 // q = A u plus the zero-diagonal term (Q2) for the CHUNK_RPT rows of this thread, loads batched: every cell
 // ordinal of up to NB slabs first, then every segment sum, then the adds in slab order
 template <int NB>
-__device__ __forceinline__ void rows_q_batched(const KRArgs &A, int c, double (&qq)[CHUNK_RPT]) {
+__device__ __forceinline__ void rows_q_batched(const KRArgs &A, const double *opnd, int c, double (&qq)[CHUNK_RPT]) {
     int o[CHUNK_RPT][NB];
     double df[CHUNK_RPT], uu[CHUNK_RPT], t[CHUNK_RPT][NB];
 #pragma unroll
@@ -720,7 +756,7 @@ __device__ __forceinline__ void rows_q_batched(const KRArgs &A, int c, double (&
         for (int k = 0; k < NB; ++k)
             o[i][k] = (ok && k < A.S) ? __ldg(A.seg_of + (int64_t)k * A.npad + (r - A.row_lo)) : -1;
         df[i] = ok ? __ldcg(A.dfix + r) : 0.0;
-        uu[i] = ok ? __ldcg(A.u + r) : 0.0;
+        uu[i] = ok ? __ldcg(opnd + r) : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i)
@@ -737,16 +773,17 @@ __device__ __forceinline__ void rows_q_batched(const KRArgs &A, int c, double (&
     }
 }
 
-__device__ __forceinline__ void rows_q(const KRArgs &A, int c, double (&qq)[CHUNK_RPT]) {
-    if (A.S <= 4) return rows_q_batched<4>(A, c, qq);
-    if (A.S <= ROWQ_S) return rows_q_batched<ROWQ_S>(A, c, qq);
+// `opnd`: the vector the SpMV just multiplied (u, or x for a residual), for the zero-diagonal term
+__device__ __forceinline__ void rows_q(const KRArgs &A, const double *opnd, int c, double (&qq)[CHUNK_RPT]) {
+    if (A.S <= 4) return rows_q_batched<4>(A, opnd, c, qq);
+    if (A.S <= ROWQ_S) return rows_q_batched<ROWQ_S>(A, opnd, c, qq);
 #pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i) {
         const int64_t r = KR_ROW(c, i);
         qq[i] = 0.0;
         if (r < A.row_hi) {
             qq[i] = row_q(A, r);
-            if (__ldcg(A.dfix + r) != 0.0) qq[i] = __dadd_rn(qq[i], __ldcg(A.u + r));
+            if (__ldcg(A.dfix + r) != 0.0) qq[i] = __dadd_rn(qq[i], __ldcg(opnd + r));
         }
     }
 }
@@ -765,11 +802,26 @@ __device__ __forceinline__ void phase_init(const KRArgs &A) {
     }
 }
 
-// v = x * (A x), rk = 1 - v, partial rk.rk           (sparse_utils.py:136-139, 196-199)
-__device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red, unsigned ll = 0) {
+// persistent kernel: x = 1 on the rows of this rank, published to every rank (the first SpMV multiplies x itself)
+__device__ __forceinline__ void phase_init_p(const KRArgs &A) {
     KR_FOR_CHUNKS(c) {
-        double acc = 0.0;
+        if (!chunk_local(A, c)) continue;
+#pragma unroll
+        for (int i = 0; i < CHUNK_RPT; ++i) {
+            const int64_t r = KR_ROW(c, i);
+            if (r < A.row_hi) put_x(A, r, 1.0);
+        }
+    }
+}
+
+// v = x * (A x), rk = 1 - v, partial rk.rk           (sparse_utils.py:136-139, 196-199)
+// and -- used only if an inner loop follows -- Z = rk / v of its first CG step with the partial rk.Z (Q1,
+// sparse_utils.py:158-160), published with the residual's own hand-over.  `opnd` is what the SpMV multiplied.
+__device__ __forceinline__ void phase_resid(const KRArgs &A, const double *opnd, double *s_red, unsigned ll = 0) {
+    KR_FOR_CHUNKS(c) {
+        double acc = 0.0, accz = 0.0;
         const bool loc = chunk_local(A, c);
+        if (!loc && A.n_rank > 1) continue;            // peer mode: the owner of a chunk publishes its partials
         if (loc) {
             double xx[CHUNK_RPT], qq[CHUNK_RPT];
 #pragma unroll
@@ -778,7 +830,7 @@ __device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red, unsi
                 xx[i] = r < A.row_hi ? __ldcg(A.x + r) : 0.0;
             }
             boundary_fix(A, c);
-            rows_q(A, c, qq);
+            rows_q(A, opnd, c, qq);
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
@@ -788,14 +840,46 @@ __device__ __forceinline__ void phase_resid(const KRArgs &A, double *s_red, unsi
                     A.v[r] = vv;
                     A.rk[r] = rr;
                     acc = __dadd_rn(acc, __dmul_rn(rr, rr));
+                    const double z = __ddiv_rn(rr, vv);                       // sparse_utils.py:158
+                    put_z(A, r, z);
+                    accz = __dadd_rn(accz, __dmul_rn(rr, z));
                 }
             }
         }
-        double r[1] = {acc};
-        block_reduce<1, 0>(r, s_red);
+        double r[2] = {acc, accz};
+        block_reduce<2, 0>(r, s_red);
         if (threadIdx.x == 0) {
+            put_part(A, PB, c, r[1], loc, 0.0);
             put_part(A, PA, c, r[0], loc, 0.0, ll);
             if (ll) ll_arrive(A);
+        }
+    }
+}
+
+// persistent kernel: the direction of a CG step for ALL rows, on every rank (x and Z are complete everywhere, p is
+// kept for all rows): first step p = Z (sparse_utils.py:159), later steps p = Z + beta p (:163); u = x * p.  No data
+// leaves the GPU, so the phase ends with a local grid barrier.
+__device__ __forceinline__ void phase_dir_all(const KRArgs &A, bool first, double beta, double *ycur) {
+    KR_FOR_CHUNKS(c) {
+        const bool loc = chunk_local(A, c);
+        double zz[CHUNK_RPT], pp[CHUNK_RPT], xx[CHUNK_RPT];
+#pragma unroll
+        for (int i = 0; i < CHUNK_RPT; ++i) {
+            const int64_t r = KR_ROW(c, i);
+            const bool ok = r < A.n;
+            zz[i] = ok ? __ldcg(A.Z + r) : 0.0;
+            pp[i] = (ok && !first) ? __ldcg(A.p + r) : 0.0;
+            xx[i] = ok ? __ldcg(A.x + r) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < CHUNK_RPT; ++i) {
+            const int64_t r = KR_ROW(c, i);
+            if (r < A.n) {
+                const double pn = first ? zz[i] : __dadd_rn(zz[i], __dmul_rn(beta, pp[i]));
+                A.p[r] = pn;
+                A.u[r] = __dmul_rn(xx[i], pn);
+                if (first && loc) ycur[r] = 1.0;                              // y[:] = e (sparse_utils.py:150)
+            }
         }
     }
 }
@@ -849,6 +933,7 @@ __device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red, unsigned
     KR_FOR_CHUNKS(c) {
         double acc = 0.0;
         const bool loc = chunk_local(A, c);
+        if (!loc && A.n_rank > 1) continue;
         if (loc) {
             double xx[CHUNK_RPT], vv[CHUNK_RPT], pp[CHUNK_RPT], qq[CHUNK_RPT];
 #pragma unroll
@@ -860,7 +945,7 @@ __device__ __forceinline__ void phase_w(const KRArgs &A, double *s_red, unsigned
                 pp[i] = ok ? __ldcg(A.p + r) : 0.0;
             }
             boundary_fix(A, c);
-            rows_q(A, c, qq);
+            rows_q(A, A.u, c, qq);
 #pragma unroll
             for (int i = 0; i < CHUNK_RPT; ++i) {
                 const int64_t r = KR_ROW(c, i);
@@ -887,6 +972,7 @@ __device__ __forceinline__ void phase_step(const KRArgs &A, double alpha, double
     KR_FOR_CHUNKS(c) {
         double rho = 0.0, mn = INFINITY, nmx = INFINITY, g1 = INFINITY, g2 = INFINITY;
         const bool loc = chunk_local(A, c);
+        if (!loc && A.n_rank > 1) continue;
         if (loc) {
             double pp[CHUNK_RPT], yv[CHUNK_RPT], rk[CHUNK_RPT], ww[CHUNK_RPT], vv[CHUNK_RPT];
 #pragma unroll
@@ -914,7 +1000,7 @@ __device__ __forceinline__ void phase_step(const KRArgs &A, double alpha, double
                     const double rr = __dsub_rn(rk[i], __dmul_rn(alpha, ww[i]));          // :186
                     const double z = __dmul_rn(rr, vv[i]);                                // :189
                     A.rk[r] = rr;
-                    A.Z[r] = z;
+                    put_z(A, r, z);
                     rho = __dadd_rn(rho, __dmul_rn(rr, z));
                 }
             }
@@ -933,6 +1019,7 @@ __device__ __forceinline__ void phase_step(const KRArgs &A, double alpha, double
 }
 
 // x *= y (y possibly clamped: y + gamma * alpha p), u = x      (sparse_utils.py:176,182,195)
+template <bool PUBLISH_X>
 __device__ __forceinline__ void phase_update(const KRArgs &A, int ymode, double gamma, double alpha,
                                              const double *ycur) {
     KR_FOR_CHUNKS(c) {
@@ -953,8 +1040,12 @@ __device__ __forceinline__ void phase_update(const KRArgs &A, int ymode, double 
                 double yy = yv[i];
                 if (ymode == 2) yy = __dadd_rn(yy, __dmul_rn(gamma, __dmul_rn(alpha, pp[i])));
                 const double xn = __dmul_rn(xx[i], yy);
-                A.x[r] = xn;
-                put_u(A, r, xn);
+                if (PUBLISH_X) {
+                    put_x(A, r, xn);                   // persistent kernel: the next SpMV multiplies x itself
+                } else {
+                    A.x[r] = xn;
+                    put_u(A, r, xn);
+                }
             }
         }
     }
@@ -1184,45 +1275,54 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
         for (int i = 0; i < 2 * T_COUNT; ++i) tim_work[i] = 0;
     }
 
-    // single GPU: the phases that only produce partials hand over through flagged words instead of a grid barrier
-    const bool use_ll = A.n_rank <= 1 && (A.opts & KR_OPT_LL_PARTIALS);
+    // Hand-overs that carry only reduction partials can go through flagged words instead of a barrier: on one GPU all
+    // three of them (KR_OPT_LL_PARTIALS, off: measured slower than the 1.5 us grid barrier); across GPUs the one after
+    // `w` (KR_OPT_PEER_LL_W), where the alternative is a system-scope fence plus a flag round over the NVLink.
+    const bool ll_single = A.n_rank <= 1 && (A.opts & KR_OPT_LL_PARTIALS);
+    const bool ll_w = ll_single || (A.n_rank > 1 && (A.opts & KR_OPT_PEER_LL_W));
     unsigned ll_epoch = 0;
 
     int mode = -1;                                        // -1: first trip (x = 1)
     for (;;) {
-        if (mode < 0) KR_PHASE(T_INIT, true, phase_init(A));
-        else if (mode == KR_STATE_INNER) KR_PHASE(T_DIR, true, phase_dir(A, S.k == 1, S.beta, ybuf[S.ysel], s_red));
-        else KR_PHASE(T_UPDATE, true, phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
-        KR_PHASE(T_SPMV, false, phase_spmv<SLAB>(A, A.u, sm));
-        const unsigned ll = use_ll ? ++ll_epoch : 0u;      // epoch of this trip's first partial hand-over
+        if (mode < 0) KR_PHASE(T_INIT, true, phase_init_p(A));
+        else if (mode == KR_STATE_INNER) KR_PHASE(T_DIR, false, phase_dir_all(A, S.k == 1, S.beta, ybuf[S.ysel]));
+        else KR_PHASE(T_UPDATE, true, phase_update<true>(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
+        const double *opnd = mode == KR_STATE_INNER ? A.u : A.x;
+        KR_PHASE(T_SPMV, false, phase_spmv<SLAB>(A, opnd, sm));
         if (mode == KR_STATE_INNER) {
             {
                 double r[2];
                 const int ids[2] = {PA, PB};
-                KR_PHASE_B(T_W, !use_ll, phase_w(A, s_red, ll));
-                KR_REDUCE((reduce_parts<2, 0>(A, nc, ids, r, s_red, use_ll ? 1u : 0u, ll)));   // PB dates from the dir phase
+                const unsigned ll = ll_w ? ++ll_epoch : 0u;
+                KR_PHASE_B(T_W, !ll_w, phase_w(A, s_red, ll));
+                KR_REDUCE((reduce_parts<2, 0>(A, nc, ids, r, s_red, ll_w ? 1u : 0u, ll)));   // PB dates from the residual phase
                 KR_SCALAR(KRS_ALPHA, r);
             }
             {
                 double r[5];
                 const int ids[5] = {PC, PMIN, PNEGMAX, PG1, PG2};
-                const unsigned ll2 = use_ll ? ++ll_epoch : 0u;
-                KR_PHASE_B(T_STEP, !use_ll,
-                           phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red, ll2));
-                KR_REDUCE((reduce_parts<1, 4>(A, nc, ids, r, s_red, use_ll ? 31u : 0u, ll2)));
+                const unsigned ll = ll_single ? ++ll_epoch : 0u;
+                KR_PHASE_B(T_STEP, !ll_single,
+                           phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red, ll));
+                KR_REDUCE((reduce_parts<1, 4>(A, nc, ids, r, s_red, ll_single ? 31u : 0u, ll)));
                 KR_SCALAR(KRS_DECIDE, r);
             }
         } else {
             double r[1];
             const int ids[1] = {PA};
-            KR_PHASE_B(T_RESID, !use_ll, phase_resid(A, s_red, ll));
-            KR_REDUCE((reduce_parts<1, 0>(A, nc, ids, r, s_red, use_ll ? 1u : 0u, ll)));
+            const unsigned ll = ll_single ? ++ll_epoch : 0u;
+            KR_PHASE_B(T_RESID, !ll_single, phase_resid(A, opnd, s_red, ll));
+            KR_REDUCE((reduce_parts<1, 0>(A, nc, ids, r, s_red, ll_single ? 1u : 0u, ll)));
             KR_SCALAR(mode < 0 ? KRS_OUTER_FIRST : KRS_OUTER, r);
         }
         mode = S.state;
         if (mode == KR_STATE_DONE) break;
         __syncthreads();                                  // everybody has read the state before thread 0 moves on
     }
+    // the scale vector leaves the exchange buffer before anybody can start another run on it
+    if (A.xout != nullptr)
+        for (int64_t r = (int64_t)blockIdx.x * KR_THREADS + threadIdx.x; r < A.n; r += (int64_t)gridDim.x * KR_THREADS)
+            A.xout[r] = __ldcg(A.x + r);
     if (threadIdx.x == 0) A.cta_spmv[blockIdx.x] = *my_spmv;
     if (timing) {
         *A.ctl = S;
@@ -1564,7 +1664,7 @@ __global__ void __launch_bounds__(KR_THREADS) k_krp_phase(KRArgs A, int phase) {
             zero_nonlocal_u(A);
             break;
         case KRP_RESID:
-            phase_resid(A, s_red);
+            phase_resid(A, A.u, s_red);
             break;
         case KRP_DIR:
             phase_dir(A, S.k == 1, S.beta, ybuf[S.ysel], s_red);
@@ -1577,7 +1677,7 @@ __global__ void __launch_bounds__(KR_THREADS) k_krp_phase(KRArgs A, int phase) {
             phase_step(A, S.alpha, S.delta, S.Delta, ybuf[S.ysel], ybuf[S.ysel ^ 1], s_red);
             break;
         case KRP_UPDATE:
-            phase_update(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]);
+            phase_update<false>(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]);
             zero_nonlocal_u(A);
             break;
         default:
@@ -1622,7 +1722,7 @@ static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
 // KR_OPT_LL_PARTIALS stays off: measured slower than the barrier it replaces (profiles/r1_kr_phases.md)
 // KR_OPT_BANK_ORDER stays off too: the reordering pass costs 91 us at C2 and saves 0.5 us per SpMV, so it would
 // only pay for solves of more than ~180 SpMV (typical: 24-40)
-static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER};
+static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER | KR_OPT_PEER_LL_W};
 constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
 
 struct KRLayout {
@@ -1741,9 +1841,12 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.n_rank = 0;
     A.rank = 0;
     A.epoch = nullptr;
+    A.xout = nullptr;
     for (int g = 0; g < KR_MAX_RANKS; ++g) {
-        A.xu[g] = nullptr;
+        A.xx[g] = nullptr;
+        A.xz[g] = nullptr;
         A.xpart[g] = nullptr;
+        A.xll[g] = nullptr;
         A.xflag[g] = nullptr;
     }
 }
@@ -1884,7 +1987,7 @@ int b3c_set_option(int32_t key, int64_t value) {
             g_slab_s_max.store((int)value);
             return B3C_OK;
         case B3C_OPT_KR_FLAGS:
-            B3C_REQUIRE(value >= 0 && value <= 15, "KR option flags must be in [0, 15]");
+            B3C_REQUIRE(value >= 0 && value <= 31, "KR option flags must be in [0, 31]");
             g_kr_opts.store((int)value);
             return B3C_OK;
         case B3C_OPT_PEER_TIMEOUT_MS:
@@ -1910,6 +2013,7 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
         B3C_CUDA(cudaEventCreate(&ev[1]));
     }
     const int grid = A.n_bnd;
+    A.xout = d_x;                                       // the kernel leaves the whole scale vector here
     void *args[] = {&A};
     B3C_CUDA(cudaMemsetAsync(A.bar_count, 0, 256, s));
     B3C_CUDA(cudaMemsetAsync(A.ll, 0, (size_t)A.n_chunks * 16 * P_COUNT + 128, s));      // epoch 0 = never written
@@ -1924,7 +2028,6 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     count_launch();
     KRScalars S;
     KRTimers T;
-    B3C_CUDA(cudaMemcpyAsync(d_x, A.x, (size_t)A.n * 8, cudaMemcpyDeviceToDevice, s));
     B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaMemcpyAsync(&T, A.timers, sizeof(T), cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaStreamSynchronize(s));
@@ -2018,17 +2121,20 @@ int b3c_kr_run_counts(int32_t n, int64_t nnz, const int64_t *d_indptr, const int
 }
 
 // ---- peer mode: one persistent kernel per GPU of a node, exchange buffers mapped over NVLink ------------
-// exchange buffer of a rank: [flags: KR_MAX_RANKS x u64 | epoch u64 | pad to 256 B][u: nvec x f64][partials]
+// exchange buffer of a rank: [flags: KR_MAX_RANKS x u64][epoch u64][x: nvec x f64][Z: nvec x f64][partials]
+// [flagged partial words + their arrival counter]
 struct XLayout {
-    int64_t o_flag, o_epoch, o_u, o_part, total;
+    int64_t o_flag, o_epoch, o_x, o_z, o_part, o_ll, total;
 };
 static XLayout x_layout(int32_t n) {
     XLayout X;
     Carver c;
     X.o_flag = c.take(KR_MAX_RANKS * 8);
     X.o_epoch = c.take(8);
-    X.o_u = c.take(align_up(n, 32) * 8);
+    X.o_x = c.take(align_up(n, 32) * 8);
+    X.o_z = c.take(align_up(n, 32) * 8);
     X.o_part = c.take(ceil_div(n, CHUNK) * 8 * P_COUNT);
+    X.o_ll = c.take(ceil_div(n, CHUNK) * 16 * P_COUNT + 128);
     X.total = c.cur;
     return X;
 }
@@ -2091,14 +2197,19 @@ static int kr_run_peer_impl(int32_t n, int32_t row_lo, int32_t row_hi, int64_t n
         B3C_REQUIRE(h_exchange[g] != nullptr, "null exchange buffer of rank %d", g);
         char *b = (char *)h_exchange[g];
         A.xflag[g] = (unsigned long long *)(b + X.o_flag);
-        A.xu[g] = (double *)(b + X.o_u);
+        A.xx[g] = (double *)(b + X.o_x);
+        A.xz[g] = (double *)(b + X.o_z);
         A.xpart[g] = (double *)(b + X.o_part);
+        A.xll[g] = (unsigned long long *)(b + X.o_ll);
     }
     A.n_rank = n_ranks;
     A.rank = rank;
     A.epoch = (unsigned long long *)((char *)h_exchange[rank] + X.o_epoch);
-    A.u = A.xu[rank];
+    // x, Z, the partials and their flagged words live in the exchange buffer: every rank's slice is written by its owner
+    A.x = A.xx[rank];
+    A.Z = A.xz[rank];
     A.part = A.xpart[rank];
+    A.ll = A.xll[rank];
     KRScalars S;
     kr_scalars_init(S, tol, delta, Delta, max_iter);
     B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));

@@ -617,10 +617,10 @@ class ShardedHotPath(object):
             st = kr_block_loop(eng, comm)
         self.trace.mark('kr')
         if self.peer:
-            # x: every rank puts its slice into all arenas; zero-diagonal count summed through the arenas
-            eng.peer_put(comm, 'x', self.row_lo, eng.x[self.row_lo:self.row_hi])
+            # the persistent kernel leaves the WHOLE scale vector on every rank (x lives in the exchange buffers);
+            # only the zero-diagonal count, kept per row block, is summed through the arenas
             eng._scal[0] = float(st['zero_diag'])
-            z = eng.peer_allreduce(comm, eng._scal[:1], 'sum')           # also the barrier behind the x slices
+            z = eng.peer_allreduce(comm, eng._scal[:1], 'sum')
             st['zero_diag'] = int(z.cpu()[0])
         else:
             z = torch.tensor([st['zero_diag']], dtype=torch.int64, device=eng.x.device)
@@ -632,8 +632,8 @@ class ShardedHotPath(object):
             raise RuntimeError('matrix balancing failed to converge in {} iterations'.format(st['n_iter']))
         # x: every rank wrote its own slice; assemble the whole vector
         xs = eng.x
-        if self.peer:
-            xs = eng.x_view
+        if peer:
+            pass                                   # complete on every rank already
         elif comm.world > 1:
             full = torch.zeros_like(xs)
             full[self.row_lo:self.row_hi].copy_(xs[self.row_lo:self.row_hi])
