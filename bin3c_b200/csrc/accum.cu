@@ -33,8 +33,8 @@ constexpr int RS_THREADS = 512;
 constexpr int RS_KPT = 8;
 constexpr int RS_TILE = RS_THREADS * RS_KPT;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_BITS = 8;
-constexpr int RS_BINS = 1 << RS_BITS;
+constexpr int RS_BITS = 9;                       // widest digit (k_rs_*<9>); k_rs_*<8> where it needs no more passes
+constexpr int RS_BINS = 1 << RS_BITS;            // sizes the histogram buffers
 constexpr int RS_BLOCKS = kNumSMs * 4;
 
 struct AccumState {
@@ -377,9 +377,11 @@ __device__ __forceinline__ void rs_segment(int64_t n, int64_t *lo, int64_t *hi, 
     *hi = min(n, *t1 * RS_TILE);
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *__restrict__ keys,
                                                         const unsigned long long *__restrict__ d_n, int shift,
                                                         unsigned mask, uint32_t *__restrict__ hist) {
+    constexpr int RS_BINS = 1 << BITS;
     __shared__ uint32_t s_h[RS_BINS];
     for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) s_h[i] = 0;
     __syncthreads();
@@ -411,11 +413,14 @@ __global__ void __launch_bounds__(256) k_rs_scan_digit(uint32_t *__restrict__ hi
     if (threadIdx.x == 0) totals[blockIdx.x] = tot;
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__restrict__ in,
                                                            uint64_t *__restrict__ out,
                                                            const unsigned long long *__restrict__ d_n, int shift,
                                                            unsigned mask, const uint32_t *__restrict__ offs,
                                                            const uint32_t *__restrict__ totals) {
+    constexpr int RS_BITS = BITS, RS_BINS = 1 << BITS;
+    static_assert(RS_BINS <= RS_THREADS, "one thread per digit");
     __shared__ uint32_t s_wcnt[RS_WARPS][RS_BINS + 1];
     __shared__ uint32_t s_off[RS_BINS];
     __shared__ uint32_t s_tot[RS_BINS];
@@ -516,25 +521,37 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
 }
 
 // sort keys on bits [bit_lo, bit_hi); returns the index (0=a,1=b) of the buffer with the result
+// Digits are as wide as it takes to sort `bits` bits in the fewest passes of at most 9 bits (36 key bits: 4 x 9
+// instead of 5 x 8; 18 column bits: 2 x 9 instead of 3 x 8); where 8-bit digits need no more passes (32 bits: 4 x 8)
+// the lighter 256-bin kernels run.
+static int radix_passes(int bits) { return bits <= 0 ? 0 : (bits + RS_BITS - 1) / RS_BITS; }
+
 static int radix_sort(uint64_t *a, uint64_t *b, const unsigned long long *d_n, int bit_lo, int bit_hi,
                       uint32_t *d_hist, cudaStream_t s, int *where) {
     static bool attr_done = false;
     if (!attr_done) {
-        B3C_CUDA(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 8));
+        B3C_CUDA(cudaFuncSetAttribute(k_rs_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 8));
+        B3C_CUDA(cudaFuncSetAttribute(k_rs_scatter<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 8));
         attr_done = true;
     }
+    const int bits = bit_hi - bit_lo, passes = radix_passes(bits);
+    const bool wide = passes > 0 && passes * 8 < bits;           // 8-bit digits would need another pass
+    const int digit = passes > 0 ? (bits + passes - 1) / passes : 0;
     int cur = 0;
-    for (int shift = bit_lo; shift < bit_hi; shift += RS_BITS) {
-        const int w = (bit_hi - shift) < RS_BITS ? (bit_hi - shift) : RS_BITS;
+    for (int shift = bit_lo; shift < bit_hi; shift += digit) {
+        const int w = (bit_hi - shift) < digit ? (bit_hi - shift) : digit;
         const unsigned mask = (1u << w) - 1u;
+        const int bins = wide ? 512 : 256;
         const uint64_t *src = cur ? b : a;
         uint64_t *dst = cur ? a : b;
-        k_rs_hist<<<RS_BLOCKS, RS_THREADS, 0, s>>>(src, d_n, shift, mask, d_hist);
+        uint32_t *d_totals = d_hist + (int64_t)bins * RS_BLOCKS;
+        if (wide) k_rs_hist<9><<<RS_BLOCKS, RS_THREADS, 0, s>>>(src, d_n, shift, mask, d_hist);
+        else k_rs_hist<8><<<RS_BLOCKS, RS_THREADS, 0, s>>>(src, d_n, shift, mask, d_hist);
         B3C_LAUNCH_CHECK();
-        uint32_t *d_totals = d_hist + (int64_t)RS_BINS * RS_BLOCKS;
-        k_rs_scan_digit<<<RS_BINS, 256, 0, s>>>(d_hist, RS_BLOCKS, d_totals);
+        k_rs_scan_digit<<<bins, 256, 0, s>>>(d_hist, RS_BLOCKS, d_totals);
         B3C_LAUNCH_CHECK();
-        k_rs_scatter<<<RS_BLOCKS, RS_THREADS, RS_TILE * 8, s>>>(src, dst, d_n, shift, mask, d_hist, d_totals);
+        if (wide) k_rs_scatter<9><<<RS_BLOCKS, RS_THREADS, RS_TILE * 8, s>>>(src, dst, d_n, shift, mask, d_hist, d_totals);
+        else k_rs_scatter<8><<<RS_BLOCKS, RS_THREADS, RS_TILE * 8, s>>>(src, dst, d_n, shift, mask, d_hist, d_totals);
         B3C_LAUNCH_CHECK();
         cur ^= 1;
     }

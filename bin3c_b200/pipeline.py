@@ -30,6 +30,9 @@ class HotPath(object):
         self._acc = None
         self._capacity = 0
         self.pool = dev.BufferPool()      # outputs live in grow-only buffers reused by every run
+        # pair_capacity: the accumulator's KEY capacity (off-diagonal accepted pairs).  Given explicitly it is kept --
+        # a run whose keys exceed it fails with B3C_ERR_CAPACITY; otherwise it grows to the record count of a run.
+        self._fixed_capacity = bool(pair_capacity)
         if pair_capacity:
             self._ensure_accumulator(pair_capacity)
         self.events = None
@@ -54,7 +57,7 @@ class HotPath(object):
 
     # ---- accumulation ----------------------------------------------------------------------------
     def _ensure_accumulator(self, n_records):
-        if self._acc is None or self._capacity < n_records:
+        if self._acc is None or (self._capacity < n_records and not self._fixed_capacity):
             self._acc = None
             self._capacity = max(int(n_records), 1)
             self._acc = dev.Accumulator(self.n_seq, self.tid2idx, self._capacity)
