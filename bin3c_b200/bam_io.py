@@ -215,9 +215,12 @@ def pair_records_from_bam(path, sites=None, min_mapq=60, strong=None, min_insert
                 parts.append((r, e))
             records = np.concatenate([p[0] for p in parts]) if parts else np.empty(0, dtype=np.uint64)
             extent = np.concatenate([p[1] for p in parts]) if parts else np.empty(0, dtype=np.uint64)
-            return PairRecords(bam.lengths, s, records, references=bam.references, extent_records=extent), bam.stats()
-        records = bam.read_all()
-        return PairRecords(bam.lengths, s, records, references=bam.references), bam.stats()
+        else:
+            records = bam.read_all()
+        stats = bam.stats()
+        meta = dict(min_mapq=min_mapq, strong=strong, min_insert=min_insert or None, min_len=min_len,
+                    bin_size=bin_size or None, short_insert=stats['short_insert'])
+        return PairRecords(bam.lengths, s, records, references=bam.references, extent_records=extent, meta=meta), stats
 
 
 def records_bytes(n_refs):

@@ -48,8 +48,12 @@ class PairRecords(object):
                   needed by ContactMap(bin_size=...)
     """
 
-    def __init__(self, lengths, sites, records, references=None, extent_records=None):
+    def __init__(self, lengths, sites, records, references=None, extent_records=None, meta=None):
         self.extent_records = extent_records      # bin-level records for the extent map (bam_io, bin_size=...)
+        # how the records were made (bam_io.pair_records_from_bam): min_mapq, strong, min_insert, min_len, bin_size and
+        # the reader's short_insert count.  ContactMap checks its own arguments against these, so that e.g. an extent
+        # map is never built over bins other than the ones the reader used.
+        self.meta = dict(meta) if meta else None
         self.lengths = np.asarray(lengths, dtype=np.int64)
         self.sites = np.asarray(sites, dtype=np.int64)
         assert self.lengths.shape == self.sites.shape
@@ -182,12 +186,29 @@ class ContactMap(object):
                  min_size=0, max_fold=None, random_seed=None, strong=None, bin_size=None, tip_size=None,
                  precount=False):
 
-        assert isinstance(bam_file, PairRecords), \
-            'bam_file must be a PairRecords (BAM decoding is outside the accelerated path)'
         assert tip_size is None, 'tip-based maps are out of scope (unreachable from the bin3C CLI)'
+        if not isinstance(bam_file, PairRecords):
+            # the call bin3C.py mkmap makes (bin3C.py:148-158): a BAM path and a FASTA path.  The BAM is decoded by
+            # the native reader (libbin3c_io.so) with this map's matcher, insert filter and bins; the site counts come
+            # from the FASTA (seq_sites.fasta_site_table), or from `seq_file` given as an array / dict / callable.
+            bam_file = self._open_bam(bam_file, enzymes, seq_file, min_insert, min_mapq, min_len, strong, bin_size)
+        meta = bam_file.meta
         assert not bin_size or bam_file.extent_records is not None, \
             'bin_size needs extent records: bam_io.pair_records_from_bam(path, bin_size=..., min_len=...)'
-        assert not min_insert, 'min_insert needs alignment positions, which packed pair records do not carry'
+        if meta is None:
+            assert not min_insert, 'min_insert needs alignment positions: read the BAM with ' \
+                                   'bam_io.pair_records_from_bam(path, min_insert=...) or pass its path'
+        else:
+            # the records were cut with these settings: the map must be described by the same ones
+            assert (meta.get('min_insert') or None) == (min_insert or None), \
+                'records were read with min_insert={}, the map asks for {}'.format(meta.get('min_insert'), min_insert)
+            if bin_size:
+                assert meta.get('bin_size') == bin_size and meta.get('min_len') == min_len, \
+                    'extent records were binned with bin_size={}, min_len={}; the map asks for {}, {}'.format(
+                        meta.get('bin_size'), meta.get('min_len'), bin_size, min_len)
+            if min_insert:
+                assert meta.get('min_len') == min_len, \
+                    'the insert filter was applied with min_len={}; the map asks for {}'.format(meta.get('min_len'), min_len)
 
         self.strong = strong
         self.bam_file = None            # records are not retained on the (pickled) instance
@@ -254,6 +275,40 @@ class ContactMap(object):
 
         # create an initial acceptance mask
         self.set_primary_acceptance_mask()
+
+    @staticmethod
+    def _open_bam(path, enzymes, seq_file, min_insert, min_mapq, min_len, strong, bin_size):
+        """BAM path -> PairRecords with this map's filters (contact_map.py:520-564: FASTA pass, header, reference table).
+        `seq_file`: a FASTA path; or per-reference site counts as an array (one per BAM reference), a dict
+        {reference name: sites} (absent = not in the FASTA), or a callable (name, length) -> sites."""
+        import os
+        from . import bam_io
+        with bam_io.BamPairReader(path) as hdr:
+            names, lengths = list(hdr.references), np.asarray(hdr.lengths, dtype=np.int64)
+        if callable(seq_file):
+            sites = np.array([seq_file(nm, int(ln)) for nm, ln in zip(names, lengths)], dtype=np.int64)
+        elif isinstance(seq_file, dict):
+            sites = np.array([seq_file.get(nm, -1) for nm in names], dtype=np.int64)
+        elif isinstance(seq_file, (str, bytes, os.PathLike)):
+            from .seq_sites import fasta_site_table
+            logger.info('Analyzing sites...')
+            info = fasta_site_table(seq_file, enzymes, min_len or 0)
+            sites = np.full(len(names), -1, dtype=np.int64)
+            for n, (nm, ln) in enumerate(zip(names, lengths)):
+                fa = info.get(nm)
+                if fa is None:
+                    if ln >= (min_len or 0):
+                        logger.info('Sequence: "{}" was not present in reference fasta'.format(nm))
+                    continue
+                assert fa['length'] == ln, \
+                    'Sequence lengths in {} do not agree: bam {} fasta {}'.format(nm, fa['length'], ln)
+                sites[n] = fa['sites']
+        else:
+            sites = np.asarray(seq_file, dtype=np.int64)
+            assert sites.shape == lengths.shape, 'one site count per BAM reference'
+        rec, _ = bam_io.pair_records_from_bam(path, sites=sites, min_mapq=min_mapq, strong=strong, min_insert=min_insert,
+                                              min_len=min_len, bin_size=bin_size)
+        return rec
 
     # ---- pickling: host containers only ------------------------------------------------------
     def __getstate__(self):
@@ -331,6 +386,9 @@ class ContactMap(object):
         counts['accepted'] = info['accepted']
         counts['ref_excluded'] = info['ref_excluded']
         counts['poor_match'] = info['poor_match']
+        if bam.meta is not None:
+            # pairs the reader dropped for a short insert (contact_map.py:761-766) never became records
+            counts['short_insert'] = int(bam.meta.get('short_insert') or 0)
         self.pair_counts = counts
         self._map_weight = info['map_weight']
 

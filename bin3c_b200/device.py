@@ -15,6 +15,23 @@ from . import _cabi
 from ._cabi import lib, check
 
 
+class nvtx_range(object):
+    """NVTX range around a stage of the path (tracing), so nsys / ncu timelines show
+    `b3c:accumulate`, `b3c:mask`, `b3c:kr`, `b3c:edges` ...  A push/pop pair costs nothing measurable without a
+    profiler attached."""
+
+    def __init__(self, name):
+        self.name = 'b3c:' + name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError('bin3c_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')

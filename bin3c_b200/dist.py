@@ -477,6 +477,19 @@ def kr_block_loop(eng, comm, max_phases=1_000_000):
     return st
 
 
+class _no_range(object):
+    """Stand-in for device.nvtx_range when the engine is not the CUDA engine (gloo tests)."""
+
+    def __init__(self, name):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class _Trace(object):
     """Optional wall-clock trace of the driver's sub-steps (device-synchronised; for tuning, never in timed runs)."""
 
@@ -668,7 +681,12 @@ class ShardedHotPath(object):
         return dict(self.trace.out)
 
     def run(self, records, record_bytes=8, n_records=None):
-        self.accumulate(records, record_bytes, n_records)
-        self.compute_mask()
-        self.balance()
-        return self.edges()
+        rng = getattr(getattr(self.engine, 'dev', None), 'nvtx_range', None) or _no_range
+        with rng('accumulate(sharded)'):
+            self.accumulate(records, record_bytes, n_records)
+        with rng('mask'):
+            self.compute_mask()
+        with rng('kr(row block)'):
+            self.balance()
+        with rng('edges'):
+            return self.edges()

@@ -12,6 +12,13 @@ class NoneAcceptedException(ApplicationException):
         super(NoneAcceptedException, self).__init__('all sequences were excluded')
 
 
+class UnknownEnzymeException(ApplicationException):
+    """An enzyme name that is not in the table (raised by seq_utils.py:119-131 in the reference)"""
+    def __init__(self, target, similar):
+        super(UnknownEnzymeException, self).__init__(
+            '{} is undefined, but its similar to: {}'.format(target, ', '.join(similar)))
+
+
 class ParsingError(ApplicationException):
     """An error during input parsing (raised at contact_map.py:571-573)"""
     def __init__(self, msg):

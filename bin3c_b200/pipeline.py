@@ -148,15 +148,22 @@ class HotPath(object):
         self.reset()
         if self.events is not None:
             self.events = []
-        self.accumulate(records, record_bytes=record_bytes, n_records=n_records)
-        self.compute_mask()
+        with dev.nvtx_range('accumulate'):
+            self.accumulate(records, record_bytes=record_bytes, n_records=n_records)
+        with dev.nvtx_range('mask'):
+            self.compute_mask()
         if fused:
-            self.balance_fused()
-            res = self.edges_fused()
+            with dev.nvtx_range('kr'):
+                self.balance_fused()
+            with dev.nvtx_range('edges'):
+                res = self.edges_fused()
         else:
-            self.normalise()
-            self.balance()
-            res = self.edges()
+            with dev.nvtx_range('site_norm'):
+                self.normalise()
+            with dev.nvtx_range('kr'):
+                self.balance()
+            with dev.nvtx_range('edges'):
+                res = self.edges()
         if to_host:
             # one asynchronous D2H per array into pinned, grow-only host buffers, then one sync
             n_edges = int(res['n_edges'])

@@ -346,7 +346,7 @@ def run_reference_path(alignments, ref_lengths, ref_sites, min_len, min_sig, min
           'NoneAcceptedException': NoneAcceptedException, 'find_nearest_jit': find_nearest}
     with open(os.path.join(REFERENCE_ROOT, 'mzd', 'contact_map.py'), 'r') as fh:
         lines = fh.readlines()
-    for lo, hi in ((101, 113), (116, 156), (159, 485), (486, len(lines))):
+    for lo, hi in ((25, 46), (101, 113), (116, 156), (159, 485), (486, len(lines))):      # mean_selector: :25-46
         exec(compile(textwrap.dedent(''.join(lines[lo - 1:hi])), 'mzd/contact_map.py:{}-{}'.format(lo, hi), 'exec'), ns)
     # tqdm is imported inside _bin_map ("import tqdm"): give it the stub through sys.modules for the call
     import sys

@@ -815,3 +815,79 @@ def test_cuda_path_vs_whole_reference_path(dev):
     o1, o2 = np.lexsort((pm.col, pm.row)), np.lexsort((g['bal_col'], g['bal_row']))
     assert np.array_equal(pm.row[o1], g['bal_row'][o2]) and np.array_equal(pm.col[o1], g['bal_col'][o2])
     assert _relerr(pm.data[o1], g['bal_data'][o2]) <= REL_TOL
+
+
+def test_contact_map_from_bam_and_fasta_paths(dev, tmp_path):
+    """
+    The call bin3C.py mkmap makes (bin3C.py:148-158): ContactMap(BAM path, enzymes, FASTA path, min_insert, ...).  The
+    BAM is decoded by the native reader with the map's own matcher and insert filter, the site counts come from the
+    FASTA; matrix, counters (short_insert included) and edges against the oracle's pairing loop + path on the same
+    alignments, site counts against a naive count.
+    """
+    import bam_writer
+    from bin3c_b200 import cluster, synth
+    from bin3c_b200.contact_map import ContactMap
+    from bin3c_b200.exceptions import UnknownEnzymeException
+    from oracle import oracle
+    rng = np.random.default_rng(2718)
+    n_refs, min_len, min_insert = 90, 1000, 400
+    lengths = rng.integers(600, 4000, n_refs)
+    seqs = [''.join(rng.choice(list('ACGT'), int(ln))) for ln in lengths]
+    names = ['ctg%03d' % i for i in range(n_refs)]
+    fasta = str(tmp_path / 'asm.fa')
+    with open(fasta, 'w') as fh:
+        for i, (nm, sq) in enumerate(zip(names, seqs)):
+            if i == 7:
+                continue                                    # one long-enough reference is missing from the FASTA
+            fh.write('>{} some description\n'.format(nm))
+            for k in range(0, len(sq), 70):
+                fh.write(sq[k:k + 70] + '\n')
+    naive = lambda sq: sum(1 for k in range(len(sq) - 3) if sq[k:k + 4] in ('AATT', 'GATC'))      # MluCI + Sau3AI
+    keep = np.array([lengths[i] >= min_len and i != 7 for i in range(n_refs)])
+    idx_of = np.where(keep, np.cumsum(keep) - 1, -1)
+    n_seq = int(keep.sum())
+    # alignments: pairs mostly inside a handful of "genomes", some proper pairs with short inserts
+    alns = []
+    for k in range(40_000):
+        a = int(rng.integers(n_refs))
+        b = a if rng.random() < 0.6 else int((a + rng.integers(1, 6)) % n_refs)
+        good = rng.random() < 0.85
+        proper = a == b and rng.random() < 0.5
+        p1 = int(rng.integers(0, max(1, lengths[a] - 300)))
+        p2 = p1 + int(rng.integers(50, 900)) if proper else int(rng.integers(0, max(1, lengths[b] - 100)))
+        f1, f2 = 0x41 | (0x2 if proper else 0), 0x81 | (0x2 if proper else 0)
+        if rng.random() < 0.5:                              # read 2 first in the file
+            (a, p1, f1), (b, p2, f2) = (b, p2, f2), (a, p1, f1)
+        alns.append(dict(name='q%06d' % k, flag=f1, tid=a, pos=p1, mapq=60 if good else 11, cigar=[(0, 100)]))
+        alns.append(dict(name='q%06d' % k, flag=f2, tid=b, pos=p2, mapq=60, cigar=[(0, 100)]))
+    path = str(tmp_path / 'hic.bam')
+    bam_writer.write_bam(path, names, lengths.tolist(), alns, block_bytes=40000, level=1)
+
+    cm = ContactMap(path, ['MluCI', 'Sau3AI'], fasta, min_insert, 60, min_len=min_len, min_sig=2, random_seed=1)
+    assert cm.total_seq == n_seq and cm.min_insert == min_insert
+    assert [si.sites for si in cm.seq_info] == [naive(seqs[i]) for i in range(n_refs) if keep[i]]
+    assert [si.refid for si in cm.seq_info] == np.flatnonzero(keep).tolist()
+    rec, st = oracle.pair_alignments(alns, n_refs, min_mapq=60, min_insert=min_insert, idx_of=idx_of)
+    assert st['short_insert'] > 100 and cm.pair_counts['short_insert'] == st['short_insert']
+    ti, tj, ok = synth.unpack_pairs(rec)
+    sites = np.array([si.sites for si in cm.seq_info], dtype=np.int64)
+    ref = oracle.run_path(ti, tj, ok, idx_of.astype(np.int32), lengths[keep], sites, min_len=min_len, min_sig=2)
+    assert {k: cm.pair_counts[k] for k in ref['counts']} == ref['counts']
+    sm = cm.seq_map
+    assert np.array_equal(sm.row, ref['seq_map'].row) and np.array_equal(sm.col, ref['seq_map'].col)
+    assert np.array_equal(sm.data, ref['seq_map'].data)
+    u, v, w, scl = cluster.to_edges(cm, norm=True, bisto=True, scale=True)
+    assert np.array_equal(u, ref['u']) and np.array_equal(v, ref['v']) and _relerr(w, ref['w']) <= REL_TOL
+    # site counts handed over directly (array / dict / callable) give the same map
+    by_name = {nm: naive(sq) for i, (nm, sq) in enumerate(zip(names, seqs)) if i != 7}
+    for seq_file in (np.array([by_name.get(nm, -1) for nm in names]), by_name, lambda nm, ln: by_name.get(nm, -1)):
+        cm2 = ContactMap(path, ['MluCI', 'Sau3AI'], seq_file, min_insert, 60, min_len=min_len, min_sig=2)
+        assert np.array_equal(cm2.seq_map.data, sm.data) and cm2.pair_counts == cm.pair_counts
+    with pytest.raises(UnknownEnzymeException):
+        ContactMap(path, ['MluC1'], fasta, None, 60, min_len=min_len)
+    # records read with one insert filter cannot describe a map with another
+    from bin3c_b200 import bam_io
+    pr, _ = bam_io.pair_records_from_bam(path, sites=np.array([by_name.get(nm, -1) for nm in names]), min_mapq=60,
+                                         min_insert=min_insert, min_len=min_len)
+    with pytest.raises(AssertionError):
+        ContactMap(pr, ['x'], None, None, 60, min_len=min_len)
