@@ -92,6 +92,7 @@ SIGNATURES = {
                                     _p]),
     'b3c_edges_count': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _pi64, _p]),
     'b3c_edges_fill': (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p]),
+    'b3c_extent_norm': (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i32, _p, _p]),
     'b3c_synth_pairs': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _f64, _f64, _f64, _f64, C.c_uint64,
                                   C.c_uint64, _i64, _p, _p]),
 }

@@ -569,6 +569,78 @@ class ContactMap(object):
         logger.info('After removing filtered sequences map dimensions: {}'.format((res['n_accepted'],) * 2))
         return res['sub'].to_scipy_coo().astype(dtype)
 
+    # ---- extent (binned) map post-processing (contact_map.py:1001-1036, 1147-1165, 1197-1249) -----------------------
+    def _extent_dev(self, _map=None):
+        """The extent map (or a caller's matrix of the same shape) as a device CSR of raw counts."""
+        m = self.extent_map if _map is None else _map
+        assert scisp.isspmatrix(m), 'Extent matrix is not a scipy matrix type'
+        return dev.DeviceCSR.from_scipy(m, np.uint32)
+
+    def _bin_vectors(self):
+        """Per bin: the length of its sequence (float64, device) and whether that sequence is accepted (uint8)."""
+        import torch
+        bins = np.asarray(self.grouping.bins, dtype=np.int64)
+        bin_len = np.repeat(self.order.lengths().astype(np.float64), bins)
+        bin_ok = np.repeat(self.order.mask_vector().astype(np.uint8), bins)
+        return dev.to_device(bin_len), dev.to_device(bin_ok, torch.uint8)
+
+    def _norm_extent(self, _map, mean_type='geometric'):
+        """
+        Normalise an extent map by the mean of the interacting sequences' lengths (contact_map.py:1147-1165):
+        every entry is divided by 1e-3 * mean(L_i, L_j) on the device (b3c_extent_norm).
+
+        :return: a normalized extent map in lil_matrix format
+        """
+        assert scisp.isspmatrix(_map), 'Extent matrix is not a scipy matrix type'
+        bin_len, _ = self._bin_vectors()
+        return dev.extent_norm(self._extent_dev(_map), bin_len, mean_type).to_scipy_csr().tolil()
+
+    def _compress_extent(self, _map):
+        """
+        Compress the extent map for each sequence that is presently masked: all bins of a masked sequence are
+        removed and the remaining bins renumbered (contact_map.py:1197-1249), with the device compaction kernels.
+
+        :return: a scipy.sparse.coo_matrix pertaining to only the unmasked sequences.
+        """
+        assert scisp.isspmatrix(_map), 'Extent matrix is not a scipy sparse matrix type'
+        _, bin_ok = self._bin_vectors()
+        csr = dev.DeviceCSR.from_scipy(_map, np.float64)
+        res = dev.compress_edges(csr, bin_ok, want_sub=True, want_edges=False, scale=False)
+        return res['sub'].to_scipy_coo()
+
+    def get_extent_map(self, norm=True, bisto=False, permute=False, mean_type='geometric'):
+        """
+        Return the extent map after applying specified processing steps. Masked sequences are always removed
+        (contact_map.py:1001-1036).  Normalisation, compaction and balancing all run on the device; nothing but the
+        result comes back to the host.
+
+        :param norm: sequence length normalisation
+        :param bisto: make map bistochastic
+        :param permute: permute the map using current order (plot-only, contact_map.py:1167-1195: not built)
+        :param mean_type: length normalisation mean (geometric, harmonic, arithmetic)
+        :return: processed extent map
+        """
+        assert self.extent_map is not None, 'this map was built without bin_size'
+        if permute:
+            raise NotImplementedError('reordering is plot-only (contact_map.py:1167-1195) and out of scope')
+        logger.info('Preparing extent map with fill dimensions: {}'.format(self.extent_map.shape))
+        bin_len, bin_ok = self._bin_vectors()
+        m = dev.extent_norm(self._extent_dev(), bin_len, mean_type if norm else None)
+        if norm:
+            logger.debug('Map normalized')
+        compressed = self.order.count_accepted() < self.total_seq
+        if compressed:
+            m = dev.compress_edges(m, bin_ok, want_sub=True, want_edges=False, scale=False)['sub']
+            logger.info('After removing filtered sequences map dimensions: {}'.format((m.n, m.n)))
+        if bisto:
+            x, _ = dev.kr_scale_vector(m)
+            m = dev.kr_apply(m, x)
+            logger.debug('Map balanced')
+            return m.to_scipy_csr()
+        if compressed:
+            return m.to_scipy_coo()
+        return m.to_scipy_csr().tolil() if norm else m.to_scipy_coo()
+
     def _subspace_dev(self, external_mask, want_sub, want_edges, scale, force=False):
         import torch
         if external_mask is not None:

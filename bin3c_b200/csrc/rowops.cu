@@ -68,6 +68,36 @@ __global__ void __launch_bounds__(ROW_THREADS) k_site_norm(int32_t n, int32_t ro
     }
 }
 
+// ---- extent-map length normalisation (contact_map.py:1147-1165, mean_selector :25-46) -----------------
+// out[e] = in[e] / (1e-3 * mean(L_r, L_c)), L the length of the sequence a bin belongs to (one entry per bin);
+// mean_type 0 geometric (x*y)**0.5, 1 harmonic 2*x*y/(x+y), 2 arithmetic 0.5*(x+y), -1: no normalisation (a plain
+// uint32 -> float64 copy).  Operations in the reference's order, each correctly rounded.
+template <typename T>
+__global__ void __launch_bounds__(ROW_THREADS) k_extent_norm(int32_t n, int32_t row_lo,
+                                                             const int64_t *__restrict__ indptr,
+                                                             const int32_t *__restrict__ indices, const T *in,
+                                                             const double *__restrict__ bin_len, int mean_type,
+                                                             double *out) {
+    const unsigned lane = lane_id();
+    const int64_t nw = (int64_t)gridDim.x * ROW_WARPS;
+    for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
+        const int64_t lo = indptr[r], hi = indptr[r + 1];
+        const double li = mean_type >= 0 ? bin_len[r + row_lo] : 1.0;
+        for (int64_t e = lo + lane; e < hi; e += 32) {
+            double v = (double)in[e];
+            if (mean_type >= 0) {
+                const double lj = __ldg(bin_len + indices[e]);
+                double m;
+                if (mean_type == 0) m = __dsqrt_rn(__dmul_rn(li, lj));
+                else if (mean_type == 1) m = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, li), lj), __dadd_rn(li, lj));
+                else m = __dmul_rn(0.5, __dadd_rn(li, lj));
+                v = __ddiv_rn(v, __dmul_rn(1e-3, m));
+            }
+            out[e] = v;
+        }
+    }
+}
+
 // ---- diag(x).A.diag(x) (sparse_utils.py:223-224) ----------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) k_kr_scale(int32_t n, int32_t row_lo,
                                                           const int64_t *__restrict__ indptr,
@@ -412,6 +442,17 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr, 
     B3C_REQUIRE(n_local > 0 && row_lo >= 0 && d_indptr && d_sites && d_data, "bad arguments");
     k_site_norm<double><<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(
         n_local, row_lo, d_indptr, d_indices, d_data, d_sites, d_data);
+    B3C_LAUNCH_CHECK();
+    return B3C_OK;
+}
+
+int b3c_extent_norm(int32_t n_local, int32_t row_lo, const int64_t *d_indptr, const int32_t *d_indices,
+                    const uint32_t *d_counts, const double *d_bin_len, int32_t mean_type, double *d_out,
+                    void *stream) {
+    B3C_REQUIRE(n_local > 0 && row_lo >= 0 && d_indptr && d_out, "bad arguments");
+    B3C_REQUIRE(mean_type >= -1 && mean_type <= 2 && (mean_type < 0 || d_bin_len), "mean_type must be -1..2");
+    k_extent_norm<uint32_t><<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        n_local, row_lo, d_indptr, d_indices, d_counts, d_bin_len, mean_type, d_out);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
 }

@@ -282,6 +282,21 @@ def site_norm(csr, sites, pool=None):
     return csr
 
 
+MEAN_TYPES = {'geometric': 0, 'harmonic': 1, 'arithmetic': 2, None: -1}
+
+
+def extent_norm(csr, bin_len, mean_type='geometric', pool=None):
+    """Extent-map counts (uint32) -> float64 divided by 1e-3 * mean(L_r, L_c) (contact_map.py:1147-1165); mean_type
+    None only converts.  bin_len: CUDA float64, the sequence length of every bin."""
+    assert csr.counts, 'the extent map holds raw uint32 counts'
+    if mean_type not in MEAN_TYPES:
+        raise RuntimeError('unsupported mean type [{}]'.format(mean_type))        # contact_map.py:46
+    out = _alloc(pool, 'extent_normed', csr.nnz, torch.float64)
+    check(lib.b3c_extent_norm(csr.n, csr.row_lo, _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(bin_len),
+                              MEAN_TYPES[mean_type], _ptr(out), _stream()))
+    return csr.like(out)
+
+
 # --------------------------------------------------------------------------------------
 # Knight-Ruiz
 # --------------------------------------------------------------------------------------

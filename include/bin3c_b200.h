@@ -377,6 +377,17 @@ int b3c_edges_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_
                    double *d_edge_w, double *d_scl, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Extent (binned) map length normalisation.  ContactMap._norm_extent with mean_selector
+ * (contact_map.py:1147-1165, :25-46): out[e] = count[e] / (1e-3 * mean(L_r, L_c)), d_bin_len[b] = length
+ * of the sequence bin b belongs to (global bin index); mean_type 0 geometric, 1 harmonic, 2 arithmetic,
+ * -1 none (uint32 -> float64 copy).  The compressed / balanced forms of get_extent_map (:1001-1036) are
+ * b3c_compress_* with the mask expanded to bins and b3c_kr_run / b3c_kr_scale on the result.
+ * ------------------------------------------------------------------------------------ */
+int b3c_extent_norm(int32_t n_local, int32_t row_lo, const int64_t *d_indptr, const int32_t *d_indices,
+                    const uint32_t *d_counts, const double *d_bin_len, int32_t mean_type, double *d_out,
+                    void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Synthetic pair-record stream (bench / test tool -- NOT part of the hot path; the reference has no
  * counterpart).  SURVEY.md section 8(d): the pair streams of the large BASELINE configs (C3: 4 GB,
  * C4: 16 GB of packed records) are generated on the device, per shard, by a counter-based generator:

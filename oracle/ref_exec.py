@@ -357,6 +357,16 @@ def run_reference_path(alignments, ref_lengths, ref_sites, min_len, min_sig, min
     sys.modules['tqdm'] = stub
 
     CM = ns['ContactMap']
+    # _norm_extent (contact_map.py:1147-1165) leaves NumPy arrays in the rows of its LIL matrix (`list /= ndarray`);
+    # SciPy 1.1 converted such a matrix, SciPy 1.18's LIL -> CSR wants lists again: same values, list rows
+    _norm_extent_ref = CM._norm_extent
+
+    def _norm_extent_lists(self, _map, mean_type='geometric'):
+        out = _norm_extent_ref(self, _map, mean_type)
+        for i in range(out.shape[0]):
+            out.data[i] = [float(v) for v in np.asarray(out.data[i], dtype=np.float64).ravel()]
+        return out
+    CM._norm_extent = _norm_extent_lists
     cm = CM.__new__(CM)
     cm.strong, cm.bam_file, cm.bin_size, cm.min_mapq, cm.min_insert = strong, None, bin_size, min_mapq, min_insert
     cm.min_len, cm.min_sig, cm.min_extent, cm.min_size, cm.max_fold = min_len, min_sig, 0, 0, None

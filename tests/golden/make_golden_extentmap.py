@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import ref_exec           # noqa: E402
 
-MIN_LEN, MIN_SIG, BIN_SIZE = 1000, 4, 1500
+MIN_LEN, MIN_SIG, BIN_SIZE = 1000, 26, 1500
 
 
 def main():
@@ -50,6 +50,7 @@ def main():
                bin_size=np.int64(BIN_SIZE), mask=np.asarray(res['mask']).astype(np.uint8),
                bins=np.asarray(cm.grouping.bins, dtype=np.int64),
                ext_row=em.row.astype(np.int64), ext_col=em.col.astype(np.int64), ext_data=em.data.astype(np.int64))
+    print('mask', int(out['mask'].sum()), 'of', len(out['mask']))
     assert 0 < out['mask'].sum() < len(out['mask']), 'the mask must remove some, not all, sequences'
     for tag, kw in (('geo', dict(norm=True, bisto=False, mean_type='geometric')),
                     ('har', dict(norm=True, bisto=False, mean_type='harmonic')),

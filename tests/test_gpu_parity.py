@@ -891,3 +891,55 @@ def test_contact_map_from_bam_and_fasta_paths(dev, tmp_path):
                                          min_insert=min_insert, min_len=min_len)
     with pytest.raises(AssertionError):
         ContactMap(pr, ['x'], None, None, 60, min_len=min_len)
+
+
+def test_extent_map_post_processing_vs_reference(dev, tmp_path):
+    """
+    SURVEY 8f-3 complete: bin3C mkmap --bin-size from a BAM file, then ContactMap.get_extent_map / _norm_extent /
+    _compress_extent on the device against what the REFERENCE'S OWN class returned for the same alignments
+    (tests/golden/extentmap.npz: every mean type, raw, and balanced).
+    """
+    import bam_writer
+    from conftest import load_golden
+    from bin3c_b200.contact_map import ContactMap
+    g = load_golden('extentmap')
+    n_refs = len(g['lengths'])
+    alns = [dict(name='q%d' % (k // 2), flag=int(f), tid=int(t), pos=int(p), mapq=int(q), cigar=[(0, 100)])
+            for k, (t, p, f, q) in enumerate(zip(g['a_tid'], g['a_pos'], g['a_flag'], g['a_mapq']))]
+    path = str(tmp_path / 'ext.bam')
+    bam_writer.write_bam(path, ['r%03d' % i for i in range(n_refs)], g['lengths'].tolist(), alns, block_bytes=50000, level=1)
+    cm = ContactMap(path, ['synthetic'], g['sites'], None, 60, min_len=int(g['min_len']), min_sig=int(g['min_sig']),
+                    bin_size=int(g['bin_size']))
+    assert np.array_equal(cm.grouping.bins, g['bins'])
+    assert np.array_equal(cm.get_primary_acceptance_mask().astype(np.uint8), g['mask'])
+    em = cm.extent_map.tocoo()
+    em.sum_duplicates()
+    o = np.lexsort((em.col, em.row))
+    assert np.array_equal(em.row[o], g['ext_row']) and np.array_equal(em.col[o], g['ext_col'])
+    assert np.array_equal(em.data[o].astype(np.int64), g['ext_data'])
+
+    def check(m, tag, tol):
+        m = sp.coo_matrix(m)
+        m.sum_duplicates()
+        oo = np.lexsort((m.col, m.row))
+        assert np.array_equal(m.row[oo], g[tag + '_row']) and np.array_equal(m.col[oo], g[tag + '_col']), tag
+        assert _relerr(m.data[oo], g[tag + '_data']) <= tol, tag
+
+    for tag, kw, tol in (('geo', dict(norm=True, mean_type='geometric'), 1e-14),
+                         ('har', dict(norm=True, mean_type='harmonic'), 1e-14),
+                         ('ari', dict(norm=True, mean_type='arithmetic'), 1e-14),
+                         ('raw', dict(norm=False), 0.0),
+                         ('geo_bisto', dict(norm=True, bisto=True), REL_TOL)):
+        m = cm.get_extent_map(**kw)
+        assert list(m.shape) == g[tag + '_shape'].tolist()
+        check(m, tag, tol)
+    normed = cm._norm_extent(cm.extent_map.astype(float), 'geometric')
+    assert sp.isspmatrix_lil(normed)
+    check(normed, 'normonly', 1e-14)
+    comp = cm._compress_extent(normed)
+    assert sp.isspmatrix_coo(comp)
+    check(comp, 'geo', 1e-14)
+    with pytest.raises(RuntimeError):
+        cm.get_extent_map(mean_type='quadratic')
+    with pytest.raises(NotImplementedError):
+        cm.get_extent_map(permute=True)

@@ -189,3 +189,36 @@ def test_oracle_vs_whole_reference_path():
     assert np.max(np.abs(ref['x'] - g['kr_x']) / np.abs(g['kr_x'])) <= 1e-12
     assert np.array_equal(ref['u'], g['edge_u']) and np.array_equal(ref['v'], g['edge_v'])
     assert np.max(np.abs(ref['w'] - g['edge_w']) / g['edge_w']) <= 4.5e-16
+
+
+def _sorted_coo(m):
+    import scipy.sparse as sp
+    m = sp.coo_matrix(m)
+    m.sum_duplicates()
+    o = np.lexsort((m.col, m.row))
+    return m.row[o], m.col[o], m.data[o]
+
+
+def test_extent_map_post_processing_against_the_reference():
+    """oracle.norm_extent / compress_extent / extent_map against what the reference's own ContactMap.get_extent_map,
+    _norm_extent and _compress_extent returned (tests/golden/extentmap.npz, make_golden_extentmap.py)."""
+    import scipy.sparse as sp
+    from conftest import load_golden
+    from oracle import oracle
+    g = load_golden('extentmap')
+    nb = int(g['bins'].sum())
+    keep = g['lengths'] >= int(g['min_len'])
+    seq_len = g['lengths'][keep]
+    assert len(seq_len) == len(g['bins']) == len(g['mask'])
+    ext = sp.coo_matrix((g['ext_data'], (g['ext_row'], g['ext_col'])), shape=(nb, nb))
+    r, c, d = _sorted_coo(oracle.norm_extent(ext, seq_len, g['bins']))
+    assert np.array_equal(r, g['normonly_row']) and np.array_equal(c, g['normonly_col'])
+    assert np.max(np.abs(d - g['normonly_data']) / g['normonly_data']) <= 1e-14
+    for tag, kw in (('geo', dict(norm=True, mean_type='geometric')), ('har', dict(norm=True, mean_type='harmonic')),
+                    ('ari', dict(norm=True, mean_type='arithmetic')), ('raw', dict(norm=False)),
+                    ('geo_bisto', dict(norm=True, bisto=True))):
+        m = oracle.extent_map(ext, seq_len, g['bins'], g['mask'].astype(bool), **kw)
+        assert list(m.shape) == g[tag + '_shape'].tolist()
+        r, c, d = _sorted_coo(m)
+        assert np.array_equal(r, g[tag + '_row']) and np.array_equal(c, g[tag + '_col']), tag
+        assert np.max(np.abs(d - g[tag + '_data']) / np.abs(g[tag + '_data'])) <= (1e-9 if 'bisto' in tag else 1e-14), tag
