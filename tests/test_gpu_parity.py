@@ -925,6 +925,9 @@ def test_extent_map_post_processing_vs_reference(dev, tmp_path):
         assert np.array_equal(m.row[oo], g[tag + '_row']) and np.array_equal(m.col[oo], g[tag + '_col']), tag
         assert _relerr(m.data[oo], g[tag + '_data']) <= tol, tag
 
+    # as in the reference, the sequence mask reaches the order (and with it the extent map) in prepare_seq_map
+    assert cm.get_extent_map(norm=False).shape == em.shape
+    cm.prepare_seq_map(norm=True, bisto=True)
     for tag, kw, tol in (('geo', dict(norm=True, mean_type='geometric'), 1e-14),
                          ('har', dict(norm=True, mean_type='harmonic'), 1e-14),
                          ('ari', dict(norm=True, mean_type='arithmetic'), 1e-14),
