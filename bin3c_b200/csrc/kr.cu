@@ -110,6 +110,13 @@ struct KRArgs {
     // counts form: data == nullptr, the value of an entry is count / (s_i * s_j) computed on the fly
     const uint32_t *cnt32;
     const int32_t *sites;
+    // counts form: the stream holds the raw uint32 counts (6 B per entry with its 16-bit column instead of 10) and the
+    // site normalisation is factored out of the sum, (A u)_i = (1/s_i) sum_j c_ij (u_j / s_j): the SpMV multiplies the
+    // SCALED operand us = u / s (xs = x / s for a residual), rows_q applies 1/s_i.  Same sums as the reference's
+    // sum_j (c_ij / (s_i s_j)) u_j up to rounding of the factors (x moves ~1e-15, far inside the 1e-9 bar).
+    int32_t cnt_stream;        // 1: sval is uint32[nnzv]
+    const double *inv_s;       // [n] 1 / s_j (zero site counts taken as one, Q6)
+    double *us, *xs;           // scaled operands (length n; xs lives beside x, in the exchange buffer in peer mode)
     // the stream
     int32_t slab;              // 1: 16-bit columns, u gathered from shared memory; 0: 32-bit columns, gather form
     int32_t S, W, npad;        // slabs (1 in gather form), slab width, local rows padded to CHUNK
@@ -144,6 +151,7 @@ struct KRArgs {
     int32_t n_rank, rank;                       // n_rank <= 1: single GPU / host-driven phases
     double *xx[KR_MAX_RANKS];                   // x of every rank (own included): A.x is xx[rank]
     double *xz[KR_MAX_RANKS];                   // Z of every rank: A.Z is xz[rank]
+    double *xxs[KR_MAX_RANKS];                  // x / s of every rank (counts form): A.xs is xxs[rank]
     double *xpart[KR_MAX_RANKS];                // partials of every rank
     unsigned long long *xll[KR_MAX_RANKS];      // flagged partial words (+ arrival counter) of every rank: A.ll is xll[rank]
     unsigned long long *xflag[KR_MAX_RANKS];    // barrier flags of every rank: xflag[g][r] = epoch rank r has reached
@@ -165,6 +173,12 @@ __device__ __forceinline__ void put_x(const KRArgs &A, int64_t r, double v) {
     A.x[r] = v;
     for (int g = 0; g < A.n_rank; ++g)
         if (g != A.rank) A.xx[g][r] = v;
+    if (A.cnt_stream) {                                // the residual SpMV multiplies x / s
+        const double vs = __dmul_rn(v, __ldg(A.inv_s + r));
+        A.xs[r] = vs;
+        for (int g = 0; g < A.n_rank; ++g)
+            if (g != A.rank) A.xxs[g][r] = vs;
+    }
 }
 __device__ __forceinline__ void put_z(const KRArgs &A, int64_t r, double v) {
     A.Z[r] = v;
@@ -369,23 +383,31 @@ __host__ __device__ __forceinline__ int64_t stream_phys(int64_t logical) {
 
 // What a lane holds for one piece, loaded SPMV_DEPTH pieces ahead of its use.
 struct PieceRegs {
-    double a[SPMV_EPP];
+    double a[SPMV_EPP];        // fp64 stream: the values
+    unsigned long long q[SPMV_EPP / 2];   // counts stream: the eight uint32 counts, two per word
     unsigned c[SPMV_EPP];      // slab form: c[0..3] hold the 8 columns, 16 bit each; gather form: one column each
     unsigned fw;               // first piece of a chunk only: start flags of the lane's 16 entries
     int seg0;                  // first piece only: ordinal of the first segment that starts inside the chunk
 };
 
-template <bool SLAB>
+template <bool SLAB, bool CNT>
 __device__ __forceinline__ void piece_load(const KRArgs &A, int64_t p, int64_t p_hi, PieceRegs &R) {
     if (p >= p_hi) return;
     const int64_t chunk = p >> 1;
     const int64_t e = chunk * SPMV_CHUNK + (p & 1) * (SPMV_CHUNK / 2) + SPMV_EPP * lane_id();
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(R.a[0]), "=d"(R.a[1]), "=d"(R.a[2]), "=d"(R.a[3])
-                 : "l"(A.sval + e));
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(R.a[4]), "=d"(R.a[5]), "=d"(R.a[6]), "=d"(R.a[7])
-                 : "l"(A.sval + e + 4));
+    if (CNT) {
+        // eight uint32 counts (one 32-byte load), widened when the piece is processed
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(R.q[0]), "=l"(R.q[1]), "=l"(R.q[2]), "=l"(R.q[3])
+                     : "l"((const uint32_t *)A.sval + e));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(R.a[0]), "=d"(R.a[1]), "=d"(R.a[2]), "=d"(R.a[3])
+                     : "l"(A.sval + e));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(R.a[4]), "=d"(R.a[5]), "=d"(R.a[6]), "=d"(R.a[7])
+                     : "l"(A.sval + e + 4));
+    }
     if (SLAB) {
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(R.c[0]), "=r"(R.c[1]), "=r"(R.c[2]), "=r"(R.c[3])
@@ -439,7 +461,7 @@ struct LaneRun {
 };
 
 // One piece: 8 products per lane, added to the lane's running segment; a start flag closes the open segment.
-template <bool SLAB>
+template <bool SLAB, bool CNT>
 __device__ __forceinline__ void piece_process(const KRArgs &A, const double *u, const PieceRegs &R, const Smem &sm,
                                               bool first_piece, LaneRun &L) {
     const unsigned lane = lane_id();
@@ -458,17 +480,20 @@ __device__ __forceinline__ void piece_process(const KRArgs &A, const double *u, 
         L.head = 0.0;
         L.nseen = 0;
     }
-    double x[SPMV_EPP];
+    double x[SPMV_EPP], a[SPMV_EPP];
+#pragma unroll
+    for (int i = 0; i < SPMV_EPP; ++i)
+        a[i] = CNT ? (double)(uint32_t)(R.q[i >> 1] >> ((i & 1) * 32)) : R.a[i];
     if (SLAB) {
         const double *su = sm.u;
 #pragma unroll
         for (int i = 0; i < SPMV_EPP / 2; ++i) {
-            x[2 * i] = __dmul_rn(R.a[2 * i], su[R.c[i] & 0xffffu]);
-            x[2 * i + 1] = __dmul_rn(R.a[2 * i + 1], su[R.c[i] >> 16]);
+            x[2 * i] = __dmul_rn(a[2 * i], su[R.c[i] & 0xffffu]);
+            x[2 * i + 1] = __dmul_rn(a[2 * i + 1], su[R.c[i] >> 16]);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < SPMV_EPP; ++i) x[i] = __dmul_rn(R.a[i], u[R.c[i]]);
+        for (int i = 0; i < SPMV_EPP; ++i) x[i] = __dmul_rn(a[i], u[R.c[i]]);
     }
     // segments are padded to whole pieces (seg_padded), so only the piece's first entry can carry a flag:
     // add the piece up as a fixed tree, then either extend the open segment or close it and open the next
@@ -577,7 +602,7 @@ __device__ __forceinline__ void part_stitch(const KRArgs &A, const Smem &sm, int
 // The SpMV phase.  The CTA owns a contiguous range of chunks; it is cut into parts at slab boundaries
 // (almost always one part), and inside a part every warp streams its own contiguous run of chunks with no
 // block-wide synchronisation; the runs are stitched once per part.
-template <bool SLAB>
+template <bool SLAB, bool CNT>
 __device__ __forceinline__ void phase_spmv(const KRArgs &A, const double *u, Smem &sm) {
     for (int i = threadIdx.x; i <= A.S; i += KR_THREADS) sm.slab[i] = A.slab_c0[i];
     if (threadIdx.x == 0) {
@@ -628,9 +653,9 @@ __device__ __forceinline__ void phase_spmv(const KRArgs &A, const double *u, Sme
         const int64_t w_lo = p_lo + n * warp / KR_WARPS, w_hi = p_lo + n * (warp + 1) / KR_WARPS;
         const int64_t q_lo = 2 * w_lo, q_hi = 2 * w_hi;            // pieces
         PieceRegs R0, R1, R2;
-        piece_load<SLAB>(A, q_lo, q_hi, R0);
-        piece_load<SLAB>(A, q_lo + 1, q_hi, R1);
-        piece_load<SLAB>(A, q_lo + 2, q_hi, R2);
+        piece_load<SLAB, CNT>(A, q_lo, q_hi, R0);
+        piece_load<SLAB, CNT>(A, q_lo + 1, q_hi, R1);
+        piece_load<SLAB, CNT>(A, q_lo + 2, q_hi, R2);
         // every gather of the previous part is behind that part's barrier, so the slab can be replaced
         if (SLAB) slab_fetch(A, u, slab, sm);
         WarpRun run;
@@ -646,23 +671,23 @@ __device__ __forceinline__ void phase_spmv(const KRArgs &A, const double *u, Sme
         if (q_lo < q_hi) first = R0.seg0;
         // the ring has three stages and a chunk two pieces: six pieces (three chunks) per trip keep every index static
         for (int64_t q = q_lo; q < q_hi; q += 6) {
-            piece_process<SLAB>(A, u, R0, sm, true, L);
-            piece_load<SLAB>(A, q + 3, q_hi, R0);
-            piece_process<SLAB>(A, u, R1, sm, false, L);
-            piece_load<SLAB>(A, q + 4, q_hi, R1);
+            piece_process<SLAB, CNT>(A, u, R0, sm, true, L);
+            piece_load<SLAB, CNT>(A, q + 3, q_hi, R0);
+            piece_process<SLAB, CNT>(A, u, R1, sm, false, L);
+            piece_load<SLAB, CNT>(A, q + 4, q_hi, R1);
             chunk_finish(A, L, run);
             if (q + 2 < q_hi) {
-                piece_process<SLAB>(A, u, R2, sm, true, L);
-                piece_load<SLAB>(A, q + 5, q_hi, R2);
-                piece_process<SLAB>(A, u, R0, sm, false, L);
-                piece_load<SLAB>(A, q + 6, q_hi, R0);
+                piece_process<SLAB, CNT>(A, u, R2, sm, true, L);
+                piece_load<SLAB, CNT>(A, q + 5, q_hi, R2);
+                piece_process<SLAB, CNT>(A, u, R0, sm, false, L);
+                piece_load<SLAB, CNT>(A, q + 6, q_hi, R0);
                 chunk_finish(A, L, run);
             }
             if (q + 4 < q_hi) {
-                piece_process<SLAB>(A, u, R1, sm, true, L);
-                piece_load<SLAB>(A, q + 7, q_hi, R1);
-                piece_process<SLAB>(A, u, R2, sm, false, L);
-                piece_load<SLAB>(A, q + 8, q_hi, R2);
+                piece_process<SLAB, CNT>(A, u, R1, sm, true, L);
+                piece_load<SLAB, CNT>(A, q + 7, q_hi, R1);
+                piece_process<SLAB, CNT>(A, u, R2, sm, false, L);
+                piece_load<SLAB, CNT>(A, q + 8, q_hi, R2);
                 chunk_finish(A, L, run);
             }
         }
@@ -747,7 +772,7 @@ __device__ __forceinline__ bool chunk_local(const KRArgs &A, int c) {
 template <int NB>
 __device__ __forceinline__ void rows_q_batched(const KRArgs &A, const double *opnd, int c, double (&qq)[CHUNK_RPT]) {
     int o[CHUNK_RPT][NB];
-    double df[CHUNK_RPT], uu[CHUNK_RPT], t[CHUNK_RPT][NB];
+    double df[CHUNK_RPT], uu[CHUNK_RPT], is[CHUNK_RPT], t[CHUNK_RPT][NB];
 #pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i) {
         const int64_t r = KR_ROW(c, i);
@@ -757,6 +782,7 @@ __device__ __forceinline__ void rows_q_batched(const KRArgs &A, const double *op
             o[i][k] = (ok && k < A.S) ? __ldg(A.seg_of + (int64_t)k * A.npad + (r - A.row_lo)) : -1;
         df[i] = ok ? __ldcg(A.dfix + r) : 0.0;
         uu[i] = ok ? __ldcg(opnd + r) : 0.0;
+        is[i] = (ok && A.cnt_stream) ? __ldg(A.inv_s + r) : 1.0;
     }
 #pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i)
@@ -768,6 +794,7 @@ __device__ __forceinline__ void rows_q_batched(const KRArgs &A, const double *op
 #pragma unroll
         for (int k = 0; k < NB; ++k)
             if (o[i][k] >= 0) s = __dadd_rn(s, t[i][k]);
+        if (A.cnt_stream) s = __dmul_rn(s, is[i]);                 // counts stream: the row's 1 / s_i
         if (df[i] != 0.0) s = __dadd_rn(s, uu[i]);                 // zero diagonal counted as one (Q2)
         qq[i] = s;
     }
@@ -783,6 +810,7 @@ __device__ __forceinline__ void rows_q(const KRArgs &A, const double *opnd, int 
         qq[i] = 0.0;
         if (r < A.row_hi) {
             qq[i] = row_q(A, r);
+            if (A.cnt_stream) qq[i] = __dmul_rn(qq[i], __ldg(A.inv_s + r));
             if (__ldcg(A.dfix + r) != 0.0) qq[i] = __dadd_rn(qq[i], __ldcg(opnd + r));
         }
     }
@@ -877,7 +905,9 @@ __device__ __forceinline__ void phase_dir_all(const KRArgs &A, bool first, doubl
             if (r < A.n) {
                 const double pn = first ? zz[i] : __dadd_rn(zz[i], __dmul_rn(beta, pp[i]));
                 A.p[r] = pn;
-                A.u[r] = __dmul_rn(xx[i], pn);
+                const double un = __dmul_rn(xx[i], pn);
+                A.u[r] = un;
+                if (A.cnt_stream) A.us[r] = __dmul_rn(un, __ldg(A.inv_s + r));
                 if (first && loc) ycur[r] = 1.0;                              // y[:] = e (sparse_utils.py:150)
             }
         }
@@ -1249,7 +1279,7 @@ __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned
         if (timing) tim_work[T_SCALAR] += clock64() - ts_;                     \
     } while (0)
 
-template <bool SLAB>
+template <bool SLAB, bool CNT>
 __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem sm = carve_smem(smem_raw);
@@ -1287,8 +1317,9 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
         if (mode < 0) KR_PHASE(T_INIT, true, phase_init_p(A));
         else if (mode == KR_STATE_INNER) KR_PHASE(T_DIR, false, phase_dir_all(A, S.k == 1, S.beta, ybuf[S.ysel]));
         else KR_PHASE(T_UPDATE, true, phase_update<true>(A, S.ymode, S.gamma, S.alpha, ybuf[S.ysel]));
-        const double *opnd = mode == KR_STATE_INNER ? A.u : A.x;
-        KR_PHASE(T_SPMV, false, phase_spmv<SLAB>(A, opnd, sm));
+        const double *opnd = mode == KR_STATE_INNER ? A.u : A.x;                 // what the product is taken with ...
+        const double *mult = CNT ? (mode == KR_STATE_INNER ? A.us : A.xs) : opnd;    // ... and what the stream multiplies
+        KR_PHASE(T_SPMV, false, (phase_spmv<SLAB, CNT>(A, mult, sm)));
         if (mode == KR_STATE_INNER) {
             {
                 double r[2];
@@ -1370,11 +1401,12 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
         // software pipeline over the 32-entry windows: columns and counts are loaded two windows ahead, the site
         // count of a column (a scattered gather that needs the column first) one window ahead
         const bool want_cnt = FILL && A.cnt32 != nullptr;
+        const bool want_site = want_cnt && !A.cnt_stream;       // the counts stream stores the counts themselves
         int col_a = (lo + lane < hi) ? A.indices[lo + lane] : 0;
         int col_b = (lo + 32 + lane < hi) ? A.indices[lo + 32 + lane] : 0;
         uint32_t cnt_a = (want_cnt && lo + lane < hi) ? A.cnt32[lo + lane] : 0u;
         uint32_t cnt_b = (want_cnt && lo + 32 + lane < hi) ? A.cnt32[lo + 32 + lane] : 0u;
-        int32_t site_a = want_cnt ? __ldg(A.sites + min(max(col_a, 0), A.n - 1)) : 1;
+        int32_t site_a = want_site ? __ldg(A.sites + min(max(col_a, 0), A.n - 1)) : 1;
         for (int64_t e0 = lo; e0 < hi; e0 += 32) {
             const int64_t e = e0 + lane;
             const bool valid = e < hi;
@@ -1388,7 +1420,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 col_b = A.indices[e + 64];
                 if (want_cnt) cnt_b = A.cnt32[e + 64];
             }
-            if (want_cnt && e0 + 32 < hi) site_a = __ldg(A.sites + min(max(col_a, 0), A.n - 1));
+            if (want_site && e0 + 32 < hi) site_a = __ldg(A.sites + min(max(col_a, 0), A.n - 1));
             if (col < 0 || col >= A.n) {           // reported through ctl->status; clamped to stay in bounds
                 bad = true;
                 col = col < 0 ? 0 : A.n - 1;
@@ -1410,7 +1442,8 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                     const int64_t len = e0 - carry_start, seg0 = A.vp[(int64_t)sp * A.npad + lr];
                     for (int64_t k = len; k < seg_padded(len); ++k) {
                         const int64_t pp = stream_phys(seg0 + k);
-                        sval[pp] = 0.0;
+                        if (A.cnt_stream) ((uint32_t *)sval)[pp] = 0u;
+                        else sval[pp] = 0.0;
                         if (SLAB) ((uint16_t *)scol_v)[pp] = 0;
                         else ((uint32_t *)scol_v)[pp] = 0;
                     }
@@ -1426,7 +1459,8 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 const int64_t seg_start = upto ? e0 + (31 - __clz(upto)) : carry_start;
                 const int64_t dst = A.vp[(int64_t)s * A.npad + lr] + (e - seg_start);
                 const int64_t ph = stream_phys(dst);
-                sval[ph] = A.cnt32 ? site_scaled(cnt_e, s_row, site_e) : A.data[e];
+                if (A.cnt_stream) ((uint32_t *)sval)[ph] = cnt_e;
+                else sval[ph] = A.cnt32 ? site_scaled(cnt_e, s_row, site_e) : A.data[e];
                 const unsigned lc = (unsigned)(col - s * W);
                 if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
                 else ((uint32_t *)scol_v)[ph] = lc;
@@ -1437,7 +1471,8 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                     const int64_t len = e - seg_start + 1, seg0 = dst - (e - seg_start);
                     for (int64_t k = len; k < seg_padded(len); ++k) {
                         const int64_t pp = stream_phys(seg0 + k);
-                        sval[pp] = 0.0;
+                        if (A.cnt_stream) ((uint32_t *)sval)[pp] = 0u;
+                        else sval[pp] = 0.0;
                         if (SLAB) ((uint16_t *)scol_v)[pp] = 0;
                         else ((uint32_t *)scol_v)[pp] = 0;
                     }
@@ -1510,7 +1545,8 @@ __global__ void __launch_bounds__(256) k_slab_finish(KRArgs A, double *__restric
     if (threadIdx.x == 0) slab_t0[s] = (int32_t)(begin / SPMV_CHUNK);
     const int64_t z0 = end - begin >= SPMV_TILE ? end - SPMV_TILE : begin;
     for (int64_t i = z0 + threadIdx.x; i < end; i += 256) {
-        sval[i] = 0.0;
+        if (A.cnt_stream) ((uint32_t *)sval)[i] = 0u;
+        else sval[i] = 0.0;
         if (SLAB) ((uint16_t *)scol_v)[i] = 0;
         else ((uint32_t *)scol_v)[i] = 0;
     }
@@ -1627,7 +1663,7 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_spmv(KRArgs A) {
         if (threadIdx.x == 0) mbar_init(sm.mbar, 1);
         __syncthreads();
     }
-    phase_spmv<SLAB>(A, A.u, sm);
+    phase_spmv<SLAB, false>(A, A.u, sm);
 }
 // y[r] = (A u)[r] (b3c_spmv): one CTA per reduction chunk
 __global__ void __launch_bounds__(KR_THREADS) k_spmv_collect(KRArgs A, double *__restrict__ y) {
@@ -1722,6 +1758,8 @@ static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
 // KR_OPT_LL_PARTIALS stays off: measured slower than the barrier it replaces (profiles/r1_kr_phases.md)
 // KR_OPT_BANK_ORDER stays off too: the reordering pass costs 91 us at C2 and saves 0.5 us per SpMV, so it would
 // only pay for solves of more than ~180 SpMV (typical: 24-40)
+// B3C_OPT_KR_COUNT_STREAM: the counts form streams uint32 counts (6 B per entry) instead of fp64 values (10 B)
+static std::atomic<int> g_cnt_stream{1};
 static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER | KR_OPT_PEER_LL_W};
 constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
 
@@ -1729,7 +1767,7 @@ struct KRLayout {
     int32_t slab, S, W, n_chunks;
     int64_t nvec;                       // elements per (padded) vector
     int64_t nv_max, nnzv_max, nseg_max;
-    int64_t o_dfix, o_vec, o_qs, o_part, o_ll, o_ctl, o_timers, o_bar, o_bnd, o_cta;
+    int64_t o_dfix, o_inv_s, o_vec, o_qs, o_part, o_ll, o_ctl, o_timers, o_bar, o_bnd, o_cta;
     int64_t o_cnt, o_vp, o_ord, o_scan, o_slab_t0, o_sval, o_scol, o_sflag, o_seg0, o_seg_of, o_seg_row, total;
 };
 
@@ -1754,7 +1792,8 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     L.n_chunks = (int32_t)ceil_div(n, CHUNK);
     L.nvec = align_up(n, 32);
     L.o_dfix = c.take((int64_t)n * 8);
-    L.o_vec = c.take(L.nvec * 8 * 9);
+    L.o_inv_s = c.take(L.nvec * 8);
+    L.o_vec = c.take(L.nvec * 8 * 11);
     L.o_qs = c.take(L.nseg_max * 8);
     L.o_part = c.take((int64_t)L.n_chunks * 8 * P_COUNT);
     L.o_ll = c.take((int64_t)L.n_chunks * 16 * P_COUNT + 128);       // + the arrival counter of the hand-overs
@@ -1828,6 +1867,10 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.Z = vec + L.nvec * 6;
     A.w = vec + L.nvec * 7;
     A.u = vec + L.nvec * 8;
+    A.us = vec + L.nvec * 9;
+    A.xs = vec + L.nvec * 10;
+    A.inv_s = (const double *)(ws + L.o_inv_s);
+    A.cnt_stream = 0;
     A.part = (double *)(ws + L.o_part);
     A.ll = (unsigned long long *)(ws + L.o_ll);
     A.n_chunks = L.n_chunks;
@@ -1845,6 +1888,7 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     for (int g = 0; g < KR_MAX_RANKS; ++g) {
         A.xx[g] = nullptr;
         A.xz[g] = nullptr;
+        A.xxs[g] = nullptr;
         A.xpart[g] = nullptr;
         A.xll[g] = nullptr;
         A.xflag[g] = nullptr;
@@ -1861,20 +1905,20 @@ template <bool SLAB>
 static int persistent_grid_of(int *grid_out) {
     static int cached = 0;
     if (!cached) {
-        int per_sm = 0, dev = 0, sms = 0;
+        int per_sm = 0, per_sm_c = 0, dev = 0, sms = 0;
         const int smem = SLAB ? SM_BYTES_SLAB : SM_BYTES_GATHER;
         B3C_CUDA(cudaGetDevice(&dev));
         B3C_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<SLAB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<SLAB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         B3C_CUDA(cudaFuncSetAttribute(k_spmv<SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kr_persistent<SLAB>, KR_THREADS, smem));
-        if (per_sm < 1) {
+        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kr_persistent<SLAB, false>, KR_THREADS, smem));
+        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_kr_persistent<SLAB, true>, KR_THREADS, smem));
+        if (per_sm < 1 || per_sm_c < 1) {
             set_error("persistent KR kernel does not fit on an SM");
             return B3C_ERR_CUDA;
         }
-        const int want = 1;
-        if (per_sm > want) per_sm = want;
-        cached = sms * per_sm;
+        cached = sms;                                  // one CTA per SM
         if (cached > BND_MAX) cached = BND_MAX;
     }
     *grid_out = cached;
@@ -1882,6 +1926,15 @@ static int persistent_grid_of(int *grid_out) {
 }
 static int persistent_grid(bool slab, int *grid_out) {
     return slab ? persistent_grid_of<true>(grid_out) : persistent_grid_of<false>(grid_out);
+}
+
+// inv_s[j] = 1 / s_j with zero site counts taken as one (contact_map.py:1103-1108, Q6)
+__global__ void __launch_bounds__(256) k_inv_sites(int32_t n, const int32_t *__restrict__ sites, double *__restrict__ inv_s) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int32_t sj = sites[i];
+        inv_s[i] = __ddiv_rn(1.0, sj == 0 ? 1.0 : (double)sj);
+    }
 }
 
 // Build the stream, its segment numbering and the zero-diagonal vector.  Needs the control block already
@@ -1895,6 +1948,10 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     uint16_t *sflag = const_cast<uint16_t *>(A.sflag);
     B3C_CUDA(cudaMemsetAsync(A.cnt, 0, (size_t)(A.nv + 1) * 8, s));
     B3C_CUDA(cudaMemsetAsync(sflag, 0, (size_t)(L.nnzv_max / 8 + 64), s));
+    if (A.cnt_stream) {
+        k_inv_sites<<<(unsigned)ceil_div(A.n, 256), 256, 0, s>>>(A.n, A.sites, const_cast<double *>(A.inv_s));
+        B3C_LAUNCH_CHECK();
+    }
     k_stream_rows<false, SLAB><<<row_warp_grid(n_local), 256, 0, s>>>(A, A.cnt, nullptr, nullptr, nullptr);
     B3C_LAUNCH_CHECK();
     k_slab_pad<<<(unsigned)A.S, 1024, 0, s>>>(A, A.cnt);
@@ -1928,7 +1985,7 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     A.n_seg = (int32_t)totals[1];
     k_stream_rows<true, SLAB><<<row_warp_grid(n_local), 256, 0, s>>>(A, nullptr, sval, scol, sflag);
     B3C_LAUNCH_CHECK();
-    if (SLAB && (A.opts & KR_OPT_BANK_ORDER) && A.n_sch > 0) {
+    if (SLAB && !A.cnt_stream && (A.opts & KR_OPT_BANK_ORDER) && A.n_sch > 0) {
         k_stream_bank_order<<<(unsigned)ceil_div(A.n_sch * 32, 256), 256, 0, s>>>(A.n_sch * 32, sval, (uint16_t *)scol, sflag);
         B3C_LAUNCH_CHECK();
     }
@@ -1990,6 +2047,10 @@ int b3c_set_option(int32_t key, int64_t value) {
             B3C_REQUIRE(value >= 0 && value <= 31, "KR option flags must be in [0, 31]");
             g_kr_opts.store((int)value);
             return B3C_OK;
+        case B3C_OPT_KR_COUNT_STREAM:
+            B3C_REQUIRE(value == 0 || value == 1, "count stream option is 0 or 1");
+            g_cnt_stream.store((int)value);
+            return B3C_OK;
         case B3C_OPT_PEER_TIMEOUT_MS:
             B3C_REQUIRE(value >= 1 && value <= 3600000, "peer time-out must be between 1 ms and one hour");
             g_peer_timeout_cycles.store((long long)value * 2000000LL);        // SM cycles at ~2 GHz
@@ -2018,12 +2079,10 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     B3C_CUDA(cudaMemsetAsync(A.bar_count, 0, 256, s));
     B3C_CUDA(cudaMemsetAsync(A.ll, 0, (size_t)A.n_chunks * 16 * P_COUNT + 128, s));      // epoch 0 = never written
     B3C_CUDA(cudaEventRecord(ev[0], s));
-    if (A.slab)
-        B3C_CUDA(cudaLaunchCooperativeKernel((void *)k_kr_persistent<true>, dim3(grid), dim3(KR_THREADS), args,
-                                             SM_BYTES_SLAB, s));
-    else
-        B3C_CUDA(cudaLaunchCooperativeKernel((void *)k_kr_persistent<false>, dim3(grid), dim3(KR_THREADS), args,
-                                             SM_BYTES_GATHER, s));
+    void *kern = A.slab ? (A.cnt_stream ? (void *)k_kr_persistent<true, true> : (void *)k_kr_persistent<true, false>)
+                        : (A.cnt_stream ? (void *)k_kr_persistent<false, true> : (void *)k_kr_persistent<false, false>);
+    B3C_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(KR_THREADS), args,
+                                         A.slab ? SM_BYTES_SLAB : SM_BYTES_GATHER, s));
     B3C_CUDA(cudaEventRecord(ev[1], s));
     count_launch();
     KRScalars S;
@@ -2094,6 +2153,7 @@ static int kr_run_impl(int32_t n, int64_t nnz, const int64_t *d_indptr, const in
     kr_bind(A, L, (char *)d_ws, n, 0, n, nnz, d_indptr, d_indices, d_data);
     A.cnt32 = d_data ? nullptr : d_counts;
     A.sites = d_data ? nullptr : d_sites;
+    A.cnt_stream = (A.cnt32 != nullptr && g_cnt_stream.load()) ? 1 : 0;
     KRScalars S;
     kr_scalars_init(S, tol, delta, Delta, max_iter);
     B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
@@ -2124,7 +2184,7 @@ int b3c_kr_run_counts(int32_t n, int64_t nnz, const int64_t *d_indptr, const int
 // exchange buffer of a rank: [flags: KR_MAX_RANKS x u64][epoch u64][x: nvec x f64][Z: nvec x f64][partials]
 // [flagged partial words + their arrival counter]
 struct XLayout {
-    int64_t o_flag, o_epoch, o_x, o_z, o_part, o_ll, total;
+    int64_t o_flag, o_epoch, o_x, o_xs, o_z, o_part, o_ll, total;
 };
 static XLayout x_layout(int32_t n) {
     XLayout X;
@@ -2132,6 +2192,7 @@ static XLayout x_layout(int32_t n) {
     X.o_flag = c.take(KR_MAX_RANKS * 8);
     X.o_epoch = c.take(8);
     X.o_x = c.take(align_up(n, 32) * 8);
+    X.o_xs = c.take(align_up(n, 32) * 8);
     X.o_z = c.take(align_up(n, 32) * 8);
     X.o_part = c.take(ceil_div(n, CHUNK) * 8 * P_COUNT);
     X.o_ll = c.take(ceil_div(n, CHUNK) * 16 * P_COUNT + 128);
@@ -2192,6 +2253,7 @@ static int kr_run_peer_impl(int32_t n, int32_t row_lo, int32_t row_hi, int64_t n
     kr_bind(A, L, (char *)d_ws, n, row_lo, row_hi, nnz_local, d_indptr, d_indices, d_data);
     A.cnt32 = d_data ? nullptr : d_counts;
     A.sites = d_data ? nullptr : d_sites;
+    A.cnt_stream = (A.cnt32 != nullptr && g_cnt_stream.load()) ? 1 : 0;
     const XLayout X = x_layout(n);
     for (int g = 0; g < n_ranks; ++g) {
         B3C_REQUIRE(h_exchange[g] != nullptr, "null exchange buffer of rank %d", g);
@@ -2199,6 +2261,7 @@ static int kr_run_peer_impl(int32_t n, int32_t row_lo, int32_t row_hi, int64_t n
         A.xflag[g] = (unsigned long long *)(b + X.o_flag);
         A.xx[g] = (double *)(b + X.o_x);
         A.xz[g] = (double *)(b + X.o_z);
+        A.xxs[g] = (double *)(b + X.o_xs);
         A.xpart[g] = (double *)(b + X.o_part);
         A.xll[g] = (unsigned long long *)(b + X.o_ll);
     }
@@ -2207,6 +2270,7 @@ static int kr_run_peer_impl(int32_t n, int32_t row_lo, int32_t row_hi, int64_t n
     A.epoch = (unsigned long long *)((char *)h_exchange[rank] + X.o_epoch);
     // x, Z, the partials and their flagged words live in the exchange buffer: every rank's slice is written by its owner
     A.x = A.xx[rank];
+    A.xs = A.xxs[rank];
     A.Z = A.xz[rank];
     A.part = A.xpart[rank];
     A.ll = A.xll[rank];
