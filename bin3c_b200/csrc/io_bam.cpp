@@ -433,23 +433,61 @@ int next_alignment(b3c_bam *h, Aln *a) {
     if (32 + (size_t)l_name + 4 * (size_t)n_cig > bs) return fail_format(h, "alignment record overruns its block size");
     a->name = (const char *)p + 32;
     a->name_len = l_name ? strnlen(a->name, l_name) : 0;
+    // the CIGAR: in the record, or -- beyond 65535 operations -- in the CG:B,I tag behind the placeholder
+    // <l_seq>S<ref span>N (SAM specification, section 4.2.2); htslib / pysam hand the tag's operations to the caller
+    const uint8_t *cg = p + 32 + l_name;
+    uint32_t n_ops = n_cig;
+    const uint32_t l_seq = rd32(p + 16);
+    if (n_cig == 2 && (rd32(cg) & 0xf) == 4 && (rd32(cg) >> 4) == l_seq && (rd32(cg + 4) & 0xf) == 3) {
+        const uint8_t *aux = cg + 8 + ((size_t)l_seq + 1) / 2 + l_seq, *end = p + bs;
+        while (aux + 3 <= end) {
+            const uint8_t t = aux[2];
+            const uint8_t *v = aux + 3;
+            size_t len = 0;
+            auto size_of = [](uint8_t c) -> size_t {
+                return (c == 'A' || c == 'c' || c == 'C') ? 1 : (c == 's' || c == 'S') ? 2 : (c == 'i' || c == 'I' || c == 'f') ? 4 : 0;
+            };
+            if (t == 'Z' || t == 'H') {
+                const void *z = memchr(v, 0, (size_t)(end - v));
+                if (!z) return fail_format(h, "unterminated string tag");
+                len = (size_t)((const uint8_t *)z - v) + 1;
+            } else if (t == 'B') {
+                if (v + 5 > end) return fail_format(h, "truncated array tag");
+                const size_t es = size_of(v[0]), cnt = rd32(v + 1);
+                if (es == 0 || v + 5 + es * cnt > end) return fail_format(h, "malformed array tag");
+                if (aux[0] == 'C' && aux[1] == 'G' && v[0] == 'I' && cnt > 0) {
+                    cg = v + 5;
+                    n_ops = (uint32_t)cnt;
+                    break;
+                }
+                len = 5 + es * cnt;
+            } else {
+                len = size_of(t);
+                if (len == 0) return fail_format(h, "unknown tag type");
+            }
+            aux = v + len;
+        }
+    }
     // _simple_match / _strong_match (contact_map.py:612-619)
     bool m = (int32_t)mapq >= h->min_mapq;
     if (m && h->strong > 0) {
-        if (n_cig == 0) {
+        if (n_ops == 0) {
             m = false;                                               // r.cigarstring is None
         } else {
-            const uint8_t *cg = p + 32 + l_name;
-            const uint32_t op = rd32(cg + 4 * ((a->flag & 0x10) ? (n_cig - 1) : 0));
+            const uint32_t op = rd32(cg + 4 * ((a->flag & 0x10) ? (n_ops - 1) : 0));
             m = (op & 0xf) == 0 && (int32_t)(op >> 4) >= h->strong;
         }
     }
     a->match = m;
     a->pos5 = a->pos;
     if (h->extent && (a->flag & 0x10)) {
-        // r.alen = pysam reference_length: the CIGAR operations that consume the reference (M, D, N, =, X)
-        const uint8_t *cg = p + 32 + l_name;
+        // r.alen = pysam reference_length: the CIGAR operations that consume the reference (M, D, N, =, X).  A mapped
+        // reverse read without a CIGAR has alen None in the reference, whose `r.pos + r.alen` then raises: an error
+        // here too, not a silent span of zero.
+        if (n_ops == 0 && !(a->flag & 0x4))
+            return fail_format(h, "mapped reverse read without a CIGAR: its 5' end is undefined (extent records)");
         int64_t span = 0;
+        const uint32_t n_cig = n_ops;
         for (uint32_t k = 0; k < n_cig; ++k) {
             const uint32_t op = rd32(cg + 4 * k), t = op & 0xf;
             if (t == 0 || t == 2 || t == 3 || t == 7 || t == 8) span += op >> 4;

@@ -139,9 +139,11 @@ class HotPath(object):
     def run(self, records, to_host=False, fused=True, record_bytes=8, n_records=None):
         """
         The whole path.  fused=True (default) never materialises the normalised and the balanced matrix:
-        their entries are recomputed where they are consumed, with the same operations in the same
-        order, so the edge list is bit-identical to the staged form (fused=False: site_norm -> KR ->
-        kr_apply -> compress, the stages ContactMap exposes).  Returns the edge result dict (CUDA tensors, or NumPy arrays if to_host).
+        KR iterates on the raw counts (6 B per stream entry, the site normalisation factored out of the row
+        sums) and the edge weights are recomputed where they are consumed with the reference's operations in
+        the reference's order.  The staged form (fused=False: site_norm -> KR -> kr_apply -> compress, the
+        stages ContactMap exposes) gives the same n_iter and edge structure, x and w equal to rounding (~1e-15).
+        Returns the edge result dict (CUDA tensors, or NumPy arrays if to_host).
         Both are views of the pipeline's reusable buffers (device buffers, or pinned host buffers
         with to_host): they are overwritten by the next run(), so copy what must outlive it.
         """

@@ -125,9 +125,13 @@ def test_c2_full_size_against_the_oracle(dev):
         r2 = hp.run(rec, fused=fused)
         n = int(r2['n_edges'])
         assert n == len(out['u'])
-        for k in ('u', 'v', 'w'):
+        for k in ('u', 'v'):
             assert np.array_equal(r2[k][:n].cpu().numpy(), out[k])
-        assert np.array_equal(hp.x.cpu().numpy(), x)
+        if fused:           # the same form again: the same bits
+            assert np.array_equal(r2['w'][:n].cpu().numpy(), out['w']) and np.array_equal(hp.x.cpu().numpy(), x)
+        else:               # the staged form iterates on fp64 values, the fused one on counts: equal to rounding
+            assert _relerr(r2['w'][:n].cpu().numpy(), out['w']) <= 1e-12 and _relerr(hp.x.cpu().numpy(), x) <= 1e-12
+            assert hp.kr_info['n_iter'] == ref['n_iter']
         if not fused:
             wk = hp.normed.to_scipy_csr()
             work = wk + sp.diags((wk.diagonal() == 0).astype(float))

@@ -382,6 +382,8 @@ def test_bam_extent_records_match_oracle(tmp_path, bin_size, block_bytes):
     lengths = [rng.choice([300, 800, 1500, 2499, 2500, 7000, 20000]) for _ in range(n_refs)]
     alns = random_alignments(rng, n_refs, 2500)
     for a in alns:                                             # richer CIGARs and positions up to the contig end
+        if not a['cigar'] and a['flag'] & 0x10 and not a['flag'] & 0x4:
+            a['cigar'] = [(0, 50)]          # a mapped reverse read without a CIGAR has no 5' end (separate test)
         if a['cigar'] and rng.random() < 0.5:
             a['cigar'] = a['cigar'] + [(2, rng.randrange(1, 9)), (0, rng.randrange(1, 50)), (1, 3), (3, 100)]
         if 0 <= a['tid'] < n_refs:
@@ -513,3 +515,50 @@ def test_pair_loop_against_the_reference_bin_map(tmp_path, via):
             assert m.shape[0] == int(g['p%d_%s_n' % (k, nm)])
             assert np.array_equal(m.row, g['p%d_%s_row' % (k, nm)]) and np.array_equal(m.col, g['p%d_%s_col' % (k, nm)])
             assert np.array_equal(m.data, g['p%d_%s_data' % (k, nm)])
+
+
+def test_bam_long_cigar_in_cg_tag_and_reverse_read_without_cigar(tmp_path):
+    """CIGARs of more than 65535 operations live in the CG:B,I tag behind the placeholder <l_seq>S<span>N (SAM
+    specification 4.2.2; htslib hands the tag's operations to the caller): the strong matcher and the reference span of
+    a reverse read must come from the tag.  A mapped reverse read WITHOUT any CIGAR has `alen` None in the reference,
+    whose `r.pos + r.alen` raises: the reader reports a format error instead of a silent span of zero."""
+    import struct
+    from bin3c_b200.contact_map import ExtentGrouping
+    refs, lengths = ['a', 'b'], [50000, 40000]
+    real = [(0, 30), (2, 5), (0, 20), (1, 2), (3, 1000), (0, 40)]                  # spans 30+5+20+1000+40 = 1095
+    l_seq = sum(n for op, n in real if op in (0, 1, 4, 7, 8))
+    tag = b'CGBI' + struct.pack('<I', len(real)) + b''.join(struct.pack('<I', (n << 4) | op) for op, n in real)
+    other = b'NMC\x03' + b'XZZabc\0'                                             # tags in front of CG are skipped
+    alns = [dict(name='p0', flag=0x41 | 0x10, tid=0, pos=1000, mapq=60, cigar=[(4, l_seq), (3, 1095)], seq_len=l_seq,
+                 tags=other + tag),
+            dict(name='p0', flag=0x81, tid=1, pos=700, mapq=60, cigar=[(0, 100)])]
+    path = str(tmp_path / 'cg.bam')
+    bam_writer.write_bam(path, refs, lengths, alns)
+    lut = np.array([0, 1], dtype=np.int32)
+    g = ExtentGrouping.from_lengths(lengths, 500)
+    with bam_io.BamPairReader(path) as bam:
+        bam.set_extent(lut, g)
+        bam.set_filter(min_mapq=30, strong=35)                 # the tag's last operation is 40M: a strong match
+        rec, ext = bam.read_pairs_extent(10)
+    assert len(rec) == 1 and (int(rec[0]) >> 31) & 1 == 1
+    og = oracle.extent_grouping(lengths, 500)
+    b1 = oracle.find_nearest(og['map'][0], 1000 + 1095)        # the reverse read's 5' end: pos + span of the REAL CIGAR
+    b2 = oracle.find_nearest(og['map'][1], 700)
+    assert int(ext[0]) & 0x7fffffff == b1 and (int(ext[0]) >> 32) & 0x7fffffff == b2
+    with bam_io.BamPairReader(path) as bam:                    # with the placeholder (1 op of 'S') it would not match
+        bam.set_filter(min_mapq=30, strong=41)
+        assert (int(bam.read_pairs(10)[0]) >> 31) & 1 == 0
+    # mapped reverse read without a CIGAR: an error when 5' ends are needed, as in the reference
+    bad = [dict(name='q', flag=0x41 | 0x10, tid=0, pos=10, mapq=60, cigar=[]),
+           dict(name='q', flag=0x81, tid=1, pos=20, mapq=60, cigar=[(0, 50)])]
+    path2 = str(tmp_path / 'nocigar.bam')
+    bam_writer.write_bam(path2, refs, lengths, bad)
+    with bam_io.BamPairReader(path2) as bam:
+        bam.set_extent(lut, g)
+        with pytest.raises(ValueError) as ei:
+            bam.read_pairs_extent(10)
+        assert 'without a CIGAR' in str(ei.value)
+    with bam_io.BamPairReader(path2) as bam:                   # the contig map alone does not need the 5' end
+        assert len(bam.read_pairs(10)) == 1
+    with pytest.raises(TypeError):
+        oracle.pair_alignments(bad, 2, idx_of=lut, grouping=og)
