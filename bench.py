@@ -597,6 +597,9 @@ def main_multi(args, rank, local_rank, world):
     names = ('accumulate', 'mask', 'kr', 'edges')
     acc_t = torch.zeros(len(names), dtype=torch.float64, device='cuda')
     n_st = max(2, min(args.steps, 5))
+    sub_acc = {}
+    if hasattr(hp.engine, 'substep_ms'):
+        hp.engine.events = []
     for _ in range(n_st):
         marks = []
         for fn in (lambda: hp.accumulate(rec_dev), hp.compute_mask, hp.balance, hp.edges):
@@ -608,6 +611,15 @@ def main_multi(args, rank, local_rank, world):
             marks.append((a, b))
         torch.cuda.synchronize()
         acc_t += torch.tensor([a.elapsed_time(b) for a, b in marks], dtype=torch.float64, device='cuda')
+        if hasattr(hp.engine, 'substep_ms'):
+            for k, v in hp.engine.substep_ms().items():
+                sub_acc[k] = sub_acc.get(k, 0.0) + v / n_st
+    if hasattr(hp.engine, 'substep_ms'):
+        hp.engine.events = None
+    sub_names = ('classify', 'publish', 'barrier1', 'route', 'barrier2', 'sort_reduce', 'emit')
+    sub_t = torch.tensor([sub_acc.get(k, 0.0) for k in sub_names], dtype=torch.float64, device='cuda')
+    sub_max = sub_t.clone()
+    comm.all_reduce(sub_max, 'max')
     acc_t /= n_st
     st_max, st_sum = acc_t.clone(), acc_t.clone()
     comm.all_reduce(st_max, 'max')
@@ -740,6 +752,8 @@ def main_multi(args, rank, local_rank, world):
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
         'stages_ms_synced': {'max_over_ranks': {k: round(float(v), 4) for k, v in zip(names, st_max.cpu())},
                              'mean_over_ranks': {k: round(float(v) / world, 4) for k, v in zip(names, st_sum.cpu())},
+                             'accumulate_substeps_rank0': {k: round(float(v), 4) for k, v in zip(sub_names, sub_t.cpu())},
+                             'accumulate_substeps_max': {k: round(float(v), 4) for k, v in zip(sub_names, sub_max.cpu())},
                              'note': 'a device-side barrier over all ranks precedes every stage (not part of the timed '
                                      'steps above)'},
         'kr': {'n_iter': kr['n_iter'], 'n_spmv': kr['n_spmv'], 'outer': kr['outer'], 'zero_diag': kr['zero_diag'],

@@ -240,16 +240,24 @@ class CudaEngine(object):
         """
         dev, lib = self.dev, self.lib
         ptrs = self.open_arena(comm)
+        mark = self._mark
+        mark('start')
         self.acc.begin()
         self.add_records(records, record_bytes, n_records)
+        mark('classify')
         ws = dev._ptr(self.acc.ws)
         self.check(lib.b3c_shard_publish(ws, ptrs, comm.rank, comm.world, dev._stream()))
+        mark('publish')
         self.peer_barrier(comm)
+        mark('barrier1')
         self.check(lib.b3c_shard_scatter(ws, ptrs, comm.rank, comm.world, dev._ptr(self._splits_dev), dev._stream()))
+        mark('route')
         self.peer_barrier(comm)
+        mark('barrier2')
         sizes = (C.c_int64 * 24)()
         self.check(lib.b3c_shard_reduce_block(ws, ptrs, comm.rank, comm.world, dev._ptr(self._splits_dev), sizes,
                                               dev._stream()))
+        mark('sort_reduce')
         nnz, row_lo, row_hi = int(sizes[0]), int(sizes[1]), int(sizes[2])
         info = dict(accepted=int(sizes[3]), ref_excluded=int(sizes[4]), poor_match=int(sizes[5]),
                     keys_received=int(sizes[6]), splits=[int(sizes[8 + g]) for g in range(comm.world + 1)])
@@ -262,7 +270,26 @@ class CudaEngine(object):
             self.check(lib.b3c_accum_emit_block(ws, row_lo, row_hi, dev._ptr(indptr), dev._ptr(indices),
                                                 dev._ptr(counts), dev._stream()))
             block = dev.DeviceCSR(nl, indptr, indices, counts, counts=True, row_lo=row_lo, n_total=self.n)
+        mark('emit')
         return block, info
+
+    # sub-step CUDA events of the sharded accumulation (bench.py's stage table; off unless `events` is a list)
+    events = None
+
+    def _mark(self, name):
+        if self.events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.events.append((name, ev))
+
+    def substep_ms(self):
+        """{sub-step: ms} from the recorded events (call after a synchronize); clears them."""
+        out = {}
+        evs, self.events = self.events or [], []
+        for (na, a), (nb, b) in zip(evs[:-1], evs[1:]):
+            if nb != 'start':
+                out[nb] = out.get(nb, 0.0) + a.elapsed_time(b)
+        return out
 
     # ---- accumulation ------------------------------------------------------------------------
     def classify(self, records, record_bytes=8, n_records=None):
