@@ -700,7 +700,7 @@ def test_hotpath_host_records_match_device_records(dev):
     com = synth.make_community(n_genomes=12, n_contigs=3000, n_pairs=700_001, seed=99)
     hp = HotPath(com.tid2idx(), com.lengths, com.sites, pair_capacity=com.n_pairs)
     rec = torch.from_numpy(com.records.view(np.int64))
-    r0 = hp.run(rec.to('cuda'))
+    r0 = hp.run(rec.to('cuda'), fused=False)             # the staged form, as driven stage by stage below
     n = int(r0['n_edges'])
     want = [r0[k][:n].cpu().numpy().copy() for k in ('u', 'v', 'w')] + [float(r0['scl'].cpu()[0])]
     for host, chunk in ((rec.pin_memory(), 100_000), (rec, 1 << 24), (rec.pin_memory(), 233_334)):
@@ -712,7 +712,9 @@ def test_hotpath_host_records_match_device_records(dev):
         assert int(got['n_edges']) == n
         for k, w in zip(('u', 'v', 'w'), want):
             assert np.array_equal(got[k][:n].cpu().numpy(), w)
-    out = hp.run(rec.pin_memory(), to_host=True)
+    r1 = hp.run(rec.to('cuda'))                          # the fused form, device records ...
+    want = [r1[k][:n].cpu().numpy().copy() for k in ('u', 'v', 'w')] + [float(r1['scl'].cpu()[0])]
+    out = hp.run(rec.pin_memory(), to_host=True)         # ... and host records in, host edges out
     assert out['n_edges'] == n and hp.d2h_bytes == 16 * n + 8
     for k, w in zip(('u', 'v', 'w'), want):
         assert np.array_equal(out[k], w)
