@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle leg (and with it the parity check)')
     ap.add_argument('--e2e-record-bytes', default='auto', help="auto: the narrowest record the reference table allows (5, 6 or 8 bytes); 8: native records")
     ap.add_argument('--no-microbench', action='store_true', help='skip the C5 KR SpMV microbench points')
+    ap.add_argument('--microbench', default='default', choices=['default', 'full'], help='full: also the 3M-row C5 point')
     ap.add_argument('--no-c2', action='store_true', help='N=1: skip the secondary C2 measurement')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--parity', default='sample', choices=['sample', 'full', 'none'],
@@ -535,8 +536,16 @@ def main_single(args, local_rank):
         line['c2'] = c2
         torch.cuda.empty_cache()
     if not args.no_microbench and args.scale == 1.0:
+        # BASELINE config 5 points (fp64 CSR in, b3c_spmv): 250k rows keep the slab form (shared-memory gathers);
+        # 1M and 3M rows are wider than 16 column slabs with sparse (row, slab) cells and take the gather form
         peak, _ = measured_peak()
-        line['kr_spmv_microbench'] = [spmv_point(dev, torch, peak, 250_000, 100_000_000)]
+        pts = [(250_000, 100_000_000, True), (1_000_000, 100_000_000, False), (1_000_000, 300_000_000, False)]
+        if args.microbench == 'full':
+            pts.append((3_000_000, 300_000_000, False))
+        line['kr_spmv_microbench'] = []
+        for rows, nnz, compare in pts:
+            line['kr_spmv_microbench'].append(spmv_point(dev, torch, peak, rows, nnz, compare=compare))
+            torch.cuda.empty_cache()
     print(json.dumps(line))
 
 
