@@ -793,13 +793,19 @@ def main():
     __graft_entry__.build()
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local_rank)
+    from bin3c_b200 import device as dev
+    # everything runs on one capturable (non-default) stream: the sort-reduce sequences replay as CUDA graphs, and
+    # the timing events sit on the stream the kernels are launched on
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-        main_multi(args, rank, local_rank, world)
+        with dev.pipeline_stream():
+            main_multi(args, rank, local_rank, world)
+        torch.cuda.synchronize()
         dist.destroy_process_group()
         return
-    main_single(args, local_rank)
+    with dev.pipeline_stream():
+        main_single(args, local_rank)
 
 
 if __name__ == '__main__':

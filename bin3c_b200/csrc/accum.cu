@@ -526,14 +526,22 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
 // the lighter 256-bin kernels run.
 static int radix_passes(int bits) { return bits <= 0 ? 0 : (bits + RS_BITS - 1) / RS_BITS; }
 
-static int radix_sort(uint64_t *a, uint64_t *b, const unsigned long long *d_n, int bit_lo, int bit_hi,
-                      uint32_t *d_hist, cudaStream_t s, int *where) {
+// which buffer (0 = a, 1 = b) holds the result of radix_sort over these bits: the parity of the pass count
+static int radix_where(int bit_lo, int bit_hi) { return radix_passes(bit_hi - bit_lo) & 1; }
+
+// once per process, outside any graph capture
+static int radix_init() {
     static bool attr_done = false;
     if (!attr_done) {
         B3C_CUDA(cudaFuncSetAttribute(k_rs_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 8));
         B3C_CUDA(cudaFuncSetAttribute(k_rs_scatter<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 8));
         attr_done = true;
     }
+    return B3C_OK;
+}
+
+static int radix_sort(uint64_t *a, uint64_t *b, const unsigned long long *d_n, int bit_lo, int bit_hi,
+                      uint32_t *d_hist, cudaStream_t s, int *where) {
     const int bits = bit_hi - bit_lo, passes = radix_passes(bits);
     const bool wide = passes > 0 && passes * 8 < bits;           // 8-bit digits would need another pass
     const int digit = passes > 0 ? (bits + passes - 1) / passes : 0;
@@ -1197,6 +1205,7 @@ int b3c_accum_begin(void *d_ws, int64_t ws_bytes, int64_t pair_capacity, int32_t
         return B3C_ERR_CAPACITY;
     }
     st.d_lut = d_tid2idx;
+    graph_forget(d_ws);                                  // a re-planned workspace invalidates its captured sequences
     cudaStream_t s = (cudaStream_t)stream;
     char *ws = (char *)d_ws;
     B3C_CUDA(cudaMemsetAsync(ws + st.o_ctr, 0, C_COUNT * 8, s));
@@ -1308,43 +1317,48 @@ int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream) {
     int64_t *up = (int64_t *)(ws + st.o_up_ptr), *lo = (int64_t *)(ws + st.o_lo_ptr), *len = (int64_t *)(ws + st.o_len);
     int64_t *ip_f = (int64_t *)(ws + st.o_indptr_f), *ip_u = (int64_t *)(ws + st.o_indptr_u);
 
-    k_accum_guard<<<1, 1, 0, s>>>(ctr, st.cap);
-    B3C_LAUNCH_CHECK();
-    // 1. sort the off-diagonal keys on their 2b significant bits
-    int where = 0;
-    rc = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
+    rc = radix_init();
     if (rc) return rc;
-    uint64_t *sorted = where ? kb : ka, *other = where ? ka : kb;
-    // 2. run-length reduce -> unique keys + counts, composite (j, e) for the mirror half
-    k_rle_count<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads);
-    B3C_LAUNCH_CHECK();
-    rc = scan_exclusive_i64(heads, heads_ex, RS_BLOCKS, scan_tmp, s);
-    if (rc) return rc;
-    k_rle_write<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads_ex, uniq, pos);
-    B3C_LAUNCH_CHECK();
-    k_rle_finish<<<1, 1, 0, s>>>(heads_ex, RS_BLOCKS, ctr + C_NKEYS, pos, ctr);
-    B3C_LAUNCH_CHECK();
-    k_rle_counts<<<kNumSMs * 8, 256, 0, s>>>(pos, ctr, cnt, st.b, uniq, sorted);   // composite overwrites the sorted keys
-    B3C_LAUNCH_CHECK();
-    k_diag_stats<<<kNumSMs * 2, 256, 0, s>>>(diag, st.n_seq, ctr);
-    B3C_LAUNCH_CHECK();
-    // 3. stable sort of the composite on the column bits only -> (j, i) order
-    int where2 = 0;
-    rc = radix_sort(sorted, other, ctr + C_NNZ_UO, 32, 32 + st.b, hist, s, &where2);
-    if (rc) return rc;
-    uint64_t *comp = where2 ? other : sorted;
+    // where the two sorts leave their results is a function of the key width alone
+    uint64_t *sorted = radix_where(0, 2 * st.b) ? kb : ka, *other = radix_where(0, 2 * st.b) ? ka : kb;
+    uint64_t *comp = radix_where(32, 32 + st.b) ? other : sorted;
     st.comp_in_a = (comp == ka) ? 1 : 0;
-    // 4. row pointers of both halves, row lengths, indptr of both output forms
-    k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(uniq, ctr + C_NNZ_UO, st.b, st.n_seq, up);
-    B3C_LAUNCH_CHECK();
-    k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(comp, ctr + C_NNZ_UO, 32, st.n_seq, lo);
-    B3C_LAUNCH_CHECK();
-    k_row_len<<<kNumSMs * 4, 256, 0, s>>>(up, lo, diag, st.n_seq, len, ip_u /* scratch: upper lengths */);
-    B3C_LAUNCH_CHECK();
-    rc = scan_exclusive_i64(len, ip_f, st.n_seq, scan_tmp, s);
-    if (rc) return rc;
-    B3C_CUDA(cudaMemcpyAsync(len, ip_u, (size_t)st.n_seq * 8, cudaMemcpyDeviceToDevice, s));
-    rc = scan_exclusive_i64(len, ip_u, st.n_seq, scan_tmp, s);
+    // The whole sequence (~60 launches; every size is read from device counters) is one CUDA graph per workspace.
+    rc = graph_run(s, d_ws, /*id*/ 1, nullptr, [&]() -> int {
+        int where = 0, rc2;
+        k_accum_guard<<<1, 1, 0, s>>>(ctr, st.cap);
+        B3C_LAUNCH_CHECK();
+        // 1. sort the off-diagonal keys on their 2b significant bits
+        rc2 = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
+        if (rc2) return rc2;
+        // 2. run-length reduce -> unique keys + counts, composite (j, e) for the mirror half
+        k_rle_count<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads);
+        B3C_LAUNCH_CHECK();
+        rc2 = scan_exclusive_i64(heads, heads_ex, RS_BLOCKS, scan_tmp, s);
+        if (rc2) return rc2;
+        k_rle_write<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads_ex, uniq, pos);
+        B3C_LAUNCH_CHECK();
+        k_rle_finish<<<1, 1, 0, s>>>(heads_ex, RS_BLOCKS, ctr + C_NKEYS, pos, ctr);
+        B3C_LAUNCH_CHECK();
+        k_rle_counts<<<kNumSMs * 8, 256, 0, s>>>(pos, ctr, cnt, st.b, uniq, sorted);   // composite overwrites the sorted keys
+        B3C_LAUNCH_CHECK();
+        k_diag_stats<<<kNumSMs * 2, 256, 0, s>>>(diag, st.n_seq, ctr);
+        B3C_LAUNCH_CHECK();
+        // 3. stable sort of the composite on the column bits only -> (j, i) order
+        rc2 = radix_sort(sorted, other, ctr + C_NNZ_UO, 32, 32 + st.b, hist, s, &where);
+        if (rc2) return rc2;
+        // 4. row pointers of both halves, row lengths, indptr of both output forms
+        k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(uniq, ctr + C_NNZ_UO, st.b, st.n_seq, up);
+        B3C_LAUNCH_CHECK();
+        k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(comp, ctr + C_NNZ_UO, 32, st.n_seq, lo);
+        B3C_LAUNCH_CHECK();
+        k_row_len<<<kNumSMs * 4, 256, 0, s>>>(up, lo, diag, st.n_seq, len, ip_u /* scratch: upper lengths */);
+        B3C_LAUNCH_CHECK();
+        rc2 = scan_exclusive_i64(len, ip_f, st.n_seq, scan_tmp, s);
+        if (rc2) return rc2;
+        B3C_CUDA(cudaMemcpyAsync(len, ip_u, (size_t)st.n_seq * 8, cudaMemcpyDeviceToDevice, s));
+        return scan_exclusive_i64(len, ip_u, st.n_seq, scan_tmp, s);
+    });
     if (rc) return rc;
 
     unsigned long long h[C_COUNT];
@@ -1492,6 +1506,8 @@ int b3c_accum_reduce_block(void *d_ws, const uint64_t *d_keys, int64_t n_keys, i
     const unsigned long long nk = (unsigned long long)n_keys;
     B3C_CUDA(cudaMemcpyAsync(ctr + C_NKEYS, &nk, 8, cudaMemcpyHostToDevice, s));
     B3C_CUDA(cudaMemsetAsync(ctr + C_NNZ_UO, 0, 3 * 8, s));       // nnz_uo, nnz_diag, weight
+    rc = radix_init();
+    if (rc) return rc;
     int where = 0;
     rc = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
     if (rc) return rc;
@@ -1702,24 +1718,31 @@ int b3c_shard_reduce_block(void *d_ws, void *const *h_arena, int32_t rank, int32
     // the splits decide the row block: they are needed on the host to size the launches below
     int32_t h_splits[XA_MAX_RANKS + 1];
     B3C_CUDA(cudaMemcpyAsync(h_splits, d_splits, (size_t)(n_ranks + 1) * 4, cudaMemcpyDeviceToHost, s));
-    k_shard_collect<<<1, 32, 0, s>>>(P, rank, n_ranks, X.o_ctl, X.o_cnt3, st.cap, ctr, d_out);
-    B3C_LAUNCH_CHECK();
-    int where = 0;
-    rc = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
+    rc = radix_init();
     if (rc) return rc;
-    uint64_t *sorted = where ? kb : ka;
-    k_rle_count<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads);
-    B3C_LAUNCH_CHECK();
-    rc = scan_exclusive_i64(heads, heads_ex, RS_BLOCKS, scan_tmp, s);
+    uint64_t *sorted = radix_where(0, 2 * st.b) ? kb : ka;
+    // collect + sort + run-length reduce + row pointers: one CUDA graph per (workspace, arena)
+    rc = graph_run(s, d_ws, /*id*/ 2, P.a[rank], [&]() -> int {
+        int where = 0, rc2;
+        k_shard_collect<<<1, 32, 0, s>>>(P, rank, n_ranks, X.o_ctl, X.o_cnt3, st.cap, ctr, d_out);
+        B3C_LAUNCH_CHECK();
+        rc2 = radix_sort(ka, kb, ctr + C_NKEYS, 0, 2 * st.b, hist, s, &where);
+        if (rc2) return rc2;
+        k_rle_count<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads);
+        B3C_LAUNCH_CHECK();
+        rc2 = scan_exclusive_i64(heads, heads_ex, RS_BLOCKS, scan_tmp, s);
+        if (rc2) return rc2;
+        k_rle_write<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads_ex, uniq, pos);
+        B3C_LAUNCH_CHECK();
+        k_rle_finish<<<1, 1, 0, s>>>(heads_ex, RS_BLOCKS, ctr + C_NKEYS, pos, ctr);
+        B3C_LAUNCH_CHECK();
+        k_rle_counts<<<kNumSMs * 8, 256, 0, s>>>(pos, ctr, cnt, st.b, uniq, sorted);
+        B3C_LAUNCH_CHECK();
+        k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(uniq, ctr + C_NNZ_UO, st.b, st.n_seq, ptr);
+        B3C_LAUNCH_CHECK();
+        return B3C_OK;
+    });
     if (rc) return rc;
-    k_rle_write<<<RS_BLOCKS, RS_THREADS, 0, s>>>(sorted, ctr + C_NKEYS, heads_ex, uniq, pos);
-    B3C_LAUNCH_CHECK();
-    k_rle_finish<<<1, 1, 0, s>>>(heads_ex, RS_BLOCKS, ctr + C_NKEYS, pos, ctr);
-    B3C_LAUNCH_CHECK();
-    k_rle_counts<<<kNumSMs * 8, 256, 0, s>>>(pos, ctr, cnt, st.b, uniq, sorted);
-    B3C_LAUNCH_CHECK();
-    k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(uniq, ctr + C_NNZ_UO, st.b, st.n_seq, ptr);
-    B3C_LAUNCH_CHECK();
     B3C_CUDA(cudaStreamSynchronize(s));                       // h_splits
     const int32_t row_lo = h_splits[rank], row_hi = h_splits[rank + 1];
     const int32_t n_local = row_hi - row_lo;

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <functional>
 #include <mutex>
 #include <unordered_map>
 
@@ -49,6 +50,17 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- CUDA-graph cache ------------------------------------------------------------------------------
+// The sort-reduce of an accumulator is ~60 short launches whose grids and arguments are fixed per workspace (all
+// sizes are read from device counters), so the sequence is captured once per (workspace, sequence id, aux pointer)
+// and replayed with ONE cudaGraphLaunch: the inter-launch gaps (a few microseconds each) are what dominates these
+// sequences at multi-GPU shard sizes.  `enqueue` must only enqueue work on `s` (kernels, device-to-device copies,
+// memsets): no host-pointer copies, no synchronisation, no attribute calls.  b3c_set_option(B3C_OPT_USE_GRAPHS, 0)
+// turns replay off (every call enqueues directly).
+int graph_run(cudaStream_t s, const void *ws, int id, const void *aux, const std::function<int()> &enqueue);
+void graph_forget(const void *ws);            // the workspace was re-planned: drop its graphs
+extern std::atomic<int> g_use_graphs;
 
 // carve a workspace: returns the offset of a block of `bytes` and advances the cursor
 struct Carver {

@@ -1,6 +1,8 @@
 // Library plumbing: error reporting, launch accounting, generic exclusive scan.
 #include <stdarg.h>
 
+#include <map>
+
 #include "common.cuh"
 
 namespace b3c {
@@ -14,6 +16,81 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(t_err, sizeof(t_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- CUDA-graph cache (see common.cuh) ----------------------------------------------------
+std::atomic<int> g_use_graphs{1};
+namespace {
+struct GraphKey {
+    const void *ws, *aux;
+    int id;
+    cudaStream_t s;
+    bool operator<(const GraphKey &o) const {
+        if (ws != o.ws) return ws < o.ws;
+        if (aux != o.aux) return aux < o.aux;
+        if (id != o.id) return id < o.id;
+        return s < o.s;
+    }
+};
+struct GraphEntry {
+    cudaGraphExec_t exec;
+    int64_t launches;
+};
+std::mutex g_graph_mu;
+std::map<GraphKey, GraphEntry> g_graphs;
+}  // namespace
+
+int graph_run(cudaStream_t s, const void *ws, int id, const void *aux, const std::function<int()> &enqueue) {
+    if (!g_use_graphs.load()) return enqueue();
+    const GraphKey key{ws, aux, id, s};
+    {
+        std::lock_guard<std::mutex> g(g_graph_mu);
+        auto it = g_graphs.find(key);
+        if (it != g_graphs.end()) {
+            B3C_CUDA(cudaGraphLaunch(it->second.exec, s));
+            count_launch((int)it->second.launches);
+            return B3C_OK;
+        }
+    }
+    const int64_t before = g_launches.load();
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return enqueue();                              // the stream cannot be captured (already capturing?): run directly
+    }
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc != B3C_OK || e != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        if (rc != B3C_OK) return rc;
+        set_error("CUDA graph capture failed: %s", cudaGetErrorString(e));
+        return B3C_ERR_CUDA;
+    }
+    GraphEntry ent;
+    ent.launches = g_launches.load() - before;         // counted while capturing; stands for this first replay
+    const cudaError_t ei = cudaGraphInstantiate(&ent.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+        set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+        return B3C_ERR_CUDA;
+    }
+    B3C_CUDA(cudaGraphLaunch(ent.exec, s));
+    std::lock_guard<std::mutex> g(g_graph_mu);
+    g_graphs[key] = ent;
+    return B3C_OK;
+}
+
+void graph_forget(const void *ws) {
+    std::lock_guard<std::mutex> g(g_graph_mu);
+    for (auto it = g_graphs.begin(); it != g_graphs.end();) {
+        if (it->first.ws == ws) {
+            cudaGraphExecDestroy(it->second.exec);
+            it = g_graphs.erase(it);
+        } else {
+            ++it;
+        }
+    }
 }
 
 // ---- exclusive scan ---------------------------------------------------------------------

@@ -2051,6 +2051,10 @@ int b3c_set_option(int32_t key, int64_t value) {
             B3C_REQUIRE(value == 0 || value == 1, "count stream option is 0 or 1");
             g_cnt_stream.store((int)value);
             return B3C_OK;
+        case B3C_OPT_USE_GRAPHS:
+            B3C_REQUIRE(value == 0 || value == 1, "graph option is 0 or 1");
+            g_use_graphs.store((int)value);
+            return B3C_OK;
         case B3C_OPT_PEER_TIMEOUT_MS:
             B3C_REQUIRE(value >= 1 && value <= 3600000, "peer time-out must be between 1 ms and one hour");
             g_peer_timeout_cycles.store((long long)value * 2000000LL);        // SM cycles at ~2 GHz

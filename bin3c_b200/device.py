@@ -32,6 +32,37 @@ class nvtx_range(object):
         return False
 
 
+class pipeline_stream(object):
+    """
+    Run a pass of the path on a capturable stream.  The sort-reduce sequences replay as CUDA graphs
+    (include/bin3c_b200.h: B3C_OPT_USE_GRAPHS), and a graph cannot be captured on the legacy default stream -- which is
+    what torch hands out unless the caller chose a stream.  So: if the current stream is the default one, the pass
+    runs on the pipeline's own stream, ordered after everything already enqueued, and the default stream is ordered
+    after the pass on exit; a caller's own stream is used as it is.
+    """
+    _own = {}
+
+    def __enter__(self):
+        cur = torch.cuda.current_stream()
+        self._ctx = None
+        if cur.cuda_stream == 0:
+            d = torch.cuda.current_device()
+            side = pipeline_stream._own.get(d)
+            if side is None:
+                side = pipeline_stream._own[d] = torch.cuda.Stream()
+            side.wait_stream(cur)
+            self._outer, self._side = cur, side
+            self._ctx = torch.cuda.stream(side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+            self._outer.wait_stream(self._side)
+        return False
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError('bin3c_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')

@@ -708,12 +708,14 @@ class ShardedHotPath(object):
         return dict(self.trace.out)
 
     def run(self, records, record_bytes=8, n_records=None):
-        rng = getattr(getattr(self.engine, 'dev', None), 'nvtx_range', None) or _no_range
-        with rng('accumulate(sharded)'):
-            self.accumulate(records, record_bytes, n_records)
-        with rng('mask'):
-            self.compute_mask()
-        with rng('kr(row block)'):
-            self.balance()
-        with rng('edges'):
-            return self.edges()
+        dev = getattr(self.engine, 'dev', None)
+        rng = getattr(dev, 'nvtx_range', None) or _no_range
+        with (dev.pipeline_stream() if dev is not None else _no_range('')):
+            with rng('accumulate(sharded)'):
+                self.accumulate(records, record_bytes, n_records)
+            with rng('mask'):
+                self.compute_mask()
+            with rng('kr(row block)'):
+                self.balance()
+            with rng('edges'):
+                return self.edges()

@@ -147,6 +147,10 @@ class HotPath(object):
         Both are views of the pipeline's reusable buffers (device buffers, or pinned host buffers
         with to_host): they are overwritten by the next run(), so copy what must outlive it.
         """
+        with dev.pipeline_stream():
+            return self._run(records, to_host, fused, record_bytes, n_records)
+
+    def _run(self, records, to_host, fused, record_bytes, n_records):
         self.reset()
         if self.events is not None:
             self.events = []

@@ -184,9 +184,11 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  * at the start of the next run.
  * B3C_OPT_KR_COUNT_STREAM (default 1): b3c_kr_run_counts / b3c_kr_run_peer_counts stream the raw uint32 counts
  * (6 bytes per entry with the 16-bit column) and factor the site normalisation out of the row sums,
- * (A u)_i = (1/s_i) sum_j c_ij (u_j / s_j); 0 streams fp64 values c_ij / (s_i s_j) (10 bytes per entry). */
+ * (A u)_i = (1/s_i) sum_j c_ij (u_j / s_j); 0 streams fp64 values c_ij / (s_i s_j) (10 bytes per entry).
+ * B3C_OPT_USE_GRAPHS (default 1): the sort-reduce sequences of an accumulator (~60 launches with fixed grids;
+ * all sizes are read from device counters) are captured once per workspace as a CUDA graph and replayed. */
 enum { B3C_OPT_KR_SLAB_WIDTH = 1, B3C_OPT_KR_MAX_SLABS = 2, B3C_OPT_KR_FLAGS = 3, B3C_OPT_PEER_TIMEOUT_MS = 4,
-       B3C_OPT_KR_COUNT_STREAM = 5 };
+       B3C_OPT_KR_COUNT_STREAM = 5, B3C_OPT_USE_GRAPHS = 6 };
 int b3c_set_option(int32_t key, int64_t value);
 
 int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz);
