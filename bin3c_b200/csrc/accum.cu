@@ -49,7 +49,7 @@ struct AccumState {
         o_up_ptr, o_lo_ptr, o_len, o_indptr_f, o_indptr_u, o_scan_tmp, o_tmp64, total;
     bool reduced = false;
     int64_t nnz_uo = 0, nnz_diag = 0;
-    int comp_in_a = 0;        // which key buffer holds the (j,e)-sorted composite after reduce
+    int comp_in_a = 0;        // which key buffer holds the (j,i)-sorted composite after reduce
 };
 
 static std::mutex g_mu;
@@ -567,6 +567,15 @@ static int radix_sort(uint64_t *a, uint64_t *b, const unsigned long long *d_n, i
     return B3C_OK;
 }
 
+// ---- composite of the mirror half ------------------------------------------------------------
+// The lower half of the symmetric matrix is the upper half transposed: entry (i, j, c) of the unique list becomes
+// (row j, column i, count c).  It is produced by a stable sort on the column bits of a COMPOSITE that carries its own
+// payload -- j in the top b bits, then i, then the count in the remaining cbits = min(32, 64 - 2b) bits -- so the emit
+// kernel streams the sorted composites instead of gathering i and c through an entry id (at C3 those scattered 8- and
+// 4-byte gathers moved 6 GB through DRAM for 0.44 GB of payload).  A count that does not fit (>= 2^cbits - 1) is stored
+// as the all-ones escape and looked up exactly by bisection in the sorted unique keys.
+__host__ __device__ __forceinline__ int comp_cbits(int b) { return 64 - 2 * b < 32 ? 64 - 2 * b : 32; }
+
 // ---- run-length reduce ----------------------------------------------------------------------
 __global__ void __launch_bounds__(RS_THREADS) k_rle_count(const uint64_t *__restrict__ keys,
                                                           const unsigned long long *__restrict__ d_n,
@@ -627,7 +636,11 @@ __global__ void k_rle_counts(const uint32_t *__restrict__ pos, const unsigned lo
         const uint32_t c = pos[e + 1] - pos[e];
         cnt[e] = c;
         w += c;
-        comp[e] = ((uint64_t)(uniq[e] & jmask) << 32) | (uint64_t)e;    // (column, entry id)
+        const int cbits = comp_cbits(b);
+        const uint64_t cmask = cbits >= 64 ? ~0ull : ((1ull << cbits) - 1ull);
+        const uint64_t k = uniq[e];
+        const uint64_t cc = (uint64_t)c < cmask ? (uint64_t)c : cmask;      // all ones: escape, looked up exactly
+        comp[e] = ((k & jmask) << (b + cbits)) | ((k >> b) << cbits) | cc;  // (column j, row i, count)
     }
     w = warp_sum(w);
     if (lane_id() == 0 && w) atomicAdd((unsigned long long *)&ctr[C_WEIGHT], 2ull * w);   // mirrored entries (Q7)
@@ -701,15 +714,28 @@ __global__ void k_emit(int symmetric, int b, int32_t n_seq, const unsigned long 
             counts[d] = c;
         }
     }
-    // lower half (mirror): composite t is sorted by (column j, entry id) == (j, i)
+    // lower half (mirror): composite t is sorted by (column j, row i) and carries the count
     if (symmetric) {
+        const int cbits = comp_cbits(b);
+        const uint64_t cmask = (1ull << cbits) - 1ull;
         for (int64_t t = gid; t < nnz; t += stride) {
             const uint64_t c = comp[t];
-            const int64_t j = (int64_t)(c >> 32);
-            const int64_t e = (int64_t)(c & 0xffffffffull);
+            const int64_t j = (int64_t)(c >> (b + cbits));
+            const uint64_t i = (c >> cbits) & jmask;
+            uint32_t cv = (uint32_t)(c & cmask);
+            if ((c & cmask) == cmask) {                 // escape: the exact count sits beside the unique key (i, j)
+                const uint64_t key = (i << b) | (uint64_t)j;
+                int64_t a = 0, z = nnz;
+                while (a < z) {
+                    const int64_t mid = (a + z) >> 1;
+                    if (uniq[mid] < key) a = mid + 1;
+                    else z = mid;
+                }
+                cv = cnt[a];
+            }
             const int64_t d = indptr[j] + (t - lo[j]);
-            indices[d] = (int32_t)(uniq[e] >> b);
-            counts[d] = cnt[e];
+            indices[d] = (int32_t)i;
+            counts[d] = cv;
         }
     }
 }
@@ -1321,7 +1347,8 @@ int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream) {
     if (rc) return rc;
     // where the two sorts leave their results is a function of the key width alone
     uint64_t *sorted = radix_where(0, 2 * st.b) ? kb : ka, *other = radix_where(0, 2 * st.b) ? ka : kb;
-    uint64_t *comp = radix_where(32, 32 + st.b) ? other : sorted;
+    const int csh = st.b + comp_cbits(st.b);             // the column j sits in bits [csh, csh + b) of a composite
+    uint64_t *comp = radix_where(csh, csh + st.b) ? other : sorted;
     st.comp_in_a = (comp == ka) ? 1 : 0;
     // The whole sequence (~60 launches; every size is read from device counters) is one CUDA graph per workspace.
     rc = graph_run(s, d_ws, /*id*/ 1, nullptr, [&]() -> int {
@@ -1345,12 +1372,12 @@ int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream) {
         k_diag_stats<<<kNumSMs * 2, 256, 0, s>>>(diag, st.n_seq, ctr);
         B3C_LAUNCH_CHECK();
         // 3. stable sort of the composite on the column bits only -> (j, i) order
-        rc2 = radix_sort(sorted, other, ctr + C_NNZ_UO, 32, 32 + st.b, hist, s, &where);
+        rc2 = radix_sort(sorted, other, ctr + C_NNZ_UO, csh, csh + st.b, hist, s, &where);
         if (rc2) return rc2;
         // 4. row pointers of both halves, row lengths, indptr of both output forms
         k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(uniq, ctr + C_NNZ_UO, st.b, st.n_seq, up);
         B3C_LAUNCH_CHECK();
-        k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(comp, ctr + C_NNZ_UO, 32, st.n_seq, lo);
+        k_row_ptr<<<kNumSMs * 8, 256, 0, s>>>(comp, ctr + C_NNZ_UO, csh, st.n_seq, lo);
         B3C_LAUNCH_CHECK();
         k_row_len<<<kNumSMs * 4, 256, 0, s>>>(up, lo, diag, st.n_seq, len, ip_u /* scratch: upper lengths */);
         B3C_LAUNCH_CHECK();

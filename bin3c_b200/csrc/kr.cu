@@ -2091,9 +2091,11 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     count_launch();
     KRScalars S;
     KRTimers T;
+    long long cta[BND_MAX];
     B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaMemcpyAsync(&T, A.timers, sizeof(T), cudaMemcpyDeviceToHost, s));
-    B3C_CUDA(cudaStreamSynchronize(s));
+    B3C_CUDA(cudaMemcpyAsync(cta, A.cta_spmv, (size_t)grid * 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaStreamSynchronize(s));                // the one host synchronisation of the solve's result
     float ms = 0.f;
     B3C_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1]));
     h_info[0] = S.n_iter;
@@ -2111,8 +2113,6 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     h_info[26] = A.n_seg;
     h_info[27] = (int64_t)(ms * 1000.0f + 0.5f);       // the persistent kernel alone, microseconds (CUDA events)
     {
-        long long cta[BND_MAX];
-        B3C_CUDA(cudaMemcpy(cta, A.cta_spmv, (size_t)grid * 8, cudaMemcpyDeviceToHost));
         long long mn = cta[0], mx = cta[0], sum = 0;
         for (int i = 0; i < grid; ++i) {
             mn = cta[i] < mn ? cta[i] : mn;

@@ -660,8 +660,8 @@ class ShardedHotPath(object):
             # the persistent kernel leaves the WHOLE scale vector on every rank (x lives in the exchange buffers);
             # only the zero-diagonal count, kept per row block, is summed through the arenas
             eng._scal[0] = float(st['zero_diag'])
-            z = eng.peer_allreduce(comm, eng._scal[:1], 'sum')
-            st['zero_diag'] = int(z.cpu()[0])
+            self._zero_diag_dev = eng.peer_allreduce(comm, eng._scal[:1], 'sum').clone()
+            st['zero_diag'] = None                 # read back with the edge sizes (edges()): no host sync of its own
         else:
             z = torch.tensor([st['zero_diag']], dtype=torch.int64, device=eng.x.device)
             st['zero_diag'] = int(comm.all_reduce(z, 'sum').cpu()[0])
@@ -697,6 +697,9 @@ class ShardedHotPath(object):
             self.edge_res = eng.compress_edges(self.block, self.mask, reduce_max, scale=scale, x=self.x)
         else:
             self.edge_res = eng.compress_edges(self.balanced, self.mask, reduce_max, scale=scale)
+        if getattr(self, '_zero_diag_dev', None) is not None and self.kr_info.get('zero_diag') is None:
+            self.kr_info['zero_diag'] = int(self._zero_diag_dev.cpu()[0])     # the stream has just been synchronised
+            self._zero_diag_dev = None
         self.trace.mark('edges')
         return self.edge_res
 

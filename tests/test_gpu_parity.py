@@ -967,3 +967,25 @@ def test_extent_map_post_processing_vs_reference(dev, tmp_path):
         cm.get_extent_map(mean_type='quadratic')
     with pytest.raises(NotImplementedError):
         cm.get_extent_map(permute=True)
+
+
+def test_accumulate_mirror_composite_count_escape(dev):
+    """The composite of the mirror half carries (column, row, count) in 64 bits: with 27-bit indices only 10 bits are
+    left for the count, so cells counted 1023 times or more take the escape (exact count looked up by bisection in the
+    unique keys).  70M contigs, a few hot cells and many ordinary ones, against the oracle."""
+    from bin3c_b200 import synth
+    n = 70_000_000
+    lut = np.arange(n, dtype=np.int32)
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, n, 40_000)
+    b = rng.integers(0, n, 40_000)
+    hot_a = np.repeat(np.array([5, 69_999_999, 123_456, 5]), [1022, 1023, 5000, 70_000])
+    hot_b = np.repeat(np.array([7, 3, 69_000_000, 60_000_001]), [1022, 1023, 5000, 70_000])
+    ti, tj = np.concatenate([a, hot_a, hot_b[:2045]]), np.concatenate([b, hot_b, hot_a[:2045]])
+    rec = synth.pack_pairs(ti, tj, np.ones(len(ti), bool))
+    csr, info = _accumulate(dev, rec, lut, n)
+    want, counts = _oracle_full(rec, lut, n)
+    got = csr.to_scipy_coo()
+    assert np.array_equal(got.row, want.row) and np.array_equal(got.col, want.col)
+    assert np.array_equal(got.data, want.data) and got.data.max() == 70_000
+    assert {k: info[k] for k in counts} == counts
