@@ -42,7 +42,7 @@ struct AccumState {
     int32_t n_seq = 0, n_refs = 0;
     int b = 0;                // bits per index in the key
     int64_t rank_words = 0;   // 64-bit words of the tid bitmap
-    bool smem_diag = false, smem_rank = false;
+    bool smem_diag = false, smem_rank = false, cls_dbl = false;
     int cls_smem = 0, cls_grid = 0;
     const int32_t *d_lut = nullptr;
     int64_t o_ctr, o_diag, o_bits, o_pref, o_keys_a, o_keys_b, o_uniq, o_pos, o_cnt, o_hist, o_heads,
@@ -113,6 +113,12 @@ static void plan(AccumState &st, int64_t cap, int32_t n_seq, int32_t n_refs) {
     } else {
         st.cls_smem = (int)(hdr + stage64);
     }
+    // a second staging buffer (alternating tiles: two block barriers per tile instead of three) where it fits
+    {
+        const int64_t stage = st.smem_diag ? stage32 : stage64;
+        st.cls_dbl = (int64_t)st.cls_smem + stage <= SMEM_MAX;
+        if (st.cls_dbl) st.cls_smem += (int)stage;
+    }
     st.cls_grid = kNumSMs;      // persistent: one 1024-thread CTA per SM, tiles strided over the grid
     layout(st);
 }
@@ -161,15 +167,17 @@ struct ClsParams {
     uint64_t *keys;
     int64_t cap;
     unsigned long long *ctr;
+    int dbl;                 // two staging buffers
 };
 
 template <bool SMEM_DIAG, bool RANK>
 __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char *smem) {
     using stage_t = typename std::conditional<SMEM_DIAG, uint32_t, uint64_t>::type;
-    unsigned *s_cnt = reinterpret_cast<unsigned *>(smem);
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + 8);
-    stage_t *s_stage = reinterpret_cast<stage_t *>(smem + 32);
-    unsigned char *cur = smem + 32 + sizeof(stage_t) * CLS_TILE;
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(smem);                              // [2]
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + 8);     // [2]
+    stage_t *s_stage0 = reinterpret_cast<stage_t *>(smem + 32);
+    const int n_buf = P.dbl ? 2 : 1;
+    unsigned char *cur = smem + 32 + sizeof(stage_t) * CLS_TILE * n_buf;
     const uint32_t *s_bits = nullptr;
     const uint32_t *s_pref = nullptr;
     if (RANK) {
@@ -193,7 +201,7 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
     uint32_t *s_diag = reinterpret_cast<uint32_t *>(cur);
     if (SMEM_DIAG)
         for (int i = threadIdx.x; i < P.n_seq; i += CLS_THREADS) s_diag[i] = 0;
-    if (threadIdx.x == 0) *s_cnt = 0;
+    if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
     __syncthreads();
 
     const unsigned lane = lane_id();
@@ -271,9 +279,17 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
         uint4 vnn[CLS_RPT / 2];
         unsigned oknn = 0;
         if (tile + 2 * (int64_t)gridDim.x < n_tiles) oknn = load_tile(tile + 2 * (int64_t)gridDim.x, vnn);
+        // Staging: the tile's off-diagonal keys go to shared memory first -- ONE reservation per warp and tile (the four
+        // ballots give every lane its slot) -- then to the key buffer with one global atomic per tile.  With two
+        // staging buffers (alternating tiles) a tile costs two block barriers: a buffer is refilled only after the
+        // barriers of the tile in between, and its counter is reset by thread 0 between those barriers.
+        const int buf = P.dbl ? (int)(((tile - blockIdx.x) / gridDim.x) & 1) : 0;
+        stage_t *s_stage = s_stage0 + (size_t)buf * CLS_TILE;
         bool ok[CLS_RPT];
 #pragma unroll
         for (int k = 0; k < CLS_RPT; ++k) ok[k] = (okm >> k) & 1u;
+        uint64_t keyv[CLS_RPT];
+        unsigned offm[CLS_RPT];
 #pragma unroll
         for (int k = 0; k < CLS_RPT; ++k) {
             const uint32_t lo = (k & 1) ? v[k >> 1].z : v[k >> 1].x;
@@ -300,30 +316,38 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
                     }
                 }
             }
-            const unsigned m = __ballot_sync(kFullMask, off);
-            if (m) {
-                const int leader = __ffs(m) - 1;
+            keyv[k] = key;
+            offm[k] = __ballot_sync(kFullMask, off);
+        }
+        {
+            unsigned wtot = 0;
+#pragma unroll
+            for (int k = 0; k < CLS_RPT; ++k) wtot += __popc(offm[k]);
+            if (wtot) {
                 unsigned at = 0;
-                if ((int)lane == leader) at = atomicAdd(s_cnt, __popc(m));
-                at = __shfl_sync(kFullMask, at, leader);
-                if (off) s_stage[at + __popc(m & lt)] = (stage_t)key;
+                if (lane == 0) at = atomicAdd(&s_cnt[buf], wtot);
+                at = __shfl_sync(kFullMask, at, 0);
+#pragma unroll
+                for (int k = 0; k < CLS_RPT; ++k) {
+                    if ((offm[k] >> lane) & 1u) s_stage[at + __popc(offm[k] & lt)] = (stage_t)keyv[k];
+                    at += __popc(offm[k]);
+                }
             }
         }
         __syncthreads();
-        const unsigned total = *s_cnt;
-        if (threadIdx.x == 0 && total) *s_base = atomicAdd(&P.ctr[C_NKEYS], (unsigned long long)total);
+        const unsigned total = s_cnt[buf];
+        if (threadIdx.x == 0 && total) s_base[buf] = atomicAdd(&P.ctr[C_NKEYS], (unsigned long long)total);
         __syncthreads();
+        if (threadIdx.x == 0) s_cnt[buf] = 0;       // everybody read `total` before the barrier above
         if (total) {
-            const unsigned long long gb = *s_base;
+            const unsigned long long gb = s_base[buf];
             if ((int64_t)(gb + total) <= P.cap) {
                 for (unsigned i = threadIdx.x; i < total; i += CLS_THREADS) P.keys[gb + i] = (uint64_t)s_stage[i];
             } else if (threadIdx.x == 0) {
                 P.ctr[C_OVERFLOW] = 1;
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) *s_cnt = 0;
-        __syncthreads();            // the reset must precede the next tile's staging atomics
+        if (!P.dbl) __syncthreads();                // one buffer: the flush must finish before the next tile stages
 #pragma unroll
         for (int l = 0; l < CLS_RPT / 2; ++l) {
             v[l] = vn[l];
@@ -668,10 +692,15 @@ __global__ void k_row_ptr(const uint64_t *__restrict__ keys, const unsigned long
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t e = gid; e < n; e += stride) {
+        if (e == 0) continue;                          // the rows up to the first key's are filled in parallel below
         const int64_t r = (int64_t)(keys[e] >> shift);
-        const int64_t rp = e > 0 ? (int64_t)(keys[e - 1] >> shift) : -1;
+        const int64_t rp = (int64_t)(keys[e - 1] >> shift);
         for (int64_t q = rp + 1; q <= r; ++q) ptr[q] = e;
     }
+    // Leading and trailing rows without keys.  A row block of a sharded run starts at row_lo: one thread walking
+    // there alone cost the last of 8 ranks ~1 ms at C3 and ~4 ms at C4 -- the whole grid does it instead.
+    const int64_t rf = n > 0 ? (int64_t)(keys[0] >> shift) : -1;
+    for (int64_t q = gid; q <= rf; q += stride) ptr[q] = 0;
     const int64_t rl = n > 0 ? (int64_t)(keys[n - 1] >> shift) : -1;
     for (int64_t q = rl + 1 + gid; q <= n_seq; q += stride) ptr[q] = n;
 }
@@ -1318,6 +1347,7 @@ static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int
     P.keys = (uint64_t *)(ws + st.o_keys_a);
     P.cap = st.cap;
     P.ctr = (unsigned long long *)(ws + st.o_ctr);
+    P.dbl = st.cls_dbl ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (st.smem_diag && st.smem_rank) return launch_classify<true, true>(st, P, s);
     if (st.smem_diag) return launch_classify<true, false>(st, P, s);
