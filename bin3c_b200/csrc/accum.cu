@@ -26,7 +26,9 @@ enum { C_NKEYS = 0, C_ACCEPT, C_EXCL, C_POOR, C_NNZ_UO, C_NNZ_DIAG, C_WEIGHT, C_
 
 constexpr int CLS_THREADS = 1024;
 constexpr int CLS_RPT = 4;                       // records per thread per tile (two 128-bit loads)
-constexpr int CLS_TILE = CLS_THREADS * CLS_RPT;  // 4096 records = 32 KB of input per tile
+constexpr int CLS_WARPS = CLS_THREADS / 32;
+constexpr int CLS_WTILE = 32 * CLS_RPT;          // 128 records = 1 KB of input per warp tile
+constexpr int CLS_CAPW_MAX = 512;                // keys a warp stages before it flushes (at most)
 constexpr int SMEM_MAX = 232448;                 // 227 KB opt-in limit per CTA on sm_100
 
 constexpr int RS_THREADS = 512;
@@ -42,8 +44,9 @@ struct AccumState {
     int32_t n_seq = 0, n_refs = 0;
     int b = 0;                // bits per index in the key
     int64_t rank_words = 0;   // 64-bit words of the tid bitmap
-    bool smem_diag = false, smem_rank = false, cls_dbl = false;
-    int cls_smem = 0, cls_grid = 0;
+    bool smem_diag = false;
+    int smem_rank = 0;        // 0 gather, 1 pair table, 2 packed table (classify_tiles)
+    int cls_smem = 0, cls_grid = 0, cls_cap_w = 0;
     const int32_t *d_lut = nullptr;
     int64_t o_ctr, o_diag, o_bits, o_pref, o_keys_a, o_keys_b, o_uniq, o_pos, o_cnt, o_hist, o_heads,
         o_up_ptr, o_lo_ptr, o_len, o_indptr_f, o_indptr_u, o_scan_tmp, o_tmp64, total;
@@ -94,31 +97,55 @@ static void plan(AccumState &st, int64_t cap, int32_t n_seq, int32_t n_refs) {
     st.n_refs = n_refs;
     st.b = key_bits_for(n_seq);
     st.rank_words = ceil_div(n_refs > 0 ? n_refs : 1, 64);
-    // shared-memory plan of k_classify: header | staging | rank table | diagonal histogram
-    const int64_t hdr = 32;
-    // in shared memory the table is held as 32-bit words with one prefix per word (cheaper look-ups than 64-bit)
-    const int64_t rank_bytes = align_up(st.rank_words * 8, 16) + align_up(st.rank_words * 8, 16);
+    // shared-memory plan of k_classify: per-warp key staging | rank table | diagonal histogram
+    // (in shared memory the table is held as (32-bit word, prefix) pairs plus one zero sentinel)
+    const int64_t rank64_bytes = align_up((st.rank_words * 2 + 1) * 8, 16);
+    const int64_t rank32_bytes = align_up((ceil_div(n_refs > 0 ? n_refs : 1, 12) + 1) * 4, 16);
     const int64_t diag_bytes = align_up((int64_t)n_seq * 4, 16);
-    const int64_t stage32 = (int64_t)CLS_TILE * 4, stage64 = (int64_t)CLS_TILE * 8;
-    st.smem_diag = st.smem_rank = false;
-    if (st.b <= 16 && hdr + stage32 + rank_bytes + diag_bytes <= SMEM_MAX) {
-        st.smem_diag = st.smem_rank = true;
-        st.cls_smem = (int)(hdr + stage32 + rank_bytes + diag_bytes);
-    } else if (st.b <= 16 && hdr + stage32 + diag_bytes <= SMEM_MAX) {
+    // staging keys per warp that fit beside `fixed` bytes: at least one warp tile, at most CLS_CAPW_MAX
+    auto cap_w = [](int64_t fixed, int key_bytes) -> int {
+        int64_t c = (SMEM_MAX - fixed) / ((int64_t)CLS_WARPS * key_bytes);
+        if (c > CLS_CAPW_MAX) c = CLS_CAPW_MAX;
+        c &= ~(int64_t)31;
+        return c >= CLS_WTILE ? (int)c : 0;
+    };
+    // the packed table (mode 2) where it fits with room for 256 staged keys per warp and the index fits its 20-bit
+    // prefix; else the pair table (mode 1); else look-ups gather from global memory (mode 0)
+    auto rank_mode = [&](int64_t other, int key_bytes, int64_t *bytes) -> int {
+        if (st.b <= 20 && cap_w(other + rank32_bytes, key_bytes) >= 256) {
+            *bytes = rank32_bytes;
+            return 2;
+        }
+        if (cap_w(other + rank64_bytes, key_bytes)) {
+            *bytes = rank64_bytes;
+            return 1;
+        }
+        if (st.b <= 20 && cap_w(other + rank32_bytes, key_bytes)) {
+            *bytes = rank32_bytes;
+            return 2;
+        }
+        *bytes = 0;
+        return 0;
+    };
+    st.smem_diag = false;
+    st.smem_rank = 0;
+    int64_t fixed = 0, rb = 0;
+    int kb = 8;
+    if (st.b <= 16 && rank_mode(diag_bytes, 4, &rb)) {
         st.smem_diag = true;
-        st.cls_smem = (int)(hdr + stage32 + diag_bytes);
-    } else if (hdr + stage64 + rank_bytes <= SMEM_MAX) {
-        st.smem_rank = true;
-        st.cls_smem = (int)(hdr + stage64 + rank_bytes);
+        st.smem_rank = rank_mode(diag_bytes, 4, &rb);
+        fixed = rb + diag_bytes;
+        kb = 4;
+    } else if (st.b <= 16 && cap_w(diag_bytes, 4)) {
+        st.smem_diag = true;
+        fixed = diag_bytes;
+        kb = 4;
     } else {
-        st.cls_smem = (int)(hdr + stage64);
+        st.smem_rank = rank_mode(0, 8, &rb);
+        fixed = rb;
     }
-    // a second staging buffer (alternating tiles: two block barriers per tile instead of three) where it fits
-    {
-        const int64_t stage = st.smem_diag ? stage32 : stage64;
-        st.cls_dbl = (int64_t)st.cls_smem + stage <= SMEM_MAX;
-        if (st.cls_dbl) st.cls_smem += (int)stage;
-    }
+    st.cls_cap_w = cap_w(fixed, kb);
+    st.cls_smem = (int)((int64_t)CLS_WARPS * st.cls_cap_w * kb + fixed);
     st.cls_grid = kNumSMs;      // persistent: one 1024-thread CTA per SM, tiles strided over the grid
     layout(st);
 }
@@ -167,65 +194,119 @@ struct ClsParams {
     uint64_t *keys;
     int64_t cap;
     unsigned long long *ctr;
-    int dbl;                 // two staging buffers
+    int cap_w;               // staging keys per warp
 };
 
-template <bool SMEM_DIAG, bool RANK>
+// Every warp runs on its own: its own stream of 128-record warp tiles (strided over all warps of the grid, loads
+// issued two tiles ahead), its own staging area of `cap_w` keys in shared memory and its own flushes -- one global
+// atomic per flush reserves the run in the key buffer (the order of the keys does not matter: they are sorted next).
+// There is no block barrier inside the loop.  The record logic is written without branches (look-ups read a zero
+// sentinel word for out-of-table ids; exclusion, matcher and diagonal tests are predicates), because the four
+// outcomes -- excluded, poor match, diagonal, off-diagonal -- are mixed in every warp and a branchy form executes
+// all of them one after the other (it was 147 issued instructions per 32 records; this form is ~60).
+// RANK: 0 = look-ups gather from the global tid -> index table; 1 = rank table in shared memory as (32-bit bitmap
+// word, prefix) pairs, one 8-byte load per look-up; 2 = packed form, one 32-bit word per 12 references (12-bit bitmap,
+// 20-bit prefix): a scattered 4-byte shared-memory load costs about half the wavefronts of an 8-byte one, and at C3
+// the kernel is bound by the L1/shared-memory pipe (scattered diagonal REDs + table look-ups), not by issue or HBM.
+template <bool SMEM_DIAG, int RANK>
 __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char *smem) {
     using stage_t = typename std::conditional<SMEM_DIAG, uint32_t, uint64_t>::type;
-    unsigned *s_cnt = reinterpret_cast<unsigned *>(smem);                              // [2]
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(smem + 8);     // [2]
-    stage_t *s_stage0 = reinterpret_cast<stage_t *>(smem + 32);
-    const int n_buf = P.dbl ? 2 : 1;
-    unsigned char *cur = smem + 32 + sizeof(stage_t) * CLS_TILE * n_buf;
-    const uint32_t *s_bits = nullptr;
-    const uint32_t *s_pref = nullptr;
-    if (RANK) {
-        // the global table has 64-bit words with one prefix each; here it is re-cut into 32-bit words (the halves of a
-        // little-endian 64-bit word, in place) with a prefix per half, so a look-up is 32-bit shifts and one POPC
-        uint32_t *wb = reinterpret_cast<uint32_t *>(cur);
-        cur += (P.rank_words * 8 + 15) / 16 * 16;
-        uint32_t *wp = reinterpret_cast<uint32_t *>(cur);
-        cur += (P.rank_words * 8 + 15) / 16 * 16;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+    stage_t *s_stage = reinterpret_cast<stage_t *>(smem) + (size_t)warp * P.cap_w;
+    unsigned char *cur = smem + sizeof(stage_t) * (size_t)CLS_WARPS * P.cap_w;
+    const uint2 *s_tab = nullptr;
+    const uint32_t *s_tab32 = nullptr;
+    const uint32_t nw32 = (uint32_t)(P.rank_words * 2);
+    const uint32_t nw12 = (uint32_t)((P.n_refs + 11) / 12);
+    if (RANK == 1) {
+        // the global table has 64-bit words with one prefix each; here it is re-cut into (32-bit word, prefix) pairs so
+        // a look-up is ONE 8-byte shared-memory load, 32-bit shifts and a POPC; entry nw32 is the all-zero sentinel
+        uint2 *tab = reinterpret_cast<uint2 *>(cur);
+        cur += (((size_t)nw32 + 1) * 8 + 15) / 16 * 16;
         for (int64_t i = threadIdx.x; i < P.rank_words; i += CLS_THREADS) {
             const unsigned long long m = P.g_bits[i];
             const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32), pf = P.g_pref[i];
-            wb[2 * i] = lo;
-            wb[2 * i + 1] = hi;
-            wp[2 * i] = pf;
-            wp[2 * i + 1] = pf + __popc(lo);
+            tab[2 * i] = make_uint2(lo, pf);
+            tab[2 * i + 1] = make_uint2(hi, pf + __popc(lo));
         }
-        s_bits = wb;
-        s_pref = wp;
+        if (threadIdx.x == 0) tab[nw32] = make_uint2(0u, 0u);
+        s_tab = tab;
+    }
+    if (RANK == 2) {
+        // word w covers references [12 w, 12 w + 12): bitmap in bits 0..11, rank of reference 12 w in bits 12..31
+        uint32_t *tab = reinterpret_cast<uint32_t *>(cur);
+        cur += (((size_t)nw12 + 1) * 4 + 15) / 16 * 16;
+        for (uint32_t w = threadIdx.x; w < nw12; w += CLS_THREADS) {
+            const uint32_t t0 = w * 12u;
+            const int64_t q = t0 >> 6;
+            const unsigned sh = t0 & 63u;
+            const unsigned long long m0 = P.g_bits[q];
+            unsigned long long m = m0 >> sh;
+            if (sh > 52 && q + 1 < P.rank_words) m |= P.g_bits[q + 1] << (64 - sh);
+            const uint32_t pf = P.g_pref[q] + (uint32_t)__popcll(m0 & ((1ull << sh) - 1ull));
+            tab[w] = ((uint32_t)m & 0xfffu) | (pf << 12);
+        }
+        if (threadIdx.x == 0) tab[nw12] = 0u;
+        s_tab32 = tab;
     }
     uint32_t *s_diag = reinterpret_cast<uint32_t *>(cur);
     if (SMEM_DIAG)
         for (int i = threadIdx.x; i < P.n_seq; i += CLS_THREADS) s_diag[i] = 0;
-    if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
     __syncthreads();
 
-    const unsigned lane = lane_id();
-    const unsigned lt = lanemask_lt();
-    unsigned n_acc = 0, n_excl = 0, n_poor = 0;
-    const int64_t n_tiles = (P.n_rec + CLS_TILE - 1) / CLS_TILE;
+    unsigned n_ok = 0, n_valid = 0, n_acc = 0;
+    unsigned cnt = 0;                                  // keys staged by this warp (warp-uniform)
+    const int64_t n_tiles = (P.n_rec + CLS_WTILE - 1) / CLS_WTILE;
+    const int64_t n_warps = (int64_t)gridDim.x * CLS_WARPS;
+    const int64_t w0 = (int64_t)blockIdx.x * CLS_WARPS + warp;
 
-    auto lookup = [&](uint32_t t) -> int32_t {
-        if (t >= (uint32_t)P.n_refs) return -1;
-        if (RANK) {
-            const uint32_t m = s_bits[t >> 5];
+    // index of a kept reference, or hit = false (excluded, or beyond the table); `on` = false skips the load
+    auto lookup = [&](uint32_t t, bool on, bool &hit) -> uint32_t {
+        if (RANK == 2) {
+            uint32_t w = __umulhi(t, 0xAAAAAAABu) >> 3;             // t / 12
+            const unsigned bit = t - w * 12u;
+            w = min(w, nw12);
+            uint32_t e = 0;
+            if (on) e = s_tab32[w];
+            hit = (e >> bit) & 1u;
+            return (e >> 12) + __popc(e & ~(0xffffffffu << bit) & 0xfffu);
+        } else if (RANK == 1) {
+            uint2 e = make_uint2(0u, 0u);
+            if (on) e = s_tab[min(t >> 5, nw32)];
             const unsigned bit = t & 31u;
-            if (!((m >> bit) & 1u)) return -1;
-            return (int32_t)(s_pref[t >> 5] + __popc(m & ((1u << bit) - 1u)));
+            hit = (e.x >> bit) & 1u;
+            return e.y + __popc(e.x & ~(0xffffffffu << bit));
         } else {
-            const int32_t v = __ldg(P.lut + t);
-            return v < P.n_seq ? v : -1;
+            int32_t v = -1;
+            if (on && t < (uint32_t)P.n_refs) v = __ldg(P.lut + t);
+            hit = v >= 0 && v < P.n_seq;
+            return (uint32_t)v;
         }
     };
 
-    // two 128-bit streaming loads per thread; the next tile's loads are issued before the current
-    // tile is processed, so their latency hides behind the classification work
+    auto flush = [&]() {
+        __syncwarp();
+        unsigned long long gb = 0;
+        if (lane == 0) gb = atomicAdd(&P.ctr[C_NKEYS], (unsigned long long)cnt);
+        gb = __shfl_sync(kFullMask, gb, 0);
+        if ((int64_t)(gb + cnt) <= P.cap) {
+            for (unsigned i = lane; i < cnt; i += 32) P.keys[gb + i] = (uint64_t)s_stage[i];
+        } else if (lane == 0) {
+            P.ctr[C_OVERFLOW] = 1;
+        }
+        __syncwarp();
+        cnt = 0;
+    };
+
+    // lane l of the warp reads records [base + h*64 + 2*l, +2) for h = 0, 1: two 128-bit streaming loads per tile
     auto load_tile = [&](int64_t tile, uint4 (&v)[CLS_RPT / 2]) -> unsigned {
-        const int64_t base = tile * CLS_TILE;
+        const int64_t base = tile * CLS_WTILE;
+        if (P.rec_bytes == 8 && base + CLS_WTILE <= P.n_rec) {
+#pragma unroll
+            for (int h = 0; h < CLS_RPT / 2; ++h) v[h] = ld_stream_u4(P.rec + base + h * 64 + lane * 2);
+            return (1u << CLS_RPT) - 1u;
+        }
         unsigned okm = 0;
         if (P.rec_bytes != 8) {
             // narrow records: B bytes each, little endian, tid1 in bits [0, tb), the pass flag in bit tb, tid2 in
@@ -235,152 +316,137 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
             const uint64_t tmask = (1ull << tb) - 1ull;
             const int64_t last_word = (P.n_rec * B - 1) >> 3;
 #pragma unroll
-            for (int l = 0; l < CLS_RPT / 2; ++l) {
-                uint32_t h[4] = {0u, 0u, 0u, 0u};
+            for (int h = 0; h < CLS_RPT / 2; ++h) {
+                uint32_t q4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int64_t i = base + ((int64_t)l * CLS_THREADS + threadIdx.x) * 2 + q;
+                    const int64_t i = base + h * 64 + lane * 2 + q;
                     if (i < P.n_rec) {
                         const int64_t o = i * B, w = o >> 3;
                         const int sh = (int)(o & 7) * 8;
                         uint64_t r = __ldg(P.rec + w) >> sh;
                         if (sh + 8 * B > 64) r |= __ldg(P.rec + (w < last_word ? w + 1 : last_word)) << (64 - sh);
-                        h[2 * q] = (uint32_t)(r & tmask) | ((uint32_t)((r >> tb) & 1ull) << 31);
-                        h[2 * q + 1] = (uint32_t)((r >> (tb + 1)) & tmask);
-                        okm |= 1u << (2 * l + q);
+                        q4[2 * q] = (uint32_t)(r & tmask) | ((uint32_t)((r >> tb) & 1ull) << 31);
+                        q4[2 * q + 1] = (uint32_t)((r >> (tb + 1)) & tmask);
+                        okm |= 1u << (2 * h + q);
                     }
                 }
-                v[l] = make_uint4(h[0], h[1], h[2], h[3]);
+                v[h] = make_uint4(q4[0], q4[1], q4[2], q4[3]);
             }
             return okm;
         }
 #pragma unroll
-        for (int l = 0; l < CLS_RPT / 2; ++l) {
-            const int64_t i = base + ((int64_t)l * CLS_THREADS + threadIdx.x) * 2;
+        for (int h = 0; h < CLS_RPT / 2; ++h) {
+            const int64_t i = base + h * 64 + lane * 2;
             if (i + 1 < P.n_rec) {
-                v[l] = ld_stream_u4(P.rec + i);
-                okm |= 3u << (2 * l);
+                v[h] = ld_stream_u4(P.rec + i);
+                okm |= 3u << (2 * h);
             } else if (i < P.n_rec) {
                 const uint2 t = ld_stream_u2(P.rec + i);
-                v[l] = make_uint4(t.x, t.y, 0u, 0u);
-                okm |= 1u << (2 * l);
+                v[h] = make_uint4(t.x, t.y, 0u, 0u);
+                okm |= 1u << (2 * h);
             } else {
-                v[l] = make_uint4(0u, 0u, 0u, 0u);
+                v[h] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
         return okm;
     };
+
     // register ring of three tiles: the loads of the tile after next are issued before this tile is processed
     uint4 v[CLS_RPT / 2], vn[CLS_RPT / 2];
     unsigned okm = 0, okn = 0;
-    if ((int64_t)blockIdx.x < n_tiles) okm = load_tile(blockIdx.x, v);
-    if ((int64_t)blockIdx.x + gridDim.x < n_tiles) okn = load_tile(blockIdx.x + gridDim.x, vn);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (w0 < n_tiles) okm = load_tile(w0, v);
+    if (w0 + n_warps < n_tiles) okn = load_tile(w0 + n_warps, vn);
+    for (int64_t tile = w0; tile < n_tiles; tile += n_warps) {
         uint4 vnn[CLS_RPT / 2];
         unsigned oknn = 0;
-        if (tile + 2 * (int64_t)gridDim.x < n_tiles) oknn = load_tile(tile + 2 * (int64_t)gridDim.x, vnn);
-        // Staging: the tile's off-diagonal keys go to shared memory first -- ONE reservation per warp and tile (the four
-        // ballots give every lane its slot) -- then to the key buffer with one global atomic per tile.  With two
-        // staging buffers (alternating tiles) a tile costs two block barriers: a buffer is refilled only after the
-        // barriers of the tile in between, and its counter is reset by thread 0 between those barriers.
-        const int buf = P.dbl ? (int)(((tile - blockIdx.x) / gridDim.x) & 1) : 0;
-        stage_t *s_stage = s_stage0 + (size_t)buf * CLS_TILE;
-        bool ok[CLS_RPT];
-#pragma unroll
-        for (int k = 0; k < CLS_RPT; ++k) ok[k] = (okm >> k) & 1u;
+        if (tile + 2 * n_warps < n_tiles) oknn = load_tile(tile + 2 * n_warps, vnn);
         uint64_t keyv[CLS_RPT];
         unsigned offm[CLS_RPT];
+        uint32_t ixv[CLS_RPT], jxv[CLS_RPT];
+        bool accv[CLS_RPT];
+        // all look-ups of the tile first (eight independent shared-memory loads in flight per thread); the second
+        // mate of an intra-contig pair -- two thirds of Hi-C pairs -- has the first one's reference and is not looked up
 #pragma unroll
         for (int k = 0; k < CLS_RPT; ++k) {
             const uint32_t lo = (k & 1) ? v[k >> 1].z : v[k >> 1].x;
             const uint32_t hi = (k & 1) ? v[k >> 1].w : v[k >> 1].y;
-            bool off = false;
-            uint64_t key = 0;
-            if (ok[k]) {
-                const uint32_t ti = lo & 0x7fffffffu, tj = hi & 0x7fffffffu;
-                const int32_t ix = lookup(ti);
-                const int32_t jx = (tj == ti) ? ix : lookup(tj);
-                if (ix < 0 || jx < 0) {
-                    ++n_excl;                                   // contact_map.py:733-735
-                } else if (!(lo >> 31)) {
-                    ++n_poor;                                   // contact_map.py:737-739
-                } else {
-                    ++n_acc;                                    // contact_map.py:796
-                    if (ix == jx) {
-                        if (SMEM_DIAG) atomicAdd(&s_diag[ix], 1u);
-                        else atomicAdd(&P.diag[ix], 1u);
-                    } else {
-                        const uint32_t a = min(ix, jx), c = max(ix, jx);   // contact_map.py:774-777
-                        key = ((uint64_t)a << P.b) | c;
-                        off = true;
-                    }
-                }
+            const bool ok = (okm >> k) & 1u;
+            const uint32_t ti = lo & 0x7fffffffu, tj = hi & 0x7fffffffu;
+            bool hit_i, hit_j;
+            const uint32_t ix = lookup(ti, ok, hit_i);
+            uint32_t jx = lookup(tj, ok && tj != ti, hit_j);
+            if (tj == ti) {
+                jx = ix;
+                hit_j = hit_i;
             }
-            keyv[k] = key;
-            offm[k] = __ballot_sync(kFullMask, off);
+            const bool valid = ok && hit_i && hit_j;            // else excluded: contact_map.py:733-735
+            const bool acc = valid && (lo >> 31);               // else poor match: contact_map.py:737-739
+            n_ok += ok ? 1u : 0u;
+            n_valid += valid ? 1u : 0u;
+            n_acc += acc ? 1u : 0u;                             // contact_map.py:796
+            ixv[k] = ix;
+            jxv[k] = jx;
+            accv[k] = acc;
         }
-        {
-            unsigned wtot = 0;
 #pragma unroll
-            for (int k = 0; k < CLS_RPT; ++k) wtot += __popc(offm[k]);
-            if (wtot) {
-                unsigned at = 0;
-                if (lane == 0) at = atomicAdd(&s_cnt[buf], wtot);
-                at = __shfl_sync(kFullMask, at, 0);
-#pragma unroll
-                for (int k = 0; k < CLS_RPT; ++k) {
-                    if ((offm[k] >> lane) & 1u) s_stage[at + __popc(offm[k] & lt)] = (stage_t)keyv[k];
-                    at += __popc(offm[k]);
-                }
+        for (int k = 0; k < CLS_RPT; ++k) {
+            const uint32_t ix = ixv[k], jx = jxv[k];
+            const bool same = ix == jx;
+            if (accv[k] && same) {
+                if (SMEM_DIAG) atomicAdd(&s_diag[ix], 1u);
+                else atomicAdd(&P.diag[ix], 1u);
             }
+            const uint32_t a = min(ix, jx), c = max(ix, jx);    // contact_map.py:774-777
+            keyv[k] = ((uint64_t)a << P.b) | c;
+            offm[k] = __ballot_sync(kFullMask, accv[k] && !same);
         }
-        __syncthreads();
-        const unsigned total = s_cnt[buf];
-        if (threadIdx.x == 0 && total) s_base[buf] = atomicAdd(&P.ctr[C_NKEYS], (unsigned long long)total);
-        __syncthreads();
-        if (threadIdx.x == 0) s_cnt[buf] = 0;       // everybody read `total` before the barrier above
-        if (total) {
-            const unsigned long long gb = s_base[buf];
-            if ((int64_t)(gb + total) <= P.cap) {
-                for (unsigned i = threadIdx.x; i < total; i += CLS_THREADS) P.keys[gb + i] = (uint64_t)s_stage[i];
-            } else if (threadIdx.x == 0) {
-                P.ctr[C_OVERFLOW] = 1;
-            }
-        }
-        if (!P.dbl) __syncthreads();                // one buffer: the flush must finish before the next tile stages
+        unsigned wtot = 0;
 #pragma unroll
-        for (int l = 0; l < CLS_RPT / 2; ++l) {
-            v[l] = vn[l];
-            vn[l] = vnn[l];
+        for (int k = 0; k < CLS_RPT; ++k) wtot += __popc(offm[k]);
+        if (cnt + wtot > (unsigned)P.cap_w) flush();            // warp-uniform
+        unsigned at = cnt;
+#pragma unroll
+        for (int k = 0; k < CLS_RPT; ++k) {
+            if ((offm[k] >> lane) & 1u) s_stage[at + __popc(offm[k] & lt)] = (stage_t)keyv[k];
+            at += __popc(offm[k]);
+        }
+        cnt = at;
+#pragma unroll
+        for (int h = 0; h < CLS_RPT / 2; ++h) {
+            v[h] = vn[h];
+            vn[h] = vnn[h];
         }
         okm = okn;
         okn = oknn;
     }
+    if (cnt) flush();
 
     if (SMEM_DIAG) {
+        __syncthreads();
         for (int i = threadIdx.x; i < P.n_seq; i += CLS_THREADS) {
             const uint32_t c = s_diag[i];
             if (c) atomicAdd(&P.diag[i], c);
         }
     }
     // counters: warp reduce, then one atomic per warp
+    n_ok = warp_sum(n_ok);
+    n_valid = warp_sum(n_valid);
     n_acc = warp_sum(n_acc);
-    n_excl = warp_sum(n_excl);
-    n_poor = warp_sum(n_poor);
     if (lane == 0) {
         if (n_acc) atomicAdd(&P.ctr[C_ACCEPT], (unsigned long long)n_acc);
-        if (n_excl) atomicAdd(&P.ctr[C_EXCL], (unsigned long long)n_excl);
-        if (n_poor) atomicAdd(&P.ctr[C_POOR], (unsigned long long)n_poor);
+        if (n_ok - n_valid) atomicAdd(&P.ctr[C_EXCL], (unsigned long long)(n_ok - n_valid));
+        if (n_valid - n_acc) atomicAdd(&P.ctr[C_POOR], (unsigned long long)(n_valid - n_acc));
     }
 }
 
-template <bool SMEM_DIAG, bool SMEM_RANK>
+template <bool SMEM_DIAG, int SMEM_RANK>
 __global__ void __launch_bounds__(CLS_THREADS, 1) k_classify(ClsParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     // the rank table is only valid when the tid->index map is the dense rank map (checked on device)
     const bool rank_ok = SMEM_RANK && (P.ctr[C_LUT_OK] != 0);
-    if (rank_ok) classify_tiles<SMEM_DIAG, true>(P, smem);
-    else classify_tiles<SMEM_DIAG, false>(P, smem);
+    if (rank_ok) classify_tiles<SMEM_DIAG, SMEM_RANK>(P, smem);
+    else classify_tiles<SMEM_DIAG, 0>(P, smem);
 }
 
 // an overflowed key buffer must not be sorted: drop the keys, keep the flag (reported by reduce)
@@ -1211,7 +1277,7 @@ __global__ void k_shard_collect(Peers P, int rank, int G, int64_t o_ctl, int64_t
     }
 }
 
-template <bool A, bool B>
+template <bool A, int B>
 static int launch_classify(const AccumState &st, const ClsParams &P, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -1347,12 +1413,16 @@ static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int
     P.keys = (uint64_t *)(ws + st.o_keys_a);
     P.cap = st.cap;
     P.ctr = (unsigned long long *)(ws + st.o_ctr);
-    P.dbl = st.cls_dbl ? 1 : 0;
+    P.cap_w = st.cls_cap_w;
     cudaStream_t s = (cudaStream_t)stream;
-    if (st.smem_diag && st.smem_rank) return launch_classify<true, true>(st, P, s);
-    if (st.smem_diag) return launch_classify<true, false>(st, P, s);
-    if (st.smem_rank) return launch_classify<false, true>(st, P, s);
-    return launch_classify<false, false>(st, P, s);
+    if (st.smem_diag) {
+        if (st.smem_rank == 2) return launch_classify<true, 2>(st, P, s);
+        if (st.smem_rank == 1) return launch_classify<true, 1>(st, P, s);
+        return launch_classify<true, 0>(st, P, s);
+    }
+    if (st.smem_rank == 2) return launch_classify<false, 2>(st, P, s);
+    if (st.smem_rank == 1) return launch_classify<false, 1>(st, P, s);
+    return launch_classify<false, 0>(st, P, s);
 }
 
 int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream) {
