@@ -317,6 +317,25 @@ class ContactMap(object):
         state['_dev'] = {}
         return state
 
+    def __setstate__(self, state):
+        """Accepts this package's own state and a STOCK bin3C ContactMap's attribute dict (contact_map.py:492-518:
+        `seq_map` / `processed_map` as plain attributes; io_utils.load_object maps the classes)."""
+        from .io_utils import unstock
+        state = dict(state)
+        host = dict(state.pop('_host', None) or {})
+        for k in ('seq_map', 'processed_map'):
+            if k in state:
+                host[k] = state.pop(k)
+        state['_host'] = {k: unstock(v) for k, v in host.items()}
+        state['_dev'] = {}
+        if 'extent_map' in state:
+            state['extent_map'] = unstock(state['extent_map'])
+        self.__dict__.update(state)
+        self.__dict__.setdefault('pair_counts', None)
+        self.__dict__.setdefault('kr_info', None)
+        if 'n_refs' not in self.__dict__ and self.__dict__.get('seq_info'):
+            self.n_refs = max(si.refid for si in self.seq_info) + 1      # a stock map does not keep the table size
+
     @property
     def seq_map(self):
         """coo_matrix[uint32], symmetric, canonical row-major -- what get_coo() returns (Q10)."""

@@ -505,6 +505,14 @@ def test_contact_map_end_to_end(dev, golden):
     assert cm2._dev == {} and np.array_equal(cm2.seq_map.data, g['map_data'])
     assert _relerr(cm2.processed_map.tocsr().data, g['bal_data']) <= REL_TOL
 
+    # the stock-layout stream (io_utils.save_object(stock=True)) read back: the map a `cluster` stage
+    # would start from gives the same edges
+    from bin3c_b200 import io_utils
+    cm3 = io_utils.loads(io_utils.dumps_stock(cm))
+    assert cm3._dev == {} and np.array_equal(cm3.seq_map.data, g['map_data'])
+    u3, v3, w3, scl3 = cluster.to_edges(cm3, norm=True, bisto=True, scale=True)
+    assert np.array_equal(u3, u) and np.array_equal(v3, v) and np.array_equal(w3, w) and scl3 == scl
+
 
 def test_bam_file_to_edge_file(dev, tmp_path):
     """
