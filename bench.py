@@ -446,9 +446,13 @@ def run_single_gpu(work, args, torch, dev, local_rank, steps, warmup, want_cpu, 
     roof_kr = {'kernel': 'k_kr_persistent', 'bound': 'hbm', 'achieved': kr_bytes / (t_kr * 1e-3) / 1e9, 'peak': peak,
                'unit': 'GB/s', 'frac': kr_bytes / (t_kr * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
                'bytes_per_launch': kr_bytes, 'ms_per_launch': t_kr,
-               'note': '{} SpMV x (12*nnz + 24*N) B per launch (SURVEY 8d formula; the kernel streams 10 B per entry), '
-                       'vector phases and grid barriers are inside the launch but add no counted bytes; {}'.format(
-                           kr['n_spmv'], l2_note)}
+               'note': '{} SpMV x (12*nnz + 24*N) B per launch (SURVEY 8d formula: what a CSR SpMV has to move; the kernel '
+                       'streams {} B per entry, see streamed_gbs), vector phases and grid barriers are inside the launch '
+                       'but add no counted bytes; {}'.format(kr['n_spmv'], kr.get('stream_bytes_per_entry', 0), l2_note)}
+    # what the kernel's own operand stream amounts to (entries incl. padding x bytes per entry + the vectors), per launch
+    streamed = kr['n_spmv'] * (kr['nnz_stream'] * kr.get('stream_bytes_per_entry', 0) + 24 * N)
+    roof_kr['streamed_bytes_per_launch'] = streamed
+    roof_kr['streamed_gbs'] = streamed / (t_kr * 1e-3) / 1e9
     roof_cls = {'kernel': 'k_classify', 'bound': 'hbm', 'achieved': cls_bytes / (t_cls * 1e-3) / 1e9, 'peak': peak,
                 'unit': 'GB/s', 'frac': cls_bytes / (t_cls * 1e-3) / 1e9 / peak, 'traffic': None,
                 'peak_source': peak_src, 'bytes_per_launch': cls_bytes, 'ms_per_launch': t_cls,
@@ -509,6 +513,7 @@ def run_single_gpu(work, args, torch, dev, local_rank, steps, warmup, want_cpu, 
         'kr': {'n_iter': kr['n_iter'], 'n_spmv': kr['n_spmv'], 'outer': kr['outer'], 'zero_diag': kr['zero_diag'],
                'spmv_gbs_by_formula': roof_kr['achieved'], 'kernel_ms': t_kr, 'stage_ms': stage_ms.get('kr'),
                'slabs': kr['slabs'], 'stream_entries': kr['nnz_stream'], 'segments': kr['segments'],
+               'stream_bytes_per_entry': kr.get('stream_bytes_per_entry'),
                'spmv_phase_gbs': (spmv_bytes * kr['n_spmv'] / 1e9) /
                                  max((kr['work_cycles']['spmv'] + kr['sync_cycles']['spmv']) / (sm_mhz * 1e6), 1e-12)},
         'pair_counts': {k: info[k] for k in ('accepted', 'ref_excluded', 'poor_match')},

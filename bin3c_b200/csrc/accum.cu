@@ -46,7 +46,7 @@ struct AccumState {
     int64_t rank_words = 0;   // 64-bit words of the tid bitmap
     bool smem_diag = false;
     int smem_rank = 0;        // 0 gather, 1 pair table, 2 packed table (classify_tiles)
-    int cls_smem = 0, cls_grid = 0, cls_cap_w = 0;
+    int cls_smem = 0, cls_grid = 0, cls_cap_w = 0, cls_diag_k = 0;
     const int32_t *d_lut = nullptr;
     int64_t o_ctr, o_diag, o_bits, o_pref, o_keys_a, o_keys_b, o_uniq, o_pos, o_cnt, o_hist, o_heads,
         o_up_ptr, o_lo_ptr, o_len, o_indptr_f, o_indptr_u, o_scan_tmp, o_tmp64, total;
@@ -145,7 +145,16 @@ static void plan(AccumState &st, int64_t cap, int32_t n_seq, int32_t n_refs) {
         fixed = rb;
     }
     st.cls_cap_w = cap_w(fixed, kb);
-    st.cls_smem = (int)((int64_t)CLS_WARPS * st.cls_cap_w * kb + fixed);
+    st.cls_diag_k = 0;
+    if (!st.smem_diag) {
+        // a partial diagonal histogram in what is left beside the smallest staging, if it covers >= 5 % of the contigs
+        const int64_t room = (SMEM_MAX - fixed - (int64_t)CLS_WARPS * CLS_WTILE * kb) / 4;
+        if (room >= (int64_t)n_seq / 20 && room > 0) {
+            st.cls_cap_w = CLS_WTILE;
+            st.cls_diag_k = (int)(room < n_seq ? room : n_seq);
+        }
+    }
+    st.cls_smem = (int)((int64_t)CLS_WARPS * st.cls_cap_w * kb + fixed + (int64_t)st.cls_diag_k * 4);
     st.cls_grid = kNumSMs;      // persistent: one 1024-thread CTA per SM, tiles strided over the grid
     layout(st);
 }
@@ -195,6 +204,7 @@ struct ClsParams {
     int64_t cap;
     unsigned long long *ctr;
     int cap_w;               // staging keys per warp
+    int diag_k;              // without SMEM_DIAG: the first diag_k contigs' diagonal counters are in shared memory
 };
 
 // Every warp runs on its own: its own stream of 128-record warp tiles (strided over all warps of the grid, loads
@@ -250,9 +260,12 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
         if (threadIdx.x == 0) tab[nw12] = 0u;
         s_tab32 = tab;
     }
+    // diagonal counters of the first `dk` contigs live in shared memory (all of them with SMEM_DIAG; else as many as
+    // fit beside the table and the staging: every one of them is a global RED less, and at C3 the kernel runs at
+    // the rate the L2 retires the diagonal REDs -- 333M of them, ~140 G/s)
     uint32_t *s_diag = reinterpret_cast<uint32_t *>(cur);
-    if (SMEM_DIAG)
-        for (int i = threadIdx.x; i < P.n_seq; i += CLS_THREADS) s_diag[i] = 0;
+    const uint32_t dk = SMEM_DIAG ? (uint32_t)P.n_seq : (uint32_t)P.diag_k;
+    for (uint32_t i = threadIdx.x; i < dk; i += CLS_THREADS) s_diag[i] = 0;
     __syncthreads();
 
     unsigned n_ok = 0, n_valid = 0, n_acc = 0;
@@ -394,7 +407,7 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
             const uint32_t ix = ixv[k], jx = jxv[k];
             const bool same = ix == jx;
             if (accv[k] && same) {
-                if (SMEM_DIAG) atomicAdd(&s_diag[ix], 1u);
+                if (SMEM_DIAG || ix < dk) atomicAdd(&s_diag[ix], 1u);
                 else atomicAdd(&P.diag[ix], 1u);
             }
             const uint32_t a = min(ix, jx), c = max(ix, jx);    // contact_map.py:774-777
@@ -422,9 +435,9 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
     }
     if (cnt) flush();
 
-    if (SMEM_DIAG) {
+    if (dk) {
         __syncthreads();
-        for (int i = threadIdx.x; i < P.n_seq; i += CLS_THREADS) {
+        for (uint32_t i = threadIdx.x; i < dk; i += CLS_THREADS) {
             const uint32_t c = s_diag[i];
             if (c) atomicAdd(&P.diag[i], c);
         }
@@ -1414,6 +1427,7 @@ static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int
     P.cap = st.cap;
     P.ctr = (unsigned long long *)(ws + st.o_ctr);
     P.cap_w = st.cls_cap_w;
+    P.diag_k = st.cls_diag_k;
     cudaStream_t s = (cudaStream_t)stream;
     if (st.smem_diag) {
         if (st.smem_rank == 2) return launch_classify<true, 2>(st, P, s);

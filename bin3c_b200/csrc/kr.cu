@@ -68,6 +68,7 @@ struct KRScalars {
     double tol, delta, Delta, rt, stop_tol;
     double rho_km1, rho_km2, rout, rold, eta, inner_tol, alpha, beta, gamma;
     long long n_iter, max_iter, k, outer, n_spmv, zero_diag;
+    long long ovf16;           // the count pass met an off-diagonal count above 65535: the packed stream cannot hold the matrix
     int status, ymode, ysel, state;
 };
 
@@ -114,7 +115,11 @@ struct KRArgs {
     // site normalisation is factored out of the sum, (A u)_i = (1/s_i) sum_j c_ij (u_j / s_j): the SpMV multiplies the
     // SCALED operand us = u / s (xs = x / s for a residual), rows_q applies 1/s_i.  Same sums as the reference's
     // sum_j (c_ij / (s_i s_j)) u_j up to rounding of the factors (x moves ~1e-15, far inside the 1e-9 bar).
-    int32_t cnt_stream;        // 1: sval is uint32[nnzv]
+    int32_t cnt_stream;        // 1: sval is uint32[nnzv]; 2 (slab form): sval is uint32[nnzv] of PACKED entries, the 16-bit
+                               // count in the high half and the 16-bit slab-local column in the low half -- 4 B per entry,
+                               // one 32-byte load per lane and piece.  The high part of a DIAGONAL count above 65535 goes
+                               // into dfix (a term coefficient * operand_i added by rows_q); an off-diagonal count above
+                               // 65535 is detected by the count pass and the stream falls back to form 1
     const double *inv_s;       // [n] 1 / s_j (zero site counts taken as one, Q6)
     double *us, *xs;           // scaled operands (length n; xs lives beside x, in the exchange buffer in peer mode)
     // the stream
@@ -163,7 +168,8 @@ struct KRArgs {
     long long *cta_spmv;                        // [n_bnd] cycles every CTA spent inside its SpMV phases
     unsigned long long *ll;                     // [P_COUNT][n_chunks][2] flagged words: partials exchanged without a barrier
 };
-enum { KR_OPT_BANK_ORDER = 1, KR_OPT_SLAB_ALIGN = 2, KR_OPT_FAST_BARRIER = 4, KR_OPT_LL_PARTIALS = 8, KR_OPT_PEER_LL_W = 16 };
+enum { KR_OPT_BANK_ORDER = 1, KR_OPT_SLAB_ALIGN = 2, KR_OPT_FAST_BARRIER = 4, KR_OPT_LL_PARTIALS = 8, KR_OPT_PEER_LL_W = 16,
+       KR_OPT_L2_PREFETCH = 32, KR_OPT_L2_PREFETCH_FAR = 64 };
 
 // What crosses the NVLink in peer mode: the owner of row r writes x[r] (once per Newton update) and Z[r] (once per CG
 // step) straight into every rank's copy, and its chunk partials likewise.  Every rank then derives p and u = x * p for
@@ -390,13 +396,14 @@ struct PieceRegs {
     int seg0;                  // first piece only: ordinal of the first segment that starts inside the chunk
 };
 
-template <bool SLAB, bool CNT>
+template <bool SLAB, int CNT>
 __device__ __forceinline__ void piece_load(const KRArgs &A, int64_t p, int64_t p_hi, PieceRegs &R) {
     if (p >= p_hi) return;
     const int64_t chunk = p >> 1;
     const int64_t e = chunk * SPMV_CHUNK + (p & 1) * (SPMV_CHUNK / 2) + SPMV_EPP * lane_id();
     if (CNT) {
-        // eight uint32 counts (one 32-byte load), widened when the piece is processed
+        // eight uint32 counts -- or, packed form, eight (count << 16 | column) words -- in one 32-byte load, widened when
+        // the piece is processed
         asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                      : "=l"(R.q[0]), "=l"(R.q[1]), "=l"(R.q[2]), "=l"(R.q[3])
                      : "l"((const uint32_t *)A.sval + e));
@@ -408,7 +415,9 @@ __device__ __forceinline__ void piece_load(const KRArgs &A, int64_t p, int64_t p
                      : "=d"(R.a[4]), "=d"(R.a[5]), "=d"(R.a[6]), "=d"(R.a[7])
                      : "l"(A.sval + e + 4));
     }
-    if (SLAB) {
+    if (CNT == 2) {
+        // the columns came with the counts
+    } else if (SLAB) {
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(R.c[0]), "=r"(R.c[1]), "=r"(R.c[2]), "=r"(R.c[3])
                      : "l"((const uint16_t *)A.scol + e));
@@ -426,6 +435,18 @@ __device__ __forceinline__ void piece_load(const KRArgs &A, int64_t p, int64_t p
         R.fw = fw;
         R.seg0 = __ldg(A.chunk_seg0 + chunk);
     }
+}
+
+// L2 prefetch of the stream `dist` chunks ahead of the chunk a warp is about to process (KR_OPT_L2_PREFETCH: 6 chunks,
+// + KR_OPT_L2_PREFETCH_FAR: 12 more): the register ring covers ~1.5 chunks, less than the DRAM latency under load --
+// the SpMV's largest stall was the wait for a piece's own load -- so the ring's loads should find their lines in L2.
+template <bool SLAB, int CNT>
+__device__ __forceinline__ void chunk_prefetch(const KRArgs &A, int64_t chunk, int64_t chunk_hi) {
+    if (chunk >= chunk_hi || lane_id() != 0) return;
+    const char *v = (const char *)A.sval + chunk * SPMV_CHUNK * (CNT ? 4 : 8);
+    const char *c = (const char *)A.scol + chunk * SPMV_CHUNK * (SLAB ? 2 : 4);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(v), "r"(SPMV_CHUNK * (CNT ? 4 : 8)) : "memory");
+    if (CNT != 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c), "r"(SPMV_CHUNK * (SLAB ? 2 : 4)) : "memory");
 }
 
 // bring slab `slab` of u into shared memory: one thread issues TMA bulk copies, everybody waits on the mbarrier
@@ -461,7 +482,7 @@ struct LaneRun {
 };
 
 // One piece: 8 products per lane, added to the lane's running segment; a start flag closes the open segment.
-template <bool SLAB, bool CNT>
+template <bool SLAB, int CNT>
 __device__ __forceinline__ void piece_process(const KRArgs &A, const double *u, const PieceRegs &R, const Smem &sm,
                                               bool first_piece, LaneRun &L) {
     const unsigned lane = lane_id();
@@ -481,6 +502,14 @@ __device__ __forceinline__ void piece_process(const KRArgs &A, const double *u, 
         L.nseen = 0;
     }
     double x[SPMV_EPP], a[SPMV_EPP];
+    if (CNT == 2) {
+        const double *su = sm.u;
+#pragma unroll
+        for (int i = 0; i < SPMV_EPP; ++i) {
+            const uint32_t w = (uint32_t)(R.q[i >> 1] >> ((i & 1) * 32));
+            x[i] = __dmul_rn((double)(w >> 16), su[w & 0xffffu]);
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < SPMV_EPP; ++i)
         a[i] = CNT ? (double)(uint32_t)(R.q[i >> 1] >> ((i & 1) * 32)) : R.a[i];
@@ -494,6 +523,7 @@ __device__ __forceinline__ void piece_process(const KRArgs &A, const double *u, 
     } else {
 #pragma unroll
         for (int i = 0; i < SPMV_EPP; ++i) x[i] = __dmul_rn(a[i], u[R.c[i]]);
+    }
     }
     // segments are padded to whole pieces (seg_padded), so only the piece's first entry can carry a flag:
     // add the piece up as a fixed tree, then either extend the open segment or close it and open the next
@@ -602,7 +632,7 @@ __device__ __forceinline__ void part_stitch(const KRArgs &A, const Smem &sm, int
 // The SpMV phase.  The CTA owns a contiguous range of chunks; it is cut into parts at slab boundaries
 // (almost always one part), and inside a part every warp streams its own contiguous run of chunks with no
 // block-wide synchronisation; the runs are stitched once per part.
-template <bool SLAB, bool CNT>
+template <bool SLAB, int CNT>
 __device__ __forceinline__ void phase_spmv(const KRArgs &A, const double *u, Smem &sm) {
     for (int i = threadIdx.x; i <= A.S; i += KR_THREADS) sm.slab[i] = A.slab_c0[i];
     if (threadIdx.x == 0) {
@@ -670,7 +700,16 @@ __device__ __forceinline__ void phase_spmv(const KRArgs &A, const double *u, Sme
         int first = 0;
         if (q_lo < q_hi) first = R0.seg0;
         // the ring has three stages and a chunk two pieces: six pieces (three chunks) per trip keep every index static
+        const int pf_dist = ((A.opts & KR_OPT_L2_PREFETCH) ? 6 : 0) + ((A.opts & KR_OPT_L2_PREFETCH_FAR) ? 12 : 0);
+        if (pf_dist)
+            for (int d = 2; d < pf_dist; ++d) chunk_prefetch<SLAB, CNT>(A, w_lo + d, w_hi);
         for (int64_t q = q_lo; q < q_hi; q += 6) {
+            if (pf_dist) {
+                const int64_t ck = (q >> 1) + pf_dist;
+                chunk_prefetch<SLAB, CNT>(A, ck, w_hi);
+                chunk_prefetch<SLAB, CNT>(A, ck + 1, w_hi);
+                chunk_prefetch<SLAB, CNT>(A, ck + 2, w_hi);
+            }
             piece_process<SLAB, CNT>(A, u, R0, sm, true, L);
             piece_load<SLAB, CNT>(A, q + 3, q_hi, R0);
             piece_process<SLAB, CNT>(A, u, R1, sm, false, L);
@@ -795,7 +834,8 @@ __device__ __forceinline__ void rows_q_batched(const KRArgs &A, const double *op
         for (int k = 0; k < NB; ++k)
             if (o[i][k] >= 0) s = __dadd_rn(s, t[i][k]);
         if (A.cnt_stream) s = __dmul_rn(s, is[i]);                 // counts stream: the row's 1 / s_i
-        if (df[i] != 0.0) s = __dadd_rn(s, uu[i]);                 // zero diagonal counted as one (Q2)
+        if (df[i] != 0.0) s = __dadd_rn(s, __dmul_rn(df[i], uu[i]));   // zero diagonal counted as one (Q2): df = 1; or the
+                                                                    // high part of a packed diagonal count (KRArgs.cnt_stream)
         qq[i] = s;
     }
 }
@@ -811,7 +851,8 @@ __device__ __forceinline__ void rows_q(const KRArgs &A, const double *opnd, int 
         if (r < A.row_hi) {
             qq[i] = row_q(A, r);
             if (A.cnt_stream) qq[i] = __dmul_rn(qq[i], __ldg(A.inv_s + r));
-            if (__ldcg(A.dfix + r) != 0.0) qq[i] = __dadd_rn(qq[i], __ldcg(opnd + r));
+            const double df = __ldcg(A.dfix + r);
+            if (df != 0.0) qq[i] = __dadd_rn(qq[i], __dmul_rn(df, __ldcg(opnd + r)));
         }
     }
 }
@@ -1279,7 +1320,7 @@ __device__ __forceinline__ void kr_barrier(const KRArgs &A, bool cross, unsigned
         if (timing) tim_work[T_SCALAR] += clock64() - ts_;                     \
     } while (0)
 
-template <bool SLAB, bool CNT>
+template <bool SLAB, int CNT>
 __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem sm = carve_smem(smem_raw);
@@ -1392,7 +1433,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
     // col / W as a multiplication: with Wm = ceil(2^40 / W) the quotient is exact while col * W < 2^40 (col < 2^21, W < 2^15)
     // (slab form); with a single slab (the gather form, W = n) the multiplier is 0 and every column is in slab 0
     const uint64_t Wm = A.S == 1 ? 0ull : ((1ull << 40) + (uint64_t)W - 1) / (uint64_t)W;
-    bool bad = false;
+    bool bad = false, bad16 = false;
     for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < n_local; lr += nw) {
         const int64_t lo = A.indptr[lr], hi = A.indptr[lr + 1];
         const int32_t s_row = (FILL && A.cnt32) ? A.sites[A.row_lo + lr] : 1;
@@ -1400,7 +1441,8 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
         int64_t carry_start = lo;
         // software pipeline over the 32-entry windows: columns and counts are loaded two windows ahead, the site
         // count of a column (a scattered gather that needs the column first) one window ahead
-        const bool want_cnt = FILL && A.cnt32 != nullptr;
+        // the count pass of a packed stream looks at the counts too: an off-diagonal count above 65535 does not fit
+        const bool want_cnt = (FILL || A.cnt_stream == 2) && A.cnt32 != nullptr;
         const bool want_site = want_cnt && !A.cnt_stream;       // the counts stream stores the counts themselves
         int col_a = (lo + lane < hi) ? A.indices[lo + lane] : 0;
         int col_b = (lo + 32 + lane < hi) ? A.indices[lo + 32 + lane] : 0;
@@ -1425,6 +1467,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 bad = true;
                 col = col < 0 ? 0 : A.n - 1;
             }
+            if (!FILL && A.cnt_stream == 2 && valid && cnt_e > 0xffffu && col != A.row_lo + (int)lr) bad16 = true;
             const int s = valid ? (int)(((uint64_t)col * Wm) >> 40) : 0x7fffffff;      // col / W
             int sp = __shfl_up_sync(kFullMask, s, 1);
             if (lane == 0) sp = carry_s;
@@ -1459,10 +1502,12 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
                 const int64_t seg_start = upto ? e0 + (31 - __clz(upto)) : carry_start;
                 const int64_t dst = A.vp[(int64_t)s * A.npad + lr] + (e - seg_start);
                 const int64_t ph = stream_phys(dst);
-                if (A.cnt_stream) ((uint32_t *)sval)[ph] = cnt_e;
-                else sval[ph] = A.cnt32 ? site_scaled(cnt_e, s_row, site_e) : A.data[e];
                 const unsigned lc = (unsigned)(col - s * W);
-                if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
+                if (A.cnt_stream == 2) ((uint32_t *)sval)[ph] = (cnt_e << 16) | lc;      // low 16 bits of the count | column
+                else if (A.cnt_stream) ((uint32_t *)sval)[ph] = cnt_e;
+                else sval[ph] = A.cnt32 ? site_scaled(cnt_e, s_row, site_e) : A.data[e];
+                if (A.cnt_stream == 2) {}
+                else if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
                 else ((uint32_t *)scol_v)[ph] = lc;
                 if (e == seg_start) stream_set_flag(sflag, dst);
                 // the segment's last entry also writes its padding (zero value, column 0) up to a whole piece
@@ -1485,6 +1530,7 @@ __global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restri
         if (!FILL && hi > lo && lane == 0) cnt[(int64_t)carry_s * A.npad + lr] = seg_padded(hi - carry_start);
     }
     if (!FILL && bad) A.ctl->status = B3C_ERR_ARG;     // unsorted or out-of-range columns
+    if (!FILL && bad16) A.ctl->ovf16 = 1;
 }
 
 // one CTA per slab: pad the slab's entry count to whole tiles (the padding belongs to its last cell)
@@ -1629,7 +1675,8 @@ __global__ void __launch_bounds__(256) k_chunk_seg0(int64_t n_chunks, int64_t nv
 __global__ void __launch_bounds__(256) k_diag_fix(int32_t row_lo, int32_t row_hi, const int64_t *__restrict__ indptr,
                                                   const int32_t *__restrict__ indices, const double *__restrict__ data,
                                                   const uint32_t *__restrict__ cnt32, const int32_t *__restrict__ sites,
-                                                  double *__restrict__ dfix, KRScalars *ctl) {
+                                                  double *__restrict__ dfix, KRScalars *ctl, int packed,
+                                                  const double *__restrict__ inv_s) {
     // One thread per row: the columns of a row are sorted (k_stream_rows rejects the matrix otherwise), so the
     // diagonal is found by bisection instead of walking the row.
     const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1645,10 +1692,16 @@ __global__ void __launch_bounds__(256) k_diag_fix(int32_t row_lo, int32_t row_hi
             else hi = mid;
         }
         double d = 0.0;           // duplicates of the diagonal would be summed by scipy's diagonal()
-        for (int64_t e = lo; e < end && indices[e] == gr; ++e)
+        double hi16 = 0.0;        // packed stream: what the 16-bit counts of the diagonal entries leave out
+        for (int64_t e = lo; e < end && indices[e] == gr; ++e) {
             d += cnt32 ? site_scaled(cnt32[e], sites[gr], sites[gr]) : data[e];
+            if (packed) hi16 += (double)(cnt32[e] & 0xffff0000u);
+        }
         z = (d == 0.0);
-        dfix[gr] = z ? 1.0 : 0.0;
+        // rows_q adds dfix * operand_i: 1 for a zero diagonal (Q2); (high part of c_ii) / s_i^2 in the packed form
+        double f = z ? 1.0 : 0.0;
+        if (packed && hi16 != 0.0) f = __dmul_rn(__dmul_rn(hi16, inv_s[gr]), inv_s[gr]);
+        dfix[gr] = f;
     }
     const unsigned nz = __popc(__ballot_sync(kFullMask, z));
     if (lane_id() == 0 && nz) atomicAdd((unsigned long long *)&ctl->zero_diag, (unsigned long long)nz);
@@ -1663,7 +1716,7 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_spmv(KRArgs A) {
         if (threadIdx.x == 0) mbar_init(sm.mbar, 1);
         __syncthreads();
     }
-    phase_spmv<SLAB, false>(A, A.u, sm);
+    phase_spmv<SLAB, 0>(A, A.u, sm);
 }
 // y[r] = (A u)[r] (b3c_spmv): one CTA per reduction chunk
 __global__ void __launch_bounds__(KR_THREADS) k_spmv_collect(KRArgs A, double *__restrict__ y) {
@@ -1759,7 +1812,7 @@ static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
 // KR_OPT_BANK_ORDER stays off too: the reordering pass costs 91 us at C2 and saves 0.5 us per SpMV, so it would
 // only pay for solves of more than ~180 SpMV (typical: 24-40)
 // B3C_OPT_KR_COUNT_STREAM: the counts form streams uint32 counts (6 B per entry) instead of fp64 values (10 B)
-static std::atomic<int> g_cnt_stream{1};
+static std::atomic<int> g_cnt_stream{2};
 static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER | KR_OPT_PEER_LL_W};
 constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
 
@@ -1909,11 +1962,12 @@ static int persistent_grid_of(int *grid_out) {
         const int smem = SLAB ? SM_BYTES_SLAB : SM_BYTES_GATHER;
         B3C_CUDA(cudaGetDevice(&dev));
         B3C_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<SLAB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<SLAB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<SLAB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<SLAB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (SLAB) B3C_CUDA(cudaFuncSetAttribute(k_kr_persistent<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         B3C_CUDA(cudaFuncSetAttribute(k_spmv<SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kr_persistent<SLAB, false>, KR_THREADS, smem));
-        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_kr_persistent<SLAB, true>, KR_THREADS, smem));
+        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kr_persistent<SLAB, 0>, KR_THREADS, smem));
+        B3C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_kr_persistent<SLAB, 1>, KR_THREADS, smem));
         if (per_sm < 1 || per_sm_c < 1) {
             set_error("persistent KR kernel does not fit on an SM");
             return B3C_ERR_CUDA;
@@ -1975,6 +2029,7 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
         set_error("KR: column indices must be sorted within rows and lie in [0, n)");
         return B3C_ERR_ARG;
     }
+    if (A.cnt_stream == 2 && S.ovf16) A.cnt_stream = 1;        // an off-diagonal count above 65535: 32-bit counts
     if (totals[0] > L.nnzv_max || totals[0] % SPMV_TILE != 0 || totals[1] > L.nseg_max) {
         set_error("stream layout: %lld entries, %lld segments (capacity %lld, %lld)", (long long)totals[0],
                   (long long)totals[1], (long long)L.nnzv_max, (long long)L.nseg_max);
@@ -2000,7 +2055,7 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     }
     B3C_CUDA(cudaMemsetAsync(A.qs, 0, (size_t)(A.n_seg + 1) * 8, s));
     k_diag_fix<<<(unsigned)ceil_div(n_local > 0 ? n_local : 1, 256), 256, 0, s>>>(A.row_lo, A.row_hi, A.indptr, A.indices, A.data, A.cnt32, A.sites,
-                                                              A.dfix, A.ctl);
+                                                              A.dfix, A.ctl, A.cnt_stream == 2 ? 1 : 0, A.inv_s);
     B3C_LAUNCH_CHECK();
     rc = persistent_grid(SLAB, &A.n_bnd);
     return rc;
@@ -2044,11 +2099,11 @@ int b3c_set_option(int32_t key, int64_t value) {
             g_slab_s_max.store((int)value);
             return B3C_OK;
         case B3C_OPT_KR_FLAGS:
-            B3C_REQUIRE(value >= 0 && value <= 31, "KR option flags must be in [0, 31]");
+            B3C_REQUIRE(value >= 0 && value <= 127, "KR option flags must be in [0, 127]");
             g_kr_opts.store((int)value);
             return B3C_OK;
         case B3C_OPT_KR_COUNT_STREAM:
-            B3C_REQUIRE(value == 0 || value == 1, "count stream option is 0 or 1");
+            B3C_REQUIRE(value >= 0 && value <= 2, "count stream option is 0, 1 or 2");
             g_cnt_stream.store((int)value);
             return B3C_OK;
         case B3C_OPT_USE_GRAPHS:
@@ -2083,8 +2138,9 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     B3C_CUDA(cudaMemsetAsync(A.bar_count, 0, 256, s));
     B3C_CUDA(cudaMemsetAsync(A.ll, 0, (size_t)A.n_chunks * 16 * P_COUNT + 128, s));      // epoch 0 = never written
     B3C_CUDA(cudaEventRecord(ev[0], s));
-    void *kern = A.slab ? (A.cnt_stream ? (void *)k_kr_persistent<true, true> : (void *)k_kr_persistent<true, false>)
-                        : (A.cnt_stream ? (void *)k_kr_persistent<false, true> : (void *)k_kr_persistent<false, false>);
+    void *kern = A.slab ? (A.cnt_stream == 2 ? (void *)k_kr_persistent<true, 2>
+                                             : A.cnt_stream ? (void *)k_kr_persistent<true, 1> : (void *)k_kr_persistent<true, 0>)
+                        : (A.cnt_stream ? (void *)k_kr_persistent<false, 1> : (void *)k_kr_persistent<false, 0>);
     B3C_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(KR_THREADS), args,
                                          A.slab ? SM_BYTES_SLAB : SM_BYTES_GATHER, s));
     B3C_CUDA(cudaEventRecord(ev[1], s));
@@ -2111,6 +2167,7 @@ static int kr_launch_collect(KRArgs &A, int32_t max_iter, double *d_x, int64_t *
     h_info[24] = A.slab ? A.S : 0;
     h_info[25] = A.nnzv;
     h_info[26] = A.n_seg;
+    h_info[31] = A.cnt_stream == 2 ? 4 : A.cnt_stream ? (A.slab ? 6 : 8) : (A.slab ? 10 : 12);      // stream bytes per entry
     h_info[27] = (int64_t)(ms * 1000.0f + 0.5f);       // the persistent kernel alone, microseconds (CUDA events)
     {
         long long mn = cta[0], mx = cta[0], sum = 0;
@@ -2157,7 +2214,7 @@ static int kr_run_impl(int32_t n, int64_t nnz, const int64_t *d_indptr, const in
     kr_bind(A, L, (char *)d_ws, n, 0, n, nnz, d_indptr, d_indices, d_data);
     A.cnt32 = d_data ? nullptr : d_counts;
     A.sites = d_data ? nullptr : d_sites;
-    A.cnt_stream = (A.cnt32 != nullptr && g_cnt_stream.load()) ? 1 : 0;
+    A.cnt_stream = (A.cnt32 != nullptr && g_cnt_stream.load()) ? ((g_cnt_stream.load() == 2 && A.slab) ? 2 : 1) : 0;
     KRScalars S;
     kr_scalars_init(S, tol, delta, Delta, max_iter);
     B3C_CUDA(cudaMemcpyAsync(A.ctl, &S, sizeof(S), cudaMemcpyHostToDevice, s));
@@ -2257,7 +2314,7 @@ static int kr_run_peer_impl(int32_t n, int32_t row_lo, int32_t row_hi, int64_t n
     kr_bind(A, L, (char *)d_ws, n, row_lo, row_hi, nnz_local, d_indptr, d_indices, d_data);
     A.cnt32 = d_data ? nullptr : d_counts;
     A.sites = d_data ? nullptr : d_sites;
-    A.cnt_stream = (A.cnt32 != nullptr && g_cnt_stream.load()) ? 1 : 0;
+    A.cnt_stream = (A.cnt32 != nullptr && g_cnt_stream.load()) ? ((g_cnt_stream.load() == 2 && A.slab) ? 2 : 1) : 0;
     const XLayout X = x_layout(n);
     for (int g = 0; g < n_ranks; ++g) {
         B3C_REQUIRE(h_exchange[g] != nullptr, "null exchange buffer of rank %d", g);

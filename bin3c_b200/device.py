@@ -369,7 +369,8 @@ def kr_scale_vector(csr, tol=1e-6, delta=0.1, Delta=3, max_iter=1000, pool=None,
                work_cycles={k: int(info[6 + i]) for i, k in enumerate(names)},
                sync_cycles={k: int(info[15 + i]) for i, k in enumerate(names)},
                slabs=int(info[24]), nnz_stream=int(info[25]), segments=int(info[26]), kernel_us=int(info[27]),
-               cta_spmv_cycles=dict(min=int(info[28]), max=int(info[29]), mean=int(info[30])))
+               cta_spmv_cycles=dict(min=int(info[28]), max=int(info[29]), mean=int(info[30])),
+               stream_bytes_per_entry=int(info[31]))
     check(rc)
     return x, out
 

@@ -182,9 +182,12 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  * accumulation, hand-overs of peer-mode KR) may last before it gives up.  A time-out is reported as
  * B3C_ERR_CUDA by the next call that synchronises and the results of that run are invalid; it is cleared
  * at the start of the next run.
- * B3C_OPT_KR_COUNT_STREAM (default 1): b3c_kr_run_counts / b3c_kr_run_peer_counts stream the raw uint32 counts
- * (6 bytes per entry with the 16-bit column) and factor the site normalisation out of the row sums,
- * (A u)_i = (1/s_i) sum_j c_ij (u_j / s_j); 0 streams fp64 values c_ij / (s_i s_j) (10 bytes per entry).
+ * B3C_OPT_KR_COUNT_STREAM (default 2): b3c_kr_run_counts / b3c_kr_run_peer_counts stream the raw counts and factor
+ * the site normalisation out of the row sums, (A u)_i = (1/s_i) sum_j c_ij (u_j / s_j).  1: uint32 counts, 6 bytes
+ * per entry with the 16-bit column.  2 (slab form): packed entries, 16-bit count | 16-bit column = 4 bytes; the high
+ * part of a DIAGONAL count above 65535 (intra-contig pairs of a long contig) is applied as a per-row term, and a matrix
+ * with an OFF-diagonal count above 65535 falls back to form 1 (detected while the stream is laid out).  0 streams fp64
+ * values c_ij / (s_i s_j) (10 bytes per entry), bit-identical to the staged form.  h_info[31] reports the bytes per entry.
  * B3C_OPT_USE_GRAPHS (default 1): the sort-reduce sequences of an accumulator (~60 launches with fixed grids;
  * all sizes are read from device counters) are captured once per workspace as a CUDA graph and replayed. */
 enum { B3C_OPT_KR_SLAB_WIDTH = 1, B3C_OPT_KR_MAX_SLABS = 2, B3C_OPT_KR_FLAGS = 3, B3C_OPT_PEER_TIMEOUT_MS = 4,

@@ -765,7 +765,51 @@ def test_fused_counts_form_matches_the_staged_form(dev):
             assert np.array_equal(r_f64[k][:n].cpu().numpy(), w)
         assert np.array_equal(r_f64['scl'].cpu().numpy(), staged[3])
     finally:
-        dev.check(dev.lib.b3c_set_option(5, 1))
+        dev.check(dev.lib.b3c_set_option(5, 2))
+
+
+@pytest.mark.parametrize('offdiag_big', [False, True])
+def test_packed_count_stream_large_counts(dev, offdiag_big):
+    """The packed stream (16-bit count | 16-bit column, 4 B per entry; B3C_OPT_KR_COUNT_STREAM = 2, the default in the
+    slab form): diagonal counts above 65535 -- intra-contig pair counts of long contigs -- keep their low 16 bits in
+    the stream and their high part as a per-row term; an OFF-diagonal count above 65535 makes the build fall back to
+    32-bit counts.  Either way: n_iter equal to the oracle's and to the 32-bit stream's, x <= 1e-9 (measured
+    ~1e-15), and the stream width reported."""
+    import torch
+    from oracle import oracle
+    rng = np.random.default_rng(77)
+    n = 3000
+    up = sp.triu(sp.random(n, n, density=0.004, random_state=5, data_rvs=lambda k: rng.integers(1, 400, size=k)), 1).tocsr()
+    diag = rng.integers(0, 3000, size=n).astype(np.int64)
+    diag[[3, 70, 71, 500, 2999]] = [65535, 65536, 65537, 4_000_000_000, 1_234_567]
+    if offdiag_big:
+        up = up.tolil()
+        up[10, 2000] = 70000
+        up[11, 12] = 65536
+        up = up.tocsr()
+    m = (up + up.T + sp.diags(diag, dtype=np.int64)).tocsr().astype(np.uint32)
+    m.sort_indices()
+    sites = rng.integers(0, 60, size=n).astype(np.int32)
+    s1 = np.where(sites == 0, 1, sites).astype(np.float64)
+    norm = m.astype(np.float64).tocoo()
+    norm.data = norm.data * (1.0 / (s1[norm.row] * s1[norm.col]))
+    _, x_ref, it_ref = oracle.kr_biostochastic(norm.tocsr())
+    csr = dev.DeviceCSR.from_scipy(m, np.uint32)
+    d_sites = dev.to_device(sites, torch.int32)
+    got = {}
+    for mode in (2, 1):
+        dev.check(dev.lib.b3c_set_option(5, mode))
+        try:
+            x, info = dev.kr_scale_vector(csr, sites=d_sites)
+        finally:
+            dev.check(dev.lib.b3c_set_option(5, 2))
+        got[mode] = (x.cpu().numpy().copy(), info)
+    assert got[2][1]['stream_bytes_per_entry'] == (6 if offdiag_big else 4)
+    assert got[1][1]['stream_bytes_per_entry'] == 6
+    assert got[2][1]['n_iter'] == got[1][1]['n_iter']
+    assert got[2][1]['n_iter'] == it_ref
+    assert _relerr(got[2][0], x_ref) <= REL_TOL and _relerr(got[1][0], x_ref) <= REL_TOL
+    assert _relerr(got[2][0], got[1][0]) <= 1e-12
 
 
 def test_extent_map_from_bam(dev, tmp_path):
