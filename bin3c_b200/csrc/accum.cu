@@ -45,7 +45,7 @@ struct AccumState {
     int b = 0;                // bits per index in the key
     int64_t rank_words = 0;   // 64-bit words of the tid bitmap
     bool smem_diag = false;
-    int smem_rank = 0;        // 0 gather, 1 pair table, 2 packed table (classify_tiles)
+    int smem_rank = 0;        // 0 gather, 1 pair table, 2 packed table, 3 two-level table (classify_tiles)
     int cls_smem = 0, cls_grid = 0, cls_cap_w = 0, cls_diag_k = 0;
     const int32_t *d_lut = nullptr;
     int64_t o_ctr, o_diag, o_bits, o_pref, o_keys_a, o_keys_b, o_uniq, o_pos, o_cnt, o_hist, o_heads,
@@ -101,6 +101,10 @@ static void plan(AccumState &st, int64_t cap, int32_t n_seq, int32_t n_refs) {
     // (in shared memory the table is held as (32-bit word, prefix) pairs plus one zero sentinel)
     const int64_t rank64_bytes = align_up((st.rank_words * 2 + 1) * 8, 16);
     const int64_t rank32_bytes = align_up((ceil_div(n_refs > 0 ? n_refs : 1, 12) + 1) * 4, 16);
+    // mode 3, for tables too long for the other two (C4: 1.1M references): the 64-bit bitmap words, a 16-bit prefix
+    // per word relative to its block of 32 words, a 32-bit prefix per block -- 10.1 bytes per 64 references
+    const int64_t rank3_bytes = align_up((st.rank_words + 1) * 8, 16) + align_up((st.rank_words + 1) * 2, 16) +
+                                align_up((st.rank_words / 32 + 2) * 4, 16);
     const int64_t diag_bytes = align_up((int64_t)n_seq * 4, 16);
     // staging keys per warp that fit beside `fixed` bytes: at least one warp tile, at most CLS_CAPW_MAX
     auto cap_w = [](int64_t fixed, int key_bytes) -> int {
@@ -123,6 +127,10 @@ static void plan(AccumState &st, int64_t cap, int32_t n_seq, int32_t n_refs) {
         if (st.b <= 20 && cap_w(other + rank32_bytes, key_bytes)) {
             *bytes = rank32_bytes;
             return 2;
+        }
+        if (cap_w(other + rank3_bytes, key_bytes)) {
+            *bytes = rank3_bytes;
+            return 3;
         }
         *bytes = 0;
         return 0;
@@ -260,6 +268,34 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
         if (threadIdx.x == 0) tab[nw12] = 0u;
         s_tab32 = tab;
     }
+    const unsigned long long *s_bits3 = nullptr;
+    const uint16_t *s_rel3 = nullptr;
+    const uint32_t *s_sup3 = nullptr;
+    const uint32_t nw64 = (uint32_t)P.rank_words;
+    if (RANK == 3) {
+        // two-level form: word w (64 references) | its rank relative to block w / 32 (16 bit: < 2048) | the block's rank;
+        // three shared-memory loads per look-up instead of a gather from global memory; entry nw64 is the zero sentinel
+        unsigned long long *bits = reinterpret_cast<unsigned long long *>(cur);
+        cur += (((size_t)nw64 + 1) * 8 + 15) / 16 * 16;
+        uint16_t *rel = reinterpret_cast<uint16_t *>(cur);
+        cur += (((size_t)nw64 + 1) * 2 + 15) / 16 * 16;
+        uint32_t *sup = reinterpret_cast<uint32_t *>(cur);
+        cur += (((size_t)nw64 / 32 + 2) * 4 + 15) / 16 * 16;
+        for (uint32_t i = threadIdx.x; i < nw64; i += CLS_THREADS) {
+            const uint32_t base = P.g_pref[i & ~31u];
+            bits[i] = P.g_bits[i];
+            rel[i] = (uint16_t)(P.g_pref[i] - base);
+            if ((i & 31u) == 0) sup[i >> 5] = base;
+        }
+        if (threadIdx.x == 0) {
+            bits[nw64] = 0ull;
+            rel[nw64] = 0;
+            if ((nw64 & 31u) == 0) sup[nw64 >> 5] = 0u;            // the sentinel opens a block of its own
+        }
+        s_bits3 = bits;
+        s_rel3 = rel;
+        s_sup3 = sup;
+    }
     // diagonal counters of the first `dk` contigs live in shared memory (all of them with SMEM_DIAG; else as many as
     // fit beside the table and the staging: every one of them is a global RED less, and at C3 the kernel runs at
     // the rate the L2 retires the diagonal REDs -- 333M of them, ~140 G/s)
@@ -284,6 +320,17 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
             if (on) e = s_tab32[w];
             hit = (e >> bit) & 1u;
             return (e >> 12) + __popc(e & ~(0xffffffffu << bit) & 0xfffu);
+        } else if (RANK == 3) {
+            const uint32_t w = min(t >> 6, nw64);
+            unsigned long long m = 0ull;
+            uint32_t pf = 0;
+            if (on) {
+                m = s_bits3[w];
+                pf = (uint32_t)s_rel3[w] + s_sup3[w >> 5];
+            }
+            const unsigned bit = t & 63u;
+            hit = (m >> bit) & 1ull;
+            return pf + __popcll(m & ~(~0ull << bit));
         } else if (RANK == 1) {
             uint2 e = make_uint2(0u, 0u);
             if (on) e = s_tab[min(t >> 5, nw32)];
@@ -1430,10 +1477,12 @@ static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int
     P.diag_k = st.cls_diag_k;
     cudaStream_t s = (cudaStream_t)stream;
     if (st.smem_diag) {
+        if (st.smem_rank == 3) return launch_classify<true, 3>(st, P, s);
         if (st.smem_rank == 2) return launch_classify<true, 2>(st, P, s);
         if (st.smem_rank == 1) return launch_classify<true, 1>(st, P, s);
         return launch_classify<true, 0>(st, P, s);
     }
+    if (st.smem_rank == 3) return launch_classify<false, 3>(st, P, s);
     if (st.smem_rank == 2) return launch_classify<false, 2>(st, P, s);
     if (st.smem_rank == 1) return launch_classify<false, 1>(st, P, s);
     return launch_classify<false, 0>(st, P, s);

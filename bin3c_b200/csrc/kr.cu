@@ -59,6 +59,7 @@ constexpr int SLAB_S_MAX = 16;                       // more slabs than this: ga
 constexpr int SLAB_S_CAP = 48;                       // the most slabs the tables are sized for
 constexpr int SLAB_DENSE_CELL = 6;                   // mean entries per (row, slab) cell from which slabs beyond SLAB_S_MAX pay
 constexpr int KR_MAX_RANKS = 8;                      // GPUs of one node in peer mode
+constexpr int BIG_CAP = 4096;                        // side list of off-diagonal counts above 65535 (packed count stream)
 static_assert(KR_WARPS <= 32 && SLAB_W_MAX <= 65536, "warp records are stitched by one warp; 16-bit columns");
 
 // partial arrays, each n_chunks long
@@ -68,7 +69,8 @@ struct KRScalars {
     double tol, delta, Delta, rt, stop_tol;
     double rho_km1, rho_km2, rout, rold, eta, inner_tol, alpha, beta, gamma;
     long long n_iter, max_iter, k, outer, n_spmv, zero_diag;
-    long long ovf16;           // the count pass met an off-diagonal count above 65535: the packed stream cannot hold the matrix
+    long long ovf16;           // the count pass met more than BIG_CAP off-diagonal counts above 65535: no packed stream
+    long long n_big;           // off-diagonal counts above 65535 met by the count pass (their high parts go to a side list)
     int status, ymode, ysel, state;
 };
 
@@ -118,8 +120,15 @@ struct KRArgs {
     int32_t cnt_stream;        // 1: sval is uint32[nnzv]; 2 (slab form): sval is uint32[nnzv] of PACKED entries, the 16-bit
                                // count in the high half and the 16-bit slab-local column in the low half -- 4 B per entry,
                                // one 32-byte load per lane and piece.  The high part of a DIAGONAL count above 65535 goes
-                               // into dfix (a term coefficient * operand_i added by rows_q); an off-diagonal count above
-                               // 65535 is detected by the count pass and the stream falls back to form 1
+                               // into dfix (a term coefficient * operand_i added by rows_q); the high part of an
+                               // OFF-DIAGONAL count above 65535 goes into a short side list sorted by (row, column) --
+                               // rows_q adds hi * operand_j for the rows the list names (sign bit of dfix set) -- and the
+                               // stream falls back to form 1 only if the count pass meets more than BIG_CAP of them
+    int32_t *cstart;           // [nv] offset of a cell's first entry inside its CSR row (k_cell_bounds -> k_stream_fill)
+    int32_t n_big;             // entries of the side list
+    long long *big_e;          // [BIG_CAP] CSR positions collected by the count pass, then sorted
+    int32_t *big_row, *big_col;    // [n_big] global row and column
+    double *big_hi;            // [n_big] (double)(count & 0xffff0000)
     const double *inv_s;       // [n] 1 / s_j (zero site counts taken as one, Q6)
     double *us, *xs;           // scaled operands (length n; xs lives beside x, in the exchange buffer in peer mode)
     // the stream
@@ -799,62 +808,91 @@ __device__ __forceinline__ double row_q(const KRArgs &A, int64_t r) {
 // store can never force a later load to wait.
 #define KR_FOR_CHUNKS(c) for (int c = blockIdx.x; c < A.n_chunks; c += gridDim.x)
 #define KR_ROW(c, i) ((int64_t)(c) * CHUNK + (i) * KR_THREADS + threadIdx.x)
-constexpr int ROWQ_S = 12;                     // slabs handled by the fully batched rows_q; more fall back to the loop
+constexpr int ROWQ_S = 12;                     // slabs per round of the batched rows_q
 
 __device__ __forceinline__ bool chunk_local(const KRArgs &A, int c) {
     const int64_t r0 = (int64_t)c * CHUNK;
     return r0 >= A.row_lo && r0 < A.row_hi;
 }
 
+// Packed count stream: the high parts of row r's off-diagonal counts above 65535 (side list sorted by row, then
+// column) times the scaled operand, added to the row sum in list order
+__device__ __forceinline__ double add_big(const KRArgs &A, int64_t r, double s, const double *mult) {
+    int lo = 0, hi = A.n_big;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(A.big_row + mid) < (int32_t)r) lo = mid + 1;
+        else hi = mid;
+    }
+    for (; lo < A.n_big && __ldg(A.big_row + lo) == (int32_t)r; ++lo)
+        s = __dadd_rn(s, __dmul_rn(__ldg(A.big_hi + lo), __ldcg(mult + __ldg(A.big_col + lo))));
+    return s;
+}
+
 // q = A u plus the zero-diagonal term (Q2) for the CHUNK_RPT rows of this thread, loads batched: every cell
-// ordinal of up to NB slabs first, then every segment sum, then the adds in slab order
-template <int NB>
+// ordinal of NB slabs (of all the thread's rows) first, then every segment sum, then the adds in slab order; matrices
+// wider than NB slabs take several such rounds (C4's 35 slabs: 3 rounds of 2 dependent trips instead of the 20 a
+// row-by-row walk in batches of eight took -- the vector phases of a wide matrix are latency-bound)
+template <int NB, bool MULTI>
 __device__ __forceinline__ void rows_q_batched(const KRArgs &A, const double *opnd, int c, double (&qq)[CHUNK_RPT]) {
     int o[CHUNK_RPT][NB];
-    double df[CHUNK_RPT], uu[CHUNK_RPT], is[CHUNK_RPT], t[CHUNK_RPT][NB];
+    double df[CHUNK_RPT], uu[CHUNK_RPT], is[CHUNK_RPT], t[CHUNK_RPT][NB], s[CHUNK_RPT];
+    bool ok[CHUNK_RPT];
 #pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i) {
         const int64_t r = KR_ROW(c, i);
-        const bool ok = r < A.row_hi;
+        ok[i] = r < A.row_hi;
 #pragma unroll
         for (int k = 0; k < NB; ++k)
-            o[i][k] = (ok && k < A.S) ? __ldg(A.seg_of + (int64_t)k * A.npad + (r - A.row_lo)) : -1;
-        df[i] = ok ? __ldcg(A.dfix + r) : 0.0;
-        uu[i] = ok ? __ldcg(opnd + r) : 0.0;
-        is[i] = (ok && A.cnt_stream) ? __ldg(A.inv_s + r) : 1.0;
+            o[i][k] = (ok[i] && k < A.S) ? __ldg(A.seg_of + (int64_t)k * A.npad + (r - A.row_lo)) : -1;
+        df[i] = ok[i] ? __ldcg(A.dfix + r) : 0.0;
+        uu[i] = ok[i] ? __ldcg(opnd + r) : 0.0;
+        is[i] = (ok[i] && A.cnt_stream) ? __ldg(A.inv_s + r) : 1.0;
+        s[i] = 0.0;
+    }
+    for (int k0 = 0;;) {
+#pragma unroll
+        for (int i = 0; i < CHUNK_RPT; ++i)
+#pragma unroll
+            for (int k = 0; k < NB; ++k) t[i][k] = o[i][k] >= 0 ? __ldcg(A.qs + o[i][k]) : 0.0;
+#pragma unroll
+        for (int i = 0; i < CHUNK_RPT; ++i)
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+                if (o[i][k] >= 0) s[i] = __dadd_rn(s[i], t[i][k]);
+        if constexpr (MULTI) {
+            k0 += NB;
+            if (k0 >= A.S) break;
+#pragma unroll
+            for (int i = 0; i < CHUNK_RPT; ++i) {
+                const int64_t r = KR_ROW(c, i);
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                    o[i][k] = (ok[i] && k0 + k < A.S) ? __ldg(A.seg_of + (int64_t)(k0 + k) * A.npad + (r - A.row_lo)) : -1;
+            }
+        } else {
+            break;
+        }
     }
 #pragma unroll
-    for (int i = 0; i < CHUNK_RPT; ++i)
-#pragma unroll
-        for (int k = 0; k < NB; ++k) t[i][k] = o[i][k] >= 0 ? __ldcg(A.qs + o[i][k]) : 0.0;
-#pragma unroll
     for (int i = 0; i < CHUNK_RPT; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < NB; ++k)
-            if (o[i][k] >= 0) s = __dadd_rn(s, t[i][k]);
-        if (A.cnt_stream) s = __dmul_rn(s, is[i]);                 // counts stream: the row's 1 / s_i
-        if (df[i] != 0.0) s = __dadd_rn(s, __dmul_rn(df[i], uu[i]));   // zero diagonal counted as one (Q2): df = 1; or the
+        double q = s[i];
+        if (__double_as_longlong(df[i]) < 0) {                    // the side list names this row (sign bit of dfix)
+            q = add_big(A, KR_ROW(c, i), q, opnd == A.u ? A.us : A.xs);
+            df[i] = fabs(df[i]);
+        }
+        if (A.cnt_stream) q = __dmul_rn(q, is[i]);                 // counts stream: the row's 1 / s_i
+        if (df[i] != 0.0) q = __dadd_rn(q, __dmul_rn(df[i], uu[i]));   // zero diagonal counted as one (Q2): df = 1; or the
                                                                     // high part of a packed diagonal count (KRArgs.cnt_stream)
-        qq[i] = s;
+        qq[i] = q;
     }
 }
 
 // `opnd`: the vector the SpMV just multiplied (u, or x for a residual), for the zero-diagonal term
 __device__ __forceinline__ void rows_q(const KRArgs &A, const double *opnd, int c, double (&qq)[CHUNK_RPT]) {
-    if (A.S <= 4) return rows_q_batched<4>(A, opnd, c, qq);
-    if (A.S <= ROWQ_S) return rows_q_batched<ROWQ_S>(A, opnd, c, qq);
-#pragma unroll
-    for (int i = 0; i < CHUNK_RPT; ++i) {
-        const int64_t r = KR_ROW(c, i);
-        qq[i] = 0.0;
-        if (r < A.row_hi) {
-            qq[i] = row_q(A, r);
-            if (A.cnt_stream) qq[i] = __dmul_rn(qq[i], __ldg(A.inv_s + r));
-            const double df = __ldcg(A.dfix + r);
-            if (df != 0.0) qq[i] = __dadd_rn(qq[i], __dmul_rn(df, __ldcg(opnd + r)));
-        }
-    }
+    if (A.S <= 4) return rows_q_batched<4, false>(A, opnd, c, qq);
+    if (A.S <= ROWQ_S) return rows_q_batched<ROWQ_S, false>(A, opnd, c, qq);
+    return rows_q_batched<ROWQ_S, true>(A, opnd, c, qq);
 }
 
 __device__ __forceinline__ void phase_init(const KRArgs &A) {
@@ -1409,10 +1447,10 @@ __global__ void __launch_bounds__(KR_THREADS, 1) k_kr_persistent(KRArgs A) {
 
 // ---- building the stream (once per balancing run) ---------------------------------------------------
 // Columns are sorted within a row, so the entries of row r that fall in slab s are one contiguous
-// segment.  Pass 1 counts the segment lengths into cnt[s * npad + r]; the slab totals are padded to
-// whole tiles; an exclusive scan gives the position vp of every cell; a second scan numbers the
-// non-empty cells; pass 2 copies the segments.  A warp walks one row in 32-entry windows; a lane whose
-// slab differs from its left neighbour's starts a segment.
+// segment.  Pass 1 (k_cell_bounds, a thread per cell) finds every cell's first entry by bisection and writes the
+// padded segment length into cnt[s * npad + r]; the slab totals are padded to whole tiles; an exclusive scan gives
+// the position vp of every cell; a second scan numbers the non-empty cells; pass 2 (k_stream_fill) copies the
+// segments piece by piece.
 // Every segment is padded with zero entries to a whole number of 8-entry pieces, so a segment can only start at
 // the first entry of a lane's piece: the SpMV adds a piece up unconditionally and looks at ONE flag per piece.
 __host__ __device__ __forceinline__ int64_t seg_padded(int64_t len) { return (len + SPMV_EPP - 1) & ~(int64_t)(SPMV_EPP - 1); }
@@ -1423,114 +1461,136 @@ __device__ __forceinline__ void stream_set_flag(uint16_t *sflag, int64_t pos) {
     atomicOr((unsigned *)sflag + (w16 >> 1), (1u << (pos & 15)) << ((w16 & 1) * 16));
 }
 
-template <bool FILL, bool SLAB>
-__global__ void __launch_bounds__(256) k_stream_rows(KRArgs A, int64_t *__restrict__ cnt, double *__restrict__ sval,
+// Pass 1, one thread per (row, slab) cell: columns are sorted within a row, so the cell's entries are the run between
+// two lower bounds.  cstart[v] = offset of the cell's first entry inside its row, cnt[v] = its padded length.
+template <bool SLAB>
+__global__ void __launch_bounds__(256) k_cell_bounds(KRArgs A, int64_t *__restrict__ cnt, int32_t *__restrict__ cstart) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= A.nv) return;
+    const int s = (int)(v / A.npad);
+    const int64_t lr = v - (int64_t)s * A.npad;
+    if (lr >= A.row_hi - A.row_lo) {
+        cnt[v] = 0;
+        cstart[v] = 0;
+        return;
+    }
+    const int64_t lo = A.indptr[lr], hi = A.indptr[lr + 1];
+    int64_t first = lo, last = hi;
+    if (s > 0) {                                       // first entry with column >= s * W
+        const int32_t key = s * A.W;
+        int64_t a = lo, b = hi;
+        while (a < b) {
+            const int64_t mid = (a + b) >> 1;
+            if (A.indices[mid] < key) a = mid + 1;
+            else b = mid;
+        }
+        first = a;
+    }
+    if (s < A.S - 1) {
+        const int32_t key = (s + 1) * A.W;
+        int64_t a = lo, b = hi;                        // over the whole row, exactly as cell s + 1 finds its start: the
+        while (a < b) {                                // two agree even on an unsorted row (which pass 2 reports)
+            const int64_t mid = (a + b) >> 1;
+            if (A.indices[mid] < key) a = mid + 1;
+            else b = mid;
+        }
+        last = a;
+    }
+    cstart[v] = (int32_t)(first - lo);
+    cnt[v] = seg_padded(last > first ? last - first : 0);
+}
+
+// Pass 2: copy the cells into the stream.  A warp takes 32 consecutive cells (same slab, consecutive rows) and spreads
+// their 8-entry PIECES over its four 8-lane groups -- a piece is eight consecutive CSR entries in and eight physically
+// consecutive stream entries (one 32-byte sector of the packed form) out, so a long cell does not hold up a lane and a
+// short one does not idle 31.  The last piece of a cell carries its zero padding; the first one sets the start flag.
+// Entries are checked against their cell's column range: an unsorted or out-of-range row shows up here.
+template <bool SLAB>
+__global__ void __launch_bounds__(256) k_stream_fill(KRArgs A, const int32_t *__restrict__ cstart, double *__restrict__ sval,
                                                      void *__restrict__ scol_v, uint16_t *__restrict__ sflag) {
-    const unsigned lane = lane_id();
+    const unsigned lane = lane_id(), grp = lane >> 3, sub = lane & 7u;
     const int64_t nw = (int64_t)gridDim.x * 8;
     const int n_local = A.row_hi - A.row_lo;
-    const int W = A.W;
-    // col / W as a multiplication: with Wm = ceil(2^40 / W) the quotient is exact while col * W < 2^40 (col < 2^21, W < 2^15)
-    // (slab form); with a single slab (the gather form, W = n) the multiplier is 0 and every column is in slab 0
-    const uint64_t Wm = A.S == 1 ? 0ull : ((1ull << 40) + (uint64_t)W - 1) / (uint64_t)W;
+    const int64_t n_batch = A.nv >> 5;                 // npad is a multiple of 1024: whole batches, one slab each
     bool bad = false, bad16 = false;
-    for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < n_local; lr += nw) {
-        const int64_t lo = A.indptr[lr], hi = A.indptr[lr + 1];
-        const int32_t s_row = (FILL && A.cnt32) ? A.sites[A.row_lo + lr] : 1;
-        int carry_s = -1;
-        int64_t carry_start = lo;
-        // software pipeline over the 32-entry windows: columns and counts are loaded two windows ahead, the site
-        // count of a column (a scattered gather that needs the column first) one window ahead
-        // the count pass of a packed stream looks at the counts too: an off-diagonal count above 65535 does not fit
-        const bool want_cnt = (FILL || A.cnt_stream == 2) && A.cnt32 != nullptr;
-        const bool want_site = want_cnt && !A.cnt_stream;       // the counts stream stores the counts themselves
-        int col_a = (lo + lane < hi) ? A.indices[lo + lane] : 0;
-        int col_b = (lo + 32 + lane < hi) ? A.indices[lo + 32 + lane] : 0;
-        uint32_t cnt_a = (want_cnt && lo + lane < hi) ? A.cnt32[lo + lane] : 0u;
-        uint32_t cnt_b = (want_cnt && lo + 32 + lane < hi) ? A.cnt32[lo + 32 + lane] : 0u;
-        int32_t site_a = want_site ? __ldg(A.sites + min(max(col_a, 0), A.n - 1)) : 1;
-        for (int64_t e0 = lo; e0 < hi; e0 += 32) {
-            const int64_t e = e0 + lane;
-            const bool valid = e < hi;
-            int col = col_a;
-            const uint32_t cnt_e = cnt_a;
-            const int32_t site_e = site_a;
-            col_a = col_b;
-            cnt_a = cnt_b;
-            col_b = 0;
-            if (e + 64 < hi) {
-                col_b = A.indices[e + 64];
-                if (want_cnt) cnt_b = A.cnt32[e + 64];
-            }
-            if (want_site && e0 + 32 < hi) site_a = __ldg(A.sites + min(max(col_a, 0), A.n - 1));
-            if (col < 0 || col >= A.n) {           // reported through ctl->status; clamped to stay in bounds
-                bad = true;
-                col = col < 0 ? 0 : A.n - 1;
-            }
-            if (!FILL && A.cnt_stream == 2 && valid && cnt_e > 0xffffu && col != A.row_lo + (int)lr) bad16 = true;
-            const int s = valid ? (int)(((uint64_t)col * Wm) >> 40) : 0x7fffffff;      // col / W
-            int sp = __shfl_up_sync(kFullMask, s, 1);
-            if (lane == 0) sp = carry_s;
-            const bool flag = valid && (s != sp);
-            bad |= valid && s < sp;
-            const unsigned fm = __ballot_sync(kFullMask, flag);
-            const unsigned below = fm & lanemask_lt();
-            // slab of the entry after mine: my right neighbour's.  Lane 31 cannot know yet (the next window is still
-            // in flight) and assumes its segment goes on; if it did end there, lane 0 of the next window pads it.
-            int s_nb = 0;
-            if (FILL) {
-                s_nb = __shfl_down_sync(kFullMask, s, 1);
-                if (lane == 31) s_nb = s;
-                if (lane == 0 && flag && sp >= 0) {
-                    const int64_t len = e0 - carry_start, seg0 = A.vp[(int64_t)sp * A.npad + lr];
-                    for (int64_t k = len; k < seg_padded(len); ++k) {
-                        const int64_t pp = stream_phys(seg0 + k);
-                        if (A.cnt_stream) ((uint32_t *)sval)[pp] = 0u;
-                        else sval[pp] = 0.0;
-                        if (SLAB) ((uint16_t *)scol_v)[pp] = 0;
-                        else ((uint32_t *)scol_v)[pp] = 0;
-                    }
-                }
-            }
-            if (!FILL) {
-                if (flag && sp >= 0) {             // this entry closes the segment of slab sp
-                    const int64_t prev_start = below ? e0 + (31 - __clz(below)) : carry_start;
-                    cnt[(int64_t)sp * A.npad + lr] = seg_padded(e - prev_start);
-                }
-            } else if (valid) {
-                const unsigned upto = fm & (lanemask_lt() | (1u << lane));
-                const int64_t seg_start = upto ? e0 + (31 - __clz(upto)) : carry_start;
-                const int64_t dst = A.vp[(int64_t)s * A.npad + lr] + (e - seg_start);
-                const int64_t ph = stream_phys(dst);
-                const unsigned lc = (unsigned)(col - s * W);
-                if (A.cnt_stream == 2) ((uint32_t *)sval)[ph] = (cnt_e << 16) | lc;      // low 16 bits of the count | column
-                else if (A.cnt_stream) ((uint32_t *)sval)[ph] = cnt_e;
-                else sval[ph] = A.cnt32 ? site_scaled(cnt_e, s_row, site_e) : A.data[e];
-                if (A.cnt_stream == 2) {}
-                else if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
-                else ((uint32_t *)scol_v)[ph] = lc;
-                if (e == seg_start) stream_set_flag(sflag, dst);
-                // the segment's last entry also writes its padding (zero value, column 0) up to a whole piece
-                const int s_next = (e + 1 < hi) ? s_nb : -1;
-                if (s_next != s) {
-                    const int64_t len = e - seg_start + 1, seg0 = dst - (e - seg_start);
-                    for (int64_t k = len; k < seg_padded(len); ++k) {
-                        const int64_t pp = stream_phys(seg0 + k);
-                        if (A.cnt_stream) ((uint32_t *)sval)[pp] = 0u;
-                        else sval[pp] = 0.0;
-                        if (SLAB) ((uint16_t *)scol_v)[pp] = 0;
-                        else ((uint32_t *)scol_v)[pp] = 0;
-                    }
-                }
-            }
-            if (fm) carry_start = e0 + (31 - __clz(fm));
-            const int last = (int)((hi - 1 - e0) < 31 ? (hi - 1 - e0) : 31);
-            carry_s = __shfl_sync(kFullMask, s, last);
+    for (int64_t bt = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); bt < n_batch; bt += nw) {
+        const int64_t v = bt * 32 + lane;
+        const int s = (int)(v / A.npad);
+        const int64_t lr = v - (int64_t)s * A.npad;
+        int64_t c_src = 0, c_dst = 0;
+        int c_len = 0;
+        if (lr < n_local) {
+            const int64_t lo = A.indptr[lr], hi = A.indptr[lr + 1];
+            const int32_t c0 = cstart[v];
+            const int64_t c1 = s < A.S - 1 ? (int64_t)cstart[v + A.npad] : hi - lo;
+            c_src = lo + c0;
+            c_len = c1 > c0 ? (int)(c1 - c0) : 0;
+            bad |= c1 < c0;                            // boundaries out of order: the row is not sorted
+            c_dst = A.vp[v];
         }
-        if (!FILL && hi > lo && lane == 0) cnt[(int64_t)carry_s * A.npad + lr] = seg_padded(hi - carry_start);
+        const int np = (c_len + SPMV_EPP - 1) / SPMV_EPP;
+        int off = np;                                  // inclusive scan over the lanes, then exclusive
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, off, d);
+            if ((int)lane >= d) off += t;
+        }
+        const int total = __shfl_sync(kFullMask, off, 31);
+        off -= np;
+        const int col_lo = s * A.W, col_hi = (s == A.S - 1) ? A.n : (s + 1) * A.W;
+        for (int t0 = 0; t0 < total; t0 += 4) {
+            // which cell holds piece t0 + g: the highest lane whose first piece is <= it
+            unsigned m_own = 0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const unsigned m = __ballot_sync(kFullMask, off <= t0 + g);
+                if ((int)grp == g) m_own = m;
+            }
+            const int t = t0 + (int)grp;
+            const int sel = 31 - __clz(m_own);
+            const int64_t src = __shfl_sync(kFullMask, c_src, sel);
+            const int64_t dst = __shfl_sync(kFullMask, c_dst, sel);
+            const int len = __shfl_sync(kFullMask, c_len, sel);
+            const int p = t - __shfl_sync(kFullMask, off, sel);
+            if (t >= total) continue;
+            const int k = p * SPMV_EPP + (int)sub;
+            const bool valid = k < len;
+            const int64_t e = src + k;
+            int col = valid ? A.indices[e] : col_lo;
+            if (col < col_lo || col >= col_hi) {       // reported through ctl->status; clamped to stay in bounds
+                bad = true;
+                col = col_lo;
+            }
+            const unsigned lc = (unsigned)(col - col_lo);
+            const int64_t ph = stream_phys(dst + (int64_t)p * SPMV_EPP) + sub;
+            if (A.cnt_stream) {
+                const uint32_t cnt_e = valid ? A.cnt32[e] : 0u;
+                if (A.cnt_stream == 2) {
+                    ((uint32_t *)sval)[ph] = (cnt_e << 16) | lc;            // low 16 bits of the count | column
+                    if (cnt_e > 0xffffu && col != A.row_lo + (int)(bt * 32 - (int64_t)s * A.npad) + sel) {
+                        // the high part of this off-diagonal count goes to the side list (sorted afterwards: k_big_build)
+                        const unsigned long long q = atomicAdd((unsigned long long *)&A.ctl->n_big, 1ull);
+                        if (q < (unsigned long long)BIG_CAP) A.big_e[q] = (long long)e;
+                        else bad16 = true;
+                    }
+                } else {
+                    ((uint32_t *)sval)[ph] = cnt_e;
+                }
+            } else if (A.cnt32) {
+                const int row = A.row_lo + (int)(bt * 32 - (int64_t)s * A.npad) + sel;
+                sval[ph] = valid ? site_scaled(A.cnt32[e], A.sites[row], __ldg(A.sites + col)) : 0.0;
+            } else {
+                sval[ph] = valid ? A.data[e] : 0.0;
+            }
+            if (A.cnt_stream != 2) {
+                if (SLAB) ((uint16_t *)scol_v)[ph] = (uint16_t)lc;
+                else ((uint32_t *)scol_v)[ph] = lc;
+            }
+            if (k == 0) stream_set_flag(sflag, dst);
+        }
     }
-    if (!FILL && bad) A.ctl->status = B3C_ERR_ARG;     // unsorted or out-of-range columns
-    if (!FILL && bad16) A.ctl->ovf16 = 1;
+    if (bad) A.ctl->status = B3C_ERR_ARG;              // unsorted or out-of-range columns
+    if (bad16) A.ctl->ovf16 = 1;
 }
 
 // one CTA per slab: pad the slab's entry count to whole tiles (the padding belongs to its last cell)
@@ -1677,7 +1737,7 @@ __global__ void __launch_bounds__(256) k_diag_fix(int32_t row_lo, int32_t row_hi
                                                   const uint32_t *__restrict__ cnt32, const int32_t *__restrict__ sites,
                                                   double *__restrict__ dfix, KRScalars *ctl, int packed,
                                                   const double *__restrict__ inv_s) {
-    // One thread per row: the columns of a row are sorted (k_stream_rows rejects the matrix otherwise), so the
+    // One thread per row: the columns of a row are sorted (k_stream_fill rejects the matrix otherwise), so the
     // diagonal is found by bisection instead of walking the row.
     const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool z = false;
@@ -1705,6 +1765,53 @@ __global__ void __launch_bounds__(256) k_diag_fix(int32_t row_lo, int32_t row_hi
     }
     const unsigned nz = __popc(__ballot_sync(kFullMask, z));
     if (lane_id() == 0 && nz) atomicAdd((unsigned long long *)&ctl->zero_diag, (unsigned long long)nz);
+}
+
+// Side list of the packed count stream (one CTA): sort the CSR positions the count pass collected -- position order
+// is (row, column) order, so every run adds a row's terms in the same order --, look up row, column and the high part
+// of each count, and set the sign bit of dfix on the rows the list names (after k_diag_fix).
+__global__ void __launch_bounds__(1024) k_big_build(KRArgs A) {
+    __shared__ long long s_e[BIG_CAP];
+    const int nb = A.n_big;
+    int m = 1;
+    while (m < nb) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s_e[i] = i < nb ? A.big_e[i] : 0x7fffffffffffffffLL;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const long long a = s_e[i], b = s_e[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        s_e[i] = b;
+                        s_e[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    const int n_local = A.row_hi - A.row_lo;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        const long long e = s_e[i];
+        int lo = 0, hi = n_local;                      // last local row with indptr[row] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (A.indptr[mid] <= e) lo = mid;
+            else hi = mid;
+        }
+        A.big_e[i] = e;
+        A.big_row[i] = A.row_lo + lo;
+        A.big_col[i] = A.indices[e];
+        A.big_hi[i] = (double)(A.cnt32[e] & 0xffff0000u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        const int32_t r = A.big_row[i];
+        if (i == 0 || A.big_row[i - 1] != r)
+            A.dfix[r] = __longlong_as_double(__double_as_longlong(A.dfix[r]) | (long long)0x8000000000000000ULL);
+    }
 }
 
 // ---- stand-alone kernels (microbench SpMV, host-driven phases) ------------------------------------
@@ -1821,7 +1928,7 @@ struct KRLayout {
     int64_t nvec;                       // elements per (padded) vector
     int64_t nv_max, nnzv_max, nseg_max;
     int64_t o_dfix, o_inv_s, o_vec, o_qs, o_part, o_ll, o_ctl, o_timers, o_bar, o_bnd, o_cta;
-    int64_t o_cnt, o_vp, o_ord, o_scan, o_slab_t0, o_sval, o_scol, o_sflag, o_seg0, o_seg_of, o_seg_row, total;
+    int64_t o_cnt, o_vp, o_ord, o_scan, o_slab_t0, o_sval, o_scol, o_sflag, o_seg0, o_seg_of, o_seg_row, o_big, o_cstart, total;
 };
 
 static KRLayout kr_layout(int32_t n, int64_t nnz) {
@@ -1866,6 +1973,8 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     L.o_seg0 = c.take((L.nnzv_max / SPMV_CHUNK + 1) * 4);
     L.o_seg_of = c.take(L.nv_max * 4);
     L.o_seg_row = c.take(L.nseg_max * 4);
+    L.o_big = c.take((int64_t)BIG_CAP * (8 + 4 + 4 + 8));
+    L.o_cstart = c.take(L.nv_max * 4);
     L.total = c.cur;
     return L;
 }
@@ -1924,6 +2033,12 @@ static void kr_bind(KRArgs &A, const KRLayout &L, char *ws, int32_t n, int32_t r
     A.xs = vec + L.nvec * 10;
     A.inv_s = (const double *)(ws + L.o_inv_s);
     A.cnt_stream = 0;
+    A.n_big = 0;
+    A.cstart = (int32_t *)(ws + L.o_cstart);
+    A.big_e = (long long *)(ws + L.o_big);
+    A.big_hi = (double *)(ws + L.o_big + (int64_t)BIG_CAP * 8);
+    A.big_row = (int32_t *)(ws + L.o_big + (int64_t)BIG_CAP * 16);
+    A.big_col = (int32_t *)(ws + L.o_big + (int64_t)BIG_CAP * 20);
     A.part = (double *)(ws + L.o_part);
     A.ll = (unsigned long long *)(ws + L.o_ll);
     A.n_chunks = L.n_chunks;
@@ -1992,22 +2107,24 @@ __global__ void __launch_bounds__(256) k_inv_sites(int32_t n, const int32_t *__r
 }
 
 // Build the stream, its segment numbering and the zero-diagonal vector.  Needs the control block already
-// uploaded (k_stream_rows / k_diag_fix write into it).  The entry and segment counts are needed on the host
-// to size things: one small D2H copy + sync.
+// uploaded (k_stream_fill / k_diag_fix write into it).  Two small D2H copies + syncs: the entry and segment counts
+// size the fill; the fill reports bad columns and, in the packed form, how many large counts it met.
 template <bool SLAB>
 static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     const int32_t n_local = A.row_hi - A.row_lo;
     double *sval = const_cast<double *>(A.sval);
     void *scol = const_cast<void *>(A.scol);
     uint16_t *sflag = const_cast<uint16_t *>(A.sflag);
-    B3C_CUDA(cudaMemsetAsync(A.cnt, 0, (size_t)(A.nv + 1) * 8, s));
+    B3C_CUDA(cudaMemsetAsync(A.cnt + A.nv, 0, 8, s));
     B3C_CUDA(cudaMemsetAsync(sflag, 0, (size_t)(L.nnzv_max / 8 + 64), s));
     if (A.cnt_stream) {
         k_inv_sites<<<(unsigned)ceil_div(A.n, 256), 256, 0, s>>>(A.n, A.sites, const_cast<double *>(A.inv_s));
         B3C_LAUNCH_CHECK();
     }
-    k_stream_rows<false, SLAB><<<row_warp_grid(n_local), 256, 0, s>>>(A, A.cnt, nullptr, nullptr, nullptr);
-    B3C_LAUNCH_CHECK();
+    if (A.nv > 0) {
+        k_cell_bounds<SLAB><<<(unsigned)ceil_div(A.nv, 256), 256, 0, s>>>(A, A.cnt, A.cstart);
+        B3C_LAUNCH_CHECK();
+    }
     k_slab_pad<<<(unsigned)A.S, 1024, 0, s>>>(A, A.cnt);
     B3C_LAUNCH_CHECK();
     int rc = scan_exclusive_i64(A.cnt, A.vp, A.nv, A.scan_tmp, s);
@@ -2023,13 +2140,7 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     KRScalars S;
     B3C_CUDA(cudaMemcpyAsync(&totals[0], A.vp + A.nv, 8, cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaMemcpyAsync(&totals[1], A.ord + A.nv, 8, cudaMemcpyDeviceToHost, s));
-    B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaStreamSynchronize(s));
-    if (S.status == B3C_ERR_ARG) {
-        set_error("KR: column indices must be sorted within rows and lie in [0, n)");
-        return B3C_ERR_ARG;
-    }
-    if (A.cnt_stream == 2 && S.ovf16) A.cnt_stream = 1;        // an off-diagonal count above 65535: 32-bit counts
     if (totals[0] > L.nnzv_max || totals[0] % SPMV_TILE != 0 || totals[1] > L.nseg_max) {
         set_error("stream layout: %lld entries, %lld segments (capacity %lld, %lld)", (long long)totals[0],
                   (long long)totals[1], (long long)L.nnzv_max, (long long)L.nseg_max);
@@ -2038,8 +2149,24 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     A.nnzv = totals[0];
     A.n_sch = A.nnzv / SPMV_CHUNK;
     A.n_seg = (int32_t)totals[1];
-    k_stream_rows<true, SLAB><<<row_warp_grid(n_local), 256, 0, s>>>(A, nullptr, sval, scol, sflag);
-    B3C_LAUNCH_CHECK();
+    const int64_t n_batch = A.nv / 32;
+    const unsigned fill_grid = row_warp_grid(n_batch);                           // a warp per batch of 32 cells, grid-stride
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        k_stream_fill<SLAB><<<fill_grid, 256, 0, s>>>(A, A.cstart, sval, scol, sflag);
+        B3C_LAUNCH_CHECK();
+        B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
+        B3C_CUDA(cudaStreamSynchronize(s));
+        if (S.status == B3C_ERR_ARG) {
+            set_error("KR: column indices must be sorted within rows and lie in [0, n)");
+            return B3C_ERR_ARG;
+        }
+        if (A.cnt_stream == 2 && S.ovf16) {            // more large off-diagonal counts than the side list holds:
+            A.cnt_stream = 1;                          // fill again with 32-bit counts
+            continue;
+        }
+        break;
+    }
+    A.n_big = A.cnt_stream == 2 ? (int32_t)S.n_big : 0;       // (at most BIG_CAP, or ovf16 would be set)
     if (SLAB && !A.cnt_stream && (A.opts & KR_OPT_BANK_ORDER) && A.n_sch > 0) {
         k_stream_bank_order<<<(unsigned)ceil_div(A.n_sch * 32, 256), 256, 0, s>>>(A.n_sch * 32, sval, (uint16_t *)scol, sflag);
         B3C_LAUNCH_CHECK();
@@ -2057,6 +2184,10 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     k_diag_fix<<<(unsigned)ceil_div(n_local > 0 ? n_local : 1, 256), 256, 0, s>>>(A.row_lo, A.row_hi, A.indptr, A.indices, A.data, A.cnt32, A.sites,
                                                               A.dfix, A.ctl, A.cnt_stream == 2 ? 1 : 0, A.inv_s);
     B3C_LAUNCH_CHECK();
+    if (A.n_big > 0) {
+        k_big_build<<<1, 1024, 0, s>>>(A);
+        B3C_LAUNCH_CHECK();
+    }
     rc = persistent_grid(SLAB, &A.n_bnd);
     return rc;
 }

@@ -125,6 +125,8 @@ def test_accumulate_edge_cases(dev, case):
     (70_000, 80_000, 400_000, True),      # 17-bit indices: global diagonal, 64-bit staging
     (70_000, 80_000, 400_000, False),
     (300_000, 2_400_000, 300_000, True),  # rank table too large for shared memory
+    (1_000_000, 1_100_000, 400_000, True),    # two-level rank table (C4's size: bitmap + 16-bit relative prefixes)
+    (900_000, 1_048_576, 300_000, True),      # ... with the sentinel word opening a block of its own
     (257, 257, 50_001, True),             # odd sizes, no excluded refs
 ])
 def test_accumulate_random(dev, n, n_refs, p, rank_lut):
@@ -768,13 +770,15 @@ def test_fused_counts_form_matches_the_staged_form(dev):
         dev.check(dev.lib.b3c_set_option(5, 2))
 
 
-@pytest.mark.parametrize('offdiag_big', [False, True])
+@pytest.mark.parametrize('offdiag_big', ['none', 'few', 'many'])
 def test_packed_count_stream_large_counts(dev, offdiag_big):
     """The packed stream (16-bit count | 16-bit column, 4 B per entry; B3C_OPT_KR_COUNT_STREAM = 2, the default in the
     slab form): diagonal counts above 65535 -- intra-contig pair counts of long contigs -- keep their low 16 bits in
-    the stream and their high part as a per-row term; an OFF-diagonal count above 65535 makes the build fall back to
-    32-bit counts.  Either way: n_iter equal to the oracle's and to the 32-bit stream's, x <= 1e-9 (measured
-    ~1e-15), and the stream width reported."""
+    the stream and their high part as a per-row term; the high part of an OFF-diagonal count above 65535 goes to a short
+    side list sorted by (row, column) that the row sums add in (rows with a zero diagonal, a large diagonal and several
+    large off-diagonal counts among them); more than 4096 such counts make the build fall back to 32-bit counts.
+    Either way: n_iter equal to the oracle's and to the 32-bit stream's, x <= 1e-9 (measured ~1e-15), the same bits
+    when run twice, and the stream width reported."""
     import torch
     from oracle import oracle
     rng = np.random.default_rng(77)
@@ -782,12 +786,21 @@ def test_packed_count_stream_large_counts(dev, offdiag_big):
     up = sp.triu(sp.random(n, n, density=0.004, random_state=5, data_rvs=lambda k: rng.integers(1, 400, size=k)), 1).tocsr()
     diag = rng.integers(0, 3000, size=n).astype(np.int64)
     diag[[3, 70, 71, 500, 2999]] = [65535, 65536, 65537, 4_000_000_000, 1_234_567]
-    if offdiag_big:
+    if offdiag_big == 'few':
         up = up.tolil()
         up[10, 2000] = 70000
+        up[10, 2500] = 3_000_000_000
         up[11, 12] = 65536
+        up[70, 71] = 131072                # both rows have a large diagonal too
+        up[0, 2999] = 65537
+        up[40, 41] = 100000                # rows 40 and 2000 have a zero diagonal (Q2)
         up = up.tocsr()
-    m = (up + up.T + sp.diags(diag, dtype=np.int64)).tocsr().astype(np.uint32)
+        diag[[40, 2000]] = 0
+    elif offdiag_big == 'many':
+        up = (up * 1000).tocsr()           # ~9000 of the 18000 upper entries exceed 65535
+    m = (up + up.T + sp.diags(diag, dtype=np.int64)).tocsr()
+    m.eliminate_zeros()
+    m = m.astype(np.uint32)
     m.sort_indices()
     sites = rng.integers(0, 60, size=n).astype(np.int32)
     s1 = np.where(sites == 0, 1, sites).astype(np.float64)
@@ -797,19 +810,20 @@ def test_packed_count_stream_large_counts(dev, offdiag_big):
     csr = dev.DeviceCSR.from_scipy(m, np.uint32)
     d_sites = dev.to_device(sites, torch.int32)
     got = {}
-    for mode in (2, 1):
-        dev.check(dev.lib.b3c_set_option(5, mode))
+    for mode in (2, 1, 22):
+        dev.check(dev.lib.b3c_set_option(5, mode % 10))
         try:
             x, info = dev.kr_scale_vector(csr, sites=d_sites)
         finally:
             dev.check(dev.lib.b3c_set_option(5, 2))
         got[mode] = (x.cpu().numpy().copy(), info)
-    assert got[2][1]['stream_bytes_per_entry'] == (6 if offdiag_big else 4)
+    assert got[2][1]['stream_bytes_per_entry'] == (6 if offdiag_big == 'many' else 4)
     assert got[1][1]['stream_bytes_per_entry'] == 6
     assert got[2][1]['n_iter'] == got[1][1]['n_iter']
     assert got[2][1]['n_iter'] == it_ref
     assert _relerr(got[2][0], x_ref) <= REL_TOL and _relerr(got[1][0], x_ref) <= REL_TOL
     assert _relerr(got[2][0], got[1][0]) <= 1e-12
+    assert np.array_equal(got[2][0], got[22][0])                  # the side list is sorted: the same bits every run
 
 
 def test_extent_map_from_bam(dev, tmp_path):
