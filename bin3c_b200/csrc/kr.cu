@@ -1931,7 +1931,8 @@ struct KRLayout {
     int64_t o_cnt, o_vp, o_ord, o_scan, o_slab_t0, o_sval, o_scol, o_sflag, o_seg0, o_seg_of, o_seg_row, o_big, o_cstart, total;
 };
 
-static KRLayout kr_layout(int32_t n, int64_t nnz) {
+// `rows`: rows of the block the stream is built for (n for a whole matrix): the density rule counts the block's cells
+static KRLayout kr_layout(int32_t n, int64_t nnz, int32_t rows) {
     KRLayout L;
     Carver c;
     // Slab form whenever the matrix is at most B3C_OPT_KR_MAX_SLABS (16) slabs wide.  Wider matrices cut every row
@@ -1940,7 +1941,7 @@ static KRLayout kr_layout(int32_t n, int64_t nnz) {
     // form 0.42 ms, slab form 0.69 ms; 9.2 per cell -> gather 1.37 ms, slab 1.06 ms; break-even near 5.
     const int64_t s_need = ceil_div(n, g_slab_w_max.load());
     const int s_max = g_slab_s_max.load();
-    const bool dense_cells = s_max >= SLAB_S_MAX && s_need <= SLAB_S_CAP && nnz >= SLAB_DENSE_CELL * (int64_t)n * s_need;
+    const bool dense_cells = s_max >= SLAB_S_MAX && s_need <= SLAB_S_CAP && nnz >= SLAB_DENSE_CELL * (int64_t)rows * s_need;
     L.slab = (s_need <= s_max || dense_cells) ? 1 : 0;
     L.S = L.slab ? (int32_t)s_need : 1;
     L.W = L.slab ? (int32_t)align_up(ceil_div(n, L.S), 2) : n;
@@ -2253,7 +2254,7 @@ int b3c_set_option(int32_t key, int64_t value) {
 
 int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz) {
     if (n <= 0 || nnz < 0) return B3C_ERR_ARG;
-    return kr_layout(n, nnz).total;
+    return kr_layout(n, nnz, n).total;
 }
 
 // launch the persistent kernel on a prepared operand, wait, and report
@@ -2335,7 +2336,7 @@ static int kr_run_impl(int32_t n, int64_t nnz, const int64_t *d_indptr, const in
                        int32_t max_iter, double *d_x, void *d_ws, int64_t ws_bytes, int64_t *h_info, void *stream) {
     B3C_REQUIRE(n > 0 && nnz >= 0 && d_indptr && d_x && d_ws && h_info, "bad arguments");
     B3C_REQUIRE(nnz == 0 || (d_indices && (d_data || (d_counts && d_sites))), "null matrix arrays");
-    const KRLayout L = kr_layout(n, nnz);
+    const KRLayout L = kr_layout(n, nnz, n);
     if (ws_bytes < L.total) {
         set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
         return B3C_ERR_CAPACITY;
@@ -2435,7 +2436,7 @@ static int kr_run_peer_impl(int32_t n, int32_t row_lo, int32_t row_hi, int64_t n
     B3C_REQUIRE(d_indptr && d_x && d_ws && h_info && h_exchange && nnz_local >= 0, "bad arguments");
     B3C_REQUIRE(n_ranks >= 1 && n_ranks <= KR_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank %d of %d (at most %d)",
                 rank, n_ranks, KR_MAX_RANKS);
-    const KRLayout L = kr_layout(n, nnz_local);
+    const KRLayout L = kr_layout(n, nnz_local, row_hi - row_lo);
     if (ws_bytes < L.total) {
         set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
         return B3C_ERR_CAPACITY;
@@ -2497,7 +2498,7 @@ int b3c_kr_run_peer_counts(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nn
 int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
              const double *d_u, double *d_y, void *d_ws, int64_t ws_bytes, int32_t prepared, void *stream) {
     B3C_REQUIRE(n > 0 && nnz >= 0 && d_indptr && d_u && d_y && d_ws, "bad arguments");
-    const KRLayout L = kr_layout(n, nnz);
+    const KRLayout L = kr_layout(n, nnz, n);
     if (ws_bytes < L.total) {
         set_error("SpMV workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
         return B3C_ERR_CAPACITY;
@@ -2535,7 +2536,10 @@ int b3c_spmv(int32_t n, int64_t nnz, const int64_t *d_indptr, const int32_t *d_i
 
 int64_t b3c_krp_workspace_bytes(int32_t n, int64_t nnz_local) {
     if (n <= 0 || nnz_local < 0) return B3C_ERR_ARG;
-    return kr_layout(n, nnz_local).total;
+    // the form (slab or gather) depends on how dense the block's cells are, i.e. on its row count, which is not known
+    // here: room for either
+    const int64_t a = kr_layout(n, nnz_local, n).total, b = kr_layout(n, nnz_local, CHUNK).total;
+    return a > b ? a : b;
 }
 
 int b3c_krp_setup(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, const int64_t *d_indptr,
@@ -2544,7 +2548,7 @@ int b3c_krp_setup(int32_t n, int32_t row_lo, int32_t row_hi, int64_t nnz_local, 
     B3C_REQUIRE(n > 0 && 0 <= row_lo && row_lo < row_hi && row_hi <= n, "bad row block [%d,%d) of %d", row_lo, row_hi, n);
     B3C_REQUIRE(row_lo % CHUNK == 0 && (row_hi % CHUNK == 0 || row_hi == n), "row blocks must be %d-row aligned", CHUNK);
     B3C_REQUIRE(d_indptr && d_ws && h_offsets && nnz_local >= 0, "bad arguments");
-    const KRLayout L = kr_layout(n, nnz_local);
+    const KRLayout L = kr_layout(n, nnz_local, n);
     if (ws_bytes < L.total) {
         set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
         return B3C_ERR_CAPACITY;

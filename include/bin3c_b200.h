@@ -170,7 +170,8 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  * a time (see csrc/kr.cu); B3C_OPT_KR_SLAB_WIDTH caps the slab width (default 28672 columns, the most
  * that fits in a CTA's shared memory), B3C_OPT_KR_MAX_SLABS the slab count (default 16, at most 48; wider
  * matrices, or 0, select the form that gathers through L1/L2 -- except that at the default, matrices of up
- * to 48 slabs whose (row, slab) cells hold 6 or more entries on average stay in the slab form).  Results are
+ * to 48 slabs whose (row, slab) cells hold 6 or more entries on average stay in the slab form; b3c_kr_run_peer*
+ * applies that rule to its own row block).  Results are
  * identical up to fp64 summation order.  Workspace sizes depend on these, so set them before the *_workspace_bytes() query.
  * B3C_OPT_KR_FLAGS (default 22) is a bit set for A/B measurements: 1 = order every lane's run of the
  * stream by shared-memory bank (off: the pass costs more than it saves below ~180 SpMV per solve), 2 = align the SpMV CTA ranges with the slabs, 4 = single-word grid

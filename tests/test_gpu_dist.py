@@ -16,6 +16,10 @@ sys.path.insert(0, os.path.dirname(HERE))
 pytestmark = pytest.mark.gpu
 
 CFG = dict(n_genomes=12, n_contigs=9000, n_pairs=1_500_000, seed=654)
+# with 512-column slabs: 18 slabs (more than B3C_OPT_KR_MAX_SLABS) of ~7.8 entries per (row, slab) cell -- the slab form of
+# the SpMV stream by the density rule, decided per row block (C4 on 8 GPUs in miniature)
+WIDE = dict(n_genomes=12, n_contigs=9000, n_pairs=6_000_000, seed=656)
+WIDE_SLAB_W = 512
 
 
 def _check(parts, com, min_sig):
@@ -43,10 +47,12 @@ def _check(parts, com, min_sig):
     assert np.max(np.abs(w[o] - ref['w']) / np.abs(ref['w'])) <= 1e-9
 
 
-def _run_rank(rank, world, com, min_sig, host_driven_kr=False):
+def _run_rank(rank, world, com, min_sig, host_driven_kr=False, slab_w=None):
     import torch
     from bin3c_b200 import device as dev
     from bin3c_b200.dist import ShardedHotPath, Comm
+    if slab_w:
+        dev.check(dev.lib.b3c_set_option(1, slab_w))                      # B3C_OPT_KR_SLAB_WIDTH
     per = -(-com.n_pairs // world)
     per += per & 1
     mine = com.records[rank * per:(rank + 1) * per]
@@ -54,6 +60,8 @@ def _run_rank(rank, world, com, min_sig, host_driven_kr=False):
                         min_len=1000, min_sig=min_sig, comm=Comm(), host_driven_kr=host_driven_kr)
     res = hp.run(dev.to_device(mine))
     torch.cuda.synchronize()
+    if slab_w and not host_driven_kr:
+        assert hp.kr_info['slabs'] == -(-com.n_contigs // slab_w) > 16, hp.kr_info['slabs']
     indptr, indices, data = hp.block.host_arrays()
     row = np.repeat(np.arange(hp.block.n), np.diff(indptr)) + hp.row_lo
     out = dict(row=row, col=indices, data=data, mask=hp.mask.cpu().numpy(), x=hp.x.cpu().numpy(),
@@ -78,7 +86,20 @@ def test_sharded_path_world1(host_driven_kr):
     _check([_run_rank(0, 1, com, 3, host_driven_kr)], com, 3)
 
 
-def _nccl_worker(rank, world, port, out_dir, cfg):
+def test_sharded_path_world1_many_slabs():
+    """Peer-mode KR on a matrix wider than B3C_OPT_KR_MAX_SLABS slabs whose cells are dense enough for the slab form."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from bin3c_b200 import synth, device as dev
+    com = synth.make_community(**WIDE)
+    try:
+        _check([_run_rank(0, 1, com, 3, False, WIDE_SLAB_W)], com, 3)
+    finally:
+        dev.check(dev.lib.b3c_set_option(1, 28672))
+
+
+def _nccl_worker(rank, world, port, out_dir, cfg, slab_w=None):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -88,15 +109,16 @@ def _nccl_worker(rank, world, port, out_dir, cfg):
     from bin3c_b200 import synth
     com = synth.make_community(**cfg)
     for tag, host_driven in (('peer', False), ('host', True)):
-        np.savez(os.path.join(out_dir, '{}{}.npz'.format(tag, rank)), **_run_rank(rank, world, com, 3, host_driven))
+        np.savez(os.path.join(out_dir, '{}{}.npz'.format(tag, rank)),
+                 **_run_rank(rank, world, com, 3, host_driven, slab_w))
     dist.destroy_process_group()
 
 
 BIG = dict(n_genomes=30, n_contigs=40_000, n_pairs=3_000_000, seed=655)     # >= 4 row chunks per rank at 8 ranks
 
 
-@pytest.mark.parametrize('world,cfg', [(2, CFG), (4, BIG), (8, BIG)])
-def test_sharded_path_ranks(tmp_path, world, cfg):
+@pytest.mark.parametrize('world,cfg,slab_w', [(2, CFG, None), (4, BIG, None), (8, BIG, None), (2, WIDE, WIDE_SLAB_W)])
+def test_sharded_path_ranks(tmp_path, world, cfg, slab_w):
     """2 / 4 / 8 NCCL ranks, both exchange forms (peer arenas + persistent KR, host-driven collectives):
     the assembled result equals the single-process oracle (counts, mask, n_iter exact; x, w <= 1e-9)."""
     import torch
@@ -104,7 +126,8 @@ def test_sharded_path_ranks(tmp_path, world, cfg):
     if torch.cuda.device_count() < world:
         pytest.skip('needs {} GPUs'.format(world))
     from bin3c_b200 import synth
-    mp.spawn(_nccl_worker, args=(world, 29655 + world, str(tmp_path), cfg), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, 29655 + world + (10 if slab_w else 0), str(tmp_path), cfg, slab_w), nprocs=world,
+             join=True)
     com = synth.make_community(**cfg)
     for tag in ('peer', 'host'):
         parts = [dict(np.load(os.path.join(str(tmp_path), '{}{}.npz'.format(tag, r)))) for r in range(world)]
