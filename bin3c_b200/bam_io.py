@@ -51,6 +51,8 @@ SIGNATURES = {
     'b3c_bam_read_pairs': (_i64, [_p, _p, _i64]),
     'b3c_bam_set_extent': (C.c_int, [_p, _p, _i32, _p, _p, _p, _i32]),
     'b3c_bam_read_pairs_extent': (_i64, [_p, _p, _p, _i64]),
+    'b3c_bam_set_tips': (C.c_int, [_p, _i64, _p, _i32]),
+    'b3c_bam_read_pairs_tips': (_i64, [_p, _p, _p, _i64]),
     'b3c_bam_stats': (C.c_int, [_p, _p, _i32]),
     'b3c_edges_write': (_i64, [C.c_char_p, _p, _p, _p, _i64, C.c_char, _i32]),
     'b3c_edges_write_fmt': (_i64, [C.c_char_p, _p, _p, _p, _i64, C.c_char, _i32, _i32]),
@@ -86,7 +88,7 @@ def check(rc):
 
 
 STAT_NAMES = ('alignments', 'informative', 'pairs', 'short_insert', 'unpaired', 'bgzf_blocks', 'compressed_bytes',
-              'uncompressed_bytes')
+              'uncompressed_bytes', 'not_tip')
 
 
 class BamPairReader(object):
@@ -138,6 +140,18 @@ class BamPairReader(object):
         n = check(lib.b3c_bam_read_pairs_extent(self._h, rec.ctypes.data, ext.ctypes.data, int(capacity)))
         return rec[:n], ext[:n]
 
+    def set_tips(self, tip_size, tid2idx):
+        """Emit tip records (contact_map.py:631-670, 791-798): doubled ids 2 * tid + tip; before the first read."""
+        t = np.ascontiguousarray(tid2idx, dtype=np.int32)
+        check(lib.b3c_bam_set_tips(self._h, int(tip_size), t.ctypes.data, len(t)))
+
+    def read_pairs_tips(self, capacity):
+        """Up to `capacity` further (tip records, flags of the accepted same-sequence (tail, head) pairs)."""
+        rec = np.empty(int(capacity), dtype=np.uint64)
+        t10 = np.empty(int(capacity), dtype=np.uint8)
+        n = check(lib.b3c_bam_read_pairs_tips(self._h, rec.ctypes.data, t10.ctypes.data, int(capacity)))
+        return rec[:n], t10[:n]
+
     def read_pairs(self, capacity, out=None):
         """Up to `capacity` further records (an empty array at end of file)."""
         if out is None:
@@ -179,7 +193,7 @@ class BamPairReader(object):
 
 
 def pair_records_from_bam(path, sites=None, min_mapq=60, strong=None, min_insert=None, min_len=None, threads=0,
-                          bin_size=None):
+                          bin_size=None, tip_size=None):
     """
     BAM file -> (PairRecords, stats): the object `ContactMap(bam_file=...)` takes in this package.
 
@@ -187,22 +201,33 @@ def pair_records_from_bam(path, sites=None, min_mapq=60, strong=None, min_insert
                   part of this path); None -> ones.  A negative value marks "not in the FASTA".
     :param min_insert: needs `min_len` (and `sites`) to know which references are excluded, because the
                   reference applies the insert filter only to pairs that passed the exclusion test.
+    :param tip_size: tip-based map (contact_map.py:631-670): records carry doubled ids 2 * tid + tip and
+                  PairRecords.tip10 the same-sequence (tail, head) pairs; needs `min_len` like min_insert; `sites`
+                  may then be an (n_refs, 2) array of (head, tail) site counts (seq_utils.py:146-158).
     """
     from .contact_map import PairRecords
     with BamPairReader(path, threads=threads) as bam:
         s = np.ones(bam.n_refs, dtype=np.int64) if sites is None else np.asarray(sites, dtype=np.int64)
         assert len(s) == bam.n_refs, 'one site count per BAM reference'
+        in_fasta = (s >= 0) if s.ndim == 1 else (s >= 0).all(axis=1)
         tid2idx = None
+        tip10 = None
+        assert not (bin_size and tip_size), 'extent records and tip records do not combine in this build'
         if min_insert:
             assert min_len is not None, 'min_insert needs min_len'
-            keep = (bam.lengths >= min_len) & (s >= 0)                 # contact_map.py:545-564
+            keep = (bam.lengths >= min_len) & in_fasta                 # contact_map.py:545-564
             tid2idx = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+        if tip_size:
+            assert min_len is not None, 'tip_size needs min_len'
+            keep = (bam.lengths >= min_len) & in_fasta
+            tid2idx = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
+            bam.set_tips(tip_size, tid2idx)
         extent = None
         if bin_size:
             # the extent map (bin3C mkmap --bin-size): bins over the sequences that pass the length filter
             from .contact_map import ExtentGrouping
             assert min_len is not None, 'bin_size needs min_len'
-            keep = (bam.lengths >= min_len) & (s >= 0)
+            keep = (bam.lengths >= min_len) & in_fasta
             tid2idx = np.where(keep, np.cumsum(keep) - 1, -1).astype(np.int32)
             bam.set_extent(tid2idx, ExtentGrouping.from_lengths(bam.lengths[keep], bin_size))
         bam.set_filter(min_mapq=min_mapq, strong=strong, min_insert=min_insert, tid2idx=tid2idx)
@@ -215,12 +240,25 @@ def pair_records_from_bam(path, sites=None, min_mapq=60, strong=None, min_insert
                 parts.append((r, e))
             records = np.concatenate([p[0] for p in parts]) if parts else np.empty(0, dtype=np.uint64)
             extent = np.concatenate([p[1] for p in parts]) if parts else np.empty(0, dtype=np.uint64)
+        elif tip_size:
+            parts = []
+            while True:
+                r, t = bam.read_pairs_tips(1 << 22)
+                if len(r) == 0:
+                    break
+                parts.append((r, t))
+            records = np.concatenate([p[0] for p in parts]) if parts else np.empty(0, dtype=np.uint64)
+            flags = np.concatenate([p[1] for p in parts]) if parts else np.empty(0, dtype=np.uint8)
+            # BAM reference ids of the accepted same-sequence (tail, head) pairs
+            tip10 = ((records[flags != 0] & np.uint64(0x7fffffff)) >> np.uint64(1)).astype(np.int64)
         else:
             records = bam.read_all()
         stats = bam.stats()
         meta = dict(min_mapq=min_mapq, strong=strong, min_insert=min_insert or None, min_len=min_len,
-                    bin_size=bin_size or None, short_insert=stats['short_insert'])
-        return PairRecords(bam.lengths, s, records, references=bam.references, extent_records=extent, meta=meta), stats
+                    bin_size=bin_size or None, short_insert=stats['short_insert'], tip_size=tip_size or None,
+                    not_tip=stats['not_tip'])
+        return PairRecords(bam.lengths, s, records, references=bam.references, extent_records=extent, meta=meta,
+                           tip10=tip10), stats
 
 
 def records_bytes(n_refs):

@@ -36,7 +36,19 @@ def to_edges(contact_map, norm=True, bisto=False, scale=False, min_len=None, min
     else:
         contact_map.order.set_mask_only(contact_map.get_primary_acceptance_mask())
 
-    res = contact_map._subspace_dev(None, want_sub=False, want_edges=True, scale=scale, force=True)
+    if contact_map.is_tipbased():
+        # the tensor's 2-D marginal over the accepted sequences (get_subspace(marginalise=True), cluster.py:310),
+        # turned into edges by the same device kernels
+        import torch
+        from . import device as dev
+        sub = contact_map.get_subspace(marginalise=True, flatten=False).tocsr()
+        keep = dev.to_device(np.ones(sub.shape[0], dtype=np.uint8), torch.uint8)
+        res = dev.compress_edges(dev.DeviceCSR.from_scipy(sub, np.float64), keep, want_sub=False, want_edges=True,
+                                 scale=scale)
+        for k in ('u', 'v', 'w'):
+            res[k] = res[k][:res['n_edges']]
+    else:
+        res = contact_map._subspace_dev(None, want_sub=False, want_edges=True, scale=scale, force=True)
     logger.info('Graph will have {} nodes'.format(contact_map.order.count_accepted()))
     if device:
         return res['u'], res['v'], res['w'], res['scl']

@@ -48,15 +48,18 @@ class PairRecords(object):
                   needed by ContactMap(bin_size=...)
     """
 
-    def __init__(self, lengths, sites, records, references=None, extent_records=None, meta=None):
+    def __init__(self, lengths, sites, records, references=None, extent_records=None, meta=None, tip10=None):
         self.extent_records = extent_records      # bin-level records for the extent map (bam_io, bin_size=...)
+        # tip-based map (bam_io, tip_size=...): the records carry doubled ids 2 * tid + tip; tip10 = BAM reference ids
+        # of the accepted same-sequence pairs whose tips are (tail, head) in read order; sites is then [n_refs, 2]
+        self.tip10 = tip10
         # how the records were made (bam_io.pair_records_from_bam): min_mapq, strong, min_insert, min_len, bin_size and
         # the reader's short_insert count.  ContactMap checks its own arguments against these, so that e.g. an extent
         # map is never built over bins other than the ones the reader used.
         self.meta = dict(meta) if meta else None
         self.lengths = np.asarray(lengths, dtype=np.int64)
         self.sites = np.asarray(sites, dtype=np.int64)
-        assert self.lengths.shape == self.sites.shape
+        assert self.lengths.shape == self.sites.shape[:1] and (self.sites.ndim == 1 or self.sites.shape[1] == 2)
         self.references = references
         self.records = records
 
@@ -186,13 +189,21 @@ class ContactMap(object):
                  min_size=0, max_fold=None, random_seed=None, strong=None, bin_size=None, tip_size=None,
                  precount=False):
 
-        assert tip_size is None, 'tip-based maps are out of scope (unreachable from the bin3C CLI)'
+        assert not (tip_size and bin_size), 'tip records and extent records do not combine in this build'
         if not isinstance(bam_file, PairRecords):
             # the call bin3C.py mkmap makes (bin3C.py:148-158): a BAM path and a FASTA path.  The BAM is decoded by
             # the native reader (libbin3c_io.so) with this map's matcher, insert filter and bins; the site counts come
             # from the FASTA (seq_sites.fasta_site_table), or from `seq_file` given as an array / dict / callable.
-            bam_file = self._open_bam(bam_file, enzymes, seq_file, min_insert, min_mapq, min_len, strong, bin_size)
+            bam_file = self._open_bam(bam_file, enzymes, seq_file, min_insert, min_mapq, min_len, strong, bin_size,
+                                      tip_size)
         meta = bam_file.meta
+        if tip_size:
+            assert meta is not None and meta.get('tip_size') == tip_size and meta.get('min_len') == min_len, \
+                'tip_size needs tip records: bam_io.pair_records_from_bam(path, tip_size=..., min_len=...) with the ' \
+                "map's own tip_size and min_len"
+            assert bam_file.sites.ndim == 2, 'a tip-based map takes (head, tail) site counts per reference'
+        else:
+            assert meta is None or not meta.get('tip_size'), 'these are tip records: the map needs tip_size'
         assert not bin_size or bam_file.extent_records is not None, \
             'bin_size needs extent records: bam_io.pair_records_from_bam(path, bin_size=..., min_len=...)'
         if meta is None:
@@ -243,14 +254,16 @@ class ContactMap(object):
         ref_count = {'seq_missing': 0, 'too_short': 0}
         logger.info('Reading sequences...')
         too_short = bam_file.lengths < min_len
-        missing = ~too_short & (bam_file.sites < 0)
+        missing = ~too_short & ((bam_file.sites < 0) if bam_file.sites.ndim == 1 else (bam_file.sites < 0).any(axis=1))
         ref_count['too_short'] = int(too_short.sum())
         ref_count['seq_missing'] = int(missing.sum())
         keep = np.flatnonzero(~too_short & ~missing)
         offset = 0
         for n in keep:
             rlen = int(bam_file.lengths[n])
-            self.seq_info.append(SeqInfo(offset, int(n), bam_file.name(n), rlen, int(bam_file.sites[n])))
+            # tip-based: [head sites, tail sites] (seq_utils.py:146-158)
+            st = [int(v) for v in bam_file.sites[n]] if bam_file.sites.ndim == 2 else int(bam_file.sites[n])
+            self.seq_info.append(SeqInfo(offset, int(n), bam_file.name(n), rlen, st))
             offset += rlen
 
         self.total_len = offset
@@ -277,7 +290,7 @@ class ContactMap(object):
         self.set_primary_acceptance_mask()
 
     @staticmethod
-    def _open_bam(path, enzymes, seq_file, min_insert, min_mapq, min_len, strong, bin_size):
+    def _open_bam(path, enzymes, seq_file, min_insert, min_mapq, min_len, strong, bin_size, tip_size=None):
         """BAM path -> PairRecords with this map's filters (contact_map.py:520-564: FASTA pass, header, reference table).
         `seq_file`: a FASTA path; or per-reference site counts as an array (one per BAM reference), a dict
         {reference name: sites} (absent = not in the FASTA), or a callable (name, length) -> sites."""
@@ -288,12 +301,12 @@ class ContactMap(object):
         if callable(seq_file):
             sites = np.array([seq_file(nm, int(ln)) for nm, ln in zip(names, lengths)], dtype=np.int64)
         elif isinstance(seq_file, dict):
-            sites = np.array([seq_file.get(nm, -1) for nm in names], dtype=np.int64)
+            sites = np.array([seq_file.get(nm, [-1, -1] if tip_size else -1) for nm in names], dtype=np.int64)
         elif isinstance(seq_file, (str, bytes, os.PathLike)):
             from .seq_sites import fasta_site_table
             logger.info('Analyzing sites...')
-            info = fasta_site_table(seq_file, enzymes, min_len or 0)
-            sites = np.full(len(names), -1, dtype=np.int64)
+            info = fasta_site_table(seq_file, enzymes, min_len or 0, tip_size=tip_size)
+            sites = np.full((len(names), 2) if tip_size else len(names), -1, dtype=np.int64)
             for n, (nm, ln) in enumerate(zip(names, lengths)):
                 fa = info.get(nm)
                 if fa is None:
@@ -305,9 +318,11 @@ class ContactMap(object):
                 sites[n] = fa['sites']
         else:
             sites = np.asarray(seq_file, dtype=np.int64)
-            assert sites.shape == lengths.shape, 'one site count per BAM reference'
+            assert sites.shape[:1] == lengths.shape, 'one site count per BAM reference'
+        if tip_size and sites.ndim == 1:
+            sites = np.array([[v, v] if np.ndim(v) == 0 else list(v) for v in sites.tolist()], dtype=np.int64)
         rec, _ = bam_io.pair_records_from_bam(path, sites=sites, min_mapq=min_mapq, strong=strong, min_insert=min_insert,
-                                              min_len=min_len, bin_size=bin_size)
+                                              min_len=min_len, bin_size=bin_size, tip_size=tip_size)
         return rec
 
     # ---- pickling: host containers only ------------------------------------------------------
@@ -394,6 +409,24 @@ class ContactMap(object):
         idx = self.make_reverse_index('refid')
         lut[np.fromiter(idx.keys(), dtype=np.int64, count=len(idx))] = \
             np.fromiter(idx.values(), dtype=np.int32, count=len(idx))
+
+        if self.is_tipbased():
+            # each tip is tracked separately: the single count becomes a 2x2 interaction matrix and the map a tensor
+            # of dimension NxNx2x2 (contact_map.py:681-684); accumulated on the device over the doubled ids
+            from . import sparse_utils
+            n_rec = int(bam.records.numel()) if isinstance(bam.records, torch.Tensor) else len(bam.records)
+            acc = sparse_utils.Sparse4DAccumulator(self.total_seq, tid2idx=lut, pair_capacity=max(n_rec, 1))
+            acc.add_tip_pairs(bam.records, bam.tip10)
+            self._dev.pop('seq_map', None)
+            self._host['seq_map'] = acc.get_coo()
+            counts.update(acc.counts)
+            counts['short_insert'] = int(bam.meta.get('short_insert') or 0)
+            counts['not_tip'] = int(bam.meta.get('not_tip') or 0)
+            self.pair_counts = counts
+            self._map_weight = int(self._host['seq_map'].data.sum(dtype=np.uint64))
+            logger.info('Pair accounting: {}'.format(counts))
+            logger.info('Total extent map weight {}'.format(self.map_weight()))
+            return
 
         from .pipeline import HotPath
         hp = HotPath(lut, self.order.lengths(), np.array([si.sites for si in self.seq_info], dtype=np.int32),
@@ -484,6 +517,20 @@ class ContactMap(object):
             logger.debug('Using existing mask')
             return self.get_primary_acceptance_mask()
 
+        if self.is_tipbased():
+            # signal of a tensor: maximum off-diagonal of its 2-D marginal (sparse_utils.max_offdiag_4d, :896-897)
+            from . import sparse_utils
+            acceptance_mask = np.ones(self.total_seq, dtype=np.bool_)
+            _mask = self.order.lengths() >= min_len
+            logger.debug('Minimum length threshold removing: {}'.format(self.total_seq - _mask.sum()))
+            acceptance_mask &= _mask
+            _mask = sparse_utils.max_offdiag_4d(self.seq_map) >= min_sig
+            logger.debug('Minimum signal threshold removing: {}'.format(self.total_seq - _mask.sum()))
+            acceptance_mask &= _mask
+            self.primary_acceptance_mask = acceptance_mask
+            logger.debug('Accepted sequences: {}'.format(self.primary_acceptance_mask.sum()))
+            return self.get_primary_acceptance_mask()
+
         csr = self._seq_map_dev()
         lengths = dev.to_device(np.ascontiguousarray(self.order.lengths()), torch.int32)
         signal = dev.max_offdiag(csr)
@@ -513,6 +560,21 @@ class ContactMap(object):
 
         if self.order.count_accepted() < 1:
             raise NoneAcceptedException()
+
+        if self.is_tipbased():
+            from . import sparse_utils
+            _map = self.seq_map.astype(np.float64)
+            if norm:
+                _map = self._norm_seq(_map, True, mean_type=mean_type, use_sites=True)
+                logger.debug('Map normalized')
+            if bisto:
+                _map, scl = sparse_utils.kr_biostochastic_4d(_map)
+                self.kr_info = sparse_utils.kr_biostochastic.last_info
+                self.bisto_scale = scl
+                logger.debug('Map balanced')
+            self._dev.pop('processed_map', None)
+            self._host['processed_map'] = _map
+            return
 
         _map = self._seq_map_dev()
 
@@ -558,7 +620,16 @@ class ContactMap(object):
         (contact_map.py:1110-1145 with fast_norm_fullseq_bysite, :100-113).
         """
         import torch
-        assert not tip_based, 'tip-based maps are out of scope'
+        if tip_based:
+            # fast_norm_tipbased_bysite (contact_map.py:84-97): data[n] *= 1.0 / (sites[i, k] * sites[j, l]) over the
+            # (head, tail) site counts, zeros taken as one (:1103-1108)
+            assert use_sites, 'length-based normalisation is dead code from the bin3C CLI'
+            logger.debug('Doing site based normalisation')
+            _sites = self._get_sites()
+            _map = _map.astype(np.float64)
+            i, j, k, l = _map.coords
+            _map.data *= 1.0 / (_sites[i, k] * _sites[j, l])
+            return _map
         if not use_sites:
             raise NotImplementedError('length-based normalisation is dead code from the bin3C CLI '
                                       '(prepare_seq_map hard-codes use_sites=True, contact_map.py:933)')
@@ -581,6 +652,26 @@ class ContactMap(object):
             'marginalise and flatten are mutually exclusive'
         if permute:
             raise NotImplementedError('reordering is plot-only (contact_map.py:1066-1085) and out of scope')
+
+        if self.is_tipbased():
+            from . import sparse_utils
+            _map = self.processed_map.astype(dtype)
+            if external_mask is not None:
+                _mask = self.get_primary_acceptance_mask()
+                logger.info('Beginning with sequences after primary filtering: {}'.format(_mask.sum()))
+                _mask &= external_mask
+                logger.info('Active sequences after applying external mask: {}'.format(_mask.sum()))
+                self.order.set_mask_only(_mask)
+            if self.order.count_accepted() < self.total_seq:
+                _map = sparse_utils.compress_4d(_map, self.order.mask_vector())
+                logger.info('After removing filtered sequences map dimensions: {}'.format(_map.shape))
+            if marginalise:
+                logger.debug('Marginalising NxNx2x2 tensor to NxN matrix')
+                _map = _map.sum(axis=(2, 3)).to_scipy_sparse()
+            elif flatten:
+                logger.debug('Flattening NxNx2x2 tensor to 2Nx2N matrix')
+                _map = sparse_utils.flatten_tensor_4d(_map)
+            return _map
 
         res = self._subspace_dev(external_mask, want_sub=True, want_edges=False, scale=False)
         if res is None:

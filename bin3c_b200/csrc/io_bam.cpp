@@ -95,6 +95,9 @@ struct b3c_bam {
     // extent map (contact_map.py:779-788): bins per sequence
     bool extent = false;
     std::vector<int64_t> ext_first, ext_ptr, ext_edges;
+    // tip-based map (contact_map.py:631-670): size of the sequence ends that count, 0 = whole sequences
+    int64_t tip_size = 0;
+    int64_t n_not_tip = 0;
     // pairing state (contact_map.py:720-731): the pending first mate
     bool have_r1 = false;
     std::string r1_name;
@@ -480,12 +483,12 @@ int next_alignment(b3c_bam *h, Aln *a) {
     }
     a->match = m;
     a->pos5 = a->pos;
-    if (h->extent && (a->flag & 0x10)) {
+    if ((h->extent || h->tip_size > 0) && (a->flag & 0x10)) {
         // r.alen = pysam reference_length: the CIGAR operations that consume the reference (M, D, N, =, X).  A mapped
         // reverse read without a CIGAR has alen None in the reference, whose `r.pos + r.alen` then raises: an error
         // here too, not a silent span of zero.
         if (n_ops == 0 && !(a->flag & 0x4))
-            return fail_format(h, "mapped reverse read without a CIGAR: its 5' end is undefined (extent records)");
+            return fail_format(h, "mapped reverse read without a CIGAR: its 5' end is undefined (extent / tip records)");
         int64_t span = 0;
         const uint32_t n_cig = n_ops;
         for (uint32_t k = 0; k < n_cig; ++k) {
@@ -589,14 +592,40 @@ int b3c_bam_set_filter(b3c_bam *h, int32_t min_mapq, int32_t strong, int32_t min
     h->strong = strong < 0 ? 0 : strong;
     h->min_insert = min_insert < 0 ? 0 : min_insert;
     if (h_tid2idx) h->tid2idx.assign(h_tid2idx, h_tid2idx + n_refs);
-    else if (!h->extent) h->tid2idx.clear();          // the extent table (b3c_bam_set_extent) is kept
+    else if (!h->extent && h->tip_size <= 0) h->tid2idx.clear();      // the table of b3c_bam_set_extent / _set_tips is kept
     return 0;
 }
 
-static int64_t read_pairs_impl(b3c_bam *h, uint64_t *h_records, uint64_t *h_extent, int64_t capacity);
+static int64_t read_pairs_impl(b3c_bam *h, uint64_t *h_records, uint64_t *h_extent, int64_t capacity, uint8_t *h_tip10);
 
 int64_t b3c_bam_read_pairs(b3c_bam *h, uint64_t *h_records, int64_t capacity) {
-    return read_pairs_impl(h, h_records, nullptr, capacity);
+    return read_pairs_impl(h, h_records, nullptr, capacity, nullptr);
+}
+
+int b3c_bam_set_tips(b3c_bam *h, int64_t tip_size, const int32_t *h_tid2idx, int32_t n_refs) {
+    if (!h || tip_size <= 0 || !h_tid2idx || n_refs != (int32_t)h->ref_names.size()) {
+        set_err("b3c_bam_set_tips: needs a positive tip size and the tid -> index table of all references");
+        return B3C_IO_ERR_ARG;
+    }
+    if (h->started || h->extent) {
+        set_err("b3c_bam_set_tips: records have already been read, or extent records are on (the two do not combine)");
+        return B3C_IO_ERR_ARG;
+    }
+    if (n_refs >= (1 << 30)) {
+        set_err("b3c_bam_set_tips: doubled reference ids do not fit in 31 bits");
+        return B3C_IO_ERR_ARG;
+    }
+    h->tid2idx.assign(h_tid2idx, h_tid2idx + n_refs);
+    h->tip_size = tip_size;
+    return 0;
+}
+
+int64_t b3c_bam_read_pairs_tips(b3c_bam *h, uint64_t *h_records, uint8_t *h_tip10, int64_t capacity) {
+    if (!h || h->tip_size <= 0 || (!h_tip10 && capacity > 0)) {
+        set_err("b3c_bam_read_pairs_tips: call b3c_bam_set_tips first");
+        return B3C_IO_ERR_ARG;
+    }
+    return read_pairs_impl(h, h_records, nullptr, capacity, h_tip10);
 }
 
 int64_t b3c_bam_read_pairs_extent(b3c_bam *h, uint64_t *h_records, uint64_t *h_extent_records, int64_t capacity) {
@@ -604,7 +633,7 @@ int64_t b3c_bam_read_pairs_extent(b3c_bam *h, uint64_t *h_records, uint64_t *h_e
         set_err("b3c_bam_read_pairs_extent: call b3c_bam_set_extent first");
         return B3C_IO_ERR_ARG;
     }
-    return read_pairs_impl(h, h_records, h_extent_records, capacity);
+    return read_pairs_impl(h, h_records, h_extent_records, capacity, nullptr);
 }
 
 int b3c_bam_set_extent(b3c_bam *h, const int32_t *h_tid2idx, int32_t n_refs, const int64_t *h_first_bin,
@@ -653,7 +682,21 @@ static uint64_t extent_bin(const b3c_bam *h, int32_t tid, int64_t x, int32_t n_r
     return (uint64_t)(h->ext_first[ix] + (a - lo));
 }
 
-static int64_t read_pairs_impl(b3c_bam *h, uint64_t *h_records, uint64_t *h_extent, int64_t capacity) {
+// _on_tip_withlocs (contact_map.py:631-670), one mate: which end of a sequence of length `len` the position p falls in
+// (0 = head, 1 = tail), or -1.  Ends of `tip` bp when they do not overlap (len > 2 tip); otherwise the nearer end, and
+// neither when p is exactly in the middle.
+static int tip_of(int64_t p, int64_t len, int64_t tip) {
+    if (len > 2 * tip) {
+        if (p < tip) return 0;
+        if (p > len - tip) return 1;
+        return -1;
+    }
+    if (p < len - p) return 0;
+    if (len - p < p) return 1;
+    return -1;
+}
+
+static int64_t read_pairs_impl(b3c_bam *h, uint64_t *h_records, uint64_t *h_extent, int64_t capacity, uint8_t *h_tip10) {
     if (!h || (!h_records && capacity > 0) || capacity < 0) {
         set_err("b3c_bam_read_pairs: bad argument");
         return B3C_IO_ERR_ARG;
@@ -703,7 +746,34 @@ static int64_t read_pairs_impl(b3c_bam *h, uint64_t *h_records, uint64_t *h_exte
                 continue;
             }
         }
-        const uint64_t t1 = in1 ? (uint32_t)h->r1_tid : BAD_TID, t2 = in2 ? (uint32_t)a.tid : BAD_TID;
+        uint64_t t1 = in1 ? (uint32_t)h->r1_tid : BAD_TID, t2 = in2 ? (uint32_t)a.tid : BAD_TID;
+        if (h->tip_size > 0) {
+            // Tip records: reference ids become 2 * tid + tip.  A pair that passed the exclusion and matcher tests
+            // (:733-739) is assigned tips from the 5' positions (:757-758, :791); when either mate lies in neither end it
+            // is dropped here and counted not_tip (:792-794).  The reference orders a pair by internal index (:774-777);
+            // the accumulator does the same with the doubled ids.  On ONE sequence the tensor element is
+            // [tip(read 1), tip(read 2)] in read order (:746, no swap for ix1 == ix2): the (tail, head) pairs are marked
+            // in h_tip10, because the symmetric accumulator merges them with the (head, tail) ones.
+            if (h_tip10) h_tip10[n] = 0;
+            if (pass && in1 && in2 && h->tid2idx[h->r1_tid] >= 0 && h->tid2idx[a.tid] >= 0) {
+                const int k1 = tip_of(h->r1_pos5, h->ref_lens[h->r1_tid], h->tip_size);
+                const int k2 = tip_of(a.pos5, h->ref_lens[a.tid], h->tip_size);
+                if (k1 < 0 || k2 < 0) {
+                    h->n_not_tip += 1;
+                    continue;
+                }
+                t1 = 2 * t1 + (uint64_t)k1;
+                t2 = 2 * t2 + (uint64_t)k2;
+                if (h->r1_tid == a.tid && h_tip10) {
+                    const bool swap = (h->r1_flag & 0x80) != 0;                     // r1.is_read2 (:746)
+                    const int ka = swap ? k2 : k1, kb = swap ? k1 : k2;
+                    h_tip10[n] = (ka == 1 && kb == 0) ? 1 : 0;
+                }
+            } else {
+                t1 = in1 ? 2 * t1 : BAD_TID;                                        // counted by the accumulator as
+                t2 = in2 ? 2 * t2 : BAD_TID;                                        // ref_excluded / poor_match
+            }
+        }
         if (h_extent) {
             const uint64_t b1 = extent_bin(h, h->r1_tid, h->r1_pos5, n_refs), b2 = extent_bin(h, a.tid, a.pos5, n_refs);
             h_extent[n] = b1 | ((uint64_t)(pass ? 1u : 0u) << 31) | (b2 << 32);
@@ -715,9 +785,9 @@ static int64_t read_pairs_impl(b3c_bam *h, uint64_t *h_records, uint64_t *h_exte
 
 int b3c_bam_stats(const b3c_bam *h, int64_t *h_stats, int32_t n_stats) {
     if (!h || !h_stats || n_stats < 0) return B3C_IO_ERR_ARG;
-    const int64_t v[8] = {h->n_aln, h->n_inf, h->n_pairs, h->n_short, h->n_orphan, h->n_blocks.load(), h->c_bytes.load(),
-                          h->u_bytes.load()};
-    for (int i = 0; i < n_stats && i < 8; ++i) h_stats[i] = v[i];
+    const int64_t v[9] = {h->n_aln, h->n_inf, h->n_pairs, h->n_short, h->n_orphan, h->n_blocks.load(), h->c_bytes.load(),
+                          h->u_bytes.load(), h->n_not_tip};
+    for (int i = 0; i < n_stats && i < 9; ++i) h_stats[i] = v[i];
     return 0;
 }
 

@@ -45,9 +45,22 @@ def count_sites(seq, patterns):
     return sum(sum(1 for _ in p.finditer(seq)) for p in patterns)
 
 
-def fasta_site_table(path, enzyme_names, min_len=0):
+def tip_sites(seq, patterns, tip_size):
+    """[head sites, tail sites] of a tip-based map (SiteCounter.count_sites, seq_utils.py:146-158): the first and last
+    tip_size bases, or the two halves of a sequence shorter than 2 tip_size -- with Python 2's integer division,
+    seq[:n/2] and seq[-n/2:]: -n/2 rounds towards minus infinity, so the tail half of an odd-length sequence is the
+    longer one."""
+    n = len(seq)
+    if n < 2 * tip_size:
+        l_tip, r_tip = seq[:n // 2], seq[(-n) // 2:]
+    else:
+        l_tip, r_tip = seq[:tip_size], seq[-tip_size:]
+    return [count_sites(l_tip, patterns), count_sites(r_tip, patterns)]
+
+
+def fasta_site_table(path, enzyme_names, min_len=0, tip_size=None):
     """{sequence id: {'sites': n, 'length': L}} for the sequences of at least min_len bases -- the reference's
-    `fasta_info` (contact_map.py:520-531).  Plain or gzip'd FASTA."""
+    `fasta_info` (contact_map.py:520-531).  Plain or gzip'd FASTA.  With tip_size, 'sites' is [head, tail]."""
     pats = _patterns(enzyme_names)
     opener = gzip.open if str(path).endswith('.gz') else open
     info = {}
@@ -57,7 +70,8 @@ def fasta_site_table(path, enzyme_names, min_len=0):
             return
         seq = ''.join(parts).upper()
         if len(seq) >= min_len:
-            info[name] = {'sites': count_sites(seq, pats), 'length': len(seq)}
+            info[name] = {'sites': tip_sites(seq, pats, tip_size) if tip_size else count_sites(seq, pats),
+                          'length': len(seq)}
 
     name, parts = None, []
     with opener(path, 'rt') as fh:

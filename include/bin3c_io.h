@@ -90,14 +90,27 @@ int b3c_bam_set_extent(b3c_bam *bam, const int32_t *h_tid2idx, int32_t n_refs, c
                        const int64_t *h_edge_ptr, const int64_t *h_upper_edges, int32_t n_seq);
 int64_t b3c_bam_read_pairs_extent(b3c_bam *bam, uint64_t *h_records, uint64_t *h_extent_records, int64_t capacity);
 
+/* The TIP-BASED map (contact_map.py:631-670, 791-798; the N x N x 2 x 2 tensor of sparse_utils.py:317-409).  After
+ * b3c_bam_set_tips every pair that passes the exclusion and matcher tests (and the insert filter) is assigned the
+ * sequence end each mate's 5' position falls in -- ends of tip_size bp, or the nearer end of a sequence of at most
+ * 2 tip_size bp -- and b3c_bam_read_pairs_tips writes its record with the DOUBLED ids 2 * tid + tip (0 = head,
+ * 1 = tail); a pair with a mate in neither end is dropped and counted not_tip (b3c_bam_stats, index 8).  Fed to an
+ * accumulator over 2 N ids (table entry 2 t + k -> 2 idx[t] + k), the records give the flattened, symmetric
+ * 2N x 2N tensor.  On ONE sequence the reference keeps [tip(read 1), tip(read 2)] unordered (no swap for ix1 == ix2,
+ * :774-777): h_tip10[i] = 1 marks the accepted (tail, head) pairs, which the symmetric accumulator merges with the
+ * (head, tail) ones, so that the host can take them apart again.  Does not combine with extent records. */
+int b3c_bam_set_tips(b3c_bam *bam, int64_t tip_size, const int32_t *h_tid2idx, int32_t n_refs);
+int64_t b3c_bam_read_pairs_tips(b3c_bam *bam, uint64_t *h_records, uint8_t *h_tip10, int64_t capacity);
+
 /* h_stats[0] alignments read (what bam.count(until_eof=True) returns once the file is exhausted)
  * h_stats[1] informative alignments (mapped, primary, not supplementary; :628)
- * h_stats[2] pairs found (records written + short_insert)
+ * h_stats[2] pairs found (records written + short_insert + not_tip)
  * h_stats[3] short_insert (:765)
  * h_stats[4] informative alignments left without a mate
  * h_stats[5] BGZF blocks inflated
  * h_stats[6] compressed bytes consumed
- * h_stats[7] uncompressed bytes produced */
+ * h_stats[7] uncompressed bytes produced
+ * h_stats[8] not_tip (:792-794; tip records only) */
 int b3c_bam_stats(const b3c_bam *bam, int64_t *h_stats, int32_t n_stats);
 
 /* Narrow pair records for the host->device copy (include/bin3c_b200.h: b3c_accum_add_pairs_packed).

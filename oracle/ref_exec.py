@@ -102,6 +102,94 @@ def kr_with_iterations(fns, m, **kw):
     return bal, x, cap.n_iter, cap.warnings
 
 
+# ---- the tip-based tensor functions (sparse_utils.py:317-509) over a stand-in for pydata `sparse` -------------------
+class SparseShim(object):
+    """
+    Stand-in for the `sparse` module (sparse==0.3.1, Pipfile.lock:381; not installed here): the part of sparse.COO the
+    reference's 4-D functions touch.  COO(coords, data, shape, has_duplicates): coordinates sorted row-major,
+    duplicates summed when flagged (COO.__init__ of 0.3.1 sorts unless sorted=True and sums when has_duplicates);
+    .coords .data .shape .nnz .astype() .sum(axis=(2, 3)) -> 2-D COO with .tocsr() / .to_scipy_sparse().
+    TEST INFRASTRUCTURE: lets the reference's own code run here; it is not the reference's dependency itself.
+    """
+
+    class COO(object):
+        def __init__(self, coords, data=None, shape=None, has_duplicates=True, sorted=False):
+            coords = np.asarray(coords, dtype=np.int64)
+            data = np.asarray(data)
+            if coords.ndim == 1:
+                coords = coords.reshape(len(shape), -1)
+            self.shape = tuple(int(v) for v in shape)
+            if not sorted and coords.shape[1]:
+                lin = np.ravel_multi_index(tuple(coords), self.shape)
+                o = np.argsort(lin, kind='stable')
+                coords, data, lin = coords[:, o], data[o], lin[o]
+                if has_duplicates and len(lin) > 1:
+                    first = np.concatenate([[True], lin[1:] != lin[:-1]])
+                    if not first.all():
+                        data = np.add.reduceat(data, np.flatnonzero(first)).astype(data.dtype)
+                        coords = coords[:, first]
+            self.coords, self.data = coords, data
+
+        @property
+        def nnz(self):
+            return self.coords.shape[1]
+
+        @property
+        def ndim(self):
+            return len(self.shape)
+
+        def astype(self, dtype):
+            return SparseShim.COO(self.coords.copy(), self.data.astype(dtype), self.shape, has_duplicates=False,
+                                  sorted=True)
+
+        def sum(self, axis=None):
+            if axis is None:
+                return self.data.sum()
+            keep = [a for a in range(self.ndim) if a not in tuple(axis)]
+            data = self.data
+            if np.issubdtype(data.dtype, np.unsignedinteger):
+                data = data.astype(np.uint64)              # numpy's sum of uint32 accumulates in uint64
+            return SparseShim.COO(self.coords[keep], data, tuple(self.shape[a] for a in keep), has_duplicates=True)
+
+        def to_scipy_sparse(self):
+            assert self.ndim == 2
+            return scisp.coo_matrix((self.data, (self.coords[0], self.coords[1])), shape=self.shape)
+
+        def tocsr(self):
+            return self.to_scipy_sparse().tocsr()
+
+        def to_coo(self):
+            return self
+
+    class DOK(object):
+        pass
+
+
+SLICES_4D = {
+    'Sparse4DAccumulator': ('mzd/sparse_utils.py', 317, 409),
+    'max_offdiag_4d': ('mzd/sparse_utils.py', 412, 421),
+    'flatten_tensor_4d': ('mzd/sparse_utils.py', 424, 443),
+    'compress_4d': ('mzd/sparse_utils.py', 446, 477),
+    'dotdot': ('mzd/sparse_utils.py', 480, 492),
+    'kr_biostochastic_4d': ('mzd/sparse_utils.py', 495, 509),
+}
+
+
+def load_4d():
+    """Exec the reference's tip-based tensor functions (sparse_utils.py:317-509) with SparseShim as `sparse`; returns
+    them in a dict together with the 2-D functions they call."""
+    fns = load()
+    ns = {'np': _NpShim(), 'scisp': scisp, 'sparse': SparseShim, 'logger': fns['logger'], 'xrange': range,
+          'max_offdiag': fns['max_offdiag'], 'kr_biostochastic': fns['kr_biostochastic']}
+    for name, (rel, lo, hi) in SLICES_4D.items():
+        with open(os.path.join(REFERENCE_ROOT, rel), 'r') as fh:
+            lines = fh.readlines()[lo - 1:hi]
+        exec(compile(textwrap.dedent(''.join(lines)), '{}:{}-{}'.format(rel, lo, hi), 'exec'), ns)
+    out = dict(fns)
+    out.update({k: ns[k] for k in SLICES_4D})
+    return out
+
+
 # ---- the extent map's bins (contact_map.py:116-156) and find_nearest_jit (:49-62) -----------------------------
 class Py2Int(int):
     """An int whose `/` is Python 2's: integer division when the other operand is an int (contact_map.py:132), true
@@ -189,16 +277,19 @@ class _FakeBam(object):
         return It()
 
 
-def run_bin_map(alignments, ref_lengths, idx_of, n_seq, min_mapq=0, strong=None, min_insert=None, grouping=None):
+def run_bin_map(alignments, ref_lengths, idx_of, n_seq, min_mapq=0, strong=None, min_insert=None, grouping=None,
+                tip_size=None):
     """
     Exec the reference's ContactMap._bin_map verbatim (contact_map.py:602-809) on a stub instance and a fake BAM of
     duck-typed records; Sparse2DAccumulator and find_nearest_jit are the reference's own too.  `grouping` is an
     exec'd reference ExtentGrouping (load_extent) or None.  A mapped record without CIGAR has alen None, which the
     reference cannot add to a position: feed such records only as forward reads.
+    With `tip_size` the map is the tip-based tensor: the reference's own Sparse4DAccumulator (over SparseShim) and
+    _on_tip_withlocs; seq_map is then a SparseShim.COO of shape (N, N, 2, 2).
     Returns dict(seq_map coo, extent_map coo or None, counts dict).
     """
     import collections
-    fns = load()
+    fns = load_4d() if tip_size else load()
     _, find_nearest = load_extent()
     logger = logging.getLogger('mzd.contact_map.exec')
     captured = {}
@@ -214,6 +305,7 @@ def run_bin_map(alignments, ref_lengths, idx_of, n_seq, min_mapq=0, strong=None,
 
     class SU(object):
         Sparse2DAccumulator = fns['Sparse2DAccumulator']
+        Sparse4DAccumulator = fns.get('Sparse4DAccumulator')
 
     ns = {'np': _NpShim(), 'sparse_utils': SU, 'logger': logger, 'OrderedDict': collections.OrderedDict,
           'find_nearest_jit': find_nearest, 'xrange': range}
@@ -227,11 +319,11 @@ def run_bin_map(alignments, ref_lengths, idx_of, n_seq, min_mapq=0, strong=None,
     me.strong, me.min_insert, me.min_mapq = strong, min_insert, min_mapq
     me.total_seq, me.total_len, me.total_reads = n_seq, 0, None
     me.bin_size = grouping.bin_size if grouping is not None else None
-    me.grouping, me.tip_size = grouping, None
+    me.grouping, me.tip_size = grouping, tip_size
     me.extent_map = me.seq_map = None
-    me.is_tipbased = lambda: False
+    me.is_tipbased = lambda: tip_size is not None
     me.make_reverse_index = lambda field: dict(idx_of)
-    me.map_weight = lambda: int(me.seq_map.sum())
+    me.map_weight = lambda: int(me.seq_map.data.sum()) if tip_size else int(me.seq_map.sum())
     try:
         ns['_bin_map'](me, _FakeBam(alignments, ref_lengths))
     finally:
@@ -292,7 +384,7 @@ def run_to_graph(sub_map, n_accepted, scale=True, contact_map=None):
 
 # ---- the whole reference path: SeqOrder + ContactMap classes exec'd, driven as bin3C.py mkmap / cluster do ------------
 def run_reference_path(alignments, ref_lengths, ref_sites, min_len, min_sig, min_mapq=60, strong=None, min_insert=None,
-                       bin_size=None, seed=1):
+                       bin_size=None, seed=1, tip_size=None):
     """
     Exec the reference's SeqOrder and ContactMap classes (contact_map.py:159-485, 486-end), find_nearest_jit,
     fast_norm_fullseq_bysite (without their numba decorators) and ExtentGrouping, build a ContactMap without its
@@ -300,10 +392,14 @@ def run_reference_path(alignments, ref_lengths, ref_sites, min_len, min_sig, min
     table), then call the reference's own methods in the order bin3C.py mkmap / cluster call them:
         _bin_map(fake bam) -> set_primary_acceptance_mask() -> to_graph(...) [prepare_seq_map(norm, bisto),
         get_subspace(marginalise=True, flatten=False)]
+    With `tip_size` the map is the tip-based tensor (`ref_sites` then holds (head, tail) pairs, seq_utils.py:146-158):
+    the 4-D functions of sparse_utils.py:317-509 over SparseShim and fast_norm_tipbased_bysite (contact_map.py:84-97,
+    without its numba decorator, whose signature -- float64 arrays of 4, 2 and 2 dimensions, :83 -- is not what
+    _norm_seq passes).
     Returns dict(cm, seq_map, mask, bisto_scale, processed_map, sub_map, graph, counts).
     """
     import collections
-    fns = load(skip_hermitian_check=False)
+    fns = load_4d() if tip_size else load(skip_hermitian_check=False)
     _, find_nearest = load_extent()
     logger = logging.getLogger('mzd.contact_map.exec')
     captured = {}
@@ -322,6 +418,12 @@ def run_reference_path(alignments, ref_lengths, ref_sites, min_len, min_sig, min
         max_offdiag = staticmethod(fns['max_offdiag'])
         compress = staticmethod(fns['compress'])
         kr_biostochastic = staticmethod(fns['kr_biostochastic'])
+        if tip_size:
+            Sparse4DAccumulator = fns['Sparse4DAccumulator']
+            max_offdiag_4d = staticmethod(fns['max_offdiag_4d'])
+            flatten_tensor_4d = staticmethod(fns['flatten_tensor_4d'])
+            compress_4d = staticmethod(fns['compress_4d'])
+            kr_biostochastic_4d = staticmethod(fns['kr_biostochastic_4d'])
 
     class NoneAcceptedException(Exception):
         pass
@@ -346,7 +448,7 @@ def run_reference_path(alignments, ref_lengths, ref_sites, min_len, min_sig, min
           'NoneAcceptedException': NoneAcceptedException, 'find_nearest_jit': find_nearest}
     with open(os.path.join(REFERENCE_ROOT, 'mzd', 'contact_map.py'), 'r') as fh:
         lines = fh.readlines()
-    for lo, hi in ((25, 46), (101, 113), (116, 156), (159, 485), (486, len(lines))):      # mean_selector: :25-46
+    for lo, hi in ((25, 46), (84, 97), (101, 113), (116, 156), (159, 485), (486, len(lines))):      # mean_selector: :25-46
         exec(compile(textwrap.dedent(''.join(lines[lo - 1:hi])), 'mzd/contact_map.py:{}-{}'.format(lo, hi), 'exec'), ns)
     # tqdm is imported inside _bin_map ("import tqdm"): give it the stub through sys.modules for the call
     import sys
@@ -372,13 +474,14 @@ def run_reference_path(alignments, ref_lengths, ref_sites, min_len, min_sig, min
     cm.min_len, cm.min_sig, cm.min_extent, cm.min_size, cm.max_fold = min_len, min_sig, 0, 0, None
     cm.random_state = np.random.RandomState(seed)
     cm.seq_info, cm.seq_map, cm.seq_file, cm.grouping, cm.extent_map, cm.order = [], None, None, None, None, None
-    cm.tip_size, cm.precount, cm.total_reads, cm.cov_info, cm.processed_map = None, False, None, None, None
+    cm.tip_size, cm.precount, cm.total_reads, cm.cov_info, cm.processed_map = tip_size, False, None, None, None
     cm.primary_acceptance_mask, cm.bisto_scale, cm.seq_analyzer, cm.enzymes = None, None, None, ['synthetic']
     offset = 0
     for n, (rlen, sites) in enumerate(zip(ref_lengths, ref_sites)):                 # contact_map.py:545-564
-        if rlen < min_len or sites < 0:
+        if rlen < min_len or np.min(sites) < 0:
             continue
-        cm.seq_info.append(SeqInfo(offset, n, 'ref{:07d}'.format(n), Py2Int(int(rlen)), int(sites)))
+        cm.seq_info.append(SeqInfo(offset, n, 'ref{:07d}'.format(n), Py2Int(int(rlen)),
+                                   [int(v) for v in sites] if tip_size else int(sites)))
         offset += int(rlen)
     cm.total_len, cm.total_seq = offset, len(cm.seq_info)
     cm.current_mask = np.ones(cm.total_seq, dtype=bool)

@@ -1055,3 +1055,73 @@ def test_accumulate_mirror_composite_count_escape(dev):
     assert np.array_equal(got.row, want.row) and np.array_equal(got.col, want.col)
     assert np.array_equal(got.data, want.data) and got.data.max() == 70_000
     assert {k: info[k] for k in counts} == counts
+
+
+# ---------------------------------------------------------------------------------------------
+# tip-based N x N x 2 x 2 map
+# ---------------------------------------------------------------------------------------------
+
+def test_tip_based_map_vs_reference(dev, tmp_path):
+    """ContactMap(tip_size=...) end to end from a BAM file -- the reader's tip records, the device accumulation over the
+    doubled ids, mask from the tensor's marginal, site normalisation per (sequence, tip), KR on the marginal, compress,
+    marginalise / flatten, edges -- and the sparse_utils 4-D drop-ins, against tests/golden/tipmap.npz: what the
+    REFERENCE'S OWN classes and functions produced (contact_map.py:631-670, 791-798, sparse_utils.py:317-509, exec'd by
+    tests/golden/make_golden_tip.py).  Tensor, counters and mask exact; scale factors, processed tensor and edge
+    weights <= 1e-9."""
+    import pickle
+    import bam_writer
+    from test_tips import golden_tip, params
+    from bin3c_b200 import sparse_utils as su
+    from bin3c_b200.cluster import to_edges
+    from bin3c_b200.contact_map import ContactMap
+    g, alns = golden_tip()
+    lengths = g['lengths']
+    n_refs = len(lengths)
+    min_len, min_sig = int(g['min_len']), int(g['min_sig'])
+    keep = lengths >= min_len
+    n_seq = int(keep.sum())
+    path = str(tmp_path / 'tips.bam')
+    bam_writer.write_bam(path, ['r%d' % i for i in range(n_refs)], lengths.tolist(), alns, block_bytes=30000, level=1)
+    for k in range(int(g['n_params'])):
+        p, kw, tip = params(g, k)
+        cm = ContactMap(path, ['MluCI'], g['sites2'], kw['min_insert'], min_mapq=kw['min_mapq'], min_len=min_len,
+                        min_sig=min_sig, strong=kw['strong'], tip_size=tip)
+        assert cm.is_tipbased() and cm.total_seq == n_seq
+        c = cm.pair_counts
+        assert [c['accepted'], c['ref_excluded'], c['poor_match'], c['short_insert'], c['not_tip']] == g[p + 'counts'].tolist()
+        sm = cm.seq_map
+        assert sm.shape == (n_seq, n_seq, 2, 2) and sm.data.dtype == np.uint32
+        assert np.array_equal(sm.coords, g[p + 'coords']) and np.array_equal(sm.data, g[p + 'data'])
+        assert cm.map_weight() == int(g[p + 'data'].sum())
+        assert np.array_equal(cm.get_primary_acceptance_mask(), g[p + 'mask'])
+        # the 4-D drop-ins on the tensor
+        assert np.array_equal(su.max_offdiag_4d(sm), g[p + 'signal'])
+        fl = su.flatten_tensor_4d(sm)
+        assert np.array_equal(fl.row, g[p + 'flat_row']) and np.array_equal(fl.col, g[p + 'flat_col'])
+        assert np.array_equal(fl.data, g[p + 'flat_data'])
+        cp = su.compress_4d(sm, np.arange(n_seq) % 4 != 1)
+        assert cp.shape == (int(g[p + 'cmp_n']),) * 2 + (2, 2)
+        assert np.array_equal(cp.coords, g[p + 'cmp_coords']) and np.array_equal(cp.data, g[p + 'cmp_data'])
+        bal, scl = su.kr_biostochastic_4d(sm)
+        assert _relerr(scl, g[p + 'kr_scl']) <= REL_TOL and _relerr(bal.data, g[p + 'kr_data']) <= REL_TOL
+        # the path: prepare_seq_map(norm, bisto) -> get_subspace(marginalise) -> edges
+        u, v, w, scale = to_edges(cm, norm=True, bisto=True, scale=True)
+        assert _relerr(cm.bisto_scale, g[p + 'bisto_scale']) <= REL_TOL
+        assert np.array_equal(cm.processed_map.coords, g[p + 'proc_coords'])
+        assert _relerr(cm.processed_map.data, g[p + 'proc_data']) <= REL_TOL
+        assert np.array_equal(u, g[p + 'edge_u']) and np.array_equal(v, g[p + 'edge_v'])
+        assert _relerr(w, g[p + 'edge_w']) <= REL_TOL
+        fs = cm.get_subspace(marginalise=False, flatten=True).tocsr()
+        fs.sort_indices()
+        assert np.array_equal(fs.indptr, g[p + 'fsub_indptr']) and np.array_equal(fs.indices, g[p + 'fsub_indices'])
+        assert _relerr(fs.data, g[p + 'fsub_data']) <= REL_TOL
+        assert pickle.loads(pickle.dumps(cm)).seq_map.nnz == sm.nnz
+    # the per-pair protocol of the reference's accumulator (a dict of 2 x 2 cells, contact_map.py:798)
+    acc = su.Sparse4DAccumulator(5)
+    cell = np.zeros((2, 2), dtype=np.uint32)
+    cell[1, 0] = 1
+    acc[1, 3] += cell
+    acc[1, 3] += cell
+    acc[2, 2] += cell
+    t = acc.get_coo()
+    assert t.coords.T.tolist() == [[1, 3, 1, 0], [2, 2, 1, 0], [3, 1, 0, 1]] and t.data.tolist() == [2, 1, 2]

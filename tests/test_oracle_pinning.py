@@ -318,3 +318,36 @@ def test_infomap_partition_of_gpu_edge_file(tmp_path):
             shutil.copyfileobj(src, dst)
         node, label = mc.partition_arrays(mc.infomap_partition(f, str(work)))
         assert np.array_equal(node, want[0]) and np.array_equal(label, want[1]), name
+
+
+def test_reference_tip_based_path_vs_oracle():
+    """The tip-based map, live: the reference's _bin_map with tip_size, its Sparse4DAccumulator and
+    4-D functions over SparseShim, and its ContactMap class driven to the graph, beside the oracle on a fresh stream."""
+    import random
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from make_golden_binmap import make_alignments
+    rng = random.Random(777)
+    n_refs = 40
+    lengths = [rng.choice([500, 1000, 1300, 2100, 5000, 12000]) for _ in range(n_refs)]
+    alns = [dict(a, name='q%d' % a['name']) for a in make_alignments(rng, n_refs, lengths, 5000)]
+    sites2 = [[rng.randrange(0, 12), rng.randrange(0, 12)] for _ in range(n_refs)]
+    keep = np.array(lengths) >= 1000
+    lut = np.where(keep, np.cumsum(keep) - 1, -1)
+    idx = {t: int(i) for t, i in enumerate(lut) if i >= 0}
+    n_seq = int(keep.sum())
+    for tip, kw in ((250, dict(min_mapq=20)), (3000, dict(min_mapq=10, min_insert=800))):
+        res = ref_exec.run_bin_map(alns, lengths, idx, n_seq, tip_size=tip, **kw)
+        cells, c = oracle.tip_pairs_loop(alns, lengths, idx, n_seq, tip, **kw)
+        assert {k: res['counts'][k] for k in c} == c
+        coords, data = oracle.tip_tensor(cells, n_seq)
+        assert np.array_equal(res['seq_map'].coords, coords) and np.array_equal(res['seq_map'].data, data)
+        path = ref_exec.run_reference_path(alns, lengths, sites2, 1000, 2, min_mapq=kw['min_mapq'],
+                                           min_insert=kw.get('min_insert'), tip_size=tip)
+        mine = oracle.run_tip_path(cells, np.array(lengths)[keep], np.array(sites2)[keep], 1000, 2)
+        assert np.array_equal(path['mask'], mine['mask'])
+        assert np.max(np.abs(path['bisto_scale'] - mine['x']) / np.abs(mine['x'])) <= 1e-12
+        e = sorted((min(u, v), max(u, v), d['weight']) for u, v, d in path['graph'].edges(data=True))
+        assert [x[0] for x in e] == mine['u'].tolist() and [x[1] for x in e] == mine['v'].tolist()
+        assert np.max(np.abs(np.array([x[2] for x in e]) - mine['w']) / np.abs(mine['w'])) <= 1e-12
