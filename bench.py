@@ -60,7 +60,9 @@ def parse_args():
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the pair count (debugging only)')
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle leg (and with it the parity check)')
-    ap.add_argument('--e2e-record-bytes', default='auto', help="auto: the narrowest record the reference table allows (5, 6 or 8 bytes); 8: native records")
+    ap.add_argument('--e2e-record-bytes', default='auto',
+                    help="auto: the narrowest hand-over (same-reference pairs as 3/4-byte records, the rest as 5/6/8-byte "
+                         "pair records); narrow: 5/6/8-byte pair records only; 8: native records")
     ap.add_argument('--no-microbench', action='store_true', help='skip the C5 KR SpMV microbench points')
     ap.add_argument('--microbench', default='default', choices=['default', 'full'], help='full: also the 3M-row C5 point')
     ap.add_argument('--no-c2', action='store_true', help='N=1: skip the secondary C2 measurement')
@@ -401,16 +403,22 @@ def run_single_gpu(work, args, torch, dev, local_rank, steps, warmup, want_cpu, 
               'x_sum': dg['x_sum'], 'w_sum': dg['w_sum']}
 
     # ---- end-to-end arm: pinned host records in, host edge list out ------------------------------------
-    # The records cross PCIe in the narrowest layout the reference table allows (5 bytes per pair below 2^19 - 1
-    # references, 6 below 2^23 - 1, else the native 8): what the BAM reader hands over for the bulk path
-    # (bam_io.pack_records / b3c_records_pack); packing is the producer's job and is not timed, like the BAM decode.
+    # The records cross PCIe in the narrowest layout the reference table allows: the pairs whose mates lie on one
+    # reference (four in five) as 3-byte records, the rest as 5-byte pair records (6 / 8 for larger tables) -- what
+    # the BAM reader hands over for the bulk path (bam_io.split_records / b3c_records_split).  Packing is the
+    # producer's job and is not timed, like the BAM decode; the map does not depend on the order of its records.
     e2e = None
     clocks = None
     if not args.no_e2e:
         e2e_steps = args.e2e_steps or max(3, min(steps, 10))
         rec_bytes = 8 if args.e2e_record_bytes == '8' else bam_io.records_bytes(work.n_refs)
         host64 = rec_dev.cpu().numpy().view(np.uint64) if work.v2 else work.com.records
-        if rec_bytes == 8:
+        rec_desc = rec_bytes
+        if args.e2e_record_bytes == 'auto':
+            e2e_in, e2e_kw = bam_io.split_records(host64, work.n_refs, pin=True), {}
+            rec_desc = {'same_reference': e2e_in.bytes_same, 'pair': e2e_in.bytes_pair, 'n_same': e2e_in.n_same,
+                        'n_pair': e2e_in.n_pairs, 'mean': round(e2e_in.nbytes / float(P), 3)}
+        elif rec_bytes == 8:
             e2e_in, e2e_kw = torch.from_numpy(host64.view(np.int64)).pin_memory(), {}
         else:
             nb = (P * rec_bytes + 7) // 8 * 8
@@ -429,7 +437,7 @@ def run_single_gpu(work, args, torch, dev, local_rank, steps, warmup, want_cpu, 
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         e2e = {'value': P / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(hp.h2d_bytes),
                'd2h_bytes_per_step': int(hp.d2h_bytes), 'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps,
-               'record_bytes': rec_bytes}
+               'record_bytes': rec_desc}
         del e2e_in
     clocks = sampler.stop()
 
@@ -656,7 +664,11 @@ def main_multi(args, rank, local_rank, world):
     if not args.no_e2e:
         rec_bytes = 8 if args.e2e_record_bytes == '8' else bam_io.records_bytes(work.n_refs)
         host64 = rec_dev.cpu().numpy().view(np.uint64)
-        if rec_bytes == 8:
+        rec_desc, run_kw = rec_bytes, {'record_bytes': rec_bytes, 'n_records': pairs_local}
+        if args.e2e_record_bytes == 'auto':
+            e2e_in, run_kw = bam_io.split_records(host64, work.n_refs, pin=True), {}
+            rec_desc = {'same_reference': e2e_in.bytes_same, 'pair': e2e_in.bytes_pair}
+        elif rec_bytes == 8:
             e2e_in = torch.from_numpy(host64.view(np.int64)).pin_memory()
         else:
             nb = (pairs_local * rec_bytes + 7) // 8 * 8
@@ -667,7 +679,7 @@ def main_multi(args, rank, local_rank, world):
         pinned = {}
 
         def e2e_step():
-            r = hp.run(e2e_in, record_bytes=rec_bytes, n_records=pairs_local)
+            r = hp.run(e2e_in, **run_kw)
             n = int(r['n_edges'])
             nbytes = 0
             for k, m in (('u', n), ('v', n), ('w', n), ('scl', 1)):
@@ -691,7 +703,7 @@ def main_multi(args, rank, local_rank, world):
         comm.all_reduce(io_t, 'sum')
         e2e = {'value': total_pairs / float(e2e_t.cpu()[0]), 'unit': UNIT, 'h2d_bytes_per_step': int(io_t.cpu()[1]),
                'd2h_bytes_per_step': int(io_t.cpu()[0]), 'ms_per_step': float(e2e_t.cpu()[0]) * 1e3, 'steps': e2e_steps,
-               'record_bytes': rec_bytes}
+               'record_bytes': rec_desc}
         del e2e_in
     clocks = sampler.stop()
 

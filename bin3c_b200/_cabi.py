@@ -45,6 +45,7 @@ SIGNATURES = {
     'b3c_accum_reset': (C.c_int, [_p, _p]),
     'b3c_accum_add_pairs': (C.c_int, [_p, _p, _i64, _p]),
     'b3c_accum_add_pairs_packed': (C.c_int, [_p, _p, _i64, _i32, _p]),
+    'b3c_accum_add_pairs_same': (C.c_int, [_p, _p, _i64, _i32, _p]),
     'b3c_accum_reduce': (C.c_int, [_p, _pi64, _p]),
     'b3c_accum_emit_csr': (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     'b3c_accum_offsets': (C.c_int, [_p, _pi64]),

@@ -59,6 +59,8 @@ SIGNATURES = {
     'b3c_records_bytes': (_i32, [_i64]),
     'b3c_records_pack': (_i64, [_p, _i64, _i32, _p, _i32]),
     'b3c_records_unpack': (_i64, [_p, _i64, _i32, _p]),
+    'b3c_records_same_bytes': (_i32, [_i64]),
+    'b3c_records_split': (_i64, [_p, _i64, _i32, _i32, _p, _p, _p, _i32]),
     'b3c_format_weight': (_i32, [C.c_double, _p, _i32]),
     'b3c_format_weight_fmt': (_i32, [C.c_double, _i32, _p, _i32]),
 }
@@ -275,6 +277,41 @@ def pack_records(records, bytes_per_record, out=None, threads=0):
     assert out.dtype == np.uint8 and out.flags.c_contiguous and len(out) >= nbytes
     check(lib.b3c_records_pack(r.ctypes.data, len(r), int(bytes_per_record), out.ctypes.data, int(threads)))
     return out[:nbytes]
+
+
+def split_records(records, n_refs, pin=False, threads=0):
+    """
+    uint64 native records -> device.SplitRecords, the narrowest form for the host->device copy: the pairs whose mates
+    lie on one reference as 3- / 4-byte records, the rest as 5- / 6- / 8-byte pair records (b3c_records_split).
+    `pin`: allocate the two buffers in pinned host memory (asynchronous copies).
+    """
+    import torch
+    from .device import SplitRecords
+    r = np.ascontiguousarray(records, dtype=np.uint64)
+    B, Bs = records_bytes(n_refs), int(lib.b3c_records_same_bytes(int(n_refs)))
+    assert Bs in (3, 4), 'reference table too large for same-reference records'
+    cnt = np.zeros(2, dtype=np.int64)
+    check(lib.b3c_records_split(r.ctypes.data, len(r), B, Bs, None, None, cnt.ctypes.data, int(threads)))
+    n_same, n_pair = int(cnt[0]), int(cnt[1])
+    same = torch.empty((n_same * Bs + 7) // 8 * 8, dtype=torch.uint8, pin_memory=bool(pin))
+    pair = torch.empty((n_pair * B + 7) // 8 * 8, dtype=torch.uint8, pin_memory=bool(pin))
+    check(lib.b3c_records_split(r.ctypes.data, len(r), B, Bs, same.numpy().ctypes.data, pair.numpy().ctypes.data,
+                                cnt.ctypes.data, int(threads)))
+    return SplitRecords(same, n_same, Bs, pair, n_pair, B)
+
+
+def unsplit_records(split):
+    """device.SplitRecords (host) -> uint64 native records: the same-reference ones first, then the others."""
+    s = np.ascontiguousarray(split.same.numpy())
+    Bs, ts = split.bytes_same, 8 * split.bytes_same - 1
+    v = np.zeros(split.n_same, dtype=np.uint64)
+    for k in range(Bs):
+        v |= s[k:split.n_same * Bs:Bs].astype(np.uint64) << np.uint64(8 * k)
+    t = v & np.uint64((1 << ts) - 1)
+    t[t == np.uint64((1 << ts) - 1)] = np.uint64(0x7fffffff)
+    same = t | (((v >> np.uint64(ts)) & np.uint64(1)) << np.uint64(31)) | (t << np.uint64(32))
+    pairs = unpack_records(split.pairs.numpy(), split.n_pairs, split.bytes_pair)
+    return np.concatenate([same, pairs])
 
 
 def unpack_records(packed, n, bytes_per_record):

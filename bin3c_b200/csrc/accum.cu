@@ -201,6 +201,7 @@ struct ClsParams {
     const uint64_t *rec;
     int64_t n_rec;
     int32_t rec_bytes;       // 8: native records; 5 or 6: narrow records (b3c_accum_add_pairs_packed)
+    int32_t rec_same;        // 1: 3- or 4-byte records of pairs whose mates lie on ONE reference (b3c_accum_add_pairs_same)
     const int32_t *lut;
     int32_t n_refs, n_seq;
     int b;
@@ -372,7 +373,8 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
             // narrow records: B bytes each, little endian, tid1 in bits [0, tb), the pass flag in bit tb, tid2 in
             // bits [tb + 1, 2 tb + 1), tb = (8 B - 1) / 2.  A record is cut out of the one or two 8-byte words that
             // hold it and widened to the native (lo, hi) halves, so the rest of the kernel does not change.
-            const int B = P.rec_bytes, tb = (8 * B - 1) / 2;
+            // (same-reference records: one id in bits [0, 8 B - 1), the flag in the top bit; widened to tid1 = tid2)
+            const int B = P.rec_bytes, tb = P.rec_same ? 8 * B - 1 : (8 * B - 1) / 2;
             const uint64_t tmask = (1ull << tb) - 1ull;
             const int64_t last_word = (P.n_rec * B - 1) >> 3;
 #pragma unroll
@@ -387,7 +389,7 @@ __device__ __forceinline__ void classify_tiles(const ClsParams &P, unsigned char
                         uint64_t r = __ldg(P.rec + w) >> sh;
                         if (sh + 8 * B > 64) r |= __ldg(P.rec + (w < last_word ? w + 1 : last_word)) << (64 - sh);
                         q4[2 * q] = (uint32_t)(r & tmask) | ((uint32_t)((r >> tb) & 1ull) << 31);
-                        q4[2 * q + 1] = (uint32_t)((r >> (tb + 1)) & tmask);
+                        q4[2 * q + 1] = P.rec_same ? (uint32_t)(r & tmask) : (uint32_t)((r >> (tb + 1)) & tmask);
                         okm |= 1u << (2 * h + q);
                     }
                 }
@@ -1429,7 +1431,8 @@ int b3c_accum_reset(void *d_ws, void *stream) {
     return B3C_OK;
 }
 
-static int accum_add(void *d_ws, const void *d_records, int64_t n_records, int32_t rec_bytes, void *stream);
+static int accum_add(void *d_ws, const void *d_records, int64_t n_records, int32_t rec_bytes, void *stream,
+                     int32_t rec_same = 0);
 
 int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records, void *stream) {
     return accum_add(d_ws, d_records, n_records, 8, stream);
@@ -1442,7 +1445,14 @@ int b3c_accum_add_pairs_packed(void *d_ws, const void *d_bytes, int64_t n_record
     return accum_add(d_ws, d_bytes, n_records, bytes_per_record, stream);
 }
 
-static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int32_t rec_bytes, void *stream) {
+int b3c_accum_add_pairs_same(void *d_ws, const void *d_bytes, int64_t n_records, int32_t bytes_per_record,
+                             void *stream) {
+    B3C_REQUIRE(bytes_per_record == 3 || bytes_per_record == 4, "bytes_per_record must be 3 or 4");
+    return accum_add(d_ws, d_bytes, n_records, bytes_per_record, stream, 1);
+}
+
+static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int32_t rec_bytes, void *stream,
+                     int32_t rec_same) {
     const uint64_t *d_records = (const uint64_t *)d_records_v;
     AccumState st;
     int rc = get_state(d_ws, &st);
@@ -1452,7 +1462,7 @@ static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int
     B3C_REQUIRE(d_records != nullptr, "null records");
     B3C_REQUIRE(((uintptr_t)d_records & 15) == 0, "records must be 16-byte aligned");
     if (rec_bytes != 8) {
-        const int tb = (8 * rec_bytes - 1) / 2;
+        const int tb = rec_same ? 8 * rec_bytes - 1 : (8 * rec_bytes - 1) / 2;
         B3C_REQUIRE((int64_t)st.n_refs < (1ll << tb) - 1, "%d-byte records hold reference ids below %lld; the table has %d",
                     rec_bytes, (1ll << tb) - 1, st.n_refs);
     }
@@ -1462,6 +1472,7 @@ static int accum_add(void *d_ws, const void *d_records_v, int64_t n_records, int
     P.rec = d_records;
     P.n_rec = n_records;
     P.rec_bytes = rec_bytes;
+    P.rec_same = rec_same;
     P.lut = st.d_lut;
     P.n_refs = st.n_refs;
     P.n_seq = st.n_seq;

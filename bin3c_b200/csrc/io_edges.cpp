@@ -237,6 +237,93 @@ int64_t b3c_records_pack(const uint64_t *h_records, int64_t n, int32_t B, uint8_
     return total;
 }
 
+int32_t b3c_records_same_bytes(int64_t n_refs) {
+    if (n_refs < (1ll << 23) - 1) return 3;
+    if (n_refs < (1ll << 31) - 1) return 4;
+    return 0;
+}
+
+// a record whose mates lie on the same reference (ids compared after the clamp a narrow record applies)
+static inline bool rec_is_same(uint64_t r) { return (r & 0x7fffffffull) == ((r >> 32) & 0x7fffffffull); }
+
+static void split_count(const uint64_t *in, int64_t lo, int64_t hi, int64_t *n_same) {
+    int64_t c = 0;
+    for (int64_t i = lo; i < hi; ++i) c += rec_is_same(in[i]) ? 1 : 0;
+    *n_same = c;
+}
+
+static void split_fill(const uint64_t *in, int64_t lo, int64_t hi, int B, int Bs, uint8_t *out_same, int64_t at_same,
+                       uint8_t *out_pair, int64_t at_pair) {
+    const int tb = (8 * B - 1) / 2, ts = 8 * Bs - 1;
+    const uint64_t tmask = (1ull << tb) - 1ull, smask = (1ull << ts) - 1ull;
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint64_t r = in[i];
+        uint64_t t1 = r & 0x7fffffffull, t2 = (r >> 32) & 0x7fffffffull;
+        const uint64_t pass = (r >> 31) & 1ull;
+        if (t1 == t2) {
+            if (t1 > smask) t1 = smask;
+            const uint64_t v = t1 | (pass << ts);
+            uint8_t *o = out_same + at_same * Bs;
+            for (int k = 0; k < Bs; ++k) o[k] = (uint8_t)(v >> (8 * k));
+            ++at_same;
+        } else {
+            if (t1 > tmask) t1 = tmask;
+            if (t2 > tmask) t2 = tmask;
+            const uint64_t v = t1 | (pass << tb) | (t2 << (tb + 1));
+            uint8_t *o = out_pair + at_pair * B;
+            for (int k = 0; k < B; ++k) o[k] = (uint8_t)(v >> (8 * k));
+            ++at_pair;
+        }
+    }
+}
+
+int64_t b3c_records_split(const uint64_t *h_records, int64_t n, int32_t B, int32_t Bs, uint8_t *h_out_same,
+                          uint8_t *h_out_pair, int64_t *h_counts, int32_t n_threads) {
+    if (n < 0 || (n > 0 && !h_records) || !h_counts || (B != 5 && B != 6 && B != 8) || (Bs != 3 && Bs != 4) ||
+        ((h_out_same == nullptr) != (h_out_pair == nullptr))) {
+        b3cio::set_err("b3c_records_split: bad argument");
+        return B3C_IO_ERR_ARG;
+    }
+    if (n_threads <= 0) n_threads = (int32_t)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (n < (1 << 16)) n_threads = 1;
+    std::vector<int64_t> same(n_threads, 0);
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_threads; ++t)
+            th.emplace_back(split_count, h_records, n * t / n_threads, n * (t + 1) / n_threads, &same[t]);
+        split_count(h_records, 0, n / n_threads, &same[0]);
+        for (auto &t : th) t.join();
+    }
+    int64_t n_same = 0;
+    for (int t = 0; t < n_threads; ++t) n_same += same[t];
+    h_counts[0] = n_same;
+    h_counts[1] = n - n_same;
+    if (!h_out_same) return n;                          // count only: the caller sizes its buffers
+    {
+        std::vector<std::thread> th;
+        int64_t at_same = 0, at_pair = 0;
+        int64_t a0 = 0, p0 = 0;
+        for (int t = 0; t < n_threads; ++t) {
+            const int64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+            if (t == 0) {
+                a0 = at_same;
+                p0 = at_pair;
+            } else {
+                th.emplace_back(split_fill, h_records, lo, hi, (int)B, (int)Bs, h_out_same, at_same, h_out_pair, at_pair);
+            }
+            at_same += same[t];
+            at_pair += (hi - lo) - same[t];
+        }
+        split_fill(h_records, 0, n / n_threads, (int)B, (int)Bs, h_out_same, a0, h_out_pair, p0);
+        for (auto &t : th) t.join();
+    }
+    for (int64_t k = n_same * Bs; k < (n_same * Bs + 7) / 8 * 8; ++k) h_out_same[k] = 0;
+    for (int64_t k = (n - n_same) * B; k < ((n - n_same) * B + 7) / 8 * 8; ++k) h_out_pair[k] = 0;
+    return n;
+}
+
 int64_t b3c_records_unpack(const uint8_t *h_bytes, int64_t n, int32_t B, uint64_t *h_records) {
     if (n < 0 || (n > 0 && (!h_bytes || !h_records)) || (B != 5 && B != 6 && B != 8)) {
         b3cio::set_err("b3c_records_unpack: bad argument");

@@ -204,12 +204,13 @@ class Accumulator(object):
         assert records.is_cuda and records.element_size() == 8 and records.is_contiguous()
         check(lib.b3c_accum_add_pairs(_ptr(self.ws), _ptr(records), records.numel(), _stream()))
 
-    def add_packed(self, packed, n_records, bytes_per_record):
-        """packed: CUDA uint8 tensor of narrow records (bam_io.pack_records), 16-byte aligned, padded to 8 bytes."""
+    def add_packed(self, packed, n_records, bytes_per_record, same=False):
+        """packed: CUDA uint8 tensor of narrow records (bam_io.pack_records), 16-byte aligned, padded to 8 bytes.
+        same=True: 3- or 4-byte records of pairs on one reference (bam_io.split_records)."""
         assert packed.is_cuda and packed.element_size() == 1 and packed.is_contiguous()
         assert packed.numel() >= (int(n_records) * int(bytes_per_record) + 7) // 8 * 8
-        check(lib.b3c_accum_add_pairs_packed(_ptr(self.ws), _ptr(packed), int(n_records), int(bytes_per_record),
-                                             _stream()))
+        fn = lib.b3c_accum_add_pairs_same if same else lib.b3c_accum_add_pairs_packed
+        check(fn(_ptr(self.ws), _ptr(packed), int(n_records), int(bytes_per_record), _stream()))
 
     def finish(self, symmetric=True, pool=None):
         """Sort-reduce and emit the canonical CSR.  Returns (DeviceCSR[uint32 counts], info dict)."""
@@ -226,6 +227,42 @@ class Accumulator(object):
         return DeviceCSR(self.n_seq, indptr, indices, counts, counts=True), self.info
 
 
+class SplitRecords(object):
+    """
+    Host (or device) pair records in the narrowest layout (bam_io.split_records): the pairs whose mates lie on one
+    reference as 3- or 4-byte records (`same`, uint8 tensor), the rest as 5- / 6- / 8-byte pair records (`pairs`).
+    The contact map does not depend on the order of its records, so the two parts are simply accumulated one after
+    the other.
+    """
+
+    def __init__(self, same, n_same, bytes_same, pairs, n_pairs, bytes_pair):
+        self.same, self.n_same, self.bytes_same = same, int(n_same), int(bytes_same)
+        self.pairs, self.n_pairs, self.bytes_pair = pairs, int(n_pairs), int(bytes_pair)
+
+    def parts(self):
+        return ((self.same, self.n_same, self.bytes_same, True), (self.pairs, self.n_pairs, self.bytes_pair, False))
+
+    @property
+    def n_records(self):
+        return self.n_same + self.n_pairs
+
+    @property
+    def nbytes(self):
+        return int(self.same.numel()) + int(self.pairs.numel()) * self.pairs.element_size()
+
+    @property
+    def is_cuda(self):
+        return bool(self.same.is_cuda)
+
+    def pin_memory(self):
+        return SplitRecords(self.same.pin_memory(), self.n_same, self.bytes_same, self.pairs.pin_memory(), self.n_pairs,
+                            self.bytes_pair)
+
+    def cuda(self):
+        return SplitRecords(self.same.cuda(), self.n_same, self.bytes_same, self.pairs.cuda(), self.n_pairs,
+                            self.bytes_pair)
+
+
 class RecordStreamer(object):
     """
     Host pair records -> accumulator through a ring of two device staging buffers: the H2D copy of chunk k+1 runs
@@ -239,7 +276,14 @@ class RecordStreamer(object):
         self._copy_stream = None
         self._ring_ev = None
 
-    def feed(self, acc, records, n_rec=None, record_bytes=8, chunk_records=1 << 24):
+    def feed(self, acc, records, n_rec=None, record_bytes=8, chunk_records=1 << 24, same=False):
+        if isinstance(records, SplitRecords):
+            # same-reference records first, then the pair records: one stream through the same ring
+            total = 0
+            for part, n, B, sm in records.parts():
+                if n:
+                    total += self.feed(acc, part, n, B, chunk_records, same=sm)
+            return total
         B = int(record_bytes)
         main = torch.cuda.current_stream()
         if self._copy_stream is None:
@@ -275,7 +319,7 @@ class RecordStreamer(object):
             if B == 8:
                 acc.add(buf)
             else:
-                acc.add_packed(buf, hi - lo, B)
+                acc.add_packed(buf, hi - lo, B, same=same)
             consumed.record(main)
             copied_bytes += nel * (8 if B == 8 else 1)
         return copied_bytes

@@ -221,6 +221,16 @@ class CudaEngine(object):
         copy; native 8-byte or narrow 5/6-byte, bam_io.pack_records) streamed through the staging ring."""
         B = int(record_bytes)
         self.h2d_bytes = 0
+        if isinstance(records, self.dev.SplitRecords):
+            if records.is_cuda:
+                for part, n, pb, same in records.parts():
+                    if n:
+                        self.acc.add_packed(part, n, pb, same=same)
+                return
+            if getattr(self, '_streamer', None) is None:
+                self._streamer = self.dev.RecordStreamer(self.pool)
+            self.h2d_bytes = self._streamer.feed(self.acc, records)
+            return
         if records.is_cuda:
             if B == 8:
                 self.acc.add(records)

@@ -74,6 +74,24 @@ class HotPath(object):
         the classification of chunk k.
         """
         B = int(record_bytes)
+        if isinstance(records, dev.SplitRecords):
+            # the narrowest hand-over (bam_io.split_records): same-reference pairs as 3- / 4-byte records, the rest as
+            # pair records; accumulated one part after the other
+            acc = self._ensure_accumulator(records.n_records)
+            self.h2d_bytes = 0
+            self._mark('start')
+            if records.is_cuda:
+                for part, n, pb, same in records.parts():
+                    if n:
+                        acc.add_packed(part, n, pb, same=same)
+            else:
+                if self._streamer is None:
+                    self._streamer = dev.RecordStreamer(self.pool)
+                self.h2d_bytes = self._streamer.feed(acc, records, chunk_records=chunk_records)
+            self._mark('classify')
+            self.seq_map, self.acc_info = acc.finish(symmetric=True, pool=self.pool)
+            self._mark('sort_reduce_emit')
+            return self.seq_map
         if not isinstance(records, torch.Tensor):
             if B == 8:
                 records = torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint64).view(np.int64))

@@ -68,6 +68,12 @@ int64_t b3c_launch_count(void);
  *              n_refs < 2^tb - 1; an id outside the table is stored as 2^tb - 1.  The buffer must be
  *              16-byte aligned and readable up to the next multiple of 8 bytes; a chunk boundary
  *              must fall on a multiple of 8 records.  bin3c_io.h: b3c_records_pack packs on the host.
+ *   add_pairs_same  records of pairs whose two mates lie on ONE reference (four in five Hi-C pairs): B = 3 or
+ *              4 little-endian bytes holding the reference id in bits [0, 8B-1) and the pass flag in the top
+ *              bit (n_refs < 2^(8B-1) - 1; an id outside the table is stored as all ones).  Same alignment
+ *              rules.  The order of records does not matter to the map, so a producer may hand the same-
+ *              reference pairs over in this form and only the others as pair records (bin3c_io.h:
+ *              b3c_records_split): 3.4 instead of 5 bytes per pair over PCIe on the bench communities.
  *   reduce     radix sort the keys + run-length reduce; returns sizes to the host:
  *              h_sizes[0] = nnz of the upper triangle incl. diagonal
  *              h_sizes[1] = nnz of the full symmetric matrix
@@ -84,6 +90,8 @@ int b3c_accum_reset(void *d_ws, void *stream);
 int b3c_accum_add_pairs(void *d_ws, const uint64_t *d_records, int64_t n_records, void *stream);
 int b3c_accum_add_pairs_packed(void *d_ws, const void *d_bytes, int64_t n_records, int32_t bytes_per_record,
                                void *stream);
+int b3c_accum_add_pairs_same(void *d_ws, const void *d_bytes, int64_t n_records, int32_t bytes_per_record,
+                             void *stream);
 int b3c_accum_reduce(void *d_ws, int64_t *h_sizes, void *stream);
 int b3c_accum_emit_csr(void *d_ws, int symmetric, int64_t *d_indptr, int32_t *d_indices,
                        uint32_t *d_counts, void *stream);

@@ -122,6 +122,17 @@ int32_t b3c_records_bytes(int64_t n_refs);
 int64_t b3c_records_pack(const uint64_t *h_records, int64_t n, int32_t bytes_per_record, uint8_t *h_out, int32_t n_threads);
 int64_t b3c_records_unpack(const uint8_t *h_bytes, int64_t n, int32_t bytes_per_record, uint64_t *h_records);
 
+/* The narrowest hand-over: pairs whose mates lie on ONE reference (four in five Hi-C pairs) need one id, not two.
+ * b3c_records_same_bytes: 3 or 4 bytes per same-reference record for a table of n_refs (id in bits [0, 8B-1), pass
+ * flag in the top bit; include/bin3c_b200.h: b3c_accum_add_pairs_same).  b3c_records_split: n native records -> the
+ * same-reference ones as such records into h_out_same, the others as bytes_per_record-byte pair records into
+ * h_out_pair, each in input order, each buffer sized to the next multiple of 8 bytes (tail zeroed);
+ * h_counts[0] = same-reference records, h_counts[1] = pair records.  With both output pointers NULL only the counts
+ * are produced.  Returns n or a negative status.  (The contact map does not depend on the order of its records.) */
+int32_t b3c_records_same_bytes(int64_t n_refs);
+int64_t b3c_records_split(const uint64_t *h_records, int64_t n, int32_t bytes_per_record, int32_t bytes_per_same,
+                          uint8_t *h_out_same, uint8_t *h_out_pair, int64_t *h_counts, int32_t n_threads);
+
 /* How a weight is printed.  networkx prints it with str(): the shortest round-trip decimal on Python 3
  * (== repr), '%.12g' plus '.0' on integer-looking values on the Python 2.7 the reference pins. */
 typedef enum {

@@ -197,6 +197,68 @@ def test_accumulate_narrow_records(dev, B, n_pairs):
         assert hp.acc_info == winfo
 
 
+@pytest.mark.parametrize('n_pairs', [0, 9, 4099, 300_001])
+def test_accumulate_split_records(dev, n_pairs):
+    """The narrowest hand-over (bam_io.split_records): pairs on one reference as 3-byte records, the others as pair
+    records -- the same matrix, counters and edges as the native 8-byte records, device-resident and streamed from the
+    host in ragged chunks; out-of-table ids included (an all-ones same-reference record counts as excluded)."""
+    import torch
+    from bin3c_b200 import bam_io, synth
+    from bin3c_b200.pipeline import HotPath
+    com = synth.make_community(n_genomes=6, n_contigs=900, n_pairs=max(n_pairs, 1), seed=47)
+    rec = com.records[:n_pairs].copy()
+    if n_pairs > 20:
+        rec[5] = np.uint64(0x7fffffff) | (rec[5] & np.uint64(0xffffffff80000000))          # out-of-table id in mate 1
+        rec[6] = np.uint64(0x7fffffff) | (np.uint64(0x7fffffff) << np.uint64(32)) | np.uint64(1 << 31)   # in both
+    lut = com.tid2idx()
+    want, winfo = _accumulate(dev, rec, lut, com.n_contigs)
+    sp_host = bam_io.split_records(rec, com.n_refs)
+    assert sp_host.bytes_same == 3 and sp_host.bytes_pair == 5 and sp_host.n_records == n_pairs
+    m31 = np.uint64(0x7fffffff)
+    same = (rec & m31) == ((rec >> np.uint64(32)) & m31)
+    assert sp_host.n_same == int(same.sum())
+    assert np.array_equal(bam_io.unsplit_records(sp_host), np.concatenate([rec[same], rec[~same]]))
+    acc = dev.Accumulator(com.n_contigs, lut, max(n_pairs, 1))
+    for part, n, B, sm in sp_host.cuda().parts():
+        if n:
+            acc.add_packed(part, n, B, same=sm)
+    got, ginfo = acc.finish()
+    torch.cuda.synchronize()
+    assert ginfo == winfo
+    assert np.array_equal(got.indptr.cpu().numpy(), want.indptr.cpu().numpy())
+    assert np.array_equal(got.indices.cpu().numpy(), want.indices.cpu().numpy())
+    assert np.array_equal(got.data.cpu().numpy(), want.data.cpu().numpy())
+    if n_pairs >= 4099:
+        hp = HotPath(lut, com.lengths, com.sites, pair_capacity=n_pairs, min_sig=1)
+        r8 = hp.run(dev.to_device(rec))
+        n = int(r8['n_edges'])
+        ref = [r8[k][:n].cpu().numpy().copy() for k in ('u', 'v', 'w')]
+        out = hp.run(bam_io.split_records(rec, com.n_refs, pin=True), to_host=True)
+        assert hp.h2d_bytes == sp_host.nbytes and out['n_edges'] == n
+        for k, w in zip(('u', 'v', 'w'), ref):
+            assert np.array_equal(out[k], w)
+        out = hp.run(sp_host.cuda())                                              # device-resident split records
+        assert int(out['n_edges']) == n
+        hp.reset()
+        hp.accumulate(sp_host, chunk_records=1000)                                # pageable, many chunks
+        assert hp.acc_info == winfo
+
+
+def test_accumulate_same_records_need_a_small_table(dev):
+    import torch
+    acc = dev.Accumulator(64, np.arange(64, dtype=np.int32), 16)
+    z = torch.zeros(64, dtype=torch.uint8, device='cuda')
+    acc.add_packed(z, 8, 3, same=True)
+    acc.add_packed(z, 8, 4, same=True)
+    with pytest.raises(AssertionError):
+        acc.add_packed(z, 8, 5, same=True)
+    lut = np.arange(9_000_000, dtype=np.int32)            # more references than the 23 bits of a 3-byte record hold
+    acc = dev.Accumulator(9_000_000, lut, 16)
+    with pytest.raises(AssertionError):
+        acc.add_packed(z, 8, 3, same=True)
+    acc.add_packed(z, 8, 4, same=True)
+
+
 def test_accumulate_narrow_records_need_a_small_table(dev):
     import torch
     lut = np.arange(600_000, dtype=np.int32)              # more references than 19 bits hold

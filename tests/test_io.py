@@ -562,3 +562,35 @@ def test_bam_long_cigar_in_cg_tag_and_reverse_read_without_cigar(tmp_path):
         assert len(bam.read_pairs(10)) == 1
     with pytest.raises(TypeError):
         oracle.pair_alignments(bad, 2, idx_of=lut, grouping=og)
+
+
+def test_split_records_round_trip():
+    """b3c_records_split: same-reference pairs as 3- / 4-byte records, the others as pair records, input order kept
+    within each part; counts-only call; argument errors; single- and multi-threaded packing agree."""
+    rng = np.random.default_rng(8)
+    for n_refs, n in ((1000, 0), (1000, 5), (300_000, 70_001), (9_000_000, 66_000)):
+        a = rng.integers(0, n_refs, n).astype(np.uint64)
+        b = np.where(rng.random(n) < 0.7, a, rng.integers(0, n_refs, n).astype(np.uint64))
+        ok = (rng.random(n) < 0.8).astype(np.uint64)
+        rec = a | (ok << np.uint64(31)) | (b << np.uint64(32))
+        if n > 4:
+            rec[3] = np.uint64(0x7fffffff) | (np.uint64(0x7fffffff) << np.uint64(32))
+            rec[4] = np.uint64(0x7fffffff) | (np.uint64(2) << np.uint64(32)) | np.uint64(1 << 31)
+        sp1 = bam_io.split_records(rec, n_refs, threads=1)
+        sp4 = bam_io.split_records(rec, n_refs, threads=4)
+        assert sp1.bytes_same == bam_io.lib.b3c_records_same_bytes(n_refs) == (3 if n_refs < (1 << 23) - 1 else 4)
+        assert sp1.bytes_pair == bam_io.records_bytes(n_refs)
+        assert np.array_equal(sp1.same.numpy(), sp4.same.numpy()) and np.array_equal(sp1.pairs.numpy(), sp4.pairs.numpy())
+        same = (a == b) if n <= 4 else ((rec & np.uint64(0x7fffffff)) == ((rec >> np.uint64(32)) & np.uint64(0x7fffffff)))
+        assert sp1.n_same == int(same.sum()) and sp1.n_pairs == n - int(same.sum())
+        assert np.array_equal(bam_io.unsplit_records(sp1), np.concatenate([rec[same], rec[~same]]))
+    cnt = np.zeros(2, dtype=np.int64)
+    r = np.zeros(4, dtype=np.uint64)
+    assert bam_io.lib.b3c_records_split(r.ctypes.data, 4, 5, 3, None, None, cnt.ctypes.data, 1) == 4 and cnt.tolist() == [4, 0]
+    out = np.zeros(64, dtype=np.uint8)
+    with pytest.raises(AssertionError):
+        bam_io.check(bam_io.lib.b3c_records_split(r.ctypes.data, 4, 7, 3, out.ctypes.data, out.ctypes.data, cnt.ctypes.data, 1))
+    with pytest.raises(AssertionError):
+        bam_io.check(bam_io.lib.b3c_records_split(r.ctypes.data, 4, 5, 2, out.ctypes.data, out.ctypes.data, cnt.ctypes.data, 1))
+    with pytest.raises(AssertionError):
+        bam_io.check(bam_io.lib.b3c_records_split(r.ctypes.data, 4, 5, 3, out.ctypes.data, None, cnt.ctypes.data, 1))
