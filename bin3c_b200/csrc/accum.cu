@@ -1011,36 +1011,39 @@ __global__ void k_block_row_len(const int64_t *__restrict__ ptr, const uint32_t 
     }
 }
 
+// One thread per entry of the block (the key holds its row), then one per row for the diagonal, placed by bisection
+// among the row's sorted columns: a warp-per-row walk left the longest row of a heavy-tailed community to one warp
+// (C4 on 8 GPUs: 2.2 ms on the rank that held it against 1.1 ms elsewhere).
 __global__ void __launch_bounds__(256) k_emit_block(int b, int32_t row_lo, int32_t n_local,
                                                     const uint64_t *__restrict__ uniq, const uint32_t *__restrict__ cnt,
                                                     const uint32_t *__restrict__ diag, const int64_t *__restrict__ ptr,
                                                     const int64_t *__restrict__ indptr, int32_t *__restrict__ indices,
                                                     uint32_t *__restrict__ counts) {
-    const unsigned lane = lane_id();
     const uint64_t jmask = (1ull << b) - 1ull;
-    const int64_t nw = (int64_t)gridDim.x * 8;
-    for (int64_t lr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); lr < n_local; lr += nw) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e_lo = ptr[row_lo], e_hi = ptr[row_lo + n_local];
+    for (int64_t e = e_lo + gid; e < e_hi; e += stride) {
+        const uint64_t k = uniq[e];
+        const int64_t r = (int64_t)(k >> b);
+        const int32_t c = (int32_t)(k & jmask);
+        const int64_t dst = indptr[r - row_lo] + (e - ptr[r]) + ((c >= (int32_t)r && diag[r]) ? 1 : 0);
+        indices[dst] = c;
+        counts[dst] = cnt[e];
+    }
+    for (int64_t lr = gid; lr < n_local; lr += stride) {
         const int64_t r = row_lo + lr;
-        const int64_t lo = ptr[r], hi = ptr[r + 1];
         const uint32_t d = diag[r];
-        const int64_t out0 = indptr[lr];
-        unsigned below = 0;          // entries with col < r, counted as they stream by
-        for (int64_t e0 = lo; e0 < hi; e0 += 32) {
-            const int64_t e = e0 + lane;
-            int32_t c = 0x7fffffff;
-            if (e < hi) c = (int32_t)(uniq[e] & jmask);
-            const bool lower = c < (int32_t)r;
-            if (e < hi) {
-                const int64_t dst = out0 + (e - lo) + ((!lower && d) ? 1 : 0);
-                indices[dst] = c;
-                counts[dst] = cnt[e];
-            }
-            below += __popc(__ballot_sync(kFullMask, lower));
+        if (!d) continue;
+        int64_t a = ptr[r], z = ptr[r + 1];
+        const int64_t first = a;
+        while (a < z) {                                 // entries of the row with column < r
+            const int64_t mid = (a + z) >> 1;
+            if ((int64_t)(uniq[mid] & jmask) < r) a = mid + 1;
+            else z = mid;
         }
-        if (lane == 0 && d) {
-            indices[out0 + below] = (int32_t)r;
-            counts[out0 + below] = d;
-        }
+        indices[indptr[lr] + (a - first)] = (int32_t)r;
+        counts[indptr[lr] + (a - first)] = d;
     }
 }
 
@@ -1752,8 +1755,7 @@ int b3c_accum_emit_block(void *d_ws, int32_t row_lo, int32_t row_hi, int64_t *d_
     const int32_t n_local = row_hi - row_lo;
     const int64_t *ip = (const int64_t *)(ws + st.o_indptr_f);
     B3C_CUDA(cudaMemcpyAsync(d_indptr, ip, ((size_t)n_local + 1) * 8, cudaMemcpyDeviceToDevice, s));
-    int64_t blocks = ceil_div(n_local, 8);
-    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    const int64_t blocks = (int64_t)kNumSMs * 16;          // grid-stride over the block's entries, then its rows
     k_emit_block<<<(unsigned)blocks, 256, 0, s>>>(st.b, row_lo, n_local, (const uint64_t *)(ws + st.o_uniq),
                                                   (const uint32_t *)(ws + st.o_cnt), (const uint32_t *)(ws + st.o_diag),
                                                   (const int64_t *)(ws + st.o_up_ptr), ip, d_indices, d_counts);

@@ -57,6 +57,7 @@ constexpr int RED_MAX = 8;                           // values reduced together 
 constexpr int SLAB_W_MAX = 28672;                    // fp64 entries of u held in shared memory (15-bit columns)
 constexpr int SLAB_S_MAX = 16;                       // more slabs than this: gather form (default; B3C_OPT_KR_MAX_SLABS)
 constexpr int SLAB_S_CAP = 48;                       // the most slabs the tables are sized for
+constexpr int SLAB_DENSE_CELL_PACKED = 4;            // the same for the packed count stream (4 B per entry instead of 10)
 constexpr int SLAB_DENSE_CELL = 6;                   // mean entries per (row, slab) cell from which slabs beyond SLAB_S_MAX pay
 constexpr int KR_MAX_RANKS = 8;                      // GPUs of one node in peer mode
 constexpr int BIG_CAP = 4096;                        // side list of off-diagonal counts above 65535 (packed count stream)
@@ -1932,7 +1933,8 @@ struct KRLayout {
 };
 
 // `rows`: rows of the block the stream is built for (n for a whole matrix): the density rule counts the block's cells
-static KRLayout kr_layout(int32_t n, int64_t nnz, int32_t rows) {
+// `packed`: the stream will hold packed counts (b3c_kr_run*_counts with B3C_OPT_KR_COUNT_STREAM = 2)
+static KRLayout kr_layout(int32_t n, int64_t nnz, int32_t rows, bool packed = false) {
     KRLayout L;
     Carver c;
     // Slab form whenever the matrix is at most B3C_OPT_KR_MAX_SLABS (16) slabs wide.  Wider matrices cut every row
@@ -1941,7 +1943,10 @@ static KRLayout kr_layout(int32_t n, int64_t nnz, int32_t rows) {
     // form 0.42 ms, slab form 0.69 ms; 9.2 per cell -> gather 1.37 ms, slab 1.06 ms; break-even near 5.
     const int64_t s_need = ceil_div(n, g_slab_w_max.load());
     const int s_max = g_slab_s_max.load();
-    const bool dense_cells = s_max >= SLAB_S_MAX && s_need <= SLAB_S_CAP && nnz >= SLAB_DENSE_CELL * (int64_t)rows * s_need;
+    // (the packed count stream moves 4 B per padded entry against the gather form's 8 B plus an L1 wavefront per entry:
+    // measured on C4's row blocks at 6 entries per cell, 1.9 us per million entries against 3.9)
+    const int dense = packed ? SLAB_DENSE_CELL_PACKED : SLAB_DENSE_CELL;
+    const bool dense_cells = s_max >= SLAB_S_MAX && s_need <= SLAB_S_CAP && nnz >= dense * (int64_t)rows * s_need;
     L.slab = (s_need <= s_max || dense_cells) ? 1 : 0;
     L.S = L.slab ? (int32_t)s_need : 1;
     L.W = L.slab ? (int32_t)align_up(ceil_div(n, L.S), 2) : n;
@@ -2254,7 +2259,9 @@ int b3c_set_option(int32_t key, int64_t value) {
 
 int64_t b3c_kr_workspace_bytes(int32_t n, int64_t nnz) {
     if (n <= 0 || nnz < 0) return B3C_ERR_ARG;
-    return kr_layout(n, nnz, n).total;
+    // the fp64 and the packed-count form of one matrix may choose differently between slab and gather: room for either
+    const int64_t a = kr_layout(n, nnz, n, false).total, b = kr_layout(n, nnz, n, true).total;
+    return a > b ? a : b;
 }
 
 // launch the persistent kernel on a prepared operand, wait, and report
@@ -2336,7 +2343,8 @@ static int kr_run_impl(int32_t n, int64_t nnz, const int64_t *d_indptr, const in
                        int32_t max_iter, double *d_x, void *d_ws, int64_t ws_bytes, int64_t *h_info, void *stream) {
     B3C_REQUIRE(n > 0 && nnz >= 0 && d_indptr && d_x && d_ws && h_info, "bad arguments");
     B3C_REQUIRE(nnz == 0 || (d_indices && (d_data || (d_counts && d_sites))), "null matrix arrays");
-    const KRLayout L = kr_layout(n, nnz, n);
+    const bool want_packed = !d_data && d_counts && g_cnt_stream.load() == 2;
+    const KRLayout L = kr_layout(n, nnz, n, want_packed);
     if (ws_bytes < L.total) {
         set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
         return B3C_ERR_CAPACITY;
@@ -2436,7 +2444,7 @@ static int kr_run_peer_impl(int32_t n, int32_t row_lo, int32_t row_hi, int64_t n
     B3C_REQUIRE(d_indptr && d_x && d_ws && h_info && h_exchange && nnz_local >= 0, "bad arguments");
     B3C_REQUIRE(n_ranks >= 1 && n_ranks <= KR_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank %d of %d (at most %d)",
                 rank, n_ranks, KR_MAX_RANKS);
-    const KRLayout L = kr_layout(n, nnz_local, row_hi - row_lo);
+    const KRLayout L = kr_layout(n, nnz_local, row_hi - row_lo, !d_data && d_counts && g_cnt_stream.load() == 2);
     if (ws_bytes < L.total) {
         set_error("KR workspace too small: %lld < %lld", (long long)ws_bytes, (long long)L.total);
         return B3C_ERR_CAPACITY;
@@ -2538,7 +2546,7 @@ int64_t b3c_krp_workspace_bytes(int32_t n, int64_t nnz_local) {
     if (n <= 0 || nnz_local < 0) return B3C_ERR_ARG;
     // the form (slab or gather) depends on how dense the block's cells are, i.e. on its row count, which is not known
     // here: room for either
-    const int64_t a = kr_layout(n, nnz_local, n).total, b = kr_layout(n, nnz_local, CHUNK).total;
+    const int64_t a = kr_layout(n, nnz_local, n).total, b = kr_layout(n, nnz_local, CHUNK, true).total;
     return a > b ? a : b;
 }
 

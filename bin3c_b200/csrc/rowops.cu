@@ -25,9 +25,22 @@ __global__ void __launch_bounds__(ROW_THREADS) k_max_offdiag(int32_t n, int32_t 
     for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
         const int64_t lo = indptr[r], hi = indptr[r + 1];
         T m = T(0);     // the zeroed diagonal is always a member of the column
-        for (int64_t e = lo + lane; e < hi; e += 32) {
-            const T v = val[e];
-            if (indices[e] != (int32_t)r + row_lo && v > m) m = v;
+        // four windows per trip, their loads in flight together: a row of 300k entries (C4's longest contigs) is walked
+        // by ONE warp, and its trips -- one memory round trip each -- are the kernel's tail
+#pragma unroll 1
+        for (int64_t e0 = lo + lane; e0 < hi; e0 += 128) {
+            T v[4];
+            int32_t c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t e = e0 + 32 * u;
+                const bool ok = e < hi;
+                v[u] = ok ? val[e] : T(0);
+                c[u] = ok ? indices[e] : (int32_t)r + row_lo;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c[u] != (int32_t)r + row_lo && v[u] > m) m = v[u];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -320,22 +333,32 @@ __global__ void __launch_bounds__(ROW_THREADS) k_edges_count(int32_t n, int32_t 
         const ContigAttr ar = ld_attr(attr + gr);
         if (ar.newidx >= 0) {
             const int64_t lo = indptr[r], hi = indptr[r + 1];
-            // the next window's column and count are loaded before this window's scattered gather is consumed
-            int32_t c_nx = (lo + lane < hi) ? indices[lo + lane] : 0;
-            uint32_t n_nx = (lo + lane < hi) ? counts[lo + lane] : 0u;
-            for (int64_t e = lo + lane; e < hi; e += 32) {
-                const int32_t c = c_nx;
-                const uint32_t cnt = n_nx;
-                if (e + 32 < hi) {
-                    c_nx = indices[e + 32];
-                    n_nx = counts[e + 32];
+            // four 32-entry windows per trip: their columns and counts, then their four scattered gathers, are in
+            // flight together (a long row is walked by one warp; its trips are the kernel's tail on heavy-tailed
+            // communities -- 2.4 ms of C4's pass with one window per trip)
+#pragma unroll 1
+            for (int64_t e0 = lo + lane; e0 < hi; e0 += 128) {
+                int32_t c[4];
+                uint32_t cnt[4];
+                ContigAttr ac[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t e = e0 + 32 * u;
+                    c[u] = e < hi ? indices[e] : -1;
+                    cnt[u] = e < hi ? counts[e] : 0u;
                 }
-                const ContigAttr ac = ld_attr(attr + c);
-                if (ac.newidx >= 0) {
-                    ++k;
-                    ed += (c >= gr) ? 1u : 0u;
-                    wmax = fmax(wmax, edge_value(cnt, ar, ac));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ac[u].newidx = -1;
+                    if (c[u] >= 0) ac[u] = ld_attr(attr + c[u]);
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ac[u].newidx >= 0) {
+                        ++k;
+                        ed += (c[u] >= gr) ? 1u : 0u;
+                        wmax = fmax(wmax, edge_value(cnt[u], ar, ac[u]));
+                    }
             }
         }
         k = warp_sum(k);
@@ -366,31 +389,49 @@ __global__ void __launch_bounds__(ROW_THREADS) k_edges_fill(int32_t n, int32_t r
         const int32_t gr = (int32_t)r + row_lo;
         const ContigAttr ar = ld_attr(attr + gr);
         if (ar.newidx < 0) continue;
-        const int64_t lo = indptr[r], hi = indptr[r + 1];
+        int64_t lo = indptr[r];
+        const int64_t hi = indptr[r + 1];
         int64_t ebase = edge_ex[r];
-        // columns are sorted: the upper-triangle entries (c >= row) are the tail of the row
-        int32_t c_nx = (lo + lane < hi) ? indices[lo + lane] : -1;
-        uint32_t n_nx = (lo + lane < hi) ? counts[lo + lane] : 0u;
-        for (int64_t e0 = lo; e0 < hi; e0 += 32) {
-            const int64_t e = e0 + lane;
-            const int32_t c = (e < hi) ? c_nx : -1;
-            const uint32_t cnt = n_nx;
-            if (e + 32 < hi) {                                              // next window, ahead of this one's gather
-                c_nx = indices[e + 32];
-                n_nx = counts[e + 32];
+        // columns are sorted: the upper-triangle entries (c >= row) are the tail of the row; a long row skips its
+        // lower part by bisection
+        if (hi - lo > 512) {
+            int64_t a = lo, z = hi;
+            while (a < z) {
+                const int64_t mid = (a + z) >> 1;
+                if (indices[mid] < gr) a = mid + 1;
+                else z = mid;
             }
-            ContigAttr ac;
-            ac.newidx = -1;
-            if (c >= gr) ac = ld_attr(attr + c);
-            const bool is_edge = ac.newidx >= 0;
-            const unsigned me = __ballot_sync(kFullMask, is_edge);
-            if (is_edge) {
-                const int64_t d = ebase + __popc(me & lt);
-                eu[d] = ar.newidx;
-                ev[d] = ac.newidx;
-                ew[d] = __dmul_rn(edge_value(cnt, ar, ac), scl);            // cluster.py:321
+            lo = a;
+        }
+        // four windows per trip, as in k_edges_count; the edges keep the row's column order
+#pragma unroll 1
+        for (int64_t e0 = lo + lane; e0 < hi + lane; e0 += 128) {           // (+ lane: every lane makes the same trips)
+            int32_t c[4];
+            uint32_t cnt[4];
+            ContigAttr ac[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t e = e0 + 32 * u;
+                c[u] = e < hi ? indices[e] : -1;
+                cnt[u] = e < hi ? counts[e] : 0u;
             }
-            ebase += __popc(me);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ac[u].newidx = -1;
+                if (c[u] >= gr) ac[u] = ld_attr(attr + c[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool is_edge = ac[u].newidx >= 0;
+                const unsigned me = __ballot_sync(kFullMask, is_edge);
+                if (is_edge) {
+                    const int64_t d = ebase + __popc(me & lt);
+                    eu[d] = ar.newidx;
+                    ev[d] = ac[u].newidx;
+                    ew[d] = __dmul_rn(edge_value(cnt[u], ar, ac[u]), scl);  // cluster.py:321
+                }
+                ebase += __popc(me);
+            }
         }
     }
 }
