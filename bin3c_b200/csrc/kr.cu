@@ -1463,42 +1463,41 @@ __device__ __forceinline__ void stream_set_flag(uint16_t *sflag, int64_t pos) {
 }
 
 // Pass 1, one thread per (row, slab) cell: columns are sorted within a row, so the cell's entries are the run between
-// two lower bounds.  cstart[v] = offset of the cell's first entry inside its row, cnt[v] = its padded length.
+// two lower bounds.  cstart[v] = offset of the cell's first entry inside its row (k_cell_bounds, one bisection per
+// cell); cnt[v] = its padded length, from the start of the same row's next cell (k_cell_len).
 template <bool SLAB>
-__global__ void __launch_bounds__(256) k_cell_bounds(KRArgs A, int64_t *__restrict__ cnt, int32_t *__restrict__ cstart) {
+__global__ void __launch_bounds__(256) k_cell_bounds(KRArgs A, int32_t *__restrict__ cstart) {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= A.nv) return;
     const int s = (int)(v / A.npad);
     const int64_t lr = v - (int64_t)s * A.npad;
-    if (lr >= A.row_hi - A.row_lo) {
-        cnt[v] = 0;
+    if (lr >= A.row_hi - A.row_lo || s == 0) {
         cstart[v] = 0;
         return;
     }
     const int64_t lo = A.indptr[lr], hi = A.indptr[lr + 1];
-    int64_t first = lo, last = hi;
-    if (s > 0) {                                       // first entry with column >= s * W
-        const int32_t key = s * A.W;
-        int64_t a = lo, b = hi;
-        while (a < b) {
-            const int64_t mid = (a + b) >> 1;
-            if (A.indices[mid] < key) a = mid + 1;
-            else b = mid;
-        }
-        first = a;
+    const int32_t key = s * A.W;                       // first entry with column >= s * W, over the whole row: on an
+    int64_t a = lo, b = hi;                            // unsorted row (which pass 2 reports) cells may then overlap or
+    while (a < b) {                                    // come out of order, but never reach outside the row
+        const int64_t mid = (a + b) >> 1;
+        if (A.indices[mid] < key) a = mid + 1;
+        else b = mid;
     }
-    if (s < A.S - 1) {
-        const int32_t key = (s + 1) * A.W;
-        int64_t a = lo, b = hi;                        // over the whole row, exactly as cell s + 1 finds its start: the
-        while (a < b) {                                // two agree even on an unsorted row (which pass 2 reports)
-            const int64_t mid = (a + b) >> 1;
-            if (A.indices[mid] < key) a = mid + 1;
-            else b = mid;
-        }
-        last = a;
+    cstart[v] = (int32_t)(a - lo);
+}
+
+__global__ void __launch_bounds__(256) k_cell_len(KRArgs A, const int32_t *__restrict__ cstart, int64_t *__restrict__ cnt) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= A.nv) return;
+    const int s = (int)(v / A.npad);
+    const int64_t lr = v - (int64_t)s * A.npad;
+    int64_t len = 0;
+    if (lr < A.row_hi - A.row_lo) {
+        const int64_t c0 = cstart[v];
+        const int64_t c1 = s < A.S - 1 ? (int64_t)cstart[v + A.npad] : A.indptr[lr + 1] - A.indptr[lr];
+        len = c1 > c0 ? c1 - c0 : 0;
     }
-    cstart[v] = (int32_t)(first - lo);
-    cnt[v] = seg_padded(last > first ? last - first : 0);
+    cnt[v] = seg_padded(len);
 }
 
 // Pass 2: copy the cells into the stream.  A warp takes 32 consecutive cells (same slab, consecutive rows) and spreads
@@ -2128,7 +2127,9 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
         B3C_LAUNCH_CHECK();
     }
     if (A.nv > 0) {
-        k_cell_bounds<SLAB><<<(unsigned)ceil_div(A.nv, 256), 256, 0, s>>>(A, A.cnt, A.cstart);
+        k_cell_bounds<SLAB><<<(unsigned)ceil_div(A.nv, 256), 256, 0, s>>>(A, A.cstart);
+        B3C_LAUNCH_CHECK();
+        k_cell_len<<<(unsigned)ceil_div(A.nv, 256), 256, 0, s>>>(A, A.cstart, A.cnt);
         B3C_LAUNCH_CHECK();
     }
     k_slab_pad<<<(unsigned)A.S, 1024, 0, s>>>(A, A.cnt);

@@ -25,22 +25,9 @@ __global__ void __launch_bounds__(ROW_THREADS) k_max_offdiag(int32_t n, int32_t 
     for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
         const int64_t lo = indptr[r], hi = indptr[r + 1];
         T m = T(0);     // the zeroed diagonal is always a member of the column
-        // four windows per trip, their loads in flight together: a row of 300k entries (C4's longest contigs) is walked
-        // by ONE warp, and its trips -- one memory round trip each -- are the kernel's tail
-#pragma unroll 1
-        for (int64_t e0 = lo + lane; e0 < hi; e0 += 128) {
-            T v[4];
-            int32_t c[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t e = e0 + 32 * u;
-                const bool ok = e < hi;
-                v[u] = ok ? val[e] : T(0);
-                c[u] = ok ? indices[e] : (int32_t)r + row_lo;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (c[u] != (int32_t)r + row_lo && v[u] > m) m = v[u];
+        for (int64_t e = lo + lane; e < hi; e += 32) {
+            const T v = val[e];
+            if (indices[e] != (int32_t)r + row_lo && v > m) m = v;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
