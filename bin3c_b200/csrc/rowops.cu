@@ -143,23 +143,50 @@ __global__ void __launch_bounds__(ROW_THREADS) k_asym_count(int32_t n, const int
 // ---- compress + edge weighting ------------------------------------------------------------------
 // workspace layout (int64 elements unless noted)
 struct CompressWs {
-    int64_t o_flag, o_newidx64, o_kept, o_kept_ex, o_edge, o_edge_ex, o_scan, o_max, o_attr, total;
+    int64_t o_flag, o_newidx64, o_kept, o_kept_ex, o_edge, o_edge_ex, o_scan, o_max, o_attr;
+    int64_t o_nseg, o_seg_ex, o_seg_row, o_seg_len, total;
 };
+// The fused edge kernels work on row SEGMENTS (a row cut into pieces of seg_len entries, seg_len = max(EDGE_SEG, mean
+// row length): at most 2 n_local + 1 of them), so their per-row arrays are sized for that.
+constexpr int EDGE_SEG = 4096;
 static CompressWs compress_layout(int32_t n) {
     Carver c;
     CompressWs w;
-    const int64_t n1 = (int64_t)n + 1;
+    const int64_t n1 = (int64_t)n + 1, n2 = 2 * (int64_t)n + 2;
     w.o_flag = c.take(n1 * 8);
     w.o_newidx64 = c.take(n1 * 8);
-    w.o_kept = c.take(n1 * 8);
-    w.o_kept_ex = c.take(n1 * 8);
-    w.o_edge = c.take(n1 * 8);
-    w.o_edge_ex = c.take(n1 * 8);
-    w.o_scan = c.take(scan_tmp_elems(n) * 8);
+    w.o_kept = c.take(n2 * 8);
+    w.o_kept_ex = c.take(n2 * 8);
+    w.o_edge = c.take(n2 * 8);
+    w.o_edge_ex = c.take(n2 * 8);
+    w.o_scan = c.take(scan_tmp_elems(n2) * 8);
     w.o_max = c.take(64);
     w.o_attr = c.take((int64_t)n * 16);
+    w.o_nseg = c.take(n1 * 8);
+    w.o_seg_ex = c.take(n1 * 8);
+    w.o_seg_row = c.take(n2 * 4);
+    w.o_seg_len = c.take(64);
     w.total = c.cur;
     return w;
+}
+
+// ---- row segments: a heavy-tailed community has rows of 10^5 entries next to rows of ten; a warp per ROW leaves
+// the longest row to one warp (its trips were C4's edge stage), a warp per SEGMENT does not --------------------------
+__global__ void k_seg_len(int32_t n_local, const int64_t *__restrict__ indptr, int64_t *__restrict__ seg_len) {
+    const int64_t mean = (indptr[n_local] - indptr[0] + n_local - 1) / (n_local > 0 ? n_local : 1);
+    *seg_len = mean > EDGE_SEG ? mean : EDGE_SEG;
+}
+__global__ void k_seg_count(int32_t n_local, const int64_t *__restrict__ indptr, const int64_t *__restrict__ seg_len,
+                            int64_t *__restrict__ nseg) {
+    const int64_t T = *seg_len;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_local; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t len = indptr[r + 1] - indptr[r];
+        nseg[r] = len > T ? (len + T - 1) / T : 1;
+    }
+}
+__global__ void k_seg_rows(int32_t n_local, const int64_t *__restrict__ seg_ex, int32_t *__restrict__ seg_row) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_local; r += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t q = seg_ex[r]; q < seg_ex[r + 1]; ++q) seg_row[q] = (int32_t)r;
 }
 
 __global__ void k_mask_flags(int32_t n, const uint8_t *__restrict__ mask, int64_t *__restrict__ flag) {
@@ -304,25 +331,29 @@ __device__ __forceinline__ double edge_value(uint32_t count, const ContigAttr &a
     return __dmul_rn(ar.x, __dmul_rn(site_scaled(count, ar.site, ac.site), ac.x));
 }
 
-__global__ void __launch_bounds__(ROW_THREADS) k_edges_count(int32_t n, int32_t row_lo,
-                                                             const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(ROW_THREADS) k_edges_count(int32_t row_lo, const int64_t *__restrict__ indptr,
                                                              const int32_t *__restrict__ indices,
                                                              const uint32_t *__restrict__ counts,
                                                              const ContigAttr *__restrict__ attr,
+                                                             const int64_t *__restrict__ seg_ex,
+                                                             const int32_t *__restrict__ seg_row, int32_t n_local,
+                                                             const int64_t *__restrict__ seg_len,
                                                              int64_t *__restrict__ kept, int64_t *__restrict__ edge,
                                                              unsigned long long *__restrict__ vmax) {
     const unsigned lane = lane_id();
     const int64_t nw = (int64_t)gridDim.x * ROW_WARPS;
+    const int64_t n_seg = seg_ex[n_local], T = *seg_len;
     double wmax = 0.0;
-    for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
+    for (int64_t q = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); q < n_seg; q += nw) {
         unsigned k = 0, ed = 0;
-        const int32_t gr = (int32_t)r + row_lo;
+        const int32_t r = seg_row[q];
+        const int32_t gr = r + row_lo;
         const ContigAttr ar = ld_attr(attr + gr);
         if (ar.newidx >= 0) {
-            const int64_t lo = indptr[r], hi = indptr[r + 1];
+            const int64_t lo = indptr[r] + (q - seg_ex[r]) * T;
+            const int64_t hi = min(indptr[r + 1], lo + T);
             // four 32-entry windows per trip: their columns and counts, then their four scattered gathers, are in
-            // flight together (a long row is walked by one warp; its trips are the kernel's tail on heavy-tailed
-            // communities -- 2.4 ms of C4's pass with one window per trip)
+            // flight together
 #pragma unroll 1
             for (int64_t e0 = lo + lane; e0 < hi; e0 += 128) {
                 int32_t c[4];
@@ -351,46 +382,41 @@ __global__ void __launch_bounds__(ROW_THREADS) k_edges_count(int32_t n, int32_t 
         k = warp_sum(k);
         ed = warp_sum(ed);
         if (lane == 0) {
-            kept[r] = k;
-            edge[r] = ed;
+            kept[q] = k;
+            edge[q] = ed;
         }
     }
     wmax = warp_max(wmax);
     if (lane == 0 && wmax > 0.0) atomicMax(vmax, (unsigned long long)__double_as_longlong(wmax));
 }
 
-__global__ void __launch_bounds__(ROW_THREADS) k_edges_fill(int32_t n, int32_t row_lo,
-                                                            const int64_t *__restrict__ indptr,
+__global__ void __launch_bounds__(ROW_THREADS) k_edges_fill(int32_t row_lo, const int64_t *__restrict__ indptr,
                                                             const int32_t *__restrict__ indices,
                                                             const uint32_t *__restrict__ counts,
                                                             const ContigAttr *__restrict__ attr,
+                                                            const int64_t *__restrict__ seg_ex,
+                                                            const int32_t *__restrict__ seg_row, int32_t n_local,
+                                                            const int64_t *__restrict__ seg_len,
                                                             const int64_t *__restrict__ edge_ex,
                                                             const double *__restrict__ vmax, int scale,
                                                             int32_t *__restrict__ eu, int32_t *__restrict__ ev,
                                                             double *__restrict__ ew, double *__restrict__ scl_out) {
     const unsigned lane = lane_id(), lt = lanemask_lt();
     const int64_t nw = (int64_t)gridDim.x * ROW_WARPS;
+    const int64_t n_seg = seg_ex[n_local], T = *seg_len;
     const double scl = scale ? __ddiv_rn(1.0, *vmax) : 1.0;                 // cluster.py:316
     if (blockIdx.x == 0 && threadIdx.x == 0 && scl_out) *scl_out = scl;
-    for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < n; r += nw) {
-        const int32_t gr = (int32_t)r + row_lo;
+    for (int64_t q = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); q < n_seg; q += nw) {
+        const int32_t r = seg_row[q];
+        const int32_t gr = r + row_lo;
         const ContigAttr ar = ld_attr(attr + gr);
         if (ar.newidx < 0) continue;
-        int64_t lo = indptr[r];
-        const int64_t hi = indptr[r + 1];
-        int64_t ebase = edge_ex[r];
-        // columns are sorted: the upper-triangle entries (c >= row) are the tail of the row; a long row skips its
-        // lower part by bisection
-        if (hi - lo > 512) {
-            int64_t a = lo, z = hi;
-            while (a < z) {
-                const int64_t mid = (a + z) >> 1;
-                if (indices[mid] < gr) a = mid + 1;
-                else z = mid;
-            }
-            lo = a;
-        }
-        // four windows per trip, as in k_edges_count; the edges keep the row's column order
+        const int64_t lo = indptr[r] + (q - seg_ex[r]) * T;
+        const int64_t hi = min(indptr[r + 1], lo + T);
+        if (edge_ex[q + 1] == edge_ex[q]) continue;                         // no upper-triangle entry in this piece
+        int64_t ebase = edge_ex[q];
+        // columns are sorted: the upper-triangle entries (c >= row) are the tail of the row; the edges keep the row's
+        // column order (segments are numbered along the row, four windows per trip as in k_edges_count)
 #pragma unroll 1
         for (int64_t e0 = lo + lane; e0 < hi + lane; e0 += 128) {           // (+ lane: every lane makes the same trips)
             int32_t c[4];
@@ -599,16 +625,32 @@ int b3c_edges_count(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d
     if (rc) return rc;
     k_edge_attr<<<g, 256, 0, s>>>(n, d_mask, nidx, d_sites, d_x, attr, d_newidx);
     B3C_LAUNCH_CHECK();
-    k_edges_count<<<row_grid(n_local), ROW_THREADS, 0, s>>>(n_local, row_lo, d_indptr, d_indices, d_counts, attr, kept,
-                                                            edge, (unsigned long long *)d_vmax);
+    // row segments (at most 2 n_local + 1), then a warp per segment
+    int64_t *nseg = (int64_t *)(ws + w.o_nseg), *seg_ex = (int64_t *)(ws + w.o_seg_ex);
+    int64_t *seg_len = (int64_t *)(ws + w.o_seg_len);
+    int32_t *seg_row = (int32_t *)(ws + w.o_seg_row);
+    const int64_t n2 = 2 * (int64_t)n_local + 1;
+    const unsigned gl = (unsigned)ceil_div(n_local, 256);
+    k_seg_len<<<1, 1, 0, s>>>(n_local, d_indptr, seg_len);
     B3C_LAUNCH_CHECK();
-    rc = scan_exclusive_i64(kept, kept_ex, n_local, scan, s);
+    k_seg_count<<<gl, 256, 0, s>>>(n_local, d_indptr, seg_len, nseg);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(nseg, seg_ex, n_local, scan, s);
     if (rc) return rc;
-    rc = scan_exclusive_i64(edge, edge_ex, n_local, scan, s);
+    k_seg_rows<<<gl, 256, 0, s>>>(n_local, seg_ex, seg_row);
+    B3C_LAUNCH_CHECK();
+    B3C_CUDA(cudaMemsetAsync(kept, 0, (size_t)n2 * 8, s));
+    B3C_CUDA(cudaMemsetAsync(edge, 0, (size_t)n2 * 8, s));
+    k_edges_count<<<row_grid(n_local), ROW_THREADS, 0, s>>>(row_lo, d_indptr, d_indices, d_counts, attr, seg_ex, seg_row,
+                                                            n_local, seg_len, kept, edge, (unsigned long long *)d_vmax);
+    B3C_LAUNCH_CHECK();
+    rc = scan_exclusive_i64(kept, kept_ex, n2, scan, s);
+    if (rc) return rc;
+    rc = scan_exclusive_i64(edge, edge_ex, n2, scan, s);
     if (rc) return rc;
     B3C_CUDA(cudaMemcpyAsync(&h_out[0], nidx + n, 8, cudaMemcpyDeviceToHost, s));
-    B3C_CUDA(cudaMemcpyAsync(&h_out[1], kept_ex + n_local, 8, cudaMemcpyDeviceToHost, s));
-    B3C_CUDA(cudaMemcpyAsync(&h_out[2], edge_ex + n_local, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(&h_out[1], kept_ex + n2, 8, cudaMemcpyDeviceToHost, s));
+    B3C_CUDA(cudaMemcpyAsync(&h_out[2], edge_ex + n2, 8, cudaMemcpyDeviceToHost, s));
     B3C_CUDA(cudaStreamSynchronize(s));
     return B3C_OK;
 }
@@ -622,7 +664,8 @@ int b3c_edges_fill(int32_t n, int32_t row_lo, int32_t n_local, const int64_t *d_
     const CompressWs w = compress_layout(n);
     char *ws = (char *)d_ws;
     k_edges_fill<<<row_grid(n_local), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-        n_local, row_lo, d_indptr, d_indices, d_counts, (const ContigAttr *)(ws + w.o_attr),
+        row_lo, d_indptr, d_indices, d_counts, (const ContigAttr *)(ws + w.o_attr), (const int64_t *)(ws + w.o_seg_ex),
+        (const int32_t *)(ws + w.o_seg_row), n_local, (const int64_t *)(ws + w.o_seg_len),
         (const int64_t *)(ws + w.o_edge_ex), d_vmax, scale, d_edge_u, d_edge_v, d_edge_w, d_scl);
     B3C_LAUNCH_CHECK();
     return B3C_OK;
