@@ -577,6 +577,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
     __shared__ uint32_t s_off[RS_BINS];
     __shared__ uint32_t s_tot[RS_BINS];
     __shared__ uint32_t s_bin[RS_BINS];
+    __shared__ uint32_t s_dst[RS_BINS];         // s_off - s_bin of the current tile: out index = s_dst[d] + q
     __shared__ uint32_t s_scan[33];
     extern __shared__ __align__(16) unsigned char rs_dyn[];
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(rs_dyn);     // RS_TILE keys (32 KB, dynamic)
@@ -654,7 +655,13 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
             const uint32_t v = (threadIdx.x < RS_BINS) ? s_tot[threadIdx.x] : 0u;
             uint32_t tot;
             const uint32_t ex = block_scan_excl<uint32_t>(v, s_scan, &tot);
-            if (threadIdx.x < RS_BINS) s_bin[threadIdx.x] = ex;
+            if (threadIdx.x < RS_BINS) {
+                // digit d's keys of this tile go to out[s_off[d] ...]; thread d alone touches s_off[d], so it moves
+                // on to the next tile here (the write-out below reads s_dst): no barrier at the end of the tile
+                s_bin[threadIdx.x] = ex;
+                s_dst[threadIdx.x] = s_off[threadIdx.x] - ex;            // (mod 2^32, undone by + q below)
+                s_off[threadIdx.x] += v;
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -664,11 +671,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *__res
         for (int q = threadIdx.x; q < cnt; q += RS_THREADS) {
             const uint64_t kk = s_keys[q];
             const unsigned d = (unsigned)(kk >> shift) & mask;
-            out[(int64_t)s_off[d] + (q - (int)s_bin[d])] = kk;
+            out[(int64_t)(uint32_t)(s_dst[d] + (uint32_t)q)] = kk;
         }
-        __syncthreads();
-        if (threadIdx.x < RS_BINS) s_off[threadIdx.x] += s_tot[threadIdx.x];
-        __syncthreads();
+        // the next tile's first writes to s_wcnt / s_keys / s_tot / s_bin / s_dst all lie behind its own barriers;
+        // s_wcnt (zeroed at the top) was last read before the barrier above
     }
 }
 

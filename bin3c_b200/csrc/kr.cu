@@ -179,7 +179,7 @@ struct KRArgs {
     unsigned long long *ll;                     // [P_COUNT][n_chunks][2] flagged words: partials exchanged without a barrier
 };
 enum { KR_OPT_BANK_ORDER = 1, KR_OPT_SLAB_ALIGN = 2, KR_OPT_FAST_BARRIER = 4, KR_OPT_LL_PARTIALS = 8, KR_OPT_PEER_LL_W = 16,
-       KR_OPT_L2_PREFETCH = 32, KR_OPT_L2_PREFETCH_FAR = 64 };
+       KR_OPT_L2_PREFETCH = 32, KR_OPT_L2_PREFETCH_FAR = 64, KR_OPT_PIECE_SPREAD = 128 };
 
 // What crosses the NVLink in peer mode: the owner of row r writes x[r] (once per Newton update) and Z[r] (once per CG
 // step) straight into every rank's copy, and its chunk partials likewise.  Every rank then derives p and u = x * p for
@@ -1562,7 +1562,23 @@ __global__ void __launch_bounds__(256) k_stream_fill(KRArgs A, const int32_t *__
                 col = col_lo;
             }
             const unsigned lc = (unsigned)(col - col_lo);
-            const int64_t ph = stream_phys(dst + (int64_t)p * SPMV_EPP) + sub;
+            // Where inside its piece an entry goes is free (a piece is added up whole).  At step i of a piece the 32
+            // lanes of the SpMV gather u[col] of their own pieces' i-th entries from shared memory, 16 fp64 bank pairs
+            // per half-warp: consecutive lanes hold consecutive pieces of one row, whose columns run on (dense blocks)
+            // or are spread evenly, so entry i of all of them falls on the same one or two bank pairs.  Order a piece by
+            // bank pair (descending for odd lanes) and rotate it by half the lane number: the lanes then walk the bank
+            // pairs out of step with each other.
+            unsigned slot = sub;
+            if (SLAB && (A.opts & KR_OPT_PIECE_SPREAD)) {
+                const unsigned gmask = 0xffu << (8 * grp);
+                const unsigned key = ((lc & 15u) << 3) | sub;
+                unsigned rank = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rank += __shfl_sync(gmask, key, j, 8) < key ? 1u : 0u;
+                const unsigned pl = (unsigned)(((dst + (int64_t)p * SPMV_EPP) & (SPMV_CHUNK - 1)) >> 4);   // its lane
+                slot = (((pl & 1u) ? 7u - rank : rank) - (pl >> 1)) & 7u;
+            }
+            const int64_t ph = stream_phys(dst + (int64_t)p * SPMV_EPP) + slot;
             if (A.cnt_stream) {
                 const uint32_t cnt_e = valid ? A.cnt32[e] : 0u;
                 if (A.cnt_stream == 2) {
@@ -1920,7 +1936,7 @@ static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
 // only pay for solves of more than ~180 SpMV (typical: 24-40)
 // B3C_OPT_KR_COUNT_STREAM: the counts form streams uint32 counts (6 B per entry) instead of fp64 values (10 B)
 static std::atomic<int> g_cnt_stream{2};
-static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER | KR_OPT_PEER_LL_W};
+static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER | KR_OPT_PEER_LL_W | KR_OPT_PIECE_SPREAD};
 constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
 
 struct KRLayout {
@@ -2237,7 +2253,7 @@ int b3c_set_option(int32_t key, int64_t value) {
             g_slab_s_max.store((int)value);
             return B3C_OK;
         case B3C_OPT_KR_FLAGS:
-            B3C_REQUIRE(value >= 0 && value <= 127, "KR option flags must be in [0, 127]");
+            B3C_REQUIRE(value >= 0 && value <= 255, "KR option flags must be in [0, 255]");
             g_kr_opts.store((int)value);
             return B3C_OK;
         case B3C_OPT_KR_COUNT_STREAM:
