@@ -1505,7 +1505,7 @@ __global__ void __launch_bounds__(256) k_cell_len(KRArgs A, const int32_t *__res
 // consecutive stream entries (one 32-byte sector of the packed form) out, so a long cell does not hold up a lane and a
 // short one does not idle 31.  The last piece of a cell carries its zero padding; the first one sets the start flag.
 // Entries are checked against their cell's column range: an unsorted or out-of-range row shows up here.
-template <bool SLAB>
+template <bool SLAB, bool SPREAD = false>
 __global__ void __launch_bounds__(256) k_stream_fill(KRArgs A, const int32_t *__restrict__ cstart, double *__restrict__ sval,
                                                      void *__restrict__ scol_v, uint16_t *__restrict__ sflag) {
     const unsigned lane = lane_id(), grp = lane >> 3, sub = lane & 7u;
@@ -1568,8 +1568,9 @@ __global__ void __launch_bounds__(256) k_stream_fill(KRArgs A, const int32_t *__
             // or are spread evenly, so entry i of all of them falls on the same one or two bank pairs.  Order a piece by
             // bank pair (descending for odd lanes) and rotate it by half the lane number: the lanes then walk the bank
             // pairs out of step with each other.
+            // (SPREAD is a template parameter: the default build of this kernel must not carry the ranking's registers)
             unsigned slot = sub;
-            if (SLAB && (A.opts & KR_OPT_PIECE_SPREAD)) {
+            if (SLAB && SPREAD) {
                 const unsigned gmask = 0xffu << (8 * grp);
                 const unsigned key = ((lc & 15u) << 3) | sub;
                 unsigned rank = 0;
@@ -1936,7 +1937,10 @@ static std::atomic<int> g_slab_s_max{SLAB_S_MAX};
 // only pay for solves of more than ~180 SpMV (typical: 24-40)
 // B3C_OPT_KR_COUNT_STREAM: the counts form streams uint32 counts (6 B per entry) instead of fp64 values (10 B)
 static std::atomic<int> g_cnt_stream{2};
-static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER | KR_OPT_PEER_LL_W | KR_OPT_PIECE_SPREAD};
+// KR_OPT_PIECE_SPREAD stays off as well: it takes 5 % of the u gather's shared-memory wavefronts away (C3: 592.8M -> 564.3M,
+// KR kernel 5.11 -> 5.04 ms) but the ranking shuffles cost k_stream_fill more than that (0.60 -> 0.82 ms at C3, + 1.0 ms
+// of set-up at C4 where the kernel gains nothing): profiles/raw/r4b_*, r4d_*, r4e_launch_table_c3_n1.md
+static std::atomic<int> g_kr_opts{KR_OPT_SLAB_ALIGN | KR_OPT_FAST_BARRIER | KR_OPT_PEER_LL_W};
 constexpr int BND_MAX = 148 * 2 + 8;                   // >= any SpMV grid
 
 struct KRLayout {
@@ -2175,7 +2179,8 @@ static int kr_prepare_t(KRArgs &A, const KRLayout &L, cudaStream_t s) {
     const int64_t n_batch = A.nv / 32;
     const unsigned fill_grid = row_warp_grid(n_batch);                           // a warp per batch of 32 cells, grid-stride
     for (int attempt = 0; attempt < 2; ++attempt) {
-        k_stream_fill<SLAB><<<fill_grid, 256, 0, s>>>(A, A.cstart, sval, scol, sflag);
+        if (SLAB && (A.opts & KR_OPT_PIECE_SPREAD)) k_stream_fill<SLAB, true><<<fill_grid, 256, 0, s>>>(A, A.cstart, sval, scol, sflag);
+        else k_stream_fill<SLAB><<<fill_grid, 256, 0, s>>>(A, A.cstart, sval, scol, sflag);
         B3C_LAUNCH_CHECK();
         B3C_CUDA(cudaMemcpyAsync(&S, A.ctl, sizeof(S), cudaMemcpyDeviceToHost, s));
         B3C_CUDA(cudaStreamSynchronize(s));

@@ -181,14 +181,16 @@ int b3c_site_norm_f64(int32_t n_local, int32_t row_lo, const int64_t *d_indptr,
  * to 48 slabs whose (row, slab) cells hold 6 or more entries on average stay in the slab form; b3c_kr_run_peer*
  * applies that rule to its own row block).  Results are
  * identical up to fp64 summation order.  Workspace sizes depend on these, so set them before the *_workspace_bytes() query.
- * B3C_OPT_KR_FLAGS (default 150) is a bit set for A/B measurements: 1 = order every lane's run of the
+ * B3C_OPT_KR_FLAGS (default 22) is a bit set for A/B measurements: 1 = order every lane's run of the
  * stream by shared-memory bank (off: the pass costs more than it saves below ~180 SpMV per solve), 2 = align the SpMV CTA ranges with the slabs, 4 = single-word grid
  * barrier (release-add + acquire-poll), 8 = on one GPU the phases that only produce reduction partials
  * hand them over as flagged 8-byte words instead of passing a grid barrier (off: measured slower), 16 = in
  * peer mode (several GPUs) the p.w partials after the `w` phase cross the NVLink as such flagged words
  * instead of a system-fenced flag barrier, 32 / 64 = L2 prefetch of the stream 6 / + 12 chunks ahead (off: no gain
  * measured), 128 = the stream builder orders every 8-entry piece by shared-memory bank pair and rotates it by the lane
- * that will process it, so that the lanes of a half-warp gather from different banks (slab form; costs no extra pass).
+ * that will process it, so that the lanes of a half-warp gather from different banks (slab form; off: with shuffled contig
+ * order the columns of a piece are random, the order removes 5 % of the gather's wavefronts and its ranking costs the
+ * stream builder more than the kernel gains).
  * B3C_OPT_PEER_TIMEOUT_MS (default 60000): how long a cross-GPU flag wait (peer barriers of the sharded
  * accumulation, hand-overs of peer-mode KR) may last before it gives up.  A time-out is reported as
  * B3C_ERR_CUDA by the next call that synchronises and the results of that run are invalid; it is cleared

@@ -63,7 +63,7 @@ def main():
                        sync_us={n: round(v / mhz, 1) for n, v in k['sync_cycles'].items() if v},
                        cta_spmv_us={n: round(v / mhz, 1) for n, v in k['cta_spmv_cycles'].items()})
             print(json.dumps(out), flush=True)
-    dev.check(dev.lib.b3c_set_option(3, 150))
+    dev.check(dev.lib.b3c_set_option(3, 22))
 
 
 if __name__ == '__main__':
