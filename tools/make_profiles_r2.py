@@ -19,6 +19,21 @@ sys.path.insert(0, os.path.join(ROOT, 'tools'))
 from make_profiles import SHORT, fmt      # noqa: E402
 
 
+# what a reader has to know about a visit's build
+NOTES = {
+    'r4e': '''
+Note on this visit's build.  It ran with the KR stream's piece spread ON (`B3C_OPT_KR_FLAGS` bit 128, then the default):
+`k_stream_fill` carries the ranking shuffles here (816 us per launch against 598 us in the previous visit,
+`raw/r3b_launch_table_c3_n1.md`) and `k_kr_persistent` has 5 % fewer shared-memory wavefronts in its `u` gather
+(`raw/r4d_ncu_kr_piece_spread_c3.csv`: 592.8M -> 564.3M loads' wavefronts, 5.107 -> 5.052 ms).  The set-up lost more than
+the kernel gained, so the spread is now an opt-in template instantiation and the default `k_stream_fill` is again the
+598 us kernel (instruction-identical to the earlier build; live line of the final default build: `raw/r4g_bench_n1.json`,
+14.84 ms per pass, KR stage 6.15 ms = kernel 5.14 + set-up 1.01; with the spread on it was 6.25 = 5.03 + 1.22,
+`raw/r4e_bench_n1.json`).  Every other kernel of the list is the final build's.
+''',
+}
+
+
 def launches(tag, bench):
     tab = open(os.path.join(OUT, 'launch_table_%s.md' % tag)).read()
     rows = [[x.strip() for x in l.strip('|').split('|')] for l in tab.splitlines() if l.startswith('| b3c::')]
@@ -38,7 +53,7 @@ host records in chunks, hence the 65 `k_classify` launches) plus the one-off dev
 (`k_synth_pairs`, not part of a pass).  Times are cold-cache and serialised under ncu: compare SHARES, not absolutes.
 
 ''' % tag + tab + '''
-Share check against the live run of the same box visit (`profiles/raw/r3b_bench_n1_final.json`, pass %.3f ms), shares
+Share check against the live run of the same box visit (`profiles/raw/TAG_bench_n1.json`, pass %.3f ms), shares
 of the pass itself (generator excluded):
 k_kr_persistent %.1f %% here vs %.3f ms / %.3f ms = %.1f %% live; k_classify %.1f %% vs %.3f / %.3f = %.1f %% live;
 radix sort + RLE + emit (k_rs_*, k_rle_*, k_emit, k_row_*, k_diag_stats, k_accum_guard and the scans) %.1f %% here vs
@@ -52,7 +67,8 @@ edges (k_edges_*, k_edge_attr, k_mask_flags) %.1f %% here vs compress_edges %.3f
        100 * st['sort_reduce_emit'] / step,
        scale * share(r'k_stream_|k_slab_|k_chunk_seg0|k_cell_|k_diag_fix|k_inv_sites|k_big_build'), st['kr'],
        kr['ms_per_launch'], step, 100 * (st['kr'] - kr['ms_per_launch']) / step,
-       scale * share(r'k_edges_|k_edge_attr|k_mask_flags'), st['compress_edges'], step, 100 * st['compress_edges'] / step)
+       scale * share(r'k_edges_|k_edge_attr|k_mask_flags|k_seg_'), st['compress_edges'], step, 100 * st['compress_edges'] / step)
+    txt = txt.replace('TAG_bench_n1', tag + '_bench_n1') + NOTES.get(tag, '')
     open(os.path.join(PROF, 'r2_launches_final.md'), 'w').write(txt)
 
 
@@ -79,8 +95,8 @@ def ncu_top(tag):
            'Command: `ncu --set full --clock-control none --import-source on -k regex:"k_kr_persistent|k_stream_fill|'
            'k_cell_bounds|k_emit|k_classify|k_rs_scatter|k_edges_count|k_edges_fill|k_rle_write" -c 16 -o '
            'gpurun_out/prof_top_%s python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-microbench --no-c2 --no-e2e` '
-           '(`tools/gpu_call_final.sh`; per-kernel tables by `tools/ncu_summary.py` in `profiles/raw/r3b_ncu_top_c3_n1.md`, '
-           'this file by `tools/make_profiles_r2.py`).' % tag, '',
+           '(`tools/gpu_call_final.sh`; per-kernel tables by `tools/ncu_summary.py` in `profiles/raw/%s_prof_top_summary.md`, '
+           'this file by `tools/make_profiles_r2.py`).' % (tag, tag), '',
            'k_rs_scatter columns: pass 1 of the (i, j) sort (83M keys, 9-bit digits) and pass 1 of the column re-sort of '
            'the unique list (36.8M composites).', '',
            '| metric | ' + ' | '.join(lab[i] for i in keep) + ' |', '|---|' + '---:|' * len(keep)]
@@ -106,7 +122,7 @@ def ncu_top(tag):
             % (tr_kr / 1e9, tr_kr / 1e9 / float(kr['gpu__time_duration.sum']), tr_kr / 1e9 / 3.8,
                kr['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum'], kr['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'],
                tr_cl / 1e9)]
-    open(os.path.join(PROF, 'r2_ncu_top_final.md'), 'w').write('\n'.join(out) + '\n')
+    open(os.path.join(PROF, 'r2_ncu_top_final.md'), 'w').write('\n'.join(out) + '\n' + NOTES.get(tag, ''))
     tpath = os.path.join(PROF, 'traffic.json')
     t = json.load(open(tpath))
     src_name = 'profiles/r2_ncu_top_final.md (ncu --set full, %s)'
