@@ -90,3 +90,35 @@ def test_sharded_path_matches_oracle(tmp_path, world, port):
     o = np.lexsort((v, u))
     assert np.array_equal(u[o], ref['u']) and np.array_equal(v[o], ref['v'])
     assert np.max(np.abs(w[o] - ref['w']) / np.abs(ref['w'])) <= 1e-9
+
+
+def _worker_small(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from np_engine import NumpyEngine
+    com = synth.make_community(n_genomes=3, n_contigs=1500, n_pairs=40_000, seed=77)
+    per = -(-com.n_pairs // world)
+    mine = com.records[rank * per:(rank + 1) * per]
+    eng = NumpyEngine(com.tid2idx(), com.lengths, com.sites, len(mine))
+    hp = ShardedHotPath(com.tid2idx(), com.lengths, com.sites, len(mine), min_len=1000, min_sig=3, comm=Comm(),
+                        engine=eng)
+    msg = ''
+    try:
+        hp.run(torch.from_numpy(mine.view(np.int64)))
+    except ValueError as e:
+        msg = str(e)
+    open(os.path.join(out_dir, 'rank{}.txt'.format(rank)), 'w').write(msg)
+    dist.barrier()                     # every rank got here: nobody is left waiting inside the run
+    dist.destroy_process_group()
+
+
+def test_community_with_fewer_chunks_than_ranks_is_refused_on_all_ranks(tmp_path):
+    """1500 contigs are two 1024-row chunks: three ranks cannot all own rows.  The splits are the same everywhere, so
+    every rank raises the same ValueError after the accumulation's collectives (an assert on the
+    idle rank alone left the others spinning at a barrier)."""
+    world = 3
+    mp.spawn(_worker_small, args=(world, 29613, str(tmp_path)), nprocs=world, join=True)
+    msgs = [open(os.path.join(str(tmp_path), 'rank{}.txt'.format(r))).read() for r in range(world)]
+    assert all('cannot be cut into 3 row blocks' in m for m in msgs), msgs
+    assert len(set(msgs)) == 1
