@@ -124,3 +124,16 @@ def test_host_logic_without_gpu():
     # masked sequences are ordered last (contact_map.py:203-213)
     assert set(o.order['pos'][~m]) == {7, 8, 9}
     assert np.array_equal(o.lengths(), 1000 + np.arange(10))
+
+
+def test_tuning_options_are_range_checked(cabi):
+    """b3c_set_option is host-only state (include/bin3c_b200.h, "Tuning / test hooks"): every key rejects values outside
+    its documented range and leaves the setting alone; the defaults are restored at the end."""
+    lib = cabi.lib
+    OK, ARG = 0, cabi.B3C_ERR_ARG
+    assert lib.b3c_set_option(3, 255) == OK and lib.b3c_set_option(3, 256) == ARG and lib.b3c_set_option(3, -1) == ARG
+    assert lib.b3c_set_option(3, 22) == OK                       # the default flag set
+    assert lib.b3c_set_option(1, 1) == ARG and lib.b3c_set_option(1, 28672) == OK
+    assert lib.b3c_set_option(2, 49) == ARG and lib.b3c_set_option(2, 16) == OK
+    assert lib.b3c_set_option(5, 3) == ARG and lib.b3c_set_option(5, 2) == OK
+    assert lib.b3c_set_option(99, 0) == ARG and 'option' in cabi.last_error().lower()
