@@ -39,11 +39,15 @@ if __name__ == '__main__' and not (len(sys.argv) > 3 and sys.argv[3] == 'lines')
 def by_line(path, top_n=30):
     """Same, per CUDA source line: input from `--print-source cuda,sass`."""
     rows = list(csv.reader(open(path)))
-    out, cur, h = [], None, None
+    out, cur, h, first = [], None, None, None
     for r in rows:
         if not r:
             continue
         if r[0] == 'File Path':
+            if first is None:
+                first = r[1]
+            elif r[1] == first:
+                break                                   # the next launch of the kernel starts over: first launch only
             cur = r[1].split('/')[-1]
         elif r[0] == 'Line No':
             h = r
